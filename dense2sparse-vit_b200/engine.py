@@ -1,0 +1,294 @@
+"""Forward routines of the hot path, written against the reference's attribute names.
+
+Every function takes a module that exposes the same attributes as the corresponding reference class
+(`qkv`, `proj`, `num_heads`, `scale`, `in_conv`, `out_conv`, `blocks`, `score_predictor`, ...), so the same
+code serves this package's own nn.Modules (modules.py) and, through patch.py, the reference's classes
+themselves.  File:line citations point into the reference tree.
+
+Two execution modes, chosen per call:
+  * fused    (no gradient needed): qkv Linear -> d2s attention kernel (tcgen05 in bf16) -> proj; predictor
+             tail + selection in one kernel; gather kernel.  Dense Linear layers stay on cuBLAS.
+  * autograd (a gradient is needed): library GEMMs around the one-pass policy-softmax kernel
+             (forward + backward in both arguments), gather/scatter kernels, Gumbel decision kernel.
+"""
+import torch
+import torch.nn.functional as F
+
+from . import ops
+
+INIT_N = 14 * 14  # the reference hard-codes 196 spatial tokens (dynamic_vit.py:828, default_dynamic_vit.py:446)
+
+
+def _needs_grad(*ts):
+    return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in ts)
+
+
+def patch_embed_forward(m, img):
+    """Conv2d(kernel=stride=patch) as unfold + GEMM (dynamic_vit.py:286-303).  Avoids cuDNN's TF32 conv path
+    so fp32 runs stay within 1e-4 of the reference."""
+    B, C, Hh, Ww = img.shape
+    ph, pw = m.patch_size
+    assert Hh == m.img_size[0] and Ww == m.img_size[1], \
+        f"Input image size ({Hh}*{Ww}) doesn't match model ({m.img_size[0]}*{m.img_size[1]})."
+    gh, gw = Hh // ph, Ww // pw
+    w = m.proj.weight
+    patches = img.to(w.dtype).view(B, C, gh, ph, gw, pw).permute(0, 2, 4, 1, 3, 5).reshape(B, gh * gw, C * ph * pw)
+    return F.linear(patches, w.view(w.shape[0], -1), m.proj.bias)
+
+
+def attention_forward(m, x, policy=None, return_cls_attn=False):
+    """Attention.forward (dynamic_vit.py:216-236 / default_dynamic_vit.py:201-216)."""
+    B, T, C = x.shape
+    H = m.num_heads
+    qkv = m.qkv(x)
+    if _needs_grad(qkv, policy):
+        q, k, v = qkv.reshape(B, T, 3, H, C // H).permute(2, 0, 3, 1, 4).unbind(0)
+        attn = (q @ k.transpose(-2, -1)) * m.scale
+        attn = ops.softmax_with_policy(attn, policy)
+        o = (attn @ v).transpose(1, 2).reshape(B, T, C)
+        cls_attn = attn[:, :, 0, :] if return_cls_attn else None
+    else:
+        o, cls_attn = ops.attention_core(qkv, H, policy=policy, scale=m.scale, want_cls_row=return_cls_attn)
+        if cls_attn is not None:
+            cls_attn = cls_attn.to(x.dtype)
+    o = m.proj_drop(m.proj(o))
+    return (o, cls_attn) if return_cls_attn else o
+
+
+def block_forward(m, x, policy=None, return_cls_attn=False):
+    """Block.forward (dynamic_vit.py:263-283)."""
+    if return_cls_attn:
+        y, cls_attn = attention_forward(m.attn, m.norm1(x), policy=policy, return_cls_attn=True)
+        x = x + m.drop_path(y)
+        x = x + m.drop_path(m.mlp(m.norm2(x)))
+        return x, cls_attn
+    x = x + m.drop_path(attention_forward(m.attn, m.norm1(x), policy=policy))
+    return x + m.drop_path(m.mlp(m.norm2(x)))
+
+
+# ---- Variant A predictor (default_dynamic_vit.py:304-330) ------------------------------------------
+def predictor_a_hidden(m, x, policy):
+    h = m.in_conv(x)
+    B, N, C = h.shape
+    half = C // 2
+    pooled = (h[:, :, half:] * policy).sum(dim=1, keepdim=True) / torch.sum(policy, dim=1, keepdim=True)
+    h = torch.cat([h[:, :, :half], pooled.expand(B, N, half)], dim=-1)
+    for layer in list(m.out_conv)[:4]:      # Linear, GELU, Linear, GELU
+        h = layer(h)
+    return h
+
+
+def predictor_a_forward(m, x, policy):
+    h = predictor_a_hidden(m, x, policy)
+    lin = m.out_conv[4]
+    if _needs_grad(h, lin.weight):
+        return m.out_conv[5](lin(h))
+    logp, _ = ops.score_tail_a(h, lin.weight, lin.bias, k=0)
+    return logp.to(x.dtype)
+
+
+# ---- Variant B predictor (dynamic_vit.py:370-560) --------------------------------------------------
+def _predictor_b_tail_parts(m):
+    layers = list(m.out_conv)
+    # ..., norm, Linear(C,1), Flatten
+    return layers[:-3], layers[-3], layers[-2]
+
+
+def predictor_b_hidden(m, x):
+    h = m.in_conv(x)
+    B, N, C = h.shape
+    half = C // 2
+    pooled = torch.mean(h[:, :, half:], dim=1, keepdim=True)
+    h = torch.cat([h[:, :, :half], pooled.expand(B, N, half)], dim=-1)
+    body, norm, lin = _predictor_b_tail_parts(m)
+    for layer in body:
+        h = layer(h)
+    return h, norm, lin
+
+
+def predictor_b_forward(m, x, policy=None, current_sigma=0.0005, cls_attn=None, k_select=None):
+    """Returns (scores, keep_probs) like the reference; with k_select also (kept, dropped) from the fused
+    tail kernel.  Like the reference, only the topk_selection=True configuration is defined (:537)."""
+    if not m.topk_selection:
+        return None
+    h, norm, lin = predictor_b_hidden(m, x)
+    prob_mode = ops.PROB_SOFTMAX if m.loss_type in ["kl_div", "mse"] else ops.PROB_SIGMOID
+    if _needs_grad(h, lin.weight):
+        scores = lin(norm(h)).flatten(-2, -1)
+        probs = F.softmax(scores, dim=-1) if prob_mode == ops.PROB_SOFTMAX else torch.sigmoid(scores)
+        if k_select is None:
+            return scores, probs
+        kept, dropped = ops.select_topk(probs, k_select, ops.ORDER_INDEX_ASC)
+        return scores, probs, kept, dropped
+    if isinstance(norm, torch.nn.LayerNorm):
+        ln_w, ln_b, ln_eps = norm.weight, norm.bias, norm.eps
+    else:  # BatchNormLayer: normalise upstream, the kernel then skips its LayerNorm
+        h, ln_w, ln_b, ln_eps = norm(h), None, None, 0.0
+    scores, probs, kept, dropped = ops.score_tail_b(h, ln_w, ln_b, lin.weight, lin.bias, k_select or 0, ln_eps,
+                                                    prob_mode, select=k_select is not None)
+    scores, probs = scores.to(x.dtype), probs.to(x.dtype)
+    if k_select is None:
+        return scores, probs
+    return scores, probs, kept, dropped
+
+
+# ---- model forwards ------------------------------------------------------------------------------------
+def _embed(model, img):
+    x = patch_embed_forward(model.patch_embed, img)
+    B = x.shape[0]
+    x = torch.cat((model.cls_token.to(x.dtype).expand(B, -1, -1), x), dim=1)
+    return model.pos_drop(x + model.pos_embed.to(x.dtype))
+
+
+def _head(model, x):
+    x = model.norm(x)
+    features = x[:, 1:]
+    return model.head(model.pre_logits(x[:, 0])), features
+
+
+def draw_gumbel(like):
+    """Same draw as torch F.gumbel_softmax: -log(Exponential(1))."""
+    return -torch.empty_like(like, memory_format=torch.legacy_contiguous_format).exponential_().log()
+
+
+def variant_a_forward(model, img):
+    """DefaultVisionTransformerDiffPruning.forward (default_dynamic_vit.py:435-487).
+    Injected Gumbel noise for parity runs: set model._d2s_gumbels = [tensor (B,196,2) per stage]."""
+    x = _embed(model, img)
+    B = x.shape[0]
+    p_count = 0
+    out_pred_prob = []
+    prev_decision = torch.ones(B, INIT_N, 1, dtype=x.dtype, device=x.device)
+    policy = torch.ones(B, INIT_N + 1, 1, dtype=x.dtype, device=x.device)
+    injected = getattr(model, "_d2s_gumbels", None)
+    model.kept_token_indices = []
+    for i, blk in enumerate(model.blocks):
+        if i in model.pruning_loc:
+            pred = model.score_predictor[p_count]
+            if model.training:
+                pred_score = predictor_a_forward(pred, x[:, 1:], prev_decision).reshape(B, -1, 2)
+                g = injected[p_count] if injected is not None else draw_gumbel(pred_score)
+                hard = ops.gumbel_keep_decision(pred_score, g, prev_decision)
+                out_pred_prob.append(hard.reshape(B, INIT_N))
+                policy = torch.cat([torch.ones(B, 1, 1, dtype=hard.dtype, device=hard.device), hard], dim=1)
+                x = block_forward(blk, x, policy=policy)
+                prev_decision = hard
+            else:
+                k = int(INIT_N * model.token_ratio[p_count])
+                h = predictor_a_hidden(pred, x[:, 1:], prev_decision)
+                lin = pred.out_conv[4]
+                _, keep_policy = ops.score_tail_a(h, lin.weight, lin.bias, k=k)
+                model.kept_token_indices.append(keep_policy)
+                x = ops.gather_tokens(x, keep_policy, prepend_cls=True)
+                prev_decision = ops.batch_index_select(prev_decision, keep_policy)
+                x = block_forward(blk, x)
+            p_count += 1
+        else:
+            x = block_forward(blk, x, policy) if model.training else block_forward(blk, x)
+    x, features = _head(model, x)
+    if model.training:
+        if model.distill:
+            return x, features, prev_decision.detach(), out_pred_prob
+        return x, out_pred_prob
+    return x
+
+
+def variant_b_forward(model, img, stacked_cls_attn_weights=None):
+    """VisionTransformerDiffPruning.forward (dynamic_vit.py:814-1015)."""
+    x = _embed(model, img)
+    B, T0, D = x.shape
+    N = T0 - 1
+    p_count = 0
+    model.num_kept_tokens = []
+    model.cls_attns = []
+    model.pred_logits = []
+    model.kept_token_indices = []
+    model.dropped_token_indices = []
+    keep_mask = torch.ones((B, N + 1), dtype=x.dtype, device=x.device)
+    pred_logits = None
+    thr = model.patch_score_threshold
+    for i, blk in enumerate(model.blocks):
+        if i in model.pruning_loc:
+            num_keep_node = int(INIT_N * model.token_ratio[p_count])
+            pred = model.score_predictor[p_count]
+            if thr is None:
+                pred_logits, pred_score, kept, dropped = predictor_b_forward(pred, x[:, 1:], k_select=num_keep_node)
+                model.kept_token_indices.append(kept)
+                model.dropped_token_indices.append(dropped)
+                model.pred_logits.append(pred_logits)
+                x = ops.gather_tokens(x, kept, prepend_cls=True)
+                x, cls_attn = block_forward(blk, x, return_cls_attn=True)
+                model.cls_attns.append(cls_attn[:, :, 1:])
+            elif model.training:
+                # dynamic keep ratio: cumulative-score threshold -> 0/1 policy (dynamic_vit.py:880-894)
+                pred_logits, pred_score = predictor_b_forward(pred, x[:, 1:])
+                val, idx = torch.sort(pred_score.detach().clone())
+                th = torch.cumsum(val, dim=-1) > thr
+                model.keep_ratios = torch.sum(th, dim=1).detach().clone() / N
+                model.min_keep_ratio = torch.min(model.keep_ratios).item()
+                model.avg_keep_ratio = torch.mean(model.keep_ratios).item()
+                model.max_keep_ratio = torch.max(model.keep_ratios).item()
+                spatial_mask = torch.zeros((B, N), device=x.device, dtype=torch.bool).scatter(1, idx, th)
+                model.kept_token_indices.append(spatial_mask.unsqueeze(-1).repeat(1, 1, D).flatten())
+                model.dropped_token_indices.append(~spatial_mask.unsqueeze(-1).repeat(1, 1, D).flatten())
+                keep_mask = torch.cat((torch.ones(B, 1, dtype=x.dtype, device=x.device), spatial_mask), dim=1).float()
+                x = block_forward(blk, x, policy=keep_mask.unsqueeze(-1))
+            else:
+                # the reference's inference branch of this mode reads an undefined name (dynamic_vit.py:936)
+                raise NotImplementedError("patch_score_threshold inference is undefined in the reference "
+                                          "(vit_models/dynamic_vit.py:936 uses `score` before assignment)")
+            p_count += 1
+        else:
+            if model.training and thr is not None:
+                x = block_forward(blk, x, policy=keep_mask.unsqueeze(-1))
+            else:
+                x, cls_attn = block_forward(blk, x, return_cls_attn=True)
+                model.cls_attns.append(cls_attn[:, :, 1:])
+    x, features = _head(model, x)
+    if model.training:
+        if thr is not None:
+            return x, features, pred_logits, keep_mask[:, 1:]
+        return x, features, model.pred_logits, model.kept_token_indices
+    return x, model.cls_attns, model.pred_logits, model.kept_token_indices
+
+
+def variant_b_forward_cls_attn(model, img):
+    """VisionTransformerDiffPruning.forward_cls_attn (dynamic_vit.py:1018-1033)."""
+    x = _embed(model, img)
+    final = None
+    last = len(model.blocks) - 1
+    for i, blk in enumerate(model.blocks):
+        if i == last:
+            _, final = block_forward(blk, x, return_cls_attn=True)
+        else:
+            x = block_forward(blk, x)
+    return final
+
+
+def teacher_forward(model, img, with_cls_attn=True):
+    """VisionTransformerTeacher.forward (dynamic_vit.py:1150-1176) / DefaultVisionTransformerTeacher.forward
+    (default_dynamic_vit.py:581-598, with_cls_attn=False)."""
+    x = _embed(model, img)
+    rows = []
+    for blk in model.blocks:
+        if with_cls_attn:
+            x, ca = block_forward(blk, x, return_cls_attn=True)
+            rows.append(ca.detach())
+        else:
+            x = block_forward(blk, x)
+    feature = model.norm(x)
+    cls = model.head(model.pre_logits(feature[:, 0]))
+    tokens = feature[:, 1:]
+    if with_cls_attn:
+        return cls, tokens, torch.stack(rows, dim=1)
+    return cls, tokens
+
+
+def teacher_forward_cls_attention(model, img):
+    """VisionTransformerTeacher.forward_cls_attention (dynamic_vit.py:1134-1148)."""
+    x = _embed(model, img)
+    rows = []
+    for blk in model.blocks:
+        x, ca = block_forward(blk, x, return_cls_attn=True)
+        rows.append(ca.detach())
+    return torch.stack(rows, dim=1)

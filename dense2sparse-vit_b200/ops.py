@@ -1,0 +1,278 @@
+"""Operator layer: torch tensors in, hand-written sm_100a kernels underneath (via the C ABI in _lib.py).
+
+Every function here enqueues on torch's current CUDA stream and allocates outputs through torch's
+caching allocator; nothing synchronises with the host.  Inputs must be CUDA tensors -- there is no CPU
+fallback (the CPU restatement lives in oracle/ and is test infrastructure only).
+"""
+import torch
+
+from . import _lib
+from ._lib import BF16, F32, ORDER_INDEX_ASC, ORDER_SCORE_DESC, PROB_SIGMOID, PROB_SOFTMAX  # noqa: F401
+
+
+def _dtype_code(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.bfloat16:
+        return BF16
+    raise TypeError(f"d2s kernels take float32 or bfloat16 tensors, got {t.dtype}")
+
+
+def _check_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("d2s ops run on CUDA tensors only (no CPU fallback)")
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _f32c(t):
+    return None if t is None else t.detach().to(torch.float32).contiguous()
+
+
+# ----------------------------------------------------------------------------------------------
+# (1) selection and fused predictor tails
+# ----------------------------------------------------------------------------------------------
+
+def select_topk(score: torch.Tensor, k: int, order: int = ORDER_INDEX_ASC, want_dropped: bool = True):
+    """Stable top-k over (B,N) fp32 scores -> (kept (B,k) int64, dropped (B,N-k) int64 or None).
+    Replaces argsort/sort at vit_models/dynamic_vit.py:858-862 and default_dynamic_vit.py:463."""
+    _check_cuda(score)
+    s = _f32c(score)
+    B, N = s.shape
+    kept = torch.empty(B, k, dtype=torch.int64, device=s.device)
+    dropped = torch.empty(B, N - k, dtype=torch.int64, device=s.device) if want_dropped else None
+    _lib.call("d2s_select_topk_f32", _ptr(s), B, N, k, order, _ptr(kept), _ptr(dropped), _stream())
+    return kept, dropped
+
+
+def score_tail_a(hidden, weight, bias, k=0, gumbel=None, prev=None):
+    """Variant A predictor tail (Linear(C,2)+LogSoftmax) fused with selection or the Gumbel decision.
+    eval  (gumbel None): returns (logp (B,N,2), kept (B,k) int64 in descending-score order)
+    train (gumbel (B,N,2)): returns (logp, decision (B,N), ysoft (B,N))"""
+    _check_cuda(hidden, weight, bias)
+    h = hidden.detach().contiguous()
+    B, N, C = h.shape
+    w, b = _f32c(weight), _f32c(bias)
+    logp = torch.empty(B, N, 2, dtype=torch.float32, device=h.device)
+    if gumbel is None:
+        kept = torch.empty(B, k, dtype=torch.int64, device=h.device)
+        _lib.call("d2s_score_tail_a", _ptr(h), _dtype_code(h), B, N, C, _ptr(w), _ptr(b), k, None, None,
+                  _ptr(logp), _ptr(kept), None, None, _stream())
+        return logp, kept
+    g = _f32c(gumbel)
+    p = _f32c(prev.reshape(B, N)) if prev is not None else None
+    decision = torch.empty(B, N, dtype=torch.float32, device=h.device)
+    ysoft = torch.empty(B, N, dtype=torch.float32, device=h.device)
+    _lib.call("d2s_score_tail_a", _ptr(h), _dtype_code(h), B, N, C, _ptr(w), _ptr(b), 0, _ptr(g), _ptr(p),
+              _ptr(logp), None, _ptr(decision), _ptr(ysoft), _stream())
+    return logp, decision, ysoft
+
+
+def score_tail_b(hidden, ln_weight, ln_bias, weight, bias, k, ln_eps=1e-5, prob_mode=PROB_SOFTMAX, select=True):
+    """Variant B predictor tail ([LayerNorm]+Linear(C,1)+softmax|sigmoid) fused with the ascending-index
+    top-k.  Returns (scores (B,N), probs (B,N), kept (B,k)|None, dropped (B,N-k)|None)."""
+    _check_cuda(hidden, weight)
+    h = hidden.detach().contiguous()
+    B, N, C = h.shape
+    lw, lb = _f32c(ln_weight), _f32c(ln_bias)
+    w = _f32c(weight).reshape(-1)
+    bz = _f32c(bias).reshape(-1) if bias is not None else None
+    scores = torch.empty(B, N, dtype=torch.float32, device=h.device)
+    probs = torch.empty(B, N, dtype=torch.float32, device=h.device)
+    kept = torch.empty(B, k, dtype=torch.int64, device=h.device) if select else None
+    dropped = torch.empty(B, N - k, dtype=torch.int64, device=h.device) if select else None
+    _lib.call("d2s_score_tail_b", _ptr(h), _dtype_code(h), B, N, C, _ptr(lw), _ptr(lb), float(ln_eps), _ptr(w),
+              _ptr(bz), prob_mode, k, _ptr(scores), _ptr(probs), _ptr(kept), _ptr(dropped), _stream())
+    return scores, probs, kept, dropped
+
+
+class _GumbelKeep(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logp, gumbel, prev):
+        lp, g = _f32c(logp), _f32c(gumbel)
+        n = lp.numel() // 2
+        pv = _f32c(prev.reshape(-1)) if prev is not None else None
+        decision = torch.empty(lp.shape[:-1], dtype=torch.float32, device=lp.device)
+        ysoft = torch.empty_like(decision)
+        _lib.call("d2s_gumbel_decision_f32", _ptr(lp), _ptr(g), _ptr(pv), n, _ptr(decision), _ptr(ysoft), _stream())
+        ctx.save_for_backward(ysoft, pv if pv is not None else torch.empty(0, device=lp.device))
+        ctx.has_prev = pv is not None
+        ctx.in_dtype = logp.dtype
+        return decision.unsqueeze(-1).to(logp.dtype)
+
+    @staticmethod
+    def backward(ctx, gout):
+        ysoft, pv = ctx.saved_tensors
+        g = _f32c(gout.reshape(-1))
+        n = ysoft.numel()
+        glogp = torch.empty(*ysoft.shape, 2, dtype=torch.float32, device=ysoft.device)
+        _lib.call("d2s_gumbel_decision_bwd_f32", _ptr(g), _ptr(ysoft), _ptr(pv) if ctx.has_prev else None, n,
+                  _ptr(glogp), _stream())
+        return glogp.to(ctx.in_dtype), None, None
+
+
+def gumbel_keep_decision(logp, gumbel, prev=None):
+    """hard keep decision (B,N,1) in {0,1} * prev with the straight-through gradient of
+    F.gumbel_softmax(hard=True)[..., 0:1] (vit_models/default_dynamic_vit.py:454), noise injected."""
+    _check_cuda(logp, gumbel)
+    return _GumbelKeep.apply(logp, gumbel, prev)
+
+
+# ----------------------------------------------------------------------------------------------
+# (3) gather / scatter
+# ----------------------------------------------------------------------------------------------
+
+class _GatherTokens(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, idx, prepend_cls):
+        xc = x.contiguous()
+        ic = idx.contiguous()
+        B, T, D = xc.shape
+        K = ic.shape[1]
+        out = torch.empty(B, K + (1 if prepend_cls else 0), D, dtype=xc.dtype, device=xc.device)
+        _lib.call("d2s_gather_tokens", _ptr(xc), _dtype_code(xc), B, T, D, _ptr(ic), K, int(prepend_cls), _ptr(out), _stream())
+        ctx.save_for_backward(ic)
+        ctx.shape = (B, T, D, K, bool(prepend_cls))
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        (ic,) = ctx.saved_tensors
+        B, T, D, K, prepend_cls = ctx.shape
+        g = gout.contiguous()
+        gx = torch.empty(B, T, D, dtype=g.dtype, device=g.device)
+        _lib.call("d2s_scatter_tokens_bwd", _ptr(g), _dtype_code(g), B, T, D, _ptr(ic), K, int(prepend_cls), _ptr(gx), _stream())
+        return gx, None, None
+
+
+def gather_tokens(x, kept, prepend_cls=True):
+    """x (B,T,D) with CLS at row 0, kept (B,K) spatial indices -> (B,K+1,D) = [CLS, x[kept+1]]
+    (vit_models/dynamic_vit.py:907-912).  Differentiable in x (backward = scatter + zero fill)."""
+    _check_cuda(x, kept)
+    if kept.dtype != torch.int64:
+        raise TypeError("indices must be int64")
+    return _GatherTokens.apply(x, kept, prepend_cls)
+
+
+def scatter_tokens_bwd(gout, kept, t_in, prepend_cls=True):
+    _check_cuda(gout, kept)
+    g = gout.contiguous()
+    B, _, D = g.shape
+    gx = torch.empty(B, t_in, D, dtype=g.dtype, device=g.device)
+    _lib.call("d2s_scatter_tokens_bwd", _ptr(g), _dtype_code(g), B, t_in, D, _ptr(kept.contiguous()), kept.shape[1],
+              int(prepend_cls), _ptr(gx), _stream())
+    return gx
+
+
+def batch_index_select(x, idx):
+    """Same contract as the reference's batch_index_select (vit_models/default_dynamic_vit.py:37-53)."""
+    if x.dim() == 3:
+        return gather_tokens(x, idx, prepend_cls=False)
+    if x.dim() == 2:
+        return gather_tokens(x.unsqueeze(-1), idx, prepend_cls=False).squeeze(-1)
+    raise NotImplementedError
+
+
+# ----------------------------------------------------------------------------------------------
+# (2) PerturbedTopK
+# ----------------------------------------------------------------------------------------------
+
+class _PerturbedTopK(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, k, num_samples, sigma, noise, seed):
+        xc = _f32c(x)
+        B, N = xc.shape
+        ind = torch.empty(B, k, N, dtype=torch.float32, device=xc.device)
+        egrad = torch.empty(B, k, N, dtype=torch.float32, device=xc.device)
+        if noise is not None:
+            nz = _f32c(noise)
+            if tuple(nz.shape) != (B, num_samples, N):
+                raise ValueError(f"noise must be {(B, num_samples, N)}, got {tuple(nz.shape)}")
+            _lib.call("d2s_ptopk_fwd", _ptr(xc), _ptr(nz), B, N, k, num_samples, float(sigma), _ptr(ind), _ptr(egrad), _stream())
+        else:
+            _lib.call("d2s_ptopk_fwd_rng", _ptr(xc), int(seed), B, N, k, num_samples, float(sigma), _ptr(ind), _ptr(egrad), _stream())
+        ctx.save_for_backward(egrad)
+        ctx.in_dtype = x.dtype
+        return ind
+
+    @staticmethod
+    def backward(ctx, gout):
+        (egrad,) = ctx.saved_tensors
+        B, K, N = egrad.shape
+        g = _f32c(gout)
+        gx = torch.empty(B, N, dtype=torch.float32, device=g.device)
+        _lib.call("d2s_ptopk_bwd", _ptr(g), _ptr(egrad), B, N, K, _ptr(gx), _stream())
+        return gx.to(ctx.in_dtype), None, None, None, None, None
+
+
+def perturbed_topk(x, k, num_samples=500, sigma=0.05, noise=None, seed=None):
+    """Differentiable top-k indicators (B,k,N) of vit_models/peturbed_topk.py.  `noise` (B,num_samples,N)
+    reproduces the reference bit-for-bit given the same draws; with noise=None the kernel draws its own
+    (Philox) from `seed` (default: a fresh seed from torch's generator)."""
+    _check_cuda(x, noise)
+    if noise is None and seed is None:
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+    return _PerturbedTopK.apply(x, int(k), int(num_samples), float(sigma), noise, seed)
+
+
+# ----------------------------------------------------------------------------------------------
+# (4) policy attention
+# ----------------------------------------------------------------------------------------------
+
+class _SoftmaxPolicy(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, attn, policy, eps):
+        a = attn.contiguous()
+        B, H, T, _ = a.shape
+        pol = _f32c(policy.reshape(B, T)) if policy is not None else None
+        out = torch.empty_like(a)
+        stats = torch.empty(B, H, T, 2, dtype=torch.float32, device=a.device)
+        _lib.call("d2s_softmax_policy_fwd", _ptr(a), _ptr(pol), _dtype_code(a), B, H, T, float(eps), _ptr(out), _ptr(stats), _stream())
+        ctx.save_for_backward(a, stats, pol if pol is not None else torch.empty(0, device=a.device))
+        ctx.meta = (B, H, T, float(eps), pol is not None, None if policy is None else (policy.shape, policy.dtype))
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        a, stats, pol = ctx.saved_tensors
+        B, H, T, eps, has_pol, pol_meta = ctx.meta
+        g = gout.contiguous().to(a.dtype)
+        gattn = torch.empty_like(a)
+        gpol = torch.zeros(B, T, dtype=torch.float32, device=a.device) if has_pol else None
+        _lib.call("d2s_softmax_policy_bwd", _ptr(a), _ptr(pol) if has_pol else None, _ptr(g), _ptr(stats), _dtype_code(a),
+                  B, H, T, eps, _ptr(gattn), _ptr(gpol), _stream())
+        if has_pol:
+            gpol = gpol.reshape(pol_meta[0]).to(pol_meta[1])
+        return gattn, gpol, None
+
+
+def softmax_with_policy(attn, policy, eps=1e-6):
+    """Drop-in for Attention.softmax_with_policy (vit_models/dynamic_vit.py:195-214): attn (B,H,T,T),
+    policy (B,T,1) or None (plain softmax).  One kernel forward, one backward, differentiable in both."""
+    _check_cuda(attn, policy)
+    return _SoftmaxPolicy.apply(attn, policy, eps)
+
+
+def attention_core(qkv, num_heads, policy=None, scale=None, eps=1e-6, want_cls_row=False):
+    """Fused inference attention: packed qkv (B,T,3*H*hd) straight from the qkv Linear -> (out (B,T,H*hd),
+    cls_row (B,H,T) fp32 | None).  bf16 runs the tcgen05/TMEM kernel, fp32 the SIMT parity kernel.
+    No autograd: the training path uses softmax_with_policy around library GEMMs."""
+    _check_cuda(qkv, policy)
+    q = qkv.detach().contiguous()
+    B, T, C3 = q.shape
+    D = C3 // 3
+    hd = D // num_heads
+    scale = hd ** -0.5 if scale is None else scale
+    pol = _f32c(policy.reshape(B, T)) if policy is not None else None
+    out = torch.empty(B, T, D, dtype=q.dtype, device=q.device)
+    cls_row = torch.empty(B, num_heads, T, dtype=torch.float32, device=q.device) if want_cls_row else None
+    _lib.call("d2s_attn_policy_fwd", _ptr(q), _ptr(pol), _dtype_code(q), B, T, num_heads, hd, float(scale), float(eps),
+              _ptr(out), _ptr(cls_row), _stream())
+    return out, cls_row

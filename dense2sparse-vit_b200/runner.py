@@ -1,0 +1,124 @@
+"""Execution helpers around the models: CUDA-graph inference, host->device pipelining, data-parallel sharding.
+
+Everything per-image on the hot path is independent: inference is sharded by batch
+across ranks with no collective; training uses torch DistributedDataParallel (NCCL gradient all-reduce), which
+is the reference's own design (ddp_training.py:93).
+"""
+import os
+
+import torch
+
+
+def shard_range(global_batch: int, rank: int, world: int):
+    """Contiguous slice [lo, hi) of a global batch owned by `rank`; sizes differ by at most one image."""
+    base, rem = divmod(global_batch, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def dist_env():
+    """(rank, local_rank, world) from the torchrun environment; (0, 0, 1) when launched plainly."""
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+def wrap_ddp(model, device=None, **kw):
+    """DistributedDataParallel exactly as the reference intends (ddp_training.py:93): one process per GPU,
+    bucketed gradient all-reduce overlapped with backward."""
+    from torch.nn.parallel import DistributedDataParallel as DDP
+    if device is not None and device.type == "cuda":
+        return DDP(model, device_ids=[device.index], output_device=device.index, find_unused_parameters=False, **kw)
+    return DDP(model, find_unused_parameters=False, **kw)
+
+
+class InferenceRunner:
+    """Captures one eval forward of `model` at a fixed batch shape into a CUDA graph and replays it.
+
+    The per-stage launches around the big GEMMs (predictor tail+select, gather, attention) are small; a graph
+    removes their launch latency from the step (hard part 7).  Outputs are static tensors
+    owned by the graph's memory pool: read them (or copy them out) before the next replay.
+    """
+
+    def __init__(self, model, batch, device, dtype=torch.bfloat16, img_shape=(3, 224, 224), use_graph=True, warmup=3):
+        self.model = model.eval().to(device=device, dtype=dtype)
+        self.device, self.dtype, self.batch = device, dtype, batch
+        self.static_in = torch.zeros(batch, *img_shape, dtype=dtype, device=device)
+        self.graph = None
+        self.static_out = None
+        self._stage = None
+        self._copy_stream = None
+        self._host_out = None
+        with torch.no_grad():
+            side = torch.cuda.Stream(device=device)
+            side.wait_stream(torch.cuda.current_stream(device))
+            with torch.cuda.stream(side):
+                for _ in range(max(1, warmup)):
+                    out = self.model(self.static_in)
+            torch.cuda.current_stream(device).wait_stream(side)
+            torch.cuda.synchronize(device)
+            if use_graph:
+                self.graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self.graph):
+                    out = self.model(self.static_in)
+            self.static_out = out
+
+    @property
+    def logits(self):
+        out = self.static_out
+        return out[0] if isinstance(out, (tuple, list)) else out
+
+    def replay(self):
+        """One forward over whatever currently sits in static_in."""
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            with torch.no_grad():
+                self.static_out = self.model(self.static_in)
+        return self.static_out
+
+    def __call__(self, x):
+        self.static_in.copy_(x, non_blocking=True)
+        return self.replay()
+
+    # ---- end-to-end path: pinned host images in, host logits out ------------------------------------
+    def _ensure_pipeline(self):
+        if self._stage is None:
+            self._stage = [torch.empty_like(self.static_in) for _ in range(2)]
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+            self._ready = [torch.cuda.Event() for _ in range(2)]
+            self._free = [torch.cuda.Event() for _ in range(2)]
+            self._host_out = torch.empty(self.logits.shape, dtype=self.logits.dtype).pin_memory()
+            self._slot = 0
+            self._used = [False, False]
+
+    def prefetch(self, x_host):
+        """Start the host->device copy of the NEXT step's images on the copy stream."""
+        self._ensure_pipeline()
+        k = self._slot
+        with torch.cuda.stream(self._copy_stream):
+            if self._used[k]:  # the compute stream must have consumed this staging buffer
+                self._copy_stream.wait_event(self._free[k])
+            self._stage[k].copy_(x_host, non_blocking=True)
+            self._ready[k].record(self._copy_stream)
+        self._pending = k
+        self._slot ^= 1
+
+    def step_prefetched(self):
+        """Run one forward on the images whose copy was started by prefetch(); returns pinned host logits
+        (valid after the caller synchronises the current stream)."""
+        k = self._pending
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_event(self._ready[k])
+        self.static_in.copy_(self._stage[k], non_blocking=True)
+        self._free[k].record(cur)
+        self._used[k] = True
+        self.replay()
+        self._host_out.copy_(self.logits, non_blocking=True)
+        return self._host_out
+
+    def step_from_host(self, x_host):
+        """Unpipelined end-to-end step: H2D copy, forward, D2H of the logits, all on the current stream."""
+        self._ensure_pipeline()
+        self.static_in.copy_(x_host, non_blocking=True)
+        self.replay()
+        self._host_out.copy_(self.logits, non_blocking=True)
+        return self._host_out

@@ -1,0 +1,136 @@
+/*
+ * d2s.h -- C ABI of libd2s_b200.so: the B200 (sm_100a) token-sparsification hot path of
+ * Dense2Sparse-ViT / DynamicViT.
+ *
+ * The reference (marc345/Dense2Sparse-ViT) has no FFI or operator registry: its boundary is the Python
+ * surface of vit_models/{dynamic_vit,default_dynamic_vit,peturbed_topk}.py.  This
+ * header is the boundary introduced underneath it; each entry point names the reference call site it
+ * replaces (file:line under the reference tree).  INTEGRATION.md shows the ctypes stub a maintainer
+ * would add on the reference side.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller; nothing is allocated, no host sync is
+ *     performed, no stream is created.  Work is enqueued on `stream` (a cudaStream_t passed as void*).
+ *   - tensors are dense row-major ("contiguous"); shapes are given in the comments.
+ *   - indices are int64 (torch.long), matching the reference.
+ *   - return value 0 = ok; non-zero = error, message via d2s_last_error() (thread-local).  Shape and
+ *     alignment errors are reported before any launch.  There is no CPU fallback and no other arch.
+ */
+#ifndef D2S_H
+#define D2S_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* d2s_stream_t; /* cudaStream_t */
+
+enum { D2S_F32 = 0, D2S_BF16 = 1 };
+enum { D2S_ORDER_INDEX_ASC = 0, D2S_ORDER_SCORE_DESC = 1 };
+enum { D2S_PROB_SOFTMAX = 0, D2S_PROB_SIGMOID = 1 };
+
+enum {
+  D2S_OK = 0,
+  D2S_ERR_ARG = 1,      /* bad shape / null pointer / unsupported size */
+  D2S_ERR_ALIGN = 2,    /* pointer or row pitch not 16-byte aligned   */
+  D2S_ERR_CUDA = 3,     /* launch failed (message holds cudaGetErrorString) */
+  D2S_ERR_ARCH = 4      /* device is not sm_100 */
+};
+
+const char* d2s_last_error(void);
+int d2s_version(void);
+/* number of kernels this library has launched in the calling process (for bench.py's gpu_launches) */
+uint64_t d2s_launch_count(void);
+
+/* ---- (1a) selection --------------------------------------------------------------------------
+ * Replaces torch.argsort(descending)+slice(+2x torch.sort) at vit_models/dynamic_vit.py:858-862
+ * (order = INDEX_ASC, writes kept and dropped) and vit_models/default_dynamic_vit.py:463
+ * (order = SCORE_DESC, dropped may be NULL).  Stable: equal scores keep the lower index first;
+ * NaN sorts largest.  score (B,N) f32; kept (B,K) i64; dropped (B,N-K) i64 or NULL.  1 <= N <= 1024. */
+int d2s_select_topk_f32(const float* score, int B, int N, int K, int order,
+                        int64_t* kept, int64_t* dropped, d2s_stream_t stream);
+
+/* ---- (1b) fused predictor tails -----------------------------------------------------------------
+ * Variant A tail: Linear(C,2)+LogSoftmax (default_dynamic_vit.py:319-320), then either
+ *   eval : top-K of logp[:,:,0] in descending-score order (default_dynamic_vit.py:461-463)  -> kept
+ *   train: Gumbel keep decision with injected noise (default_dynamic_vit.py:454; torch
+ *          F.gumbel_softmax(hard=True)) times prev_decision                    -> decision, ysoft
+ * hidden (B,N,C) f32|bf16 post-GELU activations; W (2,C) f32; bias (2) f32; logp (B,N,2) f32 out.
+ * eval:  gumbel=NULL, kept (B,K) i64 (NULL: log-probs only).   train: gumbel (B,N,2) f32, prev (B,N) f32, decision (B,N) f32,
+ * ysoft (B,N) f32 (soft keep probability, saved for backward).  C <= 1024, C % 8 == 0. */
+int d2s_score_tail_a(const void* hidden, int dtype, int B, int N, int C,
+                     const float* W, const float* bias,
+                     int K, const float* gumbel, const float* prev,
+                     float* logp, int64_t* kept, float* decision, float* ysoft, d2s_stream_t stream);
+
+/* Variant B tail: [LayerNorm(C)] + Linear(C,1) + flatten + softmax over N | sigmoid
+ * (dynamic_vit.py:424-426, :547-554), then top-K with kept/dropped sorted ascending (:858-862).
+ * ln_w/ln_b NULL => no LayerNorm (BatchNorm variants normalise upstream).  W (C) f32, bias (1) f32 device pointer or NULL.
+ * scores (B,N) f32 raw logits, probs (B,N) f32, kept (B,K), dropped (B,N-K) (kept may be NULL to skip). */
+int d2s_score_tail_b(const void* hidden, int dtype, int B, int N, int C,
+                     const float* ln_w, const float* ln_b, float ln_eps,
+                     const float* W, const float* bias, int prob_mode, int K,
+                     float* scores, float* probs, int64_t* kept, int64_t* dropped, d2s_stream_t stream);
+
+/* Stand-alone Gumbel keep decision and its straight-through backward (default_dynamic_vit.py:454).
+ * logp, gumbel (n,2); prev, decision, ysoft (n); n = B*N. */
+int d2s_gumbel_decision_f32(const float* logp, const float* gumbel, const float* prev, int64_t n,
+                            float* decision, float* ysoft, d2s_stream_t stream);
+int d2s_gumbel_decision_bwd_f32(const float* gout, const float* ysoft, const float* prev, int64_t n,
+                                float* glogp, d2s_stream_t stream);
+
+/* ---- (3) gather / scatter of kept tokens ------------------------------------------------------------
+ * prepend_cls=1 replaces cat(0, kept+1) + torch.gather / batch_index_select of the token matrix
+ * (dynamic_vit.py:907-912, :954-960; default_dynamic_vit.py:464-466): x (B,T,D), idx (B,K) spatial
+ * indices in [0,T-1) -> out (B,K+1,D) with row 0 = CLS.  prepend_cls=0 is plain batch_index_select
+ * (default_dynamic_vit.py:37-53, e.g. prev_decision at :467): idx in [0,T) -> out (B,K,D).
+ * D*elem_size must be a multiple of 16 for the vector path; other sizes (e.g. D=1) use a scalar path. */
+int d2s_gather_tokens(const void* x, int dtype, int B, int T, int D,
+                      const int64_t* idx, int K, int prepend_cls, void* out, d2s_stream_t stream);
+/* Backward of the gather (autograd of torch.gather at dynamic_vit.py:912): gout (B,K[+1],D) ->
+ * gx (B,T,D), rows not selected are zero-filled here.  Indices must be unique per image. */
+int d2s_scatter_tokens_bwd(const void* gout, int dtype, int B, int T, int D,
+                           const int64_t* idx, int K, int prepend_cls, void* gx, d2s_stream_t stream);
+
+/* ---- (2) PerturbedTopK -----------------------------------------------------------------------------
+ * Replaces PerturbedTopKFunction.forward/backward (vit_models/peturbed_topk.py:16-80) without the
+ * (b,nS,k,d) one-hot tensor.  x (B,N) f32; noise (B,S,N) f32 standard normal (injected, as the
+ * reference draws it on the host at :29); indicators (B,K,N) f32; egrad (B,K,N) f32 = the backward's
+ * expected-gradient tensor (:77-78), NULL to skip.  N <= 224, 1 <= K <= N, S >= 1. */
+int d2s_ptopk_fwd(const float* x, const float* noise, int B, int N, int K, int S, float sigma,
+                  float* indicators, float* egrad, d2s_stream_t stream);
+/* Same, drawing the noise in-kernel (Philox4x32-10 + Box-Muller keyed by (seed, b, s, token)); a
+ * different, faster contract than the reference's host RNG: statistically equivalent, not bit-equal. */
+int d2s_ptopk_fwd_rng(const float* x, uint64_t seed, int B, int N, int K, int S, float sigma,
+                      float* indicators, float* egrad, d2s_stream_t stream);
+/* grad_x (B,N) = sum_k gout (B,K,N) * egrad (B,K,N)   (peturbed_topk.py:79) */
+int d2s_ptopk_bwd(const float* gout, const float* egrad, int B, int N, int K, float* gx,
+                  d2s_stream_t stream);
+
+/* ---- (4) policy-masked attention --------------------------------------------------------------------
+ * softmax_with_policy as a single pass (dynamic_vit.py:195-214 == default_dynamic_vit.py:185-199):
+ *   P_ij = (exp(s_ij - max_j s_ij) * m_ij + eps/T) / (sum_j exp(.)*m_ij + eps),  m_ij = p_j + (1-p_j)[i==j]
+ * attn (B,H,T,T) f32|bf16; policy (B,T) f32 or NULL (=> plain softmax, eps ignored); out same dtype;
+ * stats (B,H,T,2) f32 = (row max, denominator) saved for backward, may be NULL. */
+int d2s_softmax_policy_fwd(const void* attn, const float* policy, int dtype, int B, int H, int T,
+                           float eps, void* out, float* stats, d2s_stream_t stream);
+/* Backward in both arguments.  gout (B,H,T,T) same dtype as attn; gattn out; gpolicy (B,T) f32 is
+ * ACCUMULATED into (caller zero-fills), may be NULL.  Includes the gradient through the subtracted max. */
+int d2s_softmax_policy_bwd(const void* attn, const float* policy, const void* gout, const float* stats,
+                           int dtype, int B, int H, int T, float eps,
+                           void* gattn, float* gpolicy, d2s_stream_t stream);
+
+/* Fused attention core of Attention.forward (dynamic_vit.py:218-234; default_dynamic_vit.py:203-213):
+ * qkv (B,T,3,H,hd) packed as produced by the qkv Linear; out (B,T,H*hd) ready for the proj Linear;
+ * cls_row (B,H,T) f32 = probabilities of query row 0 (dynamic_vit.py:233-234) or NULL.
+ * dtype BF16: tcgen05/TMEM tensor-core kernel (hd == 64, T <= 256).
+ * dtype F32 : fp32 SIMT kernel used for 1e-4 parity runs (hd in {32,64}, T <= 256). */
+int d2s_attn_policy_fwd(const void* qkv, const float* policy, int dtype, int B, int T, int H, int hd,
+                        float scale, float eps, void* out, float* cls_row, d2s_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* D2S_H */

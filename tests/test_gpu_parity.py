@@ -1,0 +1,340 @@
+"""GPU parity tests: every d2s kernel, called through the C ABI (ctypes via ops.py), against the CPU oracle
+on the same seeded inputs, against the committed reference goldens, and - at BASELINE sizes - through
+size-independent properties.  Integer/index results are bit-exact; float tolerances are stated per test
+(north_star: 1e-4 relative in fp32, 1e-2 in bf16)."""
+import pytest
+import torch
+
+import fixtures as fx
+from oracle import ops as oo
+
+pytestmark = pytest.mark.gpu
+
+OPS, OPS_META = fx.load_npz("golden_ops.npz")
+C = OPS_META["cases"]
+FP32 = dict(rtol=1e-4, atol=1e-6)
+BF16 = dict(rtol=1e-2, atol=1e-2)
+
+
+@pytest.fixture(scope="module")
+def ops(d2s, cuda_dev):
+    return d2s.ops
+
+
+def cu(t):
+    return t.cuda()
+
+
+# ------------------------------------------------------------------------------------------ select
+@pytest.mark.parametrize("B,N,K", [(4, 196, 137), (3, 137, 96), (2, 96, 67), (1, 196, 58), (5, 196, 176),
+                                   (2, 7, 3), (2, 300, 150), (1, 1024, 512), (3, 196, 0), (3, 196, 196)])
+@pytest.mark.parametrize("order", [0, 1])
+def test_select_bit_exact(ops, B, N, K, order):
+    sc = torch.softmax(fx.randn(1000 + B * N + K, B, N), dim=-1)
+    kept, dropped = ops.select_topk(cu(sc), K, order)
+    rk, rd = oo.select_topk(sc, K, order)
+    assert torch.equal(kept.cpu(), rk)
+    if order == 0:
+        assert torch.equal(dropped.cpu(), rd)
+
+
+def test_select_ties_nan_signed_zero(ops):
+    sc = torch.tensor([[0.5, 0.7, 0.5, 0.7, 0.1, float("nan"), -0.0, 0.0],
+                       [1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0]])
+    for order in (0, 1):
+        kept, dropped = ops.select_topk(cu(sc), 4, order)
+        rk, rd = oo.select_topk(sc, 4, order)
+        assert torch.equal(kept.cpu(), rk), (order, kept, rk)
+    # heavy ties: bf16-quantised softmax scores (SURVEY hard part 1)
+    q = torch.softmax(fx.randn(7, 16, 196) * 0.02, dim=-1).bfloat16().float()
+    kept, dropped = ops.select_topk(cu(q), 137, 0)
+    rk, rd = oo.select_topk(q, 137, 0)
+    assert torch.equal(kept.cpu(), rk) and torch.equal(dropped.cpu(), rd)
+
+
+def test_select_golden_call_sites(ops):
+    c = C["select"]
+    sc = torch.softmax(fx.randn(c["seed"], *c["shape"]), dim=-1)
+    kept, dropped = ops.select_topk(cu(sc), c["k"], 0)
+    assert torch.equal(kept.cpu(), OPS["sel_keptB"]) and torch.equal(dropped.cpu(), OPS["sel_dropB"])
+    kept, _ = ops.select_topk(cu(sc), c["k"], 1)
+    assert torch.equal(kept.cpu(), OPS["sel_keptA"])
+
+
+def test_select_full_size_properties(ops):
+    B, N, K = 4096, 196, 137
+    sc = torch.rand(B, N, generator=fx.gen(5)).cuda()
+    kept, dropped = ops.select_topk(sc, K, 0)
+    allidx = torch.cat([kept, dropped], dim=1).sort(dim=1).values
+    assert torch.equal(allidx, torch.arange(N, device="cuda").expand(B, N))          # a partition of 0..N-1
+    assert bool((kept[:, 1:] > kept[:, :-1]).all()) and bool((dropped[:, 1:] > dropped[:, :-1]).all())
+    assert bool((sc.gather(1, kept).min(1).values >= sc.gather(1, dropped).max(1).values).all())
+    kept_a, _ = ops.select_topk(sc, K, 1)
+    va = sc.gather(1, kept_a)
+    assert bool((va[:, 1:] <= va[:, :-1]).all())
+    assert torch.equal(kept_a.sort(1).values, kept)
+
+
+# ------------------------------------------------------------------------------------------ gather
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("B,T,D,K", [(3, 197, 384, 137), (2, 138, 384, 96), (2, 97, 768, 67), (1, 197, 768, 176),
+                                     (5, 197, 384, 58), (2, 10, 8, 4), (2, 197, 384, 0), (1, 2, 384, 1)])
+def test_gather_scatter_bit_exact(ops, dtype, B, T, D, K):
+    x = fx.randn(31 + T + D, B, T, D).to(dtype)
+    kept = torch.stack([torch.randperm(T - 1, generator=fx.gen(40 + b))[:K].sort().values for b in range(B)]).long()
+    out = ops.gather_tokens(cu(x), cu(kept), prepend_cls=True)
+    ref = oo.gather_tokens_with_cls(x, kept)
+    assert torch.equal(out.cpu(), ref)
+    g = fx.randn(99, B, K + 1, D).to(dtype)
+    gx = ops.scatter_tokens_bwd(cu(g), cu(kept), T, prepend_cls=True)
+    assert torch.equal(gx.cpu(), oo.scatter_tokens_bwd(g, kept, T))
+
+
+def test_batch_index_select_contract(ops):
+    c = C["bis"]
+    x = fx.randn(c["x_seed"], *c["x_shape"])
+    assert torch.equal(ops.batch_index_select(cu(x), cu(OPS["bis3_idx"])).cpu(), OPS["bis3_out"])
+    x2 = fx.randn(c["x2_seed"], *c["x2_shape"])
+    assert torch.equal(ops.batch_index_select(cu(x2), cu(OPS["bis3_idx"])).cpu(), OPS["bis2_out"])
+    with pytest.raises(NotImplementedError):
+        ops.batch_index_select(torch.zeros(2, 2, 2, 2).cuda(), cu(OPS["bis3_idx"]))
+    # prev_decision case: (B,196,1) fp32 goes through the scalar path; unsorted (score-order) indices
+    pd = (torch.rand(4, 196, 1, generator=fx.gen(3)) > 0.5).float()
+    idx = torch.stack([torch.randperm(196, generator=fx.gen(50 + b))[:137] for b in range(4)])
+    assert torch.equal(ops.batch_index_select(cu(pd), cu(idx)).cpu(), oo.batch_index_select(pd, idx))
+
+
+def test_gather_autograd_matches_torch_gather(ops):
+    x = fx.randn(1, 3, 50, 64).cuda().requires_grad_(True)
+    kept = torch.stack([torch.randperm(49, generator=fx.gen(60 + b))[:20].sort().values for b in range(3)]).cuda()
+    up = fx.randn(2, 3, 21, 64).cuda()
+    (ops.gather_tokens(x, kept) * up).sum().backward()
+    g1 = x.grad.clone()
+    x.grad = None
+    rows = torch.cat([torch.zeros(3, 1, dtype=torch.long, device="cuda"), kept + 1], 1)
+    (torch.gather(x, 1, rows.unsqueeze(-1).expand(-1, -1, 64)) * up).sum().backward()
+    assert torch.equal(g1, x.grad)
+
+
+def test_gather_full_size_roundtrip(ops):
+    B, T, D, K = 1024, 197, 384, 137
+    x = torch.randn(B, T, D, device="cuda", dtype=torch.bfloat16)
+    sc = torch.rand(B, T - 1, device="cuda")
+    kept, dropped = ops.select_topk(sc, K, 0)
+    out = ops.gather_tokens(x, kept)
+    rows = torch.cat([torch.zeros(B, 1, dtype=torch.long, device="cuda"), kept + 1], 1)
+    assert torch.equal(out, torch.gather(x, 1, rows.unsqueeze(-1).expand(-1, -1, D)))
+    back = ops.scatter_tokens_bwd(out, kept, T)
+    assert torch.equal(ops.gather_tokens(back, kept), out)                       # gather(scatter(g)) == g
+    assert float(ops.gather_tokens(back, dropped, prepend_cls=True)[:, 1:].float().abs().sum()) == 0.0
+
+
+# ------------------------------------------------------------------------------------------ tails / gumbel
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_score_tail_a_eval(ops, dtype):
+    B, N, Cc, K = 5, 196, 96, 137
+    h = torch.nn.functional.gelu(fx.randn(71, B, N, Cc)).to(dtype)
+    W, b = fx.randn(72, 2, Cc, scale=0.3), fx.randn(73, 2, scale=0.1)
+    logp, kept = ops.score_tail_a(cu(h), cu(W), cu(b), k=K)
+    ref = oo.score_tail_a(h.float(), W, b)
+    torch.testing.assert_close(logp.cpu(), ref, rtol=1e-4, atol=1e-5)
+    # indices are bit-exact w.r.t. the kernel's own scores (near-ties may legitimately differ from the oracle's)
+    rk, _ = oo.select_topk(logp.cpu()[:, :, 0], K, oo.ORDER_SCORE_DESC)
+    assert torch.equal(kept.cpu(), rk)
+
+
+def test_score_tail_a_train_and_gumbel_golden(ops):
+    c = C["gumbel"]
+    logp = torch.log_softmax(fx.randn(c["logit_seed"], *c["shape"], scale=c["scale"]), dim=-1)
+    lg = cu(logp).requires_grad_(True)
+    hard = ops.gumbel_keep_decision(lg, cu(OPS["gum_noise"]), cu(OPS["gum_prev"]))
+    assert torch.equal(hard.detach().cpu(), OPS["gum_hard"])                     # bit-exact decisions
+    (hard * cu(fx.randn(c["up_seed"], 2, 50, 1))).sum().backward()
+    torch.testing.assert_close(lg.grad.cpu(), OPS["gum_grad"], rtol=1e-4, atol=1e-7)
+    # fused tail, train mode
+    B, N, Cc = 3, 196, 96
+    h = torch.nn.functional.gelu(fx.randn(74, B, N, Cc))
+    W, b = fx.randn(75, 2, Cc, scale=0.3), fx.randn(76, 2, scale=0.1)
+    g = -torch.log(-torch.log(torch.rand(B, N, 2, generator=fx.gen(77)).clamp_min(1e-9)))
+    prev = (torch.rand(B, N, generator=fx.gen(78)) > 0.2).float()
+    lp, dec, ys = ops.score_tail_a(cu(h), cu(W), cu(b), gumbel=cu(g), prev=cu(prev))
+    torch.testing.assert_close(lp.cpu(), oo.score_tail_a(h, W, b), rtol=1e-4, atol=1e-5)
+    rdec, rys = oo.gumbel_keep_decision(lp.cpu(), g, prev.unsqueeze(-1))
+    assert torch.equal(dec.cpu(), rdec[..., 0])
+    torch.testing.assert_close(ys.cpu(), rys, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("use_ln", [True, False])
+@pytest.mark.parametrize("prob_mode", [0, 1])
+def test_score_tail_b(ops, dtype, use_ln, prob_mode):
+    B, N, Cc, K = 4, 196, 96, 137
+    h = torch.relu(fx.randn(81, B, N, Cc)).to(dtype)
+    lw, lb = (1 + 0.1 * fx.randn(82, Cc), 0.1 * fx.randn(83, Cc)) if use_ln else (None, None)
+    W, b = fx.randn(84, 1, Cc, scale=0.3), fx.randn(85, 1, scale=0.1)
+    scores, probs, kept, dropped = ops.score_tail_b(cu(h), None if lw is None else cu(lw), None if lb is None else cu(lb),
+                                                    cu(W), cu(b), K, prob_mode=prob_mode)
+    rs, rp = oo.score_tail_b(h.float(), lw, lb, W, b, "kl_div" if prob_mode == 0 else "bce")
+    torch.testing.assert_close(scores.cpu(), rs, rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(probs.cpu(), rp, rtol=1e-4, atol=1e-7)
+    rk, rd = oo.select_topk(probs.cpu(), K, oo.ORDER_INDEX_ASC)
+    assert torch.equal(kept.cpu(), rk) and torch.equal(dropped.cpu(), rd)
+
+
+# ------------------------------------------------------------------------------------------ PerturbedTopK
+@pytest.mark.parametrize("tag", ["ptk_small", "ptk_vit"])
+def test_perturbed_topk_golden(ops, tag):
+    c = C[tag]
+    x = torch.softmax(fx.randn(c["x_seed"], c["b"], c["d"]), dim=-1)
+    noise = fx.randn(c["noise_seed"], c["b"], c["ns"], c["d"])
+    xg = cu(x).requires_grad_(True)
+    ind = ops.perturbed_topk(xg, c["k"], c["ns"], c["sigma"], noise=cu(noise))
+    assert torch.equal(ind.detach().cpu(), OPS[tag + "_ind"])                    # bit-exact vs the reference
+    (ind * cu(fx.randn(c["gout_seed"], c["b"], c["k"], c["d"]))).sum().backward()
+    torch.testing.assert_close(xg.grad.cpu(), OPS[tag + "_gx"], rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("B,N,K,S", [(1, 196, 98, 500), (8, 196, 98, 500), (3, 196, 137, 64), (2, 100, 1, 33),
+                                     (2, 64, 64, 20), (70, 196, 98, 40), (300, 196, 58, 16)])
+def test_perturbed_topk_vs_oracle(ops, B, N, K, S):
+    x = torch.softmax(fx.randn(90, B, N), dim=-1)
+    noise = fx.randn(91, B, S, N)
+    ind, eg = oo.perturbed_topk_fwd(x, noise, K, 0.05)
+    xg = cu(x).requires_grad_(True)
+    out = ops.perturbed_topk(xg, K, S, 0.05, noise=cu(noise))
+    assert torch.equal(out.detach().cpu(), ind)
+    g = fx.randn(92, B, K, N)
+    (out * cu(g)).sum().backward()
+    torch.testing.assert_close(xg.grad.cpu(), oo.perturbed_topk_bwd(g, eg), rtol=1e-4, atol=1e-4)
+
+
+def test_perturbed_topk_ties_and_rng(ops):
+    # all-equal scores and zero noise: every sample picks the K lowest indices (tie rule)
+    x = torch.zeros(2, 196).cuda()
+    out = ops.perturbed_topk(x, 98, 10, 0.05, noise=torch.zeros(2, 10, 196).cuda())
+    assert torch.equal(out, torch.eye(98, 196, device="cuda").expand(2, 98, 196))
+    # in-kernel RNG contract: rows sum to 1, deterministic per seed, close to the injected-noise estimate
+    xs = torch.softmax(fx.randn(93, 4, 196), dim=-1).cuda()
+    a = ops.perturbed_topk(xs, 98, 500, 0.05, seed=1234)
+    b = ops.perturbed_topk(xs, 98, 500, 0.05, seed=1234)
+    c2 = ops.perturbed_topk(xs, 98, 500, 0.05, noise=torch.randn(4, 500, 196, device="cuda"))
+    assert torch.equal(a, b)
+    torch.testing.assert_close(a.sum(-1), torch.ones(4, 98, device="cuda"))
+    assert float((a - c2).abs().max()) < 0.12 and float((a - c2).abs().mean()) < 4e-3
+    # noise statistics of the Philox/Box-Muller stream, recovered from egrad of a constant score vector
+    assert float(a.sum(1).mean()) == pytest.approx(0.5, abs=1e-3)
+
+
+# ------------------------------------------------------------------------------------------ softmax_with_policy
+def test_softmax_with_policy_golden_and_grads(ops):
+    c = C["swp"]
+    s = fx.randn(c["s_seed"], *c["s_shape"], scale=c["s_scale"])
+    torch.testing.assert_close(ops.softmax_with_policy(cu(s), cu(OPS["swp_policy"])).cpu(), OPS["swp_out"], **FP32)
+    torch.testing.assert_close(ops.softmax_with_policy(cu(s), cu(OPS["swp_policy_frac"])).cpu(), OPS["swp_out_frac"], **FP32)
+    torch.testing.assert_close(ops.softmax_with_policy(cu(s), None).cpu(), torch.softmax(s, -1), **FP32)
+    sg = cu(s).requires_grad_(True)
+    pg = cu(OPS["swp_policy_frac"]).requires_grad_(True)
+    (ops.softmax_with_policy(sg, pg) * cu(fx.randn(c["up_seed"], *c["s_shape"]))).sum().backward()
+    torch.testing.assert_close(sg.grad.cpu(), OPS["swp_grad_s"], rtol=1e-4, atol=1e-6)
+    torch.testing.assert_close(pg.grad.cpu(), OPS["swp_grad_p"], rtol=1e-4, atol=1e-6)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("T", [197, 138, 68, 300])
+def test_softmax_with_policy_sizes(ops, dtype, T):
+    B, H = 2, 3
+    s = (fx.randn(100 + T, B, H, T, T) * 2).to(dtype)
+    pol = (torch.rand(B, T, 1, generator=fx.gen(101)) > 0.3).float()
+    pol[:, 0] = 1
+    out = ops.softmax_with_policy(cu(s), cu(pol))
+    ref = oo.softmax_with_policy(s, pol)
+    tol = FP32 if dtype == torch.float32 else dict(rtol=2e-2, atol=1e-3)
+    torch.testing.assert_close(out.cpu().float(), ref.float(), **tol)
+    if dtype == torch.float32:
+        sg, pg = cu(s).requires_grad_(True), cu(pol).requires_grad_(True)
+        up = fx.randn(102, B, H, T, T)
+        (ops.softmax_with_policy(sg, pg) * cu(up)).sum().backward()
+        s2, p2 = s.clone().requires_grad_(True), pol.clone().requires_grad_(True)
+        (oo.softmax_with_policy(s2, p2) * up).sum().backward()
+        torch.testing.assert_close(sg.grad.cpu(), s2.grad, rtol=1e-4, atol=1e-6)
+        torch.testing.assert_close(pg.grad.cpu(), p2.grad, rtol=1e-4, atol=1e-5)
+
+
+# ------------------------------------------------------------------------------------------ fused attention
+def _qkv(seed, B, T, H, hd, scale=1.0):
+    return fx.randn(seed, B, T, 3 * H * hd, scale=scale)
+
+
+@pytest.mark.parametrize("T", [197, 138, 97, 68, 21, 1])
+@pytest.mark.parametrize("with_policy", [False, True])
+def test_attention_fp32_simt(ops, T, with_policy):
+    B, H, hd = 2, 6, 64
+    qkv = _qkv(110 + T, B, T, H, hd)
+    pol = None
+    if with_policy:
+        pol = (torch.rand(B, T, generator=fx.gen(111)) > 0.3).float()
+        pol[:, 0] = 1
+    out, cls = ops.attention_core(cu(qkv), H, policy=None if pol is None else cu(pol), want_cls_row=True)
+    ro, rc = oo.attention_core(qkv.view(B, T, 3, H, hd), H, policy=pol)
+    torch.testing.assert_close(out.cpu(), ro, rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(cls.cpu(), rc, rtol=1e-4, atol=1e-6)
+
+
+@pytest.mark.parametrize("T", [197, 138, 97, 68, 128, 129, 16, 5])
+@pytest.mark.parametrize("with_policy", [False, True])
+def test_attention_bf16_tcgen05(ops, T, with_policy):
+    B, H, hd = 3, 6, 64
+    qkv = _qkv(120 + T, B, T, H, hd).bfloat16()
+    pol = None
+    if with_policy:
+        pol = (torch.rand(B, T, generator=fx.gen(121)) > 0.3).float()
+        pol[:, 0] = 1
+    out, cls = ops.attention_core(cu(qkv), H, policy=None if pol is None else cu(pol), want_cls_row=True)
+    ro, rc = oo.attention_core(qkv.float().view(B, T, 3, H, hd), H, policy=pol)
+    # bf16 operands, fp32 accumulate, bf16 probabilities: 1e-2 (north_star tolerance for bf16)
+    torch.testing.assert_close(out.cpu().float(), ro, rtol=1e-2, atol=1e-2)
+    torch.testing.assert_close(cls.cpu(), rc, rtol=1e-2, atol=2e-4)
+
+
+def test_attention_bf16_large_scores_and_full_batch(ops):
+    # peaked rows (large logits), masked-max rows, and the BASELINE batch: compare with torch SDPA on device
+    B, T, H, hd = 1024, 197, 6, 64
+    qkv = torch.randn(B, T, 3 * H * hd, device="cuda", dtype=torch.bfloat16) * 2.0
+    out, cls = ops.attention_core(qkv, H, want_cls_row=True)
+    q, k, v = qkv.view(B, T, 3, H, hd).permute(2, 0, 3, 1, 4).unbind(0)
+    ref = torch.nn.functional.scaled_dot_product_attention(q.float(), k.float(), v.float()).transpose(1, 2).reshape(B, T, H * hd)
+    torch.testing.assert_close(out.float(), ref, rtol=2e-2, atol=2e-2)
+    torch.testing.assert_close(cls.sum(-1), torch.ones(B, H, device="cuda"), rtol=1e-3, atol=1e-3)
+
+
+def test_attention_golden_module(d2s, ops):
+    c = C["attn"]
+    sd = fx.seeded_state_dict(c["shapes"], c["w_seed"])
+    m = d2s.layers.Attention(c["dim"], num_heads=c["heads"], qkv_bias=True)
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda().eval()
+    x = cu(fx.randn(c["x_seed"], *c["x_shape"]))
+    with torch.no_grad():
+        o, ca = m(x, None, return_cls_attn=True)
+        torch.testing.assert_close(o.cpu(), OPS["attn_out"], **FP32)
+        torch.testing.assert_close(ca.cpu(), OPS["attn_cls"], **FP32)
+        o, ca = m(x, cu(OPS["attn_policy"]), return_cls_attn=True)
+        torch.testing.assert_close(o.cpu(), OPS["attn_out_pol"], **FP32)
+        torch.testing.assert_close(ca.cpu(), OPS["attn_cls_pol"], **FP32)
+    # autograd path gives the same forward
+    o2, ca2 = m(x.requires_grad_(True), cu(OPS["attn_policy"]), return_cls_attn=True)
+    torch.testing.assert_close(o2.detach().cpu(), OPS["attn_out_pol"], **FP32)
+
+
+# ------------------------------------------------------------------------------------------ error behaviour
+def test_errors_are_loud(ops):
+    with pytest.raises(RuntimeError):
+        ops.select_topk(torch.rand(2, 196), 10)                                   # CPU tensor: no fallback
+    with pytest.raises(RuntimeError, match="N="):
+        ops.select_topk(torch.rand(2, 2000).cuda(), 10)
+    with pytest.raises(RuntimeError, match="K="):
+        ops.select_topk(torch.rand(2, 196).cuda(), 500)
+    with pytest.raises(TypeError):
+        ops.gather_tokens(torch.zeros(2, 4, 8, dtype=torch.float16).cuda(), torch.zeros(2, 2, dtype=torch.long).cuda())
+    with pytest.raises(RuntimeError, match="head dim"):
+        ops.attention_core(torch.zeros(1, 8, 3 * 2 * 48, dtype=torch.bfloat16).cuda(), 2)
