@@ -1,0 +1,362 @@
+#!/usr/bin/env python
+"""Throughput of the token-sparsification hot path inside DynamicViT DeiT-S/16, keep rate 0.7, 224 px.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl d2s|reference] [--batch B]
+
+A "step" is one inference pass of the pruned model over one batch of synthetic images (BASELINE.json
+configs[1]: batch 1024 per GPU, bf16).  N > 1 = one process per GPU (torchrun), the batch dimension is sharded
+with no data-path collective (weak scaling: every rank owns its own 1024 images).  Rank 0 prints ONE JSON line.
+
+  value        images/s, inputs resident in HBM, CUDA-graph replay of the whole forward, CUDA-event timed
+  e2e          images/s through the public API with pinned HOST images in and HOST logits out every step
+  roofline     the dominant d2s kernel (policy attention), timed alone with CUDA events at the step's shapes
+  cpu_baseline the CPU restatement of the reference forward (oracle/), timed on this box's host cores
+  --impl reference   times that CPU forward alone (the reference is pure PyTorch-on-CPU)
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "tests", "golden")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+METRIC = "images/sec DynamicViT DeiT-S kr=0.7 @224"
+UNIT = "images/s"
+LOCS, RATIOS = [3, 6, 9], [0.7, 0.7 ** 2, 0.7 ** 3]   # upstream DynamicViT convention (SURVEY.md 8d cfg 1/2)
+DEIT_S = dict(patch_size=16, embed_dim=384, depth=12, num_heads=6, mlp_ratio=4, qkv_bias=True)
+GFLOP_PER_IMG = 5.96                                    # SURVEY.md 8d, Variant A 3 stages
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="d2s", choices=["d2s", "reference"])
+    ap.add_argument("--batch", type=int, default=1024, help="images per GPU per step")
+    ap.add_argument("--cpu-batch", type=int, default=8, help="images per CPU step (BASELINE configs[0])")
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--skip-cpu", action="store_true", help="omit the cpu_baseline leg (debugging only)")
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            p = json.load(fh)
+        return dict(hbm=float(p["hbm_gbs"]), tf_burst=float(p["bf16_tflops"]),
+                    tf_sustained=float(p.get("bf16_tflops_sustained", p["bf16_tflops"])), source="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback")
+
+
+# ---------------------------------------------------------------------------------------------------
+# CPU arm: the oracle's restatement of DefaultVisionTransformerDiffPruning.forward (eval), all host threads
+# ---------------------------------------------------------------------------------------------------
+def cpu_forward_setup(batch):
+    import torch
+    from oracle import model as om           # bench.py's cpu legs are allowed to execute oracle/
+    import d2s
+    torch.manual_seed(0)
+    m = d2s.pkg.variant_a.DefaultVisionTransformerDiffPruning(pruning_loc=LOCS, token_ratio=RATIOS, distill=True, **DEIT_S)
+    sd = {k: v.detach().float() for k, v in m.state_dict().items()}
+    cfg = om.VitCfg(embed_dim=384, depth=12, num_heads=6, pruning_loc=LOCS, token_ratio=RATIOS)
+    img = torch.randn(batch, 3, 224, 224, generator=torch.Generator().manual_seed(42))
+    return om, sd, cfg, img
+
+
+def time_cpu(batch, steps, warmup, budget_s=None):
+    import torch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    om, sd, cfg, img = cpu_forward_setup(batch)
+    with torch.no_grad():
+        for _ in range(warmup):
+            om.variant_a_eval(sd, cfg, img)
+        times = []
+        t_begin = time.perf_counter()
+        for _ in range(steps):
+            t0 = time.perf_counter()
+            om.variant_a_eval(sd, cfg, img)
+            times.append(time.perf_counter() - t0)
+            if budget_s is not None and time.perf_counter() - t_begin > budget_s and len(times) >= 3:
+                break
+    total = sum(times)
+    return dict(img_s=batch * len(times) / total, ms_per_step=1e3 * total / len(times), steps=len(times),
+                cores=torch.get_num_threads())
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    r = time_cpu(args.cpu_batch, args.steps, args.warmup)
+    sample = (f"{r['steps']} steps x batch {args.cpu_batch} fp32 images, oracle.model.variant_a_eval "
+              f"(CPU restatement of default_dynamic_vit.py:435-487), torch {r['cores']} threads")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["img_s"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": r["steps"], "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "DynamicViT DeiT-S/16 keep_rate=0.7 (3 stages @3,6,9) inference, 224px, synthetic images",
+                   "cpu_batch": args.cpu_batch, "pruning_loc": LOCS, "token_ratio": RATIOS},
+        "cpu_baseline": {"value": r["img_s"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": sample},
+        "e2e": {"value": r["img_s"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            pass
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in out.strip().splitlines():
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "power_w_max": max(pw), "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+def time_kernel(fn, iters, torch):
+    """Average duration (ms) of `fn` over `iters` back-to-back launches on the current stream (CUDA events)."""
+    for _ in range(3):
+        fn()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    s.record()
+    for _ in range(iters):
+        fn()
+    e.record()
+    torch.cuda.synchronize()
+    return s.elapsed_time(e) / iters
+
+
+def kernel_breakdown(ops, B, dev, torch, pk):
+    """Time every d2s kernel of one forward alone, at the shapes the step launches them with.
+    Returns (rows, roofline dict for the dominant kernel)."""
+    D, H, hd, N0 = 384, 6, 64, 196
+    e = 2  # bf16
+    rows = []
+    # token count per layer: blocks 0-2: 197; 3-5: 138; 6-8: 97; 9-11: 68
+    Ks = [int(N0 * r) for r in RATIOS]
+    Ts = [N0 + 1] + [k + 1 for k in Ks]
+    attn_ms, attn_bytes, attn_flops = 0.0, 0.0, 0.0
+    for T in Ts:
+        qkv = torch.randn(B, T, 3 * D, device=dev, dtype=torch.bfloat16)
+        ms = time_kernel(lambda: ops.attention_core(qkv, H), 20, torch)
+        by = B * (e * 4 * T * D)                      # q,k,v in + out, bf16
+        fl = B * 4.0 * H * T * T * hd
+        rows.append(dict(kernel="attn_policy_fwd(tcgen05)", shape=f"B={B},T={T},H={H},hd={hd}", launches_per_step=3,
+                         ms=ms, algo_bytes=by, gbs=by / ms / 1e6, tflops=fl / ms / 1e9))
+        attn_ms += 3 * ms; attn_bytes += 3 * by; attn_flops += 3 * fl
+        del qkv
+    n_in = N0
+    for s, K in enumerate(Ks):
+        T_in = n_in + 1
+        x = torch.randn(B, T_in, D, device=dev, dtype=torch.bfloat16)
+        sc = torch.rand(B, n_in, device=dev)
+        kept, _ = ops.select_topk(sc, K, ops.ORDER_SCORE_DESC, want_dropped=False)
+        ms = time_kernel(lambda: ops.gather_tokens(x, kept), 50, torch)
+        by = B * (2 * e * D * (K + 1) + 8 * (K + 1))
+        rows.append(dict(kernel="gather_tokens", shape=f"B={B},T={T_in},D={D},K={K}", launches_per_step=1, ms=ms,
+                         algo_bytes=by, gbs=by / ms / 1e6))
+        hid = torch.randn(B, n_in, D // 4, device=dev, dtype=torch.bfloat16)
+        W = torch.randn(2, D // 4, device=dev) * 0.1
+        bias = torch.zeros(2, device=dev)
+        ms = time_kernel(lambda: ops.score_tail_a(hid, W, bias, k=K), 50, torch)
+        by = B * (e * n_in * (D // 4) + 8 * n_in + 8 * K)
+        rows.append(dict(kernel="score_tail_a(+select)", shape=f"B={B},N={n_in},C={D // 4},K={K}", launches_per_step=1,
+                         ms=ms, algo_bytes=by, gbs=by / ms / 1e6))
+        pd = torch.ones(B, n_in, 1, device=dev, dtype=torch.bfloat16)
+        ms = time_kernel(lambda: ops.batch_index_select(pd, kept), 50, torch)
+        rows.append(dict(kernel="batch_index_select(prev_decision)", shape=f"B={B},N={n_in},K={K}", launches_per_step=1,
+                         ms=ms, algo_bytes=B * (2 * e * K + 8 * K), gbs=B * (2 * e * K + 8 * K) / ms / 1e6))
+        n_in = K
+        del x, sc, hid
+    roof = {"kernel": "attn_tc_fwd_kernel (12 launches/step, T=197/138/97/68)", "bound": "hbm",
+            "achieved": attn_bytes / attn_ms / 1e6, "peak": pk["hbm"], "unit": "GB/s",
+            "frac": attn_bytes / attn_ms / 1e6 / pk["hbm"], "traffic": None, "peak_source": pk["source"],
+            "ms_per_step_in_kernel": attn_ms,
+            "tensor": {"achieved": attn_flops / attn_ms / 1e9, "peak": pk["tf_burst"], "unit": "TFLOP/s",
+                       "frac": attn_flops / attn_ms / 1e9 / pk["tf_burst"]}}
+    return rows, roof
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    import d2s
+    pkg = d2s.pkg
+    rank = int(os.environ.get("RANK", 0))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (d2s arm) needs a CUDA device: there is no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    pk = peaks()
+    B, K, W = args.batch, args.steps, max(args.warmup, 3)
+
+    torch.manual_seed(0)
+    model = pkg.variant_a.DefaultVisionTransformerDiffPruning(pruning_loc=LOCS, token_ratio=RATIOS, distill=True, **DEIT_S)
+    runner = pkg.runner.InferenceRunner(model, B, dev, dtype=torch.bfloat16, use_graph=not args.no_graph, warmup=2)
+    # kernels per forward: count one eager forward through the C ABI (the graph replays exactly these)
+    n0 = pkg._lib.launch_count()
+    with torch.no_grad():
+        runner.model(runner.static_in)
+    torch.cuda.synchronize()
+    launches_per_step = pkg._lib.launch_count() - n0
+
+    g = torch.Generator(device=dev).manual_seed(42 + rank)
+    runner.static_in.copy_(torch.randn(runner.static_in.shape, device=dev, generator=g).to(torch.bfloat16))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value: inputs resident in HBM ------------------------------------------------------------
+    for _ in range(W):
+        runner.replay()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(K):
+        runner.replay()
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    total_ms = float(ms.item())
+    value = world * B * K / (total_ms / 1e3)
+    logits_ok = bool(torch.isfinite(runner.logits.float()).all())
+
+    # ---- e2e: pinned host images -> device -> forward -> host logits, every step -----------------------
+    host = [torch.randn(B, 3, 224, 224, generator=torch.Generator().manual_seed(100 + i)).to(torch.bfloat16).pin_memory()
+            for i in range(2)]
+    h2d = host[0].numel() * host[0].element_size()
+    d2h = runner.logits.numel() * runner.logits.element_size()
+    for i in range(2):
+        runner.step_prefetched(runner.prefetch(host[i & 1]))
+    barrier()
+    t0 = time.perf_counter()
+    slot = runner.prefetch(host[0])
+    out_host = None
+    for i in range(K):
+        # start the next step's copy before this step's compute is enqueued: the copy overlaps the compute
+        nxt = runner.prefetch(host[(i + 1) & 1]) if i + 1 < K else None
+        out_host = runner.step_prefetched(slot)
+        slot = nxt
+    torch.cuda.synchronize()
+    e2e_s = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+    barrier()
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_val = world * B * K / float(e2e_s.item())
+    e2e_ok = bool(torch.isfinite(out_host.float()).all())
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    # ---- rank 0: per-kernel breakdown, roofline, cpu baseline ----------------------------------------
+    rows, roof = kernel_breakdown(pkg.ops, B, dev, torch, pk)
+    own_ms = sum(r["ms"] * r["launches_per_step"] for r in rows)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "DynamicViT DeiT-S/16 keep_rate=0.7 (3 stages @3,6,9; ratios 0.7/0.49/0.343) inference, "
+                               "224px, batch 1024 per GPU, bf16, random-init weights",
+                   "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world} (batch-sharded, no collective)",
+                   "cuda_graph": not args.no_graph,
+                   "l2": "inputs larger than L2: 308 MB of images and >1 GB of activations per step vs 126 MB L2",
+                   "outputs_finite": logits_ok and e2e_ok},
+        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "note": "pinned bf16 host images, double-buffered H2D on a copy stream overlapping the previous step, "
+                        "host logits read back every step; wall clock between device synchronisations"},
+        "gpu_launches": int(launches_per_step * K),
+        "d2s_launches_per_step": int(launches_per_step),
+        "clocks": clocks,
+        "roofline": roof,
+        "model_tensor_frac": {"gflop_per_img": GFLOP_PER_IMG, "achieved_tflops": value / world * GFLOP_PER_IMG / 1e3,
+                              "peak": pk["tf_sustained"], "frac": value / world * GFLOP_PER_IMG / 1e3 / pk["tf_sustained"],
+                              "peak_source": pk["source"] + " (sustained)"},
+        "d2s_kernel_ms_per_step": own_ms, "d2s_kernel_share_of_step": own_ms / (total_ms / K),
+        "kernels": rows,
+    }
+    if not args.skip_cpu:
+        c = time_cpu(args.cpu_batch, steps=40, warmup=1, budget_s=15.0)
+        line["cpu_baseline"] = {
+            "value": c["img_s"], "unit": UNIT, "cores": c["cores"], "kind": "port",
+            "sample": f"{c['steps']} forwards of batch {args.cpu_batch} fp32 (BASELINE configs[0]) through "
+                      f"oracle.model.variant_a_eval, same architecture and pruning schedule"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    if args.gpus > 1 and "WORLD_SIZE" not in os.environ:
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.abspath(__file__)] + sys.argv[1:]
+        raise SystemExit(subprocess.call(cmd))
+    run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

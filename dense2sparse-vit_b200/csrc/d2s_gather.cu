@@ -153,7 +153,7 @@ static int splits_for(int B, int rows) {
 
 static int check_common(const void* a, const void* b, const int64_t* idx, int dtype, int B, int T, int D, int K,
                         int prepend_cls) {
-  D2S_REQUIRE(a && b && idx, D2S_ERR_ARG, "gather/scatter: null pointer");
+  D2S_REQUIRE(a && b && (idx || K == 0), D2S_ERR_ARG, "gather/scatter: null pointer");
   D2S_REQUIRE(dtype == D2S_F32 || dtype == D2S_BF16, D2S_ERR_ARG, "gather/scatter: dtype %d unsupported", dtype);
   D2S_REQUIRE(B >= 0 && T >= 1 && D >= 1 && K >= 0, D2S_ERR_ARG, "gather/scatter: bad shape B=%d T=%d D=%d K=%d", B, T, D, K);
   D2S_REQUIRE(B <= 65535, D2S_ERR_ARG, "gather/scatter: B=%d exceeds 65535", B);

@@ -46,6 +46,8 @@ def select_topk(score: torch.Tensor, k: int, order: int = ORDER_INDEX_ASC, want_
     _check_cuda(score)
     s = _f32c(score)
     B, N = s.shape
+    if not 0 <= k <= N:
+        raise RuntimeError(f"select_topk: K={k} outside [0, N={N}]")
     kept = torch.empty(B, k, dtype=torch.int64, device=s.device)
     dropped = torch.empty(B, N - k, dtype=torch.int64, device=s.device) if want_dropped else None
     _lib.call("d2s_select_topk_f32", _ptr(s), B, N, k, order, _ptr(kept), _ptr(dropped), _stream())

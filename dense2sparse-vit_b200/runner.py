@@ -91,7 +91,7 @@ class InferenceRunner:
             self._used = [False, False]
 
     def prefetch(self, x_host):
-        """Start the host->device copy of the NEXT step's images on the copy stream."""
+        """Start the host->device copy of a later step's images on the copy stream; returns the staging slot."""
         self._ensure_pipeline()
         k = self._slot
         with torch.cuda.stream(self._copy_stream):
@@ -99,13 +99,12 @@ class InferenceRunner:
                 self._copy_stream.wait_event(self._free[k])
             self._stage[k].copy_(x_host, non_blocking=True)
             self._ready[k].record(self._copy_stream)
-        self._pending = k
         self._slot ^= 1
+        return k
 
-    def step_prefetched(self):
-        """Run one forward on the images whose copy was started by prefetch(); returns pinned host logits
-        (valid after the caller synchronises the current stream)."""
-        k = self._pending
+    def step_prefetched(self, k):
+        """Run one forward on the images whose copy was started by `k = prefetch(...)`; returns pinned host
+        logits (valid after the caller synchronises the current stream)."""
         cur = torch.cuda.current_stream(self.device)
         cur.wait_event(self._ready[k])
         self.static_in.copy_(self._stage[k], non_blocking=True)
