@@ -26,7 +26,7 @@ SIGNATURES = {
     "d2s_score_tail_a": [_p, _i, _i, _i, _i, _p, _p, _i, _p, _p, _p, _p, _p, _p, _p],
     "d2s_score_tail_b": [_p, _i, _i, _i, _i, _p, _p, _f, _p, _p, _i, _i, _p, _p, _p, _p, _p],
     "d2s_gumbel_decision_f32": [_p, _p, _p, _i64, _p, _p, _p],
-    "d2s_gumbel_decision_bwd_f32": [_p, _p, _p, _i64, _p, _p],
+    "d2s_gumbel_decision_bwd_f32": [_p, _p, _p, _p, _i64, _p, _p, _p],
     "d2s_gather_tokens": [_p, _i, _i, _i, _i, _p, _i, _i, _p, _p],
     "d2s_scatter_tokens_bwd": [_p, _i, _i, _i, _i, _p, _i, _i, _p, _p],
     "d2s_ptopk_fwd": [_p, _p, _i, _i, _i, _i, _f, _p, _p, _p],

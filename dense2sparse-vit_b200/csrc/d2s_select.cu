@@ -304,13 +304,22 @@ __global__ void gumbel_decision_kernel(const float* __restrict__ logp, const flo
   }
 }
 
-// Straight-through backward: only y_soft carries gradient (value = hard - y.detach() + y).
-__global__ void gumbel_decision_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ ysoft,
-                                           const float* __restrict__ prev, int64_t n, float* __restrict__ glogp) {
+// Straight-through backward: value = (hard - y.detach() + y)[0] * prev, so
+//   d/dlogp = (+g, -g) with g = gout * prev * y0 * (1 - y0)      (only y_soft carries gradient)
+//   d/dprev = gout * hard0                                        (prev is the previous stage's decision, :459)
+// hard0 and y0 are recomputed from (logp, gumbel) with the forward's own routine: bit-identical, nothing saved.
+__global__ void gumbel_decision_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ logp,
+                                           const float* __restrict__ gumbel, const float* __restrict__ prev, int64_t n,
+                                           float* __restrict__ glogp, float* __restrict__ gprev) {
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
-    const float y = ysoft[t];
-    const float g = gout[t] * (prev ? prev[t] : 1.0f) * y * (1.0f - y);
+    const float2 lp = reinterpret_cast<const float2*>(logp)[t];
+    const float2 gm = reinterpret_cast<const float2*>(gumbel)[t];
+    float hard0, y;
+    gumbel_decide(lp.x, lp.y, gm.x, gm.y, 1.0f, hard0, y);
+    const float go = gout[t];
+    const float g = go * (prev ? prev[t] : 1.0f) * y * (1.0f - y);
     reinterpret_cast<float2*>(glogp)[t] = make_float2(g, -g);
+    if (gprev) gprev[t] = go * hard0;
   }
 }
 
@@ -396,12 +405,12 @@ extern "C" int d2s_gumbel_decision_f32(const float* logp, const float* gumbel, c
   return check_launch("d2s_gumbel_decision_f32");
 }
 
-extern "C" int d2s_gumbel_decision_bwd_f32(const float* gout, const float* ysoft, const float* prev, int64_t n,
-                                           float* glogp, d2s_stream_t stream) {
-  D2S_REQUIRE(gout && ysoft && glogp, D2S_ERR_ARG, "gumbel_decision_bwd: null pointer");
+extern "C" int d2s_gumbel_decision_bwd_f32(const float* gout, const float* logp, const float* gumbel, const float* prev,
+                                           int64_t n, float* glogp, float* gprev, d2s_stream_t stream) {
+  D2S_REQUIRE(gout && logp && gumbel && glogp, D2S_ERR_ARG, "gumbel_decision_bwd: null pointer");
   D2S_REQUIRE(n >= 0, D2S_ERR_ARG, "gumbel_decision_bwd: n < 0");
   if (n == 0) return D2S_OK;
-  gumbel_decision_bwd_kernel<<<grid_1d(n, 256), 256, 0, (cudaStream_t)stream>>>(gout, ysoft, prev, n, glogp);
+  gumbel_decision_bwd_kernel<<<grid_1d(n, 256), 256, 0, (cudaStream_t)stream>>>(gout, logp, gumbel, prev, n, glogp, gprev);
   count_launch();
   return check_launch("d2s_gumbel_decision_bwd_f32");
 }

@@ -102,22 +102,26 @@ class _GumbelKeep(torch.autograd.Function):
         n = lp.numel() // 2
         pv = _f32c(prev.reshape(-1)) if prev is not None else None
         decision = torch.empty(lp.shape[:-1], dtype=torch.float32, device=lp.device)
-        ysoft = torch.empty_like(decision)
-        _lib.call("d2s_gumbel_decision_f32", _ptr(lp), _ptr(g), _ptr(pv), n, _ptr(decision), _ptr(ysoft), _stream())
-        ctx.save_for_backward(ysoft, pv if pv is not None else torch.empty(0, device=lp.device))
+        _lib.call("d2s_gumbel_decision_f32", _ptr(lp), _ptr(g), _ptr(pv), n, _ptr(decision), None, _stream())
+        ctx.save_for_backward(lp, g, pv if pv is not None else torch.empty(0, device=lp.device))
         ctx.has_prev = pv is not None
         ctx.in_dtype = logp.dtype
+        ctx.prev_meta = None if prev is None else (prev.shape, prev.dtype)
         return decision.unsqueeze(-1).to(logp.dtype)
 
     @staticmethod
     def backward(ctx, gout):
-        ysoft, pv = ctx.saved_tensors
+        lp, gm, pv = ctx.saved_tensors
         g = _f32c(gout.reshape(-1))
-        n = ysoft.numel()
-        glogp = torch.empty(*ysoft.shape, 2, dtype=torch.float32, device=ysoft.device)
-        _lib.call("d2s_gumbel_decision_bwd_f32", _ptr(g), _ptr(ysoft), _ptr(pv) if ctx.has_prev else None, n,
-                  _ptr(glogp), _stream())
-        return glogp.to(ctx.in_dtype), None, None
+        n = lp.numel() // 2
+        glogp = torch.empty_like(lp)
+        want_gprev = ctx.has_prev and ctx.needs_input_grad[2]
+        gprev = torch.empty(n, dtype=torch.float32, device=lp.device) if want_gprev else None
+        _lib.call("d2s_gumbel_decision_bwd_f32", _ptr(g), _ptr(lp), _ptr(gm), _ptr(pv) if ctx.has_prev else None, n,
+                  _ptr(glogp), _ptr(gprev), _stream())
+        if gprev is not None:
+            gprev = gprev.reshape(ctx.prev_meta[0]).to(ctx.prev_meta[1])
+        return glogp.to(ctx.in_dtype), None, gprev
 
 
 def gumbel_keep_decision(logp, gumbel, prev=None):

@@ -74,12 +74,14 @@ int d2s_score_tail_b(const void* hidden, int dtype, int B, int N, int C,
                      const float* W, const float* bias, int prob_mode, int K,
                      float* scores, float* probs, int64_t* kept, int64_t* dropped, d2s_stream_t stream);
 
-/* Stand-alone Gumbel keep decision and its straight-through backward (default_dynamic_vit.py:454).
- * logp, gumbel (n,2); prev, decision, ysoft (n); n = B*N. */
+/* Stand-alone Gumbel keep decision and its straight-through backward (default_dynamic_vit.py:454-459).
+ * logp, gumbel (n,2); prev, decision, ysoft (n); n = B*N.  decision = hard0 * prev, hard0 = [y0 >= y1].
+ * Backward recomputes hard0 / y0 from (logp, gumbel): glogp (n,2) = gout*prev*y0*(1-y0) * (+1,-1);
+ * gprev (n) = gout*hard0 (prev is the previous stage's decision and carries gradient at :459), NULL to skip. */
 int d2s_gumbel_decision_f32(const float* logp, const float* gumbel, const float* prev, int64_t n,
                             float* decision, float* ysoft, d2s_stream_t stream);
-int d2s_gumbel_decision_bwd_f32(const float* gout, const float* ysoft, const float* prev, int64_t n,
-                                float* glogp, d2s_stream_t stream);
+int d2s_gumbel_decision_bwd_f32(const float* gout, const float* logp, const float* gumbel, const float* prev,
+                                int64_t n, float* glogp, float* gprev, d2s_stream_t stream);
 
 /* ---- (3) gather / scatter of kept tokens ------------------------------------------------------------
  * prepend_cls=1 replaces cat(0, kept+1) + torch.gather / batch_index_select of the token matrix

@@ -211,6 +211,23 @@ def model_goldens():
                  "blocks.0.attn.qkv.weight", "blocks.2.attn.proj.weight", "pos_embed"]:
         A["B_grad::" + name] = dict(mb.named_parameters())[name].grad.clone()
     meta["B"]["u_seed"], meta["B"]["v_seed0"] = 113, 114
+    # The reference's own fp32 CPU backward of the stage-0 predictor is off by up to 1e-2 (relative) from
+    # its fp64 backward (torch CPU reduction order over the expanded global-pool branch); the parity target
+    # for gradients is therefore the reference run in float64, stored as float32.
+    mb64 = ref.dvit.VisionTransformerDiffPruning(pruning_loc=locs, token_ratio=ratios, distill=True,
+                                                 topk_selection=True, predictor_loss_type="kl_div", **common)
+    mb64.load_state_dict(sd)
+    mb64 = mb64.double().train()
+    logits64, _, pred_logits64, kept64 = mb64(img.double())
+    assert all(torch.equal(a, b) for a, b in zip(kept64, kept))
+    loss64 = (logits64 * u.double()).sum() + sum((pl * fx.randn(114 + i, *pl.shape).double()).sum()
+                                                 for i, pl in enumerate(pred_logits64))
+    mb64.zero_grad()
+    loss64.backward()
+    for name in ["score_predictor.0.out_conv.13.weight", "score_predictor.0.out_conv.1.weight",
+                 "score_predictor.0.in_conv.1.weight", "score_predictor.1.in_conv.1.weight",
+                 "blocks.0.attn.qkv.weight", "blocks.2.attn.proj.weight", "pos_embed"]:
+        A["B_grad64::" + name] = dict(mb64.named_parameters())[name].grad.float().clone()
 
     # ---- Variant B threshold (dynamic keep ratio) training branch (dynamic_vit.py:880-894)
     mt = ref.dvit.VisionTransformerDiffPruning(pruning_loc=[1], token_ratio=[0.7], distill=True, topk_selection=True,

@@ -111,9 +111,15 @@ def test_variant_b_eval_train_fp32_with_grads(d2s, cuda_dev, img):
     model.zero_grad()
     loss.backward()
     params = dict(model.named_parameters())
+    # Gradient targets: the reference run in float64 (B_grad64::*).  The reference's own fp32 CPU backward of the
+    # stage-0 predictor deviates from its fp64 backward by up to 1e-2 (see make_goldens.py), so the fp32 goldens
+    # (B_grad::*) are only checked at that looser level.
+    for key in [k for k in MOD if k.startswith("B_grad64::")]:
+        g, ref = params[key.split("::")[1]].grad.cpu(), MOD[key]
+        assert _rel_max(g, ref) < 1e-4, (key, _rel_max(g, ref))
     for key in [k for k in MOD if k.startswith("B_grad::")]:
         g, ref = params[key.split("::")[1]].grad.cpu(), MOD[key]
-        assert _rel_max(g, ref) < 2e-4, (key, _rel_max(g, ref))
+        assert _rel_max(g, ref) < 2e-2, (key, _rel_max(g, ref))
 
 
 def test_variant_b_eval_bf16(d2s, cuda_dev, img):

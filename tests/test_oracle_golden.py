@@ -191,6 +191,23 @@ def test_variant_b_eval_and_train():
     torch.testing.assert_close(out["features"], MOD["B_train_feats"], rtol=1e-4, atol=1e-5)
 
 
+def test_variant_b_gradients_vs_fp64_reference():
+    """Autograd through the oracle reproduces the reference's float64 gradients (the reference's own fp32 CPU
+    backward is only accurate to ~1e-2 on the stage-0 predictor; see make_goldens.py)."""
+    m = MOD_META["B"]
+    sd = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in sd_for(m).items()}
+    out = om.variant_b_forward(sd, _cfg(m), _img(), training=True)
+    u = fx.randn(m["u_seed"], *out["logits"].shape)
+    loss = (out["logits"] * u).sum() + sum((pl * fx.randn(m["v_seed0"] + i, *pl.shape)).sum()
+                                           for i, pl in enumerate(out["pred_logits"]))
+    loss.backward()
+    keys = [k for k in MOD if k.startswith("B_grad64::")]
+    assert len(keys) == 7
+    for key in keys:
+        g, ref = sd[key.split("::")[1]].grad, MOD[key]
+        assert float((g - ref).abs().max() / ref.abs().max()) < 1e-4, key
+
+
 def test_variant_b_threshold_train():
     m = MOD_META["Bthr"]
     cfg = _cfg(m, small_predictor=True, patch_score_threshold=m["threshold"])
