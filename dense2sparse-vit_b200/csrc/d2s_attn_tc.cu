@@ -9,17 +9,25 @@
 //   out = (O + (eps/T) * colsum(V)) / (rowsum + eps)     -- the reference's "+eps/T on every entry" term
 //                    (vit_models/dynamic_vit.py:213) folded into one per-head vector; CLS row side output.
 //
-// One CTA per (image, head, 128-query-row tile); 2 CTAs per SM (256 TMEM columns and ~70 KB smem each).
-// Per image-layer (T=197, H=6): 59.6 MFLOP against 611 KB of algorithmic HBM traffic:
-// HBM-bound unless the QKV projection is fused; the scores never touch HBM.
+// Execution model: persistent CTAs (2 per SM for T > 128, 4 per SM for T <= 128), each looping over (image, head)
+// units.  Warp 4 lane 0 is the control thread: it issues the TMA loads (one 3-D tensor map over the packed
+// (B, T, 3*H*64) qkv buffer, box = 64 x 128 rows, SWIZZLE_128B, rows past T zero-filled by the TMA unit) and the
+// tcgen05.mma instructions; warps 0-3 are the softmax/epilogue warps (TMEM lane quadrant = warp id).  Inside one
+// CTA a unit is a serial chain S-MMA -> softmax -> PV-MMA -> epilogue; the loads of the NEXT unit are issued as soon
+// as their buffers die (Q/K after the last S-MMA, V after the last PV-MMA) so they land during the softmax, and the
+// other CTAs resident on the SM fill the tensor / MUFU / FMA pipes while this one waits.
+//
+// Per image-layer (T=197, H=6): 59.6 MFLOP against 611 KB of algorithmic HBM traffic: HBM-bound
+// unless the QKV projection is fused; the scores never touch HBM.  The MUFU (exp2) floor is ~64 us for B=1024.
+#include <cuda.h>
 #include "d2s_common.cuh"
 
 namespace d2s {
 
-constexpr int kTcThreads = 160;  // warps 0-3: softmax/epilogue (TMEM lane quadrant = warp id); warp 4: alloc + MMA issue
+constexpr int kTcThreads = 160;  // warps 0-3: softmax/epilogue (TMEM lane quadrant = warp id); warp 4: TMA + MMA issue
 constexpr int kTcHD = 64;
-constexpr int kTmemCols = 256;
-constexpr int kOCol = 128;       // O accumulator columns [128,192): beyond the packed-P columns [0, Tkp/2)
+constexpr int kTileRows = 128;
+constexpr uint32_t kTileBytes = kTileRows * 128;  // one TMA box: 128 rows x 64 bf16
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -28,6 +36,9 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   asm volatile(
@@ -42,11 +53,12 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
-  const int sz = valid ? 16 : 0;  // src-size 0 => zero fill
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+// TMA: 3-D tiled load (coordinates innermost first), completion on an mbarrier
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 
 // 64-bit shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout), SWIZZLE_128B, version 1.
@@ -82,25 +94,28 @@ __device__ __forceinline__ void mma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
-__device__ __forceinline__ void tmem_ld16(uint32_t addr, float (&v)[16]) {
-  uint32_t r[16];
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t addr, uint32_t (&r)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(addr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_st8(uint32_t addr, const uint32_t (&r)[8]) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(addr), "r"(r[0]),
                "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
                : "memory");
 }
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
-  const __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);  // .x = lo -> low 16 bits
-  return *reinterpret_cast<const uint32_t*>(&t);
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));  // first source -> upper half
+  return r;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
 
 // byte offset of 16-byte chunk `c` (0..7) of row `r` inside a [rows x 128 B] SWIZZLE_128B tile
@@ -108,174 +123,238 @@ __device__ __forceinline__ uint32_t sw128_off(int r, int c) {
   return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4));
 }
 
-struct TcSmemTail {
-  uint64_t bar_s, bar_p, bar_o;
+struct TcBars {
+  uint64_t q_full[2], k_full, v_full, s_full, p_full, o_full, tmem_free;
   uint32_t tmem_base;
-  float den0;
-  float pol[256];
-  float cls[256];
-  float vsum[kTcHD];
+  uint32_t pad;
 };
 
-__global__ void __launch_bounds__(kTcThreads, 2)
-attn_tc_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ policy, int T, int H, int Tkp,
-                   float scale, float eps, __nv_bfloat16* __restrict__ out, float* __restrict__ cls_row) {
+// kNT  : 128-row tiles per unit (1: T <= 128, 2: T <= 256)
+// kPol : policy given (eps terms, masked exponentials, colsum(V))
+template <int kNT, bool kPol>
+__global__ void __launch_bounds__(kTcThreads, kNT == 1 ? 4 : 2)
+attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap qkv_map, const float* __restrict__ policy, int num_units, int T,
+                   int H, int Tkp, int box_rows, float scale, float eps, __nv_bfloat16* __restrict__ out,
+                   float* __restrict__ cls_row) {
+  constexpr int kTmemCols = kNT == 1 ? 128 : 256;
+  constexpr int kOCol = kNT == 1 ? 64 : 128;  // O accumulator columns: beyond the packed-P columns [0, Tkp/2)
   extern __shared__ unsigned char smem_dyn[];
   // SWIZZLE_128B atoms are 1024 B and address based: align the tile region
   const uint32_t raw = smem_u32(smem_dyn);
   const uint32_t pad = (1024u - (raw & 1023u)) & 1023u;
   unsigned char* tiles = smem_dyn + pad;
-  unsigned char* q_s = tiles;                         // 128 x 128 B
-  unsigned char* k_s = q_s + 128 * 128;               // Tkp x 128 B
-  unsigned char* v_s = k_s + (size_t)Tkp * 128;       // Tkp x 128 B
-  TcSmemTail* tail = reinterpret_cast<TcSmemTail*>(v_s + (size_t)Tkp * 128);
+  unsigned char* q_s = tiles;                                 // kNT x (128 x 128 B)
+  unsigned char* k_s = q_s + kNT * kTileBytes;                // kNT x (128 x 128 B)
+  unsigned char* v_s = k_s + kNT * kTileBytes;                // kNT x (128 x 128 B)
+  TcBars* bars = reinterpret_cast<TcBars*>(v_s + kNT * kTileBytes);
+  float* pol_s = reinterpret_cast<float*>(bars + 1);          // 256
+  float* cls_s = pol_s + 256;                                 // 256
+  float* vsum_s = cls_s + 256;                                // 64
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int mtile = blockIdx.x, bh = blockIdx.y, b = bh / H, h = bh % H;
-  const int m0 = mtile * 128;
-  const size_t tok_stride = (size_t)3 * H * kTcHD;  // elements between consecutive tokens
-  const __nv_bfloat16* q_g = qkv + (size_t)b * T * tok_stride + (size_t)h * kTcHD;
-  const __nv_bfloat16* k_g = q_g + (size_t)H * kTcHD;
-  const __nv_bfloat16* v_g = q_g + (size_t)2 * H * kTcHD;
-
-  // ---- stage Q tile, K, V (rows beyond T are zero-filled) -------------------------------------
-  for (int idx = tid; idx < 128 * 8; idx += kTcThreads) {
-    const int r = idx >> 3, c = idx & 7, row = m0 + r;
-    cp_async16(smem_u32(q_s) + sw128_off(r, c), q_g + (size_t)min(row, T - 1) * tok_stride + c * 8, row < T);
-  }
-  for (int idx = tid; idx < Tkp * 8; idx += kTcThreads) {
-    const int r = idx >> 3, c = idx & 7;
-    const size_t goff = (size_t)min(r, T - 1) * tok_stride + c * 8;
-    cp_async16(smem_u32(k_s) + sw128_off(r, c), k_g + goff, r < T);
-    cp_async16(smem_u32(v_s) + sw128_off(r, c), v_g + goff, r < T);
-  }
-  asm volatile("cp.async.commit_group;" ::: "memory");
-  for (int j = tid; j < 256; j += kTcThreads) tail->pol[j] = (policy && j < T) ? policy[(size_t)b * T + j] : 1.0f;
+  const uint32_t box_bytes = (uint32_t)box_rows * 128u;
 
   if (tid == 0) {
-    mbar_init(smem_u32(&tail->bar_s), 1);
-    mbar_init(smem_u32(&tail->bar_p), 128);
-    mbar_init(smem_u32(&tail->bar_o), 1);
+    mbar_init(smem_u32(&bars->q_full[0]), 1);
+    mbar_init(smem_u32(&bars->q_full[1]), 1);
+    mbar_init(smem_u32(&bars->k_full), 1);
+    mbar_init(smem_u32(&bars->v_full), 1);
+    mbar_init(smem_u32(&bars->s_full), 1);
+    mbar_init(smem_u32(&bars->p_full), 128);
+    mbar_init(smem_u32(&bars->o_full), 1);
+    mbar_init(smem_u32(&bars->tmem_free), 128);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 4) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tail->tmem_base)),
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)),
                  "n"(kTmemCols)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
-  fence_async_smem();  // make the staged tiles visible to the tensor-core (async) proxy
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = tail->tmem_base;
+  const uint32_t tmem = bars->tmem_base;
 
   if (warp == 4) {
     if (lane == 0) {
-      // ---- S = Q K^T ---------------------------------------------------------------------------
+      // =============================== control thread: TMA + MMA issue ===============================
       const uint32_t idesc_s = make_idesc(128, Tkp, 0);
-      const uint64_t qd = make_desc_sw128(smem_u32(q_s), 16, 1024);
-      const uint64_t kd = make_desc_sw128(smem_u32(k_s), 16, 1024);
-#pragma unroll
-      for (int ks = 0; ks < kTcHD / 16; ++ks) mma_ss(tmem, qd + (uint64_t)(ks * 2), kd + (uint64_t)(ks * 2), idesc_s, ks > 0);
-      mma_commit(smem_u32(&tail->bar_s));
-      // ---- O = P V once the softmax warps have written P --------------------------------------------
-      mbar_wait(smem_u32(&tail->bar_p), 0);
-      tc_fence_after();
       const uint32_t idesc_o = make_idesc(128, kTcHD, 1);
+      const uint64_t kd = make_desc_sw128(smem_u32(k_s), 16, 1024);
       const uint64_t vd = make_desc_sw128(smem_u32(v_s), 16, 1024);
       const int ksteps = Tkp / 16;
-      for (int ks = 0; ks < ksteps; ++ks)
-        mma_ts(tmem + kOCol, tmem + (uint32_t)(ks * 8), vd + (uint64_t)(ks * 128), idesc_o, ks > 0);
-      mma_commit(smem_u32(&tail->bar_o));
+      auto issue_qk = [&](int unit) {
+        const int b = unit / H, h = unit % H;
+        mbar_expect_tx(smem_u32(&bars->k_full), box_bytes * kNT);
+#pragma unroll
+        for (int t = 0; t < kNT; ++t)
+          tma_load_3d(smem_u32(k_s) + t * kTileBytes, &qkv_map, (H + h) * kTcHD, t * kTileRows, b, smem_u32(&bars->k_full));
+#pragma unroll
+        for (int t = 0; t < kNT; ++t) {
+          mbar_expect_tx(smem_u32(&bars->q_full[t]), box_bytes);
+          tma_load_3d(smem_u32(q_s) + t * kTileBytes, &qkv_map, h * kTcHD, t * kTileRows, b, smem_u32(&bars->q_full[t]));
+        }
+      };
+      auto issue_v = [&](int unit) {
+        const int b = unit / H, h = unit % H;
+        mbar_expect_tx(smem_u32(&bars->v_full), box_bytes * kNT);
+#pragma unroll
+        for (int t = 0; t < kNT; ++t)
+          tma_load_3d(smem_u32(v_s) + t * kTileBytes, &qkv_map, (2 * H + h) * kTcHD, t * kTileRows, b, smem_u32(&bars->v_full));
+      };
+      int unit = blockIdx.x;
+      if (unit < num_units) { issue_qk(unit); issue_v(unit); }
+      uint32_t g = 0;  // tiles processed by this CTA: parity source for the per-tile barriers
+      for (uint32_t it = 0; unit < num_units; unit += gridDim.x, ++it) {
+        const int next = unit + gridDim.x;
+#pragma unroll
+        for (int t = 0; t < kNT; ++t, ++g) {
+          if (t * kTileRows >= T) { --g; continue; }  // (never for kNT == 1; T <= 128 with kNT == 2 is not launched)
+          if (t == 0) mbar_wait(smem_u32(&bars->k_full), it & 1);
+          mbar_wait(smem_u32(&bars->q_full[t]), it & 1);
+          if (g > 0) mbar_wait(smem_u32(&bars->tmem_free), (g - 1) & 1);
+          tc_fence_after();
+          const uint64_t qd = make_desc_sw128(smem_u32(q_s) + t * kTileBytes, 16, 1024);
+#pragma unroll
+          for (int ks = 0; ks < kTcHD / 16; ++ks) mma_ss(tmem, qd + (uint64_t)(ks * 2), kd + (uint64_t)(ks * 2), idesc_s, ks > 0);
+          mma_commit(smem_u32(&bars->s_full));
+          const bool last = (t + 1) * kTileRows >= T;
+          mbar_wait(smem_u32(&bars->p_full), g & 1);   // softmax done => the S-MMA has completed as well
+          if (last && next < num_units) issue_qk(next);  // Q and K buffers are dead: prefetch during PV / epilogue / next softmax
+          if (t == 0) mbar_wait(smem_u32(&bars->v_full), it & 1);
+          tc_fence_after();
+          for (int ks = 0; ks < ksteps; ++ks)
+            mma_ts(tmem + kOCol, tmem + (uint32_t)(ks * 8), vd + (uint64_t)(ks * 128), idesc_o, ks > 0);
+          mma_commit(smem_u32(&bars->o_full));
+          if (last && next < num_units) {
+            mbar_wait(smem_u32(&bars->o_full), g & 1);  // V is dead once the PV-MMA has completed
+            issue_v(next);
+          }
+        }
+      }
     }
   } else {
-    // ---- softmax: thread == query row ---------------------------------------------------------------
-    const int r = tid;                // row inside the tile == TMEM lane
-    const int i = m0 + r;             // query token
+    // ===================================== softmax / epilogue warps =====================================
+    const int r = tid;  // row inside the tile == TMEM lane
     const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
     const float k2 = scale * 1.4426950408889634f;
-    const float c_eps = policy ? eps / (float)T : 0.0f;
-    const float eps_den = policy ? eps : 0.0f;
-    if (policy && tid < kTcHD) {
-      // column sums of V for the eps/T term: sum_j V[j][d]
-      float acc = 0.f;
-      const int d = tid, cchunk = d >> 3, within = d & 7;
-      for (int j = 0; j < T; ++j) {
-        const __nv_bfloat16* p = reinterpret_cast<const __nv_bfloat16*>(v_s + sw128_off(j, cchunk)) + within;
-        acc += __bfloat162float(*p);
-      }
-      tail->vsum[d] = acc;
-    }
-    asm volatile("bar.sync 1, 128;" ::: "memory");  // vsum visible to all softmax threads
-    mbar_wait(smem_u32(&tail->bar_s), 0);
-    tc_fence_after();
+    const float c_eps = kPol ? eps / (float)T : 0.0f;
+    const float eps_den = kPol ? eps : 0.0f;
     const int nchunks = Tkp / 16;
-    float mx = -INFINITY;
-    for (int ch = 0; ch < nchunks; ++ch) {
-      float v[16];
-      tmem_ld16(lane_addr + (uint32_t)(ch * 16), v);
-#pragma unroll
-      for (int q = 0; q < 16; ++q)
-        if (ch * 16 + q < T) mx = fmaxf(mx, v[q]);
-    }
-    float sum = 0.f;
-    const bool want_cls = (cls_row != nullptr) && (i == 0);
-    for (int ch = 0; ch < nchunks; ++ch) {
-      float v[16];
-      tmem_ld16(lane_addr + (uint32_t)(ch * 16), v);
-      uint32_t packed[8];
-#pragma unroll
-      for (int q = 0; q < 16; ++q) {
-        const int j = ch * 16 + q;
-        float a = 0.f;
-        if (j < T) a = exp2f((v[q] - mx) * k2) * ((j == i) ? 1.0f : tail->pol[j]);
-        sum += a;
-        if (want_cls) tail->cls[j] = a;
-        v[q] = a;
-      }
-#pragma unroll
-      for (int q = 0; q < 8; ++q) packed[q] = pack_bf16x2(v[2 * q], v[2 * q + 1]);
-      tmem_st8(lane_addr + (uint32_t)(ch * 8), packed);  // P overlays the S columns already consumed
-    }
-    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-    tc_fence_before();
-    mbar_arrive(smem_u32(&tail->bar_p));
-    const float den = sum + eps_den;
-    if (want_cls) tail->den0 = den;
-    // ---- epilogue ---------------------------------------------------------------------------------------
-    mbar_wait(smem_u32(&tail->bar_o), 0);
-    tc_fence_after();
-    const float inv = 1.0f / den;
-    __nv_bfloat16* orow = out + ((size_t)b * T + min(i, T - 1)) * (size_t)(H * kTcHD) + (size_t)h * kTcHD;
-#pragma unroll
-    for (int ch = 0; ch < kTcHD / 16; ++ch) {
-      float v[16];
-      tmem_ld16(lane_addr + (uint32_t)(kOCol + ch * 16), v);
-      uint32_t w[8];
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        float o0 = v[2 * q], o1 = v[2 * q + 1];
-        if (policy) {
-          o0 += c_eps * tail->vsum[ch * 16 + 2 * q];
-          o1 += c_eps * tail->vsum[ch * 16 + 2 * q + 1];
+    uint32_t g = 0;
+    for (uint32_t it = 0, unit = blockIdx.x; (int)unit < num_units; unit += gridDim.x, ++it) {
+      const int b = unit / H, h = unit % H;
+      if (kPol) {
+        // per-unit policy row and column sums of V (for the eps/T term): sum_j V[j][d]
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // previous unit's readers of pol_s / vsum_s are done
+        for (int j = tid; j < 256; j += 128) pol_s[j] = (j < T) ? policy[(size_t)b * T + j] : 0.0f;
+        mbar_wait(smem_u32(&bars->v_full), it & 1);
+        if (tid < kTcHD) {
+          float acc = 0.f;
+          const int cchunk = tid >> 3, within = tid & 7;
+          for (int j = 0; j < T; ++j)
+            acc += __bfloat162float(*(reinterpret_cast<const __nv_bfloat16*>(v_s + sw128_off(j, cchunk)) + within));
+          vsum_s[tid] = acc;
         }
-        w[q] = pack_bf16x2(o0 * inv, o1 * inv);
+        asm volatile("bar.sync 1, 128;" ::: "memory");
       }
-      if (i < T) {
-        reinterpret_cast<uint4*>(orow)[ch * 2] = make_uint4(w[0], w[1], w[2], w[3]);
-        reinterpret_cast<uint4*>(orow)[ch * 2 + 1] = make_uint4(w[4], w[5], w[6], w[7]);
+#pragma unroll
+      for (int t = 0; t < kNT; ++t, ++g) {
+        if (t * kTileRows >= T) { --g; continue; }
+        const int i = t * kTileRows + r;                  // query token of this thread
+        const bool warp_active = t * kTileRows + warp * 32 < T;   // whole warp beyond T: nothing to compute
+        mbar_wait(smem_u32(&bars->s_full), g & 1);
+        tc_fence_after();
+        float sum = 0.f;
+        const bool want_cls = (cls_row != nullptr) && (i == 0);
+        if (warp_active) {
+          // pass 1: row max over the T valid columns
+          float mx = -INFINITY;
+          for (int ch = 0; ch < nchunks; ++ch) {
+            uint32_t v[16];
+            tmem_ld16_nowait(lane_addr + (uint32_t)(ch * 16), v);
+            tmem_ld_wait();
+            if (ch * 16 + 16 <= T) {
+#pragma unroll
+              for (int q = 0; q < 16; ++q) mx = fmaxf(mx, __uint_as_float(v[q]));
+            } else {
+#pragma unroll
+              for (int q = 0; q < 16; ++q)
+                if (ch * 16 + q < T) mx = fmaxf(mx, __uint_as_float(v[q]));
+            }
+          }
+          const float mxk = mx * k2;
+          // pass 2: a_ij = exp2(s*k2 - max*k2) [* mask], packed to bf16 over the consumed S columns
+          for (int ch = 0; ch < nchunks; ++ch) {
+            uint32_t v[16];
+            tmem_ld16_nowait(lane_addr + (uint32_t)(ch * 16), v);
+            tmem_ld_wait();
+            float a[16];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+              const int j = ch * 16 + q;
+              float e = ex2_approx(fmaf(__uint_as_float(v[q]), k2, -mxk));
+              if (kPol) e *= (j == i) ? 1.0f : pol_s[j];
+              if (ch * 16 + 16 > T && j >= T) e = 0.f;
+              a[q] = e;
+              sum += e;
+            }
+            if (want_cls) {
+#pragma unroll
+              for (int q = 0; q < 16; ++q) cls_s[ch * 16 + q] = a[q];
+            }
+            uint32_t packed[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) packed[q] = pack_bf16x2(a[2 * q], a[2 * q + 1]);
+            tmem_st8(lane_addr + (uint32_t)(ch * 8), packed);  // P overlays the S columns already consumed
+          }
+        }  // rows of an idle warp are never written out; whatever their P rows hold stays in those rows
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tc_fence_before();
+        mbar_arrive(smem_u32(&bars->p_full));
+        const float den = sum + eps_den;
+        if (cls_row != nullptr && t == 0 && warp == 0) {
+          // CLS row (query 0 = lane 0 of warp 0): probabilities of row 0, Attention.forward's second output
+          __syncwarp();
+          const float den0 = __shfl_sync(0xffffffffu, den, 0);
+          for (int j = lane; j < T; j += 32) cls_row[(size_t)unit * T + j] = (cls_s[j] + c_eps) / den0;
+          __syncwarp();
+        }
+        // ---- epilogue -----------------------------------------------------------------------------------
+        mbar_wait(smem_u32(&bars->o_full), g & 1);
+        tc_fence_after();
+        if (warp_active) {
+          const float inv = 1.0f / den;
+          __nv_bfloat16* orow = out + ((size_t)b * T + min(i, T - 1)) * (size_t)(H * kTcHD) + (size_t)h * kTcHD;
+#pragma unroll
+          for (int ch = 0; ch < kTcHD / 16; ++ch) {
+            uint32_t v[16];
+            tmem_ld16_nowait(lane_addr + (uint32_t)(kOCol + ch * 16), v);
+            tmem_ld_wait();
+            uint32_t w[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              float o0 = __uint_as_float(v[2 * q]), o1 = __uint_as_float(v[2 * q + 1]);
+              if (kPol) {
+                o0 += c_eps * vsum_s[ch * 16 + 2 * q];
+                o1 += c_eps * vsum_s[ch * 16 + 2 * q + 1];
+              }
+              w[q] = pack_bf16x2(o0 * inv, o1 * inv);
+            }
+            if (i < T) {
+              reinterpret_cast<uint4*>(orow)[ch * 2] = make_uint4(w[0], w[1], w[2], w[3]);
+              reinterpret_cast<uint4*>(orow)[ch * 2 + 1] = make_uint4(w[4], w[5], w[6], w[7]);
+            }
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(smem_u32(&bars->tmem_free));
       }
     }
-    tc_fence_before();
   }
+  tc_fence_before();
   __syncthreads();
-  if (cls_row != nullptr && mtile == 0) {
-    const float den0 = tail->den0;
-    const float c_eps = policy ? eps / (float)T : 0.0f;
-    for (int j = tid; j < T; j += kTcThreads) cls_row[(size_t)bh * T + j] = (tail->cls[j] + c_eps) / den0;
-  }
   if (warp == 4) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(kTmemCols) : "memory");
@@ -294,6 +373,42 @@ static bool force_simt() {
   return v == 1;
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                             const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                             CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeFn encode_fn() {
+  static EncodeFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeFn>(p);
+  }
+  return fn;
+}
+
+template <int kNT, bool kPol>
+static int launch_tc(const CUtensorMap& map, const float* policy, int units, int T, int H, int Tkp, int box_rows,
+                     float scale, float eps, void* out, float* cls_row, cudaStream_t stream) {
+  auto kern = attn_tc_fwd_kernel<kNT, kPol>;
+  const size_t smem = 1024 + 3 * (size_t)kNT * kTileBytes + sizeof(TcBars) + (256 + 256 + 64) * sizeof(float);
+  static bool smem_set = false;  // one flag per instantiation; the opt-in is sticky
+  if (!smem_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    D2S_REQUIRE(e == cudaSuccess, D2S_ERR_CUDA, "attn_policy_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    smem_set = true;
+  }
+  const int per_sm = kNT == 1 ? 4 : 2;
+  const int grid = units < per_sm * kNumSMs ? units : per_sm * kNumSMs;
+  kern<<<grid, kTcThreads, smem, stream>>>(map, policy, units, T, H, Tkp, box_rows, scale, eps, (__nv_bfloat16*)out, cls_row);
+  count_launch();
+  return check_launch("d2s_attn_policy_fwd(tcgen05)");
+}
+
 }  // namespace d2s
 
 using namespace d2s;
@@ -303,25 +418,35 @@ extern "C" int d2s_attn_policy_fwd(const void* qkv, const float* policy, int dty
   D2S_REQUIRE(qkv && out, D2S_ERR_ARG, "attn_policy_fwd: null pointer");
   D2S_REQUIRE(dtype == D2S_F32 || dtype == D2S_BF16, D2S_ERR_ARG, "attn_policy_fwd: dtype %d unsupported", dtype);
   D2S_REQUIRE(B >= 0 && T >= 1 && H >= 1 && hd >= 1, D2S_ERR_ARG, "attn_policy_fwd: bad shape B=%d T=%d H=%d hd=%d", B, T, H, hd);
-  D2S_REQUIRE((long long)B * H <= 65535, D2S_ERR_ARG, "attn_policy_fwd: B*H=%lld exceeds 65535", (long long)B * H);
+  D2S_REQUIRE((long long)B * H <= (1LL << 30), D2S_ERR_ARG, "attn_policy_fwd: B*H=%lld too large", (long long)B * H);
   D2S_REQUIRE(aligned16(qkv) && aligned16(out), D2S_ERR_ALIGN, "attn_policy_fwd: qkv/out must be 16-byte aligned");
   cudaStream_t stream = (cudaStream_t)stream_;
-  if (B == 0) return D2S_OK;
-  if (dtype == D2S_F32 || force_simt())
+  if (dtype == D2S_F32 || force_simt()) {
+    D2S_REQUIRE((long long)B * H <= 65535, D2S_ERR_ARG, "attn_policy_fwd(simt): B*H=%lld exceeds 65535", (long long)B * H);
+    if (B == 0) return D2S_OK;
     return attn_simt_dispatch(qkv, policy, dtype, B, T, H, hd, scale, eps, out, cls_row, stream);
+  }
   D2S_REQUIRE(hd == kTcHD, D2S_ERR_ARG, "attn_policy_fwd(bf16): head dim %d unsupported by the tcgen05 kernel (64 only)", hd);
   D2S_REQUIRE(T <= 256, D2S_ERR_ARG, "attn_policy_fwd(bf16): T=%d exceeds 256", T);
+  if (B == 0) return D2S_OK;
   const int Tkp = ceil_div(T, 16) * 16;
-  const size_t smem = 1024 + 128 * 128 + 2 * (size_t)Tkp * 128 + sizeof(TcSmemTail);
-  static size_t smem_set = 0;  // opt-in is sticky per function; skipped once raised (and during graph capture)
-  if (smem > smem_set) {
-    cudaError_t e = cudaFuncSetAttribute(attn_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    D2S_REQUIRE(e == cudaSuccess, D2S_ERR_CUDA, "attn_policy_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    smem_set = 227 * 1024;
+  const int box_rows = Tkp < kTileRows ? Tkp : kTileRows;
+  EncodeFn enc = encode_fn();
+  D2S_REQUIRE(enc != nullptr, D2S_ERR_CUDA, "attn_policy_fwd: cuTensorMapEncodeTiled is unavailable from the driver");
+  CUtensorMap map;
+  const cuuint64_t gdim[3] = {(cuuint64_t)3 * H * kTcHD, (cuuint64_t)T, (cuuint64_t)B};
+  const cuuint64_t gstride[2] = {(cuuint64_t)3 * H * kTcHD * 2, (cuuint64_t)T * 3 * H * kTcHD * 2};
+  const cuuint32_t box[3] = {(cuuint32_t)kTcHD, (cuuint32_t)box_rows, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  CUresult cr = enc(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(qkv), gdim, gstride, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  D2S_REQUIRE(cr == CUDA_SUCCESS, D2S_ERR_CUDA, "attn_policy_fwd: cuTensorMapEncodeTiled failed (%d)", (int)cr);
+  const int units = B * H;
+  if (T <= kTileRows) {
+    return policy ? launch_tc<1, true>(map, policy, units, T, H, Tkp, box_rows, scale, eps, out, cls_row, stream)
+                  : launch_tc<1, false>(map, policy, units, T, H, Tkp, box_rows, scale, eps, out, cls_row, stream);
   }
-  dim3 grid(ceil_div(T, 128), B * H);
-  attn_tc_fwd_kernel<<<grid, kTcThreads, smem, stream>>>((const __nv_bfloat16*)qkv, policy, T, H, Tkp, scale, eps,
-                                                         (__nv_bfloat16*)out, cls_row);
-  count_launch();
-  return check_launch("d2s_attn_policy_fwd(tcgen05)");
+  return policy ? launch_tc<2, true>(map, policy, units, T, H, Tkp, box_rows, scale, eps, out, cls_row, stream)
+                : launch_tc<2, false>(map, policy, units, T, H, Tkp, box_rows, scale, eps, out, cls_row, stream);
 }
