@@ -35,6 +35,7 @@ SIGNATURES = {
     "d2s_softmax_policy_fwd": [_p, _p, _i, _i, _i, _i, _f, _p, _p, _p],
     "d2s_softmax_policy_bwd": [_p, _p, _p, _p, _i, _i, _i, _i, _f, _p, _p, _p],
     "d2s_attn_policy_fwd": [_p, _p, _i, _i, _i, _i, _i, _f, _f, _p, _p, _p],
+    "d2s_add_layernorm": [_p, _p, _p, _p, _i, _i, _i, _i, ctypes.c_longlong, ctypes.c_longlong, _f, _i, _p, _p, _p],
 }
 INFO_SYMBOLS = ["d2s_last_error", "d2s_version", "d2s_launch_count"]
 ALL_SYMBOLS = sorted(list(SIGNATURES) + INFO_SYMBOLS)

@@ -1,0 +1,180 @@
+// Residual add + LayerNorm in one pass over the token matrix (inference path of Block.forward,
+// vit_models/dynamic_vit.py:263-283 / default_dynamic_vit.py:234-237, and of the predictors' leading LayerNorm,
+// dynamic_vit.py:409 / default_dynamic_vit.py:308):
+//
+//     s = x + y            (rounded to the tensor dtype, exactly like the reference's separate add)
+//     h = LayerNorm(s) * gamma + beta     (statistics in fp32, two-pass over registers)
+//
+// HBM-bound byte movement: per token row 2*e*D bytes in (x, y) and 2*e*D out (s, h); the reference's eager path
+// moves 5*e*D (add: 2 in 1 out, LayerNorm: 1 in 1 out) in two launches, and torch's bf16 LayerNorm kernel runs at a
+// fifth of HBM speed at D=384 (profiles/README.md, r01a).  One half-warp owns a row: 16 lanes x 16-byte vectors
+// cover D=384 bf16 in exactly 3 vectors per lane; reductions are 4 xor-shuffles inside the half-warp.
+#include "d2s_common.cuh"
+
+namespace d2s {
+
+constexpr int kLnThreads = 256;
+constexpr int kLnRowsPerCta = kLnThreads / 16;
+
+template <typename T_> struct LnVec;
+template <> struct LnVec<__nv_bfloat16> {
+  static constexpr int kElems = 8;
+  __device__ static void unpack(const int4& r, float (&v)[8]) {
+    const uint32_t w[4] = {(uint32_t)r.x, (uint32_t)r.y, (uint32_t)r.z, (uint32_t)r.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      v[2 * i] = __uint_as_float(w[i] << 16);
+      v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+  }
+  __device__ static int4 pack(const float (&v)[8]) {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const __nv_bfloat162 t = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+      w[i] = *reinterpret_cast<const uint32_t*>(&t);
+    }
+    return make_int4((int)w[0], (int)w[1], (int)w[2], (int)w[3]);
+  }
+  __device__ static float round(float f) { return __bfloat162float(__float2bfloat16_rn(f)); }
+};
+template <> struct LnVec<float> {
+  static constexpr int kElems = 4;
+  __device__ static void unpack(const int4& r, float (&v)[8]) {
+    v[0] = __int_as_float(r.x); v[1] = __int_as_float(r.y); v[2] = __int_as_float(r.z); v[3] = __int_as_float(r.w);
+  }
+  __device__ static int4 pack(const float (&v)[8]) {
+    return make_int4(__float_as_int(v[0]), __float_as_int(v[1]), __float_as_int(v[2]), __float_as_int(v[3]));
+  }
+  __device__ static float round(float f) { return f; }
+};
+
+__device__ __forceinline__ float half_warp_sum(float v) {
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// kVPL: 16-byte vectors per lane (D <= 16 * kVPL * elems-per-vector)
+template <typename T_, int kVPL>
+__global__ void __launch_bounds__(kLnThreads)
+add_layernorm_kernel(const T_* __restrict__ x, const T_* __restrict__ y, const T_* __restrict__ gamma,
+                     const T_* __restrict__ beta, long long rows, int T, int D, long long x_stride_b, long long x_stride_t,
+                     float eps, int norm_row0, T_* __restrict__ out_sum, T_* __restrict__ out_norm) {
+  constexpr int VE = LnVec<T_>::kElems;
+  const int sub = threadIdx.x & 15;
+  const long long row = (long long)blockIdx.x * kLnRowsPerCta + (threadIdx.x >> 4);
+  const bool row_ok = row < rows;
+  const int nvec = D / VE;
+  const long long b = row_ok ? row / T : 0;
+  const int t = row_ok ? (int)(row - b * T) : 0;
+  const T_* xr = x + b * x_stride_b + (long long)t * x_stride_t;
+  const T_* yr = y ? y + row * D : nullptr;
+
+  float v[kVPL][8];
+  float sum = 0.f;
+#pragma unroll
+  for (int k = 0; k < kVPL; ++k) {
+    const int vi = sub + 16 * k;
+    if (row_ok && vi < nvec) {
+      const int4 rx = *reinterpret_cast<const int4*>(xr + (size_t)vi * VE);
+      LnVec<T_>::unpack(rx, v[k]);
+      if (yr) {
+        float w[8];
+        const int4 ry = ld_stream16(yr + (size_t)vi * VE);  // the branch output is dead after this read
+        LnVec<T_>::unpack(ry, w);
+#pragma unroll
+        for (int q = 0; q < VE; ++q) v[k][q] = LnVec<T_>::round(v[k][q] + w[q]);
+      }
+#pragma unroll
+      for (int q = 0; q < VE; ++q) sum += v[k][q];
+    } else {
+#pragma unroll
+      for (int q = 0; q < VE; ++q) v[k][q] = 0.f;
+    }
+  }
+  if (out_sum && row_ok) {
+#pragma unroll
+    for (int k = 0; k < kVPL; ++k) {
+      const int vi = sub + 16 * k;
+      if (vi < nvec) *reinterpret_cast<int4*>(out_sum + row * D + (size_t)vi * VE) = LnVec<T_>::pack(v[k]);
+    }
+  }
+  const float mean = half_warp_sum(sum) / (float)D;
+  float var = 0.f;
+#pragma unroll
+  for (int k = 0; k < kVPL; ++k) {
+    const int vi = sub + 16 * k;
+    if (vi < nvec) {
+#pragma unroll
+      for (int q = 0; q < VE; ++q) {
+        const float d = v[k][q] - mean;
+        var = fmaf(d, d, var);
+      }
+    }
+  }
+  const float rstd = rsqrtf(half_warp_sum(var) / (float)D + eps);
+  if (!row_ok || t < norm_row0) return;
+  T_* hr = out_norm + (b * (T - norm_row0) + (t - norm_row0)) * (long long)D;
+#pragma unroll
+  for (int k = 0; k < kVPL; ++k) {
+    const int vi = sub + 16 * k;
+    if (vi < nvec) {
+      float g[8], bt[8], o[8];
+      LnVec<T_>::unpack(*reinterpret_cast<const int4*>(gamma + (size_t)vi * VE), g);
+      LnVec<T_>::unpack(*reinterpret_cast<const int4*>(beta + (size_t)vi * VE), bt);
+#pragma unroll
+      for (int q = 0; q < VE; ++q) o[q] = fmaf((v[k][q] - mean) * rstd, g[q], bt[q]);
+      *reinterpret_cast<int4*>(hr + (size_t)vi * VE) = LnVec<T_>::pack(o);
+    }
+  }
+}
+
+template <typename T_>
+static int launch_ln(const void* x, const void* y, const void* gamma, const void* beta, int B, int T, int D,
+                     long long sb, long long st, float eps, int norm_row0, void* out_sum, void* out_norm, cudaStream_t stream) {
+  constexpr int VE = LnVec<T_>::kElems;
+  const long long rows = (long long)B * T;
+  const int nvec = D / VE;
+  const int vpl = ceil_div(nvec, 16);
+  const unsigned grid = (unsigned)((rows + kLnRowsPerCta - 1) / kLnRowsPerCta);
+#define D2S_LN_LAUNCH(V)                                                                                              \
+  add_layernorm_kernel<T_, V><<<grid, kLnThreads, 0, stream>>>((const T_*)x, (const T_*)y, (const T_*)gamma,           \
+                                                               (const T_*)beta, rows, T, D, sb, st, eps, norm_row0,    \
+                                                               (T_*)out_sum, (T_*)out_norm)
+  if (vpl <= 2) D2S_LN_LAUNCH(2);
+  else if (vpl <= 3) D2S_LN_LAUNCH(3);
+  else if (vpl <= 6) D2S_LN_LAUNCH(6);
+  else D2S_LN_LAUNCH(12);
+#undef D2S_LN_LAUNCH
+  count_launch();
+  return check_launch("d2s_add_layernorm");
+}
+
+}  // namespace d2s
+
+using namespace d2s;
+
+extern "C" int d2s_add_layernorm(const void* x, const void* y, const void* gamma, const void* beta, int dtype, int B, int T,
+                                 int D, long long x_stride_b, long long x_stride_t, float eps, int norm_row0,
+                                 void* out_sum, void* out_norm, d2s_stream_t stream) {
+  D2S_REQUIRE(x && gamma && beta && out_norm, D2S_ERR_ARG, "add_layernorm: null pointer");
+  D2S_REQUIRE(dtype == D2S_F32 || dtype == D2S_BF16, D2S_ERR_ARG, "add_layernorm: dtype %d unsupported", dtype);
+  D2S_REQUIRE(B >= 0 && T >= 1 && D >= 1, D2S_ERR_ARG, "add_layernorm: bad shape B=%d T=%d D=%d", B, T, D);
+  const int ve = dtype == D2S_BF16 ? 8 : 4;
+  D2S_REQUIRE(D % ve == 0 && D / ve <= 16 * 12, D2S_ERR_ARG, "add_layernorm: D=%d must be a multiple of %d and at most %d", D,
+              ve, 16 * 12 * ve);
+  D2S_REQUIRE(norm_row0 >= 0 && norm_row0 < T, D2S_ERR_ARG, "add_layernorm: norm_row0=%d outside [0,T=%d)", norm_row0, T);
+  D2S_REQUIRE(x_stride_t >= D && x_stride_b >= 0 && x_stride_t % ve == 0 && x_stride_b % ve == 0, D2S_ERR_ARG,
+              "add_layernorm: strides (%lld, %lld) must be multiples of %d elements with rows >= D apart", x_stride_b,
+              x_stride_t, ve);
+  D2S_REQUIRE(aligned16(x) && aligned16(gamma) && aligned16(beta) && aligned16(out_norm) && (!y || aligned16(y)) &&
+                  (!out_sum || aligned16(out_sum)),
+              D2S_ERR_ALIGN, "add_layernorm: pointers must be 16-byte aligned");
+  if (B == 0) return D2S_OK;
+  return dtype == D2S_BF16
+             ? launch_ln<__nv_bfloat16>(x, y, gamma, beta, B, T, D, x_stride_b, x_stride_t, eps, norm_row0, out_sum, out_norm,
+                                        (cudaStream_t)stream)
+             : launch_ln<float>(x, y, gamma, beta, B, T, D, x_stride_b, x_stride_t, eps, norm_row0, out_sum, out_norm,
+                                (cudaStream_t)stream);
+}

@@ -55,8 +55,38 @@ def attention_forward(m, x, policy=None, return_cls_attn=False):
     return (o, cls_attn) if return_cls_attn else o
 
 
+def _is_plain_ln(n):
+    return isinstance(n, torch.nn.LayerNorm) and n.elementwise_affine and n.bias is not None
+
+
+def _fusable(m, x, *extra):
+    """The carried-residual inference path applies when no gradient is needed and the norms are plain LayerNorms."""
+    return (not _needs_grad(x, *extra, m.norm1.weight if hasattr(m.norm1, "weight") else None)
+            and x.is_cuda and _is_plain_ln(m.norm1) and _is_plain_ln(m.norm2)
+            and isinstance(m.drop_path, torch.nn.Identity))
+
+
+def block_forward_carry(m, x, y, policy=None, return_cls_attn=False):
+    """Inference form of Block.forward (dynamic_vit.py:263-283) with the residual adds folded into the LayerNorms:
+    takes the residual stream x and a pending branch output y (None at the first block), returns
+    (x', y', cls_attn) where x' + y' is the block's output.  Two d2s add+LayerNorm launches replace two adds and
+    two LayerNorms."""
+    x, h = ops.add_layernorm(x, y, m.norm1.weight, m.norm1.bias, m.norm1.eps)
+    cls_attn = None
+    if return_cls_attn:
+        a, cls_attn = attention_forward(m.attn, h, policy=policy, return_cls_attn=True)
+    else:
+        a = attention_forward(m.attn, h, policy=policy)
+    x, h = ops.add_layernorm(x, a, m.norm2.weight, m.norm2.bias, m.norm2.eps)
+    return x, m.mlp(h), cls_attn
+
+
 def block_forward(m, x, policy=None, return_cls_attn=False):
     """Block.forward (dynamic_vit.py:263-283)."""
+    if _fusable(m, x, policy):
+        x, y, cls_attn = block_forward_carry(m, x, None, policy, return_cls_attn)
+        x = x + y
+        return (x, cls_attn) if return_cls_attn else x
     if return_cls_attn:
         y, cls_attn = attention_forward(m.attn, m.norm1(x), policy=policy, return_cls_attn=True)
         x = x + m.drop_path(y)
@@ -66,9 +96,51 @@ def block_forward(m, x, policy=None, return_cls_attn=False):
     return x + m.drop_path(m.mlp(m.norm2(x)))
 
 
+class _Stream:
+    """Residual stream of the model-level inference loops: x plus a pending branch output y (x + y is the value the
+    reference holds in `x`).  Falls back to plain Block.forward when the fused path does not apply."""
+
+    def __init__(self, x):
+        self.x, self.y = x, None
+
+    def value(self):
+        if self.y is not None:
+            self.x, self.y = self.x + self.y, None
+        return self.x
+
+    def block(self, blk, policy=None, return_cls_attn=False):
+        if _fusable(blk, self.x, policy):
+            self.x, self.y, cls_attn = block_forward_carry(blk, self.x, self.y, policy, return_cls_attn)
+            return cls_attn
+        out = block_forward(blk, self.value(), policy, return_cls_attn)
+        if return_cls_attn:
+            self.x, cls_attn = out
+            return cls_attn
+        self.x = out
+        return None
+
+    def normed(self, norm, row0=0, rows=None):
+        """(x + y, norm((x + y)[:, row0:])) with the add folded in; leaves the stream holding the summed x."""
+        if _is_plain_ln(norm) and self.x.is_cuda and not _needs_grad(self.x, self.y, norm.weight):
+            self.x, h = ops.add_layernorm(self.x, self.y, norm.weight, norm.bias, norm.eps, norm_row0=row0)
+            self.y = None
+            return self.x, h
+        x = self.value()
+        return x, norm(x[:, row0:])
+
+    def cls_normed(self, norm):
+        """norm(x + y)[:, 0]: only the CLS row (what the eval heads consume)."""
+        if _is_plain_ln(norm) and self.x.is_cuda and not _needs_grad(self.x, self.y, norm.weight):
+            y0 = None if self.y is None else self.y[:, :1].contiguous()
+            _, h = ops.add_layernorm(self.x[:, :1], y0, norm.weight, norm.bias, norm.eps, want_sum=False)
+            return h[:, 0]
+        return norm(self.value())[:, 0]
+
+
 # ---- Variant A predictor (default_dynamic_vit.py:304-330) ------------------------------------------
-def predictor_a_hidden(m, x, policy):
-    h = m.in_conv(x)
+def predictor_a_hidden(m, x, policy, normed=None):
+    """`normed`: in_conv's LayerNorm already applied (by the fused add+LayerNorm kernel)."""
+    h = m.in_conv(x) if normed is None else m.in_conv[2](m.in_conv[1](normed))
     B, N, C = h.shape
     half = C // 2
     pooled = (h[:, :, half:] * policy).sum(dim=1, keepdim=True) / torch.sum(policy, dim=1, keepdim=True)
@@ -94,8 +166,8 @@ def _predictor_b_tail_parts(m):
     return layers[:-3], layers[-3], layers[-2]
 
 
-def predictor_b_hidden(m, x):
-    h = m.in_conv(x)
+def predictor_b_hidden(m, x, normed=None):
+    h = m.in_conv(x) if normed is None else m.in_conv[2](m.in_conv[1](normed))
     B, N, C = h.shape
     half = C // 2
     pooled = torch.mean(h[:, :, half:], dim=1, keepdim=True)
@@ -106,12 +178,12 @@ def predictor_b_hidden(m, x):
     return h, norm, lin
 
 
-def predictor_b_forward(m, x, policy=None, current_sigma=0.0005, cls_attn=None, k_select=None):
+def predictor_b_forward(m, x, policy=None, current_sigma=0.0005, cls_attn=None, k_select=None, normed=None):
     """Returns (scores, keep_probs) like the reference; with k_select also (kept, dropped) from the fused
     tail kernel.  Like the reference, only the topk_selection=True configuration is defined (:537)."""
     if not m.topk_selection:
         return None
-    h, norm, lin = predictor_b_hidden(m, x)
+    h, norm, lin = predictor_b_hidden(m, x, normed)
     prob_mode = ops.PROB_SOFTMAX if m.loss_type in ["kl_div", "mse"] else ops.PROB_SIGMOID
     if _needs_grad(h, lin.weight):
         scores = lin(norm(h)).flatten(-2, -1)
@@ -126,7 +198,8 @@ def predictor_b_forward(m, x, policy=None, current_sigma=0.0005, cls_attn=None, 
         h, ln_w, ln_b, ln_eps = norm(h), None, None, 0.0
     scores, probs, kept, dropped = ops.score_tail_b(h, ln_w, ln_b, lin.weight, lin.bias, k_select or 0, ln_eps,
                                                     prob_mode, select=k_select is not None)
-    scores, probs = scores.to(x.dtype), probs.to(x.dtype)
+    out_dtype = x.dtype if x is not None else normed.dtype
+    scores, probs = scores.to(out_dtype), probs.to(out_dtype)
     if k_select is None:
         return scores, probs
     return scores, probs, kept, dropped
@@ -151,52 +224,66 @@ def draw_gumbel(like):
     return -torch.empty_like(like, memory_format=torch.legacy_contiguous_format).exponential_().log()
 
 
+def _pred_ln(pred):
+    ln = pred.in_conv[0]
+    return ln if _is_plain_ln(ln) else None
+
+
 def variant_a_forward(model, img):
     """DefaultVisionTransformerDiffPruning.forward (default_dynamic_vit.py:435-487).
     Injected Gumbel noise for parity runs: set model._d2s_gumbels = [tensor (B,196,2) per stage]."""
-    x = _embed(model, img)
-    B = x.shape[0]
+    st = _Stream(_embed(model, img))
+    B = st.x.shape[0]
+    dt, dev = st.x.dtype, st.x.device
     p_count = 0
     out_pred_prob = []
-    prev_decision = torch.ones(B, INIT_N, 1, dtype=x.dtype, device=x.device)
-    policy = torch.ones(B, INIT_N + 1, 1, dtype=x.dtype, device=x.device)
+    prev_decision = torch.ones(B, INIT_N, 1, dtype=dt, device=dev)
+    policy = torch.ones(B, INIT_N + 1, 1, dtype=dt, device=dev)
     injected = getattr(model, "_d2s_gumbels", None)
     model.kept_token_indices = []
     for i, blk in enumerate(model.blocks):
         if i in model.pruning_loc:
             pred = model.score_predictor[p_count]
             if model.training:
+                x = st.value()
                 pred_score = predictor_a_forward(pred, x[:, 1:], prev_decision).reshape(B, -1, 2)
                 g = injected[p_count] if injected is not None else draw_gumbel(pred_score)
                 hard = ops.gumbel_keep_decision(pred_score, g, prev_decision)
                 out_pred_prob.append(hard.reshape(B, INIT_N))
                 policy = torch.cat([torch.ones(B, 1, 1, dtype=hard.dtype, device=hard.device), hard], dim=1)
-                x = block_forward(blk, x, policy=policy)
+                st.block(blk, policy=policy)
                 prev_decision = hard
             else:
                 k = int(INIT_N * model.token_ratio[p_count])
-                h = predictor_a_hidden(pred, x[:, 1:], prev_decision)
+                ln = _pred_ln(pred)
+                if ln is not None:      # residual add folded into the predictor's LayerNorm over x[:, 1:]
+                    x, hn = st.normed(ln, row0=1)
+                    h = predictor_a_hidden(pred, None, prev_decision, normed=hn)
+                else:
+                    x = st.value()
+                    h = predictor_a_hidden(pred, x[:, 1:], prev_decision)
                 lin = pred.out_conv[4]
                 _, keep_policy = ops.score_tail_a(h, lin.weight, lin.bias, k=k)
                 model.kept_token_indices.append(keep_policy)
-                x = ops.gather_tokens(x, keep_policy, prepend_cls=True)
+                st.x = ops.gather_tokens(x, keep_policy, prepend_cls=True)
                 prev_decision = ops.batch_index_select(prev_decision, keep_policy)
-                x = block_forward(blk, x)
+                st.block(blk)
             p_count += 1
         else:
-            x = block_forward(blk, x, policy) if model.training else block_forward(blk, x)
-    x, features = _head(model, x)
+            st.block(blk, policy if model.training else None)
     if model.training:
+        x, features = _head(model, st.value())
         if model.distill:
             return x, features, prev_decision.detach(), out_pred_prob
         return x, out_pred_prob
-    return x
+    return model.head(model.pre_logits(st.cls_normed(model.norm)))
 
 
 def variant_b_forward(model, img, stacked_cls_attn_weights=None):
     """VisionTransformerDiffPruning.forward (dynamic_vit.py:814-1015)."""
-    x = _embed(model, img)
-    B, T0, D = x.shape
+    st = _Stream(_embed(model, img))
+    B, T0, D = st.x.shape
+    dt, dev = st.x.dtype, st.x.device
     N = T0 - 1
     p_count = 0
     model.num_kept_tokens = []
@@ -204,7 +291,7 @@ def variant_b_forward(model, img, stacked_cls_attn_weights=None):
     model.pred_logits = []
     model.kept_token_indices = []
     model.dropped_token_indices = []
-    keep_mask = torch.ones((B, N + 1), dtype=x.dtype, device=x.device)
+    keep_mask = torch.ones((B, N + 1), dtype=dt, device=dev)
     pred_logits = None
     thr = model.patch_score_threshold
     for i, blk in enumerate(model.blocks):
@@ -212,15 +299,22 @@ def variant_b_forward(model, img, stacked_cls_attn_weights=None):
             num_keep_node = int(INIT_N * model.token_ratio[p_count])
             pred = model.score_predictor[p_count]
             if thr is None:
-                pred_logits, pred_score, kept, dropped = predictor_b_forward(pred, x[:, 1:], k_select=num_keep_node)
+                ln = _pred_ln(pred)
+                if ln is not None and pred.topk_selection and not _needs_grad(st.x, st.y, ln.weight):
+                    x, hn = st.normed(ln, row0=1)
+                    pred_logits, pred_score, kept, dropped = predictor_b_forward(pred, None, k_select=num_keep_node, normed=hn)
+                else:
+                    x = st.value()
+                    pred_logits, pred_score, kept, dropped = predictor_b_forward(pred, x[:, 1:], k_select=num_keep_node)
                 model.kept_token_indices.append(kept)
                 model.dropped_token_indices.append(dropped)
                 model.pred_logits.append(pred_logits)
-                x = ops.gather_tokens(x, kept, prepend_cls=True)
-                x, cls_attn = block_forward(blk, x, return_cls_attn=True)
+                st.x = ops.gather_tokens(x, kept, prepend_cls=True)
+                cls_attn = st.block(blk, return_cls_attn=True)
                 model.cls_attns.append(cls_attn[:, :, 1:])
             elif model.training:
                 # dynamic keep ratio: cumulative-score threshold -> 0/1 policy (dynamic_vit.py:880-894)
+                x = st.value()
                 pred_logits, pred_score = predictor_b_forward(pred, x[:, 1:])
                 val, idx = torch.sort(pred_score.detach().clone())
                 th = torch.cumsum(val, dim=-1) > thr
@@ -228,11 +322,11 @@ def variant_b_forward(model, img, stacked_cls_attn_weights=None):
                 model.min_keep_ratio = torch.min(model.keep_ratios).item()
                 model.avg_keep_ratio = torch.mean(model.keep_ratios).item()
                 model.max_keep_ratio = torch.max(model.keep_ratios).item()
-                spatial_mask = torch.zeros((B, N), device=x.device, dtype=torch.bool).scatter(1, idx, th)
+                spatial_mask = torch.zeros((B, N), device=dev, dtype=torch.bool).scatter(1, idx, th)
                 model.kept_token_indices.append(spatial_mask.unsqueeze(-1).repeat(1, 1, D).flatten())
                 model.dropped_token_indices.append(~spatial_mask.unsqueeze(-1).repeat(1, 1, D).flatten())
-                keep_mask = torch.cat((torch.ones(B, 1, dtype=x.dtype, device=x.device), spatial_mask), dim=1).float()
-                x = block_forward(blk, x, policy=keep_mask.unsqueeze(-1))
+                keep_mask = torch.cat((torch.ones(B, 1, dtype=dt, device=dev), spatial_mask), dim=1).float()
+                st.block(blk, policy=keep_mask.unsqueeze(-1))
             else:
                 # the reference's inference branch of this mode reads an undefined name (dynamic_vit.py:936)
                 raise NotImplementedError("patch_score_threshold inference is undefined in the reference "
@@ -240,43 +334,39 @@ def variant_b_forward(model, img, stacked_cls_attn_weights=None):
             p_count += 1
         else:
             if model.training and thr is not None:
-                x = block_forward(blk, x, policy=keep_mask.unsqueeze(-1))
+                st.block(blk, policy=keep_mask.unsqueeze(-1))
             else:
-                x, cls_attn = block_forward(blk, x, return_cls_attn=True)
+                cls_attn = st.block(blk, return_cls_attn=True)
                 model.cls_attns.append(cls_attn[:, :, 1:])
-    x, features = _head(model, x)
     if model.training:
+        x, features = _head(model, st.value())
         if thr is not None:
             return x, features, pred_logits, keep_mask[:, 1:]
         return x, features, model.pred_logits, model.kept_token_indices
-    return x, model.cls_attns, model.pred_logits, model.kept_token_indices
+    logits = model.head(model.pre_logits(st.cls_normed(model.norm)))
+    return logits, model.cls_attns, model.pred_logits, model.kept_token_indices
 
 
 def variant_b_forward_cls_attn(model, img):
     """VisionTransformerDiffPruning.forward_cls_attn (dynamic_vit.py:1018-1033)."""
-    x = _embed(model, img)
+    st = _Stream(_embed(model, img))
     final = None
     last = len(model.blocks) - 1
     for i, blk in enumerate(model.blocks):
-        if i == last:
-            _, final = block_forward(blk, x, return_cls_attn=True)
-        else:
-            x = block_forward(blk, x)
+        final = st.block(blk, return_cls_attn=(i == last))
     return final
 
 
 def teacher_forward(model, img, with_cls_attn=True):
     """VisionTransformerTeacher.forward (dynamic_vit.py:1150-1176) / DefaultVisionTransformerTeacher.forward
     (default_dynamic_vit.py:581-598, with_cls_attn=False)."""
-    x = _embed(model, img)
+    st = _Stream(_embed(model, img))
     rows = []
     for blk in model.blocks:
+        ca = st.block(blk, return_cls_attn=with_cls_attn)
         if with_cls_attn:
-            x, ca = block_forward(blk, x, return_cls_attn=True)
             rows.append(ca.detach())
-        else:
-            x = block_forward(blk, x)
-    feature = model.norm(x)
+    _, feature = st.normed(model.norm)
     cls = model.head(model.pre_logits(feature[:, 0]))
     tokens = feature[:, 1:]
     if with_cls_attn:
@@ -286,9 +376,8 @@ def teacher_forward(model, img, with_cls_attn=True):
 
 def teacher_forward_cls_attention(model, img):
     """VisionTransformerTeacher.forward_cls_attention (dynamic_vit.py:1134-1148)."""
-    x = _embed(model, img)
+    st = _Stream(_embed(model, img))
     rows = []
     for blk in model.blocks:
-        x, ca = block_forward(blk, x, return_cls_attn=True)
-        rows.append(ca.detach())
+        rows.append(st.block(blk, return_cls_attn=True).detach())
     return torch.stack(rows, dim=1)

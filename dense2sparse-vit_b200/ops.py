@@ -282,3 +282,28 @@ def attention_core(qkv, num_heads, policy=None, scale=None, eps=1e-6, want_cls_r
     _lib.call("d2s_attn_policy_fwd", _ptr(q), _ptr(pol), _dtype_code(q), B, T, num_heads, hd, float(scale), float(eps),
               _ptr(out), _ptr(cls_row), _stream())
     return out, cls_row
+
+
+# ----------------------------------------------------------------------------------------------
+# residual add + LayerNorm (inference path of Block.forward and of the predictors' leading LayerNorm)
+# ----------------------------------------------------------------------------------------------
+
+def add_layernorm(x, y, weight, bias, eps, norm_row0=0, want_sum=True):
+    """s = x + y (y may be None); returns (s or None, LayerNorm(s[:, norm_row0:]) * weight + bias).
+    x (B,T,D) may be a strided view with contiguous rows (e.g. a token slice); y contiguous.  No autograd:
+    training keeps torch's add + LayerNorm (vit_models/dynamic_vit.py:263-283)."""
+    _check_cuda(x, y, weight, bias)
+    if x.stride(-1) != 1:
+        x = x.contiguous()
+    B, T, D = x.shape
+    yc = None if y is None else y.detach().contiguous()
+    w = weight.detach().to(x.dtype).contiguous()
+    b = bias.detach().to(x.dtype).contiguous()
+    need_sum = want_sum and (y is not None)
+    out_sum = torch.empty(B, T, D, dtype=x.dtype, device=x.device) if need_sum else None
+    out_norm = torch.empty(B, T - norm_row0, D, dtype=x.dtype, device=x.device)
+    _lib.call("d2s_add_layernorm", _ptr(x), _ptr(yc), _ptr(w), _ptr(b), _dtype_code(x), B, T, D, x.stride(0), x.stride(1),
+              float(eps), int(norm_row0), _ptr(out_sum), _ptr(out_norm), _stream())
+    if want_sum and y is None:
+        out_sum = x
+    return out_sum, out_norm

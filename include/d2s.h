@@ -132,6 +132,17 @@ int d2s_softmax_policy_bwd(const void* attn, const float* policy, const void* go
 int d2s_attn_policy_fwd(const void* qkv, const float* policy, int dtype, int B, int T, int H, int hd,
                         float scale, float eps, void* out, float* cls_row, d2s_stream_t stream);
 
+/* ---- residual add + LayerNorm ("next" row of the scope table: Block.forward) -----------------------------
+ * Inference path of x = x + branch; h = norm(x) (dynamic_vit.py:263-283; default_dynamic_vit.py:234-237) and of the
+ * predictors' leading LayerNorm over x[:, 1:] (dynamic_vit.py:409, :491; default_dynamic_vit.py:308) in one pass:
+ *   s = x + y (rounded to dtype; y NULL => s = x), out_sum (B,T,D) = s (NULL to skip),
+ *   out_norm (B,T-norm_row0,D) = LayerNorm(s[:, norm_row0:]) * gamma + beta, statistics in fp32.
+ * x is (B,T,D) with element strides (x_stride_b, x_stride_t) and contiguous rows; y, outputs contiguous;
+ * gamma, beta (D) in the same dtype as x.  D % 8 == 0 (bf16) / D % 4 == 0 (f32), D <= 1536 (bf16) / 768 (f32). */
+int d2s_add_layernorm(const void* x, const void* y, const void* gamma, const void* beta, int dtype, int B, int T, int D,
+                      long long x_stride_b, long long x_stride_t, float eps, int norm_row0,
+                      void* out_sum, void* out_norm, d2s_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

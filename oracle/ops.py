@@ -310,3 +310,16 @@ def perturbed_topk_bwd(gout, egrad):
 
 def gelu_exact(x):
     return 0.5 * x * (1.0 + torch.erf(x / math.sqrt(2.0)))
+
+
+# ----------------------------------------------------------------------------------------------
+# residual add + LayerNorm
+# ----------------------------------------------------------------------------------------------
+
+def add_layernorm(x, y, weight, bias, eps, norm_row0=0):
+    """What the reference computes with two ops in Block.forward (vit_models/dynamic_vit.py:263-283):
+    s = x + y in the tensor dtype, then LayerNorm(s[:, norm_row0:]) (torch computes the statistics in fp32
+    and rounds the result to the tensor dtype).  Returns (s, h)."""
+    s = x if y is None else x + y
+    h = F.layer_norm(s[:, norm_row0:].float(), (s.shape[-1],), weight.float(), bias.float(), eps).to(s.dtype)
+    return s, h

@@ -326,6 +326,44 @@ def test_attention_golden_module(d2s, ops):
     torch.testing.assert_close(o2.detach().cpu(), OPS["attn_out_pol"], **FP32)
 
 
+# ------------------------------------------------------------------------------------------ add + LayerNorm
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("B,T,D", [(3, 197, 384), (2, 138, 768), (5, 68, 128), (2, 197, 192), (1, 1, 384), (33, 7, 1536)])
+@pytest.mark.parametrize("with_y,row0", [(True, 0), (False, 0), (True, 1), (False, 1)])
+def test_add_layernorm(ops, dtype, B, T, D, with_y, row0):
+    if dtype == torch.float32 and D > 768:
+        pytest.skip("fp32 rows are limited to D <= 768")
+    if row0 >= T:
+        pytest.skip("nothing to normalise")
+    x = (fx.randn(130 + D, B, T, D) * 2 + 0.5).to(dtype)
+    y = fx.randn(131 + T, B, T, D).to(dtype) if with_y else None
+    w, b = (1 + 0.1 * fx.randn(132, D)).to(dtype), (0.1 * fx.randn(133, D)).to(dtype)
+    s, h = ops.add_layernorm(cu(x), None if y is None else cu(y), cu(w), cu(b), 1e-6, norm_row0=row0)
+    rs, rh = oo.add_layernorm(x, y, w, b, 1e-6, norm_row0=row0)
+    assert torch.equal(s.cpu(), rs)                                    # the residual sum is bit-exact
+    tol = dict(rtol=1e-5, atol=1e-5) if dtype == torch.float32 else dict(rtol=1.6e-2, atol=1e-2)   # bf16: 1 ulp
+    torch.testing.assert_close(h.cpu().float(), rh.float(), **tol)
+
+
+def test_add_layernorm_strided_view_and_full_size(ops):
+    B, T, D = 1024, 197, 384
+    x = torch.randn(B, T, D, device="cuda", dtype=torch.bfloat16)
+    y = torch.randn(B, T, D, device="cuda", dtype=torch.bfloat16)
+    ln = torch.nn.LayerNorm(D, eps=1e-6).cuda().bfloat16()
+    torch.nn.init.normal_(ln.weight, 1.0, 0.1)
+    torch.nn.init.normal_(ln.bias, 0.0, 0.1)
+    s, h = ops.add_layernorm(x, y, ln.weight, ln.bias, ln.eps)
+    assert torch.equal(s, x + y)
+    torch.testing.assert_close(h.float(), ln(x + y).float(), rtol=1.6e-2, atol=1e-2)
+    # token-slice view (the predictors normalise x[:, 1:]) and the CLS-only view used by the eval heads
+    _, h1 = ops.add_layernorm(x, y, ln.weight, ln.bias, ln.eps, norm_row0=1)
+    assert torch.equal(h1, h[:, 1:])
+    _, h0 = ops.add_layernorm(x[:, :1], y[:, :1].contiguous(), ln.weight, ln.bias, ln.eps, want_sum=False)
+    assert torch.equal(h0, h[:, :1])
+    _, hs = ops.add_layernorm(x[:, 1:], None, ln.weight, ln.bias, ln.eps)
+    torch.testing.assert_close(hs.float(), ln(x[:, 1:]).float(), rtol=1.6e-2, atol=1e-2)
+
+
 # ------------------------------------------------------------------------------------------ error behaviour
 def test_errors_are_loud(ops):
     with pytest.raises(RuntimeError):
