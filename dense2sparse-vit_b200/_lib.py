@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(PKG_DIR, "libd2s_b200.so")
 F32, BF16 = 0, 1
 ORDER_INDEX_ASC, ORDER_SCORE_DESC = 0, 1
 PROB_SOFTMAX, PROB_SIGMOID = 0, 1
+ACT_NONE, ACT_GELU, ACT_RELU = 0, 1, 2
 
 _p = ctypes.c_void_p
 _i = ctypes.c_int
@@ -23,7 +24,7 @@ _u64 = ctypes.c_uint64
 # name -> argtypes; every entry point returns int (0 == ok).  Keep in sync with include/d2s.h.
 SIGNATURES = {
     "d2s_select_topk_f32": [_p, _i, _i, _i, _i, _p, _p, _p],
-    "d2s_score_tail_a": [_p, _i, _i, _i, _i, _p, _p, _i, _p, _p, _p, _p, _p, _p, _p],
+    "d2s_score_tail_a": [_p, _i, _i, _i, _i, _p, _p, _i, _p, _p, _p, _p, _p, _p, _i, _p, _p],
     "d2s_score_tail_b": [_p, _i, _i, _i, _i, _p, _p, _f, _p, _p, _i, _i, _p, _p, _p, _p, _p],
     "d2s_gumbel_decision_f32": [_p, _p, _p, _i64, _p, _p, _p],
     "d2s_gumbel_decision_bwd_f32": [_p, _p, _p, _p, _i64, _p, _p, _p],
@@ -35,6 +36,9 @@ SIGNATURES = {
     "d2s_softmax_policy_fwd": [_p, _p, _i, _i, _i, _i, _f, _p, _p, _p],
     "d2s_softmax_policy_bwd": [_p, _p, _p, _p, _i, _i, _i, _i, _f, _p, _p, _p],
     "d2s_attn_policy_fwd": [_p, _p, _i, _i, _i, _i, _i, _f, _f, _p, _p, _p],
+    "d2s_pool_act": [_p, _p, _i, _i, _i, _i, _i, _p, _p, _p],
+    "d2s_bias_act": [_p, _p, _i, ctypes.c_longlong, _i, _i, _i, _p],
+    "d2s_assemble_tokens": [_p, _p, _p, _i, _i, _i, _i, _p, _p],
     "d2s_add_layernorm": [_p, _p, _p, _p, _i, _i, _i, _i, ctypes.c_longlong, ctypes.c_longlong, _f, _i, _p, _p, _p],
 }
 INFO_SYMBOLS = ["d2s_last_error", "d2s_version", "d2s_launch_count"]

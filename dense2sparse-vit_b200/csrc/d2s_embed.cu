@@ -1,0 +1,67 @@
+// Token assembly after the patch-embedding GEMM (vit_models/dynamic_vit.py:816-824, default_dynamic_vit.py:437-442):
+// x = cat(cls_token.expand(B), patches) + pos_embed in ONE pass -- the reference runs a concat (read+write of the whole
+// token matrix) and then a broadcast add (another read+write).  HBM-bound: e*D*N read + e*D*(N+1) written per image.
+#include "d2s_common.cuh"
+
+namespace d2s {
+
+template <typename T_, int VE>
+__global__ void __launch_bounds__(256)
+assemble_tokens_kernel(const T_* __restrict__ patches, const T_* __restrict__ cls, const T_* __restrict__ pos, long long B,
+                       int N, int D, T_* __restrict__ out) {
+  const int nvec = D / VE;
+  const int T = N + 1;
+  const long long total = B * T * nvec;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % nvec);
+    const long long row = i / nvec;
+    const int t = (int)(row % T);
+    const long long b = row / T;
+    const T_* src = t == 0 ? cls + (size_t)v * VE : patches + ((size_t)(b * N + (t - 1)) * D + (size_t)v * VE);
+    const int4 a = t == 0 ? *reinterpret_cast<const int4*>(src) : ld_stream16(src);
+    const int4 p = *reinterpret_cast<const int4*>(pos + (size_t)t * D + (size_t)v * VE);
+    int4 r;
+    if (VE == 8) {
+      const __nv_bfloat162* a2 = reinterpret_cast<const __nv_bfloat162*>(&a);
+      const __nv_bfloat162* p2 = reinterpret_cast<const __nv_bfloat162*>(&p);
+      __nv_bfloat162* r2 = reinterpret_cast<__nv_bfloat162*>(&r);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float2 fa = __bfloat1622float2(a2[q]), fp = __bfloat1622float2(p2[q]);
+        r2[q] = __floats2bfloat162_rn(fa.x + fp.x, fa.y + fp.y);
+      }
+    } else {
+      r.x = __float_as_int(__int_as_float(a.x) + __int_as_float(p.x));
+      r.y = __float_as_int(__int_as_float(a.y) + __int_as_float(p.y));
+      r.z = __float_as_int(__int_as_float(a.z) + __int_as_float(p.z));
+      r.w = __float_as_int(__int_as_float(a.w) + __int_as_float(p.w));
+    }
+    *reinterpret_cast<int4*>(out + (size_t)row * D + (size_t)v * VE) = r;
+  }
+}
+
+}  // namespace d2s
+
+using namespace d2s;
+
+extern "C" int d2s_assemble_tokens(const void* patches, const void* cls, const void* pos, int dtype, int B, int N, int D,
+                                   void* out, d2s_stream_t stream) {
+  D2S_REQUIRE(patches && cls && pos && out, D2S_ERR_ARG, "assemble_tokens: null pointer");
+  D2S_REQUIRE(dtype == D2S_F32 || dtype == D2S_BF16, D2S_ERR_ARG, "assemble_tokens: dtype %d unsupported", dtype);
+  const int ve = dtype == D2S_BF16 ? 8 : 4;
+  D2S_REQUIRE(B >= 0 && N >= 1 && D >= ve && D % ve == 0, D2S_ERR_ARG, "assemble_tokens: bad shape B=%d N=%d D=%d", B, N, D);
+  D2S_REQUIRE(aligned16(patches) && aligned16(cls) && aligned16(pos) && aligned16(out), D2S_ERR_ALIGN,
+              "assemble_tokens: pointers must be 16-byte aligned");
+  if (B == 0) return D2S_OK;
+  const long long total = (long long)B * (N + 1) * (D / ve);
+  long long blocks = (total + 255) / 256;
+  if (blocks > 16LL * kNumSMs) blocks = 16LL * kNumSMs;
+  if (dtype == D2S_BF16)
+    assemble_tokens_kernel<__nv_bfloat16, 8><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)patches, (const __nv_bfloat16*)cls, (const __nv_bfloat16*)pos, B, N, D, (__nv_bfloat16*)out);
+  else
+    assemble_tokens_kernel<float, 4><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+        (const float*)patches, (const float*)cls, (const float*)pos, B, N, D, (float*)out);
+  count_launch();
+  return check_launch("d2s_assemble_tokens");
+}

@@ -1,0 +1,168 @@
+// Predictor body helpers (inference path of PredictorLG.forward, vit_models/default_dynamic_vit.py:324-330 and
+// dynamic_vit.py:538-546): the reference runs GELU, a policy multiply, two reductions, a division, an expand and a
+// concat as separate passes over the (B,N,C) activations.  Here:
+//
+//   pool_act_kernel : one pass over z = in_conv's Linear output.  local = act(z[:, :, :C/2]) is written densely as the
+//                     A operand of the next Linear; pooled[b] = sum_n act(z[b,n,C/2:]) * policy[b,n] / sum_n policy[b,n]
+//                     (policy NULL => plain mean, dynamic_vit.py:542) never leaves the chip as a (B,N,C/2) tensor.
+//   bias_act_kernel : u = act(u + bias[b]) in place with a PER-IMAGE bias row.  With the next Linear split as
+//                     W = [W_local | W_global], Linear(cat(local, pooled)) = local @ W_local^T + (pooled @ W_global^T + b),
+//                     so the concat (default_dynamic_vit.py:329) is never materialised.
+//
+// Both are HBM-bound: pool_act reads e*N*C and writes e*N*C/2 per image, bias_act reads and writes e*N*C' once.
+#include "d2s_common.cuh"
+
+namespace d2s {
+
+template <typename T_> struct PVec;
+template <> struct PVec<__nv_bfloat16> {
+  static constexpr int kElems = 8;
+  __device__ static void unpack(const int4& r, float (&v)[8]) {
+    const uint32_t w[4] = {(uint32_t)r.x, (uint32_t)r.y, (uint32_t)r.z, (uint32_t)r.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      v[2 * i] = __uint_as_float(w[i] << 16);
+      v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+  }
+  __device__ static int4 pack(const float (&v)[8]) {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const __nv_bfloat162 t = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+      w[i] = *reinterpret_cast<const uint32_t*>(&t);
+    }
+    return make_int4((int)w[0], (int)w[1], (int)w[2], (int)w[3]);
+  }
+  __device__ static float round(float f) { return __bfloat162float(__float2bfloat16_rn(f)); }
+};
+template <> struct PVec<float> {
+  static constexpr int kElems = 4;
+  __device__ static void unpack(const int4& r, float (&v)[8]) {
+    v[0] = __int_as_float(r.x); v[1] = __int_as_float(r.y); v[2] = __int_as_float(r.z); v[3] = __int_as_float(r.w);
+  }
+  __device__ static int4 pack(const float (&v)[8]) {
+    return make_int4(__float_as_int(v[0]), __float_as_int(v[1]), __float_as_int(v[2]), __float_as_int(v[3]));
+  }
+  __device__ static float round(float f) { return f; }
+};
+
+__device__ __forceinline__ float act_apply(float x, int act) {
+  if (act == D2S_ACT_GELU) return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));  // nn.GELU() (erf form)
+  if (act == D2S_ACT_RELU) return fmaxf(x, 0.0f);
+  return x;
+}
+
+constexpr int kPoolThreads = 256;
+
+// grid = B; thread = (16-byte vector column v, token group g); groups stride the tokens
+template <typename T_>
+__global__ void __launch_bounds__(kPoolThreads)
+pool_act_kernel(const T_* __restrict__ z, const float* __restrict__ policy, int N, int C, int act,
+                T_* __restrict__ local, T_* __restrict__ pooled) {
+  constexpr int VE = PVec<T_>::kElems;
+  extern __shared__ float red[];  // groups x (C/2) partial sums, then groups partial policy sums
+  const int b = blockIdx.x;
+  const int nvec = C / VE, half_vec = nvec / 2, half = C / 2;
+  const int groups = kPoolThreads / nvec;  // host guarantees nvec <= kPoolThreads
+  const int v = threadIdx.x % nvec, g = threadIdx.x / nvec;
+  float acc[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) acc[q] = 0.f;
+  float psum = 0.f;
+  if (g < groups) {
+    for (int n = g; n < N; n += groups) {
+      const size_t row = (size_t)b * N + n;
+      float x[8];
+      PVec<T_>::unpack(ld_stream16(z + row * C + (size_t)v * VE), x);
+#pragma unroll
+      for (int q = 0; q < VE; ++q) x[q] = PVec<T_>::round(act_apply(x[q], act));
+      if (v < half_vec) {
+        *reinterpret_cast<int4*>(local + row * half + (size_t)v * VE) = PVec<T_>::pack(x);
+      } else {
+        const float p = policy ? policy[row] : 1.0f;
+#pragma unroll
+        for (int q = 0; q < VE; ++q) acc[q] = fmaf(x[q], p, acc[q]);
+        if (v == half_vec) psum += p;
+      }
+    }
+  }
+  float* pol_red = red + (size_t)groups * half;
+  if (g < groups && v >= half_vec) {
+#pragma unroll
+    for (int q = 0; q < VE; ++q) red[(size_t)g * half + (size_t)(v - half_vec) * VE + q] = acc[q];
+    if (v == half_vec) pol_red[g] = psum;
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < half; c += kPoolThreads) {
+    float s = 0.f, ps = 0.f;
+    for (int gg = 0; gg < groups; ++gg) { s += red[(size_t)gg * half + c]; ps += pol_red[gg]; }
+    st_from_float(pooled, (size_t)b * half + c, s / ps);
+  }
+}
+
+// u (rows, C) += bias (per image: bias[(row / N) * C + c]; N == 0 => one shared row), then act, in place
+template <typename T_>
+__global__ void __launch_bounds__(256)
+bias_act_kernel(T_* __restrict__ u, const T_* __restrict__ bias, long long rows, int N, int C, int act) {
+  constexpr int VE = PVec<T_>::kElems;
+  const int nvec = C / VE;
+  const long long total = rows * nvec;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i / nvec;
+    const int v = (int)(i - row * nvec);
+    const long long brow = N > 0 ? row / N : 0;
+    float x[8], bb[8];
+    PVec<T_>::unpack(*reinterpret_cast<const int4*>(u + row * C + (size_t)v * VE), x);
+    PVec<T_>::unpack(*reinterpret_cast<const int4*>(bias + brow * C + (size_t)v * VE), bb);
+#pragma unroll
+    for (int q = 0; q < VE; ++q) x[q] = act_apply(PVec<T_>::round(x[q] + bb[q]), act);
+    *reinterpret_cast<int4*>(u + row * C + (size_t)v * VE) = PVec<T_>::pack(x);
+  }
+}
+
+}  // namespace d2s
+
+using namespace d2s;
+
+extern "C" int d2s_pool_act(const void* z, const float* policy, int dtype, int B, int N, int C, int act, void* local,
+                            void* pooled, d2s_stream_t stream) {
+  D2S_REQUIRE(z && local && pooled, D2S_ERR_ARG, "pool_act: null pointer");
+  D2S_REQUIRE(dtype == D2S_F32 || dtype == D2S_BF16, D2S_ERR_ARG, "pool_act: dtype %d unsupported", dtype);
+  const int ve = dtype == D2S_BF16 ? 8 : 4;
+  D2S_REQUIRE(B >= 0 && N >= 1 && C >= 2 * ve && C % (2 * ve) == 0 && C / ve <= kPoolThreads, D2S_ERR_ARG,
+              "pool_act: bad shape B=%d N=%d C=%d (C must be a multiple of %d, at most %d)", B, N, C, 2 * ve, kPoolThreads * ve);
+  D2S_REQUIRE(act >= D2S_ACT_NONE && act <= D2S_ACT_RELU, D2S_ERR_ARG, "pool_act: bad activation %d", act);
+  D2S_REQUIRE(aligned16(z) && aligned16(local), D2S_ERR_ALIGN, "pool_act: z/local must be 16-byte aligned");
+  if (B == 0) return D2S_OK;
+  const int groups = kPoolThreads / (C / ve);
+  const size_t smem = ((size_t)groups * (C / 2) + groups) * sizeof(float);
+  if (dtype == D2S_BF16)
+    pool_act_kernel<__nv_bfloat16><<<B, kPoolThreads, smem, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)z, policy, N, C, act, (__nv_bfloat16*)local, (__nv_bfloat16*)pooled);
+  else
+    pool_act_kernel<float><<<B, kPoolThreads, smem, (cudaStream_t)stream>>>((const float*)z, policy, N, C, act,
+                                                                           (float*)local, (float*)pooled);
+  count_launch();
+  return check_launch("d2s_pool_act");
+}
+
+extern "C" int d2s_bias_act(void* u, const void* bias, int dtype, long long rows, int N, int C, int act, d2s_stream_t stream) {
+  D2S_REQUIRE(u && bias, D2S_ERR_ARG, "bias_act: null pointer");
+  D2S_REQUIRE(dtype == D2S_F32 || dtype == D2S_BF16, D2S_ERR_ARG, "bias_act: dtype %d unsupported", dtype);
+  const int ve = dtype == D2S_BF16 ? 8 : 4;
+  D2S_REQUIRE(rows >= 0 && N >= 0 && C >= ve && C % ve == 0, D2S_ERR_ARG, "bias_act: bad shape rows=%lld N=%d C=%d", rows, N, C);
+  D2S_REQUIRE(act >= D2S_ACT_NONE && act <= D2S_ACT_RELU, D2S_ERR_ARG, "bias_act: bad activation %d", act);
+  D2S_REQUIRE(aligned16(u) && aligned16(bias), D2S_ERR_ALIGN, "bias_act: u/bias must be 16-byte aligned");
+  if (rows == 0) return D2S_OK;
+  const long long total = rows * (C / ve);
+  long long blocks = (total + 255) / 256;
+  if (blocks > 16LL * kNumSMs) blocks = 16LL * kNumSMs;
+  if (dtype == D2S_BF16)
+    bias_act_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)u, (const __nv_bfloat16*)bias,
+                                                                                     rows, N, C, act);
+  else
+    bias_act_kernel<float><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((float*)u, (const float*)bias, rows, N, C, act);
+  count_launch();
+  return check_launch("d2s_bias_act");
+}

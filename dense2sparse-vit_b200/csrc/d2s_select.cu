@@ -27,7 +27,8 @@ struct SelSmem {
 
 // All threads of the CTA call this after s.key[0..N) is filled and __syncthreads() has been issued.
 __device__ void block_select_write(SelSmem& s, int N, int K, int order, int64_t* __restrict__ kept_b,
-                                   int64_t* __restrict__ dropped_b) {
+                                   int64_t* __restrict__ dropped_b, const float* __restrict__ prev_b = nullptr,
+                                   float* __restrict__ prev_kept_b = nullptr) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   uint32_t mykey[kSelEPT];
   int rank[kSelEPT];
@@ -53,8 +54,10 @@ __device__ void block_select_write(SelSmem& s, int N, int K, int order, int64_t*
     for (int e = 0; e < kSelEPT; ++e) {
       const int i = e * kSelThreads + tid;
       if (i < N) {
-        if (rank[e] < K) { if (kept_b) kept_b[rank[e]] = i; }
-        else if (dropped_b) dropped_b[rank[e] - K] = i;
+        if (rank[e] < K) {
+          if (kept_b) kept_b[rank[e]] = i;
+          if (prev_kept_b) prev_kept_b[rank[e]] = prev_b ? prev_b[i] : 1.0f;  // batch_index_select(prev_decision, keep)
+        } else if (dropped_b) dropped_b[rank[e] - K] = i;
       }
     }
     return;
@@ -80,8 +83,10 @@ __device__ void block_select_write(SelSmem& s, int N, int K, int order, int64_t*
     }
     before += __popc(ball[e] & ((1u << lane) - 1u));
     const bool keep = rank[e] < K;
-    if (keep) { if (kept_b) kept_b[before] = i; }
-    else if (dropped_b) dropped_b[i - before] = i;
+    if (keep) {
+      if (kept_b) kept_b[before] = i;
+      if (prev_kept_b) prev_kept_b[before] = prev_b ? prev_b[i] : 1.0f;
+    } else if (dropped_b) dropped_b[i - before] = i;
   }
 }
 
@@ -119,6 +124,9 @@ template <> struct Vec16<__nv_bfloat16> {
     }
   }
 };
+
+__device__ __forceinline__ float round_to(float f, const float*) { return f; }
+__device__ __forceinline__ float round_to(float f, const __nv_bfloat16*) { return __bfloat162float(__float2bfloat16_rn(f)); }
 
 __device__ __forceinline__ float block_reduce_max(float v, SelSmem& s) {
   v = warp_max(v);
@@ -166,7 +174,7 @@ __global__ void __launch_bounds__(kSelThreads)
 score_tail_a_kernel(const T_* __restrict__ hidden, int N, int C, const float* __restrict__ W,
                     const float* __restrict__ bias, int K, const float* __restrict__ gumbel,
                     const float* __restrict__ prev, float* __restrict__ logp, int64_t* __restrict__ kept,
-                    float* __restrict__ decision, float* __restrict__ ysoft) {
+                    float* __restrict__ decision, float* __restrict__ ysoft, int act_input, float* __restrict__ prev_kept) {
   __shared__ SelSmem s;
   extern __shared__ float w_s[];  // 2*C weights
   const int b = blockIdx.x;
@@ -180,6 +188,10 @@ score_tail_a_kernel(const T_* __restrict__ hidden, int N, int C, const float* __
     for (int c = 0; c < C; c += VE) {
       float v[8];
       Vec16<T_>::load(row + c, v);
+      if (act_input) {  // the GELU in front of the last Linear (default_dynamic_vit.py:318), applied on load
+#pragma unroll
+        for (int q = 0; q < VE; ++q) v[q] = round_to(0.5f * v[q] * (1.0f + erff(v[q] * 0.70710678118654752440f)), row);
+      }
 #pragma unroll
       for (int q = 0; q < VE; ++q) {
         a0 = fmaf(v[q], w_s[c + q], a0);
@@ -203,7 +215,8 @@ score_tail_a_kernel(const T_* __restrict__ hidden, int N, int C, const float* __
   }
   if (kept == nullptr) return;
   __syncthreads();
-  block_select_write(s, N, K, D2S_ORDER_SCORE_DESC, kept + (size_t)b * K, nullptr);
+  block_select_write(s, N, K, D2S_ORDER_SCORE_DESC, kept + (size_t)b * K, nullptr, prev ? prev + (size_t)b * N : nullptr,
+                     prev_kept ? prev_kept + (size_t)b * K : nullptr);
 }
 
 template <typename T_>
@@ -357,19 +370,22 @@ static int check_tail(const void* hidden, int dtype, int B, int N, int C, int K)
 
 extern "C" int d2s_score_tail_a(const void* hidden, int dtype, int B, int N, int C, const float* W,
                                 const float* bias, int K, const float* gumbel, const float* prev, float* logp,
-                                int64_t* kept, float* decision, float* ysoft, d2s_stream_t stream) {
+                                int64_t* kept, float* decision, float* ysoft, int act_input, float* prev_kept,
+                                d2s_stream_t stream) {
   int rc = check_tail(hidden, dtype, B, N, C, K);
   if (rc) return rc;
   D2S_REQUIRE(W && bias && logp, D2S_ERR_ARG, "score_tail_a: null W/bias/logp");
   D2S_REQUIRE(!gumbel || (decision && ysoft), D2S_ERR_ARG, "score_tail_a: gumbel given without decision/ysoft outputs");
+  D2S_REQUIRE(!prev_kept || kept, D2S_ERR_ARG, "score_tail_a: prev_kept needs kept");
+  D2S_REQUIRE(act_input == D2S_ACT_NONE || act_input == D2S_ACT_GELU, D2S_ERR_ARG, "score_tail_a: bad act_input %d", act_input);
   if (B == 0) return D2S_OK;
   const size_t smem = 2 * (size_t)C * sizeof(float);
   if (dtype == D2S_F32)
     score_tail_a_kernel<float><<<B, kSelThreads, smem, (cudaStream_t)stream>>>(
-        (const float*)hidden, N, C, W, bias, K, gumbel, prev, logp, kept, decision, ysoft);
+        (const float*)hidden, N, C, W, bias, K, gumbel, prev, logp, kept, decision, ysoft, act_input, prev_kept);
   else
     score_tail_a_kernel<__nv_bfloat16><<<B, kSelThreads, smem, (cudaStream_t)stream>>>(
-        (const __nv_bfloat16*)hidden, N, C, W, bias, K, gumbel, prev, logp, kept, decision, ysoft);
+        (const __nv_bfloat16*)hidden, N, C, W, bias, K, gumbel, prev, logp, kept, decision, ysoft, act_input, prev_kept);
   count_launch();
   return check_launch("d2s_score_tail_a");
 }

@@ -159,6 +159,33 @@ def predictor_a_forward(m, x, policy):
     return logp.to(x.dtype)
 
 
+def _predictor_a_fusable(m):
+    ic, oc = list(m.in_conv), list(m.out_conv)
+    G, L = torch.nn.GELU, torch.nn.Linear
+    return (len(ic) == 3 and len(oc) == 6 and _is_plain_ln(ic[0]) and isinstance(ic[1], L) and isinstance(ic[2], G)
+            and isinstance(oc[0], L) and isinstance(oc[1], G) and isinstance(oc[2], L) and isinstance(oc[3], G)
+            and isinstance(oc[4], L) and getattr(ic[2], "approximate", "none") == "none"
+            and oc[0].in_features == ic[1].out_features and ic[1].out_features % 16 == 0)
+
+
+def predictor_a_select(m, normed, prev, k):
+    """Inference form of PredictorLG.forward + selection (default_dynamic_vit.py:324-330, :461-467) without the
+    GELU / multiply / reduce / expand / concat passes: `normed` = in_conv's LayerNorm output (from the fused
+    add+LayerNorm), `prev` (B,N) fp32 keep decisions of the previous stage or None (all ones).
+    Returns (log-probs (B,N,2) fp32, kept (B,k) int64 in descending-score order, prev gathered at kept (B,k) fp32)."""
+    z = m.in_conv[1](normed)                                     # Linear(D,D) + bias (cuBLAS)
+    local, pooled = ops.pool_act(z, prev, ops.ACT_GELU)          # GELU + policy-weighted mean pool, one pass
+    l0 = m.out_conv[0]
+    half = l0.in_features // 2
+    # Linear(cat(local, pooled)) = local @ W[:, :half]^T + (pooled @ W[:, half:]^T + b)
+    per_image = F.linear(pooled, l0.weight[:, half:], l0.bias)   # (B, D/2)
+    u = F.linear(local, l0.weight[:, :half])
+    ops.bias_act_(u, per_image, ops.ACT_GELU)
+    z2 = m.out_conv[2](u)                                        # Linear(D/2, D/4) + bias; its GELU is applied by the tail
+    lin = m.out_conv[4]
+    return ops.score_tail_a(z2, lin.weight, lin.bias, k=k, prev=prev, act_input=ops.ACT_GELU, want_prev_kept=True)
+
+
 # ---- Variant B predictor (dynamic_vit.py:370-560) --------------------------------------------------
 def _predictor_b_tail_parts(m):
     layers = list(m.out_conv)
@@ -209,6 +236,9 @@ def predictor_b_forward(m, x, policy=None, current_sigma=0.0005, cls_attn=None, 
 def _embed(model, img):
     x = patch_embed_forward(model.patch_embed, img)
     B = x.shape[0]
+    if (x.is_cuda and not _needs_grad(x, model.cls_token, model.pos_embed) and isinstance(model.pos_drop, torch.nn.Dropout)
+            and (model.pos_drop.p == 0 or not model.training) and model.pos_embed.shape[1] == x.shape[1] + 1):
+        return ops.assemble_tokens(x, model.cls_token, model.pos_embed)
     x = torch.cat((model.cls_token.to(x.dtype).expand(B, -1, -1), x), dim=1)
     return model.pos_drop(x + model.pos_embed.to(x.dtype))
 
@@ -241,6 +271,7 @@ def variant_a_forward(model, img):
     policy = torch.ones(B, INIT_N + 1, 1, dtype=dt, device=dev)
     injected = getattr(model, "_d2s_gumbels", None)
     model.kept_token_indices = []
+    prev_f32 = None                                  # eval fast path: (B,N) fp32 decisions, None = all ones
     for i, blk in enumerate(model.blocks):
         if i in model.pruning_loc:
             pred = model.score_predictor[p_count]
@@ -256,17 +287,22 @@ def variant_a_forward(model, img):
             else:
                 k = int(INIT_N * model.token_ratio[p_count])
                 ln = _pred_ln(pred)
-                if ln is not None:      # residual add folded into the predictor's LayerNorm over x[:, 1:]
+                if ln is not None and _predictor_a_fusable(pred) and not _needs_grad(st.x, st.y, ln.weight):
+                    # residual add folded into the predictor's LayerNorm over x[:, 1:]; fused predictor body
                     x, hn = st.normed(ln, row0=1)
-                    h = predictor_a_hidden(pred, None, prev_decision, normed=hn)
+                    _, keep_policy, prev_f32 = predictor_a_select(pred, hn, prev_f32, k)
+                    prev_decision = None                 # materialised on demand below
                 else:
                     x = st.value()
+                    if prev_decision is None:
+                        prev_decision = prev_f32.unsqueeze(-1).to(dt)
                     h = predictor_a_hidden(pred, x[:, 1:], prev_decision)
-                lin = pred.out_conv[4]
-                _, keep_policy = ops.score_tail_a(h, lin.weight, lin.bias, k=k)
+                    lin = pred.out_conv[4]
+                    _, keep_policy = ops.score_tail_a(h, lin.weight, lin.bias, k=k)
+                    prev_decision = ops.batch_index_select(prev_decision, keep_policy)
+                    prev_f32 = prev_decision.reshape(B, -1).float()
                 model.kept_token_indices.append(keep_policy)
                 st.x = ops.gather_tokens(x, keep_policy, prepend_cls=True)
-                prev_decision = ops.batch_index_select(prev_decision, keep_policy)
                 st.block(blk)
             p_count += 1
         else:

@@ -7,7 +7,8 @@ fallback (the CPU restatement lives in oracle/ and is test infrastructure only).
 import torch
 
 from . import _lib
-from ._lib import BF16, F32, ORDER_INDEX_ASC, ORDER_SCORE_DESC, PROB_SIGMOID, PROB_SOFTMAX  # noqa: F401
+from ._lib import (ACT_GELU, ACT_NONE, ACT_RELU, BF16, F32, ORDER_INDEX_ASC, ORDER_SCORE_DESC, PROB_SIGMOID,  # noqa: F401
+                   PROB_SOFTMAX)
 
 
 def _dtype_code(t: torch.Tensor) -> int:
@@ -54,26 +55,28 @@ def select_topk(score: torch.Tensor, k: int, order: int = ORDER_INDEX_ASC, want_
     return kept, dropped
 
 
-def score_tail_a(hidden, weight, bias, k=0, gumbel=None, prev=None):
+def score_tail_a(hidden, weight, bias, k=0, gumbel=None, prev=None, act_input=ACT_NONE, want_prev_kept=False):
     """Variant A predictor tail (Linear(C,2)+LogSoftmax) fused with selection or the Gumbel decision.
-    eval  (gumbel None): returns (logp (B,N,2), kept (B,k) int64 in descending-score order)
-    train (gumbel (B,N,2)): returns (logp, decision (B,N), ysoft (B,N))"""
+    eval  (gumbel None): returns (logp (B,N,2), kept (B,k) int64 in descending-score order[, prev_kept (B,k) f32])
+    train (gumbel (B,N,2)): returns (logp, decision (B,N), ysoft (B,N))
+    act_input=ACT_GELU: `hidden` is the previous Linear's raw output, the GELU is applied on load."""
     _check_cuda(hidden, weight, bias)
     h = hidden.detach().contiguous()
     B, N, C = h.shape
     w, b = _f32c(weight), _f32c(bias)
     logp = torch.empty(B, N, 2, dtype=torch.float32, device=h.device)
+    p = _f32c(prev.reshape(B, N)) if prev is not None else None
     if gumbel is None:
         kept = torch.empty(B, k, dtype=torch.int64, device=h.device)
-        _lib.call("d2s_score_tail_a", _ptr(h), _dtype_code(h), B, N, C, _ptr(w), _ptr(b), k, None, None,
-                  _ptr(logp), _ptr(kept), None, None, _stream())
-        return logp, kept
+        prev_kept = torch.empty(B, k, dtype=torch.float32, device=h.device) if want_prev_kept else None
+        _lib.call("d2s_score_tail_a", _ptr(h), _dtype_code(h), B, N, C, _ptr(w), _ptr(b), k, None, _ptr(p),
+                  _ptr(logp), _ptr(kept), None, None, int(act_input), _ptr(prev_kept), _stream())
+        return (logp, kept, prev_kept) if want_prev_kept else (logp, kept)
     g = _f32c(gumbel)
-    p = _f32c(prev.reshape(B, N)) if prev is not None else None
     decision = torch.empty(B, N, dtype=torch.float32, device=h.device)
     ysoft = torch.empty(B, N, dtype=torch.float32, device=h.device)
     _lib.call("d2s_score_tail_a", _ptr(h), _dtype_code(h), B, N, C, _ptr(w), _ptr(b), 0, _ptr(g), _ptr(p),
-              _ptr(logp), None, _ptr(decision), _ptr(ysoft), _stream())
+              _ptr(logp), None, _ptr(decision), _ptr(ysoft), int(act_input), None, _stream())
     return logp, decision, ysoft
 
 
@@ -307,3 +310,44 @@ def add_layernorm(x, y, weight, bias, eps, norm_row0=0, want_sum=True):
     if want_sum and y is None:
         out_sum = x
     return out_sum, out_norm
+
+
+# ----------------------------------------------------------------------------------------------
+# predictor body (inference)
+# ----------------------------------------------------------------------------------------------
+
+def pool_act(z, policy=None, act=ACT_GELU):
+    """z (B,N,C) -> (local (B,N,C/2) = act(z[..., :C/2]), pooled (B,C/2) = policy-weighted mean over tokens of
+    act(z[..., C/2:])) in one pass (vit_models/default_dynamic_vit.py:325-328; dynamic_vit.py:538-542)."""
+    _check_cuda(z, policy)
+    zc = z.detach().contiguous()
+    B, N, C = zc.shape
+    pol = _f32c(policy.reshape(B, N)) if policy is not None else None
+    local = torch.empty(B, N, C // 2, dtype=zc.dtype, device=zc.device)
+    pooled = torch.empty(B, C // 2, dtype=zc.dtype, device=zc.device)
+    _lib.call("d2s_pool_act", _ptr(zc), _ptr(pol), _dtype_code(zc), B, N, C, int(act), _ptr(local), _ptr(pooled), _stream())
+    return local, pooled
+
+
+def bias_act_(u, bias, act=ACT_GELU):
+    """In place: u (B,N,C) = act(u + bias[:, None, :]) with a per-image bias (B,C), or a shared bias (C,)."""
+    _check_cuda(u, bias)
+    if not u.is_contiguous():
+        raise ValueError("bias_act_ works in place on a contiguous tensor")
+    B, N, C = u.shape
+    bc = bias.detach().to(u.dtype).contiguous()
+    per_image = bc.dim() == 2
+    _lib.call("d2s_bias_act", _ptr(u), _ptr(bc), _dtype_code(u), B * N, N if per_image else 0, C, int(act), _stream())
+    return u
+
+
+def assemble_tokens(patches, cls_token, pos_embed):
+    """cat(cls_token.expand(B,-1,-1), patches) + pos_embed in one pass (vit_models/dynamic_vit.py:820-823)."""
+    _check_cuda(patches, cls_token, pos_embed)
+    pc = patches.detach().contiguous()
+    B, N, D = pc.shape
+    cls = cls_token.detach().to(pc.dtype).reshape(D).contiguous()
+    pos = pos_embed.detach().to(pc.dtype).reshape(N + 1, D).contiguous()
+    out = torch.empty(B, N + 1, D, dtype=pc.dtype, device=pc.device)
+    _lib.call("d2s_assemble_tokens", _ptr(pc), _ptr(cls), _ptr(pos), _dtype_code(pc), B, N, D, _ptr(out), _stream())
+    return out

@@ -30,6 +30,7 @@ typedef void* d2s_stream_t; /* cudaStream_t */
 enum { D2S_F32 = 0, D2S_BF16 = 1 };
 enum { D2S_ORDER_INDEX_ASC = 0, D2S_ORDER_SCORE_DESC = 1 };
 enum { D2S_PROB_SOFTMAX = 0, D2S_PROB_SIGMOID = 1 };
+enum { D2S_ACT_NONE = 0, D2S_ACT_GELU = 1, D2S_ACT_RELU = 2 };
 
 enum {
   D2S_OK = 0,
@@ -58,12 +59,16 @@ int d2s_select_topk_f32(const float* score, int B, int N, int K, int order,
  *   train: Gumbel keep decision with injected noise (default_dynamic_vit.py:454; torch
  *          F.gumbel_softmax(hard=True)) times prev_decision                    -> decision, ysoft
  * hidden (B,N,C) f32|bf16 post-GELU activations; W (2,C) f32; bias (2) f32; logp (B,N,2) f32 out.
- * eval:  gumbel=NULL, kept (B,K) i64 (NULL: log-probs only).   train: gumbel (B,N,2) f32, prev (B,N) f32, decision (B,N) f32,
- * ysoft (B,N) f32 (soft keep probability, saved for backward).  C <= 1024, C % 8 == 0. */
+ * eval:  gumbel=NULL, kept (B,K) i64 (NULL: log-probs only); prev_kept (B,K) f32 or NULL receives
+ *        batch_index_select(prev_decision, kept) (default_dynamic_vit.py:467; prev NULL => ones).
+ * train: gumbel (B,N,2) f32, prev (B,N) f32, decision (B,N) f32, ysoft (B,N) f32 (soft keep probability).
+ * act_input = D2S_ACT_GELU applies the GELU that precedes the last Linear (:318) on load, so `hidden` may be the
+ * previous Linear's raw output.  C <= 1024, C % 8 == 0. */
 int d2s_score_tail_a(const void* hidden, int dtype, int B, int N, int C,
                      const float* W, const float* bias,
                      int K, const float* gumbel, const float* prev,
-                     float* logp, int64_t* kept, float* decision, float* ysoft, d2s_stream_t stream);
+                     float* logp, int64_t* kept, float* decision, float* ysoft,
+                     int act_input, float* prev_kept, d2s_stream_t stream);
 
 /* Variant B tail: [LayerNorm(C)] + Linear(C,1) + flatten + softmax over N | sigmoid
  * (dynamic_vit.py:424-426, :547-554), then top-K with kept/dropped sorted ascending (:858-862).
@@ -131,6 +136,20 @@ int d2s_softmax_policy_bwd(const void* attn, const float* policy, const void* go
  * dtype F32 : fp32 SIMT kernel used for 1e-4 parity runs (hd in {32,64}, T <= 256). */
 int d2s_attn_policy_fwd(const void* qkv, const float* policy, int dtype, int B, int T, int H, int hd,
                         float scale, float eps, void* out, float* cls_row, d2s_stream_t stream);
+
+/* ---- predictor body (inference path of PredictorLG.forward, default_dynamic_vit.py:324-330; dynamic_vit.py:538-546)
+ * d2s_pool_act: z (B,N,C) = in_conv's Linear output; local (B,N,C/2) = act(z[:,:,:C/2]);
+ *   pooled (B,C/2) = sum_n act(z[b,n,C/2:]) * policy[b,n] / sum_n policy[b,n]   (policy (B,N) f32; NULL => mean).
+ * d2s_bias_act: u (rows,C) = act(u + bias[row / N]) in place; bias (rows/N, C) (N == 0: one shared row) -- the
+ *   per-image term pooled @ W_global^T + b of the split Linear that replaces cat + Linear (:329, out_conv[0]). */
+int d2s_pool_act(const void* z, const float* policy, int dtype, int B, int N, int C, int act, void* local, void* pooled,
+                 d2s_stream_t stream);
+int d2s_bias_act(void* u, const void* bias, int dtype, long long rows, int N, int C, int act, d2s_stream_t stream);
+
+/* ---- token assembly (dynamic_vit.py:816-824; default_dynamic_vit.py:437-442) -----------------------------------
+ * out (B,N+1,D) = cat(cls (D) broadcast, patches (B,N,D)) + pos (N+1,D), one pass instead of concat + add. */
+int d2s_assemble_tokens(const void* patches, const void* cls, const void* pos, int dtype, int B, int N, int D,
+                        void* out, d2s_stream_t stream);
 
 /* ---- residual add + LayerNorm ("next" row of the scope table: Block.forward) -----------------------------
  * Inference path of x = x + branch; h = norm(x) (dynamic_vit.py:263-283; default_dynamic_vit.py:234-237) and of the

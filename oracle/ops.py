@@ -323,3 +323,38 @@ def add_layernorm(x, y, weight, bias, eps, norm_row0=0):
     s = x if y is None else x + y
     h = F.layer_norm(s[:, norm_row0:].float(), (s.shape[-1],), weight.float(), bias.float(), eps).to(s.dtype)
     return s, h
+
+
+# ----------------------------------------------------------------------------------------------
+# predictor body pieces and token assembly (checkers for the fused inference kernels)
+# ----------------------------------------------------------------------------------------------
+
+def _act(x, act):
+    return F.gelu(x) if act == "gelu" else (F.relu(x) if act == "relu" else x)
+
+
+def pool_act(z, policy, act="gelu"):
+    """z (B,N,C) = in_conv Linear output.  local = act(z)[..., :C/2]; pooled = policy-weighted mean over tokens of
+    act(z)[..., C/2:] (vit_models/default_dynamic_vit.py:325-328; policy None = plain mean, dynamic_vit.py:542)."""
+    h = _act(z, act)
+    half = z.shape[-1] // 2
+    local, glob = h[..., :half], h[..., half:]
+    if policy is None:
+        pooled = glob.float().mean(dim=1)
+    else:
+        p = policy.reshape(z.shape[0], z.shape[1], 1).float()
+        pooled = (glob.float() * p).sum(dim=1) / p.sum(dim=1)
+    return local.contiguous(), pooled.to(z.dtype)
+
+
+def bias_act(u, bias, act="gelu"):
+    """act(u + bias) with bias (B,C) broadcast over tokens or (C,) shared."""
+    b = bias.unsqueeze(1) if bias.dim() == 2 else bias
+    return _act(u + b.to(u.dtype), act)
+
+
+def assemble_tokens(patches, cls_token, pos_embed):
+    """cat(cls, patches) + pos_embed (vit_models/dynamic_vit.py:820-823)."""
+    B = patches.shape[0]
+    x = torch.cat([cls_token.reshape(1, 1, -1).expand(B, -1, -1).to(patches.dtype), patches], dim=1)
+    return x + pos_embed.reshape(1, x.shape[1], -1).to(patches.dtype)

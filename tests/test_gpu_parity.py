@@ -364,6 +364,63 @@ def test_add_layernorm_strided_view_and_full_size(ops):
     torch.testing.assert_close(hs.float(), ln(x[:, 1:]).float(), rtol=1.6e-2, atol=1e-2)
 
 
+# ------------------------------------------------------------------------------------------ predictor body, embed
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("B,N,Cc", [(3, 196, 384), (2, 137, 768), (2, 96, 128), (1, 5, 1536)])
+@pytest.mark.parametrize("with_policy", [True, False])
+def test_pool_act(ops, dtype, B, N, Cc, with_policy):
+    if dtype == torch.float32 and Cc > 1024:
+        pytest.skip("fp32 rows are limited to C <= 1024")
+    z = (fx.randn(140 + Cc, B, N, Cc) * 1.5).to(dtype)
+    pol = (torch.rand(B, N, generator=fx.gen(141)) > 0.3).float() if with_policy else None
+    if pol is not None:
+        pol[:, 0] = 1
+    local, pooled = ops.pool_act(cu(z), None if pol is None else cu(pol), ops.ACT_GELU)
+    rl, rp = oo.pool_act(z, pol, "gelu")
+    tol = dict(rtol=1e-5, atol=1e-6) if dtype == torch.float32 else dict(rtol=1e-2, atol=1e-2)
+    torch.testing.assert_close(local.cpu().float(), rl.float(), **tol)
+    torch.testing.assert_close(pooled.cpu().float(), rp.float(), **tol)
+    l2, p2 = ops.pool_act(cu(z), None, ops.ACT_RELU)
+    rl2, rp2 = oo.pool_act(z, None, "relu")
+    assert torch.equal(l2.cpu(), rl2)                                      # ReLU halves are bit-exact
+    torch.testing.assert_close(p2.cpu().float(), rp2.float(), **tol)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_bias_act_and_split_linear_identity(ops, dtype):
+    B, N, Cc = 4, 196, 192
+    u = fx.randn(150, B, N, Cc).to(dtype)
+    bias = fx.randn(151, B, Cc).to(dtype)
+    out = ops.bias_act_(cu(u).clone(), cu(bias), ops.ACT_GELU)
+    tol = dict(rtol=1e-5, atol=1e-6) if dtype == torch.float32 else dict(rtol=1e-2, atol=1e-2)
+    torch.testing.assert_close(out.cpu().float(), oo.bias_act(u, bias, "gelu").float(), **tol)
+    shared = fx.randn(152, Cc).to(dtype)
+    out = ops.bias_act_(cu(u).clone(), cu(shared), ops.ACT_NONE)
+    assert torch.equal(out.cpu(), u + shared)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_assemble_tokens(ops, dtype):
+    B, N, D = 5, 196, 384
+    pe, cls, pos = fx.randn(160, B, N, D).to(dtype), fx.randn(161, 1, 1, D).to(dtype), fx.randn(162, 1, N + 1, D).to(dtype)
+    out = ops.assemble_tokens(cu(pe), cu(cls), cu(pos))
+    assert torch.equal(out.cpu(), oo.assemble_tokens(pe, cls, pos))            # one rounding per element: bit-exact
+
+
+def test_score_tail_a_gelu_on_load_and_prev_gather(ops):
+    B, N, Cc, K = 4, 196, 96, 137
+    raw = fx.randn(170, B, N, Cc)
+    W, b = fx.randn(171, 2, Cc, scale=0.3), fx.randn(172, 2, scale=0.1)
+    prev = (torch.rand(B, N, generator=fx.gen(173)) > 0.2).float()
+    logp, kept, pk = ops.score_tail_a(cu(raw), cu(W), cu(b), k=K, prev=cu(prev), act_input=ops.ACT_GELU, want_prev_kept=True)
+    torch.testing.assert_close(logp.cpu(), oo.score_tail_a(torch.nn.functional.gelu(raw), W, b), rtol=1e-4, atol=1e-5)
+    rk, _ = oo.select_topk(logp.cpu()[:, :, 0], K, oo.ORDER_SCORE_DESC)
+    assert torch.equal(kept.cpu(), rk)
+    assert torch.equal(pk.cpu(), oo.batch_index_select(prev, kept.cpu()))
+    _, _, pk1 = ops.score_tail_a(cu(raw), cu(W), cu(b), k=K, act_input=ops.ACT_GELU, want_prev_kept=True)
+    assert torch.equal(pk1.cpu(), torch.ones(B, K))
+
+
 # ------------------------------------------------------------------------------------------ error behaviour
 def test_errors_are_loud(ops):
     with pytest.raises(RuntimeError):
