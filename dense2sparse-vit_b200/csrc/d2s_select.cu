@@ -19,7 +19,7 @@ constexpr int kSelMaxN = 1024;
 constexpr int kSelEPT = kSelMaxN / kSelThreads;  // elements per thread
 
 struct SelSmem {
-  uint32_t key[kSelMaxN];
+  alignas(16) uint32_t key[kSelMaxN + 4];
   int warp_cnt[kSelEPT][kSelWarps];
   float red[kSelWarps];
   float bcast;
@@ -39,13 +39,34 @@ __device__ void block_select_write(SelSmem& s, int N, int K, int order, int64_t*
     rank[e] = 0;
   }
   const int nchunks = (N + kSelThreads - 1) / kSelThreads;
-  for (int j = 0; j < N; ++j) {
-    const uint32_t kj = s.key[j];  // broadcast read
+  if (nchunks == 1) {
+    // N <= 256 (196 / 137 / 96 in the models): four keys per 16-byte broadcast load, loop unrolled so that several
+    // loads are in flight.  The caller pads s.key[N .. round_up(N,4)) with 0, which is below every real key
+    // (float_to_ordered never returns 0), so padded entries never count.
+    const uint4* k4 = reinterpret_cast<const uint4*>(s.key);
+    const uint32_t my = mykey[0];
+    const int i = tid;
+    int r0 = 0, r1 = 0, r2 = 0, r3 = 0;
+    const int n4 = (N + 3) >> 2;
+#pragma unroll 8
+    for (int j4 = 0; j4 < n4; ++j4) {
+      const uint4 k = k4[j4];
+      const int j = 4 * j4;
+      r0 += (k.x > my) || (k.x == my && j < i);
+      r1 += (k.y > my) || (k.y == my && j + 1 < i);
+      r2 += (k.z > my) || (k.z == my && j + 2 < i);
+      r3 += (k.w > my) || (k.w == my && j + 3 < i);
+    }
+    rank[0] = (r0 + r1) + (r2 + r3);
+  } else {
+    for (int j = 0; j < N; ++j) {
+      const uint32_t kj = s.key[j];  // broadcast read
 #pragma unroll
-    for (int e = 0; e < kSelEPT; ++e) {
-      if (e < nchunks) {
-        const int i = e * kSelThreads + tid;
-        rank[e] += (kj > mykey[e]) || (kj == mykey[e] && j < i);
+      for (int e = 0; e < kSelEPT; ++e) {
+        if (e < nchunks) {
+          const int i = e * kSelThreads + tid;
+          rank[e] += (kj > mykey[e]) || (kj == mykey[e] && j < i);
+        }
       }
     }
   }
@@ -96,6 +117,7 @@ select_topk_kernel(const float* __restrict__ score, int N, int K, int order,
   __shared__ SelSmem s;
   const int b = blockIdx.x;
   for (int i = threadIdx.x; i < N; i += kSelThreads) s.key[i] = float_to_ordered(score[(size_t)b * N + i]);
+  if (threadIdx.x < 4) s.key[N + threadIdx.x] = 0u;  // padding for the 4-wide rank loop
   __syncthreads();
   block_select_write(s, N, K, order, kept ? kept + (size_t)b * K : nullptr,
                      dropped ? dropped + (size_t)b * (N - K) : nullptr);
@@ -182,38 +204,53 @@ score_tail_a_kernel(const T_* __restrict__ hidden, int N, int C, const float* __
   __syncthreads();
   const float b0 = bias[0], b1 = bias[1];
   constexpr int VE = Vec16<T_>::kElems;
-  for (int n = threadIdx.x; n < N; n += kSelThreads) {
-    const T_* row = hidden + ((size_t)b * N + n) * C;
+  // Four lanes per token row: lane q of a quad takes the 16-byte chunks q, q+4, q+8, ... of the row, so every load
+  // instruction of the warp covers 8 rows x 64 contiguous bytes (all sectors fully used) instead of 32 rows x 16 bytes.
+  const int quad = threadIdx.x >> 2, q4 = threadIdx.x & 3;
+  const int nchunk = C / VE;
+  for (int n0 = 0; n0 < N; n0 += kSelThreads / 4) {
+    const int n = n0 + quad;
     float a0 = 0.f, a1 = 0.f;
-    for (int c = 0; c < C; c += VE) {
-      float v[8];
-      Vec16<T_>::load(row + c, v);
-      if (act_input) {  // the GELU in front of the last Linear (default_dynamic_vit.py:318), applied on load
+    if (n < N) {
+      const T_* row = hidden + ((size_t)b * N + n) * C;
+      for (int ch = q4; ch < nchunk; ch += 4) {
+        const int c = ch * VE;
+        float v[8];
+        Vec16<T_>::load(row + c, v);
+        if (act_input) {  // the GELU in front of the last Linear (default_dynamic_vit.py:318), applied on load
 #pragma unroll
-        for (int q = 0; q < VE; ++q) v[q] = round_to(0.5f * v[q] * (1.0f + erff(v[q] * 0.70710678118654752440f)), row);
-      }
+          for (int q = 0; q < VE; ++q) v[q] = round_to(0.5f * v[q] * (1.0f + erff(v[q] * 0.70710678118654752440f)), row);
+        }
 #pragma unroll
-      for (int q = 0; q < VE; ++q) {
-        a0 = fmaf(v[q], w_s[c + q], a0);
-        a1 = fmaf(v[q], w_s[C + c + q], a1);
+        for (int q = 0; q < VE; ++q) {
+          a0 = fmaf(v[q], w_s[c + q], a0);
+          a1 = fmaf(v[q], w_s[C + c + q], a1);
+        }
       }
     }
-    a0 += b0; a1 += b1;
-    const float m = fmaxf(a0, a1);
-    const float lse = m + logf(expf(a0 - m) + expf(a1 - m));
-    const float lp0 = a0 - lse, lp1 = a1 - lse;
-    const size_t t = (size_t)b * N + n;
-    logp[2 * t] = lp0;
-    logp[2 * t + 1] = lp1;
-    if (gumbel) {
-      float d, y;
-      gumbel_decide(lp0, lp1, gumbel[2 * t], gumbel[2 * t + 1], prev ? prev[t] : 1.0f, d, y);
-      decision[t] = d;
-      ysoft[t] = y;
+    a0 += __shfl_xor_sync(0xffffffffu, a0, 1);
+    a1 += __shfl_xor_sync(0xffffffffu, a1, 1);
+    a0 += __shfl_xor_sync(0xffffffffu, a0, 2);
+    a1 += __shfl_xor_sync(0xffffffffu, a1, 2);
+    if (n < N && q4 == 0) {
+      a0 += b0; a1 += b1;
+      const float m = fmaxf(a0, a1);
+      const float lse = m + logf(expf(a0 - m) + expf(a1 - m));
+      const float lp0 = a0 - lse, lp1 = a1 - lse;
+      const size_t t = (size_t)b * N + n;
+      reinterpret_cast<float2*>(logp)[t] = make_float2(lp0, lp1);
+      if (gumbel) {
+        float d, y;
+        const float2 g = reinterpret_cast<const float2*>(gumbel)[t];
+        gumbel_decide(lp0, lp1, g.x, g.y, prev ? prev[t] : 1.0f, d, y);
+        decision[t] = d;
+        ysoft[t] = y;
+      }
+      s.key[n] = float_to_ordered(lp0);
     }
-    s.key[n] = float_to_ordered(lp0);
   }
   if (kept == nullptr) return;
+  if (threadIdx.x < 4) s.key[N + threadIdx.x] = 0u;
   __syncthreads();
   block_select_write(s, N, K, D2S_ORDER_SCORE_DESC, kept + (size_t)b * K, nullptr, prev ? prev + (size_t)b * N : nullptr,
                      prev_kept ? prev_kept + (size_t)b * K : nullptr);
@@ -237,27 +274,29 @@ score_tail_b_kernel(const T_* __restrict__ hidden, int N, int C, const float* __
   const float beta_dot = block_reduce_sum(part, s);  // also orders the w_s writes before use
   constexpr int VE = Vec16<T_>::kElems;
   constexpr int kMaxPerThread = kSelEPT;
-  float sc[kMaxPerThread];
-  float lmax = -INFINITY;
-#pragma unroll
-  for (int e = 0; e < kMaxPerThread; ++e) {
-    const int n = e * kSelThreads + threadIdx.x;
-    sc[e] = -INFINITY;
-    if (n >= N) continue;
-    const T_* row = hidden + ((size_t)b * N + n) * C;
+  // Phase 1 (four lanes per token row, see score_tail_a_kernel): raw scores into shared memory.
+  const int quad = threadIdx.x >> 2, q4 = threadIdx.x & 3;
+  const int nchunk = C / VE;
+  float* sc_s = reinterpret_cast<float*>(s.key);   // scores live in the key array until they are turned into keys
+  for (int n0 = 0; n0 < N; n0 += kSelThreads / 4) {
+    const int n = n0 + quad;
+    const T_* row = hidden + ((size_t)b * N + min(n, N - 1)) * C;
     float mean = 0.f, rstd = 1.f;
     if (ln_w) {
       float sum = 0.f;
-      for (int c = 0; c < C; c += VE) {
+      for (int ch = q4; ch < nchunk; ch += 4) {
         float v[8];
-        Vec16<T_>::load(row + c, v);
+        Vec16<T_>::load(row + ch * VE, v);
 #pragma unroll
         for (int q = 0; q < VE; ++q) sum += v[q];
       }
+      sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+      sum += __shfl_xor_sync(0xffffffffu, sum, 2);
       mean = sum / (float)C;
     }
     float var = 0.f, dot = 0.f;
-    for (int c = 0; c < C; c += VE) {
+    for (int ch = q4; ch < nchunk; ch += 4) {   // second touch of the row hits L1 (8 rows x 192 B per warp pass)
+      const int c = ch * VE;
       float v[8];
       Vec16<T_>::load(row + c, v);
 #pragma unroll
@@ -267,12 +306,27 @@ score_tail_b_kernel(const T_* __restrict__ hidden, int N, int C, const float* __
         dot = fmaf(d, w_s[c + q], dot);
       }
     }
+    var += __shfl_xor_sync(0xffffffffu, var, 1);
+    dot += __shfl_xor_sync(0xffffffffu, dot, 1);
+    var += __shfl_xor_sync(0xffffffffu, var, 2);
+    dot += __shfl_xor_sync(0xffffffffu, dot, 2);
     if (ln_w) rstd = rsqrtf(var / (float)C + ln_eps);
-    const float val = dot * rstd + beta_dot + bias;
-    sc[e] = val;
-    scores[(size_t)b * N + n] = val;
-    lmax = fmaxf(lmax, val);
+    if (n < N && q4 == 0) {
+      const float val = dot * rstd + beta_dot + bias;
+      sc_s[n] = val;
+      scores[(size_t)b * N + n] = val;
+    }
   }
+  __syncthreads();
+  float sc[kMaxPerThread];
+  float lmax = -INFINITY;
+#pragma unroll
+  for (int e = 0; e < kMaxPerThread; ++e) {
+    const int n = e * kSelThreads + threadIdx.x;
+    sc[e] = (n < N) ? sc_s[n] : -INFINITY;
+    lmax = fmaxf(lmax, sc[e]);
+  }
+  __syncthreads();   // every score has been read before the key array is overwritten below
   float pr[kMaxPerThread];
   if (prob_mode == D2S_PROB_SOFTMAX) {
     const float gmax = block_reduce_max(lmax, s);
@@ -299,6 +353,7 @@ score_tail_b_kernel(const T_* __restrict__ hidden, int N, int C, const float* __
     }
   }
   if (kept == nullptr) return;
+  if (threadIdx.x < 4) s.key[N + threadIdx.x] = 0u;
   __syncthreads();
   block_select_write(s, N, K, D2S_ORDER_INDEX_ASC, kept + (size_t)b * K,
                      dropped ? dropped + (size_t)b * (N - K) : nullptr);
