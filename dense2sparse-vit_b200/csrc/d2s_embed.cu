@@ -40,9 +40,53 @@ assemble_tokens_kernel(const T_* __restrict__ patches, const T_* __restrict__ cl
   }
 }
 
+// im2col of non-overlapping patches: img (B,C,H,W) -> patches (B, gh*gw, C*ph*pw), k = (c, py, px) as Conv2d's weight
+// is laid out (PatchEmbed.proj, dynamic_vit.py:296-302).  One 16-byte vector per thread, output order (coalesced
+// writes; reads are 32-byte runs of one patch row).
+template <int VE>
+__global__ void __launch_bounds__(256)
+patchify_kernel(const int4* __restrict__ img, long long total, int C, int Hh, int Ww, int ph, int pw, int4* __restrict__ out) {
+  const int gh = Hh / ph, gw = Ww / pw;
+  const int vec_per_prow = pw / VE;                 // vectors per patch row
+  const int vec_per_patch = C * ph * vec_per_prow;  // vectors per output row
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int kv = (int)(i % vec_per_patch);
+    const long long r = i / vec_per_patch;
+    const int gx = (int)(r % gw);
+    const int gy = (int)((r / gw) % gh);
+    const long long b = r / ((long long)gw * gh);
+    const int pxv = kv % vec_per_prow;
+    const int py = (kv / vec_per_prow) % ph;
+    const int c = kv / (vec_per_prow * ph);
+    const long long src = (((b * C + c) * Hh + (gy * ph + py)) * (long long)Ww + gx * pw) / VE + pxv;
+    out[i] = ld_stream16(img + src);
+  }
+}
+
 }  // namespace d2s
 
 using namespace d2s;
+
+extern "C" int d2s_patchify(const void* img, int dtype, int B, int C, int Hh, int Ww, int ph, int pw, void* out,
+                            d2s_stream_t stream) {
+  D2S_REQUIRE(img && out, D2S_ERR_ARG, "patchify: null pointer");
+  D2S_REQUIRE(dtype == D2S_F32 || dtype == D2S_BF16, D2S_ERR_ARG, "patchify: dtype %d unsupported", dtype);
+  const int ve = dtype == D2S_BF16 ? 8 : 4;
+  D2S_REQUIRE(B >= 0 && C >= 1 && ph >= 1 && pw >= ve && Hh % ph == 0 && Ww % pw == 0 && pw % ve == 0, D2S_ERR_ARG,
+              "patchify: bad shape B=%d C=%d H=%d W=%d patch=%dx%d (patch width must be a multiple of %d)", B, C, Hh, Ww, ph,
+              pw, ve);
+  D2S_REQUIRE(aligned16(img) && aligned16(out), D2S_ERR_ALIGN, "patchify: pointers must be 16-byte aligned");
+  if (B == 0) return D2S_OK;
+  const long long total = (long long)B * C * Hh * Ww / ve;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 32LL * kNumSMs) blocks = 32LL * kNumSMs;
+  if (dtype == D2S_BF16)
+    patchify_kernel<8><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const int4*)img, total, C, Hh, Ww, ph, pw, (int4*)out);
+  else
+    patchify_kernel<4><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const int4*)img, total, C, Hh, Ww, ph, pw, (int4*)out);
+  count_launch();
+  return check_launch("d2s_patchify");
+}
 
 extern "C" int d2s_assemble_tokens(const void* patches, const void* cls, const void* pos, int dtype, int B, int N, int D,
                                    void* out, d2s_stream_t stream) {

@@ -47,11 +47,34 @@ template <> struct PVec<float> {
   __device__ static float round(float f) { return f; }
 };
 
+// erf for activations that are stored as bf16: Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7 with exact exp) evaluated with
+// MUFU rcp/ex2 -- absolute error ~1e-6, three orders of magnitude below half a bf16 ulp of the GELU it feeds, at
+// roughly a third of erff()'s instruction count (exact-erf GELU is COMPUTE-bound on B200: ~30 FP32 instructions per
+// element against 4 bytes of traffic).  fp32 tensors keep erff().
+__device__ __forceinline__ float erf_fast(float x) {
+  const float ax = fabsf(x);
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, ax, 1.0f)));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  p *= t;
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * ax * ax));
+  return copysignf(fmaf(-p, e, 1.0f), x);
+}
+template <bool kFast>
 __device__ __forceinline__ float act_apply(float x, int act) {
-  if (act == D2S_ACT_GELU) return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));  // nn.GELU() (erf form)
+  if (act == D2S_ACT_GELU) {   // nn.GELU() (erf form)
+    const float z = x * 0.70710678118654752440f;
+    return 0.5f * x * (1.0f + (kFast ? erf_fast(z) : erff(z)));
+  }
   if (act == D2S_ACT_RELU) return fmaxf(x, 0.0f);
   return x;
 }
+template <typename T_> struct ActFast { static constexpr bool value = false; };
+template <> struct ActFast<__nv_bfloat16> { static constexpr bool value = true; };
 
 constexpr int kPoolThreads = 256;
 
@@ -76,7 +99,7 @@ pool_act_kernel(const T_* __restrict__ z, const float* __restrict__ policy, int 
       float x[8];
       PVec<T_>::unpack(ld_stream16(z + row * C + (size_t)v * VE), x);
 #pragma unroll
-      for (int q = 0; q < VE; ++q) x[q] = PVec<T_>::round(act_apply(x[q], act));
+      for (int q = 0; q < VE; ++q) x[q] = PVec<T_>::round(act_apply<ActFast<T_>::value>(x[q], act));
       if (v < half_vec) {
         *reinterpret_cast<int4*>(local + row * half + (size_t)v * VE) = PVec<T_>::pack(x);
       } else {
@@ -101,23 +124,51 @@ pool_act_kernel(const T_* __restrict__ z, const float* __restrict__ policy, int 
   }
 }
 
-// u (rows, C) += bias (per image: bias[(row / N) * C + c]; N == 0 => one shared row), then act, in place
+// u (rows, C) += bias (per image: bias[(row / N) * C + c]; N == 0 => one shared row; NULL => none), then act, in place.
+// grid.x covers the 16-byte vectors of a row, grid.y strides the rows: no 64-bit divisions in the loop.
 template <typename T_>
 __global__ void __launch_bounds__(256)
 bias_act_kernel(T_* __restrict__ u, const T_* __restrict__ bias, long long rows, int N, int C, int act) {
   constexpr int VE = PVec<T_>::kElems;
   const int nvec = C / VE;
-  const long long total = rows * nvec;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const long long row = i / nvec;
-    const int v = (int)(i - row * nvec);
-    const long long brow = N > 0 ? row / N : 0;
-    float x[8], bb[8];
-    PVec<T_>::unpack(*reinterpret_cast<const int4*>(u + row * C + (size_t)v * VE), x);
-    PVec<T_>::unpack(*reinterpret_cast<const int4*>(bias + brow * C + (size_t)v * VE), bb);
+  const int v = blockIdx.x * 32 + (threadIdx.x & 31);
+  if (v >= nvec) return;
+  float bshared[8];
+  if (bias && N == 0) PVec<T_>::unpack(*reinterpret_cast<const int4*>(bias + (size_t)v * VE), bshared);
+  for (long long row = (long long)blockIdx.y * 8 + (threadIdx.x >> 5); row < rows; row += (long long)gridDim.y * 8) {
+    T_* p = u + row * C + (size_t)v * VE;
+    float x[8];
+    PVec<T_>::unpack(*reinterpret_cast<const int4*>(p), x);
+    if (bias) {
+      if (N > 0) PVec<T_>::unpack(*reinterpret_cast<const int4*>(bias + (row / N) * C + (size_t)v * VE), bshared);
 #pragma unroll
-    for (int q = 0; q < VE; ++q) x[q] = act_apply(PVec<T_>::round(x[q] + bb[q]), act);
-    *reinterpret_cast<int4*>(u + row * C + (size_t)v * VE) = PVec<T_>::pack(x);
+      for (int q = 0; q < VE; ++q) x[q] = PVec<T_>::round(x[q] + bshared[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < VE; ++q) x[q] = act_apply<ActFast<T_>::value>(x[q], act);
+    *reinterpret_cast<int4*>(p) = PVec<T_>::pack(x);
+  }
+}
+
+// flat variant for bias == NULL: the tensor is one long vector array
+template <typename T_>
+__global__ void __launch_bounds__(256)
+act_flat_kernel(T_* __restrict__ u, long long nvec_total, int act) {
+  constexpr int VE = PVec<T_>::kElems;
+  int4* p = reinterpret_cast<int4*>(u);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec_total; i += 2 * stride) {
+    const bool two = i + stride < nvec_total;
+    float x[8], y[8];
+    const int4 a = p[i];
+    int4 b = make_int4(0, 0, 0, 0);
+    if (two) b = p[i + stride];
+    PVec<T_>::unpack(a, x);
+    PVec<T_>::unpack(b, y);
+#pragma unroll
+    for (int q = 0; q < VE; ++q) { x[q] = act_apply<ActFast<T_>::value>(x[q], act); y[q] = act_apply<ActFast<T_>::value>(y[q], act); }
+    p[i] = PVec<T_>::pack(x);
+    if (two) p[i + stride] = PVec<T_>::pack(y);
   }
 }
 
@@ -148,21 +199,31 @@ extern "C" int d2s_pool_act(const void* z, const float* policy, int dtype, int B
 }
 
 extern "C" int d2s_bias_act(void* u, const void* bias, int dtype, long long rows, int N, int C, int act, d2s_stream_t stream) {
-  D2S_REQUIRE(u && bias, D2S_ERR_ARG, "bias_act: null pointer");
+  D2S_REQUIRE(u, D2S_ERR_ARG, "bias_act: null pointer");
   D2S_REQUIRE(dtype == D2S_F32 || dtype == D2S_BF16, D2S_ERR_ARG, "bias_act: dtype %d unsupported", dtype);
   const int ve = dtype == D2S_BF16 ? 8 : 4;
   D2S_REQUIRE(rows >= 0 && N >= 0 && C >= ve && C % ve == 0, D2S_ERR_ARG, "bias_act: bad shape rows=%lld N=%d C=%d", rows, N, C);
   D2S_REQUIRE(act >= D2S_ACT_NONE && act <= D2S_ACT_RELU, D2S_ERR_ARG, "bias_act: bad activation %d", act);
-  D2S_REQUIRE(aligned16(u) && aligned16(bias), D2S_ERR_ALIGN, "bias_act: u/bias must be 16-byte aligned");
+  D2S_REQUIRE(aligned16(u) && (!bias || aligned16(bias)), D2S_ERR_ALIGN, "bias_act: u/bias must be 16-byte aligned");
   if (rows == 0) return D2S_OK;
-  const long long total = rows * (C / ve);
-  long long blocks = (total + 255) / 256;
-  if (blocks > 16LL * kNumSMs) blocks = 16LL * kNumSMs;
-  if (dtype == D2S_BF16)
-    bias_act_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)u, (const __nv_bfloat16*)bias,
-                                                                                     rows, N, C, act);
-  else
-    bias_act_kernel<float><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((float*)u, (const float*)bias, rows, N, C, act);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (bias == nullptr) {
+    const long long total = rows * (C / ve);
+    long long blocks = (total + 511) / 512;
+    if (blocks > 16LL * kNumSMs) blocks = 16LL * kNumSMs;
+    if (dtype == D2S_BF16) act_flat_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, st>>>((__nv_bfloat16*)u, total, act);
+    else                   act_flat_kernel<float><<<(unsigned)blocks, 256, 0, st>>>((float*)u, total, act);
+  } else {
+    const int gx = ceil_div(C / ve, 32);
+    long long gy = (rows + 7) / 8;
+    const long long cap = (16LL * kNumSMs + gx - 1) / gx;
+    if (gy > cap) gy = cap;
+    dim3 grid(gx, (unsigned)gy);
+    if (dtype == D2S_BF16)
+      bias_act_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((__nv_bfloat16*)u, (const __nv_bfloat16*)bias, rows, N, C, act);
+    else
+      bias_act_kernel<float><<<grid, 256, 0, st>>>((float*)u, (const float*)bias, rows, N, C, act);
+  }
   count_launch();
   return check_launch("d2s_bias_act");
 }

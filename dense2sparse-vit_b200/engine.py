@@ -24,15 +24,19 @@ def _needs_grad(*ts):
 
 
 def patch_embed_forward(m, img):
-    """Conv2d(kernel=stride=patch) as unfold + GEMM (dynamic_vit.py:286-303).  Avoids cuDNN's TF32 conv path
-    so fp32 runs stay within 1e-4 of the reference."""
+    """Conv2d(kernel=stride=patch) as im2col + GEMM (dynamic_vit.py:286-303).  Avoids cuDNN's TF32 conv path so fp32
+    runs stay within 1e-4 of the reference; the im2col is one d2s kernel when no gradient flows into the image."""
     B, C, Hh, Ww = img.shape
     ph, pw = m.patch_size
     assert Hh == m.img_size[0] and Ww == m.img_size[1], \
         f"Input image size ({Hh}*{Ww}) doesn't match model ({m.img_size[0]}*{m.img_size[1]})."
     gh, gw = Hh // ph, Ww // pw
     w = m.proj.weight
-    patches = img.to(w.dtype).view(B, C, gh, ph, gw, pw).permute(0, 2, 4, 1, 3, 5).reshape(B, gh * gw, C * ph * pw)
+    img = img.to(w.dtype)
+    if img.is_cuda and not _needs_grad(img) and img.dtype in (torch.float32, torch.bfloat16) and pw % 8 == 0 and Ww % 8 == 0:
+        patches = ops.patchify(img, ph, pw)
+    else:
+        patches = img.view(B, C, gh, ph, gw, pw).permute(0, 2, 4, 1, 3, 5).reshape(B, gh * gw, C * ph * pw)
     return F.linear(patches, w.view(w.shape[0], -1), m.proj.bias)
 
 
@@ -66,6 +70,18 @@ def _fusable(m, x, *extra):
             and isinstance(m.drop_path, torch.nn.Identity))
 
 
+def mlp_forward(m, h):
+    """Mlp.forward (dynamic_vit.py:159-175) for inference: the activation runs in place on fc1's output with the d2s
+    kernel (exact-erf GELU is compute-bound in torch's elementwise kernel)."""
+    if (isinstance(m.act, torch.nn.GELU) and getattr(m.act, "approximate", "none") == "none"
+            and isinstance(m.fc1, torch.nn.Linear) and not _needs_grad(h, m.fc1.weight)
+            and (m.drop.p == 0 or not m.training)):
+        u = m.fc1(h)
+        ops.bias_act_(u, None, ops.ACT_GELU)
+        return m.fc2(u)
+    return m(h)
+
+
 def block_forward_carry(m, x, y, policy=None, return_cls_attn=False):
     """Inference form of Block.forward (dynamic_vit.py:263-283) with the residual adds folded into the LayerNorms:
     takes the residual stream x and a pending branch output y (None at the first block), returns
@@ -78,7 +94,7 @@ def block_forward_carry(m, x, y, policy=None, return_cls_attn=False):
     else:
         a = attention_forward(m.attn, h, policy=policy)
     x, h = ops.add_layernorm(x, a, m.norm2.weight, m.norm2.bias, m.norm2.eps)
-    return x, m.mlp(h), cls_attn
+    return x, mlp_forward(m.mlp, h), cls_attn
 
 
 def block_forward(m, x, policy=None, return_cls_attn=False):

@@ -330,14 +330,17 @@ def pool_act(z, policy=None, act=ACT_GELU):
 
 
 def bias_act_(u, bias, act=ACT_GELU):
-    """In place: u (B,N,C) = act(u + bias[:, None, :]) with a per-image bias (B,C), or a shared bias (C,)."""
+    """In place: u (..., N, C) = act(u + bias) with a per-image bias (B,C) broadcast over tokens, a shared bias (C,),
+    or no bias (None)."""
     _check_cuda(u, bias)
     if not u.is_contiguous():
         raise ValueError("bias_act_ works in place on a contiguous tensor")
-    B, N, C = u.shape
-    bc = bias.detach().to(u.dtype).contiguous()
-    per_image = bc.dim() == 2
-    _lib.call("d2s_bias_act", _ptr(u), _ptr(bc), _dtype_code(u), B * N, N if per_image else 0, C, int(act), _stream())
+    C = u.shape[-1]
+    rows = u.numel() // C
+    per_image = bias is not None and bias.dim() == 2
+    bc = None if bias is None else bias.detach().to(u.dtype).contiguous()
+    n = u.shape[-2] if per_image else 0
+    _lib.call("d2s_bias_act", _ptr(u), _ptr(bc), _dtype_code(u), rows, n, C, int(act), _stream())
     return u
 
 
@@ -350,4 +353,14 @@ def assemble_tokens(patches, cls_token, pos_embed):
     pos = pos_embed.detach().to(pc.dtype).reshape(N + 1, D).contiguous()
     out = torch.empty(B, N + 1, D, dtype=pc.dtype, device=pc.device)
     _lib.call("d2s_assemble_tokens", _ptr(pc), _ptr(cls), _ptr(pos), _dtype_code(pc), B, N, D, _ptr(out), _stream())
+    return out
+
+
+def patchify(img, ph, pw):
+    """img (B,C,H,W) -> (B, (H/ph)*(W/pw), C*ph*pw): im2col of non-overlapping patches, k = (c, py, px)."""
+    _check_cuda(img)
+    x = img.detach().contiguous()
+    B, C, Hh, Ww = x.shape
+    out = torch.empty(B, (Hh // ph) * (Ww // pw), C * ph * pw, dtype=x.dtype, device=x.device)
+    _lib.call("d2s_patchify", _ptr(x), _dtype_code(x), B, C, Hh, Ww, int(ph), int(pw), _ptr(out), _stream())
     return out

@@ -140,8 +140,10 @@ int d2s_attn_policy_fwd(const void* qkv, const float* policy, int dtype, int B, 
 /* ---- predictor body (inference path of PredictorLG.forward, default_dynamic_vit.py:324-330; dynamic_vit.py:538-546)
  * d2s_pool_act: z (B,N,C) = in_conv's Linear output; local (B,N,C/2) = act(z[:,:,:C/2]);
  *   pooled (B,C/2) = sum_n act(z[b,n,C/2:]) * policy[b,n] / sum_n policy[b,n]   (policy (B,N) f32; NULL => mean).
- * d2s_bias_act: u (rows,C) = act(u + bias[row / N]) in place; bias (rows/N, C) (N == 0: one shared row) -- the
- *   per-image term pooled @ W_global^T + b of the split Linear that replaces cat + Linear (:329, out_conv[0]). */
+ * d2s_bias_act: u (rows,C) = act(u + bias[row / N]) in place; bias (rows/N, C) (N == 0: one shared row; NULL: none)
+ *   -- the per-image term pooled @ W_global^T + b of the split Linear that replaces cat + Linear (:329,
+ *   out_conv[0]); with bias NULL it is the in-place activation of Mlp.forward (dynamic_vit.py:170-171).
+ *   GELU is the erf form; for bf16 tensors erf is evaluated to ~1e-6 absolute (far below bf16 resolution). */
 int d2s_pool_act(const void* z, const float* policy, int dtype, int B, int N, int C, int act, void* local, void* pooled,
                  d2s_stream_t stream);
 int d2s_bias_act(void* u, const void* bias, int dtype, long long rows, int N, int C, int act, d2s_stream_t stream);
@@ -150,6 +152,10 @@ int d2s_bias_act(void* u, const void* bias, int dtype, long long rows, int N, in
  * out (B,N+1,D) = cat(cls (D) broadcast, patches (B,N,D)) + pos (N+1,D), one pass instead of concat + add. */
 int d2s_assemble_tokens(const void* patches, const void* cls, const void* pos, int dtype, int B, int N, int D,
                         void* out, d2s_stream_t stream);
+
+/* im2col of non-overlapping patches for PatchEmbed.proj as a GEMM (dynamic_vit.py:286-303):
+ * img (B,C,H,W) -> out (B, (H/ph)*(W/pw), C*ph*pw) with k = (c, py, px); pw must be a multiple of 8 (bf16) / 4 (f32). */
+int d2s_patchify(const void* img, int dtype, int B, int C, int H, int W, int ph, int pw, void* out, d2s_stream_t stream);
 
 /* ---- residual add + LayerNorm ("next" row of the scope table: Block.forward) -----------------------------
  * Inference path of x = x + branch; h = norm(x) (dynamic_vit.py:263-283; default_dynamic_vit.py:234-237) and of the

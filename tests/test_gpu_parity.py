@@ -407,6 +407,31 @@ def test_assemble_tokens(ops, dtype):
     assert torch.equal(out.cpu(), oo.assemble_tokens(pe, cls, pos))            # one rounding per element: bit-exact
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_patchify_bit_exact(ops, dtype):
+    B, Cc, Hh, Ww, p = 3, 3, 224, 224, 16
+    img = fx.randn(180, B, Cc, Hh, Ww).to(dtype)
+    ref = img.view(B, Cc, Hh // p, p, Ww // p, p).permute(0, 2, 4, 1, 3, 5).reshape(B, (Hh // p) * (Ww // p), Cc * p * p)
+    assert torch.equal(ops.patchify(cu(img), p, p).cpu(), ref)
+    img2 = fx.randn(181, 2, 1, 32, 64).to(dtype)
+    ref2 = img2.view(2, 1, 4, 8, 4, 16).permute(0, 2, 4, 1, 3, 5).reshape(2, 16, 128)
+    assert torch.equal(ops.patchify(cu(img2), 8, 16).cpu(), ref2)
+
+
+def test_gelu_inplace_matches_exact_erf(ops):
+    u = (fx.randn(182, 64, 197, 1536) * 2.0)
+    ref = torch.nn.functional.gelu(u)
+    out32 = ops.bias_act_(cu(u).clone(), None, ops.ACT_GELU)
+    torch.testing.assert_close(out32.cpu(), ref, rtol=1e-5, atol=5e-6)           # fp32: erff
+    ub = u.bfloat16()
+    outb = ops.bias_act_(cu(ub).clone(), None, ops.ACT_GELU)
+    refb = torch.nn.functional.gelu(ub.float())
+    # bf16: erf evaluated to ~1e-6 absolute, result rounded to bf16 -> within one bf16 ulp of the exactly rounded value
+    err = (outb.cpu().float() - refb).abs()
+    assert bool((err <= refb.abs() * 2 ** -8 + 1e-6).all())
+    assert float((outb.cpu().float() != refb.bfloat16().float()).float().mean()) < 2e-3   # and almost always identical
+
+
 def test_score_tail_a_gelu_on_load_and_prev_gather(ops):
     B, N, Cc, K = 4, 196, 96, 137
     raw = fx.randn(170, B, N, Cc)
