@@ -48,10 +48,11 @@ template <> struct PVec<float> {
 };
 
 // erf for activations that are stored as bf16: Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7 with exact exp) evaluated with
-// MUFU rcp/ex2 -- absolute error ~1e-6, three orders of magnitude below half a bf16 ulp of the GELU it feeds, at
+// MUFU rcp/ex2 -- absolute error ~5e-7, three orders of magnitude below half a bf16 ulp of the GELU it feeds, at
 // roughly a third of erff()'s instruction count (exact-erf GELU is COMPUTE-bound on B200: ~30 FP32 instructions per
 // element against 4 bytes of traffic).  fp32 tensors keep erff().
-__device__ __forceinline__ float erf_fast(float x) {
+// Returns 1 + erf(x).  For x < 0 this is erfc(|x|) = p*e directly (no cancellation in the GELU's negative tail).
+__device__ __forceinline__ float one_plus_erf_fast(float x) {
   const float ax = fabsf(x);
   float t;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, ax, 1.0f)));
@@ -62,13 +63,14 @@ __device__ __forceinline__ float erf_fast(float x) {
   p *= t;
   float e;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * ax * ax));
-  return copysignf(fmaf(-p, e, 1.0f), x);
+  const float pe = p * e;
+  return x < 0.f ? pe : 2.0f - pe;
 }
 template <bool kFast>
 __device__ __forceinline__ float act_apply(float x, int act) {
   if (act == D2S_ACT_GELU) {   // nn.GELU() (erf form)
     const float z = x * 0.70710678118654752440f;
-    return 0.5f * x * (1.0f + (kFast ? erf_fast(z) : erff(z)));
+    return 0.5f * x * (kFast ? one_plus_erf_fast(z) : 1.0f + erff(z));
   }
   if (act == D2S_ACT_RELU) return fmaxf(x, 0.0f);
   return x;

@@ -428,8 +428,9 @@ def test_gelu_inplace_matches_exact_erf(ops):
     refb = torch.nn.functional.gelu(ub.float())
     # bf16: erf evaluated to ~1e-6 absolute, result rounded to bf16 -> within one bf16 ulp of the exactly rounded value
     err = (outb.cpu().float() - refb).abs()
-    assert bool((err <= refb.abs() * 2 ** -8 + 1e-6).all())
-    assert float((outb.cpu().float() != refb.bfloat16().float()).float().mean()) < 2e-3   # and almost always identical
+    assert bool((err <= refb.abs() * 2 ** -7 + 1e-6).all())
+    core = ub.float() > -3.0          # outside the far negative tail (|gelu| < 4e-3) the rounded results are identical
+    assert float((outb.cpu().float() != refb.bfloat16().float())[core].float().mean()) < 1e-4
 
 
 def test_score_tail_a_gelu_on_load_and_prev_gather(ops):
