@@ -131,8 +131,10 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
           if (g > 0) mbar_wait(smem_u32(&bars->tmem_free), (g - 1) & 1);
           tc_fence_after();
           const uint64_t qd = make_desc_sw128(smem_u32(q_s[t]), 16, 1024);
-#pragma unroll
-          for (int ks = 0; ks < kTcHD / 16; ++ks) mma_ss(tmem, qd + (uint64_t)(ks * 2), kd + (uint64_t)(ks * 2), idesc_s, ks > 0);
+          mma_ss_imm<false>(tmem, qd, kd, idesc_s);
+          mma_ss_imm<true>(tmem, qd + 2, kd + 2, idesc_s);
+          mma_ss_imm<true>(tmem, qd + 4, kd + 4, idesc_s);
+          mma_ss_imm<true>(tmem, qd + 6, kd + 6, idesc_s);
           mma_commit(smem_u32(&bars->s_full));
           const bool last = t == kNT - 1;
           mbar_wait(smem_u32(&bars->p_full), g & 1);   // softmax done => this tile's S-MMA has completed as well
@@ -142,8 +144,11 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
           }
           if (t == 0) mbar_wait(smem_u32(&bars->v_full), it & 1);
           tc_fence_after();
-          for (int ks = 0; ks < ksteps; ++ks)
-            mma_ts(tmem + kOCol, tmem + (uint32_t)(ks * 8), vd + (uint64_t)(ks * 128), idesc_o, ks > 0);
+          // fully unrolled issue (T <= 256 => at most 16 K-steps); descriptors advance by constants
+          mma_ts_imm<false>(tmem + kOCol, tmem, vd, idesc_o);
+#pragma unroll
+          for (int ks = 1; ks < 16; ++ks)
+            if (ks < ksteps) mma_ts_imm<true>(tmem + kOCol, tmem + (uint32_t)(ks * 8), vd + (uint64_t)(ks * 128), idesc_o);
           mma_commit(smem_u32(&bars->o_full));
           if (last && has_next) {
             mbar_wait(smem_u32(&bars->o_full), g & 1);  // V is dead once the PV-MMA has completed
@@ -244,32 +249,63 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         // ---- epilogue -----------------------------------------------------------------------------------
         mbar_wait(smem_u32(&bars->o_full), g & 1);
         tc_fence_after();
-        if (warp_active) {
-          const float inv = 1.0f / den;
-          __nv_bfloat16* orow = out + ((size_t)b * T + min(i, T - 1)) * (size_t)(H * kTcHD) + (size_t)h * kTcHD;
+        if constexpr (kNT == 2) {
+          // two tiles per unit: pull the whole output row into registers, release TMEM, then store -- the next
+          // tile's S-MMA overlaps the stores (the 4-CTA/SM variant below has no registers to spare for this)
+          uint32_t ow[32];   // the output row as packed bf16
+          if (warp_active) {
+            const float inv = 1.0f / den;
 #pragma unroll
-          for (int ch = 0; ch < kTcHD / 16; ++ch) {
-            uint32_t v[16];
-            tmem_ld16_nowait(lane_addr + (uint32_t)(kOCol + ch * 16), v);
-            tmem_ld_wait();
-            uint32_t w[8];
+            for (int ch = 0; ch < kTcHD / 16; ++ch) {
+              uint32_t v[16];
+              tmem_ld16_nowait(lane_addr + (uint32_t)(kOCol + ch * 16), v);
+              tmem_ld_wait();
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              float o0 = __uint_as_float(v[2 * q]), o1 = __uint_as_float(v[2 * q + 1]);
-              if (kPol) {
-                o0 += c_eps_row * vsum_s[ch * 16 + 2 * q];
-                o1 += c_eps_row * vsum_s[ch * 16 + 2 * q + 1];
+              for (int q = 0; q < 8; ++q) {
+                float o0 = __uint_as_float(v[2 * q]), o1 = __uint_as_float(v[2 * q + 1]);
+                if (kPol) {
+                  o0 += c_eps_row * vsum_s[ch * 16 + 2 * q];
+                  o1 += c_eps_row * vsum_s[ch * 16 + 2 * q + 1];
+                }
+                ow[ch * 8 + q] = pack_bf16x2(o0 * inv, o1 * inv);
               }
-              w[q] = pack_bf16x2(o0 * inv, o1 * inv);
-            }
-            if (i < T) {
-              reinterpret_cast<uint4*>(orow)[ch * 2] = make_uint4(w[0], w[1], w[2], w[3]);
-              reinterpret_cast<uint4*>(orow)[ch * 2 + 1] = make_uint4(w[4], w[5], w[6], w[7]);
             }
           }
+          tc_fence_before();
+          mbar_arrive(smem_u32(&bars->tmem_free));   // O is in registers: the next S-MMA may overwrite this TMEM region
+          if (warp_active && i < T) {
+            uint4* orow = reinterpret_cast<uint4*>(out + ((size_t)b * T + i) * (size_t)(H * kTcHD) + (size_t)h * kTcHD);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) orow[q] = make_uint4(ow[4 * q], ow[4 * q + 1], ow[4 * q + 2], ow[4 * q + 3]);
+          }
+        } else {
+          if (warp_active) {
+            const float inv = 1.0f / den;
+            __nv_bfloat16* orow = out + ((size_t)b * T + min(i, T - 1)) * (size_t)(H * kTcHD) + (size_t)h * kTcHD;
+#pragma unroll
+            for (int ch = 0; ch < kTcHD / 16; ++ch) {
+              uint32_t v[16];
+              tmem_ld16_nowait(lane_addr + (uint32_t)(kOCol + ch * 16), v);
+              tmem_ld_wait();
+              uint32_t w[8];
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                float o0 = __uint_as_float(v[2 * q]), o1 = __uint_as_float(v[2 * q + 1]);
+                if (kPol) {
+                  o0 += c_eps_row * vsum_s[ch * 16 + 2 * q];
+                  o1 += c_eps_row * vsum_s[ch * 16 + 2 * q + 1];
+                }
+                w[q] = pack_bf16x2(o0 * inv, o1 * inv);
+              }
+              if (i < T) {
+                reinterpret_cast<uint4*>(orow)[ch * 2] = make_uint4(w[0], w[1], w[2], w[3]);
+                reinterpret_cast<uint4*>(orow)[ch * 2 + 1] = make_uint4(w[4], w[5], w[6], w[7]);
+              }
+            }
+          }
+          tc_fence_before();
+          mbar_arrive(smem_u32(&bars->tmem_free));
         }
-        tc_fence_before();
-        mbar_arrive(smem_u32(&bars->tmem_free));
       }
     }
   }

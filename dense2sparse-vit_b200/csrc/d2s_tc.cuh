@@ -70,6 +70,26 @@ __device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_
       "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accum)
       : "memory");
 }
+// Variants with the accumulate flag as an immediate (no setp in the single-thread issue loop: the tcgen05.mma issue
+// cadence of one thread is what the short PV product waits on).
+template <bool kAccum>
+__device__ __forceinline__ void mma_ss_imm(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
+  if (kAccum)
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, 1, 1;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+                 ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc));
+  else
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, 1, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+                 ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc));
+}
+template <bool kAccum>
+__device__ __forceinline__ void mma_ts_imm(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc) {
+  if (kAccum)
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, 1, 1;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n"
+                 ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc));
+  else
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, 1, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n"
+                 ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc));
+}
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
