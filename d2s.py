@@ -23,4 +23,5 @@ variant_b = pkg.variant_b
 perturbed_topk = pkg.perturbed_topk
 patch = pkg.patch
 runner = pkg.runner
+losses = pkg.losses
 _lib = pkg._lib

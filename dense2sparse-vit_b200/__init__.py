@@ -9,6 +9,6 @@ csrc/ holds the CUDA kernels and the C ABI (include/d2s.h); ops.py wraps them fo
 layers.py / variant_a.py / variant_b.py / perturbed_topk.py mirror the reference's Python interface;
 patch.py installs the kernels behind the reference's own modules.
 """
-from . import _lib, ops, engine, layers, perturbed_topk, variant_a, variant_b, patch, runner  # noqa: F401
+from . import _lib, ops, engine, layers, perturbed_topk, variant_a, variant_b, patch, runner, losses  # noqa: F401
 
-__all__ = ["_lib", "ops", "engine", "layers", "perturbed_topk", "variant_a", "variant_b", "patch", "runner"]
+__all__ = ["_lib", "ops", "engine", "layers", "perturbed_topk", "variant_a", "variant_b", "patch", "runner", "losses"]

@@ -1,0 +1,243 @@
+// LayerNorm forward/backward for the training path (Block.forward, vit_models/dynamic_vit.py:263-283, under bf16
+// autocast: fp32 residual stream in, bf16 normalised activations out for the following Linear).
+//
+// Why it exists: in one training step torch spends 12.0 ms in the LayerNorm weight/bias-gradient kernel, 2.7 ms in the
+// forward, 1.4 ms in the input-gradient kernel and ~2 ms in the fp32->bf16 casts that follow every LayerNorm
+// (profiles/r01f_launches_train_step.csv).  All three passes are plain HBM streaming:
+//   fwd : read x (ex*D), write h (eh*D) + (mean, rstd)
+//   bwd : read dh, x, write dx; dgamma/dbeta are reduced per CTA in shared memory and flushed with one atomicAdd per
+//         column per CTA (rows per CTA = 128 -> 2*D atomics per 128 rows).
+// Half-warp per row, 16-byte vectors, row kept in registers (same scheme as d2s_layernorm.cu).
+#include "d2s_common.cuh"
+
+namespace d2s {
+
+constexpr int kLtThreads = 256;
+constexpr int kLtRowsPerIter = kLtThreads / 16;   // 16 rows per CTA pass
+constexpr int kLtRowsPerCta = 128;
+constexpr int kLtBwdThreads = 128;                // backward: ~150 registers per thread -> smaller CTAs, 3 per SM
+constexpr int kLtBwdRowsPerIter = kLtBwdThreads / 16;
+
+template <typename T_> struct TV;
+template <> struct TV<__nv_bfloat16> {
+  static constexpr int kElems = 8;
+  __device__ static void load(const __nv_bfloat16* p, float (&v)[8]) {
+    const int4 r = *reinterpret_cast<const int4*>(p);
+    const uint32_t w[4] = {(uint32_t)r.x, (uint32_t)r.y, (uint32_t)r.z, (uint32_t)r.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { v[2 * i] = __uint_as_float(w[i] << 16); v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
+  }
+  __device__ static void store(__nv_bfloat16* p, const float (&v)[8]) {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { const __nv_bfloat162 t = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]); w[i] = *reinterpret_cast<const uint32_t*>(&t); }
+    *reinterpret_cast<int4*>(p) = make_int4((int)w[0], (int)w[1], (int)w[2], (int)w[3]);
+  }
+};
+template <> struct TV<float> {   // 8 floats = two 16-byte vectors, so both dtypes walk the row in 8-element steps
+  static constexpr int kElems = 8;
+  __device__ static void load(const float* p, float (&v)[8]) {
+    const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+  __device__ static void store(float* p, const float (&v)[8]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+  }
+};
+
+__device__ __forceinline__ float hw_sum(float v) {
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// h = (x - mean) * rstd * gamma + beta ; stats (rows, 2) = (mean, rstd)
+template <typename TX, typename TH, int kVPL>
+__global__ void __launch_bounds__(kLtThreads)
+ln_fwd_kernel(const TX* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta, long long rows,
+              int D, float eps, TH* __restrict__ h, float* __restrict__ stats) {
+  const int sub = threadIdx.x & 15;
+  const long long row = (long long)blockIdx.x * kLtRowsPerIter + (threadIdx.x >> 4);
+  const bool ok = row < rows;
+  const int nvec = D / 8;
+  float v[kVPL][8];
+  float sum = 0.f;
+#pragma unroll
+  for (int k = 0; k < kVPL; ++k) {
+    const int vi = sub + 16 * k;
+    if (ok && vi < nvec) {
+      TV<TX>::load(x + row * D + vi * 8, v[k]);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) sum += v[k][q];
+    } else {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) v[k][q] = 0.f;
+    }
+  }
+  const float mean = hw_sum(sum) / (float)D;
+  float var = 0.f;
+#pragma unroll
+  for (int k = 0; k < kVPL; ++k)
+    if (sub + 16 * k < nvec) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) { const float d = v[k][q] - mean; var = fmaf(d, d, var); }
+    }
+  const float rstd = rsqrtf(hw_sum(var) / (float)D + eps);
+  if (!ok) return;
+  if (sub == 0) { stats[row * 2] = mean; stats[row * 2 + 1] = rstd; }
+#pragma unroll
+  for (int k = 0; k < kVPL; ++k) {
+    const int vi = sub + 16 * k;
+    if (vi < nvec) {
+      float g[8], b[8], o[8];
+      TV<float>::load(gamma + vi * 8, g);
+      TV<float>::load(beta + vi * 8, b);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) o[q] = fmaf((v[k][q] - mean) * rstd, g[q], b[q]);
+      TV<TH>::store(h + row * D + vi * 8, o);
+    }
+  }
+}
+
+// dx = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dh * gamma;  dgamma += dh * xhat;  dbeta += dh
+template <typename TX, typename TH, int kVPL>
+__global__ void __launch_bounds__(kLtBwdThreads)
+ln_bwd_kernel(const TH* __restrict__ dh, const TX* __restrict__ x, const float* __restrict__ stats,
+              const float* __restrict__ gamma, long long rows, int D, TX* __restrict__ dx, float* __restrict__ dgamma,
+              float* __restrict__ dbeta) {
+  extern __shared__ float red[];   // 2 * D : per-CTA dgamma | dbeta
+  for (int c = threadIdx.x; c < 2 * D; c += kLtBwdThreads) red[c] = 0.f;
+  __syncthreads();
+  const int sub = threadIdx.x & 15;
+  const int nvec = D / 8;
+  float g[kVPL][8];
+#pragma unroll
+  for (int k = 0; k < kVPL; ++k)
+    if (sub + 16 * k < nvec) TV<float>::load(gamma + (sub + 16 * k) * 8, g[k]);
+  float ag[kVPL][8], ab[kVPL][8];
+#pragma unroll
+  for (int k = 0; k < kVPL; ++k)
+#pragma unroll
+    for (int q = 0; q < 8; ++q) { ag[k][q] = 0.f; ab[k][q] = 0.f; }
+  const long long row_end = min(rows, ((long long)blockIdx.x + 1) * kLtRowsPerCta);
+  for (long long row0 = (long long)blockIdx.x * kLtRowsPerCta; row0 < row_end; row0 += kLtBwdRowsPerIter) {
+    const long long row = row0 + (threadIdx.x >> 4);
+    const bool ok = row < row_end;
+    const float mean = ok ? stats[row * 2] : 0.f, rstd = ok ? stats[row * 2 + 1] : 0.f;
+    float xh[kVPL][8], gg[kVPL][8];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < kVPL; ++k) {
+      const int vi = sub + 16 * k;
+      if (ok && vi < nvec) {
+        float xv[8], dv[8];
+        TV<TX>::load(x + row * D + vi * 8, xv);
+        TV<TH>::load(dh + row * D + vi * 8, dv);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          xh[k][q] = (xv[q] - mean) * rstd;
+          gg[k][q] = dv[q] * g[k][q];
+          s1 += gg[k][q];
+          s2 = fmaf(gg[k][q], xh[k][q], s2);
+          ag[k][q] = fmaf(dv[q], xh[k][q], ag[k][q]);
+          ab[k][q] += dv[q];
+        }
+      } else {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { xh[k][q] = 0.f; gg[k][q] = 0.f; }
+      }
+    }
+    s1 = hw_sum(s1) / (float)D;
+    s2 = hw_sum(s2) / (float)D;
+    if (ok) {
+#pragma unroll
+      for (int k = 0; k < kVPL; ++k) {
+        const int vi = sub + 16 * k;
+        if (vi < nvec) {
+          float o[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) o[q] = rstd * (gg[k][q] - s1 - xh[k][q] * s2);
+          TV<TX>::store(dx + row * D + vi * 8, o);
+        }
+      }
+    }
+  }
+  // 16 half-warps hold partial column sums: fold into shared memory, then one atomic per column per CTA
+#pragma unroll
+  for (int k = 0; k < kVPL; ++k) {
+    const int vi = sub + 16 * k;
+    if (vi < nvec) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        atomicAdd(&red[vi * 8 + q], ag[k][q]);
+        atomicAdd(&red[D + vi * 8 + q], ab[k][q]);
+      }
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < D; c += kLtBwdThreads) {
+    atomicAdd(&dgamma[c], red[c]);
+    atomicAdd(&dbeta[c], red[D + c]);
+  }
+}
+
+template <typename TX, typename TH>
+static int ln_fwd_launch(const void* x, const float* gamma, const float* beta, long long rows, int D, float eps, void* h,
+                         float* stats, cudaStream_t st) {
+  const int vpl = ceil_div(D / 8, 16);
+  const unsigned grid = (unsigned)((rows + kLtRowsPerIter - 1) / kLtRowsPerIter);
+  if (vpl <= 3) ln_fwd_kernel<TX, TH, 3><<<grid, kLtThreads, 0, st>>>((const TX*)x, gamma, beta, rows, D, eps, (TH*)h, stats);
+  else          ln_fwd_kernel<TX, TH, 6><<<grid, kLtThreads, 0, st>>>((const TX*)x, gamma, beta, rows, D, eps, (TH*)h, stats);
+  count_launch();
+  return check_launch("d2s_layernorm_fwd");
+}
+template <typename TX, typename TH>
+static int ln_bwd_launch(const void* dh, const void* x, const float* stats, const float* gamma, long long rows, int D, void* dx,
+                         float* dgamma, float* dbeta, cudaStream_t st) {
+  const int vpl = ceil_div(D / 8, 16);
+  const unsigned grid = (unsigned)((rows + kLtRowsPerCta - 1) / kLtRowsPerCta);
+  const size_t smem = 2 * (size_t)D * sizeof(float);
+  if (vpl <= 3) ln_bwd_kernel<TX, TH, 3><<<grid, kLtBwdThreads, smem, st>>>((const TH*)dh, (const TX*)x, stats, gamma, rows, D, (TX*)dx, dgamma, dbeta);
+  else          ln_bwd_kernel<TX, TH, 6><<<grid, kLtBwdThreads, smem, st>>>((const TH*)dh, (const TX*)x, stats, gamma, rows, D, (TX*)dx, dgamma, dbeta);
+  count_launch();
+  return check_launch("d2s_layernorm_bwd");
+}
+
+static int ln_check(const char* what, long long rows, int D, int dx, int dh) {
+  D2S_REQUIRE(rows >= 0 && D >= 8 && D % 8 == 0 && D <= 768, D2S_ERR_ARG, "%s: D=%d must be a multiple of 8 in [8,768]", what, D);
+  D2S_REQUIRE((dx == D2S_F32 || dx == D2S_BF16) && (dh == D2S_F32 || dh == D2S_BF16), D2S_ERR_ARG, "%s: bad dtypes %d/%d", what, dx, dh);
+  return D2S_OK;
+}
+
+}  // namespace d2s
+
+using namespace d2s;
+
+extern "C" int d2s_layernorm_fwd(const void* x, int x_dtype, const float* gamma, const float* beta, long long rows, int D,
+                                 float eps, void* h, int h_dtype, float* stats, d2s_stream_t stream) {
+  D2S_REQUIRE(x && gamma && beta && h && stats, D2S_ERR_ARG, "layernorm_fwd: null pointer");
+  int rc = ln_check("layernorm_fwd", rows, D, x_dtype, h_dtype);
+  if (rc) return rc;
+  D2S_REQUIRE(aligned16(x) && aligned16(h) && aligned16(gamma) && aligned16(beta), D2S_ERR_ALIGN, "layernorm_fwd: 16-byte alignment");
+  if (rows == 0) return D2S_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (x_dtype == D2S_F32 && h_dtype == D2S_BF16) return ln_fwd_launch<float, __nv_bfloat16>(x, gamma, beta, rows, D, eps, h, stats, st);
+  if (x_dtype == D2S_F32 && h_dtype == D2S_F32) return ln_fwd_launch<float, float>(x, gamma, beta, rows, D, eps, h, stats, st);
+  if (x_dtype == D2S_BF16 && h_dtype == D2S_BF16) return ln_fwd_launch<__nv_bfloat16, __nv_bfloat16>(x, gamma, beta, rows, D, eps, h, stats, st);
+  return ln_fwd_launch<__nv_bfloat16, float>(x, gamma, beta, rows, D, eps, h, stats, st);
+}
+
+extern "C" int d2s_layernorm_bwd(const void* dh, int h_dtype, const void* x, int x_dtype, const float* stats, const float* gamma,
+                                 long long rows, int D, void* dx, float* dgamma, float* dbeta, d2s_stream_t stream) {
+  D2S_REQUIRE(dh && x && stats && gamma && dx && dgamma && dbeta, D2S_ERR_ARG, "layernorm_bwd: null pointer");
+  int rc = ln_check("layernorm_bwd", rows, D, x_dtype, h_dtype);
+  if (rc) return rc;
+  D2S_REQUIRE(aligned16(dh) && aligned16(x) && aligned16(dx) && aligned16(gamma), D2S_ERR_ALIGN, "layernorm_bwd: 16-byte alignment");
+  if (rows == 0) return D2S_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (x_dtype == D2S_F32 && h_dtype == D2S_BF16) return ln_bwd_launch<float, __nv_bfloat16>(dh, x, stats, gamma, rows, D, dx, dgamma, dbeta, st);
+  if (x_dtype == D2S_F32 && h_dtype == D2S_F32) return ln_bwd_launch<float, float>(dh, x, stats, gamma, rows, D, dx, dgamma, dbeta, st);
+  if (x_dtype == D2S_BF16 && h_dtype == D2S_BF16) return ln_bwd_launch<__nv_bfloat16, __nv_bfloat16>(dh, x, stats, gamma, rows, D, dx, dgamma, dbeta, st);
+  return ln_bwd_launch<__nv_bfloat16, float>(dh, x, stats, gamma, rows, D, dx, dgamma, dbeta, st);
+}

@@ -247,9 +247,20 @@ static int ptopk_launch(bool rng, const float* x, const float* noise, uint64_t s
   const size_t cells = (size_t)K * (N - K + 1);
   const size_t smem = ((cells * 6 + 15) & ~(size_t)15) + 2 * sizeof(PtBatchBuf);
   D2S_REQUIRE(smem <= 227 * 1024, D2S_ERR_ARG, "ptopk_fwd: N=%d K=%d needs %zu B of shared memory", N, K, smem);
-  // cluster size: enough CTAs for ~3 per SM, at most 8 (portable), never more than the sample batches
+  // Cluster size G (CTAs per image, splitting the samples): per-CTA work ~ 1/G, the grid runs in ceil(B*G / slots)
+  // waves of `slots` resident CTAs, so the time ~ waves / G; pick the power of two that minimises it (ties -> smaller G,
+  // less DSMEM reduction).  B=256: G=2 would run 512 CTAs in two waves of 444 slots (time 1.0), G=8 runs five waves of
+  // eighth-size CTAs (0.625).
+  const int per_sm = (int)((227u * 1024u) / (smem + 1024u)) < 1 ? 1 : (int)((227u * 1024u) / (smem + 1024u));
+  const long long slots = (long long)kNumSMs * per_sm;
   int G = 1;
-  while (G < 8 && (long long)B * G < 3LL * kNumSMs && G * kPtWarps * 2 <= S) G *= 2;
+  double best = 1e30;
+  for (int g = 1; g <= 8; g *= 2) {
+    if (g > 1 && g * kPtWarps > S) break;  // never more CTAs than sample batches
+    const long long waves = ((long long)B * g + slots - 1) / slots;
+    const double t = (double)waves / g + 0.01 * g;
+    if (t < best - 1e-9) { best = t; G = g; }
+  }
   auto kern = rng ? ptopk_fwd_kernel<true> : ptopk_fwd_kernel<false>;
   static bool smem_set[2] = {false, false};
   cudaError_t e;

@@ -97,6 +97,15 @@ def block_forward_carry(m, x, y, policy=None, return_cls_attn=False):
     return x, mlp_forward(m.mlp, h), cls_attn
 
 
+def norm_forward(n, x):
+    """A model LayerNorm on the training path: the d2s forward/backward pair when it applies (plain LayerNorm on a CUDA
+    tensor whose rows are multiples of 8 elements), torch otherwise."""
+    if _is_plain_ln(n) and x.is_cuda and x.dtype in (torch.float32, torch.bfloat16) and x.shape[-1] % 8 == 0 \
+            and x.shape[-1] <= 768 and len(n.normalized_shape) == 1:
+        return ops.layer_norm(x, n.weight, n.bias, n.eps)
+    return n(x)
+
+
 def block_forward(m, x, policy=None, return_cls_attn=False):
     """Block.forward (dynamic_vit.py:263-283)."""
     if _fusable(m, x, policy):
@@ -104,12 +113,12 @@ def block_forward(m, x, policy=None, return_cls_attn=False):
         x = x + y
         return (x, cls_attn) if return_cls_attn else x
     if return_cls_attn:
-        y, cls_attn = attention_forward(m.attn, m.norm1(x), policy=policy, return_cls_attn=True)
+        y, cls_attn = attention_forward(m.attn, norm_forward(m.norm1, x), policy=policy, return_cls_attn=True)
         x = x + m.drop_path(y)
-        x = x + m.drop_path(m.mlp(m.norm2(x)))
+        x = x + m.drop_path(m.mlp(norm_forward(m.norm2, x)))
         return x, cls_attn
-    x = x + m.drop_path(attention_forward(m.attn, m.norm1(x), policy=policy))
-    return x + m.drop_path(m.mlp(m.norm2(x)))
+    x = x + m.drop_path(attention_forward(m.attn, norm_forward(m.norm1, x), policy=policy))
+    return x + m.drop_path(m.mlp(norm_forward(m.norm2, x)))
 
 
 class _Stream:

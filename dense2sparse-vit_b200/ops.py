@@ -364,3 +364,44 @@ def patchify(img, ph, pw):
     out = torch.empty(B, (Hh // ph) * (Ww // pw), C * ph * pw, dtype=x.dtype, device=x.device)
     _lib.call("d2s_patchify", _ptr(x), _dtype_code(x), B, C, Hh, Ww, int(ph), int(pw), _ptr(out), _stream())
     return out
+
+
+# ----------------------------------------------------------------------------------------------
+# LayerNorm with autograd (training path)
+# ----------------------------------------------------------------------------------------------
+
+class _LayerNorm(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps, out_dtype):
+        xc = x.contiguous()
+        D = xc.shape[-1]
+        rows = xc.numel() // D
+        w, b = _f32c(weight), _f32c(bias)
+        h = torch.empty(xc.shape, dtype=out_dtype, device=xc.device)
+        stats = torch.empty(rows, 2, dtype=torch.float32, device=xc.device)
+        _lib.call("d2s_layernorm_fwd", _ptr(xc), _dtype_code(xc), _ptr(w), _ptr(b), rows, D, float(eps), _ptr(h),
+                  _dtype_code(h), _ptr(stats), _stream())
+        ctx.save_for_backward(xc, stats, w)
+        ctx.meta = (weight.dtype, bias.dtype)
+        return h
+
+    @staticmethod
+    def backward(ctx, dh):
+        xc, stats, w = ctx.saved_tensors
+        D = xc.shape[-1]
+        rows = xc.numel() // D
+        g = dh.contiguous()
+        dx = torch.empty_like(xc)
+        dgb = torch.zeros(2, D, dtype=torch.float32, device=xc.device)
+        _lib.call("d2s_layernorm_bwd", _ptr(g), _dtype_code(g), _ptr(xc), _dtype_code(xc), _ptr(stats), _ptr(w), rows, D,
+                  _ptr(dx), _ptr(dgb[0]), _ptr(dgb[1]), _stream())
+        return dx, dgb[0].to(ctx.meta[0]), dgb[1].to(ctx.meta[1]), None, None
+
+
+def layer_norm(x, weight, bias, eps, out_dtype=None):
+    """LayerNorm over the last dim with autograd: x f32|bf16 -> out_dtype (default: bf16 under CUDA autocast, else
+    x.dtype), statistics in fp32.  One streaming kernel forward, one backward (dx + dgamma + dbeta)."""
+    _check_cuda(x, weight, bias)
+    if out_dtype is None:
+        out_dtype = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else x.dtype
+    return _LayerNorm.apply(x, weight, bias, eps, out_dtype)

@@ -168,6 +168,15 @@ int d2s_add_layernorm(const void* x, const void* y, const void* gamma, const voi
                       long long x_stride_b, long long x_stride_t, float eps, int norm_row0,
                       void* out_sum, void* out_norm, d2s_stream_t stream);
 
+/* LayerNorm forward / backward for the training path (norm1 / norm2 / predictor norms of Block.forward,
+ * dynamic_vit.py:263-283) with mixed dtypes for bf16 autocast: x (rows,D) f32|bf16 -> h (rows,D) f32|bf16,
+ * gamma/beta f32 (D), stats (rows,2) f32 = (mean, rstd) saved for backward.  Backward: dx (dtype of x),
+ * dgamma/dbeta (D) f32 are ACCUMULATED into (caller zero-fills).  D % 8 == 0, D <= 768. */
+int d2s_layernorm_fwd(const void* x, int x_dtype, const float* gamma, const float* beta, long long rows, int D,
+                      float eps, void* h, int h_dtype, float* stats, d2s_stream_t stream);
+int d2s_layernorm_bwd(const void* dh, int h_dtype, const void* x, int x_dtype, const float* stats, const float* gamma,
+                      long long rows, int D, void* dx, float* dgamma, float* dbeta, d2s_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

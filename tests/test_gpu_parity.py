@@ -364,6 +364,27 @@ def test_add_layernorm_strided_view_and_full_size(ops):
     torch.testing.assert_close(hs.float(), ln(x[:, 1:]).float(), rtol=1.6e-2, atol=1e-2)
 
 
+@pytest.mark.parametrize("xd,hd", [(torch.float32, torch.float32), (torch.float32, torch.bfloat16), (torch.bfloat16, torch.bfloat16)])
+@pytest.mark.parametrize("rows,D", [(3 * 197, 384), (1000, 768), (37, 128), (5, 8)])
+def test_layer_norm_autograd(ops, xd, hd, rows, D):
+    x = (fx.randn(190 + D, rows, D) * 1.5 + 0.3).to(xd)
+    w, b = 1 + 0.1 * fx.randn(191, D), 0.1 * fx.randn(192, D)
+    up = fx.randn(193, rows, D).to(hd)
+    xg, wg, bg = cu(x).requires_grad_(True), cu(w).requires_grad_(True), cu(b).requires_grad_(True)
+    h = ops.layer_norm(xg, wg, bg, 1e-6, out_dtype=hd)
+    assert h.dtype == hd
+    (h.float() * cu(up).float()).sum().backward()
+    x2, w2, b2 = x.double().requires_grad_(True), w.double().requires_grad_(True), b.double().requires_grad_(True)
+    h2 = torch.nn.functional.layer_norm(x2, (D,), w2, b2, 1e-6)
+    (h2 * up.double()).sum().backward()
+    lo = hd == torch.bfloat16 or xd == torch.bfloat16
+    torch.testing.assert_close(h.detach().cpu().double(), h2.detach(), rtol=1.6e-2 if lo else 1e-5, atol=1e-2 if lo else 1e-5)
+    def rel(a, r):
+        return float((a.cpu().double() - r).abs().max() / r.abs().max())
+    assert rel(xg.grad, x2.grad) < (2e-2 if xd == torch.bfloat16 else 1e-4)
+    assert rel(wg.grad, w2.grad) < 1e-4 and rel(bg.grad, b2.grad) < 1e-4
+
+
 # ------------------------------------------------------------------------------------------ predictor body, embed
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("B,N,Cc", [(3, 196, 384), (2, 137, 768), (2, 96, 128), (1, 5, 1536)])
