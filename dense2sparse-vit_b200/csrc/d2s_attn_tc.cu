@@ -23,7 +23,9 @@
 
 namespace d2s {
 
-constexpr int kTcThreads = 160;  // warps 0-3: softmax/epilogue (TMEM lane quadrant = warp id); warp 4: TMA + MMA issue
+// warps [0, kSW): softmax/epilogue (TMEM lane quadrant = warp % 4; with kSW == 8 the two warps of a quadrant split the
+// key columns of every row); warp kSW: TMA + MMA issue
+constexpr int tc_threads(int ksw) { return 32 * (ksw + 1); }
 
 struct TcBars {
   uint64_t q_full[2], k_full[2], v_full, s_full, p_full, o_full, tmem_free;
@@ -33,13 +35,15 @@ struct TcBars {
 
 // kNT  : 128-row tiles per unit (1: T <= 128, 2: T <= 256)
 // kPol : policy given (eps terms, masked exponentials, colsum(V))
-template <int kNT, bool kPol>
-__global__ void __launch_bounds__(kTcThreads, kNT == 1 ? 4 : 2)
+template <int kNT, bool kPol, int kSW>
+__global__ void __launch_bounds__(tc_threads(kSW), kNT == 1 ? 4 : 2)
 attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                    const float* __restrict__ policy, int num_units, int T, int H, int Tkp, int kbufs, float scale,
                    float eps, __nv_bfloat16* __restrict__ out, float* __restrict__ cls_row) {
   constexpr int kTmemCols = kNT == 1 ? 128 : 256;
-  constexpr int kOCol = kNT == 1 ? 64 : 128;  // O accumulator columns: beyond the packed-P columns [0, Tkp/2)
+  // O accumulator columns: beyond the packed-P columns.  One softmax warp per row: P at [0, Tkp/2).  Two warps per row
+  // (kSW == 8): the second column half writes its P over ITS OWN consumed S columns, at [16*ceil(n/2), ...) <= 192.
+  constexpr int kOCol = kNT == 1 ? 64 : (kSW == 8 ? 192 : 128);
   extern __shared__ unsigned char smem_dyn[];
   // SWIZZLE_128B atoms are 1024 B and address based: align the tile region.  Every buffer is a whole number of
   // 8-row atoms.  rows_a = rows of the first TMA box (map_a), rows_b = rows of the second one (map_b, kNT == 2).
@@ -58,6 +62,8 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   float* pol_s = reinterpret_cast<float*>(bars + 1);          // 256
   float* cls_s = pol_s + 256;                                 // 256
   float* vsum_s = cls_s + 256;                                // 64
+  float* sum_s = vsum_s + 64;                                 // 2 x 128 (kSW == 8: partial row sums of the column halves)
+  float* max_s = sum_s + 256;                                 // 2 x 128
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t bytes_a = (uint32_t)rows_a * 128u, bytes_b = (uint32_t)rows_b * 128u;
@@ -69,12 +75,12 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     mbar_init(smem_u32(&bars->k_full[1]), 1);
     mbar_init(smem_u32(&bars->v_full), 1);
     mbar_init(smem_u32(&bars->s_full), 1);
-    mbar_init(smem_u32(&bars->p_full), 128);
+    mbar_init(smem_u32(&bars->p_full), 32 * kSW);
     mbar_init(smem_u32(&bars->o_full), 1);
-    mbar_init(smem_u32(&bars->tmem_free), 128);
+    mbar_init(smem_u32(&bars->tmem_free), 32 * kSW);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 4) {
+  if (warp == kSW) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)),
                  "n"(kTmemCols)
                  : "memory");
@@ -85,7 +91,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   tc_fence_after();
   const uint32_t tmem = bars->tmem_base;
 
-  if (warp == 4) {
+  if (warp == kSW) {
     if (lane == 0) {
       // =============================== control thread: TMA + MMA issue ===============================
       const uint32_t idesc_s = make_idesc(128, Tkp, 0);
@@ -146,9 +152,13 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
           tc_fence_after();
           // fully unrolled issue (T <= 256 => at most 16 K-steps); descriptors advance by constants
           mma_ts_imm<false>(tmem + kOCol, tmem, vd, idesc_o);
+          const int split = kSW == 8 ? (ksteps + 1) / 2 : 16;   // first K-step whose P lives in the second half's region
 #pragma unroll
           for (int ks = 1; ks < 16; ++ks)
-            if (ks < ksteps) mma_ts_imm<true>(tmem + kOCol, tmem + (uint32_t)(ks * 8), vd + (uint64_t)(ks * 128), idesc_o);
+            if (ks < ksteps) {
+              const uint32_t pa = ks < split ? (uint32_t)(ks * 8) : (uint32_t)(split * 16 + (ks - split) * 8);
+              mma_ts_imm<true>(tmem + kOCol, tmem + pa, vd + (uint64_t)(ks * 128), idesc_o);
+            }
           mma_commit(smem_u32(&bars->o_full));
           if (last && has_next) {
             mbar_wait(smem_u32(&bars->o_full), g & 1);  // V is dead once the PV-MMA has completed
@@ -159,8 +169,9 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     }
   } else {
     // ===================================== softmax / epilogue warps =====================================
-    const int r = tid;  // row inside the tile == TMEM lane
-    const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
+    const int quad = warp & 3, half = warp >> 2;   // TMEM lane quadrant; column half (kSW == 8 only)
+    const int r = quad * 32 + lane;                // row inside the tile == TMEM lane
+    const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16);
     const float k2 = scale * 1.4426950408889634f;
     const float c_eps = kPol ? eps / (float)T : 0.0f;
     const float eps_den = kPol ? eps : 0.0f;
@@ -170,8 +181,8 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       const int b = unit / H, h = unit % H;
       if (kPol) {
         // per-unit policy row and column sums of V (for the eps/T term): sum_j V[j][d]
-        asm volatile("bar.sync 1, 128;" ::: "memory");  // previous unit's readers of pol_s / vsum_s are done
-        for (int j = tid; j < 256; j += 128) pol_s[j] = (j < T) ? policy[(size_t)b * T + j] : 0.0f;
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * kSW) : "memory");  // previous unit's readers of pol_s / vsum_s are done
+        for (int j = tid; j < 256; j += 32 * kSW) pol_s[j] = (j < T) ? policy[(size_t)b * T + j] : 0.0f;
         mbar_wait(smem_u32(&bars->v_full), it & 1);
         if (tid < kTcHD) {
           float acc = 0.f;
@@ -180,30 +191,41 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             acc += __bfloat162float(*(reinterpret_cast<const __nv_bfloat16*>(v_s + sw128_off(j, cchunk)) + within));
           vsum_s[tid] = acc;
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * kSW) : "memory");
       }
 #pragma unroll
       for (int t = 0; t < kNT; ++t, ++g) {
         const int i = t * kTileRows + r;                  // query token of this thread
-        const bool warp_active = t * kTileRows + warp * 32 < T;   // whole warp beyond T: nothing to compute
+        const bool warp_active = t * kTileRows + quad * 32 < T;   // whole warp beyond T: nothing to compute
+        // key columns of this warp: all of them (kSW == 4) or one half, split at a 16-column chunk boundary
+        const int ch_lo = (kSW == 8 && half == 1) ? (nchunks + 1) / 2 : 0;
+        const int ch_hi = (kSW == 8 && half == 0) ? (nchunks + 1) / 2 : nchunks;
         mbar_wait(smem_u32(&bars->s_full), g & 1);
         tc_fence_after();
-        float sum = 0.f, eps_scale = 1.0f;
+        float sum = 0.f, mx_true = -INFINITY, mxk = 0.f;
         const bool want_cls = (cls_row != nullptr) && (i == 0);
         if (warp_active) {
-          // ONE pass over S: exponentials against m' = max of the row's first 16 columns, true max tracked on the
-          // side for the (shift-variant) eps terms -- see d2s_attn_tc2.cu for the argument.
+          // ONE pass over S (reading S twice -- row max, then exponentials -- lengthens the serial chain of the tile).
+          // Exponentials are taken against m' = max of the row's first 16 columns, not the row max: softmax is shift
+          // invariant and bf16 keeps fp32's exponent range, so P = 2^(s - m') is as accurate as 2^(s - max).  The true
+          // max is tracked on the side because the reference's eps terms are not shift invariant; they are rescaled by
+          // 2^(max - m') below, which restores the reference formula exactly.  Exponents are clamped at 2^120.
+          // Reference chunk: chunk 0 with one warp per row.  With two warps per row both must derive the SAME m' from
+          // columns neither of them overwrites with P before the other has read them: the last chunk of the first
+          // half (the first half's P ends at column 8*ceil(n/2), below that chunk; the second half's P starts above it).
+          const int ch_ref = kSW == 8 ? (nchunks + 1) / 2 - 1 : 0;
           uint32_t v[16];
-          tmem_ld16_nowait(lane_addr, v);
+          tmem_ld16_nowait(lane_addr + (uint32_t)(ch_ref * 16), v);
           tmem_ld_wait();
           float mx = __uint_as_float(v[0]);
 #pragma unroll
           for (int q = 1; q < 16; ++q)
-            if (q < T) mx = fmaxf(mx, __uint_as_float(v[q]));
-          const float mxk = mx * k2;
+            if (ch_ref * 16 + q < T) mx = fmaxf(mx, __uint_as_float(v[q]));
+          mxk = mx * k2;
+          mx_true = mx;
           float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-          for (int ch = 0; ch < nchunks; ++ch) {
-            if (ch > 0) {
+          for (int ch = ch_lo; ch < ch_hi; ++ch) {
+            if (ch != ch_ref || ch != ch_lo) {   // (the reference chunk is still in registers only if it comes first)
               tmem_ld16_nowait(lane_addr + (uint32_t)(ch * 16), v);
               tmem_ld_wait();
             }
@@ -213,7 +235,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             for (int q = 0; q < 16; ++q) {
               const int j = ch * 16 + q;
               const float sv = __uint_as_float(v[q]);
-              if (kPol && (full || j < T)) mx = fmaxf(mx, sv);
+              if (kPol && (full || j < T)) mx_true = fmaxf(mx_true, sv);
               float e = ex2_approx(fminf(fmaf(sv, k2, -mxk), 120.0f));
               if (kPol) e *= (j == i) ? 1.0f : pol_s[j];
               if (!full && j >= T) e = 0.f;
@@ -228,14 +250,24 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             uint32_t packed[8];
 #pragma unroll
             for (int q = 0; q < 8; ++q) packed[q] = pack_bf16x2(a[2 * q], a[2 * q + 1]);
-            tmem_st8(lane_addr + (uint32_t)(ch * 8), packed);  // P overlays the S columns already consumed
+            // P overlays S columns this warp has already consumed (second column half: its own region, see kOCol)
+            const uint32_t pcol = (kSW == 8 && half == 1) ? (uint32_t)(ch_lo * 16 + (ch - ch_lo) * 8) : (uint32_t)(ch * 8);
+            tmem_st8(lane_addr + pcol, packed);
           }
           sum = (s0 + s1) + (s2 + s3);
-          if (kPol) eps_scale = ex2_approx(fminf(fmaf(mx, k2, -mxk), 120.0f));
         }  // rows of an idle warp are never written out; whatever their P rows hold stays in those rows
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         tc_fence_before();
         mbar_arrive(smem_u32(&bars->p_full));
+        if constexpr (kSW == 8) {
+          // the two column halves of a row exchange their partial sums (and running maxima) through shared memory
+          sum_s[half * kTileRows + r] = sum;
+          if (kPol) max_s[half * kTileRows + r] = mx_true;
+          asm volatile("bar.sync 2, 256;" ::: "memory");
+          sum += sum_s[(half ^ 1) * kTileRows + r];
+          if (kPol) mx_true = fmaxf(mx_true, max_s[(half ^ 1) * kTileRows + r]);
+        }
+        const float eps_scale = (kPol && warp_active) ? ex2_approx(fminf(fmaf(mx_true, k2, -mxk), 120.0f)) : 1.0f;
         const float den = sum + eps_den * eps_scale;
         const float c_eps_row = c_eps * eps_scale;
         if (cls_row != nullptr && t == 0 && warp == 0) {
@@ -246,39 +278,41 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
           for (int j = lane; j < T; j += 32) cls_row[(size_t)unit * T + j] = (cls_s[j] + ce0) / den0;
           __syncwarp();
         }
-        // ---- epilogue -----------------------------------------------------------------------------------
+        // ---- epilogue: this warp's share of the 64 output columns -------------------------------------------
+        constexpr int kOC = kSW == 8 ? 32 : 64;            // output columns per warp
+        const int oc0 = kSW == 8 ? half * 32 : 0;
         mbar_wait(smem_u32(&bars->o_full), g & 1);
         tc_fence_after();
         if constexpr (kNT == 2) {
-          // two tiles per unit: pull the whole output row into registers, release TMEM, then store -- the next
-          // tile's S-MMA overlaps the stores (the 4-CTA/SM variant below has no registers to spare for this)
-          uint32_t ow[32];   // the output row as packed bf16
+          uint32_t ow[kOC / 2];   // packed bf16
           if (warp_active) {
             const float inv = 1.0f / den;
 #pragma unroll
-            for (int ch = 0; ch < kTcHD / 16; ++ch) {
+            for (int ch = 0; ch < kOC / 16; ++ch) {
               uint32_t v[16];
-              tmem_ld16_nowait(lane_addr + (uint32_t)(kOCol + ch * 16), v);
+              tmem_ld16_nowait(lane_addr + (uint32_t)(kOCol + oc0 + ch * 16), v);
               tmem_ld_wait();
 #pragma unroll
               for (int q = 0; q < 8; ++q) {
                 float o0 = __uint_as_float(v[2 * q]), o1 = __uint_as_float(v[2 * q + 1]);
                 if (kPol) {
-                  o0 += c_eps_row * vsum_s[ch * 16 + 2 * q];
-                  o1 += c_eps_row * vsum_s[ch * 16 + 2 * q + 1];
+                  o0 += c_eps_row * vsum_s[oc0 + ch * 16 + 2 * q];
+                  o1 += c_eps_row * vsum_s[oc0 + ch * 16 + 2 * q + 1];
                 }
                 ow[ch * 8 + q] = pack_bf16x2(o0 * inv, o1 * inv);
               }
             }
           }
+          // O is in registers: release TMEM so the next tile's S-MMA overlaps the stores
           tc_fence_before();
-          mbar_arrive(smem_u32(&bars->tmem_free));   // O is in registers: the next S-MMA may overwrite this TMEM region
+          mbar_arrive(smem_u32(&bars->tmem_free));
           if (warp_active && i < T) {
-            uint4* orow = reinterpret_cast<uint4*>(out + ((size_t)b * T + i) * (size_t)(H * kTcHD) + (size_t)h * kTcHD);
+            uint4* orow = reinterpret_cast<uint4*>(out + ((size_t)b * T + i) * (size_t)(H * kTcHD) + (size_t)h * kTcHD + oc0);
 #pragma unroll
-            for (int q = 0; q < 8; ++q) orow[q] = make_uint4(ow[4 * q], ow[4 * q + 1], ow[4 * q + 2], ow[4 * q + 3]);
+            for (int q = 0; q < kOC / 8; ++q) orow[q] = make_uint4(ow[4 * q], ow[4 * q + 1], ow[4 * q + 2], ow[4 * q + 3]);
           }
         } else {
+          // 4 CTAs per SM: no registers to spare for the whole row, store chunk by chunk
           if (warp_active) {
             const float inv = 1.0f / den;
             __nv_bfloat16* orow = out + ((size_t)b * T + min(i, T - 1)) * (size_t)(H * kTcHD) + (size_t)h * kTcHD;
@@ -311,7 +345,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == kSW) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(kTmemCols) : "memory");
   }
@@ -351,13 +385,13 @@ static size_t tc_smem_bytes(int knt, int Tkp, int kbufs) {
   const int rows_a = knt == 1 ? Tkp : kTileRows, rows_b = knt == 1 ? 0 : Tkp - kTileRows;
   (void)rows_a;
   return 1024 + (size_t)(kTileRows + rows_b) * 128 + (size_t)(kbufs + 1) * Tkp * 128 + sizeof(TcBars) +
-         (256 + 256 + 64) * sizeof(float);
+         (256 + 256 + 64 + 256 + 256) * sizeof(float);
 }
 
-template <int kNT, bool kPol>
+template <int kNT, bool kPol, int kSW>
 static int launch_tc(const CUtensorMap& map_a, const CUtensorMap& map_b, const float* policy, int units, int T, int H,
                      int Tkp, float scale, float eps, void* out, float* cls_row, cudaStream_t stream) {
-  auto kern = attn_tc_fwd_kernel<kNT, kPol>;
+  auto kern = attn_tc_fwd_kernel<kNT, kPol, kSW>;
   // two K buffers when they still leave room for the intended number of CTAs per SM
   const int per_sm = kNT == 1 ? 4 : 2;
   const size_t budget = (size_t)(228 * 1024) / per_sm - 1024;
@@ -370,7 +404,7 @@ static int launch_tc(const CUtensorMap& map_a, const CUtensorMap& map_b, const f
     smem_set = 113 * 1024;
   }
   const int grid = units < per_sm * kNumSMs ? units : per_sm * kNumSMs;
-  kern<<<grid, kTcThreads, smem, stream>>>(map_a, map_b, policy, units, T, H, Tkp, kbufs, scale, eps,
+  kern<<<grid, tc_threads(kSW), smem, stream>>>(map_a, map_b, policy, units, T, H, Tkp, kbufs, scale, eps,
                                            (__nv_bfloat16*)out, cls_row);
   count_launch();
   return check_launch("d2s_attn_policy_fwd(tcgen05)");
@@ -416,9 +450,9 @@ extern "C" int d2s_attn_policy_fwd(const void* qkv, const float* policy, int dty
   }
   const int units = B * H;
   if (T <= kTileRows) {
-    return policy ? launch_tc<1, true>(map_a, map_b, policy, units, T, H, Tkp, scale, eps, out, cls_row, stream)
-                  : launch_tc<1, false>(map_a, map_b, policy, units, T, H, Tkp, scale, eps, out, cls_row, stream);
+    return policy ? launch_tc<1, true, 4>(map_a, map_b, policy, units, T, H, Tkp, scale, eps, out, cls_row, stream)
+                  : launch_tc<1, false, 4>(map_a, map_b, policy, units, T, H, Tkp, scale, eps, out, cls_row, stream);
   }
-  return policy ? launch_tc<2, true>(map_a, map_b, policy, units, T, H, Tkp, scale, eps, out, cls_row, stream)
-                : launch_tc<2, false>(map_a, map_b, policy, units, T, H, Tkp, scale, eps, out, cls_row, stream);
+  return policy ? launch_tc<2, true, 4>(map_a, map_b, policy, units, T, H, Tkp, scale, eps, out, cls_row, stream)
+                : launch_tc<2, false, 8>(map_a, map_b, policy, units, T, H, Tkp, scale, eps, out, cls_row, stream);
 }
