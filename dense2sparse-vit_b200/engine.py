@@ -11,11 +11,14 @@ Two execution modes, chosen per call:
   * autograd (a gradient is needed): library GEMMs around the one-pass policy-softmax kernel
              (forward + backward in both arguments), gather/scatter kernels, Gumbel decision kernel.
 """
+import os
+
 import torch
 import torch.nn.functional as F
 
 from . import ops
 
+_FUSED_FC1 = os.environ.get("D2S_FUSED_FC1", "1") != "0"   # A/B switch for the tcgen05 fc1+GELU GEMM
 INIT_N = 14 * 14  # the reference hard-codes 196 spatial tokens (dynamic_vit.py:828, default_dynamic_vit.py:446)
 
 
@@ -76,8 +79,12 @@ def mlp_forward(m, h):
     if (isinstance(m.act, torch.nn.GELU) and getattr(m.act, "approximate", "none") == "none"
             and isinstance(m.fc1, torch.nn.Linear) and not _needs_grad(h, m.fc1.weight)
             and (m.drop.p == 0 or not m.training)):
-        u = m.fc1(h)
-        ops.bias_act_(u, None, ops.ACT_GELU)
+        if (_FUSED_FC1 and h.dtype == torch.bfloat16 and m.fc1.weight.dtype == torch.bfloat16 and m.fc1.out_features % 256 == 0
+                and m.fc1.out_features <= 4096 and m.fc1.in_features % 64 == 0):
+            u = ops.linear_act(h, m.fc1.weight, m.fc1.bias, ops.ACT_GELU)   # tcgen05 GEMM, GELU in the epilogue
+        else:
+            u = m.fc1(h)
+            ops.bias_act_(u, None, ops.ACT_GELU)
         return m.fc2(u)
     return m(h)
 

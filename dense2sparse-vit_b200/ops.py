@@ -405,3 +405,20 @@ def layer_norm(x, weight, bias, eps, out_dtype=None):
     if out_dtype is None:
         out_dtype = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else x.dtype
     return _LayerNorm.apply(x, weight, bias, eps, out_dtype)
+
+
+def linear_act(x, weight, bias, act=ACT_GELU):
+    """act(x @ weight^T + bias) in one tcgen05 GEMM with the activation in the epilogue (bf16, inference only).
+    x (..., K) contiguous, weight (N, K), N % 256 == 0, K % 64 == 0."""
+    _check_cuda(x, weight, bias)
+    if x.dtype != torch.bfloat16:
+        raise TypeError("linear_act is a bf16 kernel")
+    xc = x.detach().contiguous()
+    w = weight.detach().to(torch.bfloat16).contiguous()
+    b = None if bias is None else bias.detach().to(torch.bfloat16).contiguous()
+    K = xc.shape[-1]
+    M = xc.numel() // K
+    N = w.shape[0]
+    out = torch.empty(*xc.shape[:-1], N, dtype=torch.bfloat16, device=xc.device)
+    _lib.call("d2s_linear_act_bf16", _ptr(xc), _ptr(w), _ptr(b), M, N, K, int(act), _ptr(out), _stream())
+    return out

@@ -168,6 +168,12 @@ int d2s_add_layernorm(const void* x, const void* y, const void* gamma, const voi
                       long long x_stride_b, long long x_stride_t, float eps, int norm_row0,
                       void* out_sum, void* out_norm, d2s_stream_t stream);
 
+/* Linear + activation in one tcgen05 GEMM (fc1 + GELU of Mlp.forward, dynamic_vit.py:159-175), bf16 only:
+ * out (M,N) = act(a (M,K) @ w (N,K)^T + bias (N)); fp32 accumulation; bias may be NULL.
+ * N % 256 == 0 (N <= 4096), K % 64 == 0. */
+int d2s_linear_act_bf16(const void* a, const void* w, const void* bias, int M, int N, int K, int act, void* out,
+                        d2s_stream_t stream);
+
 /* LayerNorm forward / backward for the training path (norm1 / norm2 / predictor norms of Block.forward,
  * dynamic_vit.py:263-283) with mixed dtypes for bf16 autocast: x (rows,D) f32|bf16 -> h (rows,D) f32|bf16,
  * gamma/beta f32 (D), stats (rows,2) f32 = (mean, rstd) saved for backward.  Backward: dx (dtype of x),

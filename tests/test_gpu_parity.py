@@ -454,6 +454,19 @@ def test_gelu_inplace_matches_exact_erf(ops):
     assert float((outb.cpu().float() != refb.bfloat16().float())[core].float().mean()) < 1e-4
 
 
+@pytest.mark.parametrize("M,N,K,act", [(1000, 1536, 384, 1), (128, 256, 64, 1), (77, 512, 128, 0), (3 * 197, 1536, 384, 2),
+                                       (20000, 1536, 384, 1), (513, 3072, 768, 1)])
+def test_linear_act_gemm(ops, M, N, K, act):
+    x = (fx.randn(200 + M % 97, M, K) * 1.0).bfloat16()
+    w = (fx.randn(201 + N % 89, N, K) / K ** 0.5).bfloat16()
+    b = (fx.randn(202, N) * 0.2).bfloat16()
+    out = ops.linear_act(cu(x), cu(w), cu(b), act)
+    ref = torch.nn.functional.linear(x.float(), w.float(), b.float())       # fp32 accumulate of the same bf16 operands
+    ref = torch.nn.functional.gelu(ref) if act == 1 else (torch.relu(ref) if act == 2 else ref)
+    torch.testing.assert_close(out.cpu().float(), ref, rtol=1e-2, atol=1e-2)
+    assert out.shape == (M, N) and out.dtype == torch.bfloat16
+
+
 def test_score_tail_a_gelu_on_load_and_prev_gather(ops):
     B, N, Cc, K = 4, 196, 96, 137
     raw = fx.randn(170, B, N, Cc)
