@@ -190,6 +190,23 @@ def kernel_breakdown(ops, B, dev, torch, pk):
                          ms=ms, algo_bytes=by, gbs=by / ms / 1e6, tflops=fl / ms / 1e9))
         attn_ms += 3 * ms; attn_bytes += 3 * by; attn_flops += 3 * fl
         del qkv
+        # the other per-block d2s kernels at this token count: residual add + LayerNorm (x2 per block) and the fc1 GEMM
+        # with the GELU epilogue (tensor-pipe kernel: flops quoted next to the bytes)
+        xr = torch.randn(B, T, D, device=dev, dtype=torch.bfloat16)
+        yr = torch.randn(B, T, D, device=dev, dtype=torch.bfloat16)
+        gw, gb = torch.ones(D, device=dev, dtype=torch.bfloat16), torch.zeros(D, device=dev, dtype=torch.bfloat16)
+        ms = time_kernel(lambda: ops.add_layernorm(xr, yr, gw, gb, 1e-6), 20, torch)
+        by = B * T * D * e * 4
+        rows.append(dict(kernel="add_layernorm", shape=f"B={B},T={T},D={D}", launches_per_step=6, ms=ms, algo_bytes=by,
+                         gbs=by / ms / 1e6))
+        w1 = torch.randn(4 * D, D, device=dev, dtype=torch.bfloat16) * 0.05
+        b1 = torch.zeros(4 * D, device=dev, dtype=torch.bfloat16)
+        ms = time_kernel(lambda: ops.linear_act(xr, w1, b1, ops.ACT_GELU), 10, torch)
+        by = B * T * e * (D + 4 * D)
+        fl = 2.0 * B * T * D * 4 * D
+        rows.append(dict(kernel="linear_act(fc1+GELU, tcgen05)", shape=f"M={B * T},N={4 * D},K={D}", launches_per_step=3, ms=ms,
+                         algo_bytes=by, gbs=by / ms / 1e6, tflops=fl / ms / 1e9))
+        del xr, yr, w1
     n_in = N0
     for s, K in enumerate(Ks):
         T_in = n_in + 1

@@ -237,6 +237,55 @@ def predictor_b_hidden(m, x, normed=None):
     return h, norm, lin
 
 
+def _act_code(a):
+    if isinstance(a, torch.nn.ReLU):
+        return ops.ACT_RELU
+    if isinstance(a, torch.nn.GELU) and getattr(a, "approximate", "none") == "none":
+        return ops.ACT_GELU
+    return None
+
+
+def _ln_ok(n, dtype):
+    return _is_plain_ln(n) and n.normalized_shape[0] % 8 == 0 and n.normalized_shape[0] <= (1536 if dtype == torch.bfloat16 else 768)
+
+
+def _predictor_b_fusable(m, dtype):
+    ic, oc = list(m.in_conv), list(m.out_conv)
+    if len(ic) != 3 or len(oc) < 3 or len(oc) % 3 != 0 or not m.topk_selection:
+        return False
+    if not (_is_plain_ln(ic[0]) and isinstance(ic[1], torch.nn.Linear) and _act_code(ic[2]) is not None):
+        return False
+    for i in range(0, len(oc) - 3, 3):
+        if not (_ln_ok(oc[i], dtype) and isinstance(oc[i + 1], torch.nn.Linear) and _act_code(oc[i + 2]) is not None):
+            return False
+    return _is_plain_ln(oc[-3]) and isinstance(oc[-2], torch.nn.Linear) and oc[-2].out_features == 1
+
+
+def _linear_act(x, lin, act):
+    """act(lin(x)): the tcgen05 GEMM with the activation in its epilogue when the shape allows, else cuBLAS + in-place act."""
+    if (x.dtype == torch.bfloat16 and lin.weight.dtype == torch.bfloat16 and lin.out_features % 256 == 0
+            and lin.out_features <= 4096 and lin.in_features % 64 == 0):
+        return ops.linear_act(x, lin.weight, lin.bias, act)
+    u = lin(x)
+    return ops.bias_act_(u, None, act)
+
+
+def predictor_b_select_fused(m, normed, k):
+    """Inference form of Variant B's PredictorLG.forward + selection (dynamic_vit.py:536-560, :858-862) for the LayerNorm
+    architectures: Linear+activation as one GEMM (or cuBLAS + in-place activation), the mean-pool / expand / concat as
+    one in-place kernel, every inner LayerNorm as the d2s kernel, LayerNorm+Linear(.,1)+softmax+top-k in the tail."""
+    z = _linear_act(normed, m.in_conv[1], _act_code(m.in_conv[2]))
+    h = ops.pool_concat_(z)
+    oc = list(m.out_conv)
+    for i in range(0, len(oc) - 3, 3):
+        _, hn = ops.add_layernorm(h, None, oc[i].weight, oc[i].bias, oc[i].eps, want_sum=False)
+        h = _linear_act(hn, oc[i + 1], _act_code(oc[i + 2]))
+    norm, lin = oc[-3], oc[-2]
+    prob_mode = ops.PROB_SOFTMAX if m.loss_type in ["kl_div", "mse"] else ops.PROB_SIGMOID
+    scores, probs, kept, dropped = ops.score_tail_b(h, norm.weight, norm.bias, lin.weight, lin.bias, k, norm.eps, prob_mode)
+    return scores.to(normed.dtype), probs.to(normed.dtype), kept, dropped
+
+
 def predictor_b_forward(m, x, policy=None, current_sigma=0.0005, cls_attn=None, k_select=None, normed=None):
     """Returns (scores, keep_probs) like the reference; with k_select also (kept, dropped) from the fused
     tail kernel.  Like the reference, only the topk_selection=True configuration is defined (:537)."""
@@ -370,7 +419,10 @@ def variant_b_forward(model, img, stacked_cls_attn_weights=None):
                 ln = _pred_ln(pred)
                 if ln is not None and pred.topk_selection and not _needs_grad(st.x, st.y, ln.weight):
                     x, hn = st.normed(ln, row0=1)
-                    pred_logits, pred_score, kept, dropped = predictor_b_forward(pred, None, k_select=num_keep_node, normed=hn)
+                    if _predictor_b_fusable(pred, hn.dtype):
+                        pred_logits, pred_score, kept, dropped = predictor_b_select_fused(pred, hn, num_keep_node)
+                    else:
+                        pred_logits, pred_score, kept, dropped = predictor_b_forward(pred, None, k_select=num_keep_node, normed=hn)
                 else:
                     x = st.value()
                     pred_logits, pred_score, kept, dropped = predictor_b_forward(pred, x[:, 1:], k_select=num_keep_node)

@@ -344,6 +344,16 @@ def bias_act_(u, bias, act=ACT_GELU):
     return u
 
 
+def pool_concat_(z):
+    """In place: z (B,N,C) <- cat(z[..., :C/2], mean over tokens of z[..., C/2:] broadcast) (dynamic_vit.py:539-545)."""
+    _check_cuda(z)
+    if not z.is_contiguous():
+        raise ValueError("pool_concat_ works in place on a contiguous tensor")
+    B, N, C = z.shape
+    _lib.call("d2s_pool_concat_inplace", _ptr(z), _dtype_code(z), B, N, C, _stream())
+    return z
+
+
 def assemble_tokens(patches, cls_token, pos_embed):
     """cat(cls_token.expand(B,-1,-1), patches) + pos_embed in one pass (vit_models/dynamic_vit.py:820-823)."""
     _check_cuda(patches, cls_token, pos_embed)

@@ -147,6 +147,8 @@ int d2s_attn_policy_fwd(const void* qkv, const float* policy, int dtype, int B, 
 int d2s_pool_act(const void* z, const float* policy, int dtype, int B, int N, int C, int act, void* local, void* pooled,
                  d2s_stream_t stream);
 int d2s_bias_act(void* u, const void* bias, int dtype, long long rows, int N, int C, int act, d2s_stream_t stream);
+/* Variant B's concat (dynamic_vit.py:539-545) in place: z (B,N,C) <- cat(z[:,:,:C/2], mean_n(z[:,:,C/2:]).expand). */
+int d2s_pool_concat_inplace(void* z, int dtype, int B, int N, int C, d2s_stream_t stream);
 
 /* ---- token assembly (dynamic_vit.py:816-824; default_dynamic_vit.py:437-442) -----------------------------------
  * out (B,N+1,D) = cat(cls (D) broadcast, patches (B,N,D)) + pos (N+1,D), one pass instead of concat + add. */

@@ -421,6 +421,20 @@ def test_bias_act_and_split_linear_identity(ops, dtype):
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("B,N,Cc", [(3, 196, 1536), (2, 137, 384), (2, 5, 64)])
+def test_pool_concat_inplace(ops, dtype, B, N, Cc):
+    if dtype == torch.float32 and Cc > 1024:
+        pytest.skip("fp32 rows are limited")
+    z = torch.relu(fx.randn(165 + Cc, B, N, Cc)).to(dtype)
+    half = Cc // 2
+    ref = torch.cat([z[..., :half], z[..., half:].float().mean(dim=1, keepdim=True).to(dtype).expand(B, N, half)], dim=-1)
+    out = ops.pool_concat_(cu(z).clone())
+    assert torch.equal(out.cpu()[..., :half], ref[..., :half])
+    torch.testing.assert_close(out.cpu()[..., half:].float(), ref[..., half:].float(), rtol=1e-2 if dtype == torch.bfloat16 else 1e-5,
+                               atol=1e-2 if dtype == torch.bfloat16 else 1e-6)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_assemble_tokens(ops, dtype):
     B, N, D = 5, 196, 384
     pe, cls, pos = fx.randn(160, B, N, D).to(dtype), fx.randn(161, 1, 1, D).to(dtype), fx.randn(162, 1, N + 1, D).to(dtype)
