@@ -326,6 +326,7 @@ def run_gpu(args):
         return
 
     # ---- rank 0: per-kernel breakdown, roofline, cpu baseline ----------------------------------------
+    time.sleep(2.0)   # kernels are timed alone against the BURST peaks: let the clocks recover from the sustained loop
     rows, roof = kernel_breakdown(pkg.ops, B, dev, torch, pk)
     own_ms = sum(r["ms"] * r["launches_per_step"] for r in rows)
     line = {
