@@ -7,12 +7,12 @@
 //   warp 0      TMA producer: A tile 128x64 and W tile 256x64 (bf16, SWIZZLE_128B) into a 3-stage ring
 //   warp 1      MMA issuer: tcgen05.mma.kind::f16 M=128 N=256 K=16, accumulators double-buffered in TMEM (2 x 256 columns)
 //   warps 2-9   epilogue: two warps per TMEM lane quadrant (128 output columns each): tcgen05.ld -> +bias -> GELU (erf
-//               form, MUFU rcp/ex2 erf accurate to ~5e-7) -> bf16 -> swizzled shared-memory block -> TMA store (one
+//               form: erfcx polynomial x one MUFU.EX2, packed fp32x2 arithmetic) -> bf16 -> swizzled shared-memory block -> TMA store (one
 //               instruction per 128x64 block; per-thread global stores of 16 bytes cost 32 LSU wavefronts per warp
 //               instruction and made the first version of this kernel store-bound)
 // A CTA walks its 128-row tiles with the N tiles innermost, so the A tile is re-read from L2, never from HBM.
-// The epilogue is the binding stage (GELU costs ~18 FP32 + 2 MUFU instructions per element against 384 MACs on the
-// tensor pipe), which is why it gets eight warps and runs concurrently with the next tile's MMAs.
+// The epilogue is the binding stage (GELU against 384 MACs per element on the tensor pipe), which is why it gets eight
+// warps, packed fp32x2 arithmetic and runs concurrently with the next tile's MMAs.
 #include "d2s_tc.cuh"
 
 namespace d2s {
@@ -27,26 +27,6 @@ struct GgBars {
   uint32_t tmem_base;
   uint32_t pad;
 };
-
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
-  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-               ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1) : "memory");
-}
-
-__device__ __forceinline__ float gelu_erf_fast(float x) {
-  const float z = x * 0.70710678118654752440f;
-  const float az = fabsf(z);
-  float t, e;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, az, 1.0f)));
-  float p = fmaf(1.061405429f, t, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
-  p *= t;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * az * az));
-  const float pe = p * e;                       // erfc(|z|)
-  return 0.5f * x * (z < 0.f ? pe : 2.0f - pe);  // 1 + erf(z)
-}
 
 __global__ void __launch_bounds__(kGgThreads, 1)
 gemm_bias_gelu_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
@@ -148,10 +128,12 @@ gemm_bias_gelu_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
             uint32_t o[16];
 #pragma unroll
             for (int q = 0; q < 16; ++q) {
-              float x0 = __uint_as_float(v[2 * q]) + bias_s[col0 + sb * 64 + c * 32 + 2 * q];
-              float x1 = __uint_as_float(v[2 * q + 1]) + bias_s[col0 + sb * 64 + c * 32 + 2 * q + 1];
-              if (act == D2S_ACT_GELU) { x0 = gelu_erf_fast(x0); x1 = gelu_erf_fast(x1); }
-              else if (act == D2S_ACT_RELU) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
+              const float2 bq = *reinterpret_cast<const float2*>(&bias_s[col0 + sb * 64 + c * 32 + 2 * q]);
+              uint64_t xp = f2_add(f2_pack(__uint_as_float(v[2 * q]), __uint_as_float(v[2 * q + 1])), f2_pack(bq.x, bq.y));
+              float x0, x1;
+              if (act == D2S_ACT_GELU) xp = gelu_erf_pair(xp);
+              f2_unpack(xp, x0, x1);
+              if (act == D2S_ACT_RELU) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
               o[q] = pack_bf16x2(x0, x1);
             }
 #pragma unroll
@@ -180,22 +162,6 @@ gemm_bias_gelu_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512) : "memory");
   }
-}
-
-typedef CUresult (*GgEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static GgEncodeFn gg_encode_fn() {
-  static GgEncodeFn fn = nullptr;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<GgEncodeFn>(p);
-  }
-  return fn;
 }
 
 }  // namespace d2s

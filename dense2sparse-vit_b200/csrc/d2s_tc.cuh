@@ -140,4 +140,82 @@ __device__ __forceinline__ uint32_t sw128_off(int r, int c) {
   return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4));
 }
 
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+
+
+// ---- packed fp32x2 arithmetic (sm_100: one FFMA2/FMUL2/FADD2 issue slot handles two elements) ----
+__device__ __forceinline__ uint64_t f2_pack(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ uint64_t f2_mul(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t f2_bcast(float c) { return f2_pack(c, c); }
+
+// Exact-erf GELU (nn.GELU(), dynamic_vit.py:162) for two elements: GELU(x) = x * Phi(x),
+//     Phi(x) = 0.5 erfc(-x / sqrt 2) = (x < 0) ? h : 1 - h,   h = 0.5 erfcx(z) exp(-z^2),  z = |x| / sqrt 2.
+// 0.5 erfcx(z) is a degree-8 polynomial on [0, 4] (relative error 2.2e-4 = 1/18 of a bf16 ulp; z is clamped, which only
+// affects |GELU| < 4e-8), exp(-z^2) one MUFU.EX2: relative error <= 2.9e-4 for x >= -5.6 including the negative tail,
+// absolute error <= 3.8e-5.  One MUFU and ~12 issue slots per element instead of two MUFU and ~23.
+__device__ __forceinline__ uint64_t gelu_erf_pair(uint64_t x) {
+  float x0, x1;
+  f2_unpack(x, x0, x1);
+  const uint64_t z = f2_pack(fminf(fabsf(x0), 5.6568542f) * 0.70710678118654752440f,
+                             fminf(fabsf(x1), 5.6568542f) * 0.70710678118654752440f);
+  uint64_t r = f2_fma(f2_bcast(5.530026916e-05f), z, f2_bcast(-1.097045025e-03f));
+  r = f2_fma(r, z, f2_bcast(9.396236795e-03f));
+  r = f2_fma(r, z, f2_bcast(-4.589582154e-02f));
+  r = f2_fma(r, z, f2_bcast(1.431557016e-01f));
+  r = f2_fma(r, z, f2_bcast(-3.057375131e-01f));
+  r = f2_fma(r, z, f2_bcast(4.743211943e-01f));
+  r = f2_fma(r, z, f2_bcast(-5.602525492e-01f));
+  r = f2_fma(r, z, f2_bcast(4.998897176e-01f));
+  float a0, a1;
+  f2_unpack(f2_mul(f2_mul(x, x), f2_bcast(-0.72134752044448170368f)), a0, a1);   // -x^2/2 * log2(e)
+  const uint64_t h = f2_mul(r, f2_pack(ex2_approx(a0), ex2_approx(a1)));
+  const uint64_t omh = f2_fma(h, f2_bcast(-1.0f), f2_bcast(1.0f));
+  float h0, h1, g0, g1;
+  f2_unpack(h, h0, h1);
+  f2_unpack(omh, g0, g1);
+  return f2_mul(x, f2_pack(x0 < 0.f ? h0 : g0, x1 < 0.f ? h1 : g1));
+}
+
+
+typedef CUresult (*GgEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static inline GgEncodeFn gg_encode_fn() {
+  static GgEncodeFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<GgEncodeFn>(p);
+  }
+  return fn;
+}
+
+
 }  // namespace d2s

@@ -19,6 +19,7 @@ import torch.nn.functional as F
 from . import ops
 
 _FUSED_FC1 = os.environ.get("D2S_FUSED_FC1", "1") != "0"   # A/B switch for the tcgen05 fc1+GELU GEMM
+_FUSED_PAIR = os.environ.get("D2S_FUSED_PAIR", "1") != "0"  # A/B switch for the CTA-pair GEMMs (fc1 pair; proj/fc2 + add + LN)
 INIT_N = 14 * 14  # the reference hard-codes 196 spatial tokens (dynamic_vit.py:828, default_dynamic_vit.py:446)
 
 
@@ -43,8 +44,8 @@ def patch_embed_forward(m, img):
     return F.linear(patches, w.view(w.shape[0], -1), m.proj.bias)
 
 
-def attention_forward(m, x, policy=None, return_cls_attn=False):
-    """Attention.forward (dynamic_vit.py:216-236 / default_dynamic_vit.py:201-216)."""
+def attention_pre_proj(m, x, policy=None, return_cls_attn=False):
+    """Attention.forward up to (not including) the output projection (dynamic_vit.py:216-231): (o (B,T,C), cls_attn)."""
     B, T, C = x.shape
     H = m.num_heads
     qkv = m.qkv(x)
@@ -58,6 +59,12 @@ def attention_forward(m, x, policy=None, return_cls_attn=False):
         o, cls_attn = ops.attention_core(qkv, H, policy=policy, scale=m.scale, want_cls_row=return_cls_attn)
         if cls_attn is not None:
             cls_attn = cls_attn.to(x.dtype)
+    return o, cls_attn
+
+
+def attention_forward(m, x, policy=None, return_cls_attn=False):
+    """Attention.forward (dynamic_vit.py:216-236 / default_dynamic_vit.py:201-216)."""
+    o, cls_attn = attention_pre_proj(m, x, policy, return_cls_attn)
     o = m.proj_drop(m.proj(o))
     return (o, cls_attn) if return_cls_attn else o
 
@@ -66,42 +73,46 @@ def _is_plain_ln(n):
     return isinstance(n, torch.nn.LayerNorm) and n.elementwise_affine and n.bias is not None
 
 
+def _drop_off(d, training):
+    return isinstance(d, torch.nn.Identity) or (isinstance(d, torch.nn.Dropout) and (d.p == 0 or not training))
+
+
 def _fusable(m, x, *extra):
     """The carried-residual inference path applies when no gradient is needed and the norms are plain LayerNorms."""
     return (not _needs_grad(x, *extra, m.norm1.weight if hasattr(m.norm1, "weight") else None)
             and x.is_cuda and _is_plain_ln(m.norm1) and _is_plain_ln(m.norm2)
-            and isinstance(m.drop_path, torch.nn.Identity))
+            and isinstance(m.drop_path, torch.nn.Identity) and _drop_off(m.attn.proj_drop, m.training))
+
+
+def _mlp_is_plain(m, h):
+    return (isinstance(m.act, torch.nn.GELU) and getattr(m.act, "approximate", "none") == "none"
+            and isinstance(m.fc1, torch.nn.Linear) and isinstance(m.fc2, torch.nn.Linear)
+            and not _needs_grad(h, m.fc1.weight) and _drop_off(m.drop, m.training))
+
+
+def mlp_hidden(m, h):
+    """act(fc1(h)) of Mlp.forward (dynamic_vit.py:159-175) for inference: the tcgen05 GEMM with the exact-erf GELU in its
+    epilogue when the shapes allow, else cuBLAS + the in-place d2s GELU kernel."""
+    if (_FUSED_FC1 and h.dtype == torch.bfloat16 and m.fc1.weight.dtype == torch.bfloat16 and m.fc1.out_features % 256 == 0
+            and m.fc1.out_features <= 4096 and m.fc1.in_features % 64 == 0):
+        return ops.linear_act(h, m.fc1.weight, m.fc1.bias, ops.ACT_GELU, pair=_FUSED_PAIR)
+    u = m.fc1(h)
+    ops.bias_act_(u, None, ops.ACT_GELU)
+    return u
 
 
 def mlp_forward(m, h):
-    """Mlp.forward (dynamic_vit.py:159-175) for inference: the activation runs in place on fc1's output with the d2s
-    kernel (exact-erf GELU is compute-bound in torch's elementwise kernel)."""
-    if (isinstance(m.act, torch.nn.GELU) and getattr(m.act, "approximate", "none") == "none"
-            and isinstance(m.fc1, torch.nn.Linear) and not _needs_grad(h, m.fc1.weight)
-            and (m.drop.p == 0 or not m.training)):
-        if (_FUSED_FC1 and h.dtype == torch.bfloat16 and m.fc1.weight.dtype == torch.bfloat16 and m.fc1.out_features % 256 == 0
-                and m.fc1.out_features <= 4096 and m.fc1.in_features % 64 == 0):
-            u = ops.linear_act(h, m.fc1.weight, m.fc1.bias, ops.ACT_GELU)   # tcgen05 GEMM, GELU in the epilogue
-        else:
-            u = m.fc1(h)
-            ops.bias_act_(u, None, ops.ACT_GELU)
-        return m.fc2(u)
+    """Mlp.forward (dynamic_vit.py:159-175) for inference."""
+    if _mlp_is_plain(m, h):
+        return m.fc2(mlp_hidden(m, h))
     return m(h)
 
 
-def block_forward_carry(m, x, y, policy=None, return_cls_attn=False):
-    """Inference form of Block.forward (dynamic_vit.py:263-283) with the residual adds folded into the LayerNorms:
-    takes the residual stream x and a pending branch output y (None at the first block), returns
-    (x', y', cls_attn) where x' + y' is the block's output.  Two d2s add+LayerNorm launches replace two adds and
-    two LayerNorms."""
-    x, h = ops.add_layernorm(x, y, m.norm1.weight, m.norm1.bias, m.norm1.eps)
-    cls_attn = None
-    if return_cls_attn:
-        a, cls_attn = attention_forward(m.attn, h, policy=policy, return_cls_attn=True)
-    else:
-        a = attention_forward(m.attn, h, policy=policy)
-    x, h = ops.add_layernorm(x, a, m.norm2.weight, m.norm2.bias, m.norm2.eps)
-    return x, mlp_forward(m.mlp, h), cls_attn
+def _pair_ok(lin, a, x):
+    """The CTA-pair GEMM with residual + LayerNorm epilogue applies: bf16, whole rows (D in {192, 384}) fit one CTA's TMEM."""
+    return (_FUSED_PAIR and isinstance(lin, torch.nn.Linear) and a.dtype == torch.bfloat16 and x.dtype == torch.bfloat16
+            and lin.weight.dtype == torch.bfloat16 and lin.out_features in (192, 384) and lin.in_features % 64 == 0
+            and x.shape[-1] == lin.out_features and a.shape[:-1] == x.shape[:-1])
 
 
 def norm_forward(n, x):
@@ -116,8 +127,9 @@ def norm_forward(n, x):
 def block_forward(m, x, policy=None, return_cls_attn=False):
     """Block.forward (dynamic_vit.py:263-283)."""
     if _fusable(m, x, policy):
-        x, y, cls_attn = block_forward_carry(m, x, None, policy, return_cls_attn)
-        x = x + y
+        st = _Stream(x)
+        cls_attn = st.block(m, policy, return_cls_attn)
+        x = st.value()
         return (x, cls_attn) if return_cls_attn else x
     if return_cls_attn:
         y, cls_attn = attention_forward(m.attn, norm_forward(m.norm1, x), policy=policy, return_cls_attn=True)
@@ -129,20 +141,50 @@ def block_forward(m, x, policy=None, return_cls_attn=False):
 
 
 class _Stream:
-    """Residual stream of the model-level inference loops: x plus a pending branch output y (x + y is the value the
-    reference holds in `x`).  Falls back to plain Block.forward when the fused path does not apply."""
+    """Residual stream of the model-level inference loops: x plus a pending branch (x + branch is the value the reference
+    holds in `x`).  The branch is either a tensor y or a deferred Linear `lin = (a, module)` (attn.proj / mlp.fc2), so
+    that the next consumer can run it as ONE kernel with the residual add and its LayerNorm (ops.linear_residual_ln).
+    Falls back to plain Block.forward when the fused path does not apply."""
 
     def __init__(self, x):
-        self.x, self.y = x, None
+        self.x, self.y, self.lin = x, None, None
+
+    def _flush_lin(self):
+        if self.lin is not None:
+            a, lin = self.lin
+            self.y, self.lin = lin(a), None
 
     def value(self):
+        self._flush_lin()
         if self.y is not None:
             self.x, self.y = self.x + self.y, None
         return self.x
 
+    def _sum_norm(self, norm, row0=0):
+        """(x + branch, norm((x + branch)[:, row0:])); leaves the stream holding the summed x."""
+        if self.lin is not None and _pair_ok(self.lin[1], self.lin[0], self.x):
+            (a, lin), self.lin = self.lin, None
+            if row0 == 0:
+                self.x, h = ops.linear_residual_ln(a, lin.weight, lin.bias, self.x, norm.weight, norm.bias, norm.eps)
+                return self.x, h
+            self.x, _ = ops.linear_residual_ln(a, lin.weight, lin.bias, self.x, want_norm=False)
+        self._flush_lin()
+        self.x, h = ops.add_layernorm(self.x, self.y, norm.weight, norm.bias, norm.eps, norm_row0=row0)
+        self.y = None
+        return self.x, h
+
     def block(self, blk, policy=None, return_cls_attn=False):
+        """Inference form of Block.forward (dynamic_vit.py:263-283): every residual add is folded into the LayerNorm that
+        follows it, and the Linear that produced the branch into the same kernel when it can be."""
         if _fusable(blk, self.x, policy):
-            self.x, self.y, cls_attn = block_forward_carry(blk, self.x, self.y, policy, return_cls_attn)
+            _, h = self._sum_norm(blk.norm1)
+            o, cls_attn = attention_pre_proj(blk.attn, h, policy, return_cls_attn)
+            self.lin = (o, blk.attn.proj)
+            _, h = self._sum_norm(blk.norm2)
+            if _mlp_is_plain(blk.mlp, h):
+                self.lin = (mlp_hidden(blk.mlp, h), blk.mlp.fc2)
+            else:
+                self.y = blk.mlp(h)
             return cls_attn
         out = block_forward(blk, self.value(), policy, return_cls_attn)
         if return_cls_attn:
@@ -154,16 +196,18 @@ class _Stream:
     def normed(self, norm, row0=0, rows=None):
         """(x + y, norm((x + y)[:, row0:])) with the add folded in; leaves the stream holding the summed x."""
         if _is_plain_ln(norm) and self.x.is_cuda and not _needs_grad(self.x, self.y, norm.weight):
-            self.x, h = ops.add_layernorm(self.x, self.y, norm.weight, norm.bias, norm.eps, norm_row0=row0)
-            self.y = None
-            return self.x, h
+            return self._sum_norm(norm, row0)
         x = self.value()
         return x, norm(x[:, row0:])
 
     def cls_normed(self, norm):
         """norm(x + y)[:, 0]: only the CLS row (what the eval heads consume)."""
         if _is_plain_ln(norm) and self.x.is_cuda and not _needs_grad(self.x, self.y, norm.weight):
-            y0 = None if self.y is None else self.y[:, :1].contiguous()
+            if self.lin is not None:                     # the last fc2 is only needed for the CLS rows
+                a, lin = self.lin
+                y0 = lin(a[:, :1])
+            else:
+                y0 = None if self.y is None else self.y[:, :1].contiguous()
             _, h = ops.add_layernorm(self.x[:, :1], y0, norm.weight, norm.bias, norm.eps, want_sum=False)
             return h[:, 0]
         return norm(self.value())[:, 0]

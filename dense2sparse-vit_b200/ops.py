@@ -417,7 +417,7 @@ def layer_norm(x, weight, bias, eps, out_dtype=None):
     return _LayerNorm.apply(x, weight, bias, eps, out_dtype)
 
 
-def linear_act(x, weight, bias, act=ACT_GELU):
+def linear_act(x, weight, bias, act=ACT_GELU, pair=False):
     """act(x @ weight^T + bias) in one tcgen05 GEMM with the activation in the epilogue (bf16, inference only).
     x (..., K) contiguous, weight (N, K), N % 256 == 0, K % 64 == 0."""
     _check_cuda(x, weight, bias)
@@ -430,5 +430,33 @@ def linear_act(x, weight, bias, act=ACT_GELU):
     M = xc.numel() // K
     N = w.shape[0]
     out = torch.empty(*xc.shape[:-1], N, dtype=torch.bfloat16, device=xc.device)
-    _lib.call("d2s_linear_act_bf16", _ptr(xc), _ptr(w), _ptr(b), M, N, K, int(act), _ptr(out), _stream())
+    fn = "d2s_linear_act_pair_bf16" if pair else "d2s_linear_act_bf16"
+    _lib.call(fn, _ptr(xc), _ptr(w), _ptr(b), M, N, K, int(act), _ptr(out), _stream())
     return out
+
+
+def linear_residual_ln(a, weight, bias, x, ln_weight=None, ln_bias=None, eps=1e-5, want_norm=True):
+    """(x', h) with x' = x + (a @ weight^T + bias) and h = LayerNorm(x') * ln_weight + ln_bias (h None when
+    want_norm is False): attn.proj / mlp.fc2 + residual add + the next LayerNorm of Block.forward
+    (vit_models/dynamic_vit.py:263-283) in one CTA-pair tcgen05 GEMM.  bf16, inference only; N in {192, 384}."""
+    _check_cuda(a, weight, bias, x, ln_weight, ln_bias)
+    if a.dtype != torch.bfloat16 or x.dtype != torch.bfloat16:
+        raise TypeError("linear_residual_ln is a bf16 kernel")
+    ac = a.detach().contiguous()
+    xc = x.detach().contiguous()
+    w = weight.detach().to(torch.bfloat16).contiguous()
+    b = None if bias is None else bias.detach().to(torch.bfloat16).contiguous()
+    K = ac.shape[-1]
+    M = ac.numel() // K
+    N = w.shape[0]
+    if xc.numel() != M * N:
+        raise RuntimeError(f"linear_residual_ln: residual has {xc.numel()} elements, expected {M}x{N}")
+    g = bt = None
+    if want_norm:
+        g = ln_weight.detach().to(torch.bfloat16).contiguous()
+        bt = ln_bias.detach().to(torch.bfloat16).contiguous()
+    out_sum = torch.empty_like(xc)
+    out_norm = torch.empty_like(xc) if want_norm else None
+    _lib.call("d2s_linear_residual_ln_bf16", _ptr(ac), _ptr(w), _ptr(b), _ptr(xc), _ptr(g), _ptr(bt), float(eps), M, N, K,
+              _ptr(out_sum), _ptr(out_norm), _stream())
+    return out_sum, out_norm

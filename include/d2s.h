@@ -176,6 +176,20 @@ int d2s_add_layernorm(const void* x, const void* y, const void* gamma, const voi
 int d2s_linear_act_bf16(const void* a, const void* w, const void* bias, int M, int N, int K, int act, void* out,
                         d2s_stream_t stream);
 
+/* The same contract on a CTA pair (tcgen05 cta_group::2, 256-row tiles, half of the weight tile per CTA). */
+int d2s_linear_act_pair_bf16(const void* a, const void* w, const void* bias, int M, int N, int K, int act, void* out,
+                             d2s_stream_t stream);
+
+/* Linear + residual add + LayerNorm in one tcgen05 GEMM: attn.proj / mlp.fc2 of Block.forward together with the
+ * residual add and the NEXT LayerNorm (dynamic_vit.py:263-283: x = x + attn(norm1(x)); x = x + mlp(norm2(x))), bf16 only:
+ *   y = bf16(a (M,K) @ w (N,K)^T + bias (N));  out_sum (M,N) = bf16(x (M,N) + y);
+ *   out_norm (M,N) = LayerNorm(out_sum) * gamma + beta (statistics in fp32), or skipped when out_norm is NULL.
+ * Roundings are the reference's (Linear output, residual sum, LayerNorm output each rounded to bf16).
+ * N in {192, 384} (a CTA keeps whole rows in TMEM), K % 64 == 0; x may alias out_sum. */
+int d2s_linear_residual_ln_bf16(const void* a, const void* w, const void* bias, const void* x, const void* gamma,
+                                const void* beta, float eps, int M, int N, int K, void* out_sum, void* out_norm,
+                                d2s_stream_t stream);
+
 /* LayerNorm forward / backward for the training path (norm1 / norm2 / predictor norms of Block.forward,
  * dynamic_vit.py:263-283) with mixed dtypes for bf16 autocast: x (rows,D) f32|bf16 -> h (rows,D) f32|bf16,
  * gamma/beta f32 (D), stats (rows,2) f32 = (mean, rstd) saved for backward.  Backward: dx (dtype of x),

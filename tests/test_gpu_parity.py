@@ -481,6 +481,67 @@ def test_linear_act_gemm(ops, M, N, K, act):
     assert out.shape == (M, N) and out.dtype == torch.bfloat16
 
 
+@pytest.mark.parametrize("M,N,K,act", [(1000, 1536, 384, 1), (256, 256, 64, 1), (77, 512, 128, 0), (3 * 197, 1536, 384, 2),
+                                       (20000, 1536, 384, 1), (513, 3072, 768, 1), (129, 256, 64, 0)])
+def test_linear_act_pair_gemm(ops, M, N, K, act):
+    """CTA-pair (cta_group::2) variant of the fc1 GEMM: same contract, ragged row tails in either CTA of the pair."""
+    x = (fx.randn(210 + M % 97, M, K) * 1.0).bfloat16()
+    w = (fx.randn(211 + N % 89, N, K) / K ** 0.5).bfloat16()
+    b = (fx.randn(212, N) * 0.2).bfloat16()
+    out = ops.linear_act(cu(x), cu(w), cu(b), act, pair=True)
+    ref = torch.nn.functional.linear(x.float(), w.float(), b.float())
+    ref = torch.nn.functional.gelu(ref) if act == 1 else (torch.relu(ref) if act == 2 else ref)
+    torch.testing.assert_close(out.cpu().float(), ref, rtol=1e-2, atol=1e-2)
+    assert out.shape == (M, N) and out.dtype == torch.bfloat16
+
+
+@pytest.mark.parametrize("pair", [False, True])
+def test_gelu_epilogue_is_erf_gelu_to_one_bf16_ulp(ops, pair):
+    """The epilogue's GELU (erfcx polynomial x one ex2) against float64 erf GELU of the exact pre-activation: identity
+    weights make the accumulator exact, so any deviation is the activation's.  <= 1 bf16 ulp down to x = -5.6 (the
+    negative tail included: |GELU| ~ 6e-8 there); below that the polynomial's argument is clamped and only |err| < 1e-8 holds."""
+    K = N = 256
+    xs = torch.linspace(-6.0, 6.0, 512 * K).reshape(512, K).bfloat16()
+    w = torch.eye(N, K).bfloat16()
+    out = ops.linear_act(cu(xs), cu(w), None, 1, pair=pair).cpu().double()
+    x64 = xs.double()
+    ref = 0.5 * x64 * torch.special.erfc(-x64 / 2 ** 0.5)
+    ulp = torch.maximum(ref.abs(), torch.tensor(1e-30, dtype=torch.float64)) * 2.0 ** -8
+    bad = ((out - ref).abs() > 1.001 * ulp) & (x64 >= -5.6)
+    assert not bool(bad.any()), (xs[bad][:5], out[bad][:5], ref[bad][:5])
+    assert float((out - ref).abs()[x64 < -5.6].max()) < 1e-8
+
+
+def _residual_ln_reference(a, w, b, x, g, bt, eps):
+    y = torch.nn.functional.linear(a.float(), w.float(), None if b is None else b.float()).bfloat16()     # Linear output, bf16
+    s = (x.float() + y.float()).bfloat16()                                                              # residual add, bf16
+    return s, y
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 384, 384), (1000, 384, 384), (77, 384, 1536), (3 * 197, 384, 1536), (20000, 384, 384),
+                                   (130, 192, 192), (1000, 192, 768), (5 * 138, 384, 64)])
+def test_linear_residual_ln(ops, M, N, K):
+    """proj / fc2 + residual + next LayerNorm (dynamic_vit.py:263-283) in one kernel vs the three separate bf16 ops."""
+    a = fx.randn(300 + M % 91, M, K).bfloat16()
+    w = (fx.randn(301 + K % 83, N, K) / K ** 0.5).bfloat16()
+    b = (fx.randn(302, N) * 0.2).bfloat16()
+    x = (fx.randn(303 + M % 7, M, N) * 1.5).bfloat16()
+    g = (1.0 + 0.3 * fx.randn(304, N)).bfloat16()
+    bt = (0.2 * fx.randn(305, N)).bfloat16()
+    s, h = ops.linear_residual_ln(cu(a), cu(w), cu(b), cu(x), cu(g), cu(bt), 1e-6)
+    s, h = s.cpu(), h.cpu()
+    s_ref, _ = _residual_ln_reference(a, w, b, x, g, bt, 1e-6)
+    # fp32 accumulation order differs from the CPU matmul: a few results land on the other side of a bf16 rounding boundary
+    torch.testing.assert_close(s.float(), s_ref.float(), rtol=1e-2, atol=1e-2)
+    assert float((s == s_ref).float().mean()) > 0.98
+    # the LayerNorm is exact on the kernel's own residual sum
+    h_ref = torch.nn.functional.layer_norm(s.float(), (N,), g.float(), bt.float(), 1e-6)
+    torch.testing.assert_close(h.float(), h_ref, rtol=8e-3, atol=8e-3)
+    assert float((h == h_ref.bfloat16()).float().mean()) > 0.97
+    s2, none = ops.linear_residual_ln(cu(a), cu(w), cu(b), cu(x), want_norm=False)
+    assert none is None and torch.equal(s2.cpu(), s)
+
+
 def test_score_tail_a_gelu_on_load_and_prev_gather(ops):
     B, N, Cc, K = 4, 196, 96, 137
     raw = fx.randn(170, B, N, Cc)
