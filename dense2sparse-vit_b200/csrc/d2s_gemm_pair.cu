@@ -17,37 +17,56 @@
 //              signalled on the LEADER's `full` barrier (cp.async.bulk.tensor ... .cta_group::2)
 //   warp 1     TMEM allocation (both CTAs); MMA issue (leader only); tcgen05.commit multicast frees the ring slot in
 //              both CTAs and publishes the accumulator to both epilogues
-//   warps 2-9  epilogue (both CTAs), two warps per TMEM lane quadrant splitting the columns
+//   warps 2-17 epilogue (both CTAs), four warps per TMEM lane quadrant splitting the columns
 //
 // MODE_LN keeps the whole 128 x D row tile (D = 192 or 384 <= 512 TMEM columns) in the CTA, so the LayerNorm of the
-// freshly produced residual stream is computed in the same kernel: pass 1 reads the accumulator and the residual tile
-// (TMA-loaded into shared memory), writes x' in place, accumulates sum / sum of squares, releases TMEM (the next tile's
-// MMAs start here), TMA-stores x'; pass 2 normalises in place and TMA-stores h.  The separate add+LayerNorm kernel
-// (8 bytes of traffic per element) and the GEMM's own output round trip disappear.
+// freshly produced residual stream is computed in the same kernel.  Each epilogue thread owns one row and half of its
+// columns and keeps them in registers: the residual rows are fetched with coalesced loads while the MMAs still run and
+// transposed to one-row-per-lane through a 4 KB per-warp buffer; pass 1 reads the accumulator, forms x' and the fp32
+// sum / sum of squares and releases TMEM (the next tile's MMAs start here); x' goes out through the same per-warp
+// transposition as coalesced 128-byte lines; pass 2 normalises the registers and writes h the same way.  No
+// CTA-wide barrier and no tile-sized staging buffer: shared memory goes to a 4-deep operand ring instead (a 96 KB
+// residual tile left only 3 stages = 48 KB of A in flight per SM, too little to cover HBM latency at K = 1536).
+// The separate add+LayerNorm kernel (8 bytes of traffic per element) and the GEMM's own output round trip disappear.
 #include <stdlib.h>
 #include "d2s_tc.cuh"
 
 namespace d2s {
 
-constexpr int kGpBM = 128, kGpBK = 64, kGpThreads = 320;
+constexpr int kGpBM = 128, kGpBK = 64, kGpMaxThreads = 576;   // warp 0 TMA, warp 1 MMA, warps 2.. epilogue (4 x PARTS of them)
 constexpr uint32_t kGpABytes = kGpBM * 128;      // 128 rows x 64 bf16
 constexpr uint32_t kGpBlkBytes = 128 * 128;      // one staged 128 x 64 bf16 block (SWIZZLE_128B)
 
 enum { kGpModeAct = 0, kGpModeLn = 1 };
 
+// clock64 phase totals per epilogue warp (profiling builds only: -DD2S_GEMM_TRACE_BUILD; see scripts/bench_gemm_trace*.py)
+#ifdef D2S_GEMM_TRACE_BUILD
+#define GP_TRACE_DECL(n) long long tr[n] = {}; long long tr_t = clock64();
+#define GP_TRACE(i) { const long long tr_n = clock64(); tr[i] += tr_n - tr_t; tr_t = tr_n; }
+#define GP_TRACE_DUMP(n, tiles) if (p.trace && lane == 0) { long long* dst = p.trace + ((size_t)blockIdx.x * 16 + ew) * 8; \
+    for (int i = 0; i < n; ++i) dst[i] = tr[i]; dst[7] = tiles; }
+#else
+#define GP_TRACE_DECL(n)
+#define GP_TRACE(i)
+#define GP_TRACE_DUMP(n, tiles)
+#endif
+
 template <int MODE, int NSUB> struct GpCfg;
 template <> struct GpCfg<kGpModeAct, 1> {        // fc1: 256-column tiles, accumulator double-buffered
   static constexpr int UN = 256, NSUB = 1, ACC = 2, STAGES = 4, BLOCKS = 4;      // BLOCKS: staging blocks of 16 KB
+  static constexpr int PARTS = 4, MAXREG = 96;     // epilogue warps per TMEM lane quadrant; 2 + 16 warps -> 20 allocated -> 102 regs
 };
 template <> struct GpCfg<kGpModeLn, 2> {         // D = 384: two N = 192 MMAs per k-step, one accumulator
-  static constexpr int UN = 192, NSUB = 2, ACC = 1, STAGES = 3, BLOCKS = 6;
+  static constexpr int UN = 192, NSUB = 2, ACC = 1, STAGES = 4, BLOCKS = 3;
+  static constexpr int PARTS = 3, MAXREG = 128;    // 2 + 12 warps -> 16 allocated -> 128 regs: a thread keeps 4 chunks (64 regs) of its row
 };
 template <> struct GpCfg<kGpModeLn, 1> {         // D = 192
   static constexpr int UN = 192, NSUB = 1, ACC = 1, STAGES = 4, BLOCKS = 3;
+  static constexpr int PARTS = 3, MAXREG = 128;
 };
 
 struct GpBars {
-  uint64_t full[4], empty[4], tmem_full[2], tmem_empty[2], xfull;
+  uint64_t full[4], empty[4], tmem_full[2], tmem_empty[2];
   uint32_t tmem_base;
   uint32_t pad;
 };
@@ -94,6 +113,16 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t sr
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1) : "memory");
 }
+__device__ __forceinline__ uint4 ld_nc16(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ uint32_t add_bf16x2(uint32_t a, uint32_t b) {
+  uint32_t r;
+  asm("add.rn.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
 __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
 
@@ -101,6 +130,9 @@ struct GpParams {
   const __nv_bfloat16* bias;    // (N) or NULL
   const __nv_bfloat16* gamma;   // MODE_LN: (N) or NULL when no LayerNorm output is wanted
   const __nv_bfloat16* beta;
+  const __nv_bfloat16* x;       // MODE_LN: residual input (M,N)
+  __nv_bfloat16* out_sum;       // MODE_LN: x' (M,N)
+  __nv_bfloat16* out_norm;      // MODE_LN: LayerNorm(x') (M,N) or NULL
   float eps;
   int M, N, K, act, want_ln;
   long long* trace;             // D2S_GEMM_TRACE: device buffer for per-warp clock64 phase totals (profiling only)
@@ -108,14 +140,13 @@ struct GpParams {
 };
 
 template <int MODE, int NSUB_, int ACT>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGpThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __maxnreg__((GpCfg<MODE, NSUB_>::MAXREG))
 gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
-                 const __grid_constant__ CUtensorMap map_o,    // MODE_ACT: out; MODE_LN: x' (sum) output
-                 const __grid_constant__ CUtensorMap map_x,    // MODE_LN: residual input
-                 const __grid_constant__ CUtensorMap map_h,    // MODE_LN: LayerNorm output
+                 const __grid_constant__ CUtensorMap map_o,    // MODE_ACT: output (TMA store)
                  const GpParams p) {
   using Cfg = GpCfg<MODE, NSUB_>;
-  constexpr int UN = Cfg::UN, NSUB = Cfg::NSUB, ACC = Cfg::ACC, STAGES = Cfg::STAGES;
+  constexpr int UN = Cfg::UN, NSUB = Cfg::NSUB, ACC = Cfg::ACC, STAGES = Cfg::STAGES, PARTS = Cfg::PARTS;
+  constexpr int kThreads = (2 + 4 * PARTS) * 32;
   constexpr int TN = UN * NSUB;                                 // output columns per tile
   constexpr uint32_t kBSub = (UN / 2) * 128;                    // this CTA's half of one W sub-tile
   constexpr uint32_t kStage = kGpABytes + NSUB * kBSub;
@@ -128,7 +159,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   unsigned char* blocks = ring + STAGES * kStage;               // MODE_ACT: store staging; MODE_LN: x / x' / h tile
   GpBars* bars = reinterpret_cast<GpBars*>(blocks + Cfg::BLOCKS * kGpBlkBytes);
   float* bias_s = reinterpret_cast<float*>(bars + 1);           // N floats (MODE_ACT) / 3 x TN floats (MODE_LN)
-  float2* red_s = reinterpret_cast<float2*>(bias_s + (MODE == kGpModeLn ? 3 * TN : p.N));   // MODE_LN: [2][128] partial stats
+  float2* red_s = reinterpret_cast<float2*>(bias_s + (MODE == kGpModeLn ? 3 * TN : p.N));   // MODE_LN: [PARTS][128] partial stats
+  volatile uint32_t* sel_s = reinterpret_cast<volatile uint32_t*>(red_s + 4 * 128);           // MODE_LN: byte-permute selectors
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t rank = cluster_ctarank();
@@ -138,22 +170,22 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 
   if (tid == 0) {
     for (int i = 0; i < STAGES; ++i) { mbar_init(smem_u32(&bars->full[i]), 1); mbar_init(smem_u32(&bars->empty[i]), 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&bars->tmem_full[i]), 1); mbar_init(smem_u32(&bars->tmem_empty[i]), 16); }
-    mbar_init(smem_u32(&bars->xfull), 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&bars->tmem_full[i]), 1); mbar_init(smem_u32(&bars->tmem_empty[i]), 8 * PARTS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if (MODE == kGpModeLn) { sel_s[0] = 0x1044u; sel_s[1] = 0x3244u; }   // {0, 0, b0, b1} and {0, 0, b2, b3}
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)), "n"(512) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
   }
   if (MODE == kGpModeLn) {
-    for (int i = tid; i < TN; i += kGpThreads) {
+    for (int i = tid; i < TN; i += kThreads) {
       bias_s[i] = p.bias ? __bfloat162float(p.bias[i]) : 0.f;
       bias_s[TN + i] = p.gamma ? __bfloat162float(p.gamma[i]) : 1.f;
       bias_s[2 * TN + i] = p.beta ? __bfloat162float(p.beta[i]) : 0.f;
     }
   } else {
-    for (int i = tid; i < p.N; i += kGpThreads) bias_s[i] = p.bias ? __bfloat162float(p.bias[i]) : 0.f;
+    for (int i = tid; i < p.N; i += kThreads) bias_s[i] = p.bias ? __bfloat162float(p.bias[i]) : 0.f;
   }
   tc_fence_before();
   __syncthreads();
@@ -214,195 +246,214 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     }
   } else {
     // ========================================= epilogue (both CTAs) =========================================
-    const int ew = warp - 2;                    // 0..7
-    const int quad = warp & 3;                  // TMEM lane quadrant this warp may touch (warp id % 4)
-    const int hc = ew >> 2;                     // which half of the tile's columns
+    // 4 x PARTS warps: PARTS per TMEM lane quadrant (a warp may only touch lanes 32 (warp % 4) ...), each taking 1/PARTS of the columns
+    const int ew = warp - 2;                    // 0..4*PARTS-1
+    const int quad = warp & 3;                  // TMEM lane quadrant of this warp
+    const int part = ew >> 2;                   // which share of the columns
     const int r = quad * 32 + lane;             // row inside this CTA's 128-row tile
     const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16);
     uint32_t tile = 0;
 
     if (MODE == kGpModeAct) {
-      long long tr[5] = {0, 0, 0, 0, 0};
-      const int gtid = tid - 64 - hc * 128;     // 0..127 inside this column-half group (4 warps)
+      // part p owns the 64-column block p of every 256-column tile: one staging block, one TMA store per tile
+      GP_TRACE_DECL(5)
+      const bool issuer = (ew & 3) == 0 && lane == 0;
+      unsigned char* blk = blocks + (size_t)part * kGpBlkBytes;
       for (int pt = pair; pt < pair_tiles; pt += num_pairs) {
         const int row0 = pt * 2 * kGpBM + (int)rank * kGpBM;
         for (int nt = 0; nt < n_tiles; ++nt, ++tile) {
           const uint32_t as = tile % ACC, an = tile / ACC;
-          long long t0 = clock64();
           mbar_wait(smem_u32(&bars->tmem_full[as]), an & 1);
           tc_fence_after();
-          long long t1 = clock64();
-          tr[0] += t1 - t0;
-          const int col0 = nt * TN + hc * (TN / 2);
-          const uint32_t taddr = lane_addr + as * kAccCols + hc * (TN / 2);
+          GP_TRACE(0)
+          const int col0 = nt * TN + part * 64;
+          const uint32_t taddr = lane_addr + as * kAccCols + part * 64;
+          // the TMA store that last read this block (previous tile) must be done before it is overwritten
+          if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + part) : "memory");
+          GP_TRACE(1)
 #pragma unroll
-          for (int sb = 0; sb < TN / 128; ++sb) {     // 64-column store blocks of this half
-            unsigned char* blk = blocks + (size_t)(hc * 2 + (sb & 1)) * kGpBlkBytes;
-            // the TMA store that last read this block must be done before it is overwritten
-            t0 = clock64();
-            if (gtid == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-            asm volatile("bar.sync %0, 128;" ::"r"(1 + hc) : "memory");
-            t1 = clock64();
-            tr[1] += t1 - t0;
+          for (int c = 0; c < 2; ++c) {
+            if (p.dbg & 2) break;
+            uint32_t v[32];
+            tmem_ld32_nowait(taddr + c * 32, v);
+            tmem_ld_wait();
+            GP_TRACE(2)
+            uint32_t o[16];
 #pragma unroll
-            for (int c = 0; c < 2; ++c) {
-              if (p.dbg & 2) break;
-              uint32_t v[32];
-              t0 = clock64();
-              tmem_ld32_nowait(taddr + sb * 64 + c * 32, v);
-              tmem_ld_wait();
-              t1 = clock64();
-              tr[2] += t1 - t0;
-              uint32_t o[16];
-#pragma unroll
-              for (int q = 0; q < 16; ++q) {
-                const float2 bq = *reinterpret_cast<const float2*>(&bias_s[col0 + sb * 64 + c * 32 + 2 * q]);
-                uint64_t xp = f2_add(f2_pack(__uint_as_float(v[2 * q]), __uint_as_float(v[2 * q + 1])), f2_pack(bq.x, bq.y));
-                float x0, x1;
-                if (ACT == D2S_ACT_GELU) xp = gelu_erf_pair(xp);
-                f2_unpack(xp, x0, x1);
-                if (ACT == D2S_ACT_RELU) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
-                o[q] = pack_bf16x2(x0, x1);
-              }
-#pragma unroll
-              for (int q = 0; q < 4; ++q)
-                *reinterpret_cast<uint4*>(blk + sw128_off(r, c * 4 + q)) = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
-              t0 = clock64();
-              tr[3] += t0 - t1;
+            for (int q = 0; q < 16; ++q) {
+              const float2 bq = *reinterpret_cast<const float2*>(&bias_s[col0 + c * 32 + 2 * q]);
+              uint64_t xp = f2_add(f2_pack(__uint_as_float(v[2 * q]), __uint_as_float(v[2 * q + 1])), f2_pack(bq.x, bq.y));
+              float x0, x1;
+              if (ACT == D2S_ACT_GELU) xp = gelu_erf_pair(xp);
+              f2_unpack(xp, x0, x1);
+              if (ACT == D2S_ACT_RELU) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
+              o[q] = pack_bf16x2(x0, x1);
             }
-            t0 = clock64();
-            if (sb == TN / 128 - 1) {   // all TMEM reads of this accumulator are done: hand it back before the stores drain
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0) mbar_arrive_cluster(mapa(smem_u32(&bars->tmem_empty[as]), 0));
-            }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            asm volatile("bar.sync %0, 128;" ::"r"(1 + hc) : "memory");
-            if (gtid == 0 && !(p.dbg & 1)) {
-              tma_store_2d(&map_o, smem_u32(blk), col0 + sb * 64, row0);
-              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            }
-            t1 = clock64();
-            tr[4] += t1 - t0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              *reinterpret_cast<uint4*>(blk + sw128_off(r, c * 4 + q)) = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+            GP_TRACE(3)
           }
+          // all TMEM reads of this accumulator are done: hand it back before the store drains
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(mapa(smem_u32(&bars->tmem_empty[as]), 0));
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + part) : "memory");
+          if (issuer && !(p.dbg & 1)) {
+            tma_store_2d(&map_o, smem_u32(blk), col0, row0);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+          GP_TRACE(4)
         }
       }
-      if (p.trace && lane == 0) {
-        long long* dst = p.trace + ((size_t)blockIdx.x * 8 + ew) * 8;
-        for (int i = 0; i < 5; ++i) dst[i] = tr[i];
-        dst[5] = tile;
-      }
+      GP_TRACE_DUMP(5, tile)
     } else {
-      // ---- MODE_LN: n_tiles == 1, TN == N ----
-      constexpr int NCH = TN / 32;              // 32-column chunks per row; this thread owns chunks [hc*NCH/2, (hc+1)*NCH/2)
+      // ---- MODE_LN: n_tiles == 1, TN == N.  This thread owns row r and the 64-column blocks b = PARTS bi + part (whole
+      // 128-byte lines), and keeps its x / x' values in registers (BPT x 32 packed bf16 pairs). ----
+      constexpr int NBLK = TN / 64, BPT = NBLK / PARTS;
+      static_assert(MODE != kGpModeLn || NBLK % PARTS == 0, "column blocks must split evenly over the epilogue warps");
       const float* gamma_s = bias_s + TN;
       const float* beta_s = bias_s + 2 * TN;
-      const uint32_t xfull = smem_u32(&bars->xfull);
-      if (tid == 64 && pair < pair_tiles) {     // residual tile of the first row tile
-        mbar_expect_tx(xfull, Cfg::BLOCKS * kGpBlkBytes);
-        for (int b = 0; b < Cfg::BLOCKS; ++b)
-          tma_load_2d(smem_u32(blocks + b * kGpBlkBytes), &map_x, b * 64, pair * 2 * kGpBM + (int)rank * kGpBM, xfull);
-      }
+      unsigned char* buf = blocks + ew * 4096;                  // per-warp [32 rows x 128 B] transposition buffer
+      const int crow = lane >> 3, cseg = lane & 7;              // coalesced pattern: 8 lanes x 16 B cover one row's 128-byte line
+      const uint32_t co_off = (uint32_t)crow * 128, co_seg = (uint32_t)cseg;
+      const uint32_t own_off = (uint32_t)lane * 128, own_sw = (uint32_t)lane & 7u;
+      GP_TRACE_DECL(7)
       for (int pt = pair; pt < pair_tiles; pt += num_pairs, ++tile) {
-        const int row0 = pt * 2 * kGpBM + (int)rank * kGpBM;
+        const int row0 = pt * 2 * kGpBM + (int)rank * kGpBM + quad * 32;     // first row of this warp
+        // ---- residual rows: coalesced loads (issued before the accumulator is awaited), transposed to one row per lane ----
+        uint32_t xr[BPT][32];      // this thread's values, 2 bf16 per word: first in the coalesced layout, then its own row
+        // element offset of (row0 + crow, column part*64 + cseg*8); block bi / row group i add compile-time constants
+        const size_t goff = (size_t)(row0 + crow) * TN + part * 64 + cseg * 8;
+        const int rows_left = p.M - row0 - crow;                  // row group i is in range iff 4 i < rows_left
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          // rows past M re-read the last valid row (their results are never stored): no predicated loads, no zero fills
+          const int grow = min(row0 + crow + 4 * i, p.M - 1);
+          const __nv_bfloat16* xp = p.x + (size_t)grow * TN + part * 64 + cseg * 8;
+#pragma unroll
+          for (int bi = 0; bi < BPT; ++bi) {
+            const uint4 t = ld_nc16(xp + bi * (PARTS * 64));
+            xr[bi][4 * i] = t.x; xr[bi][4 * i + 1] = t.y; xr[bi][4 * i + 2] = t.z; xr[bi][4 * i + 3] = t.w;
+          }
+        }
+#pragma unroll
+        for (int bi = 0; bi < BPT; ++bi) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i)    // row 4 i + crow: (row & 7) = ((4 i) & 7) + crow
+            *reinterpret_cast<uint4*>(buf + co_off + i * 512 + ((co_seg ^ (uint32_t)((4 * i + crow) & 7)) << 4)) =
+                make_uint4(xr[bi][4 * i], xr[bi][4 * i + 1], xr[bi][4 * i + 2], xr[bi][4 * i + 3]);
+          __syncwarp();
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const uint4 t = *reinterpret_cast<const uint4*>(buf + own_off + (((uint32_t)q ^ own_sw) << 4));
+            xr[bi][4 * q] = t.x; xr[bi][4 * q + 1] = t.y; xr[bi][4 * q + 2] = t.z; xr[bi][4 * q + 3] = t.w;
+          }
+          __syncwarp();
+        }
+        GP_TRACE(0)
         mbar_wait(smem_u32(&bars->tmem_full[0]), tile & 1);
         tc_fence_after();
-        mbar_wait(xfull, tile & 1);
-        // ---- pass 1: x' = bf16(x + bf16(acc + bias)) in place, fp32 sum / sum of squares of the rounded values ----
+        GP_TRACE(1)
+        // ---- pass 1: x' = bf16(x + bf16(acc + bias)) in registers, fp32 sum / sum of squares of the rounded values ----
         uint64_t acc_s = f2_bcast(0.f), acc_q = f2_bcast(0.f);
-#pragma unroll 2
-        for (int ci = 0; ci < NCH / 2; ++ci) {
-          const int ch = hc * (NCH / 2) + ci;
-          uint32_t v[32];
-          tmem_ld32_nowait(lane_addr + ch * 32, v);
-          unsigned char* blk = blocks + (size_t)(ch >> 1) * kGpBlkBytes;
-          uint4 xr[4];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) xr[q] = *reinterpret_cast<const uint4*>(blk + sw128_off(r, (ch & 1) * 4 + q));
-          tmem_ld_wait();
-          const uint32_t* xw = reinterpret_cast<const uint32_t*>(xr);
-          uint32_t o[16];
+        for (int bi = 0; bi < BPT; ++bi) {
+          const int col0 = (PARTS * bi + part) * 64;
 #pragma unroll
-          for (int q = 0; q < 16; ++q) {
-            const float2 bq = *reinterpret_cast<const float2*>(&bias_s[ch * 32 + 2 * q]);
-            float y0, y1;
-            f2_unpack(f2_add(f2_pack(__uint_as_float(v[2 * q]), __uint_as_float(v[2 * q + 1])), f2_pack(bq.x, bq.y)), y0, y1);
-            const uint32_t yb = pack_bf16x2(y0, y1);                    // the Linear's bf16 output
-            float s0, s1;
-            f2_unpack(f2_add(f2_pack(bf16_lo(xw[q]), bf16_hi(xw[q])), f2_pack(bf16_lo(yb), bf16_hi(yb))), s0, s1);
-            o[q] = pack_bf16x2(s0, s1);                                 // the residual add's bf16 output
-            const uint64_t sv = f2_pack(bf16_lo(o[q]), bf16_hi(o[q]));
-            acc_s = f2_add(acc_s, sv);
-            acc_q = f2_fma(sv, sv, acc_q);
+          for (int hh = 0; hh < 4; ++hh) {
+            uint32_t v[16];
+            tmem_ld16_nowait(lane_addr + col0 + hh * 16, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float2 bq = *reinterpret_cast<const float2*>(&bias_s[col0 + hh * 16 + 2 * q]);
+              float y0, y1;
+              f2_unpack(f2_add(f2_pack(__uint_as_float(v[2 * q]), __uint_as_float(v[2 * q + 1])), f2_pack(bq.x, bq.y)), y0, y1);
+              const uint32_t yb = pack_bf16x2(y0, y1);                  // the Linear's bf16 output
+              // the residual add's bf16 output, x + y rounded once (add.rn.bf16x2).  Working on the packed words also keeps
+              // ptxas from unpacking the whole row to fp32 ahead of the accumulator wait (2x the live registers -> spills).
+              const uint32_t sb = add_bf16x2(xr[bi][hh * 8 + q], yb);
+              xr[bi][hh * 8 + q] = sb;
+              const uint64_t sv = f2_pack(bf16_lo(sb), bf16_hi(sb));
+              acc_s = f2_add(acc_s, sv);
+              acc_q = f2_fma(sv, sv, acc_q);
+            }
           }
-#pragma unroll
-          for (int q = 0; q < 4; ++q)
-            *reinterpret_cast<uint4*>(blk + sw128_off(r, (ch & 1) * 4 + q)) = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
         }
         // accumulator drained: the next tile's MMAs may start
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(mapa(smem_u32(&bars->tmem_empty[0]), 0));
+        GP_TRACE(2)
         {
           float s0, s1, q0, q1;
           f2_unpack(acc_s, s0, s1);
           f2_unpack(acc_q, q0, q1);
-          red_s[hc * 128 + r] = make_float2(s0 + s1, q0 + q1);
+          red_s[part * 128 + r] = make_float2(s0 + s1, q0 + q1);
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        if (tid == 64) {
-          for (int b = 0; b < Cfg::BLOCKS; ++b) tma_store_2d(&map_o, smem_u32(blocks + b * kGpBlkBytes), b * 64, row0);
-          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // x' has left shared memory
+        // ---- x' out: one row per lane -> coalesced 128-byte lines ----
+#pragma unroll
+        for (int bi = 0; bi < BPT; ++bi) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            *reinterpret_cast<uint4*>(buf + own_off + (((uint32_t)q ^ own_sw) << 4)) =
+                make_uint4(xr[bi][4 * q], xr[bi][4 * q + 1], xr[bi][4 * q + 2], xr[bi][4 * q + 3]);
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const uint4 val = *reinterpret_cast<const uint4*>(buf + co_off + i * 512 + ((co_seg ^ (uint32_t)((4 * i + crow) & 7)) << 4));
+            if (4 * i < rows_left) *reinterpret_cast<uint4*>(p.out_sum + goff + 4 * i * TN + bi * (PARTS * 64)) = val;
+          }
+          __syncwarp();
         }
+        GP_TRACE(3)
         if (p.want_ln) {
-          const float2 ra = red_s[r], rb = red_s[128 + r];
-          const float mean = (ra.x + rb.x) * (1.0f / TN);
-          const float var = fmaxf((ra.y + rb.y) * (1.0f / TN) - mean * mean, 0.f);
+          asm volatile("bar.sync %0, %1;" ::"r"(1 + quad), "n"(32 * PARTS) : "memory");     // the warps of this lane quadrant
+          float sum = 0.f, sq = 0.f;
+#pragma unroll
+          for (int k = 0; k < PARTS; ++k) { const float2 t = red_s[k * 128 + r]; sum += t.x; sq += t.y; }
+          const float mean = sum * (1.0f / TN);
+          const float var = fmaxf(sq * (1.0f / TN) - mean * mean, 0.f);
           const float rstd = rsqrtf(var + p.eps);
           const uint64_t sc = f2_bcast(rstd), sh = f2_bcast(-mean * rstd);
-          asm volatile("bar.sync 1, 256;" ::: "memory");                   // x' stores have read the tile; red_s consumed
-          // ---- pass 2: h = (x' - mean) * rstd * gamma + beta in place ----
-#pragma unroll 2
-          for (int ci = 0; ci < NCH / 2; ++ci) {
-            const int ch = hc * (NCH / 2) + ci;
-            unsigned char* blk = blocks + (size_t)(ch >> 1) * kGpBlkBytes;
+          const uint32_t sel_lo = sel_s[0], sel_hi = sel_s[1];
+          asm volatile("bar.sync %0, %1;" ::"r"(1 + quad), "n"(32 * PARTS) : "memory");     // red_s may be rewritten by the next tile
+          GP_TRACE(4)
+          // ---- pass 2: h = (x' - mean) * rstd * gamma + beta, then out like x' ----
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              uint4* ptr = reinterpret_cast<uint4*>(blk + sw128_off(r, (ch & 1) * 4 + q));
-              uint4 xv = *ptr;
-              uint32_t* w = reinterpret_cast<uint32_t*>(&xv);
+          for (int bi = 0; bi < BPT; ++bi) {
+            const int col0 = (PARTS * bi + part) * 64;
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const int col = ch * 32 + q * 8 + e * 2;
-                const float2 g = *reinterpret_cast<const float2*>(&gamma_s[col]);
-                const float2 bt = *reinterpret_cast<const float2*>(&beta_s[col]);
-                float h0, h1;
-                f2_unpack(f2_fma(f2_fma(f2_pack(bf16_lo(w[e]), bf16_hi(w[e])), sc, sh), f2_pack(g.x, g.y), f2_pack(bt.x, bt.y)), h0, h1);
-                w[e] = pack_bf16x2(h0, h1);
-              }
-              *ptr = xv;
+            for (int q = 0; q < 32; ++q) {
+              const float2 g = *reinterpret_cast<const float2*>(&gamma_s[col0 + 2 * q]);
+              const float2 bt = *reinterpret_cast<const float2*>(&beta_s[col0 + 2 * q]);
+              float h0, h1;
+              const uint32_t xv = xr[bi][q];
+              // bf16 -> fp32 by byte permutes whose selectors were loaded after the barrier: a true dependency, so the
+              // unpack of the whole row cannot be scheduled ahead of its use (again: 2x the live registers)
+              const uint64_t xf = f2_pack(__uint_as_float(__byte_perm(xv, 0, sel_lo)), __uint_as_float(__byte_perm(xv, 0, sel_hi)));
+              f2_unpack(f2_fma(f2_fma(xf, sc, sh), f2_pack(g.x, g.y), f2_pack(bt.x, bt.y)), h0, h1);
+              xr[bi][q] = pack_bf16x2(h0, h1);
             }
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              *reinterpret_cast<uint4*>(buf + own_off + (((uint32_t)q ^ own_sw) << 4)) =
+                  make_uint4(xr[bi][4 * q], xr[bi][4 * q + 1], xr[bi][4 * q + 2], xr[bi][4 * q + 3]);
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const uint4 val = *reinterpret_cast<const uint4*>(buf + co_off + i * 512 + ((co_seg ^ (uint32_t)((4 * i + crow) & 7)) << 4));
+              if (4 * i < rows_left) *reinterpret_cast<uint4*>(p.out_norm + goff + 4 * i * TN + bi * (PARTS * 64)) = val;
+            }
+            __syncwarp();
           }
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          asm volatile("bar.sync 1, 256;" ::: "memory");
-          if (tid == 64) {
-            for (int b = 0; b < Cfg::BLOCKS; ++b) tma_store_2d(&map_h, smem_u32(blocks + b * kGpBlkBytes), b * 64, row0);
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-          }
-        } else {
-          asm volatile("bar.sync 1, 256;" ::: "memory");
-        }
-        // the tile buffer is free: fetch the next row tile's residual (same thread that waited for the stores)
-        if (tid == 64 && pt + num_pairs < pair_tiles) {
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          mbar_expect_tx(xfull, Cfg::BLOCKS * kGpBlkBytes);
-          for (int b = 0; b < Cfg::BLOCKS; ++b)
-            tma_load_2d(smem_u32(blocks + b * kGpBlkBytes), &map_x, b * 64, (pt + num_pairs) * 2 * kGpBM + (int)rank * kGpBM, xfull);
+          GP_TRACE(5)
         }
       }
+      GP_TRACE_DUMP(7, tile)
     }
   }
   asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // outstanding TMA stores read shared memory
@@ -440,12 +491,12 @@ static int gp_map_2d(CUtensorMap* map, const void* base, uint64_t inner, uint64_
 }
 
 template <int MODE, int NSUB, int ACT>
-static int gp_launch(const CUtensorMap& ma, const CUtensorMap& mw, const CUtensorMap& mo, const CUtensorMap& mx, const CUtensorMap& mh,
+static int gp_launch(const CUtensorMap& ma, const CUtensorMap& mw, const CUtensorMap& mo,
                      const GpParams& p, cudaStream_t stream, const char* what) {
   using Cfg = GpCfg<MODE, NSUB>;
   constexpr uint32_t kStage = kGpABytes + NSUB * (Cfg::UN / 2) * 128;
   const size_t smem = 1024 + (size_t)Cfg::STAGES * kStage + (size_t)Cfg::BLOCKS * kGpBlkBytes + sizeof(GpBars) +
-                      (MODE == kGpModeLn ? (size_t)3 * Cfg::UN * NSUB * 4 + 2 * 128 * sizeof(float2) : (size_t)p.N * 4);
+                      (MODE == kGpModeLn ? (size_t)3 * Cfg::UN * NSUB * 4 + 4 * 128 * sizeof(float2) + 16 : (size_t)p.N * 4);
   D2S_REQUIRE(smem <= 227 * 1024, D2S_ERR_ARG, "%s: needs %zu B of shared memory", what, smem);
   static bool attr_set = false;
   if (!attr_set) {
@@ -455,7 +506,7 @@ static int gp_launch(const CUtensorMap& ma, const CUtensorMap& mw, const CUtenso
   }
   const int pair_tiles = (p.M + 2 * kGpBM - 1) / (2 * kGpBM);
   const int pairs = pair_tiles < kNumSMs / 2 ? pair_tiles : kNumSMs / 2;
-  gemm_pair_kernel<MODE, NSUB, ACT><<<2 * pairs, kGpThreads, smem, stream>>>(ma, mw, mo, mx, mh, p);
+  gemm_pair_kernel<MODE, NSUB, ACT><<<2 * pairs, (2 + 4 * Cfg::PARTS) * 32, smem, stream>>>(ma, mw, mo, p);
   count_launch();
   return check_launch(what);
 }
@@ -478,10 +529,10 @@ extern "C" int d2s_linear_act_pair_bf16(const void* a, const void* w, const void
   if ((rc = gp_map_2d(&ma, a, K, M, kGpBK, kGpBM, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, what))) return rc;
   if ((rc = gp_map_2d(&mw, w, K, N, kGpBK, 128, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, what))) return rc;
   if ((rc = gp_map_2d(&mo, out, N, M, 64, kGpBM, CU_TENSOR_MAP_L2_PROMOTION_NONE, what))) return rc;
-  GpParams p{(const __nv_bfloat16*)bias, nullptr, nullptr, 0.f, M, N, K, act, 0, gp_trace(), gp_debug()};
-  if (act == D2S_ACT_GELU) return gp_launch<kGpModeAct, 1, D2S_ACT_GELU>(ma, mw, mo, mo, mo, p, (cudaStream_t)stream, what);
-  if (act == D2S_ACT_RELU) return gp_launch<kGpModeAct, 1, D2S_ACT_RELU>(ma, mw, mo, mo, mo, p, (cudaStream_t)stream, what);
-  return gp_launch<kGpModeAct, 1, D2S_ACT_NONE>(ma, mw, mo, mo, mo, p, (cudaStream_t)stream, what);
+  GpParams p{(const __nv_bfloat16*)bias, nullptr, nullptr, nullptr, nullptr, nullptr, 0.f, M, N, K, act, 0, gp_trace(), gp_debug()};
+  if (act == D2S_ACT_GELU) return gp_launch<kGpModeAct, 1, D2S_ACT_GELU>(ma, mw, mo, p, (cudaStream_t)stream, what);
+  if (act == D2S_ACT_RELU) return gp_launch<kGpModeAct, 1, D2S_ACT_RELU>(ma, mw, mo, p, (cudaStream_t)stream, what);
+  return gp_launch<kGpModeAct, 1, D2S_ACT_NONE>(ma, mw, mo, p, (cudaStream_t)stream, what);
 }
 
 extern "C" int d2s_linear_residual_ln_bf16(const void* a, const void* w, const void* bias, const void* x, const void* gamma,
@@ -496,14 +547,12 @@ extern "C" int d2s_linear_residual_ln_bf16(const void* a, const void* w, const v
   D2S_REQUIRE(aligned16(a) && aligned16(w) && aligned16(x) && aligned16(out_sum) && aligned16(out_norm), D2S_ERR_ALIGN,
               "linear_residual_ln: pointers must be 16-byte aligned");
   if (M == 0) return D2S_OK;
-  CUtensorMap ma, mw, mo, mx, mh;
+  CUtensorMap ma, mw;
   int rc;
   if ((rc = gp_map_2d(&ma, a, K, M, kGpBK, kGpBM, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, what))) return rc;
   if ((rc = gp_map_2d(&mw, w, K, N, kGpBK, 96, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, what))) return rc;
-  if ((rc = gp_map_2d(&mx, x, N, M, 64, kGpBM, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, what))) return rc;
-  if ((rc = gp_map_2d(&mo, out_sum, N, M, 64, kGpBM, CU_TENSOR_MAP_L2_PROMOTION_NONE, what))) return rc;
-  if ((rc = gp_map_2d(&mh, out_norm ? out_norm : out_sum, N, M, 64, kGpBM, CU_TENSOR_MAP_L2_PROMOTION_NONE, what))) return rc;
-  GpParams p{(const __nv_bfloat16*)bias, (const __nv_bfloat16*)gamma, (const __nv_bfloat16*)beta, eps, M, N, K, 0, out_norm ? 1 : 0, gp_trace(), gp_debug()};
-  if (N == 384) return gp_launch<kGpModeLn, 2, 0>(ma, mw, mo, mx, mh, p, (cudaStream_t)stream, what);
-  return gp_launch<kGpModeLn, 1, 0>(ma, mw, mo, mx, mh, p, (cudaStream_t)stream, what);
+  GpParams p{(const __nv_bfloat16*)bias, (const __nv_bfloat16*)gamma, (const __nv_bfloat16*)beta, (const __nv_bfloat16*)x,
+             (__nv_bfloat16*)out_sum, (__nv_bfloat16*)out_norm, eps, M, N, K, 0, out_norm ? 1 : 0, gp_trace(), gp_debug()};
+  if (N == 384) return gp_launch<kGpModeLn, 2, 0>(ma, mw, ma, p, (cudaStream_t)stream, what);
+  return gp_launch<kGpModeLn, 1, 0>(ma, mw, ma, p, (cudaStream_t)stream, what);
 }

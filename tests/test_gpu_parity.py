@@ -532,7 +532,8 @@ def test_linear_residual_ln(ops, M, N, K):
     s, h = s.cpu(), h.cpu()
     s_ref, _ = _residual_ln_reference(a, w, b, x, g, bt, 1e-6)
     # fp32 accumulation order differs from the CPU matmul: a few results land on the other side of a bf16 rounding boundary
-    torch.testing.assert_close(s.float(), s_ref.float(), rtol=1e-2, atol=1e-2)
+    # (one bf16 ulp of the Linear output y, |y| < 8, survives a cancelling residual add: atol = 2^-5)
+    torch.testing.assert_close(s.float(), s_ref.float(), rtol=1e-2, atol=3.2e-2)
     assert float((s == s_ref).float().mean()) > 0.98
     # the LayerNorm is exact on the kernel's own residual sum
     h_ref = torch.nn.functional.layer_norm(s.float(), (N,), g.float(), bt.float(), 1e-6)
