@@ -181,6 +181,7 @@ def kernel_breakdown(ops, B, dev, torch, pk):
     Ks = [int(N0 * r) for r in RATIOS]
     Ts = [N0 + 1] + [k + 1 for k in Ks]
     attn_ms, attn_bytes, attn_flops = 0.0, 0.0, 0.0
+    pair_ms, pair_bytes, pair_flops, pair_n = 0.0, 0.0, 0.0, 0
     for T in Ts:
         qkv = torch.randn(B, T, 3 * D, device=dev, dtype=torch.bfloat16)
         ms = time_kernel(lambda: ops.attention_core(qkv, H), 20, torch)
@@ -190,23 +191,45 @@ def kernel_breakdown(ops, B, dev, torch, pk):
                          ms=ms, algo_bytes=by, gbs=by / ms / 1e6, tflops=fl / ms / 1e9))
         attn_ms += 3 * ms; attn_bytes += 3 * by; attn_flops += 3 * fl
         del qkv
-        # the other per-block d2s kernels at this token count: residual add + LayerNorm (x2 per block) and the fc1 GEMM
-        # with the GELU epilogue (tensor-pipe kernel: flops quoted next to the bytes)
+        # the other per-block d2s kernels at this token count: the CTA-pair GEMMs (proj / fc2 + residual + next LayerNorm,
+        # fc1 + GELU) and the stand-alone add + LayerNorm that is left at the pruning stages and the first block
         xr = torch.randn(B, T, D, device=dev, dtype=torch.bfloat16)
         yr = torch.randn(B, T, D, device=dev, dtype=torch.bfloat16)
         gw, gb = torch.ones(D, device=dev, dtype=torch.bfloat16), torch.zeros(D, device=dev, dtype=torch.bfloat16)
-        ms = time_kernel(lambda: ops.add_layernorm(xr, yr, gw, gb, 1e-6), 20, torch)
-        by = B * T * D * e * 4
-        rows.append(dict(kernel="add_layernorm", shape=f"B={B},T={T},D={D}", launches_per_step=6, ms=ms, algo_bytes=by,
-                         gbs=by / ms / 1e6))
+        wp = torch.randn(D, D, device=dev, dtype=torch.bfloat16) * 0.05
         w1 = torch.randn(4 * D, D, device=dev, dtype=torch.bfloat16) * 0.05
+        w2 = torch.randn(D, 4 * D, device=dev, dtype=torch.bfloat16) * 0.02
         b1 = torch.zeros(4 * D, device=dev, dtype=torch.bfloat16)
-        ms = time_kernel(lambda: ops.linear_act(xr, w1, b1, ops.ACT_GELU), 10, torch)
+        ur = torch.randn(B, T, 4 * D, device=dev, dtype=torch.bfloat16)
+        gi = Ts.index(T)
+        # launches per step in this token-count group of 3 blocks (engine._Stream): proj+LN 3; fc2+LN 2; the third fc2 feeds the
+        # predictor's LayerNorm over x[:, 1:] (groups 0-2: fc2 + residual only, then add_layernorm) or the CLS head (group 3)
+        ms = time_kernel(lambda: ops.linear_residual_ln(yr, wp, gb, xr, gw, gb, 1e-6), 10, torch)
+        by, fl = B * T * e * 4 * D, 2.0 * B * T * D * D
+        rows.append(dict(kernel="linear_residual_ln(proj+add+LN, tcgen05 pair)", shape=f"M={B * T},N={D},K={D}", launches_per_step=3,
+                         ms=ms, algo_bytes=by, gbs=by / ms / 1e6, tflops=fl / ms / 1e9))
+        pair_ms += 3 * ms; pair_bytes += 3 * by; pair_flops += 3 * fl; pair_n += 3
+        ms = time_kernel(lambda: ops.linear_residual_ln(ur, w2, gb, xr, gw, gb, 1e-6), 10, torch)
+        by, fl = B * T * e * (4 * D + 3 * D), 2.0 * B * T * D * 4 * D
+        rows.append(dict(kernel="linear_residual_ln(fc2+add+LN, tcgen05 pair)", shape=f"M={B * T},N={D},K={4 * D}", launches_per_step=2,
+                         ms=ms, algo_bytes=by, gbs=by / ms / 1e6, tflops=fl / ms / 1e9))
+        pair_ms += 2 * ms; pair_bytes += 2 * by; pair_flops += 2 * fl; pair_n += 2
+        if gi < 3:
+            ms = time_kernel(lambda: ops.linear_residual_ln(ur, w2, gb, xr, want_norm=False), 10, torch)
+            by = B * T * e * (4 * D + 2 * D)
+            rows.append(dict(kernel="linear_residual_ln(fc2+add, tcgen05 pair)", shape=f"M={B * T},N={D},K={4 * D}", launches_per_step=1,
+                             ms=ms, algo_bytes=by, gbs=by / ms / 1e6, tflops=fl / ms / 1e9))
+            pair_ms += ms; pair_bytes += by; pair_flops += fl; pair_n += 1
+        ms = time_kernel(lambda: ops.add_layernorm(xr, None, gw, gb, 1e-6), 20, torch)
+        by = B * T * D * e * 2
+        rows.append(dict(kernel="add_layernorm(no branch)", shape=f"B={B},T={T},D={D}", launches_per_step=2 if gi < 3 else 1, ms=ms,
+                         algo_bytes=by, gbs=by / ms / 1e6))
+        ms = time_kernel(lambda: ops.linear_act(xr, w1, b1, ops.ACT_GELU, pair=True), 10, torch)
         by = B * T * e * (D + 4 * D)
         fl = 2.0 * B * T * D * 4 * D
-        rows.append(dict(kernel="linear_act(fc1+GELU, tcgen05)", shape=f"M={B * T},N={4 * D},K={D}", launches_per_step=3, ms=ms,
+        rows.append(dict(kernel="linear_act(fc1+GELU, tcgen05 pair)", shape=f"M={B * T},N={4 * D},K={D}", launches_per_step=3, ms=ms,
                          algo_bytes=by, gbs=by / ms / 1e6, tflops=fl / ms / 1e9))
-        del xr, yr, w1
+        del xr, yr, w1, w2, ur, wp
     n_in = N0
     for s, K in enumerate(Ks):
         T_in = n_in + 1
@@ -230,12 +253,26 @@ def kernel_breakdown(ops, B, dev, torch, pk):
                          ms=ms, algo_bytes=B * (2 * e * K + 8 * K), gbs=B * (2 * e * K + 8 * K) / ms / 1e6))
         n_in = K
         del x, sc, hid
-    roof = {"kernel": "attn_tc_fwd_kernel (12 launches/step, T=197/138/97/68)", "bound": "hbm",
-            "achieved": attn_bytes / attn_ms / 1e6, "peak": pk["hbm"], "unit": "GB/s",
-            "frac": attn_bytes / attn_ms / 1e6 / pk["hbm"], "traffic": None, "peak_source": pk["source"],
-            "ms_per_step_in_kernel": attn_ms,
-            "tensor": {"achieved": attn_flops / attn_ms / 1e9, "peak": pk["tf_burst"], "unit": "TFLOP/s",
-                       "frac": attn_flops / attn_ms / 1e9 / pk["tf_burst"]}}
+    # dominant kernel of the step (profiles/: 29 % of the serialised step): the CTA-pair GEMM with the residual + LayerNorm
+    # epilogue.  Aggregate over its launches; HBM is the tighter roof for it (proj is far below the ridge, fc2 sits on it).
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
+            tj = json.load(fh)["gemm_pair_kernel<1,2,0>"]
+            traffic = tj["dram_bytes_per_step"] / tj["launches_per_step"]
+    except (OSError, KeyError, ValueError):
+        pass
+    roof = {"kernel": f"gemm_pair_kernel<LN> (proj/fc2 + residual + LayerNorm, {pair_n} launches/step, T=197/138/97/68)",
+            "bound": "hbm", "achieved": pair_bytes / pair_ms / 1e6, "peak": pk["hbm"], "unit": "GB/s",
+            "frac": pair_bytes / pair_ms / 1e6 / pk["hbm"], "traffic": traffic, "peak_source": pk["source"],
+            "algo_bytes_per_launch": pair_bytes / pair_n, "ms_per_launch": pair_ms / pair_n,
+            "ms_per_step_in_kernel": pair_ms,
+            "tensor": {"achieved": pair_flops / pair_ms / 1e9, "peak": pk["tf_burst"], "unit": "TFLOP/s",
+                       "frac": pair_flops / pair_ms / 1e9 / pk["tf_burst"]},
+            "attention": {"kernel": "attn_tc_fwd_kernel (12 launches/step)", "bound": "hbm",
+                          "achieved": attn_bytes / attn_ms / 1e6, "frac": attn_bytes / attn_ms / 1e6 / pk["hbm"],
+                          "ms_per_step_in_kernel": attn_ms,
+                          "tensor": {"achieved": attn_flops / attn_ms / 1e9, "frac": attn_flops / attn_ms / 1e9 / pk["tf_burst"]}}}
     return rows, roof
 
 
