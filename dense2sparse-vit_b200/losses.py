@@ -44,3 +44,116 @@ class DistillDiffPruningLoss(torch.nn.Module):
                 + self.distill_weight * (cls_kl + token_kl))
         return loss, dict(cls=cls_loss.detach(), ratio=torch.as_tensor(ratio_loss).detach(), cls_kl=cls_kl.detach(),
                           token_kl=token_kl.detach())
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Loss-side consumers of the Dense2Sparse (Variant B) hot path: drop-ins for the reference's MaskLoss / BackboneLoss
+# (losses.py:6-164, :167-241; called from train.py:46-48).  Same constructor arguments (`args` namespace, phase), same
+# forward signatures, same `metrics` side effects and running averages.  The top-k masks reuse the d2s select kernel
+# (the selection the model itself ran), the teacher-token gather the d2s gather kernel.
+# ---------------------------------------------------------------------------------------------------------------
+def _topk_mask(scores, keep_ratio):
+    """MaskLoss.get_mask_from_pred_logits / get_mask_from_cls_attns (losses.py:121-164): 1.0 for the
+    int(N * keep_ratio) highest scores, in token order."""
+    from . import ops
+    n_keep = int(scores.shape[-1] * keep_ratio)
+    s = scores.detach().float()
+    kept, _ = ops.select_topk(s, n_keep, ops.ORDER_SCORE_DESC, want_dropped=False)     # CUDA only: there is no CPU fallback
+    return torch.zeros_like(s).scatter_(1, kept, 1.0)
+
+
+class MaskLoss(torch.nn.Module):
+    def __init__(self, args, phase):
+        super().__init__()
+        self.phase = phase
+        self.keep_ratios = args.keep_ratios
+        self.loss_type = args.mask_loss_type
+        self.count = 1
+        self.running_loss = 0
+        self.runnings_accs = [0 for _ in self.keep_ratios]
+
+    get_mask_from_pred_logits = staticmethod(_topk_mask)
+    get_mask_from_cls_attns = staticmethod(_topk_mask)
+
+    def forward(self, pred_logits, cls_attn_weights, kept_token_idx, metrics):
+        if self.loss_type == "bce":
+            # the reference's bce branch reads the undefined names `args` and `self.mask_criterions` (losses.py:57-58)
+            raise NameError("MaskLoss: the 'bce' branch of the reference cannot run (losses.py:57-58 read undefined names)")
+        mask_loss = 0
+        mask_accs = [0 for _ in self.keep_ratios]
+        w = torch.mean(cls_attn_weights.float(), dim=1)            # (B, H, N+1)   losses.py:82
+        w, _ = torch.max(w, dim=1)                                 # (B, N+1)      :83
+        target = w[:, 1:] / torch.sum(w[:, 1:], dim=-1, keepdim=True)
+        for i in range(len(kept_token_idx)):
+            logits = pred_logits[i].float()
+            if self.loss_type == "mse":                            # losses.py:68-80
+                if i > 0:
+                    target = torch.gather(target, 1, kept_token_idx[i - 1])
+                    target = target / torch.sum(target, dim=1, keepdim=True)
+                mask_loss = mask_loss + 100 * F.mse_loss(logits, target, reduction="mean")
+                continue
+            if i > 0:                                              # losses.py:88-97
+                ratio = self.keep_ratios[i] / self.keep_ratios[i - 1]
+                gathered = torch.gather(target, 1, kept_token_idx[i - 1])
+                gt = _topk_mask(gathered, ratio)
+                target = gathered / torch.sum(gathered, dim=1, keepdim=True)
+            else:
+                ratio = self.keep_ratios[i]
+                gt = _topk_mask(target, ratio)
+            pred = _topk_mask(F.softmax(logits, dim=-1), ratio)
+            mask_loss = mask_loss + F.kl_div(F.log_softmax(logits, dim=-1), torch.log(target), log_target=True,
+                                             reduction="batchmean")
+            mask_accs[i] = mask_accs[i] + torch.sum(pred == gt) / pred.numel()
+        self.running_loss += mask_loss.detach().item()
+        metrics[f"{self.phase}_mask_loss"] = self.running_loss / self.count
+        for i, _ in enumerate(self.keep_ratios):
+            self.runnings_accs[i] += mask_accs[i]
+            metrics[f"{self.phase}_mask_acc_{i}"] = self.runnings_accs[i] / self.count
+        self.count += 1
+        return mask_loss
+
+
+class BackboneLoss(torch.nn.Module):
+    def __init__(self, args):
+        super().__init__()
+        if args.mixup > 0.:
+            # soft-target cross entropy (timm.loss.SoftTargetCrossEntropy, timm==0.4.12): labels arrive mixed / smoothed
+            self.base_criterion = lambda x, t: torch.sum(-t * F.log_softmax(x, dim=-1), dim=-1).mean()
+        else:
+            self.base_criterion = torch.nn.CrossEntropyLoss()
+        self.patch_score_threshold = args.patch_score_threshold
+        self.count = 1
+        self.running_loss = 0
+        self.running_cls_loss = 0
+        self.running_token_kl_loss = 0
+        self.running_token_dist_loss = 0
+        self.runnings_acc = 0
+
+    def forward(self, logits_s, token_s, logits_t, token_t, kept_token_idx, train_labels, metrics):
+        from . import ops
+        logits_s, logits_t = logits_s.float(), logits_t.float()
+        cls_loss = self.base_criterion(logits_s, train_labels)
+        cls_kl_loss = F.kl_div(F.log_softmax(logits_s, dim=-1), F.log_softmax(logits_t, dim=-1), reduction="batchmean",
+                               log_target=True)
+        if self.patch_score_threshold is not None:
+            # the reference's threshold branch (losses.py:216-217) never binds `C`, which line :219 reads
+            raise UnboundLocalError("BackboneLoss: `C` is read before assignment when patch_score_threshold is set "
+                                    "(losses.py:217-219)")
+        B, N, C = token_t.size()
+        # teacher tokens of the kept positions: the LAST stage's indices into the full-length sequence (losses.py:212)
+        token_t = ops.gather_tokens(token_t.detach(), kept_token_idx[-1], prepend_cls=False)
+        token_s = token_s.reshape(-1, C).float()
+        token_t = token_t.reshape(-1, C).float()
+        token_kl_loss = F.kl_div(F.log_softmax(token_s, dim=-1), F.log_softmax(token_t, dim=-1), reduction="batchmean",
+                                 log_target=True)
+        backbone_loss = cls_loss + cls_kl_loss + token_kl_loss
+        self.running_loss += backbone_loss.detach().item()
+        self.running_cls_loss += cls_loss.detach().item()
+        self.running_token_dist_loss += cls_kl_loss.detach().item()
+        self.running_token_kl_loss += token_kl_loss.detach().item()
+        metrics["train_backbone_loss"] = self.running_loss / self.count
+        metrics["train_cls_loss"] = self.running_cls_loss / self.count
+        metrics["train_token_kl_loss"] = self.running_token_dist_loss / self.count     # (sic: losses.py:236-237 swap the names)
+        metrics["train_cls_kl_loss"] = self.running_token_kl_loss / self.count
+        self.count += 1
+        return backbone_loss

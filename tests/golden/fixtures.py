@@ -73,3 +73,19 @@ def load_npz(name):
 
 # small model used for the model-level goldens (N=196 is hard-coded by the reference: 224/16 squared)
 SMALL_CFG = dict(embed_dim=128, depth=4, num_heads=2, patch_size=16, num_classes=16)
+
+
+def loss_inputs(seed, B=4, N=196, L=4, H=3, C=32, ratios=(0.7, 0.49), classes=16):
+    """Seeded stand-ins for what train.py:40-46 feeds the losses (shapes of a 2-stage Dense2Sparse student)."""
+    K = [int(N * r) for r in ratios]
+    n_in = [N] + K[:-1]
+    g = gen(seed)
+    cls_attn = torch.softmax(torch.randn(B, L, H, N + 1, generator=g) * 2.0, dim=-1)
+    pred_logits = [torch.randn(B, n, generator=g) for n in n_in]
+    kept = [torch.stack([torch.sort(torch.randperm(n, generator=g)[:k])[0] for _ in range(B)]) for n, k in zip(n_in, K)]
+    logits_s, logits_t = torch.randn(B, classes, generator=g), torch.randn(B, classes, generator=g)
+    token_s, token_t = torch.randn(B, K[-1], C, generator=g), torch.randn(B, N, C, generator=g)
+    labels = torch.randint(0, classes, (B,), generator=g)
+    soft = torch.softmax(torch.randn(B, classes, generator=g), dim=-1)
+    return dict(cls_attn=cls_attn, pred_logits=pred_logits, kept=kept, logits_s=logits_s, logits_t=logits_t, token_s=token_s,
+                token_t=token_t, labels=labels, soft=soft, ratios=list(ratios))

@@ -196,3 +196,64 @@ def test_cuda_graph_runner_matches_eager(d2s, cuda_dev, img):
 def test_smoke_entry():
     import __graft_entry__ as ge
     ge.smoke()
+
+
+# ------------------------------------------------------------------------------------------ loss-side consumers
+@pytest.mark.parametrize("case", ["one_stage", "two_stage", "three_stage"])
+@pytest.mark.parametrize("loss_type", ["kl_div", "mse"])
+def test_mask_loss_matches_reference_goldens(d2s, cuda_dev, case, loss_type):
+    """MaskLoss (losses.py:6-164) through the product module on the GPU (d2s select kernel for the top-k masks) against
+    the unmodified reference's loss, gradients, accuracies and running-average metrics."""
+    import types
+    G, meta = fx.load_npz("golden_losses.npz")
+    c = meta["cases"][case]
+    inp = fx.loss_inputs(c["seed"], ratios=tuple(c["ratios"]))
+    args = types.SimpleNamespace(keep_ratios=c["ratios"], mask_loss_type=loss_type, batch_size=4, device="cuda")
+    mod = d2s.losses.MaskLoss(args, "train")
+    pl = [p.cuda().requires_grad_(True) for p in inp["pred_logits"]]
+    kept = [k.cuda() for k in inp["kept"]]
+    metrics = {}
+    loss = mod(pl, inp["cls_attn"].cuda(), kept, metrics)
+    loss.backward()
+    torch.testing.assert_close(loss.detach().cpu(), G[f"{case}::{loss_type}::loss"], rtol=1e-4, atol=1e-6)
+    for i, p in enumerate(pl):
+        torch.testing.assert_close(p.grad.cpu(), G[f"{case}::{loss_type}::grad{i}"], rtol=1e-4, atol=1e-7)
+    assert metrics["train_mask_loss"] == pytest.approx(float(G[f"{case}::{loss_type}::metric_loss"]), rel=1e-4)
+    for i in range(len(c["ratios"])):
+        assert float(metrics[f"train_mask_acc_{i}"]) == pytest.approx(float(G[f"{case}::{loss_type}::acc{i}"]), abs=1e-6)
+    mod([p.detach() for p in pl], inp["cls_attn"].cuda(), kept, metrics)
+    assert metrics["train_mask_loss"] == pytest.approx(float(G[f"{case}::{loss_type}::metric_loss_2"]), rel=1e-4)
+
+
+@pytest.mark.parametrize("case", ["one_stage", "three_stage"])
+@pytest.mark.parametrize("mix", [False, True])
+def test_backbone_loss_matches_reference_goldens(d2s, cuda_dev, case, mix):
+    import types
+    G, meta = fx.load_npz("golden_losses.npz")
+    c = meta["cases"][case]
+    inp = fx.loss_inputs(c["seed"], ratios=tuple(c["ratios"]))
+    mod = d2s.losses.BackboneLoss(types.SimpleNamespace(mixup=0.8 if mix else 0.0, patch_score_threshold=None))
+    ls, ts = inp["logits_s"].cuda().requires_grad_(True), inp["token_s"].cuda().requires_grad_(True)
+    metrics = {}
+    lab = (inp["soft"] if mix else inp["labels"]).cuda()
+    loss = mod(ls, ts, inp["logits_t"].cuda(), inp["token_t"].cuda(), [k.cuda() for k in inp["kept"]], lab, metrics)
+    loss.backward()
+    tag = f"{case}::backbone{'_mix' if mix else ''}"
+    torch.testing.assert_close(loss.detach().cpu(), G[f"{tag}::loss"], rtol=1e-4, atol=1e-6)
+    torch.testing.assert_close(ls.grad.cpu(), G[f"{tag}::grad_logits"], rtol=1e-4, atol=1e-7)
+    torch.testing.assert_close(ts.grad.cpu(), G[f"{tag}::grad_tokens"], rtol=1e-4, atol=1e-8)
+    for k in ("train_backbone_loss", "train_cls_loss", "train_token_kl_loss", "train_cls_kl_loss"):
+        assert metrics[k] == pytest.approx(float(G[f"{tag}::{k}"]), rel=1e-4)
+
+
+def test_losses_keep_the_reference_defects(d2s, cuda_dev):
+    import types
+    with pytest.raises(NameError):
+        d2s.losses.MaskLoss(types.SimpleNamespace(keep_ratios=[0.7], mask_loss_type="bce", batch_size=4, device="cuda"), "train")(
+            [torch.randn(4, 196).cuda()], torch.rand(4, 4, 3, 197).cuda(), [torch.zeros(4, 137, dtype=torch.long).cuda()], {})
+    with pytest.raises(UnboundLocalError):
+        d2s.losses.BackboneLoss(types.SimpleNamespace(mixup=0.0, patch_score_threshold=0.9))(
+            torch.randn(4, 16).cuda(), torch.randn(4, 10, 32).cuda(), torch.randn(4, 16).cuda(), torch.randn(4, 196, 32).cuda(),
+            [torch.zeros(40, dtype=torch.long).cuda()], torch.zeros(4, dtype=torch.long).cuda(), {})
+    with pytest.raises(RuntimeError):     # host tensors: no CPU fallback for the select kernel
+        d2s.losses.MaskLoss.get_mask_from_pred_logits(torch.rand(2, 196), 0.7)

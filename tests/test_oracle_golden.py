@@ -223,3 +223,60 @@ def test_teacher():
     torch.testing.assert_close(logits, MOD["T_logits"], **FP32_TOL)
     torch.testing.assert_close(tokens, MOD["T_tokens"], rtol=1e-4, atol=1e-5)
     torch.testing.assert_close(cls_attn, MOD["T_cls_attn"], rtol=1e-4, atol=1e-7)
+
+
+# ------------------------------------------------------------------------------------------ loss-side consumers
+def _loss_goldens():
+    return fx.load_npz("golden_losses.npz")
+
+
+@pytest.mark.parametrize("case", ["one_stage", "two_stage", "three_stage"])
+@pytest.mark.parametrize("loss_type", ["kl_div", "mse"])
+def test_oracle_mask_loss_matches_reference(case, loss_type):
+    from oracle import losses as ol
+    G, meta = _loss_goldens()
+    c = meta["cases"][case]
+    inp = fx.loss_inputs(c["seed"], ratios=tuple(c["ratios"]))
+    assert torch.allclose(torch.tensor([fx.checksum(inp["cls_attn"]), fx.checksum(inp["token_t"])]).double(),
+                          G[f"{case}::in_checksum"].double(), rtol=1e-9), "fixture RNG drifted"
+    pl = [p.clone().requires_grad_(True) for p in inp["pred_logits"]]
+    loss, accs = ol.mask_loss(pl, inp["cls_attn"], inp["kept"], c["ratios"], loss_type)
+    loss.backward()
+    torch.testing.assert_close(loss.detach(), G[f"{case}::{loss_type}::loss"], rtol=1e-5, atol=1e-6)
+    for i, p in enumerate(pl):
+        torch.testing.assert_close(p.grad, G[f"{case}::{loss_type}::grad{i}"], rtol=1e-4, atol=1e-7)
+    for i in range(len(c["ratios"])):
+        assert float(accs[i]) == pytest.approx(float(G[f"{case}::{loss_type}::acc{i}"]), abs=1e-7)
+
+
+@pytest.mark.parametrize("case", ["one_stage", "two_stage", "three_stage"])
+@pytest.mark.parametrize("mix", [False, True])
+def test_oracle_backbone_loss_matches_reference(case, mix):
+    from oracle import losses as ol
+    G, meta = _loss_goldens()
+    c = meta["cases"][case]
+    inp = fx.loss_inputs(c["seed"], ratios=tuple(c["ratios"]))
+    ls, ts = inp["logits_s"].clone().requires_grad_(True), inp["token_s"].clone().requires_grad_(True)
+    loss, parts = ol.backbone_loss(ls, ts, inp["logits_t"], inp["token_t"], inp["kept"], inp["soft"] if mix else inp["labels"],
+                                   soft_labels=mix)
+    loss.backward()
+    tag = f"{case}::backbone{'_mix' if mix else ''}"
+    torch.testing.assert_close(loss.detach(), G[f"{tag}::loss"], rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(ls.grad, G[f"{tag}::grad_logits"], rtol=1e-4, atol=1e-7)
+    torch.testing.assert_close(ts.grad, G[f"{tag}::grad_tokens"], rtol=1e-4, atol=1e-8)
+    # the reference's metric names swap the two KL terms (losses.py:236-237)
+    assert float(parts["cls_kl"].detach()) == pytest.approx(float(G[f"{tag}::train_token_kl_loss"]), rel=1e-5)
+    assert float(parts["token_kl"].detach()) == pytest.approx(float(G[f"{tag}::train_cls_kl_loss"]), rel=1e-5)
+
+
+def test_oracle_loss_masks_and_reference_defects():
+    from oracle import losses as ol
+    G, meta = _loss_goldens()
+    sc = torch.softmax(fx.randn(510, 5, 196), dim=-1)
+    assert torch.equal(ol.topk_mask(sc, 0.7), G["mask_pred"]) and torch.equal(ol.topk_mask(sc, 0.49 / 0.7), G["mask_cls"])
+    assert meta["bce_error"] == "NameError" and meta["threshold_error"] == "UnboundLocalError"
+    with pytest.raises(NameError):
+        ol.mask_loss([torch.randn(4, 196)], torch.rand(4, 4, 3, 197), [torch.zeros(4, 137, dtype=torch.long)], [0.7], "bce")
+    with pytest.raises(UnboundLocalError):
+        ol.backbone_loss(torch.randn(4, 16), torch.randn(4, 10, 32), torch.randn(4, 16), torch.randn(4, 196, 32),
+                         [torch.zeros(40, dtype=torch.long)], torch.zeros(4, dtype=torch.long), patch_score_threshold=0.9)
