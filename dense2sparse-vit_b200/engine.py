@@ -19,6 +19,7 @@ import torch.nn.functional as F
 from . import ops
 
 _FUSED_FC1 = os.environ.get("D2S_FUSED_FC1", "1") != "0"   # A/B switch for the tcgen05 fc1+GELU GEMM
+_TRAIN_ATTN = os.environ.get("D2S_TRAIN_ATTN", "1") != "0"    # A/B switch for ops.attention_train (bf16 training attention)
 _FUSED_PAIR = os.environ.get("D2S_FUSED_PAIR", "1") != "0"  # A/B switch for the CTA-pair GEMMs (fc1 pair; proj/fc2 + add + LN)
 INIT_N = 14 * 14  # the reference hard-codes 196 spatial tokens (dynamic_vit.py:828, default_dynamic_vit.py:446)
 
@@ -49,7 +50,10 @@ def attention_pre_proj(m, x, policy=None, return_cls_attn=False):
     B, T, C = x.shape
     H = m.num_heads
     qkv = m.qkv(x)
-    if _needs_grad(qkv, policy):
+    if _needs_grad(qkv, policy) and qkv.is_cuda and qkv.dtype == torch.bfloat16 and T <= 256 and _TRAIN_ATTN:
+        # training, bf16: per-head strided GEMMs on the packed tensor around the padded-row policy softmax
+        o, cls_attn = ops.attention_train(qkv, H, policy=policy, scale=m.scale, want_cls_row=return_cls_attn)
+    elif _needs_grad(qkv, policy):
         q, k, v = qkv.reshape(B, T, 3, H, C // H).permute(2, 0, 3, 1, 4).unbind(0)
         attn = (q @ k.transpose(-2, -1)) * m.scale
         attn = ops.softmax_with_policy(attn, policy)

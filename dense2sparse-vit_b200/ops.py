@@ -269,6 +269,79 @@ def softmax_with_policy(attn, policy, eps=1e-6):
     return _SoftmaxPolicy.apply(attn, policy, eps)
 
 
+class _AttentionTrain(torch.autograd.Function):
+    """Training attention on the packed qkv tensor, differentiable in qkv and in the keep policy.
+
+    Library GEMMs (per head, straight on strided views of the packed (B,T,3,H,hd) tensor: no permute copies, no cat of
+    dq/dk/dv) around the one-pass d2s policy softmax, with the score tensors kept at a row stride of round_up(T, 8) so that
+    the softmax kernels move 16-byte vectors.  Saves only the scaled scores and the (row max, denominator) pairs; the
+    probabilities are recomputed in backward."""
+
+    @staticmethod
+    def forward(ctx, qkv, policy, H, scale, eps, want_cls):
+        qkv = qkv.contiguous()
+        B, T, C3 = qkv.shape
+        D = C3 // 3
+        hd = D // H
+        q5 = qkv.view(B, T, 3, H, hd)
+        ld = (T + 7) // 8 * 8
+        S = torch.empty(B, H, T, ld, dtype=qkv.dtype, device=qkv.device)
+        for h in range(H):
+            sv = S[:, h, :, :T]
+            torch.baddbmm(sv, q5[:, :, 0, h], q5[:, :, 1, h].transpose(1, 2), beta=0, alpha=scale, out=sv)
+        pol = _f32c(policy.reshape(B, T)) if policy is not None else None
+        P = torch.empty_like(S)
+        stats = torch.empty(B, H, T, 2, dtype=torch.float32, device=qkv.device)
+        _lib.call("d2s_softmax_policy_fwd_ld", _ptr(S), _ptr(pol), B, H, T, ld, float(eps), _ptr(P), _ptr(stats), _stream())
+        O = torch.empty(B, T, H, hd, dtype=qkv.dtype, device=qkv.device)
+        for h in range(H):
+            torch.bmm(P[:, h, :, :T], q5[:, :, 2, h], out=O[:, :, h])
+        cls_attn = P[:, :, 0, :T].clone() if want_cls else None
+        ctx.save_for_backward(qkv, S, stats, pol if pol is not None else torch.empty(0, device=qkv.device))
+        ctx.meta = (B, T, H, hd, ld, float(scale), float(eps), pol is not None,
+                    None if policy is None else (policy.shape, policy.dtype))
+        return O.view(B, T, D), cls_attn
+
+    @staticmethod
+    def backward(ctx, gO, g_cls):
+        qkv, S, stats, pol = ctx.saved_tensors
+        B, T, H, hd, ld, scale, eps, has_pol, pol_meta = ctx.meta
+        polp = pol if has_pol else None
+        q5 = qkv.view(B, T, 3, H, hd)
+        g5 = gO.to(qkv.dtype).contiguous().view(B, T, H, hd)
+        P = torch.empty_like(S)
+        _lib.call("d2s_softmax_policy_fwd_ld", _ptr(S), _ptr(polp), B, H, T, ld, eps, _ptr(P), None, _stream())
+        dqkv = torch.empty_like(qkv)
+        d5 = dqkv.view(B, T, 3, H, hd)
+        dP = torch.empty_like(S)
+        for h in range(H):
+            torch.bmm(P[:, h, :, :T].transpose(1, 2), g5[:, :, h], out=d5[:, :, 2, h])          # dV = P^T dO
+            torch.bmm(g5[:, :, h], q5[:, :, 2, h].transpose(1, 2), out=dP[:, h, :, :T])          # dP = dO V^T
+        if g_cls is not None:
+            dP[:, :, 0, :T] += g_cls.to(dP.dtype)
+        gpol = torch.zeros(B, T, dtype=torch.float32, device=qkv.device) if has_pol else None
+        _lib.call("d2s_softmax_policy_bwd_ld", _ptr(S), _ptr(polp), _ptr(dP), _ptr(stats), B, H, T, ld, eps, _ptr(dP), _ptr(gpol),
+                  _stream())
+        for h in range(H):
+            dq, dk, ds = d5[:, :, 0, h], d5[:, :, 1, h], dP[:, h, :, :T]
+            torch.baddbmm(dq, ds, q5[:, :, 1, h], beta=0, alpha=scale, out=dq)                     # dQ = scale dS K
+            torch.baddbmm(dk, ds.transpose(1, 2), q5[:, :, 0, h], beta=0, alpha=scale, out=dk)     # dK = scale dS^T Q
+        if has_pol:
+            gpol = gpol.reshape(pol_meta[0]).to(pol_meta[1])
+        return dqkv, gpol, None, None, None, None
+
+
+def attention_train(qkv, num_heads, policy=None, scale=None, eps=1e-6, want_cls_row=False):
+    """Differentiable attention core of Attention.forward (vit_models/dynamic_vit.py:216-231) on the packed qkv (B,T,3*H*hd):
+    returns (out (B,T,H*hd), cls_row (B,H,T) | None).  bf16 CUDA tensors, T <= 256."""
+    _check_cuda(qkv, policy)
+    if qkv.dtype != torch.bfloat16 or qkv.shape[1] > 256:
+        raise RuntimeError("attention_train: bf16 and T <= 256 only (other cases use softmax_with_policy around torch matmuls)")
+    hd = qkv.shape[-1] // 3 // num_heads
+    scale = hd ** -0.5 if scale is None else scale
+    return _AttentionTrain.apply(qkv, policy, num_heads, float(scale), float(eps), bool(want_cls_row))
+
+
 def attention_core(qkv, num_heads, policy=None, scale=None, eps=1e-6, want_cls_row=False):
     """Fused inference attention: packed qkv (B,T,3*H*hd) straight from the qkv Linear -> (out (B,T,H*hd),
     cls_row (B,H,T) fp32 | None).  bf16 runs the tcgen05/TMEM kernel, fp32 the SIMT parity kernel.

@@ -129,6 +129,14 @@ int d2s_softmax_policy_bwd(const void* attn, const float* policy, const void* go
                            int dtype, int B, int H, int T, float eps,
                            void* gattn, float* gpolicy, d2s_stream_t stream);
 
+/* Padded-row variants used by the training attention (ops.attention_train): bf16 only, tensors are (B,H,T,ld) with
+ * ld % 8 == 0, T <= ld <= 256, so every row is 16-byte aligned and moved with 16-byte accesses; padding columns of `out`
+ * / `gattn` are written as zeros.  gattn may alias gout. */
+int d2s_softmax_policy_fwd_ld(const void* attn, const float* policy, int B, int H, int T, int ld, float eps, void* out,
+                              float* stats, d2s_stream_t stream);
+int d2s_softmax_policy_bwd_ld(const void* attn, const float* policy, const void* gout, const float* stats, int B, int H,
+                              int T, int ld, float eps, void* gattn, float* gpolicy, d2s_stream_t stream);
+
 /* Fused attention core of Attention.forward (dynamic_vit.py:218-234; default_dynamic_vit.py:203-213):
  * qkv (B,T,3,H,hd) packed as produced by the qkv Linear; out (B,T,H*hd) ready for the proj Linear;
  * cls_row (B,H,T) f32 = probabilities of query row 0 (dynamic_vit.py:233-234) or NULL.

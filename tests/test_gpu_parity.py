@@ -557,6 +557,43 @@ def test_score_tail_a_gelu_on_load_and_prev_gather(ops):
     assert torch.equal(pk1.cpu(), torch.ones(B, K))
 
 
+@pytest.mark.parametrize("B,T,H,frac", [(3, 197, 6, False), (2, 138, 6, True), (2, 64, 3, False), (1, 8, 2, True)])
+def test_attention_train_fwd_bwd_vs_oracle_autograd(ops, B, T, H, frac):
+    """bf16 training attention (per-head strided GEMMs on the packed qkv + padded-row policy softmax kernels) against the
+    fp32 oracle's autograd on the same bf16-rounded inputs: output, CLS row, d qkv and d policy at bf16 tolerance."""
+    hd = 64
+    qkv = (fx.randn(600 + T, B, T, 3 * H * hd) * 0.7).bfloat16()
+    pol = torch.rand(B, T, 1, generator=fx.gen(601 + T)) if frac else (torch.rand(B, T, 1, generator=fx.gen(602 + T)) > 0.3).float()
+    pol[:, 0] = 1.0
+    go = (fx.randn(603 + T, B, T, H * hd) * 0.5).bfloat16()
+    gc = fx.randn(604 + T, B, H, T) * 0.5
+    q1 = cu(qkv).requires_grad_(True)
+    p1 = cu(pol).requires_grad_(True)
+    o1, c1 = ops.attention_train(q1, H, policy=p1, want_cls_row=True)
+    (o1.float() * cu(go).float()).sum().add((c1.float() * cu(gc)).sum()).backward()
+    q2 = qkv.float().requires_grad_(True)
+    p2 = pol.clone().requires_grad_(True)
+    o2, c2 = oo.attention_core(q2.view(B, T, 3, H, hd), H, policy=p2)
+    (o2 * go.float()).sum().add((c2 * gc).sum()).backward()
+    tol = dict(rtol=2e-2, atol=2e-2)
+    torch.testing.assert_close(o1.detach().cpu().float(), o2.detach(), **tol)
+    torch.testing.assert_close(c1.detach().cpu().float(), c2.detach(), rtol=2e-2, atol=2e-3)
+    gq1, gq2 = q1.grad.cpu().float(), q2.grad
+    assert float((gq1 - gq2).abs().max()) <= 3e-2 * float(gq2.abs().max()) + 1e-3
+    gp1, gp2 = p1.grad.cpu().float(), p2.grad
+    assert float((gp1 - gp2).abs().max()) <= 3e-2 * float(gp2.abs().max()) + 1e-3
+    # no policy: plain softmax attention
+    q3 = cu(qkv).requires_grad_(True)
+    o3, none = ops.attention_train(q3, H)
+    (o3.float() * cu(go).float()).sum().backward()
+    q4 = qkv.float().requires_grad_(True)
+    o4, _ = oo.attention_core(q4.view(B, T, 3, H, hd), H)
+    (o4 * go.float()).sum().backward()
+    assert none is None
+    torch.testing.assert_close(o3.detach().cpu().float(), o4.detach(), **tol)
+    assert float((q3.grad.cpu().float() - q4.grad).abs().max()) <= 3e-2 * float(q4.grad.abs().max()) + 1e-3
+
+
 # ------------------------------------------------------------------------------------------ error behaviour
 def test_errors_are_loud(ops):
     with pytest.raises(RuntimeError):
