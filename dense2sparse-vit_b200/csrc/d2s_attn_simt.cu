@@ -77,8 +77,8 @@ softmax_policy_fwd_kernel(const T_* __restrict__ attn, const float* __restrict__
 // ---- bf16, padded rows (row stride ld % 8 == 0, T <= 256): lane owns columns 8*lane .. 8*lane+7, one 16-byte access per
 // lane and row instead of 2-byte scalars (rows of T = 197 bf16 are only 2-byte aligned when packed densely; the training
 // path therefore keeps its score tensors with ld = round_up(T, 8)).  Same arithmetic as the scalar kernels. ----
-__device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
-  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+__device__ __forceinline__ void unpack8(const int4& v, float (&f)[8]) {
+  const uint32_t w[4] = {(uint32_t)v.x, (uint32_t)v.y, (uint32_t)v.z, (uint32_t)v.w};
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     f[2 * k] = __uint_as_float(w[k] << 16);
@@ -95,9 +95,16 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
   return make_uint4(w[0], w[1], w[2], w[3]);
 }
 
+// exp of a non-positive bf16-rounded difference: MUFU.EX2 (relative error 2^-22, far inside bf16)
+__device__ __forceinline__ float exp_fast(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * 1.4426950408889634f));
+  return y;
+}
+
 __global__ void __launch_bounds__(kRowThreads)
-softmax_policy_fwd_vec_kernel(const __nv_bfloat16* __restrict__ attn, const float* __restrict__ policy, int H, int T, int ld,
-                              float eps, __nv_bfloat16* __restrict__ out, float* __restrict__ stats) {
+softmax_policy_fwd_vec_kernel(const __nv_bfloat16* __restrict__ attn, const float* __restrict__ policy, int H, int T, int rows,
+                              int ld, float eps, __nv_bfloat16* __restrict__ out, float* __restrict__ stats) {
   const int bh = blockIdx.y, b = bh / H;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int row_end = min(T, (int)(blockIdx.x + 1) * kRowsPerCta);
@@ -109,9 +116,9 @@ softmax_policy_fwd_vec_kernel(const __nv_bfloat16* __restrict__ attn, const floa
   const float c = policy ? eps / (float)T : 0.0f;
   const float eps_den = policy ? eps : 0.0f;
   for (int i = blockIdx.x * kRowsPerCta + warp; i < row_end; i += kRowWarps) {
-    const size_t base = ((size_t)bh * T + i) * ld + j0;
+    const size_t base = ((size_t)bh * rows + i) * ld + j0;
     float s[8];
-    if (active) unpack8(*reinterpret_cast<const uint4*>(attn + base), s);
+    if (active) unpack8(ld_stream16(attn + base), s);
     float m = -INFINITY;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
@@ -123,15 +130,16 @@ softmax_policy_fwd_vec_kernel(const __nv_bfloat16* __restrict__ attn, const floa
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       float a = 0.f;
-      if (active && j0 + k < T) a = expf(sub_in_dtype(s[k], m, attn)) * ((j0 + k == i) ? 1.0f : pol[k]);
+      if (active && j0 + k < T) a = exp_fast(sub_in_dtype(s[k], m, attn)) * ((j0 + k == i) ? 1.0f : pol[k]);
       s[k] = a;
       sum += a;
     }
     sum = warp_sum(sum);
     const float den = sum + eps_den;
+    const float rden = 1.0f / den;
     if (active) {
 #pragma unroll
-      for (int k = 0; k < 8; ++k) s[k] = (j0 + k < T) ? (s[k] + c) / den : 0.f;   // padding columns are written as zeros
+      for (int k = 0; k < 8; ++k) s[k] = (j0 + k < T) ? (s[k] + c) * rden : 0.f;   // padding columns are written as zeros
       *reinterpret_cast<uint4*>(out + base) = pack8(s);
     }
     if (stats && lane == 0) {
@@ -139,12 +147,16 @@ softmax_policy_fwd_vec_kernel(const __nv_bfloat16* __restrict__ attn, const floa
       stats[((size_t)bh * T + i) * 2 + 1] = den;
     }
   }
+  // padding rows T..rows-1 of `out` (the padded tensor is a GEMM operand)
+  if (blockIdx.x == gridDim.x - 1 && active)
+    for (int i = T + warp; i < rows; i += kRowWarps)
+      *reinterpret_cast<uint4*>(out + ((size_t)bh * rows + i) * ld + j0) = make_uint4(0, 0, 0, 0);
 }
 
 __global__ void __launch_bounds__(kRowThreads)
 softmax_policy_bwd_vec_kernel(const __nv_bfloat16* __restrict__ attn, const float* __restrict__ policy,
-                              const __nv_bfloat16* __restrict__ gout, const float* __restrict__ stats, int H, int T, int ld,
-                              float eps, __nv_bfloat16* __restrict__ gattn, float* __restrict__ gpolicy) {
+                              const __nv_bfloat16* __restrict__ gout, const float* __restrict__ stats, int H, int T, int rows,
+                              int ld, float eps, __nv_bfloat16* __restrict__ gattn, float* __restrict__ gpolicy) {
   __shared__ float gp_s[256];
   const int bh = blockIdx.y, b = bh / H;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -161,13 +173,13 @@ softmax_policy_bwd_vec_kernel(const __nv_bfloat16* __restrict__ attn, const floa
   }
   const float c = policy ? eps / (float)T : 0.0f;
   for (int i = blockIdx.x * kRowsPerCta + warp; i < row_end; i += kRowWarps) {
-    const size_t base = ((size_t)bh * T + i) * ld + j0;
+    const size_t base = ((size_t)bh * rows + i) * ld + j0;
     const float m = stats[((size_t)bh * T + i) * 2];
-    const float den = stats[((size_t)bh * T + i) * 2 + 1];
+    const float rden = 1.0f / stats[((size_t)bh * T + i) * 2 + 1];
     float sv[8], g[8], ex[8], a[8];
     if (active) {
-      unpack8(*reinterpret_cast<const uint4*>(attn + base), sv);
-      unpack8(*reinterpret_cast<const uint4*>(gout + base), g);
+      unpack8(ld_stream16(attn + base), sv);
+      unpack8(ld_stream16(gout + base), g);
     }
     float gdotp = 0.f, best = -INFINITY;
     int best_j = 0x7fffffff;
@@ -177,36 +189,36 @@ softmax_policy_bwd_vec_kernel(const __nv_bfloat16* __restrict__ attn, const floa
       ex[k] = a[k] = 0.f;
       if (active && j < T) {
         if (sv[k] > best) { best = sv[k]; best_j = j; }
-        ex[k] = expf(sub_in_dtype(sv[k], m, attn));
+        ex[k] = exp_fast(sub_in_dtype(sv[k], m, attn));
         a[k] = ex[k] * ((j == i) ? 1.0f : pol[k]);
-        gdotp += g[k] * ((a[k] + c) / den);
+        gdotp += g[k] * ((a[k] + c) * rden);
       } else {
         g[k] = 0.f;
       }
     }
     gdotp = warp_sum(gdotp);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-      const int oj = __shfl_xor_sync(0xffffffffu, best_j, o);
-      if (ob > best || (ob == best && oj < best_j)) { best = ob; best_j = oj; }
-    }
     float ds[8];
     float ds_sum = 0.f;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const int j = j0 + k;
-      const float da = (g[k] - gdotp) / den;
+      const float da = (g[k] - gdotp) * rden;
       ds[k] = (active && j < T) ? da * a[k] : 0.f;
       ds_sum += ds[k];
       if (active && j < T && j != i) gp[k] += da * ex[k];
     }
-    ds_sum = policy ? warp_sum(ds_sum) : 0.f;
-    if (active) {
+    if (policy) {   // the gradient through the subtracted row max goes to its first occurrence (plain softmax: vanishes)
+      ds_sum = warp_sum(ds_sum);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oj = __shfl_xor_sync(0xffffffffu, best_j, o);
+        if (ob > best || (ob == best && oj < best_j)) { best = ob; best_j = oj; }
+      }
 #pragma unroll
       for (int k = 0; k < 8; ++k) ds[k] -= (j0 + k == best_j ? ds_sum : 0.f);
-      *reinterpret_cast<uint4*>(gattn + base) = pack8(ds);
     }
+    if (active) *reinterpret_cast<uint4*>(gattn + base) = pack8(ds);
   }
   if (gpolicy && policy) {
 #pragma unroll
@@ -504,33 +516,35 @@ extern "C" int d2s_softmax_policy_bwd(const void* attn, const float* policy, con
 
 /* Padded-row variants for the training attention (bf16, row stride ld % 8 == 0, ld >= T, T <= 256): attn / out / gout / gattn
  * are (B,H,T,ld); out may not alias attn, gattn may alias gout. */
-extern "C" int d2s_softmax_policy_fwd_ld(const void* attn, const float* policy, int B, int H, int T, int ld, float eps, void* out,
-                                         float* stats, d2s_stream_t stream) {
+extern "C" int d2s_softmax_policy_fwd_ld(const void* attn, const float* policy, int B, int H, int T, int rows, int ld, float eps,
+                                         void* out, float* stats, d2s_stream_t stream) {
   D2S_REQUIRE(attn && out, D2S_ERR_ARG, "softmax_policy_fwd_ld: null pointer");
-  D2S_REQUIRE(B >= 0 && H >= 1 && T >= 1 && T <= 256 && ld >= T && ld % 8 == 0 && ld <= 256, D2S_ERR_ARG,
-              "softmax_policy_fwd_ld: bad shape B=%d H=%d T=%d ld=%d (need T <= ld <= 256, ld %% 8 == 0)", B, H, T, ld);
+  D2S_REQUIRE(B >= 0 && H >= 1 && T >= 1 && T <= 256 && rows >= T && ld >= T && ld % 8 == 0 && ld <= 256, D2S_ERR_ARG,
+              "softmax_policy_fwd_ld: bad shape B=%d H=%d T=%d rows=%d ld=%d (need T <= rows, T <= ld <= 256, ld %% 8 == 0)", B, H, T,
+              rows, ld);
   D2S_REQUIRE((long long)B * H <= 65535, D2S_ERR_ARG, "softmax_policy_fwd_ld: B*H=%lld exceeds 65535", (long long)B * H);
   D2S_REQUIRE(aligned16(attn) && aligned16(out), D2S_ERR_ALIGN, "softmax_policy_fwd_ld: pointers must be 16-byte aligned");
   if (B == 0) return D2S_OK;
   dim3 grid(ceil_div(T, kRowsPerCta), B * H);
-  softmax_policy_fwd_vec_kernel<<<grid, kRowThreads, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)attn, policy, H, T, ld, eps,
-                                                                                 (__nv_bfloat16*)out, stats);
+  softmax_policy_fwd_vec_kernel<<<grid, kRowThreads, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)attn, policy, H, T, rows, ld,
+                                                                                 eps, (__nv_bfloat16*)out, stats);
   count_launch();
   return check_launch("d2s_softmax_policy_fwd_ld");
 }
 
 extern "C" int d2s_softmax_policy_bwd_ld(const void* attn, const float* policy, const void* gout, const float* stats, int B, int H,
-                                         int T, int ld, float eps, void* gattn, float* gpolicy, d2s_stream_t stream) {
+                                         int T, int rows, int ld, float eps, void* gattn, float* gpolicy, d2s_stream_t stream) {
   D2S_REQUIRE(attn && gout && stats && gattn, D2S_ERR_ARG, "softmax_policy_bwd_ld: null pointer");
-  D2S_REQUIRE(B >= 0 && H >= 1 && T >= 1 && T <= 256 && ld >= T && ld % 8 == 0 && ld <= 256, D2S_ERR_ARG,
-              "softmax_policy_bwd_ld: bad shape B=%d H=%d T=%d ld=%d (need T <= ld <= 256, ld %% 8 == 0)", B, H, T, ld);
+  D2S_REQUIRE(B >= 0 && H >= 1 && T >= 1 && T <= 256 && rows >= T && ld >= T && ld % 8 == 0 && ld <= 256, D2S_ERR_ARG,
+              "softmax_policy_bwd_ld: bad shape B=%d H=%d T=%d rows=%d ld=%d (need T <= rows, T <= ld <= 256, ld %% 8 == 0)", B, H, T,
+              rows, ld);
   D2S_REQUIRE((long long)B * H <= 65535, D2S_ERR_ARG, "softmax_policy_bwd_ld: B*H=%lld exceeds 65535", (long long)B * H);
   D2S_REQUIRE(aligned16(attn) && aligned16(gout) && aligned16(gattn), D2S_ERR_ALIGN,
               "softmax_policy_bwd_ld: pointers must be 16-byte aligned");
   if (B == 0) return D2S_OK;
   dim3 grid(ceil_div(T, kRowsPerCta), B * H);
   softmax_policy_bwd_vec_kernel<<<grid, kRowThreads, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)attn, policy, (const __nv_bfloat16*)gout, stats, H, T, ld, eps, (__nv_bfloat16*)gattn, gpolicy);
+      (const __nv_bfloat16*)attn, policy, (const __nv_bfloat16*)gout, stats, H, T, rows, ld, eps, (__nv_bfloat16*)gattn, gpolicy);
   count_launch();
   return check_launch("d2s_softmax_policy_bwd_ld");
 }

@@ -272,10 +272,11 @@ def softmax_with_policy(attn, policy, eps=1e-6):
 class _AttentionTrain(torch.autograd.Function):
     """Training attention on the packed qkv tensor, differentiable in qkv and in the keep policy.
 
-    Library GEMMs (per head, straight on strided views of the packed (B,T,3,H,hd) tensor: no permute copies, no cat of
-    dq/dk/dv) around the one-pass d2s policy softmax, with the score tensors kept at a row stride of round_up(T, 8) so that
-    the softmax kernels move 16-byte vectors.  Saves only the scaled scores and the (row max, denominator) pairs; the
-    probabilities are recomputed in backward."""
+    One d2s relayout pass turns the packed (B,T,3,H,hd) tensor into head-major (3,B,H,Tp,hd) with Tp = round_up(T, 8) zero
+    padded, so that the six batched GEMMs of forward + backward run over B*H matrices whose every dimension and leading
+    dimension is a multiple of 8 (T = 197 otherwise sends cuBLAS to unaligned legacy kernels and torch to permute copies),
+    and the d2s policy-softmax kernels move 16-byte vectors.  dq/dk/dv are merged straight into the packed qkv gradient
+    (no cat).  Saves q/k/v head-major, the scaled scores, the probabilities and the (row max, denominator) pairs."""
 
     @staticmethod
     def forward(ctx, qkv, policy, H, scale, eps, want_cls):
@@ -283,49 +284,46 @@ class _AttentionTrain(torch.autograd.Function):
         B, T, C3 = qkv.shape
         D = C3 // 3
         hd = D // H
-        q5 = qkv.view(B, T, 3, H, hd)
-        ld = (T + 7) // 8 * 8
-        S = torch.empty(B, H, T, ld, dtype=qkv.dtype, device=qkv.device)
-        for h in range(H):
-            sv = S[:, h, :, :T]
-            torch.baddbmm(sv, q5[:, :, 0, h], q5[:, :, 1, h].transpose(1, 2), beta=0, alpha=scale, out=sv)
+        Tp = (T + 7) // 8 * 8
+        dev, dt = qkv.device, qkv.dtype
+        qkvh = torch.empty(3, B * H, Tp, hd, dtype=dt, device=dev)
+        _lib.call("d2s_split_heads_bf16", _ptr(qkv), B, T, Tp, 3, H, hd, _ptr(qkvh), _stream())
+        S = torch.empty(B * H, Tp, Tp, dtype=dt, device=dev)
+        torch.baddbmm(S, qkvh[0], qkvh[1].transpose(1, 2), beta=0, alpha=scale, out=S)
         pol = _f32c(policy.reshape(B, T)) if policy is not None else None
         P = torch.empty_like(S)
-        stats = torch.empty(B, H, T, 2, dtype=torch.float32, device=qkv.device)
-        _lib.call("d2s_softmax_policy_fwd_ld", _ptr(S), _ptr(pol), B, H, T, ld, float(eps), _ptr(P), _ptr(stats), _stream())
-        O = torch.empty(B, T, H, hd, dtype=qkv.dtype, device=qkv.device)
-        for h in range(H):
-            torch.bmm(P[:, h, :, :T], q5[:, :, 2, h], out=O[:, :, h])
-        cls_attn = P[:, :, 0, :T].clone() if want_cls else None
-        ctx.save_for_backward(qkv, S, stats, pol if pol is not None else torch.empty(0, device=qkv.device))
-        ctx.meta = (B, T, H, hd, ld, float(scale), float(eps), pol is not None,
+        stats = torch.empty(B, H, T, 2, dtype=torch.float32, device=dev)
+        _lib.call("d2s_softmax_policy_fwd_ld", _ptr(S), _ptr(pol), B, H, T, Tp, Tp, float(eps), _ptr(P), _ptr(stats), _stream())
+        Oh = torch.bmm(P, qkvh[2])                                                    # (B*H, Tp, hd)
+        O = torch.empty(B, T, D, dtype=dt, device=dev)
+        _lib.call("d2s_merge_heads_bf16", _ptr(Oh), B, T, Tp, 1, H, hd, _ptr(O), _stream())
+        cls_attn = P.view(B, H, Tp, Tp)[:, :, 0, :T].clone() if want_cls else None
+        ctx.save_for_backward(qkvh, S, P, stats, pol if pol is not None else torch.empty(0, device=dev))
+        ctx.meta = (B, T, Tp, H, hd, float(scale), float(eps), pol is not None,
                     None if policy is None else (policy.shape, policy.dtype))
-        return O.view(B, T, D), cls_attn
+        return O, cls_attn
 
     @staticmethod
     def backward(ctx, gO, g_cls):
-        qkv, S, stats, pol = ctx.saved_tensors
-        B, T, H, hd, ld, scale, eps, has_pol, pol_meta = ctx.meta
+        qkvh, S, P, stats, pol = ctx.saved_tensors
+        B, T, Tp, H, hd, scale, eps, has_pol, pol_meta = ctx.meta
         polp = pol if has_pol else None
-        q5 = qkv.view(B, T, 3, H, hd)
-        g5 = gO.to(qkv.dtype).contiguous().view(B, T, H, hd)
-        P = torch.empty_like(S)
-        _lib.call("d2s_softmax_policy_fwd_ld", _ptr(S), _ptr(polp), B, H, T, ld, eps, _ptr(P), None, _stream())
-        dqkv = torch.empty_like(qkv)
-        d5 = dqkv.view(B, T, 3, H, hd)
-        dP = torch.empty_like(S)
-        for h in range(H):
-            torch.bmm(P[:, h, :, :T].transpose(1, 2), g5[:, :, h], out=d5[:, :, 2, h])          # dV = P^T dO
-            torch.bmm(g5[:, :, h], q5[:, :, 2, h].transpose(1, 2), out=dP[:, h, :, :T])          # dP = dO V^T
+        dev, dt = S.device, S.dtype
+        g = gO.to(dt).contiguous()
+        gOh = torch.empty(B * H, Tp, hd, dtype=dt, device=dev)
+        _lib.call("d2s_split_heads_bf16", _ptr(g), B, T, Tp, 1, H, hd, _ptr(gOh), _stream())
+        dqkvh = torch.empty(3, B * H, Tp, hd, dtype=dt, device=dev)
+        torch.bmm(P.transpose(1, 2), gOh, out=dqkvh[2])                               # dV = P^T dO
+        dP = torch.bmm(gOh, qkvh[2].transpose(1, 2))                                  # dP = dO V^T  (padding rows are zero)
         if g_cls is not None:
-            dP[:, :, 0, :T] += g_cls.to(dP.dtype)
-        gpol = torch.zeros(B, T, dtype=torch.float32, device=qkv.device) if has_pol else None
-        _lib.call("d2s_softmax_policy_bwd_ld", _ptr(S), _ptr(polp), _ptr(dP), _ptr(stats), B, H, T, ld, eps, _ptr(dP), _ptr(gpol),
-                  _stream())
-        for h in range(H):
-            dq, dk, ds = d5[:, :, 0, h], d5[:, :, 1, h], dP[:, h, :, :T]
-            torch.baddbmm(dq, ds, q5[:, :, 1, h], beta=0, alpha=scale, out=dq)                     # dQ = scale dS K
-            torch.baddbmm(dk, ds.transpose(1, 2), q5[:, :, 0, h], beta=0, alpha=scale, out=dk)     # dK = scale dS^T Q
+            dP.view(B, H, Tp, Tp)[:, :, 0, :T] += g_cls.to(dt)
+        gpol = torch.zeros(B, T, dtype=torch.float32, device=dev) if has_pol else None
+        _lib.call("d2s_softmax_policy_bwd_ld", _ptr(S), _ptr(polp), _ptr(dP), _ptr(stats), B, H, T, Tp, Tp, eps, _ptr(dP),
+                  _ptr(gpol), _stream())
+        torch.baddbmm(dqkvh[0], dP, qkvh[1], beta=0, alpha=scale, out=dqkvh[0])                    # dQ = scale dS K
+        torch.baddbmm(dqkvh[1], dP.transpose(1, 2), qkvh[0], beta=0, alpha=scale, out=dqkvh[1])    # dK = scale dS^T Q
+        dqkv = torch.empty(B, T, 3 * H * hd, dtype=dt, device=dev)
+        _lib.call("d2s_merge_heads_bf16", _ptr(dqkvh), B, T, Tp, 3, H, hd, _ptr(dqkv), _stream())
         if has_pol:
             gpol = gpol.reshape(pol_meta[0]).to(pol_meta[1])
         return dqkv, gpol, None, None, None, None

@@ -131,11 +131,18 @@ int d2s_softmax_policy_bwd(const void* attn, const float* policy, const void* go
 
 /* Padded-row variants used by the training attention (ops.attention_train): bf16 only, tensors are (B,H,T,ld) with
  * ld % 8 == 0, T <= ld <= 256, so every row is 16-byte aligned and moved with 16-byte accesses; padding columns of `out`
- * / `gattn` are written as zeros.  gattn may alias gout. */
-int d2s_softmax_policy_fwd_ld(const void* attn, const float* policy, int B, int H, int T, int ld, float eps, void* out,
-                              float* stats, d2s_stream_t stream);
+ * / `gattn` are written as zeros.  gattn may alias gout.  `rows` >= T is the row count of the buffers (rows T..rows-1 of
+ * `out` are zero-filled by the forward so the padded tensor can be a GEMM operand; the backward leaves them untouched). */
+int d2s_softmax_policy_fwd_ld(const void* attn, const float* policy, int B, int H, int T, int rows, int ld, float eps,
+                              void* out, float* stats, d2s_stream_t stream);
 int d2s_softmax_policy_bwd_ld(const void* attn, const float* policy, const void* gout, const float* stats, int B, int H,
-                              int T, int ld, float eps, void* gattn, float* gpolicy, d2s_stream_t stream);
+                              int T, int rows, int ld, float eps, void* gattn, float* gpolicy, d2s_stream_t stream);
+
+/* Head-major relayout for the training attention (dynamic_vit.py:218-221), bf16: token-major packed (B,T,G,H,hd)
+ * (G = 3: qkv Linear output; G = 1: attention output / its gradient) <-> head-major (G,B,H,Tp,hd), Tp >= T; split writes
+ * the padding rows T..Tp-1 as zeros, merge drops them.  hd % 8 == 0. */
+int d2s_split_heads_bf16(const void* src, int B, int T, int Tp, int G, int H, int hd, void* dst, d2s_stream_t stream);
+int d2s_merge_heads_bf16(const void* src, int B, int T, int Tp, int G, int H, int hd, void* dst, d2s_stream_t stream);
 
 /* Fused attention core of Attention.forward (dynamic_vit.py:218-234; default_dynamic_vit.py:203-213):
  * qkv (B,T,3,H,hd) packed as produced by the qkv Linear; out (B,T,H*hd) ready for the proj Linear;
