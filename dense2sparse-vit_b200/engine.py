@@ -217,10 +217,17 @@ class _Stream:
         return norm(self.value())[:, 0]
 
 
+def _seq_forward(layers, h):
+    """A predictor nn.Sequential on the training path: its LayerNorms run on the d2s forward/backward kernels."""
+    for layer in layers:
+        h = norm_forward(layer, h) if isinstance(layer, torch.nn.LayerNorm) else layer(h)
+    return h
+
+
 # ---- Variant A predictor (default_dynamic_vit.py:304-330) ------------------------------------------
 def predictor_a_hidden(m, x, policy, normed=None):
     """`normed`: in_conv's LayerNorm already applied (by the fused add+LayerNorm kernel)."""
-    h = m.in_conv(x) if normed is None else m.in_conv[2](m.in_conv[1](normed))
+    h = _seq_forward(m.in_conv, x) if normed is None else m.in_conv[2](m.in_conv[1](normed))
     B, N, C = h.shape
     half = C // 2
     pooled = (h[:, :, half:] * policy).sum(dim=1, keepdim=True) / torch.sum(policy, dim=1, keepdim=True)
@@ -274,15 +281,13 @@ def _predictor_b_tail_parts(m):
 
 
 def predictor_b_hidden(m, x, normed=None):
-    h = m.in_conv(x) if normed is None else m.in_conv[2](m.in_conv[1](normed))
+    h = _seq_forward(m.in_conv, x) if normed is None else m.in_conv[2](m.in_conv[1](normed))
     B, N, C = h.shape
     half = C // 2
     pooled = torch.mean(h[:, :, half:], dim=1, keepdim=True)
     h = torch.cat([h[:, :, :half], pooled.expand(B, N, half)], dim=-1)
     body, norm, lin = _predictor_b_tail_parts(m)
-    for layer in body:
-        h = layer(h)
-    return h, norm, lin
+    return _seq_forward(body, h), norm, lin
 
 
 def _act_code(a):
@@ -342,7 +347,7 @@ def predictor_b_forward(m, x, policy=None, current_sigma=0.0005, cls_attn=None, 
     h, norm, lin = predictor_b_hidden(m, x, normed)
     prob_mode = ops.PROB_SOFTMAX if m.loss_type in ["kl_div", "mse"] else ops.PROB_SIGMOID
     if _needs_grad(h, lin.weight):
-        scores = lin(norm(h)).flatten(-2, -1)
+        scores = lin(norm_forward(norm, h)).flatten(-2, -1)
         probs = F.softmax(scores, dim=-1) if prob_mode == ops.PROB_SOFTMAX else torch.sigmoid(scores)
         if k_select is None:
             return scores, probs
@@ -373,7 +378,12 @@ def _embed(model, img):
 
 
 def _head(model, x):
-    x = model.norm(x)
+    # training heads: the final norm keeps torch autocast's fp32 output (the token features go straight into the losses)
+    if _is_plain_ln(model.norm) and x.is_cuda and x.shape[-1] % 8 == 0 and x.shape[-1] <= 768 and x.dtype in (torch.float32, torch.bfloat16):
+        x = ops.layer_norm(x, model.norm.weight, model.norm.bias, model.norm.eps,
+                           out_dtype=torch.float32 if torch.is_autocast_enabled("cuda") else None)
+    else:
+        x = model.norm(x)
     features = x[:, 1:]
     return model.head(model.pre_logits(x[:, 0])), features
 
