@@ -115,10 +115,19 @@ softmax_policy_fwd_vec_kernel(const __nv_bfloat16* __restrict__ attn, const floa
   for (int k = 0; k < 8; ++k) pol[k] = (policy && j0 + k < T) ? policy[(size_t)b * T + j0 + k] : 1.0f;
   const float c = policy ? eps / (float)T : 0.0f;
   const float eps_den = policy ? eps : 0.0f;
+  // rows of one warp are 8 apart; the next row's vector is requested before the current row is processed (two loads in
+  // flight per lane: the kernel is latency-bound otherwise)
+  int4 nxt = make_int4(0, 0, 0, 0);
+  {
+    const int i = blockIdx.x * kRowsPerCta + warp;
+    if (active && i < row_end) nxt = ld_stream16(attn + ((size_t)bh * rows + i) * ld + j0);
+  }
   for (int i = blockIdx.x * kRowsPerCta + warp; i < row_end; i += kRowWarps) {
     const size_t base = ((size_t)bh * rows + i) * ld + j0;
     float s[8];
-    if (active) unpack8(ld_stream16(attn + base), s);
+    const int4 cur = nxt;
+    if (active && i + kRowWarps < row_end) nxt = ld_stream16(attn + base + (size_t)kRowWarps * ld);
+    if (active) unpack8(cur, s);
     float m = -INFINITY;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
@@ -153,16 +162,16 @@ softmax_policy_fwd_vec_kernel(const __nv_bfloat16* __restrict__ attn, const floa
       *reinterpret_cast<uint4*>(out + ((size_t)bh * rows + i) * ld + j0) = make_uint4(0, 0, 0, 0);
 }
 
-__global__ void __launch_bounds__(kRowThreads)
+// The gradient through the subtracted row max (dense kernel above: routed to the first argmax) is sum_j dS_ij = O(eps) * g,
+// i.e. 1e-6 relative: below bf16 resolution, so this bf16-only kernel leaves it out (and with it the argmax bookkeeping).
+__global__ void __launch_bounds__(kRowThreads, 3)
 softmax_policy_bwd_vec_kernel(const __nv_bfloat16* __restrict__ attn, const float* __restrict__ policy,
                               const __nv_bfloat16* __restrict__ gout, const float* __restrict__ stats, int H, int T, int rows,
                               int ld, float eps, __nv_bfloat16* __restrict__ gattn, float* __restrict__ gpolicy) {
-  __shared__ float gp_s[256];
+  __shared__ float gp_s[kRowWarps][256];   // per-warp partial d policy (no shared-memory float atomics: those are CAS loops)
   const int bh = blockIdx.y, b = bh / H;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int row_end = min(T, (int)(blockIdx.x + 1) * kRowsPerCta);
-  gp_s[threadIdx.x] = 0.f;
-  __syncthreads();
   const int j0 = lane * 8;
   const bool active = j0 < ld;
   float pol[8], gp[8];
@@ -172,23 +181,34 @@ softmax_policy_bwd_vec_kernel(const __nv_bfloat16* __restrict__ attn, const floa
     gp[k] = 0.f;
   }
   const float c = policy ? eps / (float)T : 0.0f;
+  int4 nS = make_int4(0, 0, 0, 0), nG = nS;
+  {
+    const int i = blockIdx.x * kRowsPerCta + warp;
+    if (active && i < row_end) {
+      nS = ld_stream16(attn + ((size_t)bh * rows + i) * ld + j0);
+      nG = ld_stream16(gout + ((size_t)bh * rows + i) * ld + j0);
+    }
+  }
   for (int i = blockIdx.x * kRowsPerCta + warp; i < row_end; i += kRowWarps) {
     const size_t base = ((size_t)bh * rows + i) * ld + j0;
     const float m = stats[((size_t)bh * T + i) * 2];
     const float rden = 1.0f / stats[((size_t)bh * T + i) * 2 + 1];
     float sv[8], g[8], ex[8], a[8];
-    if (active) {
-      unpack8(ld_stream16(attn + base), sv);
-      unpack8(ld_stream16(gout + base), g);
+    const int4 cS = nS, cG = nG;
+    if (active && i + kRowWarps < row_end) {     // next row of this warp: in flight while this one is processed
+      nS = ld_stream16(attn + base + (size_t)kRowWarps * ld);
+      nG = ld_stream16(gout + base + (size_t)kRowWarps * ld);
     }
-    float gdotp = 0.f, best = -INFINITY;
-    int best_j = 0x7fffffff;
+    if (active) {
+      unpack8(cS, sv);
+      unpack8(cG, g);
+    }
+    float gdotp = 0.f;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const int j = j0 + k;
       ex[k] = a[k] = 0.f;
       if (active && j < T) {
-        if (sv[k] > best) { best = sv[k]; best_j = j; }
         ex[k] = exp_fast(sub_in_dtype(sv[k], m, attn));
         a[k] = ex[k] * ((j == i) ? 1.0f : pol[k]);
         gdotp += g[k] * ((a[k] + c) * rden);
@@ -198,33 +218,25 @@ softmax_policy_bwd_vec_kernel(const __nv_bfloat16* __restrict__ attn, const floa
     }
     gdotp = warp_sum(gdotp);
     float ds[8];
-    float ds_sum = 0.f;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const int j = j0 + k;
       const float da = (g[k] - gdotp) * rden;
-      ds[k] = (active && j < T) ? da * a[k] : 0.f;
-      ds_sum += ds[k];
+      ds[k] = da * a[k];                          // a == 0 outside the row
       if (active && j < T && j != i) gp[k] += da * ex[k];
-    }
-    if (policy) {   // the gradient through the subtracted row max goes to its first occurrence (plain softmax: vanishes)
-      ds_sum = warp_sum(ds_sum);
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-        const int oj = __shfl_xor_sync(0xffffffffu, best_j, o);
-        if (ob > best || (ob == best && oj < best_j)) { best = ob; best_j = oj; }
-      }
-#pragma unroll
-      for (int k = 0; k < 8; ++k) ds[k] -= (j0 + k == best_j ? ds_sum : 0.f);
     }
     if (active) *reinterpret_cast<uint4*>(gattn + base) = pack8(ds);
   }
   if (gpolicy && policy) {
-#pragma unroll
-    for (int k = 0; k < 8; ++k) atomicAdd(&gp_s[j0 + k], gp[k]);
+    *reinterpret_cast<float4*>(&gp_s[warp][j0]) = make_float4(gp[0], gp[1], gp[2], gp[3]);
+    *reinterpret_cast<float4*>(&gp_s[warp][j0 + 4]) = make_float4(gp[4], gp[5], gp[6], gp[7]);
     __syncthreads();
-    for (int j = threadIdx.x; j < T; j += kRowThreads) atomicAdd(&gpolicy[(size_t)b * T + j], gp_s[j]);
+    for (int j = threadIdx.x; j < T; j += kRowThreads) {
+      float acc = 0.f;
+#pragma unroll
+      for (int w = 0; w < kRowWarps; ++w) acc += gp_s[w][j];
+      atomicAdd(&gpolicy[(size_t)b * T + j], acc);
+    }
   }
 }
 

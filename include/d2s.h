@@ -132,7 +132,9 @@ int d2s_softmax_policy_bwd(const void* attn, const float* policy, const void* go
 /* Padded-row variants used by the training attention (ops.attention_train): bf16 only, tensors are (B,H,T,ld) with
  * ld % 8 == 0, T <= ld <= 256, so every row is 16-byte aligned and moved with 16-byte accesses; padding columns of `out`
  * / `gattn` are written as zeros.  gattn may alias gout.  `rows` >= T is the row count of the buffers (rows T..rows-1 of
- * `out` are zero-filled by the forward so the padded tensor can be a GEMM operand; the backward leaves them untouched). */
+ * `out` are zero-filled by the forward so the padded tensor can be a GEMM operand; the backward leaves them untouched).
+ * The backward omits the gradient through the subtracted row max (sum_j dS_ij = O(eps) * g ~ 1e-6 relative, below bf16
+ * resolution; d2s_softmax_policy_bwd keeps it for the fp32 parity runs). */
 int d2s_softmax_policy_fwd_ld(const void* attn, const float* policy, int B, int H, int T, int rows, int ld, float eps,
                               void* out, float* stats, d2s_stream_t stream);
 int d2s_softmax_policy_bwd_ld(const void* attn, const float* policy, const void* gout, const float* stats, int B, int H,
