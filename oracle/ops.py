@@ -358,3 +358,13 @@ def assemble_tokens(patches, cls_token, pos_embed):
     B = patches.shape[0]
     x = torch.cat([cls_token.reshape(1, 1, -1).expand(B, -1, -1).to(patches.dtype), patches], dim=1)
     return x + pos_embed.reshape(1, x.shape[1], -1).to(patches.dtype)
+
+
+def linear_residual_ln(a, w, b, x, gamma, beta, eps):
+    """attn.proj / mlp.fc2 + residual add + the next LayerNorm of Block.forward (vit_models/dynamic_vit.py:263-283) as the
+    reference's bf16 modules compute them: Linear output rounded to bf16, residual sum rounded to bf16, LayerNorm statistics in
+    fp32 and its output rounded to bf16.  Inputs are bf16 tensors; returns (x', h) in bf16."""
+    y = F.linear(a.float(), w.float(), None if b is None else b.float()).bfloat16()
+    s = (x.float() + y.float()).bfloat16()
+    h = F.layer_norm(s.float(), (s.shape[-1],), gamma.float(), beta.float(), eps).bfloat16()
+    return s, h
