@@ -36,8 +36,14 @@ def sources():
     return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
 
 
+def _extra_flags():
+    """Extra nvcc flags for profiling builds, e.g. D2S_NVCC_EXTRA=-DD2S_GEMM_TRACE_BUILD (clock64 phase traces)."""
+    return os.environ.get("D2S_NVCC_EXTRA", "").split()
+
+
 def _fingerprint():
     h = hashlib.sha256()
+    h.update(" ".join(_extra_flags()).encode())
     files = sources() + sorted(glob.glob(os.path.join(CSRC, "*.cuh"))) + \
         [os.path.join(PKG_DIR, "..", "include", "d2s.h"), os.path.abspath(__file__)]
     for f in files:
@@ -61,7 +67,7 @@ def build(force=False, verbose=False):
     for src in sources():
         obj = os.path.join(obj_dir, os.path.basename(src)[:-3] + ".o")
         objs.append(obj)
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+        cmd = [nvcc] + NVCC_FLAGS + _extra_flags() + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     failed = False
     for src, p in procs:

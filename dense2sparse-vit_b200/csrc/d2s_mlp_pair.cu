@@ -1,0 +1,449 @@
+// The whole MLP branch of Block.forward in ONE kernel (vit_models/dynamic_vit.py:159-175, :263-283; SURVEY.md section 8f
+// rank 1 "fuse LN2 + MLP"), inference, bf16, D = 384:
+//
+//     u  = GELU(h W1^T + b1)            (B*T, 4D)   never leaves the SM
+//     x' = x + bf16(u W2^T + b2)        residual stream
+//     hn = LayerNorm(x') gamma + beta   input of the next block's attention (optional)
+//
+// Separately, fc1 + GELU writes and fc2 re-reads the (B*T, 4D) hidden tensor: 1.24 GB per layer at B = 1024, T = 197, which
+// makes fc1 store-bound and is 60 % of the MLP's HBM traffic.  Here a CTA pair (tcgen05 cta_group::2, 256 rows) walks the
+// hidden dimension in chunks of 64 columns:
+//     G1(j): S_j (256 x 64)   = H (256 x 384, resident in shared memory)  x  W1[64 j .. 64 j + 63, :]^T        -> TMEM
+//     E1(j): P_j = bf16(GELU(S_j + b1))  TMEM -> registers -> shared memory as the SWIZZLE_128B A operand of
+//     G2(j): ACC (256 x 384) += P_j (256 x 64)  x  W2[:, 64 j .. 64 j + 63]^T                                   -> TMEM
+// with S double-buffered in TMEM (384 + 2 x 64 = 512 columns) and P double-buffered in shared memory, so the tensor pipe runs
+// G1(j+2) and G2(j) while two groups of 8 epilogue warps compute E1(j) and E1(j+1).  W1 / W2 chunks stream from L2 through two TMA rings (each CTA
+// loads half of every weight tile).  After the last chunk the same epilogue as d2s_gemm_pair.cu's MODE_LN runs from ACC:
+// bias, round, residual add, LayerNorm statistics, x' and hn written as coalesced row segments; the rows of the residual
+// are fetched into registers while the last chunks are still in the tensor pipe.
+//
+//   warp 0      TMA producer: H tile (once per row tile) and W1 k-blocks      warp 2   TMA producer: W2 chunks
+//   warp 1      TMEM allocation; G1 issue (leader CTA only)                   warp 3   G2 issue (leader CTA only)
+//   warps 4-19  epilogue (four warps per TMEM lane quadrant)
+#include <stdlib.h>
+#include "d2s_tc.cuh"
+
+namespace d2s {
+
+constexpr int kMpBM = 128, kMpD = 384, kMpCH = 64, kMpKB = kMpD / 64;
+constexpr int kMpW1Slots = 8, kMpW2Slots = 2;
+constexpr uint32_t kMpA1Blk = 128 * 128;        // 16 KB: 128 rows x 64 bf16 of H
+constexpr uint32_t kMpW1Blk = 32 * 128;         //  4 KB: this CTA's 32 of the 64 W1 rows of a chunk, one k-block
+constexpr uint32_t kMpW2Half = 96 * 128;        // 12 KB: this CTA's 96 of the 192 W2 rows of one N-half, 64 hidden columns
+constexpr uint32_t kMpW2Blk = 2 * kMpW2Half;    // 24 KB
+constexpr uint32_t kMpPBlk = 128 * 128;         // 16 KB: 128 rows x 64 bf16 of P_j
+constexpr int kMpEpiWarps = 16, kMpThreads = (4 + kMpEpiWarps) * 32;
+constexpr uint32_t kMpAccCols = 384, kMpSCols = 64;
+
+struct MpBars {
+  uint64_t a1_full[kMpKB], a1_empty[kMpKB], w1_full[kMpW1Slots], w1_empty[kMpW1Slots], w2_full[kMpW2Slots], w2_empty[kMpW2Slots];
+  uint64_t s_full[2], s_empty[2], p_full[2], p_empty[2], acc_full, acc_empty;
+  uint32_t tmem_base, pad;
+};
+
+struct MpParams {
+  long long* trace;             // profiling builds (-DD2S_GEMM_TRACE_BUILD): clock64 totals of the MMA thread's waits
+  const __nv_bfloat16 *b1, *b2, *gamma, *beta, *x;
+  __nv_bfloat16 *out_sum, *out_norm;
+  float eps;
+  int M, HID, want_ln;
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __maxnreg__(96)
+mlp_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w1,
+                const __grid_constant__ CUtensorMap map_w2, const MpParams p) {
+  constexpr int TN = kMpD;
+  extern __shared__ unsigned char smem_dyn[];
+  const uint32_t raw = smem_u32(smem_dyn);
+  const uint32_t padb = (1024u - (raw & 1023u)) & 1023u;
+  unsigned char* a1_s = smem_dyn + padb;                                  // 6 x 16 KB
+  unsigned char* p_s = a1_s + kMpKB * kMpA1Blk;                           // 2 x 16 KB (also the per-warp transposition buffers)
+  unsigned char* w1_s = p_s + 2 * kMpPBlk;                                // 8 x 4 KB
+  unsigned char* w2_s = w1_s + kMpW1Slots * kMpW1Blk;                     // 2 x 24 KB
+  MpBars* bars = reinterpret_cast<MpBars*>(w2_s + kMpW2Slots * kMpW2Blk);
+  float* b1_s = reinterpret_cast<float*>(bars + 1);                       // HID
+  float* b2_s = b1_s + p.HID;                                             // 3 x 384: b2, gamma, beta
+  float2* red_s = reinterpret_cast<float2*>(b2_s + 3 * TN);               // [4][128] partial LayerNorm statistics
+  volatile uint32_t* sel_s = reinterpret_cast<volatile uint32_t*>(red_s + 4 * 128);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int warp_u = warp_uniform(warp), rank_u = warp_uniform((int)rank);
+  const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+  const int pair_tiles = (p.M + 2 * kMpBM - 1) / (2 * kMpBM);
+  const int nch = p.HID / kMpCH;
+
+  if (tid == 0) {
+    for (int i = 0; i < kMpKB; ++i) { mbar_init(smem_u32(&bars->a1_full[i]), 1); mbar_init(smem_u32(&bars->a1_empty[i]), 1); }
+    for (int i = 0; i < kMpW1Slots; ++i) { mbar_init(smem_u32(&bars->w1_full[i]), 1); mbar_init(smem_u32(&bars->w1_empty[i]), 1); }
+    for (int i = 0; i < kMpW2Slots; ++i) { mbar_init(smem_u32(&bars->w2_full[i]), 1); mbar_init(smem_u32(&bars->w2_empty[i]), 1); }
+    for (int i = 0; i < 2; ++i) {   // one epilogue group (8 warps) per CTA arrives per chunk
+      mbar_init(smem_u32(&bars->s_full[i]), 1);
+      mbar_init(smem_u32(&bars->p_empty[i]), 1);
+      mbar_init(smem_u32(&bars->s_empty[i]), 2 * 8);
+      mbar_init(smem_u32(&bars->p_full[i]), 2 * 8);
+    }
+    mbar_init(smem_u32(&bars->acc_full), 1);
+    mbar_init(smem_u32(&bars->acc_empty), 2 * kMpEpiWarps);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    sel_s[0] = 0x1044u;   // byte-permute selectors {0, 0, b0, b1} and {0, 0, b2, b3}: bf16 pair -> two fp32
+    sel_s[1] = 0x3244u;
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)), "n"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  for (int i = tid; i < p.HID; i += kMpThreads) b1_s[i] = p.b1 ? __bfloat162float(p.b1[i]) : 0.f;
+  for (int i = tid; i < TN; i += kMpThreads) {
+    b2_s[i] = p.b2 ? __bfloat162float(p.b2[i]) : 0.f;
+    b2_s[TN + i] = p.gamma ? __bfloat162float(p.gamma[i]) : 1.f;
+    b2_s[2 * TN + i] = p.beta ? __bfloat162float(p.beta[i]) : 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem = bars->tmem_base;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ============================ TMA producer: H tile + W1 k-blocks (both CTAs) ============================
+      uint32_t w1_it = 0, tile_i = 0;
+      for (int pt = pair; pt < pair_tiles; pt += num_pairs, ++tile_i) {
+        const int row0 = pt * 2 * kMpBM + (int)rank * kMpBM;
+        if (pt + num_pairs < pair_tiles)      // next row tile's activations: pull them into L2 now, the TMA loads at the tile
+          for (int kb = 0; kb < kMpKB; ++kb)  // boundary then see L2 latency instead of HBM latency
+            asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];"
+                         ::"l"(reinterpret_cast<uint64_t>(&map_a)), "r"(kb * 64), "r"(row0 + num_pairs * 2 * kMpBM) : "memory");
+        for (int j = 0; j < nch; ++j)
+          for (int kb = 0; kb < kMpKB; ++kb, ++w1_it) {
+            if (j == 0) {   // the row tile's activations: resident for all chunks, refilled k-block by k-block
+              mbar_wait(smem_u32(&bars->a1_empty[kb]), (tile_i & 1) ^ 1);
+              const uint32_t fl = smem_u32(&bars->a1_full[kb]);
+              if (rank == 0) mbar_expect_tx(fl, 2 * kMpA1Blk);
+              tma_load_2d_pair(smem_u32(a1_s + kb * kMpA1Blk), &map_a, kb * 64, row0, mapa(fl, 0));
+            }
+            const uint32_t s = w1_it % kMpW1Slots, n = w1_it / kMpW1Slots;
+            mbar_wait(smem_u32(&bars->w1_empty[s]), (n & 1) ^ 1);
+            const uint32_t fl = smem_u32(&bars->w1_full[s]);
+            if (rank == 0) mbar_expect_tx(fl, 2 * kMpW1Blk);
+            tma_load_2d_pair(smem_u32(w1_s + s * kMpW1Blk), &map_w1, kb * 64, j * kMpCH + (int)rank * (kMpCH / 2), mapa(fl, 0));
+          }
+      }
+    }
+  } else if (warp == 2) {
+    if (lane == 0) {
+      // ================================ TMA producer: W2 chunks (both CTAs) ================================
+      uint32_t it = 0;
+      for (int pt = pair; pt < pair_tiles; pt += num_pairs)
+        for (int j = 0; j < nch; ++j, ++it) {
+          const uint32_t s = it % kMpW2Slots, n = it / kMpW2Slots;
+          mbar_wait(smem_u32(&bars->w2_empty[s]), (n & 1) ^ 1);
+          const uint32_t fl = smem_u32(&bars->w2_full[s]);
+          if (rank == 0) mbar_expect_tx(fl, 2 * kMpW2Blk);
+          const uint32_t dst = smem_u32(w2_s + s * kMpW2Blk);
+#pragma unroll
+          for (int jn = 0; jn < 2; ++jn)
+            tma_load_2d_pair(dst + jn * kMpW2Half, &map_w2, j * kMpCH, jn * 192 + (int)rank * 96, mapa(fl, 0));
+        }
+    }
+  } else if (warp_u == 1) {
+    if (rank_u == 0) {
+      // ====== G1 issuer (leader): S_c = H x W1_chunk^T.  The whole warp runs the loop, one elected lane issues (see elect_one).
+      // G1 and G2 have their own issuing warps: a single in-order issuer would hold back ready G2 work while it waits for an
+      // S buffer (and vice versa); the tensor pipe interleaves the two instruction streams as their operands become ready. ======
+      const uint32_t idesc1 = make_idesc(2 * kMpBM, kMpCH, 0);
+      uint32_t w1_it = 0, c = 0, tile_i = 0;
+      for (int pt = pair; pt < pair_tiles; pt += num_pairs, ++tile_i)
+        for (int j = 0; j < nch; ++j, ++c) {
+          const uint32_t sb = c & 1, use = c >> 1;
+          mbar_wait(smem_u32(&bars->s_empty[sb]), (use & 1) ^ 1);            // E1 two chunks ago has read this S buffer
+          tc_fence_after();
+          const uint32_t d = tmem + kMpAccCols + sb * kMpSCols;
+          for (int kb = 0; kb < kMpKB; ++kb, ++w1_it) {
+            if (j == 0) mbar_wait(smem_u32(&bars->a1_full[kb]), tile_i & 1);
+            const uint32_t s = w1_it % kMpW1Slots, n = w1_it / kMpW1Slots;
+            mbar_wait(smem_u32(&bars->w1_full[s]), n & 1);
+            tc_fence_after();
+            const uint64_t ad = make_desc_sw128(smem_u32(a1_s + kb * kMpA1Blk), 16, 1024);
+            const uint64_t bd = make_desc_sw128(smem_u32(w1_s + s * kMpW1Blk), 16, 1024);
+            if (elect_one()) {
+              if (kb == 0) mma2_ss_imm<false>(d, ad, bd, idesc1); else mma2_ss_imm<true>(d, ad, bd, idesc1);
+              mma2_ss_imm<true>(d, ad + 2, bd + 2, idesc1);
+              mma2_ss_imm<true>(d, ad + 4, bd + 4, idesc1);
+              mma2_ss_imm<true>(d, ad + 6, bd + 6, idesc1);
+              mma2_commit_both(smem_u32(&bars->w1_empty[s]));
+              if (j == nch - 1) mma2_commit_both(smem_u32(&bars->a1_empty[kb]));   // last reader of this H k-block
+            }
+            __syncwarp();
+          }
+          if (elect_one()) mma2_commit_both(smem_u32(&bars->s_full[sb]));
+          __syncwarp();
+        }
+    }
+  } else if (warp_u == 3) {
+    if (rank_u == 0) {
+      // ====== G2 issuer (leader): ACC += P_c x W2_chunk^T ======
+      const uint32_t idesc2 = make_idesc(2 * kMpBM, 192, 0);
+      uint32_t c = 0, tile_i = 0;
+      for (int pt = pair; pt < pair_tiles; pt += num_pairs, ++tile_i)
+        for (int j = 0; j < nch; ++j, ++c) {
+          const uint32_t pb = c & 1, use = c >> 1;
+          mbar_wait(smem_u32(&bars->p_full[pb]), use & 1);                     // both CTAs' epilogues have written P
+          const uint32_t s = c % kMpW2Slots, n = c / kMpW2Slots;
+          mbar_wait(smem_u32(&bars->w2_full[s]), n & 1);
+          if (j == 0) mbar_wait(smem_u32(&bars->acc_empty), (tile_i & 1) ^ 1);   // previous tile's epilogue has drained ACC
+          tc_fence_after();
+          const uint64_t ad = make_desc_sw128(smem_u32(p_s + pb * kMpPBlk), 16, 1024);
+          if (elect_one()) {
+#pragma unroll
+            for (int jn = 0; jn < 2; ++jn) {
+              const uint64_t bd = make_desc_sw128(smem_u32(w2_s + s * kMpW2Blk + jn * kMpW2Half), 16, 1024);
+              const uint32_t d = tmem + jn * 192;
+              if (j == 0) mma2_ss_imm<false>(d, ad, bd, idesc2); else mma2_ss_imm<true>(d, ad, bd, idesc2);
+              mma2_ss_imm<true>(d, ad + 2, bd + 2, idesc2);
+              mma2_ss_imm<true>(d, ad + 4, bd + 4, idesc2);
+              mma2_ss_imm<true>(d, ad + 6, bd + 6, idesc2);
+            }
+            mma2_commit_both(smem_u32(&bars->w2_empty[s]));
+            mma2_commit_both(smem_u32(&bars->p_empty[pb]));
+            if (j == nch - 1) mma2_commit_both(smem_u32(&bars->acc_full));
+          }
+          __syncwarp();
+        }
+    }
+  } else {
+    // ========================================= epilogue (both CTAs) =========================================
+    const int ew = warp - 4;                    // 0..15
+    const int quad = warp & 3;                  // TMEM lane quadrant of this warp
+    const int part = ew >> 2;                   // final epilogue: which quarter of the columns
+    const uint32_t grp = (uint32_t)ew >> 3;     // E1: which chunks (chunk number % 2 == grp)
+    const int half = part & 1;                  // E1: which 32 of the chunk's 64 columns
+    const int r = quad * 32 + lane;             // row inside this CTA's 128-row tile
+    const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16);
+    constexpr int NCH = TN / 32, CPT = NCH / 4;                 // final epilogue: 32-column chunks ch = 4 ci + part
+    const float* gamma_s = b2_s + TN;
+    const float* beta_s = b2_s + 2 * TN;
+    unsigned char* buf = p_s + ew * 2048;                        // per-warp [32 rows x 64 B] transposition buffer (P is idle then)
+    const int crow = lane >> 2, cseg = lane & 3;                 // coalesced pattern: 4 lanes x 16 B cover one row's 64 bytes
+    const uint32_t own_off = (uint32_t)lane * 64, own_sw = (uint32_t)(lane >> 1) & 3u;
+    uint32_t e_base = 0, tile_i = 0;
+    for (int pt = pair; pt < pair_tiles; pt += num_pairs, ++tile_i) {
+      const int row0 = pt * 2 * kMpBM + (int)rank * kMpBM + quad * 32;     // first row of this warp
+      uint32_t xr[CPT][16];      // residual rows: coalesced layout first, one row per lane after the transposition
+      // ---- E1(j): P_j = bf16(GELU(S_j + b1)).  Two groups of 8 warps (two per TMEM lane quadrant, 32 columns each) take the
+      // chunks alternately, each always on its own S / P buffer (chunk number mod 2): two chunks are in the activation stage at
+      // once, and a group sees every phase of the barriers it waits on. ----
+      for (int j = (int)((grp + e_base) & 1u); j < nch; j += 2) {
+        const uint32_t c = e_base + (uint32_t)j;                 // global chunk number; c & 1 == grp
+        const uint32_t use = c >> 1;
+        mbar_wait(smem_u32(&bars->s_full[grp]), use & 1);
+        tc_fence_after();
+        uint32_t v[32];
+        tmem_ld32_nowait(lane_addr + kMpAccCols + grp * kMpSCols + half * 32, v);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(mapa(smem_u32(&bars->s_empty[grp]), 0));   // S_j is in registers
+        uint32_t o[16];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+          const float2 bq = *reinterpret_cast<const float2*>(&b1_s[j * kMpCH + half * 32 + 2 * q]);
+          float g0, g1;
+          f2_unpack(gelu_erf_pair(f2_add(f2_pack(__uint_as_float(v[2 * q]), __uint_as_float(v[2 * q + 1])), f2_pack(bq.x, bq.y))), g0, g1);
+          o[q] = pack_bf16x2(g0, g1);
+        }
+        mbar_wait(smem_u32(&bars->p_empty[grp]), (use & 1) ^ 1);                      // G2(j - 2) has read this P buffer
+        unsigned char* blk = p_s + grp * kMpPBlk;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          *reinterpret_cast<uint4*>(blk + sw128_off(r, half * 4 + k)) = make_uint4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");                  // generic-proxy writes -> visible to the MMA
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(mapa(smem_u32(&bars->p_full[grp]), 0));
+      }
+      e_base += (uint32_t)nch;
+      {
+        // residual rows for the final epilogue: coalesced loads, in flight while the last chunks finish
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int grow = min(row0 + crow + 8 * i, p.M - 1);        // rows past M re-read the last row, never stored
+          const __nv_bfloat16* xp = p.x + (size_t)grow * TN + part * 32 + cseg * 8;
+#pragma unroll
+          for (int ci = 0; ci < CPT; ++ci) {
+            const uint4 t = ld_nc16(xp + ci * 128);
+            xr[ci][4 * i] = t.x; xr[ci][4 * i + 1] = t.y; xr[ci][4 * i + 2] = t.z; xr[ci][4 * i + 3] = t.w;
+          }
+        }
+      }
+      // ---- final epilogue: x' = x + bf16(ACC + b2), LayerNorm ----
+      mbar_wait(smem_u32(&bars->acc_full), tile_i & 1);      // all G2 of this tile retired: ACC complete, P buffers idle
+      tc_fence_after();
+      const size_t goff = (size_t)(row0 + crow) * TN + part * 32 + cseg * 8;
+      const int rows_left = p.M - row0 - crow;
+#pragma unroll
+      for (int ci = 0; ci < CPT; ++ci) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int row = 8 * i + crow;
+          *reinterpret_cast<uint4*>(buf + row * 64 + ((cseg ^ ((row >> 1) & 3)) << 4)) =
+              make_uint4(xr[ci][4 * i], xr[ci][4 * i + 1], xr[ci][4 * i + 2], xr[ci][4 * i + 3]);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const uint4 t = *reinterpret_cast<const uint4*>(buf + own_off + (((uint32_t)q ^ own_sw) << 4));
+          xr[ci][4 * q] = t.x; xr[ci][4 * q + 1] = t.y; xr[ci][4 * q + 2] = t.z; xr[ci][4 * q + 3] = t.w;
+        }
+        __syncwarp();
+      }
+      uint64_t acc_s = f2_bcast(0.f), acc_q = f2_bcast(0.f);
+#pragma unroll
+      for (int ci = 0; ci < CPT; ++ci) {
+        const int ch = 4 * ci + part;
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          uint32_t v[16];
+          tmem_ld16_nowait(lane_addr + ch * 32 + hh * 16, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float2 bq = *reinterpret_cast<const float2*>(&b2_s[ch * 32 + hh * 16 + 2 * q]);
+            float y0, y1;
+            f2_unpack(f2_add(f2_pack(__uint_as_float(v[2 * q]), __uint_as_float(v[2 * q + 1])), f2_pack(bq.x, bq.y)), y0, y1);
+            const uint32_t yb = pack_bf16x2(y0, y1);                  // fc2's bf16 output
+            const uint32_t sb2 = add_bf16x2(xr[ci][hh * 8 + q], yb);    // the residual add's bf16 output
+            xr[ci][hh * 8 + q] = sb2;
+            const uint64_t sv = f2_pack(bf16_lo(sb2), bf16_hi(sb2));
+            acc_s = f2_add(acc_s, sv);
+            acc_q = f2_fma(sv, sv, acc_q);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa(smem_u32(&bars->acc_empty), 0));     // the next tile's G2(0) may start
+      {
+        float s0, s1, q0, q1;
+        f2_unpack(acc_s, s0, s1);
+        f2_unpack(acc_q, q0, q1);
+        red_s[part * 128 + r] = make_float2(s0 + s1, q0 + q1);
+      }
+#pragma unroll
+      for (int ci = 0; ci < CPT; ++ci) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          *reinterpret_cast<uint4*>(buf + own_off + (((uint32_t)q ^ own_sw) << 4)) =
+              make_uint4(xr[ci][4 * q], xr[ci][4 * q + 1], xr[ci][4 * q + 2], xr[ci][4 * q + 3]);
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int row = 8 * i + crow;
+          const uint4 val = *reinterpret_cast<const uint4*>(buf + row * 64 + ((cseg ^ ((row >> 1) & 3)) << 4));
+          if (8 * i < rows_left) *reinterpret_cast<uint4*>(p.out_sum + goff + 8 * i * TN + ci * 128) = val;
+        }
+        __syncwarp();
+      }
+      if (p.want_ln) {
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + quad) : "memory");      // the four warps of this lane quadrant
+        float sum = 0.f, sq = 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { const float2 t = red_s[k * 128 + r]; sum += t.x; sq += t.y; }
+        const float mean = sum * (1.0f / TN);
+        const float var = fmaxf(sq * (1.0f / TN) - mean * mean, 0.f);
+        const float rstd = rsqrtf(var + p.eps);
+        const uint64_t sc = f2_bcast(rstd), sh = f2_bcast(-mean * rstd);
+        const uint32_t sel_lo = sel_s[0], sel_hi = sel_s[1];
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + quad) : "memory");      // red_s may be rewritten by the next tile
+#pragma unroll
+        for (int ci = 0; ci < CPT; ++ci) {
+          const int ch = 4 * ci + part;
+#pragma unroll
+          for (int q = 0; q < 16; ++q) {
+            const float2 g = *reinterpret_cast<const float2*>(&gamma_s[ch * 32 + 2 * q]);
+            const float2 bt = *reinterpret_cast<const float2*>(&beta_s[ch * 32 + 2 * q]);
+            float h0, h1;
+            const uint32_t xv = xr[ci][q];
+            const uint64_t xf = f2_pack(__uint_as_float(__byte_perm(xv, 0, sel_lo)), __uint_as_float(__byte_perm(xv, 0, sel_hi)));
+            f2_unpack(f2_fma(f2_fma(xf, sc, sh), f2_pack(g.x, g.y), f2_pack(bt.x, bt.y)), h0, h1);
+            xr[ci][q] = pack_bf16x2(h0, h1);
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            *reinterpret_cast<uint4*>(buf + own_off + (((uint32_t)q ^ own_sw) << 4)) =
+                make_uint4(xr[ci][4 * q], xr[ci][4 * q + 1], xr[ci][4 * q + 2], xr[ci][4 * q + 3]);
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int row = 8 * i + crow;
+            const uint4 val = *reinterpret_cast<const uint4*>(buf + row * 64 + ((cseg ^ ((row >> 1) & 3)) << 4));
+            if (8 * i < rows_left) *reinterpret_cast<uint4*>(p.out_norm + goff + 8 * i * TN + ci * 128) = val;
+          }
+          __syncwarp();
+        }
+      }
+      // every epilogue warp of this CTA must be done with the P region before the next tile's E1 overwrites it
+      asm volatile("bar.sync 5, %0;" ::"n"(kMpEpiWarps * 32) : "memory");
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();            // the peer may still signal barriers / read operands in this CTA's shared memory
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512) : "memory");
+  }
+}
+
+static int mp_map_2d(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer, uint32_t box_inner, uint32_t box_outer,
+                     CUtensorMapL2promotion promo, const char* what) {
+  GgEncodeFn enc = gg_encode_fn();
+  D2S_REQUIRE(enc != nullptr, D2S_ERR_CUDA, "%s: cuTensorMapEncodeTiled is unavailable from the driver", what);
+  const cuuint64_t gdim[2] = {inner, outer};
+  const cuuint64_t gstr[1] = {inner * 2};
+  const cuuint32_t box[2] = {box_inner, box_outer};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult cr = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  D2S_REQUIRE(cr == CUDA_SUCCESS, D2S_ERR_CUDA, "%s: tensor map encode failed (%d)", what, (int)cr);
+  return D2S_OK;
+}
+
+}  // namespace d2s
+
+using namespace d2s;
+
+extern "C" int d2s_mlp_residual_ln_bf16(const void* h, const void* w1, const void* b1, const void* w2, const void* b2,
+                                        const void* x, const void* gamma, const void* beta, float eps, int M, int D, int HID,
+                                        void* out_sum, void* out_norm, d2s_stream_t stream) {
+  const char* what = "d2s_mlp_residual_ln_bf16";
+  D2S_REQUIRE(h && w1 && w2 && x && out_sum, D2S_ERR_ARG, "mlp_residual_ln: null pointer");
+  D2S_REQUIRE(M >= 0 && D == kMpD && HID >= 3 * kMpCH && HID % kMpCH == 0 && HID <= 2048, D2S_ERR_ARG,
+              "mlp_residual_ln: need D == %d and HID %% %d == 0, %d <= HID <= 2048 (got M=%d D=%d HID=%d)", kMpD, kMpCH, 3 * kMpCH, M,
+              D, HID);
+  D2S_REQUIRE(!out_norm || (gamma && beta), D2S_ERR_ARG, "mlp_residual_ln: out_norm needs gamma and beta");
+  D2S_REQUIRE(aligned16(h) && aligned16(w1) && aligned16(w2) && aligned16(x) && aligned16(out_sum) && aligned16(out_norm),
+              D2S_ERR_ALIGN, "mlp_residual_ln: pointers must be 16-byte aligned");
+  if (M == 0) return D2S_OK;
+  CUtensorMap ma, mw1, mw2;
+  int rc;
+  if ((rc = mp_map_2d(&ma, h, D, M, 64, kMpBM, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, what))) return rc;
+  if ((rc = mp_map_2d(&mw1, w1, D, HID, 64, kMpCH / 2, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, what))) return rc;
+  if ((rc = mp_map_2d(&mw2, w2, HID, D, 64, 96, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, what))) return rc;
+  MpParams p{nullptr, (const __nv_bfloat16*)b1, (const __nv_bfloat16*)b2, (const __nv_bfloat16*)gamma, (const __nv_bfloat16*)beta,
+             (const __nv_bfloat16*)x, (__nv_bfloat16*)out_sum, (__nv_bfloat16*)out_norm, eps, M, HID, out_norm ? 1 : 0};
+  const size_t smem = 1024 + (size_t)kMpKB * kMpA1Blk + 2 * (size_t)kMpPBlk + (size_t)kMpW1Slots * kMpW1Blk +
+                      (size_t)kMpW2Slots * kMpW2Blk + sizeof(MpBars) + (size_t)HID * 4 + 3 * kMpD * 4 + 4 * 128 * sizeof(float2) + 16;
+  D2S_REQUIRE(smem <= 227 * 1024, D2S_ERR_ARG, "mlp_residual_ln: needs %zu B of shared memory", smem);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(mlp_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    D2S_REQUIRE(e == cudaSuccess, D2S_ERR_CUDA, "mlp_residual_ln: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  const int pair_tiles = (M + 2 * kMpBM - 1) / (2 * kMpBM);
+  const int pairs = pair_tiles < kNumSMs / 2 ? pair_tiles : kNumSMs / 2;
+  mlp_pair_kernel<<<2 * pairs, kMpThreads, smem, (cudaStream_t)stream>>>(ma, mw1, mw2, p);
+  count_launch();
+  return check_launch(what);
+}

@@ -20,6 +20,7 @@ from . import ops
 
 _FUSED_FC1 = os.environ.get("D2S_FUSED_FC1", "1") != "0"   # A/B switch for the tcgen05 fc1+GELU GEMM
 _TRAIN_ATTN = os.environ.get("D2S_TRAIN_ATTN", "1") != "0"    # A/B switch for ops.attention_train (bf16 training attention)
+_FUSED_MLP = os.environ.get("D2S_FUSED_MLP", "1") != "0"      # A/B switch for the one-kernel MLP (ops.mlp_residual_ln)
 _FUSED_PAIR = os.environ.get("D2S_FUSED_PAIR", "1") != "0"  # A/B switch for the CTA-pair GEMMs (fc1 pair; proj/fc2 + add + LN)
 INIT_N = 14 * 14  # the reference hard-codes 196 spatial tokens (dynamic_vit.py:828, default_dynamic_vit.py:446)
 
@@ -112,6 +113,13 @@ def mlp_forward(m, h):
     return m(h)
 
 
+def _mlp_fused_ok(m, h, x):
+    """The one-kernel MLP applies: bf16, D == 384 (whole rows in one CTA's TMEM next to the hidden chunks), 4D hidden."""
+    return (_FUSED_MLP and _FUSED_PAIR and h.dtype == torch.bfloat16 and x.dtype == torch.bfloat16
+            and m.fc1.weight.dtype == torch.bfloat16 and m.fc1.in_features == 384 and m.fc2.out_features == 384
+            and m.fc1.out_features % 64 == 0 and 192 <= m.fc1.out_features <= 2048 and h.shape == x.shape)
+
+
 def _pair_ok(lin, a, x):
     """The CTA-pair GEMM with residual + LayerNorm epilogue applies: bf16, whole rows (D in {192, 384}) fit one CTA's TMEM."""
     return (_FUSED_PAIR and isinstance(lin, torch.nn.Linear) and a.dtype == torch.bfloat16 and x.dtype == torch.bfloat16
@@ -151,9 +159,12 @@ class _Stream:
     Falls back to plain Block.forward when the fused path does not apply."""
 
     def __init__(self, x):
-        self.x, self.y, self.lin = x, None, None
+        self.x, self.y, self.lin, self.mlp = x, None, None, None
 
     def _flush_lin(self):
+        if self.mlp is not None:                       # deferred whole MLP (h, module): its fc2 becomes the deferred Linear
+            h, m = self.mlp
+            self.lin, self.mlp = (mlp_hidden(m, h), m.fc2), None
         if self.lin is not None:
             a, lin = self.lin
             self.y, self.lin = lin(a), None
@@ -166,6 +177,17 @@ class _Stream:
 
     def _sum_norm(self, norm, row0=0):
         """(x + branch, norm((x + branch)[:, row0:])); leaves the stream holding the summed x."""
+        if self.mlp is not None:
+            h, m = self.mlp
+            if _mlp_fused_ok(m, h, self.x):
+                self.mlp = None
+                if row0 == 0:
+                    self.x, hn = ops.mlp_residual_ln(h, m.fc1.weight, m.fc1.bias, m.fc2.weight, m.fc2.bias, self.x,
+                                                     norm.weight, norm.bias, norm.eps)
+                    return self.x, hn
+                self.x, _ = ops.mlp_residual_ln(h, m.fc1.weight, m.fc1.bias, m.fc2.weight, m.fc2.bias, self.x, want_norm=False)
+            else:
+                self.lin, self.mlp = (mlp_hidden(m, h), m.fc2), None
         if self.lin is not None and _pair_ok(self.lin[1], self.lin[0], self.x):
             (a, lin), self.lin = self.lin, None
             if row0 == 0:
@@ -186,7 +208,7 @@ class _Stream:
             self.lin = (o, blk.attn.proj)
             _, h = self._sum_norm(blk.norm2)
             if _mlp_is_plain(blk.mlp, h):
-                self.lin = (mlp_hidden(blk.mlp, h), blk.mlp.fc2)
+                self.mlp = (h, blk.mlp)                  # deferred: fused with the residual add and the next LayerNorm
             else:
                 self.y = blk.mlp(h)
             return cls_attn
@@ -207,7 +229,10 @@ class _Stream:
     def cls_normed(self, norm):
         """norm(x + y)[:, 0]: only the CLS row (what the eval heads consume)."""
         if _is_plain_ln(norm) and self.x.is_cuda and not _needs_grad(self.x, self.y, norm.weight):
-            if self.lin is not None:                     # the last fc2 is only needed for the CLS rows
+            if self.mlp is not None:                     # the last MLP is only needed for the CLS rows
+                h, m = self.mlp
+                y0 = m.fc2(mlp_hidden(m, h[:, :1].contiguous()))
+            elif self.lin is not None:                   # the last fc2 is only needed for the CLS rows
                 a, lin = self.lin
                 y0 = lin(a[:, :1])
             else:

@@ -531,3 +531,26 @@ def linear_residual_ln(a, weight, bias, x, ln_weight=None, ln_bias=None, eps=1e-
     _lib.call("d2s_linear_residual_ln_bf16", _ptr(ac), _ptr(w), _ptr(b), _ptr(xc), _ptr(g), _ptr(bt), float(eps), M, N, K,
               _ptr(out_sum), _ptr(out_norm), _stream())
     return out_sum, out_norm
+
+
+def mlp_residual_ln(h, w1, b1, w2, b2, x, ln_weight=None, ln_bias=None, eps=1e-5, want_norm=True):
+    """(x', hn) with x' = x + fc2(GELU(fc1(h))) and hn = LayerNorm(x') * ln_weight + ln_bias (None when want_norm is False):
+    the MLP branch of Block.forward with its residual add and the next LayerNorm (vit_models/dynamic_vit.py:159-175, :263-283)
+    in ONE CTA-pair tcgen05 kernel; the hidden activations stay on chip.  bf16, inference only, D == 384."""
+    _check_cuda(h, w1, b1, w2, b2, x, ln_weight, ln_bias)
+    if h.dtype != torch.bfloat16 or x.dtype != torch.bfloat16:
+        raise TypeError("mlp_residual_ln is a bf16 kernel")
+    hc, xc = h.detach().contiguous(), x.detach().contiguous()
+    bf = lambda t: None if t is None else t.detach().to(torch.bfloat16).contiguous()
+    w1c, w2c = bf(w1), bf(w2)
+    D = hc.shape[-1]
+    M = hc.numel() // D
+    HID = w1c.shape[0]
+    if xc.numel() != M * D or tuple(w2c.shape) != (D, HID) or w1c.shape[1] != D:
+        raise RuntimeError(f"mlp_residual_ln: inconsistent shapes h{tuple(h.shape)} w1{tuple(w1.shape)} w2{tuple(w2.shape)} x{tuple(x.shape)}")
+    g, bt = (bf(ln_weight), bf(ln_bias)) if want_norm else (None, None)
+    out_sum = torch.empty_like(xc)
+    out_norm = torch.empty_like(xc) if want_norm else None
+    _lib.call("d2s_mlp_residual_ln_bf16", _ptr(hc), _ptr(w1c), _ptr(bf(b1)), _ptr(w2c), _ptr(bf(b2)), _ptr(xc), _ptr(g), _ptr(bt),
+              float(eps), M, D, HID, _ptr(out_sum), _ptr(out_norm), _stream())
+    return out_sum, out_norm

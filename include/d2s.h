@@ -207,6 +207,16 @@ int d2s_linear_residual_ln_bf16(const void* a, const void* w, const void* bias, 
                                 const void* beta, float eps, int M, int N, int K, void* out_sum, void* out_norm,
                                 d2s_stream_t stream);
 
+/* The whole MLP branch of Block.forward in one kernel (dynamic_vit.py:159-175, :263-283), bf16, D == 384:
+ *   u = GELU(h (M,D) @ w1 (HID,D)^T + b1);  out_sum (M,D) = bf16(x + bf16(u @ w2 (D,HID)^T + b2));
+ *   out_norm (M,D) = LayerNorm(out_sum) * gamma + beta, or skipped when out_norm is NULL.
+ * The (M,HID) hidden activations never leave the SM (64-column chunks through TMEM and shared memory); roundings are the
+ * reference's (fc1 output after GELU, fc2 output, residual sum, LayerNorm output each rounded to bf16).
+ * HID % 64 == 0, 192 <= HID <= 2048; x may alias out_sum. */
+int d2s_mlp_residual_ln_bf16(const void* h, const void* w1, const void* b1, const void* w2, const void* b2, const void* x,
+                             const void* gamma, const void* beta, float eps, int M, int D, int HID, void* out_sum,
+                             void* out_norm, d2s_stream_t stream);
+
 /* LayerNorm forward / backward for the training path (norm1 / norm2 / predictor norms of Block.forward,
  * dynamic_vit.py:263-283) with mixed dtypes for bf16 autocast: x (rows,D) f32|bf16 -> h (rows,D) f32|bf16,
  * gamma/beta f32 (D), stats (rows,2) f32 = (mean, rstd) saved for backward.  Backward: dx (dtype of x),

@@ -543,6 +543,32 @@ def test_linear_residual_ln(ops, M, N, K):
     assert none is None and torch.equal(s2.cpu(), s)
 
 
+@pytest.mark.parametrize("M,HID", [(256, 1536), (1000, 1536), (77, 1536), (3 * 197, 1536), (20000, 1536), (513, 192), (300, 768)])
+def test_mlp_residual_ln_fused(ops, M, HID):
+    """fc1 + GELU + fc2 + residual + next LayerNorm (dynamic_vit.py:159-175, :263-283) in one kernel vs the separate bf16 ops
+    (each intermediate rounded to bf16 like the reference's modules)."""
+    D = 384
+    h = fx.randn(700 + M % 91, M, D).bfloat16()
+    w1 = (fx.randn(701, HID, D) / D ** 0.5).bfloat16()
+    b1 = (fx.randn(702, HID) * 0.2).bfloat16()
+    w2 = (fx.randn(703, D, HID) / HID ** 0.5).bfloat16()
+    b2 = (fx.randn(704, D) * 0.2).bfloat16()
+    x = (fx.randn(705 + M % 7, M, D) * 1.5).bfloat16()
+    g = (1.0 + 0.3 * fx.randn(706, D)).bfloat16()
+    bt = (0.2 * fx.randn(707, D)).bfloat16()
+    s, hn = ops.mlp_residual_ln(cu(h), cu(w1), cu(b1), cu(w2), cu(b2), cu(x), cu(g), cu(bt), 1e-6)
+    s, hn = s.cpu(), hn.cpu()
+    u = torch.nn.functional.gelu(torch.nn.functional.linear(h.float(), w1.float(), b1.float())).bfloat16()
+    y = torch.nn.functional.linear(u.float(), w2.float(), b2.float()).bfloat16()
+    s_ref = (x.float() + y.float()).bfloat16()
+    torch.testing.assert_close(s.float(), s_ref.float(), rtol=1e-2, atol=3.2e-2)
+    assert float((s == s_ref).float().mean()) > 0.95      # bf16 flips of u (1 ulp) propagate into a few sums
+    hn_ref = torch.nn.functional.layer_norm(s.float(), (D,), g.float(), bt.float(), 1e-6)
+    torch.testing.assert_close(hn.float(), hn_ref, rtol=8e-3, atol=8e-3)
+    s2, none = ops.mlp_residual_ln(cu(h), cu(w1), cu(b1), cu(w2), cu(b2), cu(x), want_norm=False)
+    assert none is None and torch.equal(s2.cpu(), s)
+
+
 def test_score_tail_a_gelu_on_load_and_prev_gather(ops):
     B, N, Cc, K = 4, 196, 96, 137
     raw = fx.randn(170, B, N, Cc)
