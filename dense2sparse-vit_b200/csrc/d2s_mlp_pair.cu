@@ -13,33 +13,56 @@
 //     G2(j): ACC (256 x 384) += P_j (256 x 64)  x  W2[:, 64 j .. 64 j + 63]^T                                   -> TMEM
 // with S double-buffered in TMEM (384 + 2 x 64 = 512 columns) and P double-buffered in shared memory, so the tensor pipe runs
 // G1(j+2) and G2(j) while two groups of 8 epilogue warps compute E1(j) and E1(j+1).  W1 / W2 chunks stream from L2 through two TMA rings (each CTA
-// loads half of every weight tile).  After the last chunk the same epilogue as d2s_gemm_pair.cu's MODE_LN runs from ACC:
-// bias, round, residual add, LayerNorm statistics, x' and hn written as coalesced row segments; the rows of the residual
-// are fetched into registers while the last chunks are still in the tensor pipe.
+// loads half of every weight tile).  After the last chunk a separate set of warps drains ACC: bias, round, residual add,
+// LayerNorm statistics, x' and hn, while the GEMM / activation warps are already on the next row tile.
 //
 //   warp 0      TMA producer: H tile (once per row tile) and W1 k-blocks      warp 2   TMA producer: W2 chunks
 //   warp 1      TMEM allocation; G1 issue (leader CTA only)                   warp 3   G2 issue (leader CTA only)
-//   warps 4-19  epilogue (four warps per TMEM lane quadrant)
+//   warps 4-11  E1: GELU of the hidden chunks (two groups of four warps)
+//   warps 12-15 output: residual add + LayerNorm of the finished row tile, overlapped with the next tile's GEMMs
 #include <stdlib.h>
 #include "d2s_tc.cuh"
 
 namespace d2s {
 
 constexpr int kMpBM = 128, kMpD = 384, kMpCH = 64, kMpKB = kMpD / 64;
-constexpr int kMpW1Slots = 8, kMpW2Slots = 2;
+constexpr int kMpW1Slots = 6, kMpW2Slots = 2;
 constexpr uint32_t kMpA1Blk = 128 * 128;        // 16 KB: 128 rows x 64 bf16 of H
 constexpr uint32_t kMpW1Blk = 32 * 128;         //  4 KB: this CTA's 32 of the 64 W1 rows of a chunk, one k-block
 constexpr uint32_t kMpW2Half = 96 * 128;        // 12 KB: this CTA's 96 of the 192 W2 rows of one N-half, 64 hidden columns
 constexpr uint32_t kMpW2Blk = 2 * kMpW2Half;    // 24 KB
 constexpr uint32_t kMpPBlk = 128 * 128;         // 16 KB: 128 rows x 64 bf16 of P_j
-constexpr int kMpEpiWarps = 16, kMpThreads = (4 + kMpEpiWarps) * 32;
+constexpr int kMpE1Warps = 8, kMpOutWarps = 4, kMpThreads = (4 + kMpE1Warps + kMpOutWarps) * 32;
 constexpr uint32_t kMpAccCols = 384, kMpSCols = 64;
+
+// clock64 totals of the issuing warps' waits (profiling builds only: -DD2S_GEMM_TRACE_BUILD, scripts/bench_mlp_trace.py)
+#ifdef D2S_GEMM_TRACE_BUILD
+#define MP_TRACE_DECL long long tr[8] = {}; long long tr_t = clock64();
+#define MP_TRACE(i) { const long long tr_n = clock64(); tr[i] += tr_n - tr_t; tr_t = tr_n; }
+#define MP_TRACE_DUMP(w, n) if (p.trace && lane == 0) { long long* d_ = p.trace + ((size_t)(blockIdx.x >> 1) * 2 + (w)) * 8; \
+    for (int i = 0; i < 7; ++i) d_[i] = tr[i]; d_[7] = (n); }
+#define ME_TRACE_DECL long long te[16] = {}; long long te_t = clock64(); long long te_n = 0;
+#define ME_TRACE(i) { const long long t_ = clock64(); te[i] += t_ - te_t; te_t = t_; }
+#define ME_COUNT ++te_n;
+#define ME_TRACE_DUMP if (p.trace && lane == 0 && rank == 0 && (ew == 0 || ew == 8)) { long long* d_ = p.trace + 74 * 16 + ((size_t)(blockIdx.x >> 1) * 2 + (ew >> 3)) * 8; \
+    for (int i = 0; i < 7; ++i) d_[i] = te[i]; d_[7] = te_n; \
+    long long* f_ = p.trace + 74 * 32 + ((size_t)(blockIdx.x >> 1) * 2 + (ew >> 3)) * 8; for (int i = 0; i < 8; ++i) f_[i] = te[8 + i]; }
+#else
+#define MP_TRACE_DECL
+#define MP_TRACE(i)
+#define MP_TRACE_DUMP(w, n)
+#define ME_TRACE_DECL
+#define ME_TRACE(i)
+#define ME_COUNT
+#define ME_TRACE_DUMP
+#endif
 
 struct MpBars {
   uint64_t a1_full[kMpKB], a1_empty[kMpKB], w1_full[kMpW1Slots], w1_empty[kMpW1Slots], w2_full[kMpW2Slots], w2_empty[kMpW2Slots];
   uint64_t s_full[2], s_empty[2], p_full[2], p_empty[2], acc_full, acc_empty;
   uint32_t tmem_base, pad;
 };
+static_assert(sizeof(MpBars) % 8 == 0, "MpBars");
 
 struct MpParams {
   long long* trace;             // profiling builds (-DD2S_GEMM_TRACE_BUILD): clock64 totals of the MMA thread's waits
@@ -49,7 +72,7 @@ struct MpParams {
   int M, HID, want_ln;
 };
 
-__global__ void __cluster_dims__(2, 1, 1) __maxnreg__(96)
+__global__ void __cluster_dims__(2, 1, 1) __maxnreg__(128)
 mlp_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w1,
                 const __grid_constant__ CUtensorMap map_w2, const MpParams p) {
   constexpr int TN = kMpD;
@@ -58,13 +81,13 @@ mlp_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   const uint32_t padb = (1024u - (raw & 1023u)) & 1023u;
   unsigned char* a1_s = smem_dyn + padb;                                  // 6 x 16 KB
   unsigned char* p_s = a1_s + kMpKB * kMpA1Blk;                           // 2 x 16 KB (also the per-warp transposition buffers)
-  unsigned char* w1_s = p_s + 2 * kMpPBlk;                                // 8 x 4 KB
+  unsigned char* w1_s = p_s + 2 * kMpPBlk;                                // 6 x 4 KB
   unsigned char* w2_s = w1_s + kMpW1Slots * kMpW1Blk;                     // 2 x 24 KB
   MpBars* bars = reinterpret_cast<MpBars*>(w2_s + kMpW2Slots * kMpW2Blk);
   float* b1_s = reinterpret_cast<float*>(bars + 1);                       // HID
   float* b2_s = b1_s + p.HID;                                             // 3 x 384: b2, gamma, beta
-  float2* red_s = reinterpret_cast<float2*>(b2_s + 3 * TN);               // [4][128] partial LayerNorm statistics
-  volatile uint32_t* sel_s = reinterpret_cast<volatile uint32_t*>(red_s + 4 * 128);
+  unsigned char* out_s = reinterpret_cast<unsigned char*>(                  // 4 x 2 KB transposition buffers of the output warps
+      (reinterpret_cast<uintptr_t>(b2_s + 3 * TN) + 15) & ~(uintptr_t)15);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t rank = cluster_ctarank();
@@ -77,17 +100,15 @@ mlp_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     for (int i = 0; i < kMpKB; ++i) { mbar_init(smem_u32(&bars->a1_full[i]), 1); mbar_init(smem_u32(&bars->a1_empty[i]), 1); }
     for (int i = 0; i < kMpW1Slots; ++i) { mbar_init(smem_u32(&bars->w1_full[i]), 1); mbar_init(smem_u32(&bars->w1_empty[i]), 1); }
     for (int i = 0; i < kMpW2Slots; ++i) { mbar_init(smem_u32(&bars->w2_full[i]), 1); mbar_init(smem_u32(&bars->w2_empty[i]), 1); }
-    for (int i = 0; i < 2; ++i) {   // one epilogue group (8 warps) per CTA arrives per chunk
+    for (int i = 0; i < 2; ++i) {   // one E1 group (4 warps) per CTA arrives per chunk
       mbar_init(smem_u32(&bars->s_full[i]), 1);
       mbar_init(smem_u32(&bars->p_empty[i]), 1);
-      mbar_init(smem_u32(&bars->s_empty[i]), 2 * 8);
-      mbar_init(smem_u32(&bars->p_full[i]), 2 * 8);
+      mbar_init(smem_u32(&bars->s_empty[i]), 2 * 4);
+      mbar_init(smem_u32(&bars->p_full[i]), 2 * 4);
     }
     mbar_init(smem_u32(&bars->acc_full), 1);
-    mbar_init(smem_u32(&bars->acc_empty), 2 * kMpEpiWarps);
+    mbar_init(smem_u32(&bars->acc_empty), 2 * kMpOutWarps);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    sel_s[0] = 0x1044u;   // byte-permute selectors {0, 0, b0, b1} and {0, 0, b2, b3}: bf16 pair -> two fp32
-    sel_s[1] = 0x3244u;
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)), "n"(512) : "memory");
@@ -154,17 +175,22 @@ mlp_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       // S buffer (and vice versa); the tensor pipe interleaves the two instruction streams as their operands become ready. ======
       const uint32_t idesc1 = make_idesc(2 * kMpBM, kMpCH, 0);
       uint32_t w1_it = 0, c = 0, tile_i = 0;
+      MP_TRACE_DECL
       for (int pt = pair; pt < pair_tiles; pt += num_pairs, ++tile_i)
         for (int j = 0; j < nch; ++j, ++c) {
           const uint32_t sb = c & 1, use = c >> 1;
+          MP_TRACE(0)
           mbar_wait(smem_u32(&bars->s_empty[sb]), (use & 1) ^ 1);            // E1 two chunks ago has read this S buffer
           tc_fence_after();
+          MP_TRACE(1)
           const uint32_t d = tmem + kMpAccCols + sb * kMpSCols;
           for (int kb = 0; kb < kMpKB; ++kb, ++w1_it) {
             if (j == 0) mbar_wait(smem_u32(&bars->a1_full[kb]), tile_i & 1);
+            MP_TRACE(2)
             const uint32_t s = w1_it % kMpW1Slots, n = w1_it / kMpW1Slots;
             mbar_wait(smem_u32(&bars->w1_full[s]), n & 1);
             tc_fence_after();
+            MP_TRACE(3)
             const uint64_t ad = make_desc_sw128(smem_u32(a1_s + kb * kMpA1Blk), 16, 1024);
             const uint64_t bd = make_desc_sw128(smem_u32(w1_s + s * kMpW1Blk), 16, 1024);
             if (elect_one()) {
@@ -180,20 +206,27 @@ mlp_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
           if (elect_one()) mma2_commit_both(smem_u32(&bars->s_full[sb]));
           __syncwarp();
         }
+      MP_TRACE(0)
+      MP_TRACE_DUMP(0, c)
     }
   } else if (warp_u == 3) {
     if (rank_u == 0) {
       // ====== G2 issuer (leader): ACC += P_c x W2_chunk^T ======
       const uint32_t idesc2 = make_idesc(2 * kMpBM, 192, 0);
       uint32_t c = 0, tile_i = 0;
+      MP_TRACE_DECL
       for (int pt = pair; pt < pair_tiles; pt += num_pairs, ++tile_i)
         for (int j = 0; j < nch; ++j, ++c) {
           const uint32_t pb = c & 1, use = c >> 1;
+          MP_TRACE(0)
           mbar_wait(smem_u32(&bars->p_full[pb]), use & 1);                     // both CTAs' epilogues have written P
+          MP_TRACE(4)
           const uint32_t s = c % kMpW2Slots, n = c / kMpW2Slots;
           mbar_wait(smem_u32(&bars->w2_full[s]), n & 1);
+          MP_TRACE(5)
           if (j == 0) mbar_wait(smem_u32(&bars->acc_empty), (tile_i & 1) ^ 1);   // previous tile's epilogue has drained ACC
           tc_fence_after();
+          MP_TRACE(6)
           const uint64_t ad = make_desc_sw128(smem_u32(p_s + pb * kMpPBlk), 16, 1024);
           if (elect_one()) {
 #pragma unroll
@@ -211,179 +244,187 @@ mlp_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
           }
           __syncwarp();
         }
+      MP_TRACE(0)
+      MP_TRACE_DUMP(1, c)
     }
-  } else {
-    // ========================================= epilogue (both CTAs) =========================================
-    const int ew = warp - 4;                    // 0..15
+  } else if (warp < 4 + kMpE1Warps) {
+    // ============================== E1 warps (both CTAs): P_j = bf16(GELU(S_j + b1)) ==============================
+    // Two groups of 4 warps (one per TMEM lane quadrant, a thread takes all 64 columns of its row) handle the chunks
+    // alternately, each always on its own S / P buffer (chunk number mod 2): two chunks are in the activation stage at
+    // once, and a group sees every phase of the barriers it waits on.
+    const int ew = warp - 4;                    // 0..7
     const int quad = warp & 3;                  // TMEM lane quadrant of this warp
-    const int part = ew >> 2;                   // final epilogue: which quarter of the columns
-    const uint32_t grp = (uint32_t)ew >> 3;     // E1: which chunks (chunk number % 2 == grp)
-    const int half = part & 1;                  // E1: which 32 of the chunk's 64 columns
-    const int r = quad * 32 + lane;             // row inside this CTA's 128-row tile
+    const uint32_t grp = (uint32_t)ew >> 2;
+    const int r = quad * 32 + lane;
     const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16);
-    constexpr int NCH = TN / 32, CPT = NCH / 4;                 // final epilogue: 32-column chunks ch = 4 ci + part
-    const float* gamma_s = b2_s + TN;
-    const float* beta_s = b2_s + 2 * TN;
-    unsigned char* buf = p_s + ew * 2048;                        // per-warp [32 rows x 64 B] transposition buffer (P is idle then)
-    const int crow = lane >> 2, cseg = lane & 3;                 // coalesced pattern: 4 lanes x 16 B cover one row's 64 bytes
-    const uint32_t own_off = (uint32_t)lane * 64, own_sw = (uint32_t)(lane >> 1) & 3u;
-    uint32_t e_base = 0, tile_i = 0;
-    for (int pt = pair; pt < pair_tiles; pt += num_pairs, ++tile_i) {
-      const int row0 = pt * 2 * kMpBM + (int)rank * kMpBM + quad * 32;     // first row of this warp
-      uint32_t xr[CPT][16];      // residual rows: coalesced layout first, one row per lane after the transposition
-      // ---- E1(j): P_j = bf16(GELU(S_j + b1)).  Two groups of 8 warps (two per TMEM lane quadrant, 32 columns each) take the
-      // chunks alternately, each always on its own S / P buffer (chunk number mod 2): two chunks are in the activation stage at
-      // once, and a group sees every phase of the barriers it waits on. ----
+    uint32_t e_base = 0;
+    for (int pt = pair; pt < pair_tiles; pt += num_pairs) {
       for (int j = (int)((grp + e_base) & 1u); j < nch; j += 2) {
         const uint32_t c = e_base + (uint32_t)j;                 // global chunk number; c & 1 == grp
         const uint32_t use = c >> 1;
         mbar_wait(smem_u32(&bars->s_full[grp]), use & 1);
         tc_fence_after();
-        uint32_t v[32];
-        tmem_ld32_nowait(lane_addr + kMpAccCols + grp * kMpSCols + half * 32, v);
-        tmem_ld_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(mapa(smem_u32(&bars->s_empty[grp]), 0));   // S_j is in registers
-        uint32_t o[16];
+        uint32_t o[32];
 #pragma unroll
-        for (int q = 0; q < 16; ++q) {
-          const float2 bq = *reinterpret_cast<const float2*>(&b1_s[j * kMpCH + half * 32 + 2 * q]);
-          float g0, g1;
-          f2_unpack(gelu_erf_pair(f2_add(f2_pack(__uint_as_float(v[2 * q]), __uint_as_float(v[2 * q + 1])), f2_pack(bq.x, bq.y))), g0, g1);
-          o[q] = pack_bf16x2(g0, g1);
+        for (int half = 0; half < 2; ++half) {
+          uint32_t v[32];
+          tmem_ld32_nowait(lane_addr + kMpAccCols + grp * kMpSCols + half * 32, v);
+          tmem_ld_wait();
+          if (half == 1) {                                       // S_j is in registers: G1(j + 2) may overwrite the buffer
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(mapa(smem_u32(&bars->s_empty[grp]), 0));
+          }
+#pragma unroll
+          for (int q = 0; q < 16; ++q) {
+            const float2 bq = *reinterpret_cast<const float2*>(&b1_s[j * kMpCH + half * 32 + 2 * q]);
+            float g0, g1;
+            f2_unpack(gelu_erf_pair(f2_add(f2_pack(__uint_as_float(v[2 * q]), __uint_as_float(v[2 * q + 1])), f2_pack(bq.x, bq.y))), g0, g1);
+            o[half * 16 + q] = pack_bf16x2(g0, g1);
+          }
         }
         mbar_wait(smem_u32(&bars->p_empty[grp]), (use & 1) ^ 1);                      // G2(j - 2) has read this P buffer
         unsigned char* blk = p_s + grp * kMpPBlk;
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          *reinterpret_cast<uint4*>(blk + sw128_off(r, half * 4 + k)) = make_uint4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]);
+        for (int k = 0; k < 8; ++k)
+          *reinterpret_cast<uint4*>(blk + sw128_off(r, k)) = make_uint4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");                  // generic-proxy writes -> visible to the MMA
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(mapa(smem_u32(&bars->p_full[grp]), 0));
       }
       e_base += (uint32_t)nch;
-      {
-        // residual rows for the final epilogue: coalesced loads, in flight while the last chunks finish
+    }
+  } else {
+    // ===================== output warps (both CTAs): x' = x + bf16(ACC + b2), hn = LayerNorm(x') =====================
+    // Their own 4 warps (one per TMEM lane quadrant; a thread owns one row, all 384 columns), so a tile's residual add,
+    // LayerNorm and ~300 KB of loads / stores run under the NEXT tile's GEMMs (with the E1 warps doing this too, a third of
+    // every tile was spent here with the tensor pipe idle).  Global memory is touched in coalesced 64-byte row segments
+    // through a 2 KB per-warp transposition buffer.  x' is not kept in registers: pass 2 re-reads it (L2-hot) once the row's
+    // mean and variance are known.  Only pass 1 holds the accumulator, so G2 of the next tile waits for little.
+    const int quad = warp & 3;
+    const int ow = warp - 4 - kMpE1Warps;       // 0..3
+    const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16);
+    const float* gamma_s = b2_s + TN;
+    const float* beta_s = b2_s + 2 * TN;
+    unsigned char* buf = out_s + ow * 2048;                     // [32 rows x 64 B]
+    const int crow = lane >> 2, cseg = lane & 3;                // coalesced pattern: 4 lanes x 16 B cover one row's 64 bytes
+    const uint32_t own_off = (uint32_t)lane * 64, own_sw = (uint32_t)(lane >> 1) & 3u;
+    constexpr int NU = TN / 32;                                  // 32-column units per row
+    uint32_t tile_i = 0;
+    for (int pt = pair; pt < pair_tiles; pt += num_pairs, ++tile_i) {
+      const int row0 = pt * 2 * kMpBM + (int)rank * kMpBM + quad * 32;     // first row of this warp
+      const int rows_left = p.M - row0 - crow;                             // row group i is in range iff 8 i < rows_left
+      // element offsets of (row0 + crow + 8 i, cseg * 8); rows past M re-read the last row and are never stored
+      size_t goff[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int grow = min(row0 + crow + 8 * i, p.M - 1);        // rows past M re-read the last row, never stored
-          const __nv_bfloat16* xp = p.x + (size_t)grow * TN + part * 32 + cseg * 8;
-#pragma unroll
-          for (int ci = 0; ci < CPT; ++ci) {
-            const uint4 t = ld_nc16(xp + ci * 128);
-            xr[ci][4 * i] = t.x; xr[ci][4 * i + 1] = t.y; xr[ci][4 * i + 2] = t.z; xr[ci][4 * i + 3] = t.w;
-          }
-        }
-      }
-      // ---- final epilogue: x' = x + bf16(ACC + b2), LayerNorm ----
-      mbar_wait(smem_u32(&bars->acc_full), tile_i & 1);      // all G2 of this tile retired: ACC complete, P buffers idle
+      for (int i = 0; i < 4; ++i) goff[i] = (size_t)min(row0 + crow + 8 * i, p.M - 1) * TN + cseg * 8;
+      mbar_wait(smem_u32(&bars->acc_full), tile_i & 1);      // all G2 of this tile retired: ACC complete
       tc_fence_after();
-      const size_t goff = (size_t)(row0 + crow) * TN + part * 32 + cseg * 8;
-      const int rows_left = p.M - row0 - crow;
+      // ---- pass 1: x' = bf16(x + bf16(ACC + b2)) -> global; fp32 sum / sum of squares of the rounded values ----
+      uint64_t acc_s = f2_bcast(0.f), acc_q = f2_bcast(0.f);
+      uint4 xn[4];
 #pragma unroll
-      for (int ci = 0; ci < CPT; ++ci) {
+      for (int i = 0; i < 4; ++i) xn[i] = ld_nc16(p.x + goff[i]);
+#pragma unroll 1
+      for (int u = 0; u < NU; ++u) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int row = 8 * i + crow;
-          *reinterpret_cast<uint4*>(buf + row * 64 + ((cseg ^ ((row >> 1) & 3)) << 4)) =
-              make_uint4(xr[ci][4 * i], xr[ci][4 * i + 1], xr[ci][4 * i + 2], xr[ci][4 * i + 3]);
+          *reinterpret_cast<uint4*>(buf + row * 64 + ((cseg ^ ((row >> 1) & 3)) << 4)) = xn[i];
         }
+        if (u + 1 < NU) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) xn[i] = ld_nc16(p.x + goff[i] + (u + 1) * 32);       // next unit in flight
+        }
+        uint32_t v[32];
+        tmem_ld32_nowait(lane_addr + u * 32, v);
         __syncwarp();
+        uint32_t xw[16];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const uint4 t = *reinterpret_cast<const uint4*>(buf + own_off + (((uint32_t)q ^ own_sw) << 4));
-          xr[ci][4 * q] = t.x; xr[ci][4 * q + 1] = t.y; xr[ci][4 * q + 2] = t.z; xr[ci][4 * q + 3] = t.w;
+          xw[4 * q] = t.x; xw[4 * q + 1] = t.y; xw[4 * q + 2] = t.z; xw[4 * q + 3] = t.w;
         }
-        __syncwarp();
-      }
-      uint64_t acc_s = f2_bcast(0.f), acc_q = f2_bcast(0.f);
+        tmem_ld_wait();
 #pragma unroll
-      for (int ci = 0; ci < CPT; ++ci) {
-        const int ch = 4 * ci + part;
-#pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
-          uint32_t v[16];
-          tmem_ld16_nowait(lane_addr + ch * 32 + hh * 16, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const float2 bq = *reinterpret_cast<const float2*>(&b2_s[ch * 32 + hh * 16 + 2 * q]);
-            float y0, y1;
-            f2_unpack(f2_add(f2_pack(__uint_as_float(v[2 * q]), __uint_as_float(v[2 * q + 1])), f2_pack(bq.x, bq.y)), y0, y1);
-            const uint32_t yb = pack_bf16x2(y0, y1);                  // fc2's bf16 output
-            const uint32_t sb2 = add_bf16x2(xr[ci][hh * 8 + q], yb);    // the residual add's bf16 output
-            xr[ci][hh * 8 + q] = sb2;
-            const uint64_t sv = f2_pack(bf16_lo(sb2), bf16_hi(sb2));
-            acc_s = f2_add(acc_s, sv);
-            acc_q = f2_fma(sv, sv, acc_q);
-          }
+        for (int q = 0; q < 16; ++q) {
+          const float2 bq = *reinterpret_cast<const float2*>(&b2_s[u * 32 + 2 * q]);
+          float y0, y1;
+          f2_unpack(f2_add(f2_pack(__uint_as_float(v[2 * q]), __uint_as_float(v[2 * q + 1])), f2_pack(bq.x, bq.y)), y0, y1);
+          const uint32_t yb = pack_bf16x2(y0, y1);                    // fc2's bf16 output
+          const uint32_t sb2 = add_bf16x2(xw[q], yb);                 // the residual add's bf16 output (rounded once)
+          xw[q] = sb2;
+          const uint64_t sv = f2_pack(bf16_lo(sb2), bf16_hi(sb2));
+          acc_s = f2_add(acc_s, sv);
+          acc_q = f2_fma(sv, sv, acc_q);
         }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(mapa(smem_u32(&bars->acc_empty), 0));     // the next tile's G2(0) may start
-      {
-        float s0, s1, q0, q1;
-        f2_unpack(acc_s, s0, s1);
-        f2_unpack(acc_q, q0, q1);
-        red_s[part * 128 + r] = make_float2(s0 + s1, q0 + q1);
-      }
-#pragma unroll
-      for (int ci = 0; ci < CPT; ++ci) {
+        __syncwarp();     // every lane has read its x row: the buffer can take x'
 #pragma unroll
         for (int q = 0; q < 4; ++q)
-          *reinterpret_cast<uint4*>(buf + own_off + (((uint32_t)q ^ own_sw) << 4)) =
-              make_uint4(xr[ci][4 * q], xr[ci][4 * q + 1], xr[ci][4 * q + 2], xr[ci][4 * q + 3]);
+          *reinterpret_cast<uint4*>(buf + own_off + (((uint32_t)q ^ own_sw) << 4)) = make_uint4(xw[4 * q], xw[4 * q + 1], xw[4 * q + 2], xw[4 * q + 3]);
         __syncwarp();
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int row = 8 * i + crow;
           const uint4 val = *reinterpret_cast<const uint4*>(buf + row * 64 + ((cseg ^ ((row >> 1) & 3)) << 4));
-          if (8 * i < rows_left) *reinterpret_cast<uint4*>(p.out_sum + goff + 8 * i * TN + ci * 128) = val;
+          if (8 * i < rows_left) *reinterpret_cast<uint4*>(p.out_sum + goff[i] + u * 32) = val;
         }
         __syncwarp();
       }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa(smem_u32(&bars->acc_empty), 0));     // the next tile's G2(0) may start
       if (p.want_ln) {
-        asm volatile("bar.sync %0, 128;" ::"r"(1 + quad) : "memory");      // the four warps of this lane quadrant
-        float sum = 0.f, sq = 0.f;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) { const float2 t = red_s[k * 128 + r]; sum += t.x; sq += t.y; }
-        const float mean = sum * (1.0f / TN);
-        const float var = fmaxf(sq * (1.0f / TN) - mean * mean, 0.f);
+        float s0, s1, q0, q1;
+        f2_unpack(acc_s, s0, s1);
+        f2_unpack(acc_q, q0, q1);
+        const float mean = (s0 + s1) * (1.0f / TN);
+        const float var = fmaxf((q0 + q1) * (1.0f / TN) - mean * mean, 0.f);
         const float rstd = rsqrtf(var + p.eps);
         const uint64_t sc = f2_bcast(rstd), sh = f2_bcast(-mean * rstd);
-        const uint32_t sel_lo = sel_s[0], sel_hi = sel_s[1];
-        asm volatile("bar.sync %0, 128;" ::"r"(1 + quad) : "memory");      // red_s may be rewritten by the next tile
+        // ---- pass 2: hn = (x' - mean) * rstd * gamma + beta; x' comes back from L2 (this warp wrote it above) ----
 #pragma unroll
-        for (int ci = 0; ci < CPT; ++ci) {
-          const int ch = 4 * ci + part;
+        for (int i = 0; i < 4; ++i) xn[i] = ld_cg16(p.out_sum + goff[i]);
+#pragma unroll 1
+        for (int u = 0; u < NU; ++u) {
 #pragma unroll
-          for (int q = 0; q < 16; ++q) {
-            const float2 g = *reinterpret_cast<const float2*>(&gamma_s[ch * 32 + 2 * q]);
-            const float2 bt = *reinterpret_cast<const float2*>(&beta_s[ch * 32 + 2 * q]);
-            float h0, h1;
-            const uint32_t xv = xr[ci][q];
-            const uint64_t xf = f2_pack(__uint_as_float(__byte_perm(xv, 0, sel_lo)), __uint_as_float(__byte_perm(xv, 0, sel_hi)));
-            f2_unpack(f2_fma(f2_fma(xf, sc, sh), f2_pack(g.x, g.y), f2_pack(bt.x, bt.y)), h0, h1);
-            xr[ci][q] = pack_bf16x2(h0, h1);
+          for (int i = 0; i < 4; ++i) {
+            const int row = 8 * i + crow;
+            *reinterpret_cast<uint4*>(buf + row * 64 + ((cseg ^ ((row >> 1) & 3)) << 4)) = xn[i];
+          }
+          if (u + 1 < NU) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) xn[i] = ld_cg16(p.out_sum + goff[i] + (u + 1) * 32);
+          }
+          __syncwarp();
+          uint32_t hw[16];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint4 t = *reinterpret_cast<const uint4*>(buf + own_off + (((uint32_t)q ^ own_sw) << 4));
+            hw[4 * q] = t.x; hw[4 * q + 1] = t.y; hw[4 * q + 2] = t.z; hw[4 * q + 3] = t.w;
           }
 #pragma unroll
+          for (int q = 0; q < 16; ++q) {
+            const float2 g = *reinterpret_cast<const float2*>(&gamma_s[u * 32 + 2 * q]);
+            const float2 bt = *reinterpret_cast<const float2*>(&beta_s[u * 32 + 2 * q]);
+            float h0, h1;
+            f2_unpack(f2_fma(f2_fma(f2_pack(bf16_lo(hw[q]), bf16_hi(hw[q])), sc, sh), f2_pack(g.x, g.y), f2_pack(bt.x, bt.y)), h0, h1);
+            hw[q] = pack_bf16x2(h0, h1);
+          }
+          __syncwarp();
+#pragma unroll
           for (int q = 0; q < 4; ++q)
-            *reinterpret_cast<uint4*>(buf + own_off + (((uint32_t)q ^ own_sw) << 4)) =
-                make_uint4(xr[ci][4 * q], xr[ci][4 * q + 1], xr[ci][4 * q + 2], xr[ci][4 * q + 3]);
+            *reinterpret_cast<uint4*>(buf + own_off + (((uint32_t)q ^ own_sw) << 4)) = make_uint4(hw[4 * q], hw[4 * q + 1], hw[4 * q + 2], hw[4 * q + 3]);
           __syncwarp();
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const int row = 8 * i + crow;
             const uint4 val = *reinterpret_cast<const uint4*>(buf + row * 64 + ((cseg ^ ((row >> 1) & 3)) << 4));
-            if (8 * i < rows_left) *reinterpret_cast<uint4*>(p.out_norm + goff + 8 * i * TN + ci * 128) = val;
+            if (8 * i < rows_left) *reinterpret_cast<uint4*>(p.out_norm + goff[i] + u * 32) = val;
           }
           __syncwarp();
         }
       }
-      // every epilogue warp of this CTA must be done with the P region before the next tile's E1 overwrites it
-      asm volatile("bar.sync 5, %0;" ::"n"(kMpEpiWarps * 32) : "memory");
     }
   }
   tc_fence_before();
@@ -430,10 +471,11 @@ extern "C" int d2s_mlp_residual_ln_bf16(const void* h, const void* w1, const voi
   if ((rc = mp_map_2d(&ma, h, D, M, 64, kMpBM, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, what))) return rc;
   if ((rc = mp_map_2d(&mw1, w1, D, HID, 64, kMpCH / 2, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, what))) return rc;
   if ((rc = mp_map_2d(&mw2, w2, HID, D, 64, 96, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, what))) return rc;
-  MpParams p{nullptr, (const __nv_bfloat16*)b1, (const __nv_bfloat16*)b2, (const __nv_bfloat16*)gamma, (const __nv_bfloat16*)beta,
+  const char* tr_env = getenv("D2S_GEMM_TRACE");
+  MpParams p{tr_env ? reinterpret_cast<long long*>(strtoull(tr_env, nullptr, 10)) : nullptr, (const __nv_bfloat16*)b1, (const __nv_bfloat16*)b2, (const __nv_bfloat16*)gamma, (const __nv_bfloat16*)beta,
              (const __nv_bfloat16*)x, (__nv_bfloat16*)out_sum, (__nv_bfloat16*)out_norm, eps, M, HID, out_norm ? 1 : 0};
   const size_t smem = 1024 + (size_t)kMpKB * kMpA1Blk + 2 * (size_t)kMpPBlk + (size_t)kMpW1Slots * kMpW1Blk +
-                      (size_t)kMpW2Slots * kMpW2Blk + sizeof(MpBars) + (size_t)HID * 4 + 3 * kMpD * 4 + 4 * 128 * sizeof(float2) + 16;
+                      (size_t)kMpW2Slots * kMpW2Blk + sizeof(MpBars) + (size_t)HID * 4 + 3 * kMpD * 4 + (size_t)kMpOutWarps * 2048 + 32;
   D2S_REQUIRE(smem <= 227 * 1024, D2S_ERR_ARG, "mlp_residual_ln: needs %zu B of shared memory", smem);
   static bool attr_set = false;
   if (!attr_set) {

@@ -226,8 +226,12 @@ __device__ __forceinline__ uint32_t mapa(uint32_t local, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(rank));
   return r;
 }
+// Arrive on a barrier of (possibly) the peer CTA.  Release at CTA scope (the PTX default), as CUTLASS's ClusterBarrier::arrive:
+// `.release.cluster` compiles to MEMBAR.ALL.GPU + ERRBAR in front of the arrive (~1000 cycles, measured in the MLP kernel's
+// activation stage, twice per chunk).  What these arrives publish is either TMEM reads (ordered by tcgen05.fence +
+// tcgen05.wait::ld) or shared-memory writes already fenced with fence.proxy.async (MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA load whose completion bytes are counted on a barrier that may live in the peer CTA of the pair
 __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar_cluster) {
@@ -261,6 +265,12 @@ __device__ __forceinline__ uint4 ld_nc16(const void* p) {
 __device__ __forceinline__ uint32_t add_bf16x2(uint32_t a, uint32_t b) {
   uint32_t r;
   asm("add.rn.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+// L2-coherent 16-byte load (bypasses L1): data this thread, or another SM, has just written
+__device__ __forceinline__ uint4 ld_cg16(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
   return r;
 }
 __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }

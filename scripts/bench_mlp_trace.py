@@ -5,12 +5,23 @@ D, T = 384, 197
 M = 1024 * T
 h = torch.randn(M, D, device="cuda", dtype=torch.bfloat16); x = torch.randn(M, D, device="cuda", dtype=torch.bfloat16)
 fc1 = torch.nn.Linear(D, 4 * D).cuda().bfloat16(); fc2 = torch.nn.Linear(4 * D, D).cuda().bfloat16(); ln = torch.nn.LayerNorm(D, eps=1e-6).cuda().bfloat16()
-buf = torch.zeros(74 * 8, dtype=torch.int64, device="cuda")
+buf = torch.zeros(74 * 6 * 8, dtype=torch.int64, device="cuda")
 f = lambda: ops.mlp_residual_ln(h, fc1.weight, fc1.bias, fc2.weight, fc2.bias, x, ln.weight, ln.bias, 1e-6)
 for _ in range(3): f()
 os.environ["D2S_GEMM_TRACE"] = str(buf.data_ptr())
 f(); torch.cuda.synchronize()
-t = buf.view(74, 8).double()
-ch = t[:, 7].mean().item()
+t = buf[:74 * 16].view(74, 2, 8).double()
+te = buf[74 * 16:74 * 32].view(74, 2, 8).double()
+tf = buf[74 * 32:].view(74, 2, 8).double()
 names = ["issue+other", "wait s_empty", "wait a1_full", "wait w1_full", "wait p_full", "wait w2_full", "wait acc_empty"]
-print(f"chunks per pair {ch:.0f}; MMA-thread cycles per chunk: " + ", ".join(f"{n} {t[:, i].mean().item() / ch:.0f}" for i, n in enumerate(names)))
+for w, nm in ((0, "G1 issuer"), (1, "G2 issuer")):
+    ch = t[:, w, 7].mean().item()
+    print(f"{nm}: {ch:.0f} chunks; cycles per chunk: " + ", ".join(f"{n} {t[:, w, i].mean().item() / ch:.0f}" for i, n in enumerate(names) if t[:, w, i].sum() > 0))
+en = ["between chunks", "wait s_full", "tmem ld + s_empty arrive", "GELU math", "wait p_empty", "P write + fence + p_full arrive", "final epilogue (per tile, /chunks)"]
+for g in (0, 1):
+    ch = te[:, g, 7].mean().item()
+    print(f"E1 group {g} (warp of quadrant 0): {ch:.0f} chunks; cycles per chunk: " + ", ".join(f"{n} {te[:, g, i].mean().item() / ch:.0f}" for i, n in enumerate(en)))
+fn = ["wait acc_full", "x transposition", "pass 1 (+acc_empty)", "x' out", "stats barriers", "pass 2 + h out", "end barrier"]
+tiles = 256 / 24
+for g in (0, 1):
+    print(f"final epilogue, group {g}: cycles per TILE: x loads issue {te[:, g, 6].mean().item() / tiles:.0f}, " + ", ".join(f"{n} {tf[:, g, i].mean().item() / tiles:.0f}" for i, n in enumerate(fn)))
