@@ -318,13 +318,20 @@ mlp_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       size_t goff[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) goff[i] = (size_t)min(row0 + crow + 8 * i, p.M - 1) * TN + cseg * 8;
+      // while the tile's GEMMs run: pull this warp's 32 residual rows (32 x 768 B = 192 lines) into L2, so that pass 1, which
+      // holds the accumulator, streams them at L2 latency; and have the first unit in registers before the wait
+      {
+        const int prow = min(row0 + lane, p.M - 1);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.x + (size_t)prow * TN + k * 64));
+      }
+      uint4 xn[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) xn[i] = ld_nc16(p.x + goff[i]);
       mbar_wait(smem_u32(&bars->acc_full), tile_i & 1);      // all G2 of this tile retired: ACC complete
       tc_fence_after();
       // ---- pass 1: x' = bf16(x + bf16(ACC + b2)) -> global; fp32 sum / sum of squares of the rounded values ----
       uint64_t acc_s = f2_bcast(0.f), acc_q = f2_bcast(0.f);
-      uint4 xn[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) xn[i] = ld_nc16(p.x + goff[i]);
 #pragma unroll 1
       for (int u = 0; u < NU; ++u) {
 #pragma unroll
