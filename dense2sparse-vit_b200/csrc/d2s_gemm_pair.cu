@@ -160,9 +160,9 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           }
       }
     }
-  } else if (warp == 1) {
-    if (lane == 0 && rank == 0) {
-      // ======================================== MMA issuer (leader) ========================================
+  } else if (warp_uniform(warp) == 1) {
+    if (warp_uniform((int)rank) == 0) {
+      // ===== MMA issuer (leader): the whole warp runs the loop warp-uniformly, one elected lane issues (see elect_one) =====
       const uint32_t idesc = make_idesc(2 * kGpBM, UN, 0);
       uint32_t it = 0, tile = 0;
       for (int pt = pair; pt < pair_tiles; pt += num_pairs)
@@ -176,17 +176,21 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             mbar_wait(smem_u32(&bars->full[s]), n & 1);
             tc_fence_after();
             const uint64_t ad = make_desc_sw128(smem_u32(ring + s * kStage), 16, 1024);
+            if (elect_one()) {
 #pragma unroll
-            for (int j = 0; j < NSUB; ++j) {
-              const uint64_t bd = make_desc_sw128(smem_u32(ring + s * kStage + kGpABytes + j * kBSub), 16, 1024);
-              if (kb == 0) mma2_ss_imm<false>(d + j * UN, ad, bd, idesc); else mma2_ss_imm<true>(d + j * UN, ad, bd, idesc);
-              mma2_ss_imm<true>(d + j * UN, ad + 2, bd + 2, idesc);
-              mma2_ss_imm<true>(d + j * UN, ad + 4, bd + 4, idesc);
-              mma2_ss_imm<true>(d + j * UN, ad + 6, bd + 6, idesc);
+              for (int j = 0; j < NSUB; ++j) {
+                const uint64_t bd = make_desc_sw128(smem_u32(ring + s * kStage + kGpABytes + j * kBSub), 16, 1024);
+                if (kb == 0) mma2_ss_imm<false>(d + j * UN, ad, bd, idesc); else mma2_ss_imm<true>(d + j * UN, ad, bd, idesc);
+                mma2_ss_imm<true>(d + j * UN, ad + 2, bd + 2, idesc);
+                mma2_ss_imm<true>(d + j * UN, ad + 4, bd + 4, idesc);
+                mma2_ss_imm<true>(d + j * UN, ad + 6, bd + 6, idesc);
+              }
+              mma2_commit_both(smem_u32(&bars->empty[s]));               // ring slot free in both CTAs once these retire
             }
-            mma2_commit_both(smem_u32(&bars->empty[s]));                 // ring slot free in both CTAs once these retire
+            __syncwarp();
           }
-          mma2_commit_both(smem_u32(&bars->tmem_full[as]));
+          if (elect_one()) mma2_commit_both(smem_u32(&bars->tmem_full[as]));
+          __syncwarp();
         }
     }
   } else {
