@@ -91,18 +91,23 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   tc_fence_after();
   const uint32_t tmem = bars->tmem_base;
 
-  if (warp == kSW) {
-    if (lane == 0) {
-      // =============================== control thread: TMA + MMA issue ===============================
+  if (warp_uniform(warp) == kSW) {
+    {
+      // ====== control warp: TMA + MMA issue.  The whole warp runs the loop warp-uniformly (waits, address arithmetic) and one
+      // elected lane issues each TMA / tcgen05 instruction: under `if (lane == 0)` every tcgen05.mma was wrapped in an
+      // ELECT / R2UR.BROADCAST waterfall loop (72-cycle issue cadence against 32 cycles of tensor work per PV step) ======
       const uint32_t idesc_s = make_idesc(128, Tkp, 0);
       const uint32_t idesc_o = make_idesc(128, kTcHD, 1);
       const uint64_t vd = make_desc_sw128(smem_u32(v_s), 16, 1024);
       const int ksteps = Tkp / 16;
       // one operand = one box of rows_a rows (+ one of rows_b rows), landing contiguously
       auto load_rows = [&](unsigned char* dst, int col, int b, uint32_t bar) {
-        mbar_expect_tx(bar, bytes_a + bytes_b);
-        tma_load_3d(smem_u32(dst), &map_a, col, 0, b, bar);
-        if (kNT == 2) tma_load_3d(smem_u32(dst) + bytes_a, &map_b, col, kTileRows, b, bar);
+        if (elect_one()) {
+          mbar_expect_tx(bar, bytes_a + bytes_b);
+          tma_load_3d(smem_u32(dst), &map_a, col, 0, b, bar);
+          if (kNT == 2) tma_load_3d(smem_u32(dst) + bytes_a, &map_b, col, kTileRows, b, bar);
+        }
+        __syncwarp();
       };
       auto issue_k = [&](int unit, uint32_t it) {
         const uint32_t kb = kbufs == 2 ? (it & 1) : 0;
@@ -110,8 +115,11 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       };
       auto issue_q = [&](int unit, int t) {
         const uint32_t bar = smem_u32(&bars->q_full[t]);
-        mbar_expect_tx(bar, t == 0 ? bytes_a : bytes_b);
-        tma_load_3d(smem_u32(q_s[t]), t == 0 ? &map_a : &map_b, (unit % H) * kTcHD, t * kTileRows, unit / H, bar);
+        if (elect_one()) {
+          mbar_expect_tx(bar, t == 0 ? bytes_a : bytes_b);
+          tma_load_3d(smem_u32(q_s[t]), t == 0 ? &map_a : &map_b, (unit % H) * kTcHD, t * kTileRows, unit / H, bar);
+        }
+        __syncwarp();
       };
       auto issue_v = [&](int unit) { load_rows(v_s, (2 * H + unit % H) * kTcHD, unit / H, smem_u32(&bars->v_full)); };
       int unit = blockIdx.x;
@@ -137,11 +145,14 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
           if (g > 0) mbar_wait(smem_u32(&bars->tmem_free), (g - 1) & 1);
           tc_fence_after();
           const uint64_t qd = make_desc_sw128(smem_u32(q_s[t]), 16, 1024);
-          mma_ss_imm<false>(tmem, qd, kd, idesc_s);
-          mma_ss_imm<true>(tmem, qd + 2, kd + 2, idesc_s);
-          mma_ss_imm<true>(tmem, qd + 4, kd + 4, idesc_s);
-          mma_ss_imm<true>(tmem, qd + 6, kd + 6, idesc_s);
-          mma_commit(smem_u32(&bars->s_full));
+          if (elect_one()) {
+            mma_ss_imm<false>(tmem, qd, kd, idesc_s);
+            mma_ss_imm<true>(tmem, qd + 2, kd + 2, idesc_s);
+            mma_ss_imm<true>(tmem, qd + 4, kd + 4, idesc_s);
+            mma_ss_imm<true>(tmem, qd + 6, kd + 6, idesc_s);
+            mma_commit(smem_u32(&bars->s_full));
+          }
+          __syncwarp();
           const bool last = t == kNT - 1;
           mbar_wait(smem_u32(&bars->p_full), g & 1);   // softmax done => this tile's S-MMA has completed as well
           if (has_next) {
@@ -151,15 +162,18 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
           if (t == 0) mbar_wait(smem_u32(&bars->v_full), it & 1);
           tc_fence_after();
           // fully unrolled issue (T <= 256 => at most 16 K-steps); descriptors advance by constants
-          mma_ts_imm<false>(tmem + kOCol, tmem, vd, idesc_o);
           const int split = kSW == 8 ? (ksteps + 1) / 2 : 16;   // first K-step whose P lives in the second half's region
+          if (elect_one()) {
+            mma_ts_imm<false>(tmem + kOCol, tmem, vd, idesc_o);
 #pragma unroll
-          for (int ks = 1; ks < 16; ++ks)
-            if (ks < ksteps) {
-              const uint32_t pa = ks < split ? (uint32_t)(ks * 8) : (uint32_t)(split * 16 + (ks - split) * 8);
-              mma_ts_imm<true>(tmem + kOCol, tmem + pa, vd + (uint64_t)(ks * 128), idesc_o);
-            }
-          mma_commit(smem_u32(&bars->o_full));
+            for (int ks = 1; ks < 16; ++ks)
+              if (ks < ksteps) {
+                const uint32_t pa = ks < split ? (uint32_t)(ks * 8) : (uint32_t)(split * 16 + (ks - split) * 8);
+                mma_ts_imm<true>(tmem + kOCol, tmem + pa, vd + (uint64_t)(ks * 128), idesc_o);
+              }
+            mma_commit(smem_u32(&bars->o_full));
+          }
+          __syncwarp();
           if (last && has_next) {
             mbar_wait(smem_u32(&bars->o_full), g & 1);  // V is dead once the PV-MMA has completed
             issue_v(next);
