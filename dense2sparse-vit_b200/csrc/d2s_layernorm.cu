@@ -60,7 +60,8 @@ template <typename T_, int kVPL>
 __global__ void __launch_bounds__(kLnThreads)
 add_layernorm_kernel(const T_* __restrict__ x, const T_* __restrict__ y, const T_* __restrict__ gamma,
                      const T_* __restrict__ beta, long long rows, int T, int D, long long x_stride_b, long long x_stride_t,
-                     float eps, int norm_row0, T_* __restrict__ out_sum, T_* __restrict__ out_norm) {
+                     float eps, int norm_row0, T_* __restrict__ out_sum, T_* __restrict__ out_norm,
+                     const int64_t* __restrict__ gather_idx) {
   constexpr int VE = LnVec<T_>::kElems;
   const int sub = threadIdx.x & 15;
   const long long row = (long long)blockIdx.x * kLnRowsPerCta + (threadIdx.x >> 4);
@@ -68,7 +69,9 @@ add_layernorm_kernel(const T_* __restrict__ x, const T_* __restrict__ y, const T
   const int nvec = D / VE;
   const long long b = row_ok ? row / T : 0;
   const int t = row_ok ? (int)(row - b * T) : 0;
-  const T_* xr = x + b * x_stride_b + (long long)t * x_stride_t;
+  // gather mode (d2s_gather_layernorm): output token 0 is the CLS row, token t >= 1 is input token idx[b, t-1] + 1
+  const long long src_t = (gather_idx && row_ok && t > 0) ? gather_idx[b * (T - 1) + (t - 1)] + 1 : (long long)t;
+  const T_* xr = x + b * x_stride_b + src_t * x_stride_t;
   const T_* yr = y ? y + row * D : nullptr;
 
   float v[kVPL][8];
@@ -132,7 +135,8 @@ add_layernorm_kernel(const T_* __restrict__ x, const T_* __restrict__ y, const T
 
 template <typename T_>
 static int launch_ln(const void* x, const void* y, const void* gamma, const void* beta, int B, int T, int D,
-                     long long sb, long long st, float eps, int norm_row0, void* out_sum, void* out_norm, cudaStream_t stream) {
+                     long long sb, long long st, float eps, int norm_row0, void* out_sum, void* out_norm, cudaStream_t stream,
+                     const int64_t* gather_idx = nullptr) {
   constexpr int VE = LnVec<T_>::kElems;
   const long long rows = (long long)B * T;
   const int nvec = D / VE;
@@ -141,7 +145,7 @@ static int launch_ln(const void* x, const void* y, const void* gamma, const void
 #define D2S_LN_LAUNCH(V)                                                                                              \
   add_layernorm_kernel<T_, V><<<grid, kLnThreads, 0, stream>>>((const T_*)x, (const T_*)y, (const T_*)gamma,           \
                                                                (const T_*)beta, rows, T, D, sb, st, eps, norm_row0,    \
-                                                               (T_*)out_sum, (T_*)out_norm)
+                                                               (T_*)out_sum, (T_*)out_norm, gather_idx)
   if (vpl <= 2) D2S_LN_LAUNCH(2);
   else if (vpl <= 3) D2S_LN_LAUNCH(3);
   else if (vpl <= 6) D2S_LN_LAUNCH(6);
@@ -177,4 +181,25 @@ extern "C" int d2s_add_layernorm(const void* x, const void* y, const void* gamma
                                         (cudaStream_t)stream)
              : launch_ln<float>(x, y, gamma, beta, B, T, D, x_stride_b, x_stride_t, eps, norm_row0, out_sum, out_norm,
                                 (cudaStream_t)stream);
+}
+
+/* Kept-token gather fused with the LayerNorm that follows it (default_dynamic_vit.py:464-468 + Block.forward's norm1,
+ * dynamic_vit.py:907-912 + :263): out_sum (B,K+1,D) = [CLS, x[idx+1]], out_norm = LayerNorm(out_sum) * gamma + beta. */
+extern "C" int d2s_gather_layernorm(const void* x, const int64_t* idx, const void* gamma, const void* beta, int dtype, int B,
+                                    int T_in, int D, int K, float eps, void* out_sum, void* out_norm, d2s_stream_t stream) {
+  D2S_REQUIRE(x && (idx || K == 0) && gamma && beta && out_sum && out_norm, D2S_ERR_ARG, "gather_layernorm: null pointer");
+  D2S_REQUIRE(dtype == D2S_F32 || dtype == D2S_BF16, D2S_ERR_ARG, "gather_layernorm: dtype %d unsupported", dtype);
+  D2S_REQUIRE(B >= 0 && T_in >= 1 && D >= 1 && K >= 0 && K <= T_in - 1, D2S_ERR_ARG,
+              "gather_layernorm: bad shape B=%d T_in=%d D=%d K=%d", B, T_in, D, K);
+  const int ve = dtype == D2S_BF16 ? 8 : 4;
+  D2S_REQUIRE(D % ve == 0 && D / ve <= 16 * 12, D2S_ERR_ARG, "gather_layernorm: D=%d must be a multiple of %d and at most %d", D,
+              ve, 16 * 12 * ve);
+  D2S_REQUIRE(aligned16(x) && aligned16(gamma) && aligned16(beta) && aligned16(out_sum) && aligned16(out_norm), D2S_ERR_ALIGN,
+              "gather_layernorm: pointers must be 16-byte aligned");
+  if (B == 0) return D2S_OK;
+  const long long sb = (long long)T_in * D, st = D;
+  return dtype == D2S_BF16
+             ? launch_ln<__nv_bfloat16>(x, nullptr, gamma, beta, B, K + 1, D, sb, st, eps, 0, out_sum, out_norm, (cudaStream_t)stream, K ? idx : nullptr)
+             : launch_ln<float>(x, nullptr, gamma, beta, B, K + 1, D, sb, st, eps, 0, out_sum, out_norm, (cudaStream_t)stream,
+                                K ? idx : nullptr);
 }

@@ -159,9 +159,19 @@ class _Stream:
     Falls back to plain Block.forward when the fused path does not apply."""
 
     def __init__(self, x):
-        self.x, self.y, self.lin, self.mlp = x, None, None, None
+        self.x, self.y, self.lin, self.mlp, self.gidx = x, None, None, None, None
+
+    def gather(self, x, kept):
+        """The pruning stage's kept-token gather (default_dynamic_vit.py:464-468, dynamic_vit.py:907-912), deferred so that it
+        runs fused with the next block's norm1 (ops.gather_layernorm)."""
+        self.x, self.y, self.lin, self.mlp, self.gidx = x, None, None, None, kept
+
+    def _flush_gather(self):
+        if self.gidx is not None:
+            self.x, self.gidx = ops.gather_tokens(self.x, self.gidx, prepend_cls=True), None
 
     def _flush_lin(self):
+        self._flush_gather()
         if self.mlp is not None:                       # deferred whole MLP (h, module): its fc2 becomes the deferred Linear
             h, m = self.mlp
             self.lin, self.mlp = (mlp_hidden(m, h), m.fc2), None
@@ -177,6 +187,12 @@ class _Stream:
 
     def _sum_norm(self, norm, row0=0):
         """(x + branch, norm((x + branch)[:, row0:])); leaves the stream holding the summed x."""
+        if self.gidx is not None:
+            if row0 == 0 and self.x.dtype in (torch.float32, torch.bfloat16):
+                (x, kept), self.gidx = (self.x, self.gidx), None
+                self.x, h = ops.gather_layernorm(x, kept, norm.weight, norm.bias, norm.eps)
+                return self.x, h
+            self._flush_gather()
         if self.mlp is not None:
             h, m = self.mlp
             if _mlp_fused_ok(m, h, self.x):
@@ -202,6 +218,8 @@ class _Stream:
     def block(self, blk, policy=None, return_cls_attn=False):
         """Inference form of Block.forward (dynamic_vit.py:263-283): every residual add is folded into the LayerNorm that
         follows it, and the Linear that produced the branch into the same kernel when it can be."""
+        if not _fusable(blk, self.x, policy):
+            self._flush_gather()
         if _fusable(blk, self.x, policy):
             _, h = self._sum_norm(blk.norm1)
             o, cls_attn = attention_pre_proj(blk.attn, h, policy, return_cls_attn)
@@ -228,6 +246,7 @@ class _Stream:
 
     def cls_normed(self, norm):
         """norm(x + y)[:, 0]: only the CLS row (what the eval heads consume)."""
+        self._flush_gather()
         if _is_plain_ln(norm) and self.x.is_cuda and not _needs_grad(self.x, self.y, norm.weight):
             if self.mlp is not None:                     # the last MLP is only needed for the CLS rows
                 h, m = self.mlp
@@ -466,7 +485,7 @@ def variant_a_forward(model, img):
                     prev_decision = ops.batch_index_select(prev_decision, keep_policy)
                     prev_f32 = prev_decision.reshape(B, -1).float()
                 model.kept_token_indices.append(keep_policy)
-                st.x = ops.gather_tokens(x, keep_policy, prepend_cls=True)
+                st.gather(x, keep_policy)
                 st.block(blk)
             p_count += 1
         else:
@@ -512,7 +531,7 @@ def variant_b_forward(model, img, stacked_cls_attn_weights=None):
                 model.kept_token_indices.append(kept)
                 model.dropped_token_indices.append(dropped)
                 model.pred_logits.append(pred_logits)
-                st.x = ops.gather_tokens(x, kept, prepend_cls=True)
+                st.gather(x, kept)
                 cls_attn = st.block(blk, return_cls_attn=True)
                 model.cls_attns.append(cls_attn[:, :, 1:])
             elif model.training:

@@ -383,6 +383,23 @@ def add_layernorm(x, y, weight, bias, eps, norm_row0=0, want_sum=True):
     return out_sum, out_norm
 
 
+def gather_layernorm(x, kept, weight, bias, eps):
+    """(xg, LayerNorm(xg)) with xg = [CLS, x[:, kept + 1]]: the kept-token gather of the pruning stage fused with the next
+    block's norm1 (vit_models/default_dynamic_vit.py:464-468, dynamic_vit.py:907-912 + :263).  Inference only."""
+    _check_cuda(x, kept, weight, bias)
+    if kept.dtype != torch.int64:
+        raise TypeError("indices must be int64")
+    xc, ic = x.detach().contiguous(), kept.contiguous()
+    B, T, D = xc.shape
+    K = ic.shape[1]
+    w, b = weight.detach().to(xc.dtype).contiguous(), bias.detach().to(xc.dtype).contiguous()
+    out_sum = torch.empty(B, K + 1, D, dtype=xc.dtype, device=xc.device)
+    out_norm = torch.empty_like(out_sum)
+    _lib.call("d2s_gather_layernorm", _ptr(xc), _ptr(ic), _ptr(w), _ptr(b), _dtype_code(xc), B, T, D, K, float(eps),
+              _ptr(out_sum), _ptr(out_norm), _stream())
+    return out_sum, out_norm
+
+
 # ----------------------------------------------------------------------------------------------
 # predictor body (inference)
 # ----------------------------------------------------------------------------------------------

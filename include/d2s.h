@@ -187,6 +187,12 @@ int d2s_add_layernorm(const void* x, const void* y, const void* gamma, const voi
                       long long x_stride_b, long long x_stride_t, float eps, int norm_row0,
                       void* out_sum, void* out_norm, d2s_stream_t stream);
 
+/* Kept-token gather fused with the LayerNorm that follows it (default_dynamic_vit.py:464-468 / dynamic_vit.py:907-912, then
+ * Block.forward's norm1): out_sum (B,K+1,D) = [CLS, x[:, idx+1]] (x (B,T_in,D) contiguous, idx (B,K) int64 spatial indices),
+ * out_norm (B,K+1,D) = LayerNorm(out_sum) * gamma + beta.  Same dtype / D constraints as d2s_add_layernorm. */
+int d2s_gather_layernorm(const void* x, const int64_t* idx, const void* gamma, const void* beta, int dtype, int B, int T_in,
+                         int D, int K, float eps, void* out_sum, void* out_norm, d2s_stream_t stream);
+
 /* Linear + activation in one tcgen05 GEMM (fc1 + GELU of Mlp.forward, dynamic_vit.py:159-175), bf16 only:
  * out (M,N) = act(a (M,K) @ w (N,K)^T + bias (N)); fp32 accumulation; bias may be NULL.
  * N % 256 == 0 (N <= 4096), K % 64 == 0. */

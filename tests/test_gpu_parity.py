@@ -569,6 +569,22 @@ def test_mlp_residual_ln_fused(ops, M, HID):
     assert none is None and torch.equal(s2.cpu(), s)
 
 
+@pytest.mark.parametrize("B,T,D,K,dtype", [(3, 197, 384, 137, torch.bfloat16), (2, 138, 384, 96, torch.float32), (1, 9, 64, 0, torch.float32),
+                                            (2, 197, 768, 196, torch.bfloat16)])
+def test_gather_layernorm_fused(ops, B, T, D, K, dtype):
+    """Kept-token gather + next LayerNorm in one kernel: the gathered rows bit-exact, the norm as add_layernorm's."""
+    x = fx.randn(800 + T, B, T, D).to(dtype)
+    kept = torch.stack([torch.sort(torch.randperm(T - 1, generator=fx.gen(801 + b))[:K])[0] for b in range(B)]).long()
+    g = (1.0 + 0.3 * fx.randn(802, D)).to(dtype)
+    bt = (0.2 * fx.randn(803, D)).to(dtype)
+    xg, h = ops.gather_layernorm(cu(x), cu(kept), cu(g), cu(bt), 1e-6)
+    ref = oo.gather_tokens_with_cls(x, kept)
+    assert torch.equal(xg.cpu(), ref)
+    href = torch.nn.functional.layer_norm(ref.float(), (D,), g.float(), bt.float(), 1e-6)
+    tol = dict(rtol=1e-2, atol=1e-2) if dtype == torch.bfloat16 else FP32
+    torch.testing.assert_close(h.cpu().float(), href, **tol)
+
+
 def test_score_tail_a_gelu_on_load_and_prev_gather(ops):
     B, N, Cc, K = 4, 196, 96, 137
     raw = fx.randn(170, B, N, Cc)
