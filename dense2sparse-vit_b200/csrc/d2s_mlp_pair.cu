@@ -70,6 +70,7 @@ struct MpParams {
   __nv_bfloat16 *out_sum, *out_norm;
   float eps;
   int M, HID, want_ln;
+  int T, ln_row0;               // LayerNorm output skips the first ln_row0 tokens of every T-token image (predictor norm over x[:, 1:])
 };
 
 __global__ void __cluster_dims__(2, 1, 1) __maxnreg__(128)
@@ -390,6 +391,16 @@ mlp_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         const float rstd = rsqrtf(var + p.eps);
         const uint64_t sc = f2_bcast(rstd), sh = f2_bcast(-mean * rstd);
         // ---- pass 2: hn = (x' - mean) * rstd * gamma + beta; x' comes back from L2 (this warp wrote it above) ----
+        // hn row of global row g = (image b, token t): b * (T - ln_row0) + t - ln_row0, tokens t < ln_row0 are not written
+        size_t hoff[4];
+        bool hok[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int g = row0 + crow + 8 * i;
+          const int bimg = g / p.T, t = g - bimg * p.T;
+          hok[i] = 8 * i < rows_left && t >= p.ln_row0;
+          hoff[i] = ((size_t)bimg * (p.T - p.ln_row0) + (size_t)max(t - p.ln_row0, 0)) * TN + cseg * 8;
+        }
 #pragma unroll
         for (int i = 0; i < 4; ++i) xn[i] = ld_cg16(p.out_sum + goff[i]);
 #pragma unroll 1
@@ -427,7 +438,7 @@ mlp_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
           for (int i = 0; i < 4; ++i) {
             const int row = 8 * i + crow;
             const uint4 val = *reinterpret_cast<const uint4*>(buf + row * 64 + ((cseg ^ ((row >> 1) & 3)) << 4));
-            if (8 * i < rows_left) *reinterpret_cast<uint4*>(p.out_norm + goff[i] + u * 32) = val;
+            if (hok[i]) *reinterpret_cast<uint4*>(p.out_norm + hoff[i] + u * 32) = val;
           }
           __syncwarp();
         }
@@ -463,13 +474,15 @@ using namespace d2s;
 
 extern "C" int d2s_mlp_residual_ln_bf16(const void* h, const void* w1, const void* b1, const void* w2, const void* b2,
                                         const void* x, const void* gamma, const void* beta, float eps, int M, int D, int HID,
-                                        void* out_sum, void* out_norm, d2s_stream_t stream) {
+                                        int T, int norm_row0, void* out_sum, void* out_norm, d2s_stream_t stream) {
   const char* what = "d2s_mlp_residual_ln_bf16";
   D2S_REQUIRE(h && w1 && w2 && x && out_sum, D2S_ERR_ARG, "mlp_residual_ln: null pointer");
   D2S_REQUIRE(M >= 0 && D == kMpD && HID >= 3 * kMpCH && HID % kMpCH == 0 && HID <= 2048, D2S_ERR_ARG,
               "mlp_residual_ln: need D == %d and HID %% %d == 0, %d <= HID <= 2048 (got M=%d D=%d HID=%d)", kMpD, kMpCH, 3 * kMpCH, M,
               D, HID);
   D2S_REQUIRE(!out_norm || (gamma && beta), D2S_ERR_ARG, "mlp_residual_ln: out_norm needs gamma and beta");
+  D2S_REQUIRE(T >= 1 && norm_row0 >= 0 && norm_row0 < T && (norm_row0 == 0 || M % T == 0), D2S_ERR_ARG,
+              "mlp_residual_ln: need 0 <= norm_row0 < T and M %% T == 0 (got M=%d T=%d norm_row0=%d)", M, T, norm_row0);
   D2S_REQUIRE(aligned16(h) && aligned16(w1) && aligned16(w2) && aligned16(x) && aligned16(out_sum) && aligned16(out_norm),
               D2S_ERR_ALIGN, "mlp_residual_ln: pointers must be 16-byte aligned");
   if (M == 0) return D2S_OK;
@@ -480,7 +493,7 @@ extern "C" int d2s_mlp_residual_ln_bf16(const void* h, const void* w1, const voi
   if ((rc = mp_map_2d(&mw2, w2, HID, D, 64, 96, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, what))) return rc;
   const char* tr_env = getenv("D2S_GEMM_TRACE");
   MpParams p{tr_env ? reinterpret_cast<long long*>(strtoull(tr_env, nullptr, 10)) : nullptr, (const __nv_bfloat16*)b1, (const __nv_bfloat16*)b2, (const __nv_bfloat16*)gamma, (const __nv_bfloat16*)beta,
-             (const __nv_bfloat16*)x, (__nv_bfloat16*)out_sum, (__nv_bfloat16*)out_norm, eps, M, HID, out_norm ? 1 : 0};
+             (const __nv_bfloat16*)x, (__nv_bfloat16*)out_sum, (__nv_bfloat16*)out_norm, eps, M, HID, out_norm ? 1 : 0, T, norm_row0};
   const size_t smem = 1024 + (size_t)kMpKB * kMpA1Blk + 2 * (size_t)kMpPBlk + (size_t)kMpW1Slots * kMpW1Blk +
                       (size_t)kMpW2Slots * kMpW2Blk + sizeof(MpBars) + (size_t)HID * 4 + 3 * kMpD * 4 + (size_t)kMpOutWarps * 2048 + 32;
   D2S_REQUIRE(smem <= 227 * 1024, D2S_ERR_ARG, "mlp_residual_ln: needs %zu B of shared memory", smem);

@@ -197,11 +197,9 @@ class _Stream:
             h, m = self.mlp
             if _mlp_fused_ok(m, h, self.x):
                 self.mlp = None
-                if row0 == 0:
-                    self.x, hn = ops.mlp_residual_ln(h, m.fc1.weight, m.fc1.bias, m.fc2.weight, m.fc2.bias, self.x,
-                                                     norm.weight, norm.bias, norm.eps)
-                    return self.x, hn
-                self.x, _ = ops.mlp_residual_ln(h, m.fc1.weight, m.fc1.bias, m.fc2.weight, m.fc2.bias, self.x, want_norm=False)
+                self.x, hn = ops.mlp_residual_ln(h, m.fc1.weight, m.fc1.bias, m.fc2.weight, m.fc2.bias, self.x,
+                                                 norm.weight, norm.bias, norm.eps, norm_row0=row0)
+                return self.x, hn
             else:
                 self.lin, self.mlp = (mlp_hidden(m, h), m.fc2), None
         if self.lin is not None and _pair_ok(self.lin[1], self.lin[0], self.x):

@@ -550,10 +550,11 @@ def linear_residual_ln(a, weight, bias, x, ln_weight=None, ln_bias=None, eps=1e-
     return out_sum, out_norm
 
 
-def mlp_residual_ln(h, w1, b1, w2, b2, x, ln_weight=None, ln_bias=None, eps=1e-5, want_norm=True):
+def mlp_residual_ln(h, w1, b1, w2, b2, x, ln_weight=None, ln_bias=None, eps=1e-5, want_norm=True, norm_row0=0):
     """(x', hn) with x' = x + fc2(GELU(fc1(h))) and hn = LayerNorm(x') * ln_weight + ln_bias (None when want_norm is False):
     the MLP branch of Block.forward with its residual add and the next LayerNorm (vit_models/dynamic_vit.py:159-175, :263-283)
-    in ONE CTA-pair tcgen05 kernel; the hidden activations stay on chip.  bf16, inference only, D == 384."""
+    in ONE CTA-pair tcgen05 kernel; the hidden activations stay on chip.  bf16, inference only, D == 384.
+    norm_row0 > 0 (x of shape (B,T,D)): hn = LayerNorm(x'[:, norm_row0:]) of shape (B, T-norm_row0, D)."""
     _check_cuda(h, w1, b1, w2, b2, x, ln_weight, ln_bias)
     if h.dtype != torch.bfloat16 or x.dtype != torch.bfloat16:
         raise TypeError("mlp_residual_ln is a bf16 kernel")
@@ -567,7 +568,14 @@ def mlp_residual_ln(h, w1, b1, w2, b2, x, ln_weight=None, ln_bias=None, eps=1e-5
         raise RuntimeError(f"mlp_residual_ln: inconsistent shapes h{tuple(h.shape)} w1{tuple(w1.shape)} w2{tuple(w2.shape)} x{tuple(x.shape)}")
     g, bt = (bf(ln_weight), bf(ln_bias)) if want_norm else (None, None)
     out_sum = torch.empty_like(xc)
-    out_norm = torch.empty_like(xc) if want_norm else None
+    T = 1
+    if norm_row0:
+        if xc.dim() != 3:
+            raise RuntimeError("mlp_residual_ln: norm_row0 needs x of shape (B, T, D)")
+        T = xc.shape[1]
+    out_norm = None
+    if want_norm:
+        out_norm = torch.empty(xc.shape[0], T - norm_row0, D, dtype=xc.dtype, device=xc.device) if norm_row0 else torch.empty_like(xc)
     _lib.call("d2s_mlp_residual_ln_bf16", _ptr(hc), _ptr(w1c), _ptr(bf(b1)), _ptr(w2c), _ptr(bf(b2)), _ptr(xc), _ptr(g), _ptr(bt),
-              float(eps), M, D, HID, _ptr(out_sum), _ptr(out_norm), _stream())
+              float(eps), M, D, HID, T, int(norm_row0), _ptr(out_sum), _ptr(out_norm), _stream())
     return out_sum, out_norm

@@ -62,16 +62,17 @@ def test_argument_errors_precede_any_launch(d2s):
     assert lib.d2s_linear_residual_ln_bf16(p, p, p, p, p, p, 1e-6, 256, 384, 100, p, p, None) == 1 and b"K %" in lib.d2s_last_error()
     assert lib.d2s_linear_act_pair_bf16(p, p, p, 256, 300, 384, 1, p, None) == 1 and b"N % 256" in lib.d2s_last_error()
     assert lib.d2s_linear_act_pair_bf16(p + 8, p, p, 256, 256, 384, 1, p, None) == 2
-    assert lib.d2s_mlp_residual_ln_bf16(p, p, p, p, p, p, p, p, 1e-6, 256, 768, 3072, p, p, None) == 1 and b"D == 384" in lib.d2s_last_error()
-    assert lib.d2s_mlp_residual_ln_bf16(p, p, p, p, p, p, p, p, 1e-6, 256, 384, 1000, p, p, None) == 1 and b"HID" in lib.d2s_last_error()
-    assert lib.d2s_mlp_residual_ln_bf16(None, p, p, p, p, p, p, p, 1e-6, 256, 384, 1536, p, p, None) == 1 and b"null" in lib.d2s_last_error()
+    assert lib.d2s_mlp_residual_ln_bf16(p, p, p, p, p, p, p, p, 1e-6, 256, 768, 3072, 1, 0, p, p, None) == 1 and b"D == 384" in lib.d2s_last_error()
+    assert lib.d2s_mlp_residual_ln_bf16(p, p, p, p, p, p, p, p, 1e-6, 256, 384, 1000, 1, 0, p, p, None) == 1 and b"HID" in lib.d2s_last_error()
+    assert lib.d2s_mlp_residual_ln_bf16(None, p, p, p, p, p, p, p, 1e-6, 256, 384, 1536, 1, 0, p, p, None) == 1 and b"null" in lib.d2s_last_error()
+    assert lib.d2s_mlp_residual_ln_bf16(p, p, p, p, p, p, p, p, 1e-6, 256, 384, 1536, 197, 1, p, p, None) == 1 and b"norm_row0" in lib.d2s_last_error()
     assert lib.d2s_softmax_policy_fwd_ld(p, None, 1, 1, 197, 200, 197, 1e-6, p, None, None) == 1 and b"ld" in lib.d2s_last_error()
     assert lib.d2s_softmax_policy_bwd_ld(p, None, p, p, 1, 1, 300, 304, 304, 1e-6, p, None, None) == 1 and b"T=300" in lib.d2s_last_error()
     assert lib.d2s_split_heads_bf16(p, 1, 197, 100, 3, 6, 64, p, None) == 1 and b"Tp=100" in lib.d2s_last_error()
     assert lib.d2s_merge_heads_bf16(p, 1, 197, 200, 3, 6, 60, p, None) == 1 and b"hd=60" in lib.d2s_last_error()
     assert d2s._lib.launch_count() == before
     # empty batches are a no-op, not an error
-    assert lib.d2s_mlp_residual_ln_bf16(p, p, p, p, p, p, p, p, 1e-6, 0, 384, 1536, p, p, None) == 0
+    assert lib.d2s_mlp_residual_ln_bf16(p, p, p, p, p, p, p, p, 1e-6, 0, 384, 1536, 1, 0, p, p, None) == 0
     assert lib.d2s_split_heads_bf16(p, 0, 197, 200, 3, 6, 64, p, None) == 0
     assert lib.d2s_select_topk_f32(p, 0, 196, 10, 0, p, p, None) == 0
     assert lib.d2s_gather_tokens(p, 0, 0, 4, 8, p, 2, 1, p, None) == 0

@@ -543,7 +543,7 @@ def test_linear_residual_ln(ops, M, N, K):
     assert none is None and torch.equal(s2.cpu(), s)
 
 
-@pytest.mark.parametrize("M,HID", [(256, 1536), (1000, 1536), (77, 1536), (3 * 197, 1536), (20000, 1536), (513, 192), (300, 768)])
+@pytest.mark.parametrize("M,HID", [(256, 1536), (1000, 1536), (77, 1536), (3 * 197, 1536), (20000, 1536), (513, 192), (300, 768), (5 * 77, 1536)])
 def test_mlp_residual_ln_fused(ops, M, HID):
     """fc1 + GELU + fc2 + residual + next LayerNorm (dynamic_vit.py:159-175, :263-283) in one kernel vs the separate bf16 ops
     (each intermediate rounded to bf16 like the reference's modules)."""
@@ -567,6 +567,12 @@ def test_mlp_residual_ln_fused(ops, M, HID):
     torch.testing.assert_close(hn.float(), hn_ref, rtol=8e-3, atol=8e-3)
     s2, none = ops.mlp_residual_ln(cu(h), cu(w1), cu(b1), cu(w2), cu(b2), cu(x), want_norm=False)
     assert none is None and torch.equal(s2.cpu(), s)
+    if M % 77 == 0:   # the predictors' norm over x[:, 1:]: images of 77 tokens, CLS rows skipped and the output compacted
+        Bn, Tn = M // 77, 77
+        s3, h3 = ops.mlp_residual_ln(cu(h).view(Bn, Tn, D), cu(w1), cu(b1), cu(w2), cu(b2), cu(x).view(Bn, Tn, D), cu(g), cu(bt), 1e-6,
+                                     norm_row0=1)
+        assert h3.shape == (Bn, Tn - 1, D) and torch.equal(s3.cpu().view(M, D), s)
+        assert torch.equal(h3.cpu(), hn.view(Bn, Tn, D)[:, 1:])
 
 
 @pytest.mark.parametrize("B,T,D,K,dtype", [(3, 197, 384, 137, torch.bfloat16), (2, 138, 384, 96, torch.float32), (1, 9, 64, 0, torch.float32),
