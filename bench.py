@@ -217,16 +217,17 @@ def kernel_breakdown(ops, B, dev, torch, pk):
         rows.append(dict(kernel="mlp_residual_ln(fc1+GELU+fc2+add+LN, tcgen05 pair)", shape=f"M={B * T},D={D},HID={4 * D}", launches_per_step=2,
                          ms=ms, algo_bytes=by, gbs=by / ms / 1e6, tflops=fl / ms / 1e9))
         mlp_ms += 2 * ms; mlp_bytes += 2 * by; mlp_flops += 2 * fl; mlp_n += 2
-        if gi < 3:
-            ms = time_kernel(lambda: ops.mlp_residual_ln(xr, w1, b1, w2, gb, yr, want_norm=False), 10, torch)
-            by = B * T * e * 3 * D
-            rows.append(dict(kernel="mlp_residual_ln(fc1+GELU+fc2+add, tcgen05 pair)", shape=f"M={B * T},D={D},HID={4 * D}", launches_per_step=1,
-                             ms=ms, algo_bytes=by, gbs=by / ms / 1e6, tflops=fl / ms / 1e9))
+        if gi < 3:   # the block in front of a pruning stage: the LayerNorm is the predictor's, over x[:, 1:]
+            ms = time_kernel(lambda: ops.mlp_residual_ln(xr, w1, b1, w2, gb, yr, gw, gb, 1e-6, norm_row0=1), 10, torch)
+            by = B * e * D * (3 * T + T - 1)
+            rows.append(dict(kernel="mlp_residual_ln(fc1+GELU+fc2+add+LN over x[:,1:], tcgen05 pair)", shape=f"M={B * T},D={D},HID={4 * D}",
+                             launches_per_step=1, ms=ms, algo_bytes=by, gbs=by / ms / 1e6, tflops=fl / ms / 1e9))
             mlp_ms += ms; mlp_bytes += by; mlp_flops += fl; mlp_n += 1
-        ms = time_kernel(lambda: ops.add_layernorm(xr, None, gw, gb, 1e-6), 20, torch)
-        by = B * T * D * e * 2
-        rows.append(dict(kernel="add_layernorm(no branch)", shape=f"B={B},T={T},D={D}", launches_per_step=2 if gi < 3 else 1, ms=ms,
-                         algo_bytes=by, gbs=by / ms / 1e6))
+        if gi == 0:   # the first block's norm1 is the only stand-alone LayerNorm over all tokens left in the step
+            ms = time_kernel(lambda: ops.add_layernorm(xr, None, gw, gb, 1e-6), 20, torch)
+            by = B * T * D * e * 2
+            rows.append(dict(kernel="add_layernorm(no branch)", shape=f"B={B},T={T},D={D}", launches_per_step=1, ms=ms,
+                             algo_bytes=by, gbs=by / ms / 1e6))
         del xr, yr, w1, w2, ur, wp
     n_in = N0
     for s, K in enumerate(Ks):
@@ -234,9 +235,10 @@ def kernel_breakdown(ops, B, dev, torch, pk):
         x = torch.randn(B, T_in, D, device=dev, dtype=torch.bfloat16)
         sc = torch.rand(B, n_in, device=dev)
         kept, _ = ops.select_topk(sc, K, ops.ORDER_SCORE_DESC, want_dropped=False)
-        ms = time_kernel(lambda: ops.gather_tokens(x, kept), 50, torch)
-        by = B * (2 * e * D * (K + 1) + 8 * (K + 1))
-        rows.append(dict(kernel="gather_tokens", shape=f"B={B},T={T_in},D={D},K={K}", launches_per_step=1, ms=ms,
+        gw2, gb2 = torch.ones(D, device=dev, dtype=torch.bfloat16), torch.zeros(D, device=dev, dtype=torch.bfloat16)
+        ms = time_kernel(lambda: ops.gather_layernorm(x, kept, gw2, gb2, 1e-6), 50, torch)
+        by = B * (3 * e * D * (K + 1) + 8 * (K + 1))
+        rows.append(dict(kernel="gather_layernorm(kept-token gather + norm1)", shape=f"B={B},T={T_in},D={D},K={K}", launches_per_step=1, ms=ms,
                          algo_bytes=by, gbs=by / ms / 1e6))
         hid = torch.randn(B, n_in, D // 4, device=dev, dtype=torch.bfloat16)
         W = torch.randn(2, D // 4, device=dev) * 0.1
