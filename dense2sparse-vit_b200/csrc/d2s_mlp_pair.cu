@@ -7,12 +7,13 @@
 //
 // Separately, fc1 + GELU writes and fc2 re-reads the (B*T, 4D) hidden tensor: 1.24 GB per layer at B = 1024, T = 197, which
 // makes fc1 store-bound and is 60 % of the MLP's HBM traffic.  Here a CTA pair (tcgen05 cta_group::2, 256 rows) walks the
-// hidden dimension in chunks of 64 columns:
-//     G1(j): S_j (256 x 64)   = H (256 x 384, resident in shared memory)  x  W1[64 j .. 64 j + 63, :]^T        -> TMEM
+// hidden dimension in chunks of 128 columns:
+//     G1(j): S_j (256 x 128)  = H (256 x 384, resident in shared memory)  x  W1[128 j .. 128 j + 127, :]^T     -> TMEM
 //     E1(j): P_j = bf16(GELU(S_j + b1))  TMEM -> registers -> shared memory as the SWIZZLE_128B A operand of
-//     G2(j): ACC (256 x 384) += P_j (256 x 64)  x  W2[:, 64 j .. 64 j + 63]^T                                   -> TMEM
-// with S double-buffered in TMEM (384 + 2 x 64 = 512 columns) and P double-buffered in shared memory, so the tensor pipe runs
-// G1(j+2) and G2(j) while two groups of 8 epilogue warps compute E1(j) and E1(j+1).  W1 / W2 chunks stream from L2 through two TMA rings (each CTA
+//     G2(j): ACC (256 x 384) += P_j (256 x 128)  x  W2[:, 128 j .. 128 j + 127]^T                              -> TMEM
+// (384 + 128 = 512 TMEM columns).  A tcgen05.mma fetches its 128 x 16 A slice from shared memory in ~64 cycles whatever N is, so
+// N = 64 chunks ran G1 at half rate (measured: 64 cycles per MMA for 32 cycles of math); N = 128 is the break-even.  S and P are
+// single-buffered: S is free once E1 holds it in registers, so the tensor pipe runs G1(j+1) and then G2(j-1)... under E1(j).  W1 / W2 chunks stream from L2 through two TMA rings (each CTA
 // loads half of every weight tile).  After the last chunk a separate set of warps drains ACC: bias, round, residual add,
 // LayerNorm statistics, x' and hn, while the GEMM / activation warps are already on the next row tile.
 //
@@ -25,15 +26,14 @@
 
 namespace d2s {
 
-constexpr int kMpBM = 128, kMpD = 384, kMpCH = 64, kMpKB = kMpD / 64;
-constexpr int kMpW1Slots = 6, kMpW2Slots = 2;
+constexpr int kMpBM = 128, kMpD = 384, kMpCH = 128, kMpKB = kMpD / 64;
+constexpr int kMpW1Slots = 5, kMpW2Slots = 3;
 constexpr uint32_t kMpA1Blk = 128 * 128;        // 16 KB: 128 rows x 64 bf16 of H
-constexpr uint32_t kMpW1Blk = 32 * 128;         //  4 KB: this CTA's 32 of the 64 W1 rows of a chunk, one k-block
-constexpr uint32_t kMpW2Half = 96 * 128;        // 12 KB: this CTA's 96 of the 192 W2 rows of one N-half, 64 hidden columns
-constexpr uint32_t kMpW2Blk = 2 * kMpW2Half;    // 24 KB
-constexpr uint32_t kMpPBlk = 128 * 128;         // 16 KB: 128 rows x 64 bf16 of P_j
+constexpr uint32_t kMpW1Blk = 64 * 128;         //  8 KB: this CTA's 64 of the 128 W1 rows of a chunk, one k-block
+constexpr uint32_t kMpW2Blk = 96 * 128;         // 12 KB: this CTA's 96 of the 192 W2 rows of one N-half, 64 of the chunk's 128 hidden columns
+constexpr uint32_t kMpPBlk = 128 * 128;         // 16 KB: 128 rows x 64 bf16; P_j is two of them
 constexpr int kMpE1Warps = 8, kMpOutWarps = 4, kMpThreads = (4 + kMpE1Warps + kMpOutWarps) * 32;
-constexpr uint32_t kMpAccCols = 384, kMpSCols = 64;
+constexpr uint32_t kMpAccCols = 384, kMpSCols = 128;
 
 // clock64 totals of the issuing warps' waits (profiling builds only: -DD2S_GEMM_TRACE_BUILD, scripts/bench_mlp_trace.py)
 #ifdef D2S_GEMM_TRACE_BUILD
@@ -59,7 +59,7 @@ constexpr uint32_t kMpAccCols = 384, kMpSCols = 64;
 
 struct MpBars {
   uint64_t a1_full[kMpKB], a1_empty[kMpKB], w1_full[kMpW1Slots], w1_empty[kMpW1Slots], w2_full[kMpW2Slots], w2_empty[kMpW2Slots];
-  uint64_t s_full[2], s_empty[2], p_full[2], p_empty[2], acc_full, acc_empty;
+  uint64_t s_full, s_empty, p_full, p_empty, acc_full, acc_empty;
   uint32_t tmem_base, pad;
 };
 static_assert(sizeof(MpBars) % 8 == 0, "MpBars");
@@ -81,9 +81,9 @@ mlp_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   const uint32_t raw = smem_u32(smem_dyn);
   const uint32_t padb = (1024u - (raw & 1023u)) & 1023u;
   unsigned char* a1_s = smem_dyn + padb;                                  // 6 x 16 KB
-  unsigned char* p_s = a1_s + kMpKB * kMpA1Blk;                           // 2 x 16 KB (also the per-warp transposition buffers)
-  unsigned char* w1_s = p_s + 2 * kMpPBlk;                                // 6 x 4 KB
-  unsigned char* w2_s = w1_s + kMpW1Slots * kMpW1Blk;                     // 2 x 24 KB
+  unsigned char* p_s = a1_s + kMpKB * kMpA1Blk;                           // 2 x 16 KB: the two k-blocks of P_j
+  unsigned char* w1_s = p_s + 2 * kMpPBlk;                                // 5 x 8 KB
+  unsigned char* w2_s = w1_s + kMpW1Slots * kMpW1Blk;                     // 3 x 12 KB
   MpBars* bars = reinterpret_cast<MpBars*>(w2_s + kMpW2Slots * kMpW2Blk);
   float* b1_s = reinterpret_cast<float*>(bars + 1);                       // HID
   float* b2_s = b1_s + p.HID;                                             // 3 x 384: b2, gamma, beta
@@ -101,12 +101,10 @@ mlp_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     for (int i = 0; i < kMpKB; ++i) { mbar_init(smem_u32(&bars->a1_full[i]), 1); mbar_init(smem_u32(&bars->a1_empty[i]), 1); }
     for (int i = 0; i < kMpW1Slots; ++i) { mbar_init(smem_u32(&bars->w1_full[i]), 1); mbar_init(smem_u32(&bars->w1_empty[i]), 1); }
     for (int i = 0; i < kMpW2Slots; ++i) { mbar_init(smem_u32(&bars->w2_full[i]), 1); mbar_init(smem_u32(&bars->w2_empty[i]), 1); }
-    for (int i = 0; i < 2; ++i) {   // one E1 group (4 warps) per CTA arrives per chunk
-      mbar_init(smem_u32(&bars->s_full[i]), 1);
-      mbar_init(smem_u32(&bars->p_empty[i]), 1);
-      mbar_init(smem_u32(&bars->s_empty[i]), 2 * 4);
-      mbar_init(smem_u32(&bars->p_full[i]), 2 * 4);
-    }
+    mbar_init(smem_u32(&bars->s_full), 1);
+    mbar_init(smem_u32(&bars->p_empty), 1);
+    mbar_init(smem_u32(&bars->s_empty), 2 * kMpE1Warps);       // every E1 warp of both CTAs arrives per chunk
+    mbar_init(smem_u32(&bars->p_full), 2 * kMpE1Warps);
     mbar_init(smem_u32(&bars->acc_full), 1);
     mbar_init(smem_u32(&bars->acc_empty), 2 * kMpOutWarps);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -158,16 +156,15 @@ mlp_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       // ================================ TMA producer: W2 chunks (both CTAs) ================================
       uint32_t it = 0;
       for (int pt = pair; pt < pair_tiles; pt += num_pairs)
-        for (int j = 0; j < nch; ++j, ++it) {
-          const uint32_t s = it % kMpW2Slots, n = it / kMpW2Slots;
-          mbar_wait(smem_u32(&bars->w2_empty[s]), (n & 1) ^ 1);
-          const uint32_t fl = smem_u32(&bars->w2_full[s]);
-          if (rank == 0) mbar_expect_tx(fl, 2 * kMpW2Blk);
-          const uint32_t dst = smem_u32(w2_s + s * kMpW2Blk);
-#pragma unroll
-          for (int jn = 0; jn < 2; ++jn)
-            tma_load_2d_pair(dst + jn * kMpW2Half, &map_w2, j * kMpCH, jn * 192 + (int)rank * 96, mapa(fl, 0));
-        }
+        for (int j = 0; j < nch; ++j)
+          for (int q = 0; q < 4; ++q, ++it) {      // ring unit q = (k-block kb2 = q >> 1 of the chunk, N-half jn = q & 1)
+            const uint32_t s = it % kMpW2Slots, n = it / kMpW2Slots;
+            mbar_wait(smem_u32(&bars->w2_empty[s]), (n & 1) ^ 1);
+            const uint32_t fl = smem_u32(&bars->w2_full[s]);
+            if (rank == 0) mbar_expect_tx(fl, 2 * kMpW2Blk);
+            tma_load_2d_pair(smem_u32(w2_s + s * kMpW2Blk), &map_w2, j * kMpCH + (q >> 1) * 64, (q & 1) * 192 + (int)rank * 96,
+                             mapa(fl, 0));
+          }
     }
   } else if (warp_u == 1) {
     if (rank_u == 0) {
@@ -179,12 +176,11 @@ mlp_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       MP_TRACE_DECL
       for (int pt = pair; pt < pair_tiles; pt += num_pairs, ++tile_i)
         for (int j = 0; j < nch; ++j, ++c) {
-          const uint32_t sb = c & 1, use = c >> 1;
           MP_TRACE(0)
-          mbar_wait(smem_u32(&bars->s_empty[sb]), (use & 1) ^ 1);            // E1 two chunks ago has read this S buffer
+          mbar_wait(smem_u32(&bars->s_empty), (c & 1) ^ 1);                  // E1 of the previous chunk has S in registers
           tc_fence_after();
           MP_TRACE(1)
-          const uint32_t d = tmem + kMpAccCols + sb * kMpSCols;
+          const uint32_t d = tmem + kMpAccCols;
           for (int kb = 0; kb < kMpKB; ++kb, ++w1_it) {
             if (j == 0) mbar_wait(smem_u32(&bars->a1_full[kb]), tile_i & 1);
             MP_TRACE(2)
@@ -204,7 +200,7 @@ mlp_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             }
             __syncwarp();
           }
-          if (elect_one()) mma2_commit_both(smem_u32(&bars->s_full[sb]));
+          if (elect_one()) mma2_commit_both(smem_u32(&bars->s_full));
           __syncwarp();
         }
       MP_TRACE(0)
@@ -214,87 +210,85 @@ mlp_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     if (rank_u == 0) {
       // ====== G2 issuer (leader): ACC += P_c x W2_chunk^T ======
       const uint32_t idesc2 = make_idesc(2 * kMpBM, 192, 0);
-      uint32_t c = 0, tile_i = 0;
+      uint32_t c = 0, w2_it = 0, tile_i = 0;
       MP_TRACE_DECL
       for (int pt = pair; pt < pair_tiles; pt += num_pairs, ++tile_i)
         for (int j = 0; j < nch; ++j, ++c) {
-          const uint32_t pb = c & 1, use = c >> 1;
           MP_TRACE(0)
-          mbar_wait(smem_u32(&bars->p_full[pb]), use & 1);                     // both CTAs' epilogues have written P
+          mbar_wait(smem_u32(&bars->p_full), c & 1);                           // both CTAs' E1 warps have written P_c
           MP_TRACE(4)
-          const uint32_t s = c % kMpW2Slots, n = c / kMpW2Slots;
-          mbar_wait(smem_u32(&bars->w2_full[s]), n & 1);
-          MP_TRACE(5)
-          if (j == 0) mbar_wait(smem_u32(&bars->acc_empty), (tile_i & 1) ^ 1);   // previous tile's epilogue has drained ACC
+          if (j == 0) mbar_wait(smem_u32(&bars->acc_empty), (tile_i & 1) ^ 1);   // previous tile's output warps have drained ACC
           tc_fence_after();
           MP_TRACE(6)
-          const uint64_t ad = make_desc_sw128(smem_u32(p_s + pb * kMpPBlk), 16, 1024);
-          if (elect_one()) {
 #pragma unroll
-            for (int jn = 0; jn < 2; ++jn) {
-              const uint64_t bd = make_desc_sw128(smem_u32(w2_s + s * kMpW2Blk + jn * kMpW2Half), 16, 1024);
-              const uint32_t d = tmem + jn * 192;
-              if (j == 0) mma2_ss_imm<false>(d, ad, bd, idesc2); else mma2_ss_imm<true>(d, ad, bd, idesc2);
+          for (int q = 0; q < 4; ++q, ++w2_it) {     // (k-block kb2 = q >> 1 of P_c, N-half jn = q & 1)
+            const uint32_t s = w2_it % kMpW2Slots, n = w2_it / kMpW2Slots;
+            mbar_wait(smem_u32(&bars->w2_full[s]), n & 1);
+            tc_fence_after();
+            MP_TRACE(5)
+            const uint64_t ad = make_desc_sw128(smem_u32(p_s + (q >> 1) * kMpPBlk), 16, 1024);
+            const uint64_t bd = make_desc_sw128(smem_u32(w2_s + s * kMpW2Blk), 16, 1024);
+            const uint32_t d = tmem + (q & 1) * 192;
+            if (elect_one()) {
+              if (j == 0 && q < 2) mma2_ss_imm<false>(d, ad, bd, idesc2); else mma2_ss_imm<true>(d, ad, bd, idesc2);
               mma2_ss_imm<true>(d, ad + 2, bd + 2, idesc2);
               mma2_ss_imm<true>(d, ad + 4, bd + 4, idesc2);
               mma2_ss_imm<true>(d, ad + 6, bd + 6, idesc2);
+              mma2_commit_both(smem_u32(&bars->w2_empty[s]));
+              if (q == 3) {
+                mma2_commit_both(smem_u32(&bars->p_empty));
+                if (j == nch - 1) mma2_commit_both(smem_u32(&bars->acc_full));
+              }
             }
-            mma2_commit_both(smem_u32(&bars->w2_empty[s]));
-            mma2_commit_both(smem_u32(&bars->p_empty[pb]));
-            if (j == nch - 1) mma2_commit_both(smem_u32(&bars->acc_full));
+            __syncwarp();
           }
-          __syncwarp();
         }
       MP_TRACE(0)
       MP_TRACE_DUMP(1, c)
     }
   } else if (warp < 4 + kMpE1Warps) {
     // ============================== E1 warps (both CTAs): P_j = bf16(GELU(S_j + b1)) ==============================
-    // Two groups of 4 warps (one per TMEM lane quadrant, a thread takes all 64 columns of its row) handle the chunks
-    // alternately, each always on its own S / P buffer (chunk number mod 2): two chunks are in the activation stage at
-    // once, and a group sees every phase of the barriers it waits on.
+    // Two warps per TMEM lane quadrant, 64 of the chunk's 128 columns each (= one of the two k-blocks of P_j).  S and P are
+    // single-buffered: S is free again as soon as it sits in registers (G1 of the next chunk then runs under this chunk's
+    // GELU), P as soon as G2 of the previous chunk has retired (which the tensor pipe executes under this chunk's GELU too).
     const int ew = warp - 4;                    // 0..7
     const int quad = warp & 3;                  // TMEM lane quadrant of this warp
-    const uint32_t grp = (uint32_t)ew >> 2;
+    const int half = ew >> 2;                   // which 64 of the chunk's 128 columns
     const int r = quad * 32 + lane;
-    const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16);
-    uint32_t e_base = 0;
-    for (int pt = pair; pt < pair_tiles; pt += num_pairs) {
-      for (int j = (int)((grp + e_base) & 1u); j < nch; j += 2) {
-        const uint32_t c = e_base + (uint32_t)j;                 // global chunk number; c & 1 == grp
-        const uint32_t use = c >> 1;
-        mbar_wait(smem_u32(&bars->s_full[grp]), use & 1);
+    const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16) + kMpAccCols + half * 64;
+    unsigned char* blk = p_s + half * kMpPBlk;
+    uint32_t c = 0;
+    for (int pt = pair; pt < pair_tiles; pt += num_pairs)
+      for (int j = 0; j < nch; ++j, ++c) {
+        mbar_wait(smem_u32(&bars->s_full), c & 1);
         tc_fence_after();
         uint32_t o[32];
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
+        for (int h2 = 0; h2 < 2; ++h2) {
           uint32_t v[32];
-          tmem_ld32_nowait(lane_addr + kMpAccCols + grp * kMpSCols + half * 32, v);
+          tmem_ld32_nowait(lane_addr + h2 * 32, v);
           tmem_ld_wait();
-          if (half == 1) {                                       // S_j is in registers: G1(j + 2) may overwrite the buffer
+          if (h2 == 1) {                                         // S_j is in registers: G1(j + 1) may overwrite it
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(mapa(smem_u32(&bars->s_empty[grp]), 0));
+            if (lane == 0) mbar_arrive_cluster(mapa(smem_u32(&bars->s_empty), 0));
           }
 #pragma unroll
           for (int q = 0; q < 16; ++q) {
-            const float2 bq = *reinterpret_cast<const float2*>(&b1_s[j * kMpCH + half * 32 + 2 * q]);
+            const float2 bq = *reinterpret_cast<const float2*>(&b1_s[j * kMpCH + half * 64 + h2 * 32 + 2 * q]);
             float g0, g1;
             f2_unpack(gelu_erf_pair(f2_add(f2_pack(__uint_as_float(v[2 * q]), __uint_as_float(v[2 * q + 1])), f2_pack(bq.x, bq.y))), g0, g1);
-            o[half * 16 + q] = pack_bf16x2(g0, g1);
+            o[h2 * 16 + q] = pack_bf16x2(g0, g1);
           }
         }
-        mbar_wait(smem_u32(&bars->p_empty[grp]), (use & 1) ^ 1);                      // G2(j - 2) has read this P buffer
-        unsigned char* blk = p_s + grp * kMpPBlk;
+        mbar_wait(smem_u32(&bars->p_empty), (c & 1) ^ 1);                             // G2(j - 1) has read P
 #pragma unroll
         for (int k = 0; k < 8; ++k)
           *reinterpret_cast<uint4*>(blk + sw128_off(r, k)) = make_uint4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");                  // generic-proxy writes -> visible to the MMA
         __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(mapa(smem_u32(&bars->p_full[grp]), 0));
+        if (lane == 0) mbar_arrive_cluster(mapa(smem_u32(&bars->p_full), 0));
       }
-      e_base += (uint32_t)nch;
-    }
   } else {
     // ===================== output warps (both CTAs): x' = x + bf16(ACC + b2), hn = LayerNorm(x') =====================
     // Their own 4 warps (one per TMEM lane quadrant; a thread owns one row, all 384 columns), so a tile's residual add,
@@ -477,8 +471,8 @@ extern "C" int d2s_mlp_residual_ln_bf16(const void* h, const void* w1, const voi
                                         int T, int norm_row0, void* out_sum, void* out_norm, d2s_stream_t stream) {
   const char* what = "d2s_mlp_residual_ln_bf16";
   D2S_REQUIRE(h && w1 && w2 && x && out_sum, D2S_ERR_ARG, "mlp_residual_ln: null pointer");
-  D2S_REQUIRE(M >= 0 && D == kMpD && HID >= 3 * kMpCH && HID % kMpCH == 0 && HID <= 2048, D2S_ERR_ARG,
-              "mlp_residual_ln: need D == %d and HID %% %d == 0, %d <= HID <= 2048 (got M=%d D=%d HID=%d)", kMpD, kMpCH, 3 * kMpCH, M,
+  D2S_REQUIRE(M >= 0 && D == kMpD && HID >= kMpCH && HID % kMpCH == 0 && HID <= 2048, D2S_ERR_ARG,
+              "mlp_residual_ln: need D == %d and HID %% %d == 0, %d <= HID <= 2048 (got M=%d D=%d HID=%d)", kMpD, kMpCH, kMpCH, M,
               D, HID);
   D2S_REQUIRE(!out_norm || (gamma && beta), D2S_ERR_ARG, "mlp_residual_ln: out_norm needs gamma and beta");
   D2S_REQUIRE(T >= 1 && norm_row0 >= 0 && norm_row0 < T && (norm_row0 == 0 || M % T == 0), D2S_ERR_ARG,

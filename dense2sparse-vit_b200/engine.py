@@ -117,7 +117,7 @@ def _mlp_fused_ok(m, h, x):
     """The one-kernel MLP applies: bf16, D == 384 (whole rows in one CTA's TMEM next to the hidden chunks), 4D hidden."""
     return (_FUSED_MLP and _FUSED_PAIR and h.dtype == torch.bfloat16 and x.dtype == torch.bfloat16
             and m.fc1.weight.dtype == torch.bfloat16 and m.fc1.in_features == 384 and m.fc2.out_features == 384
-            and m.fc1.out_features % 64 == 0 and 192 <= m.fc1.out_features <= 2048 and h.shape == x.shape)
+            and m.fc1.out_features % 128 == 0 and 128 <= m.fc1.out_features <= 2048 and h.shape == x.shape)
 
 
 def _pair_ok(lin, a, x):

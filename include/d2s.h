@@ -216,11 +216,11 @@ int d2s_linear_residual_ln_bf16(const void* a, const void* w, const void* bias, 
 /* The whole MLP branch of Block.forward in one kernel (dynamic_vit.py:159-175, :263-283), bf16, D == 384:
  *   u = GELU(h (M,D) @ w1 (HID,D)^T + b1);  out_sum (M,D) = bf16(x + bf16(u @ w2 (D,HID)^T + b2));
  *   out_norm (M,D) = LayerNorm(out_sum) * gamma + beta, or skipped when out_norm is NULL.
- * The (M,HID) hidden activations never leave the SM (64-column chunks through TMEM and shared memory); roundings are the
+ * The (M,HID) hidden activations never leave the SM (128-column chunks through TMEM and shared memory); roundings are the
  * reference's (fc1 output after GELU, fc2 output, residual sum, LayerNorm output each rounded to bf16).
  * The M rows are B images of T tokens; out_norm skips the first norm_row0 tokens of every image and is (B, T-norm_row0, D)
  * (the predictors' LayerNorm over x[:, 1:], dynamic_vit.py:409, default_dynamic_vit.py:308); T = 1, norm_row0 = 0 for plain rows.
- * HID % 64 == 0, 192 <= HID <= 2048; x may alias out_sum. */
+ * HID % 128 == 0, 128 <= HID <= 2048; x may alias out_sum. */
 int d2s_mlp_residual_ln_bf16(const void* h, const void* w1, const void* b1, const void* w2, const void* b2, const void* x,
                              const void* gamma, const void* beta, float eps, int M, int D, int HID, int T, int norm_row0,
                              void* out_sum, void* out_norm, d2s_stream_t stream);
