@@ -257,3 +257,70 @@ def test_losses_keep_the_reference_defects(d2s, cuda_dev):
             [torch.zeros(40, dtype=torch.long).cuda()], torch.zeros(4, dtype=torch.long).cuda(), {})
     with pytest.raises(RuntimeError):     # host tensors: no CPU fallback for the select kernel
         d2s.losses.MaskLoss.get_mask_from_pred_logits(torch.rand(2, 196), 0.7)
+
+
+# ------------------------------------------------------------------------------------------ fused kernels at DeiT-S width
+def _deit_s_width_models(d2s, dev, variant, ratios):
+    """DeiT-S width (D = 384, 6 heads: the widths the CTA-pair GEMM / one-kernel MLP paths apply to), 4 blocks, 2 stages."""
+    kw = dict(patch_size=16, embed_dim=384, depth=4, num_heads=6, num_classes=16, mlp_ratio=4, qkv_bias=True)
+    if variant == "a":
+        m = d2s.variant_a.DefaultVisionTransformerDiffPruning(pruning_loc=[1, 2], token_ratio=ratios, distill=True, **kw)
+    else:
+        m = d2s.variant_b.VisionTransformerDiffPruning(pruning_loc=[1, 2], token_ratio=ratios, distill=True, topk_selection=True,
+                                                       predictor_loss_type="kl_div", **kw)
+    sd = fx.seeded_state_dict({k: tuple(v.shape) for k, v in m.state_dict().items()}, 31)
+    m.load_state_dict(sd)
+    return m.to(dev).eval(), sd
+
+
+@pytest.mark.parametrize("variant", ["a", "b"])
+def test_fused_block_kernels_at_deit_s_width(d2s, cuda_dev, variant, monkeypatch):
+    """The deferred-Linear residual stream (proj + add + LN, one-kernel MLP with the predictor norm over x[:, 1:], gather + norm1,
+    CLS-only last MLP) against (1) the same model with those paths switched off and (2) the fp32 CPU oracle.  Keep ratio 1.0:
+    every kernel runs (the gather becomes a permutation) but no token can flip at the cut, so logits must agree to bf16 accuracy."""
+    from oracle import model as om
+    x = fx.randn(32, 3, 3, 224, 224)
+    m, sd = _deit_s_width_models(d2s, cuda_dev, variant, [1.0, 1.0])
+    m16 = m.to(torch.bfloat16)
+    n0 = d2s._lib.launch_count()
+    with torch.no_grad():
+        out_fused = m16(x.to(cuda_dev, torch.bfloat16))
+    n_fused = d2s._lib.launch_count() - n0
+    monkeypatch.setattr(d2s.engine, "_FUSED_PAIR", False)
+    monkeypatch.setattr(d2s.engine, "_FUSED_MLP", False)
+    n0 = d2s._lib.launch_count()
+    with torch.no_grad():
+        out_plain = m16(x.to(cuda_dev, torch.bfloat16))
+    n_plain = d2s._lib.launch_count() - n0
+    lf = (out_fused[0] if isinstance(out_fused, tuple) else out_fused).float().cpu()
+    lp = (out_plain[0] if isinstance(out_plain, tuple) else out_plain).float().cpu()
+    assert n_fused < n_plain, (n_fused, n_plain)            # the fused path really ran (fewer, larger kernels)
+    cfg = om.VitCfg(embed_dim=384, depth=4, num_heads=6, num_classes=16, pruning_loc=[1, 2], token_ratio=[1.0, 1.0])
+    ref = om.variant_a_eval(sd, cfg, x)["logits"] if variant == "a" else om.variant_b_forward(sd, cfg, x)["logits"]
+    scale = float(ref.abs().max())
+    assert float((lf - lp).abs().max()) < 3e-2 * scale, "fused and unfused bf16 paths disagree"
+    assert float((lf - ref).abs().max()) < 3e-2 * scale, "fused bf16 path deviates from the fp32 oracle"
+
+
+def test_fused_path_keeps_the_reference_token_sets_when_margins_allow(d2s, cuda_dev):
+    """At keep ratio 0.7 the bf16 fused path must select the oracle's token sets wherever the fp32 score margin at the cut is
+    larger than bf16 noise (SURVEY hard part 1); images with a near-tie at the cut are excluded, not tolerated silently."""
+    from oracle import model as om
+    x = fx.randn(33, 6, 3, 224, 224)
+    m, sd = _deit_s_width_models(d2s, cuda_dev, "a", [0.7, 0.49])
+    cfg = om.VitCfg(embed_dim=384, depth=4, num_heads=6, num_classes=16, pruning_loc=[1, 2], token_ratio=[0.7, 0.49])
+    ref = om.variant_a_eval(sd, cfg, x)
+    with torch.no_grad():
+        m.to(torch.bfloat16)(x.to(cuda_dev, torch.bfloat16))
+    kept0 = m.kept_token_indices[0].cpu()
+    K = kept0.shape[1]
+    s32 = torch.sort(ref["scores"][0][:, :, 0], dim=-1, descending=True)[0]
+    margin = s32[:, K - 1] - s32[:, K]                       # fp32 gap between the last kept and the first dropped score
+    assert kept0.shape == ref["kept"][0].shape
+    for b in range(x.shape[0]):
+        mine, theirs = set(kept0[b].tolist()), set(ref["kept"][0][b].tolist())
+        # tokens whose fp32 score is within bf16 noise of the cut may change sides; everything else must agree
+        near = int(((ref["scores"][0][b, :, 0] - s32[b, K - 1]).abs() < 0.05).sum())
+        assert len(mine ^ theirs) <= 2 * near, (b, len(mine ^ theirs), near, float(margin[b]))
+        if float(margin[b]) > 0.05:
+            assert mine == theirs, (b, float(margin[b]))
