@@ -6,7 +6,7 @@
 //     1e-4 fp32 parity runs.  The bf16 production path is the tcgen05 kernel in d2s_attn_tc.cu.
 //
 //   P_ij = (exp(s_ij - max_j s_ij) * m_ij + eps/T) / (sum_j exp(.) * m_ij + eps),  m_ij = p_j + (1-p_j)[i==j]
-#include "d2s_common.cuh"
+#include "d2s_tc.cuh"
 
 namespace d2s {
 
@@ -102,139 +102,269 @@ __device__ __forceinline__ float exp_fast(float x) {
   return y;
 }
 
+// Padded-row kernels (rows of `ld` bf16, ld % 8 == 0, the (B*H, rows, ld) head-major score tensor of the training path).
+// A CTA owns kRowsPerCta consecutive rows = ONE contiguous block of the tensor, so the whole block is fetched by 1-D bulk
+// copies (TMA unit, no tensor map) issued up front by one thread: sub-blocks of one warp step (one or two rows per warp),
+// each with its own mbarrier.  Every byte the CTA will read is in flight from the first instruction on (register-staged row loads, even
+// with a one-row prefetch, left these kernels latency-bound at 1.2-2.3 TB/s); warps start on sub-block 0 while the rest
+// still streams in.  Results go straight to global memory (16 bytes per lane, whole rows per warp).
+struct RowBars { unsigned long long full[kRowsPerCta / kRowWarps]; };
+
+// issues the loads of this CTA's row block: `ntens` tensors (1: scores; 2: scores + upstream gradient) side by side in `stage`
+template <int kSubRows>
+__device__ __forceinline__ void row_block_issue(RowBars* bars, uint8_t* stage, const __nv_bfloat16* t0, const __nv_bfloat16* t1,
+                                                size_t block_elem0, int nrows, int ld) {
+  const uint32_t row_bytes = (uint32_t)ld * 2u;
+  for (int k = 0; k < kRowsPerCta / kSubRows; ++k) {
+    const int r0 = k * kSubRows;
+    if (r0 >= nrows) break;
+    const uint32_t bytes = (uint32_t)min(kSubRows, nrows - r0) * row_bytes;
+    const uint32_t bar = smem_u32(&bars->full[k]);
+    mbar_expect_tx(bar, t1 ? 2 * bytes : bytes);
+    bulk_load_1d(smem_u32(stage + (size_t)r0 * row_bytes), t0 + block_elem0 + (size_t)r0 * ld, bytes, bar);
+    if (t1)
+      bulk_load_1d(smem_u32(stage + (size_t)(kRowsPerCta + r0) * row_bytes), t1 + block_elem0 + (size_t)r0 * ld, bytes, bar);
+  }
+}
+
+// Arithmetic is kept to ~10 issue slots per element (the first versions spent ~22 and were ISSUE-bound at 2.4 TB/s whatever
+// the load path): the row max and the reference's bf16 `attn - max` are taken on packed bf16x2 words (max.bf16x2 /
+// sub.rn.bf16x2), columns >= T are forced to -inf / 0 by two per-lane constant bit masks instead of per-element predicates,
+// and the diagonal (m_ii = 1 whatever the policy) is not special-cased per element: rows are computed with m_ij = p_j
+// throughout and corrected with the one diagonal element, read as a shared-memory broadcast.
+// LPR lanes per row (32, or 16 for ld <= 128: two consecutive rows per warp); lane sl of a row owns columns 8*sl .. 8*sl+7.
+__device__ __forceinline__ uint32_t sub_bf16x2(uint32_t a, uint32_t b) {
+  uint32_t r;
+  asm("sub.rn.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+__device__ __forceinline__ uint32_t max_bf16x2(uint32_t a, uint32_t b) {
+  uint32_t r;
+  asm("max.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+__device__ __forceinline__ float ex2_fast(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+constexpr float kLog2e = 1.4426950408889634f;
+
+template <int LPR>
+struct RowMap {
+  static constexpr int kRPW = 32 / LPR;                       // rows per warp step
+  static constexpr int kSubRows = kRowWarps * kRPW;           // rows per sub-block (one barrier each)
+  static constexpr int kSubs = kRowsPerCta / kSubRows;
+};
+
+// per-lane constants: keep[w] selects the valid halves of packed word w (columns < T), ninf[w] holds bf16 -inf in the others
+__device__ __forceinline__ void lane_masks(int j0, int T, uint32_t (&keep)[4], uint32_t (&ninf)[4]) {
+#pragma unroll
+  for (int w = 0; w < 4; ++w) {
+    keep[w] = (j0 + 2 * w < T ? 0x0000ffffu : 0u) | (j0 + 2 * w + 1 < T ? 0xffff0000u : 0u);
+    ninf[w] = ~keep[w] & 0xff80ff80u;
+  }
+}
+
+template <int LPR>
 __global__ void __launch_bounds__(kRowThreads)
 softmax_policy_fwd_vec_kernel(const __nv_bfloat16* __restrict__ attn, const float* __restrict__ policy, int H, int T, int rows,
                               int ld, float eps, __nv_bfloat16* __restrict__ out, float* __restrict__ stats) {
+  using M = RowMap<LPR>;
+  extern __shared__ __align__(128) uint8_t row_stage[];
+  __shared__ RowBars bars;
+  __shared__ float pol_s[256];
   const int bh = blockIdx.y, b = bh / H;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int row_end = min(T, (int)(blockIdx.x + 1) * kRowsPerCta);
-  const int j0 = lane * 8;
+  const int row0 = blockIdx.x * kRowsPerCta;
+  const int row_end = min(T, row0 + kRowsPerCta);
+  const size_t block0 = ((size_t)bh * rows + row0) * ld;
+  if (threadIdx.x == 0) {
+    for (int k = 0; k < M::kSubs; ++k) mbar_init(smem_u32(&bars.full[k]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    row_block_issue<M::kSubRows>(&bars, row_stage, attn, nullptr, block0, row_end - row0, ld);
+  }
+  for (int j = threadIdx.x; j < 256; j += kRowThreads) pol_s[j] = j < T ? (policy ? policy[(size_t)b * T + j] : 1.0f) : 0.0f;
+  const int sl = lane % LPR, sub = lane / LPR;
+  const int j0 = sl * 8;
   const bool active = j0 < ld;
-  float pol[8];
-#pragma unroll
-  for (int k = 0; k < 8; ++k) pol[k] = (policy && j0 + k < T) ? policy[(size_t)b * T + j0 + k] : 1.0f;
+  uint32_t keep[4], ninf[4];
+  lane_masks(j0, T, keep, ninf);
   const float c = policy ? eps / (float)T : 0.0f;
   const float eps_den = policy ? eps : 0.0f;
-  // rows of one warp are 8 apart; the next row's vector is requested before the current row is processed (two loads in
-  // flight per lane: the kernel is latency-bound otherwise)
-  int4 nxt = make_int4(0, 0, 0, 0);
-  {
-    const int i = blockIdx.x * kRowsPerCta + warp;
-    if (active && i < row_end) nxt = ld_stream16(attn + ((size_t)bh * rows + i) * ld + j0);
-  }
-  for (int i = blockIdx.x * kRowsPerCta + warp; i < row_end; i += kRowWarps) {
-    const size_t base = ((size_t)bh * rows + i) * ld + j0;
-    float s[8];
-    const int4 cur = nxt;
-    if (active && i + kRowWarps < row_end) nxt = ld_stream16(attn + base + (size_t)kRowWarps * ld);
-    if (active) unpack8(cur, s);
-    float m = -INFINITY;
+  __syncthreads();   // barriers initialised, pol_s filled
+  float pol[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      if (!active || j0 + k >= T) s[k] = -INFINITY;
-      m = fmaxf(m, s[k]);
-    }
-    m = warp_max(m);
+  for (int q = 0; q < 8; ++q) pol[q] = active ? pol_s[j0 + q] : 0.f;
+  for (int k = 0; k < M::kSubs; ++k) {
+    const int lr = (k * kRowWarps + warp) * M::kRPW;   // first row of this warp step, block-relative
+    if (row0 + lr >= row_end) break;
+    const int li = lr + sub, i = row0 + li;
+    const bool rowok = i < row_end;
+    mbar_wait(smem_u32(&bars.full[k]), 0);
+    const uint8_t* srow = row_stage + (size_t)(rowok ? li : lr) * ld * 2;
+    int4 raw = make_int4(0, 0, 0, 0);
+    if (active) raw = *reinterpret_cast<const int4*>(srow + j0 * 2);
+    uint32_t w[4] = {(uint32_t)raw.x, (uint32_t)raw.y, (uint32_t)raw.z, (uint32_t)raw.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) w[q] = (w[q] & keep[q]) | ninf[q];
+    uint32_t m2 = max_bf16x2(max_bf16x2(w[0], w[1]), max_bf16x2(w[2], w[3]));
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) m2 = max_bf16x2(m2, __shfl_xor_sync(0xffffffffu, m2, o));
+    const float m = fmaxf(__uint_as_float(m2 << 16), __uint_as_float(m2 & 0xffff0000u));
+    const uint32_t mb = __float_as_uint(m) >> 16;   // m is a bf16 value
+    const uint32_t mm = mb | (mb << 16);
+    float a[8];
     float sum = 0.f;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      float a = 0.f;
-      if (active && j0 + k < T) a = exp_fast(sub_in_dtype(s[k], m, attn)) * ((j0 + k == i) ? 1.0f : pol[k]);
-      s[k] = a;
-      sum += a;
+    for (int q = 0; q < 4; ++q) {
+      const uint32_t d = sub_bf16x2(w[q], mm);
+      a[2 * q] = ex2_fast(__uint_as_float(d << 16) * kLog2e) * pol[2 * q];
+      a[2 * q + 1] = ex2_fast(__uint_as_float(d & 0xffff0000u) * kLog2e) * pol[2 * q + 1];
+      sum += a[2 * q] + a[2 * q + 1];
     }
-    sum = warp_sum(sum);
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    // diagonal: the reference's mask is 1 there
+    const int id = rowok ? i : row0 + lr;
+    const float sd = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(srow)[id]);
+    const float exd = ex2_fast(__bfloat162float(__float2bfloat16_rn(sd - m)) * kLog2e);
+    sum += exd * (1.0f - pol_s[id]);
     const float den = sum + eps_den;
     const float rden = 1.0f / den;
-    if (active) {
+    const float crden = c * rden;
+    if (active && rowok) {
+      uint32_t pk[4];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) s[k] = (j0 + k < T) ? (s[k] + c) * rden : 0.f;   // padding columns are written as zeros
-      *reinterpret_cast<uint4*>(out + base) = pack8(s);
-    }
-    if (stats && lane == 0) {
-      stats[((size_t)bh * T + i) * 2] = m;
-      stats[((size_t)bh * T + i) * 2 + 1] = den;
+      for (int q = 0; q < 4; ++q)   // padding columns are written as zeros
+        pk[q] = pack_bf16x2(fmaf(a[2 * q], rden, crden), fmaf(a[2 * q + 1], rden, crden)) & keep[q];
+      __nv_bfloat16* orow = out + block0 + (size_t)li * ld;
+      *reinterpret_cast<uint4*>(orow + j0) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      if (sl == (i >> 3)) orow[i] = __float2bfloat16_rn((exd + c) * rden);   // same thread as the vector store: ordered
+      if (stats && sl == 0) *reinterpret_cast<float2*>(stats + ((size_t)bh * T + i) * 2) = make_float2(m, den);
     }
   }
   // padding rows T..rows-1 of `out` (the padded tensor is a GEMM operand)
-  if (blockIdx.x == gridDim.x - 1 && active)
+  if (blockIdx.x == gridDim.x - 1 && lane * 8 < ld)
     for (int i = T + warp; i < rows; i += kRowWarps)
-      *reinterpret_cast<uint4*>(out + ((size_t)bh * rows + i) * ld + j0) = make_uint4(0, 0, 0, 0);
+      *reinterpret_cast<uint4*>(out + ((size_t)bh * rows + i) * ld + lane * 8) = make_uint4(0, 0, 0, 0);
 }
 
 // The gradient through the subtracted row max (dense kernel above: routed to the first argmax) is sum_j dS_ij = O(eps) * g,
 // i.e. 1e-6 relative: below bf16 resolution, so this bf16-only kernel leaves it out (and with it the argmax bookkeeping).
+template <int LPR>
 __global__ void __launch_bounds__(kRowThreads, 3)
 softmax_policy_bwd_vec_kernel(const __nv_bfloat16* __restrict__ attn, const float* __restrict__ policy,
                               const __nv_bfloat16* __restrict__ gout, const float* __restrict__ stats, int H, int T, int rows,
                               int ld, float eps, __nv_bfloat16* __restrict__ gattn, float* __restrict__ gpolicy) {
-  __shared__ float gp_s[kRowWarps][256];   // per-warp partial d policy (no shared-memory float atomics: those are CAS loops)
+  using M = RowMap<LPR>;
+  extern __shared__ __align__(128) uint8_t row_stage[];   // scores block, then gradient block
+  __shared__ RowBars bars;
+  __shared__ float pol_s[256];
+  __shared__ float gp_fix[kRowsPerCta];                   // d policy_i the row loop over-counts on the diagonal
+  __shared__ float gp_s[kRowWarps * M::kRPW][LPR * 8];    // per-(warp, row slot) partial d policy (no shared float atomics: CAS loops)
   const int bh = blockIdx.y, b = bh / H;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int row_end = min(T, (int)(blockIdx.x + 1) * kRowsPerCta);
-  const int j0 = lane * 8;
+  const int row0 = blockIdx.x * kRowsPerCta;
+  const int row_end = min(T, row0 + kRowsPerCta);
+  const size_t block0 = ((size_t)bh * rows + row0) * ld;
+  if (threadIdx.x == 0) {
+    for (int k = 0; k < M::kSubs; ++k) mbar_init(smem_u32(&bars.full[k]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    row_block_issue<M::kSubRows>(&bars, row_stage, attn, gout, block0, row_end - row0, ld);
+  }
+  for (int j = threadIdx.x; j < 256; j += kRowThreads) pol_s[j] = j < T ? (policy ? policy[(size_t)b * T + j] : 1.0f) : 0.0f;
+  if (threadIdx.x < kRowsPerCta) gp_fix[threadIdx.x] = 0.f;
+  const int sl = lane % LPR, sub = lane / LPR;
+  const int j0 = sl * 8;
   const bool active = j0 < ld;
+  const bool want_gp = gpolicy && policy;
+  uint32_t keep[4], ninf[4];
+  lane_masks(j0, T, keep, ninf);
+  const float c = policy ? eps / (float)T : 0.0f;
+  // (max, denominator) of this warp's rows: lane k*kRPW + s holds the pair of warp step k, row slot s
+  float2 st = make_float2(0.f, 1.f);
+  {
+    const int i = row0 + ((lane / M::kRPW) * kRowWarps + warp) * M::kRPW + lane % M::kRPW;
+    if (lane < M::kSubs * M::kRPW && i < row_end) st = *reinterpret_cast<const float2*>(stats + ((size_t)bh * T + i) * 2);
+  }
+  const uint8_t* g_stage = row_stage + (size_t)kRowsPerCta * ld * 2;
+  __syncthreads();   // barriers initialised, pol_s filled
   float pol[8], gp[8];
 #pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    pol[k] = (policy && j0 + k < T) ? policy[(size_t)b * T + j0 + k] : 1.0f;
-    gp[k] = 0.f;
+  for (int q = 0; q < 8; ++q) {
+    pol[q] = active ? pol_s[j0 + q] : 0.f;
+    gp[q] = 0.f;
   }
-  const float c = policy ? eps / (float)T : 0.0f;
-  int4 nS = make_int4(0, 0, 0, 0), nG = nS;
-  {
-    const int i = blockIdx.x * kRowsPerCta + warp;
-    if (active && i < row_end) {
-      nS = ld_stream16(attn + ((size_t)bh * rows + i) * ld + j0);
-      nG = ld_stream16(gout + ((size_t)bh * rows + i) * ld + j0);
-    }
-  }
-  for (int i = blockIdx.x * kRowsPerCta + warp; i < row_end; i += kRowWarps) {
-    const size_t base = ((size_t)bh * rows + i) * ld + j0;
-    const float m = stats[((size_t)bh * T + i) * 2];
-    const float rden = 1.0f / stats[((size_t)bh * T + i) * 2 + 1];
-    float sv[8], g[8], ex[8], a[8];
-    const int4 cS = nS, cG = nG;
-    if (active && i + kRowWarps < row_end) {     // next row of this warp: in flight while this one is processed
-      nS = ld_stream16(attn + base + (size_t)kRowWarps * ld);
-      nG = ld_stream16(gout + base + (size_t)kRowWarps * ld);
-    }
+  for (int k = 0; k < M::kSubs; ++k) {
+    const int lr = (k * kRowWarps + warp) * M::kRPW;
+    if (row0 + lr >= row_end) break;
+    const int li = lr + sub, i = row0 + li;
+    const bool rowok = i < row_end;
+    const float m = __shfl_sync(0xffffffffu, st.x, k * M::kRPW + sub);
+    const float den = __shfl_sync(0xffffffffu, st.y, k * M::kRPW + sub);
+    const float rden = rowok ? 1.0f / den : 0.0f;   // a missing second row (last warp step of a block) contributes nothing
+    mbar_wait(smem_u32(&bars.full[k]), 0);
+    const size_t roff = (size_t)(rowok ? li : lr) * ld * 2;
+    int4 sraw = make_int4(0, 0, 0, 0), graw = sraw;
     if (active) {
-      unpack8(cS, sv);
-      unpack8(cG, g);
+      sraw = *reinterpret_cast<const int4*>(row_stage + roff + j0 * 2);
+      graw = *reinterpret_cast<const int4*>(g_stage + roff + j0 * 2);
     }
-    float gdotp = 0.f;
+    const uint32_t sw[4] = {(uint32_t)sraw.x, (uint32_t)sraw.y, (uint32_t)sraw.z, (uint32_t)sraw.w};
+    const uint32_t gw[4] = {(uint32_t)graw.x, (uint32_t)graw.y, (uint32_t)graw.z, (uint32_t)graw.w};
+    const uint32_t mb = __float_as_uint(m) >> 16;   // the forward's row max is a bf16 value
+    const uint32_t mm = mb | (mb << 16);
+    float g[8], ex[8], a[8];
+    float part = 0.f, gsum = 0.f;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const int j = j0 + k;
-      ex[k] = a[k] = 0.f;
-      if (active && j < T) {
-        ex[k] = exp_fast(sub_in_dtype(sv[k], m, attn));
-        a[k] = ex[k] * ((j == i) ? 1.0f : pol[k]);
-        gdotp += g[k] * ((a[k] + c) * rden);
-      } else {
-        g[k] = 0.f;
-      }
+    for (int q = 0; q < 4; ++q) {
+      const uint32_t d = sub_bf16x2((sw[q] & keep[q]) | ninf[q], mm);
+      const uint32_t gq = gw[q] & keep[q];
+      ex[2 * q] = ex2_fast(__uint_as_float(d << 16) * kLog2e);
+      ex[2 * q + 1] = ex2_fast(__uint_as_float(d & 0xffff0000u) * kLog2e);
+      g[2 * q] = __uint_as_float(gq << 16);
+      g[2 * q + 1] = __uint_as_float(gq & 0xffff0000u);
+      a[2 * q] = ex[2 * q] * pol[2 * q];
+      a[2 * q + 1] = ex[2 * q + 1] * pol[2 * q + 1];
+      part = fmaf(g[2 * q], a[2 * q], part);
+      part = fmaf(g[2 * q + 1], a[2 * q + 1], part);
+      gsum += g[2 * q] + g[2 * q + 1];
     }
-    gdotp = warp_sum(gdotp);
+    part = fmaf(c, gsum, part);
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    // diagonal element (mask 1 in the reference, p_i in the sums above)
+    const int id = rowok ? i : row0 + lr;
+    const float sd = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(row_stage + roff)[id]);
+    const float gd = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(g_stage + roff)[id]);
+    const float exd = ex2_fast(__bfloat162float(__float2bfloat16_rn(sd - m)) * kLog2e);
+    const float gdr = (part + gd * exd * (1.0f - pol_s[id])) * rden * rden;   // (g . P) / den
     float ds[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const int j = j0 + k;
-      const float da = (g[k] - gdotp) * rden;
-      ds[k] = da * a[k];                          // a == 0 outside the row
-      if (active && j < T && j != i) gp[k] += da * ex[k];
+    for (int q = 0; q < 8; ++q) {
+      const float da = fmaf(g[q], rden, -gdr);
+      ds[q] = da * a[q];                          // a == 0 outside the row
+      gp[q] = fmaf(da, ex[q], gp[q]);             // includes the diagonal: taken out again through gp_fix
     }
-    if (active) *reinterpret_cast<uint4*>(gattn + base) = pack8(ds);
+    if (active && rowok) {
+      __nv_bfloat16* drow = gattn + block0 + (size_t)li * ld;
+      *reinterpret_cast<uint4*>(drow + j0) = pack8(ds);
+      const float dsd = fmaf(gd, rden, -gdr) * exd;
+      if (sl == (i >> 3)) drow[i] = __float2bfloat16_rn(dsd);   // same thread as the vector store: ordered
+      if (sl == 0) gp_fix[li] = dsd;
+    }
   }
-  if (gpolicy && policy) {
-    *reinterpret_cast<float4*>(&gp_s[warp][j0]) = make_float4(gp[0], gp[1], gp[2], gp[3]);
-    *reinterpret_cast<float4*>(&gp_s[warp][j0 + 4]) = make_float4(gp[4], gp[5], gp[6], gp[7]);
+  if (want_gp) {
+    float* mine = gp_s[warp * M::kRPW + sub];
+    *reinterpret_cast<float4*>(mine + j0) = make_float4(gp[0], gp[1], gp[2], gp[3]);
+    *reinterpret_cast<float4*>(mine + j0 + 4) = make_float4(gp[4], gp[5], gp[6], gp[7]);
     __syncthreads();
     for (int j = threadIdx.x; j < T; j += kRowThreads) {
       float acc = 0.f;
 #pragma unroll
-      for (int w = 0; w < kRowWarps; ++w) acc += gp_s[w][j];
+      for (int w = 0; w < kRowWarps * M::kRPW; ++w) acc += gp_s[w][j];
+      if (j >= row0 && j < row_end) acc -= gp_fix[j - row0];
       atomicAdd(&gpolicy[(size_t)b * T + j], acc);
     }
   }
@@ -538,8 +668,13 @@ extern "C" int d2s_softmax_policy_fwd_ld(const void* attn, const float* policy, 
   D2S_REQUIRE(aligned16(attn) && aligned16(out), D2S_ERR_ALIGN, "softmax_policy_fwd_ld: pointers must be 16-byte aligned");
   if (B == 0) return D2S_OK;
   dim3 grid(ceil_div(T, kRowsPerCta), B * H);
-  softmax_policy_fwd_vec_kernel<<<grid, kRowThreads, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)attn, policy, H, T, rows, ld,
-                                                                                 eps, (__nv_bfloat16*)out, stats);
+  const size_t smem = (size_t)kRowsPerCta * ld * 2;
+  if (ld <= 128)
+    softmax_policy_fwd_vec_kernel<16><<<grid, kRowThreads, smem, (cudaStream_t)stream>>>((const __nv_bfloat16*)attn, policy, H, T,
+                                                                                        rows, ld, eps, (__nv_bfloat16*)out, stats);
+  else
+    softmax_policy_fwd_vec_kernel<32><<<grid, kRowThreads, smem, (cudaStream_t)stream>>>((const __nv_bfloat16*)attn, policy, H, T,
+                                                                                        rows, ld, eps, (__nv_bfloat16*)out, stats);
   count_launch();
   return check_launch("d2s_softmax_policy_fwd_ld");
 }
@@ -555,8 +690,19 @@ extern "C" int d2s_softmax_policy_bwd_ld(const void* attn, const float* policy, 
               "softmax_policy_bwd_ld: pointers must be 16-byte aligned");
   if (B == 0) return D2S_OK;
   dim3 grid(ceil_div(T, kRowsPerCta), B * H);
-  softmax_policy_bwd_vec_kernel<<<grid, kRowThreads, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)attn, policy, (const __nv_bfloat16*)gout, stats, H, T, rows, ld, eps, (__nv_bfloat16*)gattn, gpolicy);
+  const size_t smem = (size_t)2 * kRowsPerCta * ld * 2;   // scores block + gradient block (<= 64 KB at ld = 256)
+  static bool smem_set = false;
+  if (!smem_set) {
+    cudaError_t e = cudaFuncSetAttribute(softmax_policy_bwd_vec_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    D2S_REQUIRE(e == cudaSuccess, D2S_ERR_CUDA, "softmax_policy_bwd_ld: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    smem_set = true;
+  }
+  if (ld <= 128)
+    softmax_policy_bwd_vec_kernel<16><<<grid, kRowThreads, smem, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)attn, policy, (const __nv_bfloat16*)gout, stats, H, T, rows, ld, eps, (__nv_bfloat16*)gattn, gpolicy);
+  else
+    softmax_policy_bwd_vec_kernel<32><<<grid, kRowThreads, smem, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)attn, policy, (const __nv_bfloat16*)gout, stats, H, T, rows, ld, eps, (__nv_bfloat16*)gattn, gpolicy);
   count_launch();
   return check_launch("d2s_softmax_policy_bwd_ld");
 }

@@ -27,7 +27,13 @@
 namespace d2s {
 
 constexpr int kMpBM = 128, kMpD = 384, kMpCH = 128, kMpKB = kMpD / 64;
-constexpr int kMpW1Slots = 5, kMpW2Slots = 3;
+#ifndef MP_W1
+#define MP_W1 5
+#endif
+#ifndef MP_W2
+#define MP_W2 3
+#endif
+constexpr int kMpW1Slots = MP_W1, kMpW2Slots = MP_W2;
 constexpr uint32_t kMpA1Blk = 128 * 128;        // 16 KB: 128 rows x 64 bf16 of H
 constexpr uint32_t kMpW1Blk = 64 * 128;         //  8 KB: this CTA's 64 of the 128 W1 rows of a chunk, one k-block
 constexpr uint32_t kMpW2Blk = 96 * 128;         // 12 KB: this CTA's 96 of the 192 W2 rows of one N-half, 64 of the chunk's 128 hidden columns
@@ -86,9 +92,10 @@ mlp_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   unsigned char* w2_s = w1_s + kMpW1Slots * kMpW1Blk;                     // 3 x 12 KB
   MpBars* bars = reinterpret_cast<MpBars*>(w2_s + kMpW2Slots * kMpW2Blk);
   float* b1_s = reinterpret_cast<float*>(bars + 1);                       // HID
-  float* b2_s = b1_s + p.HID;                                             // 3 x 384: b2, gamma, beta
+  float* b2_s = b1_s + p.HID;                                             // 384: b2
+  uint32_t* gb_s = reinterpret_cast<uint32_t*>(b2_s + TN);                // 384: (gamma, beta) as bf16 pairs
   unsigned char* out_s = reinterpret_cast<unsigned char*>(                  // 4 x 2 KB transposition buffers of the output warps
-      (reinterpret_cast<uintptr_t>(b2_s + 3 * TN) + 15) & ~(uintptr_t)15);
+      (reinterpret_cast<uintptr_t>(gb_s + TN) + 15) & ~(uintptr_t)15);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t rank = cluster_ctarank();
@@ -116,8 +123,8 @@ mlp_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   for (int i = tid; i < p.HID; i += kMpThreads) b1_s[i] = p.b1 ? __bfloat162float(p.b1[i]) : 0.f;
   for (int i = tid; i < TN; i += kMpThreads) {
     b2_s[i] = p.b2 ? __bfloat162float(p.b2[i]) : 0.f;
-    b2_s[TN + i] = p.gamma ? __bfloat162float(p.gamma[i]) : 1.f;
-    b2_s[2 * TN + i] = p.beta ? __bfloat162float(p.beta[i]) : 0.f;
+    const __nv_bfloat16 gm = p.gamma ? p.gamma[i] : __float2bfloat16_rn(1.f), bt = p.beta ? p.beta[i] : __float2bfloat16_rn(0.f);
+    gb_s[i] = (uint32_t)__bfloat16_as_ushort(gm) | ((uint32_t)__bfloat16_as_ushort(bt) << 16);
   }
   tc_fence_before();
   __syncthreads();
@@ -262,24 +269,29 @@ mlp_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       for (int j = 0; j < nch; ++j, ++c) {
         mbar_wait(smem_u32(&bars->s_full), c & 1);
         tc_fence_after();
+        // all 64 columns first: S_j is then in registers and G1(j + 1) may overwrite it while the GELU below runs (with the
+        // second half loaded after the first half's GELU, s_empty went out ~1 k cycles later and G1 waited for it)
+        uint32_t va[32], vb[32];
+        tmem_ld32_nowait(lane_addr, va);
+        tmem_ld32_nowait(lane_addr + 32, vb);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(mapa(smem_u32(&bars->s_empty), 0));
         uint32_t o[32];
 #pragma unroll
-        for (int h2 = 0; h2 < 2; ++h2) {
-          uint32_t v[32];
-          tmem_ld32_nowait(lane_addr + h2 * 32, v);
-          tmem_ld_wait();
-          if (h2 == 1) {                                         // S_j is in registers: G1(j + 1) may overwrite it
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(mapa(smem_u32(&bars->s_empty), 0));
-          }
+        for (int q = 0; q < 16; ++q) {
+          const float2 bq = *reinterpret_cast<const float2*>(&b1_s[j * kMpCH + half * 64 + 2 * q]);
+          float g0, g1;
+          f2_unpack(gelu_erf_pair(f2_add(f2_pack(__uint_as_float(va[2 * q]), __uint_as_float(va[2 * q + 1])), f2_pack(bq.x, bq.y))), g0, g1);
+          o[q] = pack_bf16x2(g0, g1);
+        }
 #pragma unroll
-          for (int q = 0; q < 16; ++q) {
-            const float2 bq = *reinterpret_cast<const float2*>(&b1_s[j * kMpCH + half * 64 + h2 * 32 + 2 * q]);
-            float g0, g1;
-            f2_unpack(gelu_erf_pair(f2_add(f2_pack(__uint_as_float(v[2 * q]), __uint_as_float(v[2 * q + 1])), f2_pack(bq.x, bq.y))), g0, g1);
-            o[h2 * 16 + q] = pack_bf16x2(g0, g1);
-          }
+        for (int q = 0; q < 16; ++q) {
+          const float2 bq = *reinterpret_cast<const float2*>(&b1_s[j * kMpCH + half * 64 + 32 + 2 * q]);
+          float g0, g1;
+          f2_unpack(gelu_erf_pair(f2_add(f2_pack(__uint_as_float(vb[2 * q]), __uint_as_float(vb[2 * q + 1])), f2_pack(bq.x, bq.y))), g0, g1);
+          o[16 + q] = pack_bf16x2(g0, g1);
         }
         mbar_wait(smem_u32(&bars->p_empty), (c & 1) ^ 1);                             // G2(j - 1) has read P
 #pragma unroll
@@ -299,8 +311,6 @@ mlp_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     const int quad = warp & 3;
     const int ow = warp - 4 - kMpE1Warps;       // 0..3
     const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16);
-    const float* gamma_s = b2_s + TN;
-    const float* beta_s = b2_s + 2 * TN;
     unsigned char* buf = out_s + ow * 2048;                     // [32 rows x 64 B]
     const int crow = lane >> 2, cseg = lane & 3;                // coalesced pattern: 4 lanes x 16 B cover one row's 64 bytes
     const uint32_t own_off = (uint32_t)lane * 64, own_sw = (uint32_t)(lane >> 1) & 3u;
@@ -417,10 +427,10 @@ mlp_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
           }
 #pragma unroll
           for (int q = 0; q < 16; ++q) {
-            const float2 g = *reinterpret_cast<const float2*>(&gamma_s[u * 32 + 2 * q]);
-            const float2 bt = *reinterpret_cast<const float2*>(&beta_s[u * 32 + 2 * q]);
+            const uint2 gb = *reinterpret_cast<const uint2*>(&gb_s[u * 32 + 2 * q]);     // (gamma, beta) of two columns
             float h0, h1;
-            f2_unpack(f2_fma(f2_fma(f2_pack(bf16_lo(hw[q]), bf16_hi(hw[q])), sc, sh), f2_pack(g.x, g.y), f2_pack(bt.x, bt.y)), h0, h1);
+            f2_unpack(f2_fma(f2_fma(f2_pack(bf16_lo(hw[q]), bf16_hi(hw[q])), sc, sh), f2_pack(bf16_lo(gb.x), bf16_lo(gb.y)),
+                             f2_pack(bf16_hi(gb.x), bf16_hi(gb.y))), h0, h1);
             hw[q] = pack_bf16x2(h0, h1);
           }
           __syncwarp();
@@ -489,7 +499,7 @@ extern "C" int d2s_mlp_residual_ln_bf16(const void* h, const void* w1, const voi
   MpParams p{tr_env ? reinterpret_cast<long long*>(strtoull(tr_env, nullptr, 10)) : nullptr, (const __nv_bfloat16*)b1, (const __nv_bfloat16*)b2, (const __nv_bfloat16*)gamma, (const __nv_bfloat16*)beta,
              (const __nv_bfloat16*)x, (__nv_bfloat16*)out_sum, (__nv_bfloat16*)out_norm, eps, M, HID, out_norm ? 1 : 0, T, norm_row0};
   const size_t smem = 1024 + (size_t)kMpKB * kMpA1Blk + 2 * (size_t)kMpPBlk + (size_t)kMpW1Slots * kMpW1Blk +
-                      (size_t)kMpW2Slots * kMpW2Blk + sizeof(MpBars) + (size_t)HID * 4 + 3 * kMpD * 4 + (size_t)kMpOutWarps * 2048 + 32;
+                      (size_t)kMpW2Slots * kMpW2Blk + sizeof(MpBars) + (size_t)HID * 4 + 2 * kMpD * 4 + (size_t)kMpOutWarps * 2048 + 32;
   D2S_REQUIRE(smem <= 227 * 1024, D2S_ERR_ARG, "mlp_residual_ln: needs %zu B of shared memory", smem);
   static bool attr_set = false;
   if (!attr_set) {

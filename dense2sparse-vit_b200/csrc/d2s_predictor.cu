@@ -10,7 +10,7 @@
 //                     so the concat (default_dynamic_vit.py:329) is never materialised.
 //
 // Both are HBM-bound: pool_act reads e*N*C and writes e*N*C/2 per image, bias_act reads and writes e*N*C' once.
-#include "d2s_common.cuh"
+#include "d2s_tc.cuh"
 
 namespace d2s {
 
@@ -96,12 +96,21 @@ pool_act_kernel(const T_* __restrict__ z, const float* __restrict__ policy, int 
   for (int q = 0; q < 8; ++q) acc[q] = 0.f;
   float psum = 0.f;
   if (g < groups) {
-    for (int n = g; n < N; n += groups) {
+    // bf16 GELU here goes through the packed fp32x2 erfcx polynomial of the GEMM epilogues (d2s_tc.cuh gelu_erf_pair, <= 0.07
+    // bf16 ulp, one MUFU and ~10 issue slots per element): with the rcp-based erf this kernel was bound by the FP32 pipe.
+    auto token = [&](int n, const int4& raw) {
       const size_t row = (size_t)b * N + n;
       float x[8];
-      PVec<T_>::unpack(ld_stream16(z + row * C + (size_t)v * VE), x);
+      PVec<T_>::unpack(raw, x);
+      if (ActFast<T_>::value && act == D2S_ACT_GELU) {
 #pragma unroll
-      for (int q = 0; q < VE; ++q) x[q] = PVec<T_>::round(act_apply<ActFast<T_>::value>(x[q], act));
+        for (int q = 0; q < VE; q += 2) f2_unpack(gelu_erf_pair(f2_pack(x[q], x[q + 1])), x[q], x[q + 1]);
+      } else {
+#pragma unroll
+        for (int q = 0; q < VE; ++q) x[q] = act_apply<false>(x[q], act);
+      }
+#pragma unroll
+      for (int q = 0; q < VE; ++q) x[q] = PVec<T_>::round(x[q]);
       if (v < half_vec) {
         *reinterpret_cast<int4*>(local + row * half + (size_t)v * VE) = PVec<T_>::pack(x);
       } else {
@@ -110,7 +119,17 @@ pool_act_kernel(const T_* __restrict__ z, const float* __restrict__ policy, int 
         for (int q = 0; q < VE; ++q) acc[q] = fmaf(x[q], p, acc[q]);
         if (v == half_vec) psum += p;
       }
+    };
+    const T_* zb = z + (size_t)b * N * C + (size_t)v * VE;
+    int n = g;
+    for (; n + 3 * groups < N; n += 4 * groups) {      // four token rows in flight per thread
+      const int4 r0 = ld_stream16(zb + (size_t)n * C);
+      const int4 r1 = ld_stream16(zb + (size_t)(n + groups) * C);
+      const int4 r2 = ld_stream16(zb + (size_t)(n + 2 * groups) * C);
+      const int4 r3 = ld_stream16(zb + (size_t)(n + 3 * groups) * C);
+      token(n, r0); token(n + groups, r1); token(n + 2 * groups, r2); token(n + 3 * groups, r3);
     }
+    for (; n < N; n += groups) token(n, ld_stream16(zb + (size_t)n * C));
   }
   float* pol_red = red + (size_t)groups * half;
   if (g < groups && v >= half_vec) {
@@ -169,29 +188,46 @@ pool_concat_inplace_kernel(T_* __restrict__ z, int N, int C) {
 }
 
 // u (rows, C) += bias (per image: bias[(row / N) * C + c]; N == 0 => one shared row; NULL => none), then act, in place.
-// grid.x covers the 16-byte vectors of a row, grid.y strides the rows: no 64-bit divisions in the loop.
+// One CTA per block of kBiasRows rows, its 16-byte vectors dealt flat to the threads (every lane busy whatever C is), two
+// vectors in flight per thread; the one 64-bit division (first image of the block) is done once per CTA.
+constexpr int kBiasRows = 64;
 template <typename T_>
 __global__ void __launch_bounds__(256)
 bias_act_kernel(T_* __restrict__ u, const T_* __restrict__ bias, long long rows, int N, int C, int act) {
   constexpr int VE = PVec<T_>::kElems;
   const int nvec = C / VE;
-  const int v = blockIdx.x * 32 + (threadIdx.x & 31);
-  if (v >= nvec) return;
-  float bshared[8];
-  if (bias && N == 0) PVec<T_>::unpack(*reinterpret_cast<const int4*>(bias + (size_t)v * VE), bshared);
-  for (long long row = (long long)blockIdx.y * 8 + (threadIdx.x >> 5); row < rows; row += (long long)gridDim.y * 8) {
-    T_* p = u + row * C + (size_t)v * VE;
+  const long long row0 = (long long)blockIdx.x * kBiasRows;
+  const int nrows = (int)min((long long)kBiasRows, rows - row0);
+  const int items = nrows * nvec;
+  const long long img0 = N > 0 ? row0 / N : 0;
+  const int rem0 = N > 0 ? (int)(row0 - img0 * N) : 0;
+  T_* base = u + row0 * C;
+  auto bias_of = [&](int i, float (&bv)[8]) {
+    const int r = i / nvec, v = i - r * nvec;
+    const long long img = N > 0 ? img0 + (rem0 + r) / N : 0;
+    PVec<T_>::unpack(*reinterpret_cast<const int4*>(bias + img * C + (size_t)v * VE), bv);
+  };
+  auto finish = [&](int i, const int4& raw) {
     float x[8];
-    PVec<T_>::unpack(*reinterpret_cast<const int4*>(p), x);
+    PVec<T_>::unpack(raw, x);
     if (bias) {
-      if (N > 0) PVec<T_>::unpack(*reinterpret_cast<const int4*>(bias + (row / N) * C + (size_t)v * VE), bshared);
+      float bv[8];
+      bias_of(i, bv);
 #pragma unroll
-      for (int q = 0; q < VE; ++q) x[q] = PVec<T_>::round(x[q] + bshared[q]);
+      for (int q = 0; q < VE; ++q) x[q] = PVec<T_>::round(x[q] + bv[q]);
     }
 #pragma unroll
     for (int q = 0; q < VE; ++q) x[q] = act_apply<ActFast<T_>::value>(x[q], act);
-    *reinterpret_cast<int4*>(p) = PVec<T_>::pack(x);
+    reinterpret_cast<int4*>(base)[i] = PVec<T_>::pack(x);
+  };
+  int i = threadIdx.x;
+  for (; i + 256 < items; i += 512) {
+    const int4 r0 = reinterpret_cast<const int4*>(base)[i];
+    const int4 r1 = reinterpret_cast<const int4*>(base)[i + 256];
+    finish(i, r0);
+    finish(i + 256, r1);
   }
+  if (i < items) finish(i, reinterpret_cast<const int4*>(base)[i]);
 }
 
 // flat variant for bias == NULL: the tensor is one long vector array
@@ -277,11 +313,9 @@ extern "C" int d2s_bias_act(void* u, const void* bias, int dtype, long long rows
     if (dtype == D2S_BF16) act_flat_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, st>>>((__nv_bfloat16*)u, total, act);
     else                   act_flat_kernel<float><<<(unsigned)blocks, 256, 0, st>>>((float*)u, total, act);
   } else {
-    const int gx = ceil_div(C / ve, 32);
-    long long gy = (rows + 7) / 8;
-    const long long cap = (16LL * kNumSMs + gx - 1) / gx;
-    if (gy > cap) gy = cap;
-    dim3 grid(gx, (unsigned)gy);
+    const long long nblk = (rows + kBiasRows - 1) / kBiasRows;
+    D2S_REQUIRE(nblk <= 0x7fffffffLL, D2S_ERR_ARG, "bias_act: too many rows %lld", rows);
+    const unsigned grid = (unsigned)nblk;
     if (dtype == D2S_BF16)
       bias_act_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((__nv_bfloat16*)u, (const __nv_bfloat16*)bias, rows, N, C, act);
     else

@@ -31,6 +31,13 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "LAB_DONE:\n\t"
       "}\n" ::"r"(bar), "r"(parity) : "memory");
 }
+// 1-D bulk copy global -> shared::cta through the TMA unit (no tensor map): `bytes` and both addresses are multiples of 16;
+// completion is counted in bytes on `bar`.
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(bar)
+               : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 

@@ -260,6 +260,56 @@ def test_softmax_with_policy_sizes(ops, dtype, T):
         torch.testing.assert_close(pg.grad.cpu(), p2.grad, rtol=1e-4, atol=1e-5)
 
 
+@pytest.mark.parametrize("T", [197, 138, 97, 68, 64, 9])
+@pytest.mark.parametrize("polkind", ["hard", "frac", "none"])
+def test_softmax_policy_padded_rows_fwd_bwd(d2s, ops, T, polkind):
+    """d2s_softmax_policy_fwd_ld / bwd_ld (bf16, rows padded to a multiple of 8: the training attention's score tensor) against
+    the oracle's autograd on the same bf16 scores: probabilities, zeroed padding, d scores, d policy."""
+    lib = d2s._lib
+    B, H = 3, 2
+    Tp = (T + 7) // 8 * 8
+    s = (fx.randn(700 + T, B, H, T, T) * 2).bfloat16()
+    pol = None
+    if polkind == "hard":
+        pol = (torch.rand(B, T, generator=fx.gen(701 + T)) > 0.3).float()
+    elif polkind == "frac":
+        pol = torch.rand(B, T, generator=fx.gen(702 + T))
+    if pol is not None:
+        pol[:, 0] = 1
+    up = (fx.randn(703 + T, B, H, T, T) * 0.5).bfloat16()
+    S = torch.full((B * H, Tp, Tp), 7.0, dtype=torch.bfloat16)      # padding holds junk the kernels must ignore
+    G = torch.full((B * H, Tp, Tp), -3.0, dtype=torch.bfloat16)
+    S[:, :T, :T] = s.view(B * H, T, T)
+    G[:, :T, :T] = up.view(B * H, T, T)
+    S, G = cu(S), cu(G)
+    P = torch.full_like(S, 5.0)
+    dS = torch.zeros_like(S)
+    stats = torch.empty(B, H, T, 2, device="cuda")
+    gpol = torch.zeros(B, T, device="cuda")
+    pol_d = None if pol is None else cu(pol)
+    st = torch.cuda.current_stream().cuda_stream
+    lib.call("d2s_softmax_policy_fwd_ld", S.data_ptr(), None if pol is None else pol_d.data_ptr(), B, H, T, Tp, Tp, 1e-6,
+             P.data_ptr(), stats.data_ptr(), st)
+    lib.call("d2s_softmax_policy_bwd_ld", S.data_ptr(), None if pol is None else pol_d.data_ptr(), G.data_ptr(), stats.data_ptr(),
+             B, H, T, Tp, Tp, 1e-6, dS.data_ptr(), None if pol is None else gpol.data_ptr(), st)
+    s2 = s.clone().requires_grad_(True)
+    p2 = None if pol is None else pol.view(B, T, 1).clone().requires_grad_(True)
+    ref = oo.softmax_with_policy(s2, p2) if pol is not None else torch.softmax(s2.float(), -1)
+    (ref.float() * up.float()).sum().backward()
+    Pc = P.cpu().float()
+    # (the kernel subtracts the row max in bf16 like the reference's bf16 path; the oracle subtracts in fp32: same tolerance as
+    # test_softmax_with_policy_sizes)
+    torch.testing.assert_close(Pc[:, :T, :T].reshape(B, H, T, T), ref.detach().float(), rtol=2e-2, atol=1e-3)
+    assert float(Pc[:, T:, :].abs().max()) == 0 if Tp > T else True       # padding rows and columns are zero
+    assert float(Pc[:, :, T:].abs().max()) == 0 if Tp > T else True
+    g1 = dS.cpu().float()[:, :T, :T].reshape(B, H, T, T)
+    g2 = s2.grad.float()
+    assert float((g1 - g2).abs().max()) <= 1.5e-2 * float(g2.abs().max()) + 1e-4
+    if pol is not None:
+        gp2 = p2.grad.view(B, T)
+        assert float((gpol.cpu() - gp2).abs().max()) <= 1.5e-2 * float(gp2.abs().max()) + 1e-3
+
+
 # ------------------------------------------------------------------------------------------ fused attention
 def _qkv(seed, B, T, H, hd, scale=1.0):
     return fx.randn(seed, B, T, 3 * H * hd, scale=scale)
@@ -605,7 +655,7 @@ def test_score_tail_a_gelu_on_load_and_prev_gather(ops):
     assert torch.equal(pk1.cpu(), torch.ones(B, K))
 
 
-@pytest.mark.parametrize("B,T,H,frac", [(3, 197, 6, False), (2, 138, 6, True), (2, 64, 3, False), (1, 8, 2, True)])
+@pytest.mark.parametrize("B,T,H,frac", [(3, 197, 6, False), (2, 138, 6, True), (2, 97, 6, True), (2, 64, 3, False), (1, 8, 2, True)])
 def test_attention_train_fwd_bwd_vs_oracle_autograd(ops, B, T, H, frac):
     """bf16 training attention (per-head strided GEMMs on the packed qkv + padded-row policy softmax kernels) against the
     fp32 oracle's autograd on the same bf16-rounded inputs: output, CLS row, d qkv and d policy at bf16 tolerance."""
