@@ -50,7 +50,7 @@ def attention_pre_proj(m, x, policy=None, return_cls_attn=False):
     """Attention.forward up to (not including) the output projection (dynamic_vit.py:216-231): (o (B,T,C), cls_attn)."""
     B, T, C = x.shape
     H = m.num_heads
-    qkv = m.qkv(x)
+    qkv = ops.linear_train(m.qkv, x)
     if _needs_grad(qkv, policy) and qkv.is_cuda and qkv.dtype == torch.bfloat16 and T <= 256 and _TRAIN_ATTN:
         # training, bf16: per-head strided GEMMs on the packed tensor around the padded-row policy softmax
         o, cls_attn = ops.attention_train(qkv, H, policy=policy, scale=m.scale, want_cls_row=return_cls_attn)
@@ -70,7 +70,7 @@ def attention_pre_proj(m, x, policy=None, return_cls_attn=False):
 def attention_forward(m, x, policy=None, return_cls_attn=False):
     """Attention.forward (dynamic_vit.py:216-236 / default_dynamic_vit.py:201-216)."""
     o, cls_attn = attention_pre_proj(m, x, policy, return_cls_attn)
-    o = m.proj_drop(m.proj(o))
+    o = m.proj_drop(ops.linear_train(m.proj, o))
     return (o, cls_attn) if return_cls_attn else o
 
 

@@ -35,7 +35,8 @@ class Mlp(nn.Module):
         self.drop = nn.Dropout(drop)
 
     def forward(self, x):
-        return self.drop(self.fc2(self.drop(self.act(self.fc1(x)))))
+        # (ops.linear_train is the module itself unless a gradient is wanted on the bf16 CUDA path)
+        return self.drop(ops.linear_train(self.fc2, self.drop(self.act(ops.linear_train(self.fc1, x)))))
 
 
 class Attention(nn.Module):

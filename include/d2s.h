@@ -146,6 +146,11 @@ int d2s_softmax_policy_bwd_ld(const void* attn, const float* policy, const void*
 int d2s_split_heads_bf16(const void* src, int B, int T, int Tp, int G, int H, int hd, void* dst, d2s_stream_t stream);
 int d2s_merge_heads_bf16(const void* src, int B, int T, int Tp, int G, int H, int hd, void* dst, d2s_stream_t stream);
 
+/* Weight and bias gradient of a Linear layer (nn.Linear of Attention / Mlp / PredictorLG under autograd, dynamic_vit.py:159-236),
+ * bf16: dw (N,K) = dy^T x, db (N) = column sums of dy (NULL: not wanted), from dy (M,N) and x (M,K).  ONE cuBLASLt GEMM with the
+ * bias-gradient epilogue instead of torch.autograd's GEMM + separate column reduction.  N % 8 == 0, K % 8 == 0. */
+int d2s_linear_wgrad_bf16(const void* dy, const void* x, int M, int N, int K, void* dw, void* db, d2s_stream_t stream);
+
 /* Fused attention core of Attention.forward (dynamic_vit.py:218-234; default_dynamic_vit.py:203-213):
  * qkv (B,T,3,H,hd) packed as produced by the qkv Linear; out (B,T,H*hd) ready for the proj Linear;
  * cls_row (B,H,T) f32 = probabilities of query row 0 (dynamic_vit.py:233-234) or NULL.
