@@ -33,6 +33,7 @@ template <> struct TV<__nv_bfloat16> {
     for (int i = 0; i < 4; ++i) { const __nv_bfloat162 t = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]); w[i] = *reinterpret_cast<const uint32_t*>(&t); }
     *reinterpret_cast<int4*>(p) = make_int4((int)w[0], (int)w[1], (int)w[2], (int)w[3]);
   }
+  __device__ static float round(float f) { return __bfloat162float(__float2bfloat16_rn(f)); }
 };
 template <> struct TV<float> {   // 8 floats = two 16-byte vectors, so both dtypes walk the row in 8-element steps
   static constexpr int kElems = 8;
@@ -44,6 +45,7 @@ template <> struct TV<float> {   // 8 floats = two 16-byte vectors, so both dtyp
     *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
     *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
   }
+  __device__ static float round(float f) { return f; }
 };
 
 __device__ __forceinline__ float hw_sum(float v) {
@@ -55,8 +57,9 @@ __device__ __forceinline__ float hw_sum(float v) {
 // h = (x - mean) * rstd * gamma + beta ; stats (rows, 2) = (mean, rstd)
 template <typename TX, typename TH, int kVPL>
 __global__ void __launch_bounds__(kLtThreads)
-ln_fwd_kernel(const TX* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta, long long rows,
-              int D, float eps, TH* __restrict__ h, float* __restrict__ stats) {
+ln_fwd_kernel(const TX* __restrict__ x, const TX* __restrict__ res, const float* __restrict__ gamma,
+              const float* __restrict__ beta, long long rows, int D, float eps, TX* __restrict__ out_sum, TH* __restrict__ h,
+              float* __restrict__ stats) {
   const int sub = threadIdx.x & 15;
   const long long row = (long long)blockIdx.x * kLtRowsPerIter + (threadIdx.x >> 4);
   const bool ok = row < rows;
@@ -68,6 +71,13 @@ ln_fwd_kernel(const TX* __restrict__ x, const float* __restrict__ gamma, const f
     const int vi = sub + 16 * k;
     if (ok && vi < nvec) {
       TV<TX>::load(x + row * D + vi * 8, v[k]);
+      if (res) {   // residual add folded in: s = x + res rounded to the stream's dtype (what torch's add would store), kept
+        float r[8];
+        TV<TX>::load(res + row * D + vi * 8, r);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[k][q] = TV<TX>::round(v[k][q] + r[q]);
+        TV<TX>::store(out_sum + row * D + vi * 8, v[k]);
+      }
 #pragma unroll
       for (int q = 0; q < 8; ++q) sum += v[k][q];
     } else {
@@ -104,8 +114,8 @@ ln_fwd_kernel(const TX* __restrict__ x, const float* __restrict__ gamma, const f
 template <typename TX, typename TH, int kVPL>
 __global__ void __launch_bounds__(kLtBwdThreads)
 ln_bwd_kernel(const TH* __restrict__ dh, const TX* __restrict__ x, const float* __restrict__ stats,
-              const float* __restrict__ gamma, long long rows, int D, TX* __restrict__ dx, float* __restrict__ dgamma,
-              float* __restrict__ dbeta) {
+              const float* __restrict__ gamma, const TX* __restrict__ gadd, long long rows, int D, TX* __restrict__ dx,
+              float* __restrict__ dgamma, float* __restrict__ dbeta) {
   extern __shared__ float red[];   // 2 * D : per-CTA dgamma | dbeta
   for (int c = threadIdx.x; c < 2 * D; c += kLtBwdThreads) red[c] = 0.f;
   __syncthreads();
@@ -158,6 +168,12 @@ ln_bwd_kernel(const TH* __restrict__ dh, const TX* __restrict__ x, const float* 
           float o[8];
 #pragma unroll
           for (int q = 0; q < 8; ++q) o[q] = rstd * (gg[k][q] - s1 - xh[k][q] * s2);
+          if (gadd) {   // gradient that reaches x directly (the residual stream's), accumulated here instead of by a torch add
+            float ga[8];
+            TV<TX>::load(gadd + row * D + vi * 8, ga);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) o[q] += ga[q];
+          }
           TV<TX>::store(dx + row * D + vi * 8, o);
         }
       }
@@ -183,23 +199,23 @@ ln_bwd_kernel(const TH* __restrict__ dh, const TX* __restrict__ x, const float* 
 }
 
 template <typename TX, typename TH>
-static int ln_fwd_launch(const void* x, const float* gamma, const float* beta, long long rows, int D, float eps, void* h,
-                         float* stats, cudaStream_t st) {
+static int ln_fwd_launch(const void* x, const void* res, const float* gamma, const float* beta, long long rows, int D, float eps,
+                         void* out_sum, void* h, float* stats, cudaStream_t st) {
   const int vpl = ceil_div(D / 8, 16);
   const unsigned grid = (unsigned)((rows + kLtRowsPerIter - 1) / kLtRowsPerIter);
-  if (vpl <= 3) ln_fwd_kernel<TX, TH, 3><<<grid, kLtThreads, 0, st>>>((const TX*)x, gamma, beta, rows, D, eps, (TH*)h, stats);
-  else          ln_fwd_kernel<TX, TH, 6><<<grid, kLtThreads, 0, st>>>((const TX*)x, gamma, beta, rows, D, eps, (TH*)h, stats);
+  if (vpl <= 3) ln_fwd_kernel<TX, TH, 3><<<grid, kLtThreads, 0, st>>>((const TX*)x, (const TX*)res, gamma, beta, rows, D, eps, (TX*)out_sum, (TH*)h, stats);
+  else          ln_fwd_kernel<TX, TH, 6><<<grid, kLtThreads, 0, st>>>((const TX*)x, (const TX*)res, gamma, beta, rows, D, eps, (TX*)out_sum, (TH*)h, stats);
   count_launch();
   return check_launch("d2s_layernorm_fwd");
 }
 template <typename TX, typename TH>
-static int ln_bwd_launch(const void* dh, const void* x, const float* stats, const float* gamma, long long rows, int D, void* dx,
-                         float* dgamma, float* dbeta, cudaStream_t st) {
+static int ln_bwd_launch(const void* dh, const void* x, const float* stats, const float* gamma, const void* gadd, long long rows,
+                         int D, void* dx, float* dgamma, float* dbeta, cudaStream_t st) {
   const int vpl = ceil_div(D / 8, 16);
   const unsigned grid = (unsigned)((rows + kLtRowsPerCta - 1) / kLtRowsPerCta);
   const size_t smem = 2 * (size_t)D * sizeof(float);
-  if (vpl <= 3) ln_bwd_kernel<TX, TH, 3><<<grid, kLtBwdThreads, smem, st>>>((const TH*)dh, (const TX*)x, stats, gamma, rows, D, (TX*)dx, dgamma, dbeta);
-  else          ln_bwd_kernel<TX, TH, 6><<<grid, kLtBwdThreads, smem, st>>>((const TH*)dh, (const TX*)x, stats, gamma, rows, D, (TX*)dx, dgamma, dbeta);
+  if (vpl <= 3) ln_bwd_kernel<TX, TH, 3><<<grid, kLtBwdThreads, smem, st>>>((const TH*)dh, (const TX*)x, stats, gamma, (const TX*)gadd, rows, D, (TX*)dx, dgamma, dbeta);
+  else          ln_bwd_kernel<TX, TH, 6><<<grid, kLtBwdThreads, smem, st>>>((const TH*)dh, (const TX*)x, stats, gamma, (const TX*)gadd, rows, D, (TX*)dx, dgamma, dbeta);
   count_launch();
   return check_launch("d2s_layernorm_bwd");
 }
@@ -214,30 +230,60 @@ static int ln_check(const char* what, long long rows, int D, int dx, int dh) {
 
 using namespace d2s;
 
-extern "C" int d2s_layernorm_fwd(const void* x, int x_dtype, const float* gamma, const float* beta, long long rows, int D,
-                                 float eps, void* h, int h_dtype, float* stats, d2s_stream_t stream) {
-  D2S_REQUIRE(x && gamma && beta && h && stats, D2S_ERR_ARG, "layernorm_fwd: null pointer");
-  int rc = ln_check("layernorm_fwd", rows, D, x_dtype, h_dtype);
+static int ln_fwd_entry(const char* what, const void* x, const void* res, int x_dtype, const float* gamma, const float* beta,
+                        long long rows, int D, float eps, void* out_sum, void* h, int h_dtype, float* stats, d2s_stream_t stream) {
+  D2S_REQUIRE(x && gamma && beta && h && stats && (!res || out_sum), D2S_ERR_ARG, "%s: null pointer", what);
+  int rc = ln_check(what, rows, D, x_dtype, h_dtype);
   if (rc) return rc;
-  D2S_REQUIRE(aligned16(x) && aligned16(h) && aligned16(gamma) && aligned16(beta), D2S_ERR_ALIGN, "layernorm_fwd: 16-byte alignment");
+  D2S_REQUIRE(aligned16(x) && aligned16(h) && aligned16(gamma) && aligned16(beta) && (!res || (aligned16(res) && aligned16(out_sum))),
+              D2S_ERR_ALIGN, "%s: 16-byte alignment", what);
   if (rows == 0) return D2S_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  if (x_dtype == D2S_F32 && h_dtype == D2S_BF16) return ln_fwd_launch<float, __nv_bfloat16>(x, gamma, beta, rows, D, eps, h, stats, st);
-  if (x_dtype == D2S_F32 && h_dtype == D2S_F32) return ln_fwd_launch<float, float>(x, gamma, beta, rows, D, eps, h, stats, st);
-  if (x_dtype == D2S_BF16 && h_dtype == D2S_BF16) return ln_fwd_launch<__nv_bfloat16, __nv_bfloat16>(x, gamma, beta, rows, D, eps, h, stats, st);
-  return ln_fwd_launch<__nv_bfloat16, float>(x, gamma, beta, rows, D, eps, h, stats, st);
+  if (x_dtype == D2S_F32 && h_dtype == D2S_BF16) return ln_fwd_launch<float, __nv_bfloat16>(x, res, gamma, beta, rows, D, eps, out_sum, h, stats, st);
+  if (x_dtype == D2S_F32 && h_dtype == D2S_F32) return ln_fwd_launch<float, float>(x, res, gamma, beta, rows, D, eps, out_sum, h, stats, st);
+  if (x_dtype == D2S_BF16 && h_dtype == D2S_BF16) return ln_fwd_launch<__nv_bfloat16, __nv_bfloat16>(x, res, gamma, beta, rows, D, eps, out_sum, h, stats, st);
+  return ln_fwd_launch<__nv_bfloat16, float>(x, res, gamma, beta, rows, D, eps, out_sum, h, stats, st);
+}
+
+static int ln_bwd_entry(const char* what, const void* dh, int h_dtype, const void* x, int x_dtype, const float* stats,
+                        const float* gamma, const void* gadd, long long rows, int D, void* dx, float* dgamma, float* dbeta,
+                        d2s_stream_t stream) {
+  D2S_REQUIRE(dh && x && stats && gamma && dx && dgamma && dbeta, D2S_ERR_ARG, "%s: null pointer", what);
+  int rc = ln_check(what, rows, D, x_dtype, h_dtype);
+  if (rc) return rc;
+  D2S_REQUIRE(aligned16(dh) && aligned16(x) && aligned16(dx) && aligned16(gamma) && (!gadd || aligned16(gadd)), D2S_ERR_ALIGN,
+              "%s: 16-byte alignment", what);
+  if (rows == 0) return D2S_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (x_dtype == D2S_F32 && h_dtype == D2S_BF16) return ln_bwd_launch<float, __nv_bfloat16>(dh, x, stats, gamma, gadd, rows, D, dx, dgamma, dbeta, st);
+  if (x_dtype == D2S_F32 && h_dtype == D2S_F32) return ln_bwd_launch<float, float>(dh, x, stats, gamma, gadd, rows, D, dx, dgamma, dbeta, st);
+  if (x_dtype == D2S_BF16 && h_dtype == D2S_BF16) return ln_bwd_launch<__nv_bfloat16, __nv_bfloat16>(dh, x, stats, gamma, gadd, rows, D, dx, dgamma, dbeta, st);
+  return ln_bwd_launch<__nv_bfloat16, float>(dh, x, stats, gamma, gadd, rows, D, dx, dgamma, dbeta, st);
+}
+
+extern "C" int d2s_layernorm_fwd(const void* x, int x_dtype, const float* gamma, const float* beta, long long rows, int D,
+                                 float eps, void* h, int h_dtype, float* stats, d2s_stream_t stream) {
+  return ln_fwd_entry("layernorm_fwd", x, nullptr, x_dtype, gamma, beta, rows, D, eps, nullptr, h, h_dtype, stats, stream);
 }
 
 extern "C" int d2s_layernorm_bwd(const void* dh, int h_dtype, const void* x, int x_dtype, const float* stats, const float* gamma,
                                  long long rows, int D, void* dx, float* dgamma, float* dbeta, d2s_stream_t stream) {
-  D2S_REQUIRE(dh && x && stats && gamma && dx && dgamma && dbeta, D2S_ERR_ARG, "layernorm_bwd: null pointer");
-  int rc = ln_check("layernorm_bwd", rows, D, x_dtype, h_dtype);
-  if (rc) return rc;
-  D2S_REQUIRE(aligned16(dh) && aligned16(x) && aligned16(dx) && aligned16(gamma), D2S_ERR_ALIGN, "layernorm_bwd: 16-byte alignment");
-  if (rows == 0) return D2S_OK;
-  cudaStream_t st = (cudaStream_t)stream;
-  if (x_dtype == D2S_F32 && h_dtype == D2S_BF16) return ln_bwd_launch<float, __nv_bfloat16>(dh, x, stats, gamma, rows, D, dx, dgamma, dbeta, st);
-  if (x_dtype == D2S_F32 && h_dtype == D2S_F32) return ln_bwd_launch<float, float>(dh, x, stats, gamma, rows, D, dx, dgamma, dbeta, st);
-  if (x_dtype == D2S_BF16 && h_dtype == D2S_BF16) return ln_bwd_launch<__nv_bfloat16, __nv_bfloat16>(dh, x, stats, gamma, rows, D, dx, dgamma, dbeta, st);
-  return ln_bwd_launch<__nv_bfloat16, float>(dh, x, stats, gamma, rows, D, dx, dgamma, dbeta, st);
+  return ln_bwd_entry("layernorm_bwd", dh, h_dtype, x, x_dtype, stats, gamma, nullptr, rows, D, dx, dgamma, dbeta, stream);
+}
+
+// Residual add folded into the LayerNorm that follows it, with autograd (Block.forward, dynamic_vit.py:276-283: x = x + branch;
+// norm(x)): forward writes out_sum = x + res (dtype of x) and h = LayerNorm(out_sum); backward adds the gradient that reaches
+// out_sum directly (gsum, may be NULL) to the LayerNorm's input gradient, so neither the add nor the gradient accumulation is
+// a separate pass.
+extern "C" int d2s_add_layernorm_fwd(const void* x, const void* res, int x_dtype, const float* gamma, const float* beta,
+                                     long long rows, int D, float eps, void* out_sum, void* h, int h_dtype, float* stats,
+                                     d2s_stream_t stream) {
+  D2S_REQUIRE(res && out_sum, D2S_ERR_ARG, "add_layernorm_fwd: null pointer");
+  return ln_fwd_entry("add_layernorm_fwd", x, res, x_dtype, gamma, beta, rows, D, eps, out_sum, h, h_dtype, stats, stream);
+}
+
+extern "C" int d2s_add_layernorm_bwd(const void* dh, int h_dtype, const void* xsum, int x_dtype, const float* stats,
+                                     const float* gamma, const void* gsum, long long rows, int D, void* dx, float* dgamma,
+                                     float* dbeta, d2s_stream_t stream) {
+  return ln_bwd_entry("add_layernorm_bwd", dh, h_dtype, xsum, x_dtype, stats, gamma, gsum, rows, D, dx, dgamma, dbeta, stream);
 }

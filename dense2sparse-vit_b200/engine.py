@@ -20,6 +20,7 @@ from . import ops
 
 _FUSED_FC1 = os.environ.get("D2S_FUSED_FC1", "1") != "0"   # A/B switch for the tcgen05 fc1+GELU GEMM
 _TRAIN_ATTN = os.environ.get("D2S_TRAIN_ATTN", "1") != "0"    # A/B switch for ops.attention_train (bf16 training attention)
+_FUSED_ADD_LN_TRAIN = os.environ.get("D2S_FUSED_ADD_LN_TRAIN", "1") != "0"   # A/B switch: residual adds folded into LayerNorm fwd/bwd
 _FUSED_MLP = os.environ.get("D2S_FUSED_MLP", "1") != "0"      # A/B switch for the one-kernel MLP (ops.mlp_residual_ln)
 _FUSED_PAIR = os.environ.get("D2S_FUSED_PAIR", "1") != "0"  # A/B switch for the CTA-pair GEMMs (fc1 pair; proj/fc2 + add + LN)
 INIT_N = 14 * 14  # the reference hard-codes 196 spatial tokens (dynamic_vit.py:828, default_dynamic_vit.py:446)
@@ -87,6 +88,14 @@ def _fusable(m, x, *extra):
     return (not _needs_grad(x, *extra, m.norm1.weight if hasattr(m.norm1, "weight") else None)
             and x.is_cuda and _is_plain_ln(m.norm1) and _is_plain_ln(m.norm2)
             and isinstance(m.drop_path, torch.nn.Identity) and _drop_off(m.attn.proj_drop, m.training))
+
+
+def _train_fusable(m, x, y=None):
+    """The training path with fused residual adds applies: CUDA, plain LayerNorms on rows the d2s LayerNorm kernels take, no
+    stochastic depth, and a residual stream of one dtype."""
+    return (_FUSED_ADD_LN_TRAIN and x.is_cuda and x.dtype in (torch.float32, torch.bfloat16) and (y is None or y.dtype == x.dtype)
+            and _is_plain_ln(m.norm1) and _is_plain_ln(m.norm2) and x.shape[-1] % 8 == 0 and x.shape[-1] <= 768
+            and isinstance(m.drop_path, torch.nn.Identity) and isinstance(m.mlp, torch.nn.Module))
 
 
 def _mlp_is_plain(m, h):
@@ -213,6 +222,25 @@ class _Stream:
         self.y = None
         return self.x, h
 
+    def _sum_norm_train(self, norm):
+        """Training form of _sum_norm: (x + y, norm(x + y)) with autograd; one kernel forward, one backward."""
+        self._flush_lin()
+        if self.y is None:
+            return self.x, norm_forward(norm, self.x)
+        self.x, h = ops.add_layer_norm_train(self.x, self.y, norm.weight, norm.bias, norm.eps)
+        self.y = None
+        return self.x, h
+
+    def _block_train(self, blk, policy, return_cls_attn):
+        """Block.forward (dynamic_vit.py:263-283) under autograd with every residual add folded into the LayerNorm that follows
+        it (the second add of a block into the NEXT block's norm1 through the pending branch y)."""
+        _, h = self._sum_norm_train(blk.norm1)
+        o, cls_attn = attention_pre_proj(blk.attn, h, policy, return_cls_attn)
+        self.y = blk.attn.proj_drop(ops.linear_train(blk.attn.proj, o))
+        _, h = self._sum_norm_train(blk.norm2)
+        self.y = blk.mlp(h)
+        return cls_attn
+
     def block(self, blk, policy=None, return_cls_attn=False):
         """Inference form of Block.forward (dynamic_vit.py:263-283): every residual add is folded into the LayerNorm that
         follows it, and the Linear that produced the branch into the same kernel when it can be."""
@@ -228,6 +256,8 @@ class _Stream:
             else:
                 self.y = blk.mlp(h)
             return cls_attn
+        if _train_fusable(blk, self.x, self.y):
+            return self._block_train(blk, policy, return_cls_attn)
         out = block_forward(blk, self.value(), policy, return_cls_attn)
         if return_cls_attn:
             self.x, cls_attn = out

@@ -557,6 +557,52 @@ class _LayerNorm(torch.autograd.Function):
         return dx, dgb[0].to(ctx.meta[0]), dgb[1].to(ctx.meta[1]), None, None
 
 
+class _AddLayerNorm(torch.autograd.Function):
+    """(s, h) = (x + y, LayerNorm(x + y)) as one kernel each way: the forward writes both, the backward adds the gradient
+    reaching s directly into the LayerNorm's input gradient and hands the same tensor to x and y."""
+
+    @staticmethod
+    def forward(ctx, x, y, weight, bias, eps, out_dtype):
+        xc, yc = x.contiguous(), y.contiguous()
+        D = xc.shape[-1]
+        rows = xc.numel() // D
+        w, b = _f32c(weight), _f32c(bias)
+        s = torch.empty_like(xc)
+        h = torch.empty(xc.shape, dtype=out_dtype, device=xc.device)
+        stats = torch.empty(rows, 2, dtype=torch.float32, device=xc.device)
+        _lib.call("d2s_add_layernorm_fwd", _ptr(xc), _ptr(yc), _dtype_code(xc), _ptr(w), _ptr(b), rows, D, float(eps), _ptr(s),
+                  _ptr(h), _dtype_code(h), _ptr(stats), _stream())
+        ctx.save_for_backward(s, stats, w)
+        ctx.meta = (weight.dtype, bias.dtype)
+        return s, h
+
+    @staticmethod
+    def backward(ctx, gs, gh):
+        s, stats, w = ctx.saved_tensors
+        if gh is None:
+            return gs, gs, None, None, None, None
+        D = s.shape[-1]
+        rows = s.numel() // D
+        g = gh.contiguous()
+        ga = None if gs is None else gs.to(s.dtype).contiguous()
+        dx = torch.empty_like(s)
+        dgb = torch.zeros(2, D, dtype=torch.float32, device=s.device)
+        _lib.call("d2s_add_layernorm_bwd", _ptr(g), _dtype_code(g), _ptr(s), _dtype_code(s), _ptr(stats), _ptr(w), _ptr(ga), rows, D,
+                  _ptr(dx), _ptr(dgb[0]), _ptr(dgb[1]), _stream())
+        return dx, dx, dgb[0].to(ctx.meta[0]), dgb[1].to(ctx.meta[1]), None, None
+
+
+def add_layer_norm_train(x, y, weight, bias, eps, out_dtype=None):
+    """(x + y, LayerNorm(x + y)) with autograd in x, y, weight and bias: the training-path form of the fused residual add +
+    LayerNorm (x and y of one dtype, f32 or bf16; the sum is rounded to that dtype like torch's add)."""
+    _check_cuda(x, y, weight, bias)
+    if x.dtype != y.dtype or x.shape != y.shape:
+        raise RuntimeError(f"add_layer_norm_train: x {tuple(x.shape)} {x.dtype} and y {tuple(y.shape)} {y.dtype} must match")
+    if out_dtype is None:
+        out_dtype = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else x.dtype
+    return _AddLayerNorm.apply(x, y, weight, bias, eps, out_dtype)
+
+
 def layer_norm(x, weight, bias, eps, out_dtype=None):
     """LayerNorm over the last dim with autograd: x f32|bf16 -> out_dtype (default: bf16 under CUDA autocast, else
     x.dtype), statistics in fp32.  One streaming kernel forward, one backward (dx + dgamma + dbeta)."""

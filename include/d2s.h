@@ -239,6 +239,14 @@ int d2s_layernorm_fwd(const void* x, int x_dtype, const float* gamma, const floa
 int d2s_layernorm_bwd(const void* dh, int h_dtype, const void* x, int x_dtype, const float* stats, const float* gamma,
                       long long rows, int D, void* dx, float* dgamma, float* dbeta, d2s_stream_t stream);
 
+/* The residual add folded into the LayerNorm that follows it, training path (Block.forward, dynamic_vit.py:276-283:
+ * x = x + branch; norm(x)): forward writes out_sum = x + res (dtype of x) and h = LayerNorm(out_sum) (+ stats); backward
+ * returns dx = LayerNorm input gradient + gsum, gsum = the gradient that reaches out_sum directly (NULL: none). */
+int d2s_add_layernorm_fwd(const void* x, const void* res, int x_dtype, const float* gamma, const float* beta, long long rows,
+                          int D, float eps, void* out_sum, void* h, int h_dtype, float* stats, d2s_stream_t stream);
+int d2s_add_layernorm_bwd(const void* dh, int h_dtype, const void* xsum, int x_dtype, const float* stats, const float* gamma,
+                          const void* gsum, long long rows, int D, void* dx, float* dgamma, float* dbeta, d2s_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -302,6 +302,38 @@ def test_fused_block_kernels_at_deit_s_width(d2s, cuda_dev, variant, monkeypatch
     assert float((lf - ref).abs().max()) < 3e-2 * scale, "fused bf16 path deviates from the fp32 oracle"
 
 
+def test_training_fusions_match_the_unfused_training_path(d2s, cuda_dev, monkeypatch):
+    """Variant A training step under bf16 autocast with the training-path fusions (residual adds folded into LayerNorm forward /
+    backward, Linear weight + bias gradient in one GEMM) against the same step with both switched off: identical keep decisions
+    (same injected Gumbel noise), logits and parameter gradients to bf16 accuracy."""
+    x = fx.randn(40, 4, 3, 224, 224).to(cuda_dev)
+    m, _ = _deit_s_width_models(d2s, cuda_dev, "a", [0.7, 0.49])
+    m.train()
+    m._d2s_gumbels = [fx.randn(41 + i, 4, 196, 2).to(cuda_dev) for i in range(2)]
+    up = fx.randn(43, 4, 16).to(cuda_dev)
+
+    def step():
+        m.zero_grad()
+        n0 = d2s._lib.launch_count()
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            logits, feats, final_dec, decs = m(x)
+        ((logits.float() * up).sum() + feats.float().square().mean()).backward()
+        grads = {k: p.grad.detach().clone() for k, p in m.named_parameters() if p.grad is not None}
+        return logits.detach().float(), [d.detach() for d in decs], grads, d2s._lib.launch_count() - n0
+
+    lf, df, gf, nf = step()
+    monkeypatch.setattr(d2s.engine, "_FUSED_ADD_LN_TRAIN", False)
+    monkeypatch.setattr(d2s.ops, "_FUSED_WGRAD", False)
+    lp, dp, gp, npl = step()
+    for a, b in zip(df, dp):
+        assert torch.equal(a, b)
+    assert float((lf - lp).abs().max()) < 3e-2 * float(lp.abs().max())
+    assert gf.keys() == gp.keys()
+    for k in gf:
+        a, b = gf[k].float(), gp[k].float()
+        assert float((a - b).abs().max()) <= 5e-2 * float(b.abs().max()) + 1e-5, k
+
+
 def test_fused_path_keeps_the_reference_token_sets_when_margins_allow(d2s, cuda_dev):
     """At keep ratio 0.7 the bf16 fused path must select the oracle's token sets wherever the fp32 score margin at the cut is
     larger than bf16 noise (SURVEY hard part 1); images with a near-tie at the cut are excluded, not tolerated silently."""

@@ -447,6 +447,39 @@ def test_layer_norm_autograd(ops, xd, hd, rows, D):
     assert rel(wg.grad, w2.grad) < 1e-4 and rel(bg.grad, b2.grad) < 1e-4
 
 
+@pytest.mark.parametrize("xd,hd", [(torch.float32, torch.float32), (torch.float32, torch.bfloat16), (torch.bfloat16, torch.bfloat16)])
+@pytest.mark.parametrize("rows,D", [(3 * 197, 384), (1000, 768), (37, 128)])
+def test_add_layer_norm_train_autograd(ops, xd, hd, rows, D):
+    """(s, h) = (x + y, LayerNorm(x + y)) as one kernel each way, against torch autograd in float64 on the same inputs:
+    s exact (one rounding of the sum), h, and the gradients of x, y (identical), weight, bias with s and h BOTH used downstream."""
+    x = (fx.randn(290 + D, rows, D) * 1.5 + 0.3).to(xd)
+    y = fx.randn(291 + D, rows, D).to(xd)
+    w, b = 1 + 0.1 * fx.randn(292, D), 0.1 * fx.randn(293, D)
+    up_h, up_s = fx.randn(294, rows, D).to(hd), fx.randn(295, rows, D).to(xd)
+    xg, yg = cu(x).requires_grad_(True), cu(y).requires_grad_(True)
+    wg, bg = cu(w).requires_grad_(True), cu(b).requires_grad_(True)
+    s, h = ops.add_layer_norm_train(xg, yg, wg, bg, 1e-6, out_dtype=hd)
+    assert s.dtype == xd and h.dtype == hd
+    assert torch.equal(s.detach().cpu(), x + y)
+    ((h.float() * cu(up_h).float()).sum() + (s.float() * cu(up_s).float()).sum()).backward()
+    assert torch.equal(xg.grad, yg.grad)
+    s2 = (x + y).double().requires_grad_(True)
+    w2, b2 = w.double().requires_grad_(True), b.double().requires_grad_(True)
+    h2 = torch.nn.functional.layer_norm(s2, (D,), w2, b2, 1e-6)
+    ((h2 * up_h.double()).sum() + (s2 * up_s.double()).sum()).backward()
+    lo = hd == torch.bfloat16 or xd == torch.bfloat16
+    torch.testing.assert_close(h.detach().cpu().double(), h2.detach(), rtol=1.6e-2 if lo else 1e-5, atol=1e-2 if lo else 1e-5)
+    def rel(a, r):
+        return float((a.cpu().double() - r).abs().max() / r.abs().max())
+    assert rel(xg.grad, s2.grad) < (2e-2 if xd == torch.bfloat16 else 1e-4)
+    assert rel(wg.grad, w2.grad) < 1e-4 and rel(bg.grad, b2.grad) < 1e-4
+    # only s used downstream: the gradient passes straight through
+    xg2, yg2 = cu(x).requires_grad_(True), cu(y).requires_grad_(True)
+    s3, _ = ops.add_layer_norm_train(xg2, yg2, wg, bg, 1e-6, out_dtype=hd)
+    (s3.float() * cu(up_s).float()).sum().backward()
+    assert torch.equal(xg2.grad.cpu(), up_s) and torch.equal(yg2.grad.cpu(), up_s)
+
+
 # ------------------------------------------------------------------------------------------ predictor body, embed
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("B,N,Cc", [(3, 196, 384), (2, 137, 768), (2, 96, 128), (1, 5, 1536)])
