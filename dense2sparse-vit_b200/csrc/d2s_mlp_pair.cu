@@ -38,7 +38,12 @@ constexpr uint32_t kMpA1Blk = 128 * 128;        // 16 KB: 128 rows x 64 bf16 of 
 constexpr uint32_t kMpW1Blk = 64 * 128;         //  8 KB: this CTA's 64 of the 128 W1 rows of a chunk, one k-block
 constexpr uint32_t kMpW2Blk = 96 * 128;         // 12 KB: this CTA's 96 of the 192 W2 rows of one N-half, 64 of the chunk's 128 hidden columns
 constexpr uint32_t kMpPBlk = 128 * 128;         // 16 KB: 128 rows x 64 bf16; P_j is two of them
-constexpr int kMpE1Warps = 8, kMpOutWarps = 4, kMpThreads = (4 + kMpE1Warps + kMpOutWarps) * 32;
+#ifndef MP_E1W
+#define MP_E1W 8
+#endif
+constexpr int kMpE1Warps = MP_E1W, kMpOutWarps = 4, kMpThreads = (4 + kMpE1Warps + kMpOutWarps) * 32;
+constexpr int kMpE1Parts = kMpE1Warps / 4;          // E1 warps per TMEM lane quadrant
+constexpr int kMpE1Cols = kMpCH / kMpE1Parts;       // hidden columns of a chunk per E1 warp (64 or 32)
 constexpr uint32_t kMpAccCols = 384, kMpSCols = 128;
 
 // clock64 totals of the issuing warps' waits (profiling builds only: -DD2S_GEMM_TRACE_BUILD, scripts/bench_mlp_trace.py)
@@ -79,7 +84,11 @@ struct MpParams {
   int T, ln_row0;               // LayerNorm output skips the first ln_row0 tokens of every T-token image (predictor norm over x[:, 1:])
 };
 
+#if MP_E1W == 8
 __global__ void __cluster_dims__(2, 1, 1) __maxnreg__(128)
+#else
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMpThreads, 1)
+#endif
 mlp_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w1,
                 const __grid_constant__ CUtensorMap map_w2, const MpParams p) {
   constexpr int TN = kMpD;
@@ -132,6 +141,16 @@ mlp_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   tc_fence_after();
   const uint32_t tmem = bars->tmem_base;
 
+#if MP_E1W == 16
+  // 24 warps: the launch gives every thread 80 registers; the control warps hand some back to the output warps (setmaxnreg works
+  // per warpgroup = 4 aligned warps, which is how the roles are laid out).  4*32*48 + 16*32*80 + 4*32*112 = 768 * 80.
+  // (ptxas sizes a role's registers by the setmaxnreg that DOMINATES its code, so each sits at the top of its role's branch)
+#endif
+
+  if (warp_u < 4) {
+#if MP_E1W == 16
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
+#endif
   if (warp == 0) {
     if (lane == 0) {
       // ============================ TMA producer: H tile + W1 k-blocks (both CTAs) ============================
@@ -253,50 +272,55 @@ mlp_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       MP_TRACE(0)
       MP_TRACE_DUMP(1, c)
     }
-  } else if (warp < 4 + kMpE1Warps) {
+  }
+  } else if (warp_u < 4 + kMpE1Warps) {
     // ============================== E1 warps (both CTAs): P_j = bf16(GELU(S_j + b1)) ==============================
     // Two warps per TMEM lane quadrant, 64 of the chunk's 128 columns each (= one of the two k-blocks of P_j).  S and P are
     // single-buffered: S is free again as soon as it sits in registers (G1 of the next chunk then runs under this chunk's
     // GELU), P as soon as G2 of the previous chunk has retired (which the tensor pipe executes under this chunk's GELU too).
-    const int ew = warp - 4;                    // 0..7
+    const int ew = warp - 4;                    // 0 .. kMpE1Warps-1
     const int quad = warp & 3;                  // TMEM lane quadrant of this warp
-    const int half = ew >> 2;                   // which 64 of the chunk's 128 columns
+    const int part = ew >> 2;                   // which kMpE1Cols of the chunk's 128 columns
     const int r = quad * 32 + lane;
-    const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16) + kMpAccCols + half * 64;
-    unsigned char* blk = p_s + half * kMpPBlk;
+    const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16) + kMpAccCols + part * kMpE1Cols;
+    // P_j is two SWIZZLE_128B k-blocks of 64 columns; this warp's columns are 16-byte chunks kc0 .. of block pblk
+    unsigned char* blk = p_s + (part * kMpE1Cols / 64) * kMpPBlk;
+    const int kc0 = (part * kMpE1Cols % 64) / 8;
     uint32_t c = 0;
     for (int pt = pair; pt < pair_tiles; pt += num_pairs)
       for (int j = 0; j < nch; ++j, ++c) {
         mbar_wait(smem_u32(&bars->s_full), c & 1);
         tc_fence_after();
-        // all 64 columns first: S_j is then in registers and G1(j + 1) may overwrite it while the GELU below runs (with the
+        // all columns first: S_j is then in registers and G1(j + 1) may overwrite it while the GELU below runs (with the
         // second half loaded after the first half's GELU, s_empty went out ~1 k cycles later and G1 waited for it)
         uint32_t va[32], vb[32];
         tmem_ld32_nowait(lane_addr, va);
-        tmem_ld32_nowait(lane_addr + 32, vb);
+        if (kMpE1Cols == 64) tmem_ld32_nowait(lane_addr + 32, vb);
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(mapa(smem_u32(&bars->s_empty), 0));
-        uint32_t o[32];
+        uint32_t o[kMpE1Cols / 2];
 #pragma unroll
         for (int q = 0; q < 16; ++q) {
-          const float2 bq = *reinterpret_cast<const float2*>(&b1_s[j * kMpCH + half * 64 + 2 * q]);
+          const float2 bq = *reinterpret_cast<const float2*>(&b1_s[j * kMpCH + part * kMpE1Cols + 2 * q]);
           float g0, g1;
           f2_unpack(gelu_erf_pair(f2_add(f2_pack(__uint_as_float(va[2 * q]), __uint_as_float(va[2 * q + 1])), f2_pack(bq.x, bq.y))), g0, g1);
           o[q] = pack_bf16x2(g0, g1);
         }
+        if (kMpE1Cols == 64) {
 #pragma unroll
-        for (int q = 0; q < 16; ++q) {
-          const float2 bq = *reinterpret_cast<const float2*>(&b1_s[j * kMpCH + half * 64 + 32 + 2 * q]);
-          float g0, g1;
-          f2_unpack(gelu_erf_pair(f2_add(f2_pack(__uint_as_float(vb[2 * q]), __uint_as_float(vb[2 * q + 1])), f2_pack(bq.x, bq.y))), g0, g1);
-          o[16 + q] = pack_bf16x2(g0, g1);
+          for (int q = 0; q < 16; ++q) {
+            const float2 bq = *reinterpret_cast<const float2*>(&b1_s[j * kMpCH + part * kMpE1Cols + 32 + 2 * q]);
+            float g0, g1;
+            f2_unpack(gelu_erf_pair(f2_add(f2_pack(__uint_as_float(vb[2 * q]), __uint_as_float(vb[2 * q + 1])), f2_pack(bq.x, bq.y))), g0, g1);
+            o[(kMpE1Cols == 64 ? 16 : 0) + q] = pack_bf16x2(g0, g1);
+          }
         }
         mbar_wait(smem_u32(&bars->p_empty), (c & 1) ^ 1);                             // G2(j - 1) has read P
 #pragma unroll
-        for (int k = 0; k < 8; ++k)
-          *reinterpret_cast<uint4*>(blk + sw128_off(r, k)) = make_uint4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]);
+        for (int k = 0; k < kMpE1Cols / 8; ++k)
+          *reinterpret_cast<uint4*>(blk + sw128_off(r, kc0 + k)) = make_uint4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");                  // generic-proxy writes -> visible to the MMA
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(mapa(smem_u32(&bars->p_full), 0));
@@ -308,6 +332,9 @@ mlp_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     // every tile was spent here with the tensor pipe idle).  Global memory is touched in coalesced 64-byte row segments
     // through a 2 KB per-warp transposition buffer.  x' is not kept in registers: pass 2 re-reads it (L2-hot) once the row's
     // mean and variance are known.  Only pass 1 holds the accumulator, so G2 of the next tile waits for little.
+#if MP_E1W == 16
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
+#endif
     const int quad = warp & 3;
     const int ow = warp - 4 - kMpE1Warps;       // 0..3
     const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16);
