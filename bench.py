@@ -109,7 +109,7 @@ def run_reference(args):
         "e2e": {"value": r["img_s"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -399,14 +399,38 @@ def run_gpu(args):
             "value": c["img_s"], "unit": UNIT, "cores": c["cores"], "kind": "port",
             "sample": f"{c['steps']} forwards of batch {args.cpu_batch} fp32 (BASELINE configs[0]) through "
                       f"oracle.model.variant_a_eval, same architecture and pruning schedule"}
-    print(json.dumps(line), flush=True)
+    _emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
+_JSON_FD = None
+
+
+def _emit(line):
+    """The ONE JSON line of the contract, on the process's real stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
+def _stdout_for_json_only():
+    """Libraries print to stdout too (NCCL's version banner under NCCL_DEBUG=VERSION lands in front of the JSON line):
+    everything written to fd 1 from here on goes to stderr, the JSON line goes to a saved copy of the real stdout."""
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
 def main():
     args = parse()
+    if not (args.impl != "reference" and args.gpus > 1 and "WORLD_SIZE" not in os.environ):   # (not in the torchrun launcher)
+        _stdout_for_json_only()
     if args.impl == "reference":
         run_reference(args)
         return

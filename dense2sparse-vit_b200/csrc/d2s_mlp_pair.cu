@@ -52,20 +52,10 @@ constexpr uint32_t kMpAccCols = 384, kMpSCols = 128;
 #define MP_TRACE(i) { const long long tr_n = clock64(); tr[i] += tr_n - tr_t; tr_t = tr_n; }
 #define MP_TRACE_DUMP(w, n) if (p.trace && lane == 0) { long long* d_ = p.trace + ((size_t)(blockIdx.x >> 1) * 2 + (w)) * 8; \
     for (int i = 0; i < 7; ++i) d_[i] = tr[i]; d_[7] = (n); }
-#define ME_TRACE_DECL long long te[16] = {}; long long te_t = clock64(); long long te_n = 0;
-#define ME_TRACE(i) { const long long t_ = clock64(); te[i] += t_ - te_t; te_t = t_; }
-#define ME_COUNT ++te_n;
-#define ME_TRACE_DUMP if (p.trace && lane == 0 && rank == 0 && (ew == 0 || ew == 8)) { long long* d_ = p.trace + 74 * 16 + ((size_t)(blockIdx.x >> 1) * 2 + (ew >> 3)) * 8; \
-    for (int i = 0; i < 7; ++i) d_[i] = te[i]; d_[7] = te_n; \
-    long long* f_ = p.trace + 74 * 32 + ((size_t)(blockIdx.x >> 1) * 2 + (ew >> 3)) * 8; for (int i = 0; i < 8; ++i) f_[i] = te[8 + i]; }
 #else
 #define MP_TRACE_DECL
 #define MP_TRACE(i)
 #define MP_TRACE_DUMP(w, n)
-#define ME_TRACE_DECL
-#define ME_TRACE(i)
-#define ME_COUNT
-#define ME_TRACE_DUMP
 #endif
 
 struct MpBars {

@@ -1,3 +1,7 @@
+"""Issuer-side wait breakdown of the fused MLP kernel (clock64 totals per barrier; needs a trace build:
+
+    D2S_NVCC_EXTRA=-DD2S_GEMM_TRACE_BUILD python -c "import __graft_entry__ as g; g.build()"; python scripts/bench_mlp_trace.py
+"""
 import os, sys; sys.path.insert(0, "/root/repo")
 import torch, d2s
 ops = d2s.pkg.ops
@@ -11,17 +15,7 @@ for _ in range(3): f()
 os.environ["D2S_GEMM_TRACE"] = str(buf.data_ptr())
 f(); torch.cuda.synchronize()
 t = buf[:74 * 16].view(74, 2, 8).double()
-te = buf[74 * 16:74 * 32].view(74, 2, 8).double()
-tf = buf[74 * 32:].view(74, 2, 8).double()
 names = ["issue+other", "wait s_empty", "wait a1_full", "wait w1_full", "wait p_full", "wait w2_full", "wait acc_empty"]
 for w, nm in ((0, "G1 issuer"), (1, "G2 issuer")):
     ch = t[:, w, 7].mean().item()
     print(f"{nm}: {ch:.0f} chunks; cycles per chunk: " + ", ".join(f"{n} {t[:, w, i].mean().item() / ch:.0f}" for i, n in enumerate(names) if t[:, w, i].sum() > 0))
-en = ["between chunks", "wait s_full", "tmem ld + s_empty arrive", "GELU math", "wait p_empty", "P write + fence + p_full arrive", "final epilogue (per tile, /chunks)"]
-for g in (0, 1):
-    ch = te[:, g, 7].mean().item()
-    print(f"E1 group {g} (warp of quadrant 0): {ch:.0f} chunks; cycles per chunk: " + ", ".join(f"{n} {te[:, g, i].mean().item() / ch:.0f}" for i, n in enumerate(en)))
-fn = ["wait acc_full", "x transposition", "pass 1 (+acc_empty)", "x' out", "stats barriers", "pass 2 + h out", "end barrier"]
-tiles = 256 / 24
-for g in (0, 1):
-    print(f"final epilogue, group {g}: cycles per TILE: x loads issue {te[:, g, 6].mean().item() / tiles:.0f}, " + ", ".join(f"{n} {tf[:, g, i].mean().item() / tiles:.0f}" for i, n in enumerate(fn)))
