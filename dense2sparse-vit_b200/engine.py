@@ -11,7 +11,9 @@ Two execution modes, chosen per call:
   * autograd (a gradient is needed): library GEMMs around the one-pass policy-softmax kernel
              (forward + backward in both arguments), gather/scatter kernels, Gumbel decision kernel.
 """
+import copy
 import os
+import weakref
 
 import torch
 import torch.nn.functional as F
@@ -20,6 +22,7 @@ from . import ops
 
 _FUSED_FC1 = os.environ.get("D2S_FUSED_FC1", "1") != "0"   # A/B switch for the tcgen05 fc1+GELU GEMM
 _TRAIN_ATTN = os.environ.get("D2S_TRAIN_ATTN", "1") != "0"    # A/B switch for ops.attention_train (bf16 training attention)
+_FROZEN_BF16 = os.environ.get("D2S_FROZEN_BF16", "1") != "0"   # A/B switch: cached bf16 copy of a frozen teacher under bf16 autocast
 _FUSED_ADD_LN_TRAIN = os.environ.get("D2S_FUSED_ADD_LN_TRAIN", "1") != "0"   # A/B switch: residual adds folded into LayerNorm fwd/bwd
 _FUSED_MLP = os.environ.get("D2S_FUSED_MLP", "1") != "0"      # A/B switch for the one-kernel MLP (ops.mlp_residual_ln)
 _FUSED_PAIR = os.environ.get("D2S_FUSED_PAIR", "1") != "0"  # A/B switch for the CTA-pair GEMMs (fc1 pair; proj/fc2 + add + LN)
@@ -607,9 +610,36 @@ def variant_b_forward_cls_attn(model, img):
     return final
 
 
+_SHADOWS = weakref.WeakKeyDictionary()      # frozen fp32 model -> (weights fingerprint, bf16 copy)
+
+
+def _frozen_bf16_shadow(model, img):
+    """A frozen eval model called under bf16 autocast (the distillation teacher of ddp_training.py:77-81 / train.py:40-42)
+    computes in bf16 anyway -- through a cast of every fp32 weight and bias on every call and, here, through the unfused
+    fallbacks, because the fused inference kernels take bf16 weights.  Its weights cannot change between steps, so a bf16 copy
+    is kept and the call runs on the fused inference path.  The copy is rebuilt when any parameter's storage or version counter
+    changes (load_state_dict, .to(), in-place edits).  Returns None when this does not apply."""
+    if not (_FROZEN_BF16 and img.is_cuda and not model.training and torch.is_autocast_enabled("cuda")
+            and torch.get_autocast_dtype("cuda") == torch.bfloat16):
+        return None
+    params = list(model.parameters())
+    if not params or any(p.requires_grad or p.dtype != torch.float32 or not p.is_cuda for p in params):
+        return None
+    fp = hash(tuple((p.data_ptr(), p._version) for p in params))
+    hit = _SHADOWS.get(model)
+    if hit is None or hit[0] != fp:
+        hit = (fp, copy.deepcopy(model).to(torch.bfloat16).eval())
+        _SHADOWS[model] = hit
+    return hit[1]
+
+
 def teacher_forward(model, img, with_cls_attn=True):
     """VisionTransformerTeacher.forward (dynamic_vit.py:1150-1176) / DefaultVisionTransformerTeacher.forward
     (default_dynamic_vit.py:581-598, with_cls_attn=False)."""
+    shadow = _frozen_bf16_shadow(model, img)
+    if shadow is not None:
+        with torch.no_grad():
+            return teacher_forward(shadow, img.to(torch.bfloat16), with_cls_attn)
     st = _Stream(_embed(model, img))
     rows = []
     for blk in model.blocks:

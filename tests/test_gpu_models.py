@@ -334,6 +334,34 @@ def test_training_fusions_match_the_unfused_training_path(d2s, cuda_dev, monkeyp
         assert float((a - b).abs().max()) <= 5e-2 * float(b.abs().max()) + 1e-5, k
 
 
+def test_frozen_teacher_under_autocast_runs_on_a_cached_bf16_copy(d2s, cuda_dev, monkeypatch):
+    """A frozen fp32 teacher called under bf16 autocast goes through a cached bf16 copy on the fused inference path: same
+    outputs (bf16 accuracy) as the per-call-cast path, the copy is reused between calls and rebuilt when a weight changes."""
+    kw = dict(patch_size=16, embed_dim=384, depth=3, num_heads=6, num_classes=16, mlp_ratio=4, qkv_bias=True)
+    t = d2s.variant_b.VisionTransformerTeacher(**kw)
+    t.load_state_dict(fx.seeded_state_dict({k: tuple(v.shape) for k, v in t.state_dict().items()}, 77))
+    t = t.to(cuda_dev).eval()
+    for p in t.parameters():
+        p.requires_grad_(False)
+    x = fx.randn(78, 3, 3, 224, 224).to(cuda_dev)
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        cls1, tok1, ca1 = t(x)
+        shadow = d2s.engine._SHADOWS[t][1]
+        cls2, _, _ = t(x)
+        assert d2s.engine._SHADOWS[t][1] is shadow and torch.equal(cls1, cls2)          # reused
+        monkeypatch.setattr(d2s.engine, "_FROZEN_BF16", False)
+        cls0, tok0, ca0 = t(x)                                                            # per-call casts, unfused fallbacks
+        monkeypatch.setattr(d2s.engine, "_FROZEN_BF16", True)
+        for a, b in ((cls1, cls0), (tok1, tok0), (ca1, ca0)):
+            assert float((a.float() - b.float()).abs().max()) < 3e-2 * float(b.float().abs().max())
+        t.head.weight.mul_(2.0)                                                           # in-place edit: version counter moves
+        cls3, _, _ = t(x)
+        assert d2s.engine._SHADOWS[t][1] is not shadow
+        assert float((cls3.float() - cls1.float()).abs().max()) > 0.1 * float(cls1.float().abs().max())
+    with torch.no_grad():                                                                 # no autocast: the fp32 model itself
+        assert t(x)[0].dtype == torch.float32
+
+
 def test_fused_path_keeps_the_reference_token_sets_when_margins_allow(d2s, cuda_dev):
     """At keep ratio 0.7 the bf16 fused path must select the oracle's token sets wherever the fp32 score margin at the cut is
     larger than bf16 noise (SURVEY hard part 1); images with a near-tie at the cut are excluded, not tolerated silently."""
