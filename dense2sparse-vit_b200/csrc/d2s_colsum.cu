@@ -1,0 +1,72 @@
+// Column sums of a bf16 matrix: out[n] = sum_m dy[m, n] in fp32 -- the bias gradient of a Linear layer (training path).
+// torch.autograd's reduction runs at ~2.9 TB/s on these shapes and cuBLASLt's bias-gradient epilogue kernel at ~1.9 TB/s; this
+// is a plain HBM stream: a thread owns 8 consecutive columns (one 16-byte vector per row), blockDim.y row slots walk the CTA's
+// row block with four rows in flight per thread, partial sums meet in shared memory and leave as one atomicAdd per column per CTA.
+#include "d2s_common.cuh"
+
+namespace d2s {
+
+__global__ void __launch_bounds__(1024)
+colsum_bf16_kernel(const __nv_bfloat16* __restrict__ dy, long long M, int N, int rows_per_cta, float* __restrict__ out) {
+  extern __shared__ float cs_red[];   // blockDim.y x N
+  const int tx = threadIdx.x, ty = threadIdx.y, ny = blockDim.y;
+  const long long row0 = (long long)blockIdx.x * rows_per_cta;
+  const long long row_end = min(M, row0 + rows_per_cta);
+  float acc[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) acc[q] = 0.f;
+  auto add = [&](const int4& v) {
+    const uint32_t w[4] = {(uint32_t)v.x, (uint32_t)v.y, (uint32_t)v.z, (uint32_t)v.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      acc[2 * q] += __uint_as_float(w[q] << 16);
+      acc[2 * q + 1] += __uint_as_float(w[q] & 0xffff0000u);
+    }
+  };
+  const __nv_bfloat16* base = dy + (size_t)tx * 8;
+  long long r = row0 + ty;
+  for (; r + 3 * ny < row_end; r += 4 * ny) {
+    const int4 a = ld_stream16(base + (size_t)r * N);
+    const int4 b = ld_stream16(base + (size_t)(r + ny) * N);
+    const int4 c = ld_stream16(base + (size_t)(r + 2 * ny) * N);
+    const int4 d = ld_stream16(base + (size_t)(r + 3 * ny) * N);
+    add(a); add(b); add(c); add(d);
+  }
+  for (; r < row_end; r += ny) add(ld_stream16(base + (size_t)r * N));
+  float* mine = cs_red + (size_t)ty * N + tx * 8;
+  *reinterpret_cast<float4*>(mine) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+  *reinterpret_cast<float4*>(mine + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+  __syncthreads();
+  for (int c = ty * blockDim.x + tx; c < N; c += ny * blockDim.x) {
+    float s = 0.f;
+    for (int y = 0; y < ny; ++y) s += cs_red[(size_t)y * N + c];
+    atomicAdd(out + c, s);
+  }
+}
+
+}  // namespace d2s
+
+using namespace d2s;
+
+extern "C" int d2s_colsum_bf16(const void* dy, long long M, int N, float* out, d2s_stream_t stream) {
+  D2S_REQUIRE(dy && out, D2S_ERR_ARG, "colsum: null pointer");
+  D2S_REQUIRE(M >= 0 && N >= 8 && N % 8 == 0 && N <= 8192, D2S_ERR_ARG, "colsum: bad shape M=%lld N=%d (N %% 8 == 0, N <= 8192)", M, N);
+  D2S_REQUIRE(aligned16(dy), D2S_ERR_ALIGN, "colsum: dy must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = cudaMemsetAsync(out, 0, (size_t)N * sizeof(float), st);
+  D2S_REQUIRE(e == cudaSuccess, D2S_ERR_CUDA, "colsum: memset: %s", cudaGetErrorString(e));
+  if (M == 0) return D2S_OK;
+  const int nx = N / 8;
+  int ny = 1024 / nx;                      // row slots per CTA
+  if (ny > 8) ny = 8;
+  if (ny < 1) ny = 1;
+  const size_t smem = (size_t)ny * N * sizeof(float);
+  D2S_REQUIRE(smem <= 48 * 1024, D2S_ERR_ARG, "colsum: N=%d too wide", N);
+  // ~4 CTAs per SM worth of row blocks, each at least one full unrolled pass
+  long long rows_per_cta = (M + 4LL * kNumSMs - 1) / (4LL * kNumSMs);
+  if (rows_per_cta < 4LL * ny) rows_per_cta = 4LL * ny;
+  const long long grid = (M + rows_per_cta - 1) / rows_per_cta;
+  colsum_bf16_kernel<<<(unsigned)grid, dim3(nx, ny), smem, st>>>((const __nv_bfloat16*)dy, M, N, (int)rows_per_cta, out);
+  count_launch();
+  return check_launch("d2s_colsum_bf16");
+}

@@ -272,7 +272,8 @@ def softmax_with_policy(attn, policy, eps=1e-6):
     return _SoftmaxPolicy.apply(attn, policy, eps)
 
 
-_FUSED_WGRAD = os.environ.get("D2S_FUSED_WGRAD", "1") != "0"   # A/B switch for the fused weight + bias gradient GEMM
+_FUSED_WGRAD = os.environ.get("D2S_FUSED_WGRAD", "1") != "0"   # A/B switch for ops.linear_train (d2s bias gradient)
+_WGRAD_LT = os.environ.get("D2S_WGRAD", "colsum") == "lt"       # dW + db in one cuBLASLt call instead of GEMM + d2s column sum
 
 
 def linear_wgrad(dy, x, want_bias=True):
@@ -292,31 +293,54 @@ def linear_wgrad(dy, x, want_bias=True):
     return dw, db
 
 
+def colsum(dy):
+    """Column sums of a bf16 matrix (M,N) in fp32 (`d2s_colsum_bf16`): the bias gradient of a Linear layer."""
+    _check_cuda(dy)
+    if dy.dtype != torch.bfloat16 or dy.dim() != 2:
+        raise RuntimeError("colsum: a 2-D bf16 tensor is expected")
+    dy = dy.contiguous()
+    if dy.shape[0] == 0:
+        return torch.zeros(dy.shape[1], dtype=torch.float32, device=dy.device)
+    out = torch.empty(dy.shape[1], dtype=torch.float32, device=dy.device)
+    _lib.call("d2s_colsum_bf16", _ptr(dy), dy.shape[0], dy.shape[1], _ptr(out), _stream())
+    return out
+
+
 class _LinearTrain(torch.autograd.Function):
-    """nn.Linear on the bf16 training path.  Forward is the library GEMM torch would run; backward computes dx with a library
-    GEMM and (dw, db) with `linear_wgrad` -- torch.autograd's separate column reduction of dy for the bias gradient (one more
-    pass over dy per Linear: 61 launches, 3.7 ms of the 34 ms DeiT-S step) disappears into the dw GEMM's epilogue."""
+    """nn.Linear on the bf16 training path (fp32 master weights under bf16 autocast, or a bf16 module).  Forward is the library
+    GEMM torch would run on the bf16 casts; backward computes dx and dW with library GEMMs and the bias gradient with the d2s
+    column-sum kernel in fp32 (`_WGRAD_LT`: dW and db in one cuBLASLt call with the bias-gradient epilogue instead) --
+    torch.autograd's own column reduction of dy (61 launches, 3.7 ms of a 34 ms DeiT-S step) and the bf16 -> fp32 round trip of
+    the bias gradient disappear."""
 
     @staticmethod
-    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.bfloat16)
     def forward(ctx, x, w, b):
-        ctx.save_for_backward(x, w)
-        ctx.has_bias = b is not None
-        return F.linear(x, w, b)
+        xb, wb = x.to(torch.bfloat16), w.to(torch.bfloat16)
+        bb = None if b is None else b.to(torch.bfloat16)
+        ctx.save_for_backward(xb, wb)
+        ctx.meta = (x.dtype, w.dtype, None if b is None else b.dtype)
+        return F.linear(xb, wb, bb)
 
     @staticmethod
-    @torch.amp.custom_bwd(device_type="cuda")
     def backward(ctx, gy):
-        x, w = ctx.saved_tensors
-        N, K = w.shape
+        xb, wb = ctx.saved_tensors
+        xd, wd, bd = ctx.meta
+        N, K = wb.shape
         gy2 = gy.reshape(-1, N)
-        if not gy2.is_contiguous():
-            gy2 = gy2.contiguous()
-        gx = (gy2 @ w).view(x.shape) if ctx.needs_input_grad[0] else None
+        if gy2.dtype != torch.bfloat16 or not gy2.is_contiguous():
+            gy2 = gy2.to(torch.bfloat16).contiguous()
+        gx = (gy2 @ wb).view(xb.shape).to(xd) if ctx.needs_input_grad[0] else None
         gw = gb = None
-        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
-            gw, gb = linear_wgrad(gy2, x.reshape(-1, K), want_bias=ctx.has_bias and ctx.needs_input_grad[2])
-        return gx, gw, gb
+        want_b = bd is not None and ctx.needs_input_grad[2]
+        if _WGRAD_LT:
+            if ctx.needs_input_grad[1] or want_b:
+                gw, gb = linear_wgrad(gy2, xb.reshape(-1, K), want_bias=want_b)
+        else:
+            if ctx.needs_input_grad[1]:
+                gw = gy2.t() @ xb.reshape(-1, K)
+            if want_b:
+                gb = colsum(gy2)
+        return gx, None if gw is None else gw.to(wd), None if gb is None else gb.to(bd)
 
 
 def linear_train(lin, x):

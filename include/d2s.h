@@ -146,6 +146,10 @@ int d2s_softmax_policy_bwd_ld(const void* attn, const float* policy, const void*
 int d2s_split_heads_bf16(const void* src, int B, int T, int Tp, int G, int H, int hd, void* dst, d2s_stream_t stream);
 int d2s_merge_heads_bf16(const void* src, int B, int T, int Tp, int G, int H, int hd, void* dst, d2s_stream_t stream);
 
+/* Column sums of a bf16 matrix in fp32: out[n] = sum_m dy[m, n] (out is overwritten): the bias gradient of an nn.Linear
+ * under autograd (dynamic_vit.py:159-236).  N % 8 == 0, N <= 8192. */
+int d2s_colsum_bf16(const void* dy, long long M, int N, float* out, d2s_stream_t stream);
+
 /* Weight and bias gradient of a Linear layer (nn.Linear of Attention / Mlp / PredictorLG under autograd, dynamic_vit.py:159-236),
  * bf16: dw (N,K) = dy^T x, db (N) = column sums of dy (NULL: not wanted), from dy (M,N) and x (M,K).  ONE cuBLASLt GEMM with the
  * bias-gradient epilogue instead of torch.autograd's GEMM + separate column reduction.  N % 8 == 0, K % 8 == 0. */

@@ -752,6 +752,16 @@ def test_linear_wgrad_matches_autograd(ops, M, N, K):
     assert float((dw2.cpu().float() - rw).abs().max()) <= 8e-3 * float(rw.abs().max()) + 1e-3
 
 
+@pytest.mark.parametrize("M,N", [(50432, 1536), (50432, 384), (197 * 7, 1152), (3, 8), (1, 2048), (0, 384)])
+def test_colsum_matches_fp32_sum(ops, M, N):
+    """d2s_colsum_bf16: fp32 column sums of a bf16 matrix (a Linear layer's bias gradient)."""
+    dy = (fx.randn(820 + N, max(M, 1), N) * 0.5).bfloat16()[:M]
+    out = ops.colsum(cu(dy))
+    ref = dy.double().sum(0)
+    assert out.dtype == torch.float32 and out.shape == (N,)
+    assert float((out.cpu().double() - ref).abs().max()) <= 2e-5 * float(dy.double().abs().sum(0).max()) + 1e-6
+
+
 def test_linear_train_matches_module_under_autocast(ops):
     """ops.linear_train(lin, x) == lin(x) in value and in every gradient, fp32 master weights under bf16 autocast."""
     lin = torch.nn.Linear(384, 1152).cuda()
