@@ -14,7 +14,6 @@
 namespace d2s {
 
 constexpr int kLnThreads = 256;
-constexpr int kLnRowsPerCta = kLnThreads / 16;
 
 template <typename T_> struct LnVec;
 template <> struct LnVec<__nv_bfloat16> {
@@ -49,22 +48,24 @@ template <> struct LnVec<float> {
   __device__ static float round(float f) { return f; }
 };
 
-__device__ __forceinline__ float half_warp_sum(float v) {
+template <int kLPR>
+__device__ __forceinline__ float row_lanes_sum(float v) {
 #pragma unroll
-  for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  for (int o = kLPR / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
 
-// kVPL: 16-byte vectors per lane (D <= 16 * kVPL * elems-per-vector)
-template <typename T_, int kVPL>
+// kLPR lanes per row (16: two rows per warp; 32 for wide rows -- at 12 vectors per lane the 1536-wide predictor LayerNorm ran at
+// 2.6 TB/s), kVPL 16-byte vectors per lane (D <= kLPR * kVPL * elems-per-vector)
+template <typename T_, int kVPL, int kLPR>
 __global__ void __launch_bounds__(kLnThreads)
 add_layernorm_kernel(const T_* __restrict__ x, const T_* __restrict__ y, const T_* __restrict__ gamma,
                      const T_* __restrict__ beta, long long rows, int T, int D, long long x_stride_b, long long x_stride_t,
                      float eps, int norm_row0, T_* __restrict__ out_sum, T_* __restrict__ out_norm,
                      const int64_t* __restrict__ gather_idx) {
   constexpr int VE = LnVec<T_>::kElems;
-  const int sub = threadIdx.x & 15;
-  const long long row = (long long)blockIdx.x * kLnRowsPerCta + (threadIdx.x >> 4);
+  const int sub = threadIdx.x & (kLPR - 1);
+  const long long row = (long long)blockIdx.x * (kLnThreads / kLPR) + threadIdx.x / kLPR;
   const bool row_ok = row < rows;
   const int nvec = D / VE;
   const long long b = row_ok ? row / T : 0;
@@ -78,7 +79,7 @@ add_layernorm_kernel(const T_* __restrict__ x, const T_* __restrict__ y, const T
   float sum = 0.f;
 #pragma unroll
   for (int k = 0; k < kVPL; ++k) {
-    const int vi = sub + 16 * k;
+    const int vi = sub + kLPR * k;
     if (row_ok && vi < nvec) {
       const int4 rx = *reinterpret_cast<const int4*>(xr + (size_t)vi * VE);
       LnVec<T_>::unpack(rx, v[k]);
@@ -99,15 +100,15 @@ add_layernorm_kernel(const T_* __restrict__ x, const T_* __restrict__ y, const T
   if (out_sum && row_ok) {
 #pragma unroll
     for (int k = 0; k < kVPL; ++k) {
-      const int vi = sub + 16 * k;
+      const int vi = sub + kLPR * k;
       if (vi < nvec) *reinterpret_cast<int4*>(out_sum + row * D + (size_t)vi * VE) = LnVec<T_>::pack(v[k]);
     }
   }
-  const float mean = half_warp_sum(sum) / (float)D;
+  const float mean = row_lanes_sum<kLPR>(sum) / (float)D;
   float var = 0.f;
 #pragma unroll
   for (int k = 0; k < kVPL; ++k) {
-    const int vi = sub + 16 * k;
+    const int vi = sub + kLPR * k;
     if (vi < nvec) {
 #pragma unroll
       for (int q = 0; q < VE; ++q) {
@@ -116,12 +117,12 @@ add_layernorm_kernel(const T_* __restrict__ x, const T_* __restrict__ y, const T
       }
     }
   }
-  const float rstd = rsqrtf(half_warp_sum(var) / (float)D + eps);
+  const float rstd = rsqrtf(row_lanes_sum<kLPR>(var) / (float)D + eps);
   if (!row_ok || t < norm_row0) return;
   T_* hr = out_norm + (b * (T - norm_row0) + (t - norm_row0)) * (long long)D;
 #pragma unroll
   for (int k = 0; k < kVPL; ++k) {
-    const int vi = sub + 16 * k;
+    const int vi = sub + kLPR * k;
     if (vi < nvec) {
       float g[8], bt[8], o[8];
       LnVec<T_>::unpack(*reinterpret_cast<const int4*>(gamma + (size_t)vi * VE), g);
@@ -141,15 +142,14 @@ static int launch_ln(const void* x, const void* y, const void* gamma, const void
   const long long rows = (long long)B * T;
   const int nvec = D / VE;
   const int vpl = ceil_div(nvec, 16);
-  const unsigned grid = (unsigned)((rows + kLnRowsPerCta - 1) / kLnRowsPerCta);
-#define D2S_LN_LAUNCH(V)                                                                                              \
-  add_layernorm_kernel<T_, V><<<grid, kLnThreads, 0, stream>>>((const T_*)x, (const T_*)y, (const T_*)gamma,           \
-                                                               (const T_*)beta, rows, T, D, sb, st, eps, norm_row0,    \
-                                                               (T_*)out_sum, (T_*)out_norm, gather_idx)
-  if (vpl <= 2) D2S_LN_LAUNCH(2);
-  else if (vpl <= 3) D2S_LN_LAUNCH(3);
-  else if (vpl <= 6) D2S_LN_LAUNCH(6);
-  else D2S_LN_LAUNCH(12);
+#define D2S_LN_LAUNCH(V, L)                                                                                            \
+  add_layernorm_kernel<T_, V, L><<<(unsigned)((rows + kLnThreads / L - 1) / (kLnThreads / L)), kLnThreads, 0, stream>>>(  \
+      (const T_*)x, (const T_*)y, (const T_*)gamma, (const T_*)beta, rows, T, D, sb, st, eps, norm_row0, (T_*)out_sum,     \
+      (T_*)out_norm, gather_idx)
+  if (vpl <= 2) D2S_LN_LAUNCH(2, 16);
+  else if (vpl <= 3) D2S_LN_LAUNCH(3, 16);
+  else if (vpl <= 6) D2S_LN_LAUNCH(3, 32);
+  else D2S_LN_LAUNCH(6, 32);
 #undef D2S_LN_LAUNCH
   count_launch();
   return check_launch("d2s_add_layernorm");

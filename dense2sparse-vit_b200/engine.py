@@ -393,7 +393,7 @@ def _linear_act(x, lin, act):
     """act(lin(x)): the tcgen05 GEMM with the activation in its epilogue when the shape allows, else cuBLAS + in-place act."""
     if (x.dtype == torch.bfloat16 and lin.weight.dtype == torch.bfloat16 and lin.out_features % 256 == 0
             and lin.out_features <= 4096 and lin.in_features % 64 == 0):
-        return ops.linear_act(x, lin.weight, lin.bias, act)
+        return ops.linear_act(x, lin.weight, lin.bias, act, pair=_FUSED_PAIR)
     u = lin(x)
     return ops.bias_act_(u, None, act)
 
