@@ -33,13 +33,15 @@ class DistillDiffPruningLoss(torch.nn.Module):
             cls_t, token_t = self.teacher_model(inputs)[:2]
         cls_kl = F.kl_div(F.log_softmax(pred.float(), dim=-1), F.log_softmax(cls_t.float(), dim=-1),
                           reduction="batchmean", log_target=True)
+        # token distillation over the KEPT tokens: KL(teacher || student) per token row, "batchmean" over the kept rows.  Written
+        # as a masked mean over all rows (same value as indexing the kept rows first) so that every shape is static: no boolean
+        # indexing, no host synchronisation -- the whole training step can be captured in a CUDA graph (runner.TrainStepRunner).
         B, N, C = token_pred.shape
-        keep = mask.reshape(B * N) > 0.5
-        tp, tt = token_pred.reshape(B * N, C)[keep].float(), token_t.reshape(B * N, C)[keep].float()
-        if tp.shape[0] == 0:
-            token_kl = token_pred.new_zeros(())
-        else:
-            token_kl = F.kl_div(F.log_softmax(tp, dim=-1), F.log_softmax(tt, dim=-1), reduction="batchmean", log_target=True)
+        keep = (mask.reshape(B * N) > 0.5).float()
+        lp = F.log_softmax(token_pred.reshape(B * N, C).float(), dim=-1)
+        lt = F.log_softmax(token_t.reshape(B * N, C).float(), dim=-1)
+        kl_rows = (lt.exp() * (lt - lp)).sum(dim=-1)
+        token_kl = (kl_rows * keep).sum() / keep.sum().clamp_min(1.0)
         loss = (self.clf_weight * cls_loss + self.ratio_weight * ratio_loss / max(1, len(out_pred_score))
                 + self.distill_weight * (cls_kl + token_kl))
         return loss, dict(cls=cls_loss.detach(), ratio=torch.as_tensor(ratio_loss).detach(), cls_kl=cls_kl.detach(),

@@ -23,6 +23,7 @@ ap.add_argument("--steps", type=int, default=10)
 ap.add_argument("--warmup", type=int, default=3)
 ap.add_argument("--variant", default="a", choices=["a", "b"],
                 help="a: DynamicViT (3 stages, Gumbel decisions, DistillDiffPruningLoss); b: Dense2Sparse (1 stage @3, top-k, MaskLoss + BackboneLoss, train.py:40-53)")
+ap.add_argument("--graph", action="store_true", help="capture the whole step (forward, loss, backward, AdamW) in a CUDA graph (Variant A, one GPU)")
 ap.add_argument("--freeze-backbone", action="store_true", help="train the predictors only (mask_predictor.py:219-225)")
 args = ap.parse_args()
 pkg = d2s.pkg
@@ -55,7 +56,8 @@ else:
                                                              device=dev), "train")
     backbone_loss_fn = pkg.losses.BackboneLoss(types.SimpleNamespace(mixup=0.0, patch_score_threshold=None))
 metrics = {}
-opt = torch.optim.AdamW([p for p in student.parameters() if p.requires_grad], lr=5e-4, weight_decay=0.05)
+use_graph = args.graph and args.variant == "a" and world == 1
+opt = torch.optim.AdamW([p for p in student.parameters() if p.requires_grad], lr=5e-4, weight_decay=0.05, capturable=use_graph)
 g = torch.Generator(device=dev).manual_seed(42 + rank)
 x = torch.randn(args.batch, 3, 224, 224, device=dev, generator=g)
 y = torch.randint(0, 1000, (args.batch,), device=dev, generator=g)
@@ -77,6 +79,13 @@ def step():
     opt.step()
     return loss
 
+
+if use_graph:
+    def fwd_loss(xx, yy):
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            return crit(xx, model(xx), yy)[0]
+    graphed = pkg.runner.TrainStepRunner(fwd_loss, opt, x, y, warmup=max(1, args.warmup))
+    step = graphed
 
 n0 = pkg._lib.launch_count()
 for _ in range(args.warmup):
@@ -108,6 +117,6 @@ if rank == 0:
                       "d2s_launches_per_step": int(per_step),
                       "config": {"workload": "student fwd+bwd + frozen teacher fwd + AdamW, " + ("ratio/distill losses" if args.variant == "a" else "MaskLoss(kl_div) + BackboneLoss"),
                                  "batch_per_gpu": args.batch, "freeze_backbone": args.freeze_backbone,
-                                 "parallelism": f"DDP x{world} (NCCL gradient all-reduce)" if world > 1 else "single GPU"}}))
+                                 "parallelism": f"DDP x{world} (NCCL gradient all-reduce)" if world > 1 else "single GPU", "cuda_graph": bool(use_graph)}}))
 if world > 1:
     dist.destroy_process_group()

@@ -213,3 +213,31 @@ def test_bench_reference_arm_contract_two_ranks():
         assert k in out, k
     assert out["impl"] == "reference" and out["n_gpus"] == 2 and out["value"] > 0
     assert out["cpu_baseline"]["kind"] == "port" and out["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_distill_loss_masked_token_term_equals_indexing_the_kept_rows(d2s):
+    """DistillDiffPruningLoss computes the kept-token KL as a masked mean (static shapes, CUDA-graph friendly); it must equal
+    the boolean-indexing form, including the all-dropped case."""
+    import torch
+    import torch.nn.functional as F
+    torch.manual_seed(5)
+    B, N, C, K = 3, 12, 16, 10
+
+    class Teacher(torch.nn.Module):
+        def forward(self, x):
+            g = torch.Generator().manual_seed(9)
+            return torch.randn(B, K, generator=g), torch.randn(B, N, C, generator=g)
+
+    crit = d2s.losses.DistillDiffPruningLoss(Teacher(), keep_ratio=[0.7, 0.49, 0.343])
+    pred, tok = torch.randn(B, K), torch.randn(B, N, C)
+    scores = [torch.rand(B, N) for _ in range(3)]
+    labels = torch.randint(0, K, (B,))
+    for mask in ((torch.rand(B, N, 1) > 0.5).float(), torch.zeros(B, N, 1)):
+        loss, parts = crit(torch.zeros(B, 3, 8, 8), (pred, tok, mask, scores), labels)
+        keep = mask.reshape(B * N) > 0.5
+        _, tt = Teacher()(None)
+        tp_k, tt_k = tok.reshape(B * N, C)[keep], tt.reshape(B * N, C)[keep]
+        ref = tok.new_zeros(()) if tp_k.shape[0] == 0 else F.kl_div(F.log_softmax(tp_k, -1), F.log_softmax(tt_k, -1),
+                                                                     reduction="batchmean", log_target=True)
+        torch.testing.assert_close(parts["token_kl"], ref, rtol=1e-5, atol=1e-6)
+        assert torch.isfinite(loss)

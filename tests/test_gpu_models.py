@@ -362,6 +362,36 @@ def test_frozen_teacher_under_autocast_runs_on_a_cached_bf16_copy(d2s, cuda_dev,
         assert t(x)[0].dtype == torch.float32
 
 
+def test_graphed_training_step_matches_eager(d2s, cuda_dev):
+    """runner.TrainStepRunner: forward + DistillDiffPruningLoss + backward + AdamW captured in one CUDA graph follows the same
+    loss trajectory as the eager step (same weights, inputs and injected Gumbel noise)."""
+    import copy
+    x = fx.randn(50, 4, 3, 224, 224).to(cuda_dev)
+    y = torch.tensor([1, 5, 7, 3], device=cuda_dev)
+    base, _ = _deit_s_width_models(d2s, cuda_dev, "a", [0.7, 0.49])
+    teacher = d2s.variant_a.DefaultVisionTransformerTeacher(patch_size=16, embed_dim=384, depth=2, num_heads=6, num_classes=16,
+                                                            mlp_ratio=4, qkv_bias=True).to(cuda_dev).eval()
+    for p in teacher.parameters():
+        p.requires_grad_(False)
+    gumbels = [fx.randn(51 + i, 4, 196, 2).to(cuda_dev) for i in range(2)]
+    losses = {}
+    for mode in ("eager", "graph"):
+        m = copy.deepcopy(base).train()
+        m._d2s_gumbels = gumbels
+        crit = d2s.losses.DistillDiffPruningLoss(teacher, keep_ratio=[0.7, 0.49])
+        opt = torch.optim.AdamW(m.parameters(), lr=1e-4, weight_decay=0.05, capturable=True)
+
+        def fwd_loss(xx, yy, m=m, crit=crit):
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                return crit(xx, m(xx), yy)[0]
+        run = d2s.runner.TrainStepRunner(fwd_loss, opt, x, y, warmup=2, use_graph=mode == "graph")
+        assert (run.graph is not None) == (mode == "graph")
+        losses[mode] = [float(run()) for _ in range(4)]
+    for a, b in zip(losses["eager"], losses["graph"]):
+        assert abs(a - b) <= 2e-2 * abs(a) + 1e-3, losses
+    assert losses["graph"][-1] != losses["graph"][0]          # the replays really update the weights
+
+
 def test_fused_path_keeps_the_reference_token_sets_when_margins_allow(d2s, cuda_dev):
     """At keep ratio 0.7 the bf16 fused path must select the oracle's token sets wherever the fp32 score margin at the cut is
     larger than bf16 noise (SURVEY hard part 1); images with a near-tie at the cut are excluded, not tolerated silently."""
