@@ -84,13 +84,15 @@ if use_graph:
     def fwd_loss(xx, yy):
         with torch.autocast("cuda", dtype=torch.bfloat16):
             return crit(xx, model(xx), yy)[0]
+    n_cap = pkg._lib.launch_count()
     graphed = pkg.runner.TrainStepRunner(fwd_loss, opt, x, y, warmup=max(1, args.warmup))
+    per_step_captured = (pkg._lib.launch_count() - n_cap) // (max(1, args.warmup) + 1)   # eager warm-ups + the capture pass
     step = graphed
 
 n0 = pkg._lib.launch_count()
 for _ in range(args.warmup):
     loss = step()
-per_step = (pkg._lib.launch_count() - n0) // max(1, args.warmup)
+per_step = per_step_captured if use_graph else (pkg._lib.launch_count() - n0) // max(1, args.warmup)
 if world > 1:
     dist.barrier()
 torch.cuda.synchronize()
