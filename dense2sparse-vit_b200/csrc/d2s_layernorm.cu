@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(kLnThreads)
 add_layernorm_kernel(const T_* __restrict__ x, const T_* __restrict__ y, const T_* __restrict__ gamma,
                      const T_* __restrict__ beta, long long rows, int T, int D, long long x_stride_b, long long x_stride_t,
                      float eps, int norm_row0, T_* __restrict__ out_sum, T_* __restrict__ out_norm,
-                     const int64_t* __restrict__ gather_idx) {
+                     const int64_t* __restrict__ gather_idx, const T_* __restrict__ cls_row) {
   constexpr int VE = LnVec<T_>::kElems;
   const int sub = threadIdx.x & (kLPR - 1);
   const long long row = (long long)blockIdx.x * (kLnThreads / kLPR) + threadIdx.x / kLPR;
@@ -72,8 +72,10 @@ add_layernorm_kernel(const T_* __restrict__ x, const T_* __restrict__ y, const T
   const int t = row_ok ? (int)(row - b * T) : 0;
   // gather mode (d2s_gather_layernorm): output token 0 is the CLS row, token t >= 1 is input token idx[b, t-1] + 1
   const long long src_t = (gather_idx && row_ok && t > 0) ? gather_idx[b * (T - 1) + (t - 1)] + 1 : (long long)t;
-  const T_* xr = x + b * x_stride_b + src_t * x_stride_t;
-  const T_* yr = y ? y + row * D : nullptr;
+  // assemble mode (d2s_assemble_layernorm, cls_row != NULL): token 0 is the class token, token t >= 1 is patch t-1 of x, and
+  // y is the position embedding, one row per TOKEN shared by all images
+  const T_* xr = (cls_row && t == 0) ? cls_row : x + b * x_stride_b + (src_t - (cls_row ? 1 : 0)) * x_stride_t;
+  const T_* yr = y ? y + (cls_row ? (long long)t : row) * D : nullptr;
 
   float v[kVPL][8];
   float sum = 0.f;
@@ -137,7 +139,7 @@ add_layernorm_kernel(const T_* __restrict__ x, const T_* __restrict__ y, const T
 template <typename T_>
 static int launch_ln(const void* x, const void* y, const void* gamma, const void* beta, int B, int T, int D,
                      long long sb, long long st, float eps, int norm_row0, void* out_sum, void* out_norm, cudaStream_t stream,
-                     const int64_t* gather_idx = nullptr) {
+                     const int64_t* gather_idx = nullptr, const void* cls_row = nullptr) {
   constexpr int VE = LnVec<T_>::kElems;
   const long long rows = (long long)B * T;
   const int nvec = D / VE;
@@ -145,7 +147,7 @@ static int launch_ln(const void* x, const void* y, const void* gamma, const void
 #define D2S_LN_LAUNCH(V, L)                                                                                            \
   add_layernorm_kernel<T_, V, L><<<(unsigned)((rows + kLnThreads / L - 1) / (kLnThreads / L)), kLnThreads, 0, stream>>>(  \
       (const T_*)x, (const T_*)y, (const T_*)gamma, (const T_*)beta, rows, T, D, sb, st, eps, norm_row0, (T_*)out_sum,     \
-      (T_*)out_norm, gather_idx)
+      (T_*)out_norm, gather_idx, (const T_*)cls_row)
   if (vpl <= 2) D2S_LN_LAUNCH(2, 16);
   else if (vpl <= 3) D2S_LN_LAUNCH(3, 16);
   else if (vpl <= 6) D2S_LN_LAUNCH(3, 32);
@@ -202,4 +204,26 @@ extern "C" int d2s_gather_layernorm(const void* x, const int64_t* idx, const voi
              ? launch_ln<__nv_bfloat16>(x, nullptr, gamma, beta, B, K + 1, D, sb, st, eps, 0, out_sum, out_norm, (cudaStream_t)stream, K ? idx : nullptr)
              : launch_ln<float>(x, nullptr, gamma, beta, B, K + 1, D, sb, st, eps, 0, out_sum, out_norm, (cudaStream_t)stream,
                                 K ? idx : nullptr);
+}
+
+/* Token assembly fused with the first block's norm1 (dynamic_vit.py:820-823 + Block.forward :263): out_sum (B,N+1,D) =
+ * cat(cls, patches) + pos, out_norm = LayerNorm(out_sum) * gamma + beta.  patches (B,N,D), cls (D), pos (N+1,D). */
+extern "C" int d2s_assemble_layernorm(const void* patches, const void* cls, const void* pos, const void* gamma, const void* beta,
+                                      int dtype, int B, int N, int D, float eps, void* out_sum, void* out_norm,
+                                      d2s_stream_t stream) {
+  D2S_REQUIRE(patches && cls && pos && gamma && beta && out_sum && out_norm, D2S_ERR_ARG, "assemble_layernorm: null pointer");
+  D2S_REQUIRE(dtype == D2S_F32 || dtype == D2S_BF16, D2S_ERR_ARG, "assemble_layernorm: dtype %d unsupported", dtype);
+  D2S_REQUIRE(B >= 0 && N >= 1 && D >= 1, D2S_ERR_ARG, "assemble_layernorm: bad shape B=%d N=%d D=%d", B, N, D);
+  const int ve = dtype == D2S_BF16 ? 8 : 4;
+  D2S_REQUIRE(D % ve == 0 && D / ve <= 16 * 12, D2S_ERR_ARG, "assemble_layernorm: D=%d must be a multiple of %d and at most %d", D,
+              ve, 16 * 12 * ve);
+  D2S_REQUIRE(aligned16(patches) && aligned16(cls) && aligned16(pos) && aligned16(gamma) && aligned16(beta) && aligned16(out_sum) &&
+                  aligned16(out_norm),
+              D2S_ERR_ALIGN, "assemble_layernorm: pointers must be 16-byte aligned");
+  if (B == 0) return D2S_OK;
+  const long long sb = (long long)N * D, st = D;
+  return dtype == D2S_BF16 ? launch_ln<__nv_bfloat16>(patches, pos, gamma, beta, B, N + 1, D, sb, st, eps, 0, out_sum, out_norm,
+                                                      (cudaStream_t)stream, nullptr, cls)
+                           : launch_ln<float>(patches, pos, gamma, beta, B, N + 1, D, sb, st, eps, 0, out_sum, out_norm,
+                                              (cudaStream_t)stream, nullptr, cls);
 }

@@ -170,8 +170,33 @@ class _Stream:
     that the next consumer can run it as ONE kernel with the residual add and its LayerNorm (ops.linear_residual_ln).
     Falls back to plain Block.forward when the fused path does not apply."""
 
-    def __init__(self, x):
-        self.x, self.y, self.lin, self.mlp, self.gidx = x, None, None, None, None
+    def __init__(self, x, asm=None):
+        # asm = (patches, cls_token, pos_embed): the token assembly itself is deferred, so that it runs fused with the first
+        # block's norm1 (ops.assemble_layernorm); any other access to .x materialises it with the plain assembly kernel
+        self._x, self._asm = x, asm
+        self.y, self.lin, self.mlp, self.gidx = None, None, None, None
+
+    @property
+    def x(self):
+        if self._asm is not None:
+            (patches, cls, pos), self._asm = self._asm, None
+            self._x = ops.assemble_tokens(patches, cls, pos)
+        return self._x
+
+    @x.setter
+    def x(self, value):
+        self._x, self._asm = value, None
+
+    def _probe(self):
+        """A tensor with the stream's device / dtype / gradient status, without materialising a deferred assembly."""
+        return self._asm[0] if self._asm is not None else self._x
+
+    @property
+    def shape(self):
+        if self._asm is not None:
+            B, N, D = self._asm[0].shape
+            return torch.Size((B, N + 1, D))
+        return self._x.shape
 
     def gather(self, x, kept):
         """The pruning stage's kept-token gather (default_dynamic_vit.py:464-468, dynamic_vit.py:907-912), deferred so that it
@@ -199,6 +224,10 @@ class _Stream:
 
     def _sum_norm(self, norm, row0=0):
         """(x + branch, norm((x + branch)[:, row0:])); leaves the stream holding the summed x."""
+        if self._asm is not None and row0 == 0 and self.y is None and self.lin is None and self.mlp is None and self.gidx is None:
+            (patches, cls, pos), self._asm = self._asm, None
+            self._x, h = ops.assemble_layernorm(patches, cls, pos, norm.weight, norm.bias, norm.eps)
+            return self._x, h
         if self.gidx is not None:
             if row0 == 0 and self.x.dtype in (torch.float32, torch.bfloat16):
                 (x, kept), self.gidx = (self.x, self.gidx), None
@@ -247,9 +276,9 @@ class _Stream:
     def block(self, blk, policy=None, return_cls_attn=False):
         """Inference form of Block.forward (dynamic_vit.py:263-283): every residual add is folded into the LayerNorm that
         follows it, and the Linear that produced the branch into the same kernel when it can be."""
-        if not _fusable(blk, self.x, policy):
+        if not _fusable(blk, self._probe(), policy):
             self._flush_gather()
-        if _fusable(blk, self.x, policy):
+        if _fusable(blk, self._probe(), policy):
             _, h = self._sum_norm(blk.norm1)
             o, cls_attn = attention_pre_proj(blk.attn, h, policy, return_cls_attn)
             self.lin = (o, blk.attn.proj)
@@ -442,14 +471,18 @@ def predictor_b_forward(m, x, policy=None, current_sigma=0.0005, cls_attn=None, 
 
 
 # ---- model forwards ------------------------------------------------------------------------------------
-def _embed(model, img):
-    x = patch_embed_forward(model.patch_embed, img)
-    B = x.shape[0]
-    if (x.is_cuda and not _needs_grad(x, model.cls_token, model.pos_embed) and isinstance(model.pos_drop, torch.nn.Dropout)
-            and (model.pos_drop.p == 0 or not model.training) and model.pos_embed.shape[1] == x.shape[1] + 1):
-        return ops.assemble_tokens(x, model.cls_token, model.pos_embed)
-    x = torch.cat((model.cls_token.to(x.dtype).expand(B, -1, -1), x), dim=1)
-    return model.pos_drop(x + model.pos_embed.to(x.dtype))
+def _embed_stream(model, img):
+    """The residual stream after patch embedding; on the inference path the token assembly is left pending (fused with the first
+    block's norm1)."""
+    patches = patch_embed_forward(model.patch_embed, img)
+    if (patches.is_cuda and not _needs_grad(patches, model.cls_token, model.pos_embed) and isinstance(model.pos_drop, torch.nn.Dropout)
+            and (model.pos_drop.p == 0 or not model.training) and model.pos_embed.shape[1] == patches.shape[1] + 1
+            and patches.dtype in (torch.float32, torch.bfloat16) and patches.shape[-1] % 8 == 0
+            and patches.shape[-1] <= (1536 if patches.dtype == torch.bfloat16 else 768)):
+        return _Stream(None, asm=(patches, model.cls_token, model.pos_embed))
+    B = patches.shape[0]
+    x = torch.cat((model.cls_token.to(patches.dtype).expand(B, -1, -1), patches), dim=1)
+    return _Stream(model.pos_drop(x + model.pos_embed.to(patches.dtype)))
 
 
 def _head(model, x):
@@ -476,9 +509,9 @@ def _pred_ln(pred):
 def variant_a_forward(model, img):
     """DefaultVisionTransformerDiffPruning.forward (default_dynamic_vit.py:435-487).
     Injected Gumbel noise for parity runs: set model._d2s_gumbels = [tensor (B,196,2) per stage]."""
-    st = _Stream(_embed(model, img))
-    B = st.x.shape[0]
-    dt, dev = st.x.dtype, st.x.device
+    st = _embed_stream(model, img)
+    B = st.shape[0]
+    dt, dev = st._probe().dtype, st._probe().device
     p_count = 0
     out_pred_prob = []
     prev_decision = torch.ones(B, INIT_N, 1, dtype=dt, device=dev)
@@ -531,9 +564,9 @@ def variant_a_forward(model, img):
 
 def variant_b_forward(model, img, stacked_cls_attn_weights=None):
     """VisionTransformerDiffPruning.forward (dynamic_vit.py:814-1015)."""
-    st = _Stream(_embed(model, img))
-    B, T0, D = st.x.shape
-    dt, dev = st.x.dtype, st.x.device
+    st = _embed_stream(model, img)
+    B, T0, D = st.shape
+    dt, dev = st._probe().dtype, st._probe().device
     N = T0 - 1
     p_count = 0
     model.num_kept_tokens = []
@@ -602,7 +635,7 @@ def variant_b_forward(model, img, stacked_cls_attn_weights=None):
 
 def variant_b_forward_cls_attn(model, img):
     """VisionTransformerDiffPruning.forward_cls_attn (dynamic_vit.py:1018-1033)."""
-    st = _Stream(_embed(model, img))
+    st = _embed_stream(model, img)
     final = None
     last = len(model.blocks) - 1
     for i, blk in enumerate(model.blocks):
@@ -640,7 +673,7 @@ def teacher_forward(model, img, with_cls_attn=True):
     if shadow is not None:
         with torch.no_grad():
             return teacher_forward(shadow, img.to(torch.bfloat16), with_cls_attn)
-    st = _Stream(_embed(model, img))
+    st = _embed_stream(model, img)
     rows = []
     for blk in model.blocks:
         ca = st.block(blk, return_cls_attn=with_cls_attn)
@@ -656,7 +689,7 @@ def teacher_forward(model, img, with_cls_attn=True):
 
 def teacher_forward_cls_attention(model, img):
     """VisionTransformerTeacher.forward_cls_attention (dynamic_vit.py:1134-1148)."""
-    st = _Stream(_embed(model, img))
+    st = _embed_stream(model, img)
     rows = []
     for blk in model.blocks:
         rows.append(st.block(blk, return_cls_attn=True).detach())

@@ -539,6 +539,22 @@ def assemble_tokens(patches, cls_token, pos_embed):
     return out
 
 
+def assemble_layernorm(patches, cls_token, pos_embed, weight, bias, eps):
+    """(x, LayerNorm(x)) with x = cat(cls_token, patches) + pos_embed: token assembly fused with the first block's norm1
+    (vit_models/dynamic_vit.py:820-823 + :263).  Inference only."""
+    _check_cuda(patches, cls_token, pos_embed, weight, bias)
+    pc = patches.detach().contiguous()
+    B, N, D = pc.shape
+    cls = cls_token.detach().to(pc.dtype).reshape(D).contiguous()
+    pos = pos_embed.detach().to(pc.dtype).reshape(N + 1, D).contiguous()
+    w, b = weight.detach().to(pc.dtype).contiguous(), bias.detach().to(pc.dtype).contiguous()
+    out_sum = torch.empty(B, N + 1, D, dtype=pc.dtype, device=pc.device)
+    out_norm = torch.empty_like(out_sum)
+    _lib.call("d2s_assemble_layernorm", _ptr(pc), _ptr(cls), _ptr(pos), _ptr(w), _ptr(b), _dtype_code(pc), B, N, D, float(eps),
+              _ptr(out_sum), _ptr(out_norm), _stream())
+    return out_sum, out_norm
+
+
 def patchify(img, ph, pw):
     """img (B,C,H,W) -> (B, (H/ph)*(W/pw), C*ph*pw): im2col of non-overlapping patches, k = (c, py, px)."""
     _check_cuda(img)

@@ -202,6 +202,12 @@ int d2s_add_layernorm(const void* x, const void* y, const void* gamma, const voi
 int d2s_gather_layernorm(const void* x, const int64_t* idx, const void* gamma, const void* beta, int dtype, int B, int T_in,
                          int D, int K, float eps, void* out_sum, void* out_norm, d2s_stream_t stream);
 
+/* Token assembly fused with the first block's norm1 (dynamic_vit.py:820-823 + Block.forward :263; default_dynamic_vit.py:440-443):
+ * out_sum (B,N+1,D) = cat(cls, patches) + pos, out_norm = LayerNorm(out_sum) * gamma + beta.
+ * patches (B,N,D), cls (D), pos (N+1,D), all of `dtype`. */
+int d2s_assemble_layernorm(const void* patches, const void* cls, const void* pos, const void* gamma, const void* beta, int dtype,
+                           int B, int N, int D, float eps, void* out_sum, void* out_norm, d2s_stream_t stream);
+
 /* Linear + activation in one tcgen05 GEMM (fc1 + GELU of Mlp.forward, dynamic_vit.py:159-175), bf16 only:
  * out (M,N) = act(a (M,K) @ w (N,K)^T + bias (N)); fp32 accumulation; bias may be NULL.
  * N % 256 == 0 (N <= 4096), K % 64 == 0. */

@@ -74,6 +74,8 @@ def test_argument_errors_precede_any_launch(d2s):
     # empty batches are a no-op, not an error
     assert lib.d2s_mlp_residual_ln_bf16(p, p, p, p, p, p, p, p, 1e-6, 0, 384, 1536, 1, 0, p, p, None) == 0
     assert lib.d2s_split_heads_bf16(p, 0, 197, 200, 3, 6, 64, p, None) == 0
+    assert lib.d2s_assemble_layernorm(p, p, p, p, p, 1, 2, 196, 380, 1e-6, p, p, None) == 1 and b"D=380" in lib.d2s_last_error()
+    assert lib.d2s_assemble_layernorm(p, None, p, p, p, 1, 2, 196, 384, 1e-6, p, p, None) == 1
     assert lib.d2s_colsum_bf16(p, 16, 12, p, None) == 1 and b"N=12" in lib.d2s_last_error()
     assert lib.d2s_colsum_bf16(None, 16, 16, p, None) == 1
     assert lib.d2s_linear_wgrad_bf16(None, p, 8, 8, 8, p, None, None) == 1

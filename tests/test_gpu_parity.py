@@ -783,6 +783,21 @@ def test_linear_train_matches_module_under_autocast(ops):
         assert torch.equal(ops.linear_train(lin, x1), lin(x1))
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("B,N,D", [(3, 196, 384), (2, 196, 768), (1, 4, 64)])
+def test_assemble_layernorm_equals_assembly_then_layernorm(ops, dtype, B, N, D):
+    """Token assembly fused with the first norm1: x bit-identical to assemble_tokens (and to the oracle), h bit-identical to the
+    stand-alone LayerNorm kernel on that x."""
+    patches = fx.randn(830 + D, B, N, D).to(dtype)
+    cls, pos = fx.randn(831, 1, 1, D).to(dtype), (fx.randn(832, 1, N + 1, D) * 0.5).to(dtype)
+    w, b = (1 + 0.1 * fx.randn(833, D)).to(dtype), (0.1 * fx.randn(834, D)).to(dtype)
+    x, h = ops.assemble_layernorm(cu(patches), cu(cls), cu(pos), cu(w), cu(b), 1e-6)
+    x0 = ops.assemble_tokens(cu(patches), cu(cls), cu(pos))
+    assert torch.equal(x, x0) and torch.equal(x.cpu(), oo.assemble_tokens(patches, cls, pos))
+    _, h0 = ops.add_layernorm(x0, None, cu(w), cu(b), 1e-6)
+    assert torch.equal(h, h0)
+
+
 # ------------------------------------------------------------------------------------------ error behaviour
 def test_errors_are_loud(ops):
     with pytest.raises(RuntimeError):
