@@ -546,6 +546,9 @@ def test_patchify_bit_exact(ops, dtype):
     img2 = fx.randn(181, 2, 1, 32, 64).to(dtype)
     ref2 = img2.view(2, 1, 4, 8, 4, 16).permute(0, 2, 4, 1, 3, 5).reshape(2, 16, 128)
     assert torch.equal(ops.patchify(cu(img2), 8, 16).cpu(), ref2)
+    img3 = fx.randn(183, 2, 3, 32, 1024).to(dtype)          # a band wider than 48 KB of shared memory: the one-vector-per-thread kernel
+    ref3 = img3.view(2, 3, 2, 16, 64, 16).permute(0, 2, 4, 1, 3, 5).reshape(2, 128, 768)
+    assert torch.equal(ops.patchify(cu(img3), 16, 16).cpu(), ref3)
 
 
 def test_gelu_inplace_matches_exact_erf(ops):
