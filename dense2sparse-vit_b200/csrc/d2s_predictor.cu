@@ -78,7 +78,10 @@ __device__ __forceinline__ float act_apply(float x, int act) {
 template <typename T_> struct ActFast { static constexpr bool value = false; };
 template <> struct ActFast<__nv_bfloat16> { static constexpr bool value = true; };
 
-constexpr int kPoolThreads = 256;
+#ifndef D2S_POOL_THREADS
+#define D2S_POOL_THREADS 256
+#endif
+constexpr int kPoolThreads = D2S_POOL_THREADS;
 
 // grid = B; thread = (16-byte vector column v, token group g); groups stride the tokens
 template <typename T_>
@@ -216,8 +219,13 @@ bias_act_kernel(T_* __restrict__ u, const T_* __restrict__ bias, long long rows,
 #pragma unroll
       for (int q = 0; q < VE; ++q) x[q] = PVec<T_>::round(x[q] + bv[q]);
     }
+    if (ActFast<T_>::value && act == D2S_ACT_GELU) {   // packed fp32x2 erfcx polynomial (d2s_tc.cuh), as in pool_act and the GEMM epilogues
 #pragma unroll
-    for (int q = 0; q < VE; ++q) x[q] = act_apply<ActFast<T_>::value>(x[q], act);
+      for (int q = 0; q < VE; q += 2) f2_unpack(gelu_erf_pair(f2_pack(x[q], x[q + 1])), x[q], x[q + 1]);
+    } else {
+#pragma unroll
+      for (int q = 0; q < VE; ++q) x[q] = act_apply<false>(x[q], act);
+    }
     reinterpret_cast<int4*>(base)[i] = PVec<T_>::pack(x);
   };
   int i = threadIdx.x;
