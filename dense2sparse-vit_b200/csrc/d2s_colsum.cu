@@ -70,3 +70,102 @@ extern "C" int d2s_colsum_bf16(const void* dy, long long M, int N, float* out, d
   count_launch();
   return check_launch("d2s_colsum_bf16");
 }
+
+// GELU backward fused with the bias gradient of the Linear in front of it (Mlp.forward, dynamic_vit.py:170-172: fc1 -> GELU):
+//     du = ga * gelu'(u)   (bf16)        db[n] = sum_m du[m, n]   (fp32, of the rounded values the dW GEMM consumes)
+// gelu'(x) = Phi(x) + x phi(x).  With a = |x| and E = exp(-a^2/2):  Phi(-a) = 0.5 erfcx(a / sqrt 2) E  (the degree-8 polynomial of
+// gelu_erf_pair, d2s_tc.cuh) and phi(x) = E / sqrt(2 pi) share the one MUFU.EX2.  Same thread layout as colsum_bf16_kernel.
+#include "d2s_tc.cuh"
+
+namespace d2s {
+
+__device__ __forceinline__ float gelu_grad(float x) {
+  const float a = fminf(fabsf(x), 5.6568542f);
+  float r = fmaf(-3.457075050e-06f, a, 9.698495899e-05f);     // r = -0.5 erfcx(a / sqrt 2)
+  r = fmaf(r, a, -1.174711513e-03f);
+  r = fmaf(r, a, 8.114228228e-03f);
+  r = fmaf(r, a, -3.579151344e-02f);
+  r = fmaf(r, a, 1.080985674e-01f);
+  r = fmaf(r, a, -2.371637582e-01f);
+  r = fmaf(r, a, 3.961593576e-01f);
+  r = fmaf(r, a, -4.998897713e-01f);
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * x * -0.72134752044448170368f));
+  const float h = -r * e;                                      // Phi(-|x|)
+  const float cdf = x >= 0.f ? 1.0f - h : h;
+  return fmaf(x * 0.3989422804014327f, e, cdf);
+}
+
+__global__ void __launch_bounds__(1024)
+gelu_bwd_colsum_kernel(const __nv_bfloat16* __restrict__ u, const __nv_bfloat16* __restrict__ ga, long long M, int N,
+                       int rows_per_cta, __nv_bfloat16* __restrict__ du, float* __restrict__ db) {
+  extern __shared__ float gb_red[];   // blockDim.y x N
+  const int tx = threadIdx.x, ty = threadIdx.y, ny = blockDim.y;
+  const long long row0 = (long long)blockIdx.x * rows_per_cta;
+  const long long row_end = min(M, row0 + rows_per_cta);
+  float acc[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) acc[q] = 0.f;
+  auto one = [&](long long r, const int4& uv, const int4& gv) {
+    const uint32_t uw[4] = {(uint32_t)uv.x, (uint32_t)uv.y, (uint32_t)uv.z, (uint32_t)uv.w};
+    const uint32_t gw[4] = {(uint32_t)gv.x, (uint32_t)gv.y, (uint32_t)gv.z, (uint32_t)gv.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float d0 = __uint_as_float(gw[q] << 16) * gelu_grad(__uint_as_float(uw[q] << 16));
+      const float d1 = __uint_as_float(gw[q] & 0xffff0000u) * gelu_grad(__uint_as_float(uw[q] & 0xffff0000u));
+      const __nv_bfloat162 t = __floats2bfloat162_rn(d0, d1);
+      o[q] = *reinterpret_cast<const uint32_t*>(&t);
+      acc[2 * q] += __uint_as_float(o[q] << 16);
+      acc[2 * q + 1] += __uint_as_float(o[q] & 0xffff0000u);
+    }
+    *reinterpret_cast<uint4*>(du + (size_t)r * N + (size_t)tx * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+  };
+  const size_t col = (size_t)tx * 8;
+  long long r = row0 + ty;
+  for (; r + ny < row_end; r += 2 * ny) {       // two rows (four 16-byte loads) in flight per thread
+    const int4 u0 = ld_stream16(u + (size_t)r * N + col), g0 = ld_stream16(ga + (size_t)r * N + col);
+    const int4 u1 = ld_stream16(u + (size_t)(r + ny) * N + col), g1 = ld_stream16(ga + (size_t)(r + ny) * N + col);
+    one(r, u0, g0);
+    one(r + ny, u1, g1);
+  }
+  if (r < row_end) one(r, ld_stream16(u + (size_t)r * N + col), ld_stream16(ga + (size_t)r * N + col));
+  if (db == nullptr) return;
+  float* mine = gb_red + (size_t)ty * N + tx * 8;
+  *reinterpret_cast<float4*>(mine) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+  *reinterpret_cast<float4*>(mine + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+  __syncthreads();
+  for (int c = ty * blockDim.x + tx; c < N; c += ny * blockDim.x) {
+    float s = 0.f;
+    for (int y = 0; y < ny; ++y) s += gb_red[(size_t)y * N + c];
+    atomicAdd(db + c, s);
+  }
+}
+
+}  // namespace d2s
+
+extern "C" int d2s_gelu_bwd_colsum_bf16(const void* u, const void* ga, long long M, int N, void* du, float* db, d2s_stream_t stream) {
+  D2S_REQUIRE(u && ga && du, D2S_ERR_ARG, "gelu_bwd_colsum: null pointer");
+  D2S_REQUIRE(M >= 0 && N >= 8 && N % 8 == 0 && N <= 8192, D2S_ERR_ARG, "gelu_bwd_colsum: bad shape M=%lld N=%d (N %% 8 == 0, N <= 8192)",
+              M, N);
+  D2S_REQUIRE(aligned16(u) && aligned16(ga) && aligned16(du), D2S_ERR_ALIGN, "gelu_bwd_colsum: pointers must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (db) {
+    cudaError_t e = cudaMemsetAsync(db, 0, (size_t)N * sizeof(float), st);
+    D2S_REQUIRE(e == cudaSuccess, D2S_ERR_CUDA, "gelu_bwd_colsum: memset: %s", cudaGetErrorString(e));
+  }
+  if (M == 0) return D2S_OK;
+  const int nx = N / 8;
+  int ny = 1024 / nx;
+  if (ny > 8) ny = 8;
+  if (ny < 1) ny = 1;
+  const size_t smem = (size_t)ny * N * sizeof(float);
+  D2S_REQUIRE(smem <= 48 * 1024, D2S_ERR_ARG, "gelu_bwd_colsum: N=%d too wide", N);
+  long long rows_per_cta = (M + 4LL * d2s::kNumSMs - 1) / (4LL * d2s::kNumSMs);
+  if (rows_per_cta < 2LL * ny) rows_per_cta = 2LL * ny;
+  const long long grid = (M + rows_per_cta - 1) / rows_per_cta;
+  d2s::gelu_bwd_colsum_kernel<<<(unsigned)grid, dim3(nx, ny), smem, st>>>((const __nv_bfloat16*)u, (const __nv_bfloat16*)ga, M, N,
+                                                                         (int)rows_per_cta, (__nv_bfloat16*)du, db);
+  d2s::count_launch();
+  return d2s::check_launch("d2s_gelu_bwd_colsum_bf16");
+}

@@ -116,9 +116,7 @@ __global__ void __launch_bounds__(kLtBwdThreads)
 ln_bwd_kernel(const TH* __restrict__ dh, const TX* __restrict__ x, const float* __restrict__ stats,
               const float* __restrict__ gamma, const TX* __restrict__ gadd, long long rows, int D, TX* __restrict__ dx,
               float* __restrict__ dgamma, float* __restrict__ dbeta) {
-  extern __shared__ float red[];   // 2 * D : per-CTA dgamma | dbeta
-  for (int c = threadIdx.x; c < 2 * D; c += kLtBwdThreads) red[c] = 0.f;
-  __syncthreads();
+  extern __shared__ float red[];   // (half-warps per CTA) x D partial column sums
   const int sub = threadIdx.x & 15;
   const int nvec = D / 8;
   float g[kVPL][8];
@@ -179,22 +177,28 @@ ln_bwd_kernel(const TH* __restrict__ dh, const TX* __restrict__ x, const float* 
       }
     }
   }
-  // 16 half-warps hold partial column sums: fold into shared memory, then one atomic per column per CTA
+  // The CTA's half-warps hold partial column sums: they meet in shared memory as plain stores (one slot per half-warp: shared
+  // float atomics are CAS loops), first dgamma then dbeta through the same buffer, then one global atomic per column per CTA.
+  float* slot = red + (size_t)(threadIdx.x >> 4) * D;
 #pragma unroll
-  for (int k = 0; k < kVPL; ++k) {
-    const int vi = sub + 16 * k;
-    if (vi < nvec) {
+  for (int pass = 0; pass < 2; ++pass) {
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        atomicAdd(&red[vi * 8 + q], ag[k][q]);
-        atomicAdd(&red[D + vi * 8 + q], ab[k][q]);
+    for (int k = 0; k < kVPL; ++k) {
+      const int vi = sub + 16 * k;
+      if (vi < nvec) {
+        const float (&a)[8] = pass == 0 ? ag[k] : ab[k];
+        *reinterpret_cast<float4*>(slot + vi * 8) = make_float4(a[0], a[1], a[2], a[3]);
+        *reinterpret_cast<float4*>(slot + vi * 8 + 4) = make_float4(a[4], a[5], a[6], a[7]);
       }
     }
-  }
-  __syncthreads();
-  for (int c = threadIdx.x; c < D; c += kLtBwdThreads) {
-    atomicAdd(&dgamma[c], red[c]);
-    atomicAdd(&dbeta[c], red[D + c]);
+    __syncthreads();
+    for (int c = threadIdx.x; c < D; c += kLtBwdThreads) {
+      float t = 0.f;
+#pragma unroll
+      for (int h = 0; h < kLtBwdRowsPerIter; ++h) t += red[(size_t)h * D + c];
+      atomicAdd(pass == 0 ? &dgamma[c] : &dbeta[c], t);
+    }
+    __syncthreads();
   }
 }
 
@@ -213,7 +217,7 @@ static int ln_bwd_launch(const void* dh, const void* x, const float* stats, cons
                          int D, void* dx, float* dgamma, float* dbeta, cudaStream_t st) {
   const int vpl = ceil_div(D / 8, 16);
   const unsigned grid = (unsigned)((rows + kLtRowsPerCta - 1) / kLtRowsPerCta);
-  const size_t smem = 2 * (size_t)D * sizeof(float);
+  const size_t smem = (size_t)kLtBwdRowsPerIter * D * sizeof(float);
   if (vpl <= 3) ln_bwd_kernel<TX, TH, 3><<<grid, kLtBwdThreads, smem, st>>>((const TH*)dh, (const TX*)x, stats, gamma, (const TX*)gadd, rows, D, (TX*)dx, dgamma, dbeta);
   else          ln_bwd_kernel<TX, TH, 6><<<grid, kLtBwdThreads, smem, st>>>((const TH*)dh, (const TX*)x, stats, gamma, (const TX*)gadd, rows, D, (TX*)dx, dgamma, dbeta);
   count_launch();

@@ -36,7 +36,7 @@ class Mlp(nn.Module):
 
     def forward(self, x):
         # (ops.linear_train is the module itself unless a gradient is wanted on the bf16 CUDA path)
-        return self.drop(ops.linear_train(self.fc2, self.drop(self.act(ops.linear_train(self.fc1, x)))))
+        return self.drop(ops.linear_train(self.fc2, self.drop(ops.linear_gelu_train(self.fc1, self.act, x))))
 
 
 class Attention(nn.Module):

@@ -273,6 +273,7 @@ def softmax_with_policy(attn, policy, eps=1e-6):
 
 
 _FUSED_WGRAD = os.environ.get("D2S_FUSED_WGRAD", "1") != "0"   # A/B switch for ops.linear_train (d2s bias gradient)
+_FUSED_GELU_BWD = os.environ.get("D2S_FUSED_GELU_BWD", "1") != "0"   # A/B switch: fc1 -> GELU as one autograd node
 _WGRAD_LT = os.environ.get("D2S_WGRAD", "colsum") == "lt"       # dW + db in one cuBLASLt call instead of GEMM + d2s column sum
 
 
@@ -343,13 +344,70 @@ class _LinearTrain(torch.autograd.Function):
         return gx, None if gw is None else gw.to(wd), None if gb is None else gb.to(bd)
 
 
+def gelu_bwd_colsum(u, ga, want_bias=True):
+    """(du, db) = (ga * gelu'(u), column sums of du in fp32) for 2-D bf16 u, ga: the exact-erf GELU backward fused with the bias
+    gradient of the Linear that produced u (`d2s_gelu_bwd_colsum_bf16`)."""
+    _check_cuda(u, ga)
+    if u.dtype != torch.bfloat16 or ga.dtype != torch.bfloat16 or u.dim() != 2 or u.shape != ga.shape:
+        raise RuntimeError("gelu_bwd_colsum: two 2-D bf16 tensors of one shape are expected")
+    u, ga = u.contiguous(), ga.contiguous()
+    M, N = u.shape
+    du = torch.empty_like(u)
+    db = torch.zeros(N, dtype=torch.float32, device=u.device) if want_bias else None
+    if M > 0:
+        _lib.call("d2s_gelu_bwd_colsum_bf16", _ptr(u), _ptr(ga), M, N, _ptr(du), _ptr(db), _stream())
+    return du, db
+
+
+class _LinearGeluTrain(torch.autograd.Function):
+    """GELU(nn.Linear(x)) on the bf16 training path (Mlp.forward's fc1 -> act, dynamic_vit.py:170-172) as ONE autograd node: the
+    backward runs GELU' and the Linear's bias gradient in one pass over (u, dy) and then the two library GEMMs for dx and dW."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        xb, wb = x.to(torch.bfloat16), w.to(torch.bfloat16)
+        bb = None if b is None else b.to(torch.bfloat16)
+        u = F.linear(xb, wb, bb)
+        ctx.save_for_backward(xb, wb, u)
+        ctx.meta = (x.dtype, w.dtype, None if b is None else b.dtype)
+        return F.gelu(u)
+
+    @staticmethod
+    def backward(ctx, ga):
+        xb, wb, u = ctx.saved_tensors
+        xd, wd, bd = ctx.meta
+        N, K = wb.shape
+        ga2 = ga.reshape(-1, N)
+        if ga2.dtype != torch.bfloat16 or not ga2.is_contiguous():
+            ga2 = ga2.to(torch.bfloat16).contiguous()
+        want_b = bd is not None and ctx.needs_input_grad[2]
+        du, gb = gelu_bwd_colsum(u.reshape(-1, N), ga2, want_bias=want_b)
+        gx = (du @ wb).view(xb.shape).to(xd) if ctx.needs_input_grad[0] else None
+        gw = (du.t() @ xb.reshape(-1, K)).to(wd) if ctx.needs_input_grad[1] else None
+        return gx, gw, None if gb is None else gb.to(bd)
+
+
+def _linear_train_ok(lin, x):
+    bf16 = (torch.is_autocast_enabled() and torch.get_autocast_dtype("cuda") == torch.bfloat16) or \
+        (x.dtype == torch.bfloat16 and lin.weight.dtype == torch.bfloat16)
+    return (_FUSED_WGRAD and isinstance(lin, torch.nn.Linear) and x.is_cuda and bf16 and torch.is_grad_enabled()
+            and lin.weight.requires_grad and lin.in_features % 8 == 0 and lin.out_features % 8 == 0
+            and x.dtype in (torch.bfloat16, torch.float32))
+
+
+def linear_gelu_train(lin, act, x):
+    """`act(lin(x))` under autograd: one node with the fused GELU-backward + bias-gradient kernel when `act` is the exact-erf
+    nn.GELU and the bf16 training path applies, else `act(linear_train(lin, x))`."""
+    if (_FUSED_GELU_BWD and not _WGRAD_LT and _linear_train_ok(lin, x) and isinstance(act, torch.nn.GELU)
+            and getattr(act, "approximate", "none") == "none" and lin.out_features <= 8192):
+        return _LinearGeluTrain.apply(x, lin.weight, lin.bias)
+    return act(linear_train(lin, x))
+
+
 def linear_train(lin, x):
     """`lin(x)` for an nn.Linear under autograd: the fused-bias-gradient path when it applies (CUDA, bf16 compute -- a bf16
     module or bf16 autocast --, feature counts multiples of 8), else the module itself."""
-    bf16 = (torch.is_autocast_enabled() and torch.get_autocast_dtype("cuda") == torch.bfloat16) or \
-        (x.dtype == torch.bfloat16 and lin.weight.dtype == torch.bfloat16)
-    if (_FUSED_WGRAD and isinstance(lin, torch.nn.Linear) and x.is_cuda and bf16 and torch.is_grad_enabled() and lin.weight.requires_grad
-            and lin.in_features % 8 == 0 and lin.out_features % 8 == 0 and x.dtype in (torch.bfloat16, torch.float32)):
+    if _linear_train_ok(lin, x):
         return _LinearTrain.apply(x, lin.weight, lin.bias)
     return lin(x)
 

@@ -150,6 +150,10 @@ int d2s_merge_heads_bf16(const void* src, int B, int T, int Tp, int G, int H, in
  * under autograd (dynamic_vit.py:159-236).  N % 8 == 0, N <= 8192. */
 int d2s_colsum_bf16(const void* dy, long long M, int N, float* out, d2s_stream_t stream);
 
+/* GELU backward fused with the bias gradient of the Linear in front of it (Mlp.forward, dynamic_vit.py:170-172), bf16:
+ * du (M,N) = ga * gelu'(u) (exact-erf GELU), db (N) f32 = column sums of du (NULL: not wanted; overwritten otherwise). */
+int d2s_gelu_bwd_colsum_bf16(const void* u, const void* ga, long long M, int N, void* du, float* db, d2s_stream_t stream);
+
 /* Weight and bias gradient of a Linear layer (nn.Linear of Attention / Mlp / PredictorLG under autograd, dynamic_vit.py:159-236),
  * bf16: dw (N,K) = dy^T x, db (N) = column sums of dy (NULL: not wanted), from dy (M,N) and x (M,K).  ONE cuBLASLt GEMM with the
  * bias-gradient epilogue instead of torch.autograd's GEMM + separate column reduction.  N % 8 == 0, K % 8 == 0. */

@@ -77,6 +77,8 @@ def test_argument_errors_precede_any_launch(d2s):
     assert lib.d2s_assemble_layernorm(p, p, p, p, p, 1, 2, 196, 380, 1e-6, p, p, None) == 1 and b"D=380" in lib.d2s_last_error()
     assert lib.d2s_assemble_layernorm(p, None, p, p, p, 1, 2, 196, 384, 1e-6, p, p, None) == 1
     assert lib.d2s_colsum_bf16(p, 16, 12, p, None) == 1 and b"N=12" in lib.d2s_last_error()
+    assert lib.d2s_gelu_bwd_colsum_bf16(p, p, 16, 12, p, p, None) == 1 and b"N=12" in lib.d2s_last_error()
+    assert lib.d2s_gelu_bwd_colsum_bf16(p, None, 16, 16, p, p, None) == 1
     assert lib.d2s_colsum_bf16(None, 16, 16, p, None) == 1
     assert lib.d2s_linear_wgrad_bf16(None, p, 8, 8, 8, p, None, None) == 1
     assert lib.d2s_linear_wgrad_bf16(p, p, 8, 12, 8, p, None, None) == 1 and b"N=12" in lib.d2s_last_error()

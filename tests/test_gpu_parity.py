@@ -765,6 +765,44 @@ def test_colsum_matches_fp32_sum(ops, M, N):
     assert float((out.cpu().double() - ref).abs().max()) <= 2e-5 * float(dy.double().abs().sum(0).max()) + 1e-6
 
 
+@pytest.mark.parametrize("M,N", [(50432, 1536), (197 * 3, 384), (5, 8), (0, 64)])
+def test_gelu_bwd_colsum_matches_autograd(ops, M, N):
+    """du = ga * gelu'(u) (exact-erf GELU) and db = column sums of du, against torch autograd in float64 on the same bf16 inputs."""
+    u = (fx.randn(840 + N, max(M, 1), N) * 2.0).bfloat16()[:M]
+    ga = (fx.randn(841 + N, max(M, 1), N) * 0.5).bfloat16()[:M]
+    du, db = ops.gelu_bwd_colsum(cu(u), cu(ga))
+    u64 = u.double().requires_grad_(True)
+    (torch.nn.functional.gelu(u64) * ga.double()).sum().backward()
+    ref = u64.grad
+    if M > 0:
+        err = (du.cpu().double() - ref).abs()
+        assert bool((err <= ref.abs() * 2 ** -7 + 2e-4).all())                       # one bf16 ulp + the tail's absolute error
+        assert float((db.cpu().double() - du.cpu().double().sum(0)).abs().max()) <= 2e-5 * float(du.cpu().double().abs().sum(0).max()) + 1e-6
+    else:
+        assert du.shape == (0, N) and float(db.abs().max()) == 0
+    du2, none = ops.gelu_bwd_colsum(cu(u), cu(ga), want_bias=False)
+    assert none is None and torch.equal(du2, du)
+
+
+def test_linear_gelu_train_matches_modules_under_autocast(ops):
+    """ops.linear_gelu_train(fc1, GELU, x) == GELU(fc1(x)) in value and in every gradient (fp32 master weights, bf16 autocast)."""
+    lin, lin2 = torch.nn.Linear(384, 1536).cuda(), torch.nn.Linear(384, 1536).cuda()
+    lin2.load_state_dict(lin.state_dict())
+    act = torch.nn.GELU()
+    x1 = cu(fx.randn(850, 4, 197, 384)).requires_grad_(True)
+    x2 = x1.detach().clone().requires_grad_(True)
+    up = cu(fx.randn(851, 4, 197, 1536))
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        y1 = ops.linear_gelu_train(lin, act, x1)
+        y2 = act(lin2(x2))
+    assert y1.dtype == torch.bfloat16 and torch.equal(y1, y2)
+    (y1.float() * up).sum().backward()
+    (y2.float() * up).sum().backward()
+    for a, b in ((x1.grad, x2.grad), (lin.weight.grad, lin2.weight.grad), (lin.bias.grad, lin2.bias.grad)):
+        assert a.dtype == b.dtype and float((a - b).abs().max()) <= 1e-2 * float(b.abs().max()) + 1e-4
+    assert torch.equal(ops.linear_gelu_train(lin, torch.nn.ReLU(), x1.detach()), torch.relu(lin(x1.detach())))   # other activations: unfused
+
+
 def test_linear_train_matches_module_under_autocast(ops):
     """ops.linear_train(lin, x) == lin(x) in value and in every gradient, fp32 master weights under bf16 autocast."""
     lin = torch.nn.Linear(384, 1152).cuda()
