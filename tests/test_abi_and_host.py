@@ -245,3 +245,21 @@ def test_distill_loss_masked_token_term_equals_indexing_the_kept_rows(d2s):
                                                                      reduction="batchmean", log_target=True)
         torch.testing.assert_close(parts["token_kl"], ref, rtol=1e-5, atol=1e-6)
         assert torch.isfinite(loss)
+
+
+def test_training_path_helpers_fall_back_to_the_modules_off_the_gpu(d2s):
+    """ops.linear_train / linear_gelu_train are the plain modules whenever the fused bf16 CUDA path does not apply (here: CPU
+    tensors) -- same values, ordinary autograd; they never touch the library in that case."""
+    import torch
+    torch.manual_seed(3)
+    lin, act = torch.nn.Linear(16, 24), torch.nn.GELU()
+    x = torch.randn(5, 16, requires_grad=True)
+    before = d2s._lib.launch_count()
+    y = d2s.ops.linear_train(lin, x)
+    z = d2s.ops.linear_gelu_train(lin, act, x)
+    assert torch.equal(y, lin(x)) and torch.equal(z, act(lin(x)))
+    z.sum().backward()
+    assert x.grad is not None and lin.weight.grad is not None
+    assert d2s._lib.launch_count() == before
+    m = d2s.layers.Mlp(16, 32)
+    assert torch.equal(m(x), m.drop(m.fc2(m.drop(m.act(m.fc1(x))))))
