@@ -79,21 +79,26 @@ extern "C" int d2s_colsum_bf16(const void* dy, long long M, int N, float* out, d
 
 namespace d2s {
 
-__device__ __forceinline__ float gelu_grad(float x) {
-  const float a = fminf(fabsf(x), 5.6568542f);
-  float r = fmaf(-3.457075050e-06f, a, 9.698495899e-05f);     // r = -0.5 erfcx(a / sqrt 2)
-  r = fmaf(r, a, -1.174711513e-03f);
-  r = fmaf(r, a, 8.114228228e-03f);
-  r = fmaf(r, a, -3.579151344e-02f);
-  r = fmaf(r, a, 1.080985674e-01f);
-  r = fmaf(r, a, -2.371637582e-01f);
-  r = fmaf(r, a, 3.961593576e-01f);
-  r = fmaf(r, a, -4.998897713e-01f);
-  float e;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * x * -0.72134752044448170368f));
-  const float h = -r * e;                                      // Phi(-|x|)
-  const float cdf = x >= 0.f ? 1.0f - h : h;
-  return fmaf(x * 0.3989422804014327f, e, cdf);
+// two elements at a time on the packed fp32x2 pipe (the scalar form made the kernel co-bound by FP32 issue)
+__device__ __forceinline__ uint64_t gelu_grad_pair(uint64_t x) {
+  float x0, x1;
+  f2_unpack(x, x0, x1);
+  const uint64_t a = f2_pack(fminf(fabsf(x0), 5.6568542f), fminf(fabsf(x1), 5.6568542f));
+  uint64_t r = f2_fma(f2_bcast(-3.457075050e-06f), a, f2_bcast(9.698495899e-05f));     // r = -0.5 erfcx(a / sqrt 2)
+  r = f2_fma(r, a, f2_bcast(-1.174711513e-03f));
+  r = f2_fma(r, a, f2_bcast(8.114228228e-03f));
+  r = f2_fma(r, a, f2_bcast(-3.579151344e-02f));
+  r = f2_fma(r, a, f2_bcast(1.080985674e-01f));
+  r = f2_fma(r, a, f2_bcast(-2.371637582e-01f));
+  r = f2_fma(r, a, f2_bcast(3.961593576e-01f));
+  r = f2_fma(r, a, f2_bcast(-4.998897713e-01f));
+  float e0, e1;
+  f2_unpack(f2_mul(f2_mul(x, x), f2_bcast(-0.72134752044448170368f)), e0, e1);
+  const uint64_t e = f2_pack(ex2_approx(e0), ex2_approx(e1));                            // exp(-x^2 / 2)
+  float nh0, nh1;
+  f2_unpack(f2_mul(r, e), nh0, nh1);                                                     // -Phi(-|x|)
+  const uint64_t cdf = f2_pack(x0 >= 0.f ? 1.0f + nh0 : -nh0, x1 >= 0.f ? 1.0f + nh1 : -nh1);
+  return f2_fma(f2_mul(x, f2_bcast(0.3989422804014327f)), e, cdf);
 }
 
 __global__ void __launch_bounds__(1024)
@@ -112,8 +117,9 @@ gelu_bwd_colsum_kernel(const __nv_bfloat16* __restrict__ u, const __nv_bfloat16*
     uint32_t o[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      const float d0 = __uint_as_float(gw[q] << 16) * gelu_grad(__uint_as_float(uw[q] << 16));
-      const float d1 = __uint_as_float(gw[q] & 0xffff0000u) * gelu_grad(__uint_as_float(uw[q] & 0xffff0000u));
+      float d0, d1;
+      f2_unpack(f2_mul(f2_pack(__uint_as_float(gw[q] << 16), __uint_as_float(gw[q] & 0xffff0000u)),
+                       gelu_grad_pair(f2_pack(__uint_as_float(uw[q] << 16), __uint_as_float(uw[q] & 0xffff0000u)))), d0, d1);
       const __nv_bfloat162 t = __floats2bfloat162_rn(d0, d1);
       o[q] = *reinterpret_cast<const uint32_t*>(&t);
       acc[2 * q] += __uint_as_float(o[q] << 16);
@@ -123,13 +129,17 @@ gelu_bwd_colsum_kernel(const __nv_bfloat16* __restrict__ u, const __nv_bfloat16*
   };
   const size_t col = (size_t)tx * 8;
   long long r = row0 + ty;
-  for (; r + ny < row_end; r += 2 * ny) {       // two rows (four 16-byte loads) in flight per thread
+  for (; r + 3 * ny < row_end; r += 4 * ny) {       // four rows (eight 16-byte loads) in flight per thread
     const int4 u0 = ld_stream16(u + (size_t)r * N + col), g0 = ld_stream16(ga + (size_t)r * N + col);
     const int4 u1 = ld_stream16(u + (size_t)(r + ny) * N + col), g1 = ld_stream16(ga + (size_t)(r + ny) * N + col);
+    const int4 u2 = ld_stream16(u + (size_t)(r + 2 * ny) * N + col), g2 = ld_stream16(ga + (size_t)(r + 2 * ny) * N + col);
+    const int4 u3 = ld_stream16(u + (size_t)(r + 3 * ny) * N + col), g3 = ld_stream16(ga + (size_t)(r + 3 * ny) * N + col);
     one(r, u0, g0);
     one(r + ny, u1, g1);
+    one(r + 2 * ny, u2, g2);
+    one(r + 3 * ny, u3, g3);
   }
-  if (r < row_end) one(r, ld_stream16(u + (size_t)r * N + col), ld_stream16(ga + (size_t)r * N + col));
+  for (; r < row_end; r += ny) one(r, ld_stream16(u + (size_t)r * N + col), ld_stream16(ga + (size_t)r * N + col));
   if (db == nullptr) return;
   float* mine = gb_red + (size_t)ty * N + tx * 8;
   *reinterpret_cast<float4*>(mine) = make_float4(acc[0], acc[1], acc[2], acc[3]);
@@ -162,7 +172,7 @@ extern "C" int d2s_gelu_bwd_colsum_bf16(const void* u, const void* ga, long long
   const size_t smem = (size_t)ny * N * sizeof(float);
   D2S_REQUIRE(smem <= 48 * 1024, D2S_ERR_ARG, "gelu_bwd_colsum: N=%d too wide", N);
   long long rows_per_cta = (M + 4LL * d2s::kNumSMs - 1) / (4LL * d2s::kNumSMs);
-  if (rows_per_cta < 2LL * ny) rows_per_cta = 2LL * ny;
+  if (rows_per_cta < 4LL * ny) rows_per_cta = 4LL * ny;
   const long long grid = (M + rows_per_cta - 1) / rows_per_cta;
   d2s::gelu_bwd_colsum_kernel<<<(unsigned)grid, dim3(nx, ny), smem, st>>>((const __nv_bfloat16*)u, (const __nv_bfloat16*)ga, M, N,
                                                                          (int)rows_per_cta, (__nv_bfloat16*)du, db);
