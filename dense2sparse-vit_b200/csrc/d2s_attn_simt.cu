@@ -214,15 +214,20 @@ softmax_policy_fwd_vec_kernel(const __nv_bfloat16* __restrict__ attn, const floa
     const float m = fmaxf(__uint_as_float(m2 << 16), __uint_as_float(m2 & 0xffff0000u));
     const uint32_t mb = __float_as_uint(m) >> 16;   // m is a bf16 value
     const uint32_t mm = mb | (mb << 16);
-    float a[8];
-    float sum = 0.f;
+    // element pairs on the packed fp32x2 pipe (the kernel is close to issue-bound)
+    uint64_t a2[4];
+    uint64_t sum2 = f2_bcast(0.f);
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const uint32_t d = sub_bf16x2(w[q], mm);
-      a[2 * q] = ex2_fast(__uint_as_float(d << 16) * kLog2e) * pol[2 * q];
-      a[2 * q + 1] = ex2_fast(__uint_as_float(d & 0xffff0000u) * kLog2e) * pol[2 * q + 1];
-      sum += a[2 * q] + a[2 * q + 1];
+      float x0, x1;
+      f2_unpack(f2_mul(f2_pack(__uint_as_float(d << 16), __uint_as_float(d & 0xffff0000u)), f2_bcast(kLog2e)), x0, x1);
+      a2[q] = f2_mul(f2_pack(ex2_fast(x0), ex2_fast(x1)), f2_pack(pol[2 * q], pol[2 * q + 1]));
+      sum2 = f2_add(sum2, a2[q]);
     }
+    float sum, sum_hi;
+    f2_unpack(sum2, sum, sum_hi);
+    sum += sum_hi;
 #pragma unroll
     for (int o = LPR / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
     // diagonal: the reference's mask is 1 there
@@ -236,8 +241,11 @@ softmax_policy_fwd_vec_kernel(const __nv_bfloat16* __restrict__ attn, const floa
     if (active && rowok) {
       uint32_t pk[4];
 #pragma unroll
-      for (int q = 0; q < 4; ++q)   // padding columns are written as zeros
-        pk[q] = pack_bf16x2(fmaf(a[2 * q], rden, crden), fmaf(a[2 * q + 1], rden, crden)) & keep[q];
+      for (int q = 0; q < 4; ++q) {   // padding columns are written as zeros
+        float p0, p1;
+        f2_unpack(f2_fma(a2[q], f2_bcast(rden), f2_bcast(crden)), p0, p1);
+        pk[q] = pack_bf16x2(p0, p1) & keep[q];
+      }
       __nv_bfloat16* orow = out + block0 + (size_t)li * ld;
       *reinterpret_cast<uint4*>(orow + j0) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
       if (sl == (i >> 3)) orow[i] = __float2bfloat16_rn((exd + c) * rden);   // same thread as the vector store: ordered
@@ -290,12 +298,12 @@ softmax_policy_bwd_vec_kernel(const __nv_bfloat16* __restrict__ attn, const floa
   }
   const uint8_t* g_stage = row_stage + (size_t)kRowsPerCta * ld * 2;
   __syncthreads();   // barriers initialised, pol_s filled
-  float pol[8], gp[8];
+  float pol[8];
+  uint64_t gp2[4];
 #pragma unroll
-  for (int q = 0; q < 8; ++q) {
-    pol[q] = active ? pol_s[j0 + q] : 0.f;
-    gp[q] = 0.f;
-  }
+  for (int q = 0; q < 8; ++q) pol[q] = active ? pol_s[j0 + q] : 0.f;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) gp2[q] = f2_bcast(0.f);
   for (int k = 0; k < M::kSubs; ++k) {
     const int lr = (k * kRowWarps + warp) * M::kRPW;
     if (row0 + lr >= row_end) break;
@@ -315,23 +323,24 @@ softmax_policy_bwd_vec_kernel(const __nv_bfloat16* __restrict__ attn, const floa
     const uint32_t gw[4] = {(uint32_t)graw.x, (uint32_t)graw.y, (uint32_t)graw.z, (uint32_t)graw.w};
     const uint32_t mb = __float_as_uint(m) >> 16;   // the forward's row max is a bf16 value
     const uint32_t mm = mb | (mb << 16);
-    float g[8], ex[8], a[8];
-    float part = 0.f, gsum = 0.f;
+    // element pairs on the packed fp32x2 pipe (the kernel is close to issue-bound)
+    uint64_t g2[4], ex2v[4], a2[4];
+    uint64_t part2 = f2_bcast(0.f), gsum2 = f2_bcast(0.f);
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const uint32_t d = sub_bf16x2((sw[q] & keep[q]) | ninf[q], mm);
       const uint32_t gq = gw[q] & keep[q];
-      ex[2 * q] = ex2_fast(__uint_as_float(d << 16) * kLog2e);
-      ex[2 * q + 1] = ex2_fast(__uint_as_float(d & 0xffff0000u) * kLog2e);
-      g[2 * q] = __uint_as_float(gq << 16);
-      g[2 * q + 1] = __uint_as_float(gq & 0xffff0000u);
-      a[2 * q] = ex[2 * q] * pol[2 * q];
-      a[2 * q + 1] = ex[2 * q + 1] * pol[2 * q + 1];
-      part = fmaf(g[2 * q], a[2 * q], part);
-      part = fmaf(g[2 * q + 1], a[2 * q + 1], part);
-      gsum += g[2 * q] + g[2 * q + 1];
+      float x0, x1;
+      f2_unpack(f2_mul(f2_pack(__uint_as_float(d << 16), __uint_as_float(d & 0xffff0000u)), f2_bcast(kLog2e)), x0, x1);
+      ex2v[q] = f2_pack(ex2_fast(x0), ex2_fast(x1));
+      g2[q] = f2_pack(__uint_as_float(gq << 16), __uint_as_float(gq & 0xffff0000u));
+      a2[q] = f2_mul(ex2v[q], f2_pack(pol[2 * q], pol[2 * q + 1]));
+      part2 = f2_fma(g2[q], a2[q], part2);
+      gsum2 = f2_add(gsum2, g2[q]);
     }
-    part = fmaf(c, gsum, part);
+    float part, part_hi;
+    f2_unpack(f2_fma(f2_bcast(c), gsum2, part2), part, part_hi);
+    part += part_hi;
 #pragma unroll
     for (int o = LPR / 2; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
     // diagonal element (mask 1 in the reference, p_i in the sums above)
@@ -340,16 +349,18 @@ softmax_policy_bwd_vec_kernel(const __nv_bfloat16* __restrict__ attn, const floa
     const float gd = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(g_stage + roff)[id]);
     const float exd = ex2_fast(__bfloat162float(__float2bfloat16_rn(sd - m)) * kLog2e);
     const float gdr = (part + gd * exd * (1.0f - pol_s[id])) * rden * rden;   // (g . P) / den
-    float ds[8];
+    uint32_t dsw[4];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const float da = fmaf(g[q], rden, -gdr);
-      ds[q] = da * a[q];                          // a == 0 outside the row
-      gp[q] = fmaf(da, ex[q], gp[q]);             // includes the diagonal: taken out again through gp_fix
+    for (int q = 0; q < 4; ++q) {
+      const uint64_t da = f2_fma(g2[q], f2_bcast(rden), f2_bcast(-gdr));
+      float d0, d1;
+      f2_unpack(f2_mul(da, a2[q]), d0, d1);       // a == 0 outside the row
+      dsw[q] = pack_bf16x2(d0, d1);
+      gp2[q] = f2_fma(da, ex2v[q], gp2[q]);       // includes the diagonal: taken out again through gp_fix
     }
     if (active && rowok) {
       __nv_bfloat16* drow = gattn + block0 + (size_t)li * ld;
-      *reinterpret_cast<uint4*>(drow + j0) = pack8(ds);
+      *reinterpret_cast<uint4*>(drow + j0) = make_uint4(dsw[0], dsw[1], dsw[2], dsw[3]);
       const float dsd = fmaf(gd, rden, -gdr) * exd;
       if (sl == (i >> 3)) drow[i] = __float2bfloat16_rn(dsd);   // same thread as the vector store: ordered
       if (sl == 0) gp_fix[li] = dsd;
@@ -357,6 +368,9 @@ softmax_policy_bwd_vec_kernel(const __nv_bfloat16* __restrict__ attn, const floa
   }
   if (want_gp) {
     float* mine = gp_s[warp * M::kRPW + sub];
+    float gp[8];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) f2_unpack(gp2[q], gp[2 * q], gp[2 * q + 1]);
     *reinterpret_cast<float4*>(mine + j0) = make_float4(gp[0], gp[1], gp[2], gp[3]);
     *reinterpret_cast<float4*>(mine + j0 + 4) = make_float4(gp[4], gp[5], gp[6], gp[7]);
     __syncthreads();
