@@ -9,7 +9,7 @@
 //
 // Standalone select moves 4N + 8N bytes per image (2.3 KB): it is launch/latency bound, not HBM bound
 // (SURVEY.md section 7 hard part 7); the fused tails read the (N, C) hidden activations (e*N*C bytes) as well.
-#include "d2s_common.cuh"
+#include "d2s_tc.cuh"
 
 namespace d2s {
 
@@ -219,7 +219,17 @@ score_tail_a_kernel(const T_* __restrict__ hidden, int N, int C, const float* __
         Vec16<T_>::load(row + c, v);
         if (act_input) {  // the GELU in front of the last Linear (default_dynamic_vit.py:318), applied on load
 #pragma unroll
-          for (int q = 0; q < VE; ++q) v[q] = round_to(0.5f * v[q] * (1.0f + erff(v[q] * 0.70710678118654752440f)), row);
+          for (int q = 0; q < VE; q += 2) {
+            if (sizeof(T_) == 2) {   // bf16 activations: the packed fp32x2 erfcx GELU of the GEMM epilogues (<= 0.07 bf16 ulp); erff made
+              float g0, g1;          // this tail FP32-bound (19 M erff per launch at B = 1024)
+              f2_unpack(gelu_erf_pair(f2_pack(v[q], v[q + 1])), g0, g1);
+              v[q] = round_to(g0, row);
+              v[q + 1] = round_to(g1, row);
+            } else {
+              v[q] = round_to(0.5f * v[q] * (1.0f + erff(v[q] * 0.70710678118654752440f)), row);
+              v[q + 1] = round_to(0.5f * v[q + 1] * (1.0f + erff(v[q + 1] * 0.70710678118654752440f)), row);
+            }
+          }
         }
 #pragma unroll
         for (int q = 0; q < VE; ++q) {
