@@ -19,8 +19,11 @@
 //
 //   warp 0      TMA producer: H tile (once per row tile) and W1 k-blocks      warp 2   TMA producer: W2 chunks
 //   warp 1      TMEM allocation; G1 issue (leader CTA only)                   warp 3   G2 issue (leader CTA only)
-//   warps 4-11  E1: GELU of the hidden chunks (two groups of four warps)
+//   warps 4-11  E1: GELU of the hidden chunks (two groups of four warps; -DMP_E1W=16: four groups of 32 columns under setmaxnreg,
+//               measured slower -- the stage is bound by the sub-partitions' issue / MUFU slots, not by per-warp latency)
 //   warps 12-15 output: residual add + LayerNorm of the finished row tile, overlapped with the next tile's GEMMs
+// Build options for experiments: -DMP_W1 / -DMP_W2 (weight ring depths, default 5 / 3), -DMP_E1W (8 | 16), -DD2S_GEMM_TRACE_BUILD
+// (clock64 totals of the issuers' barrier waits, scripts/bench_mlp_trace.py).
 #include <stdlib.h>
 #include "d2s_tc.cuh"
 
