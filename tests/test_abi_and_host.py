@@ -263,3 +263,18 @@ def test_training_path_helpers_fall_back_to_the_modules_off_the_gpu(d2s):
     assert d2s._lib.launch_count() == before
     m = d2s.layers.Mlp(16, 32)
     assert torch.equal(m(x), m.drop(m.fc2(m.drop(m.act(m.fc1(x))))))
+
+
+def test_traffic_json_is_reproducible_from_the_committed_ncu_capture(tmp_path):
+    """profiles/traffic.json (bench.py's `roofline.traffic`) is exactly what scripts/make_traffic_json.py derives from the committed
+    ncu capture it names as its source."""
+    import json, os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    committed = json.load(open(os.path.join(root, "profiles", "traffic.json")))
+    src = committed["mlp_pair_kernel"]["source"].split()[0]
+    out = tmp_path / "traffic.json"
+    subprocess.run([sys.executable, os.path.join(root, "scripts", "make_traffic_json.py"), os.path.join(root, src), str(out)],
+                   check=True, capture_output=True)
+    assert json.load(open(out)) == committed
+    k = committed["mlp_pair_kernel"]
+    assert k["launches_per_step"] == 11 and 0.5 < k["dram_bytes_per_step"] / (11 * 409.3e6) < 1.2    # at most the algorithmic bytes
