@@ -42,7 +42,8 @@ SIGNATURES = {
     "d2s_colsum_bf16": [_p, ctypes.c_longlong, _i, _p, _p],
     "d2s_gelu_bwd_colsum_bf16": [_p, _p, ctypes.c_longlong, _i, _p, _p, _p],
     "d2s_linear_wgrad_bf16": [_p, _p, _i, _i, _i, _p, _p, _p],
-    "d2s_attn_policy_fwd": [_p, _p, _i, _i, _i, _i, _i, _f, _f, _p, _p, _p],
+    "d2s_attn_policy_fwd": [_p, _p, _i, _i, _i, _i, _i, _f, _f, _p, _p, _p, _p],
+    "d2s_attn_policy_bwd": [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _f, _p, _p, _p],
     "d2s_pool_act": [_p, _p, _i, _i, _i, _i, _i, _p, _p, _p],
     "d2s_bias_act": [_p, _p, _i, ctypes.c_longlong, _i, _i, _i, _p],
     "d2s_pool_concat_inplace": [_p, _i, _i, _i, _i, _p],

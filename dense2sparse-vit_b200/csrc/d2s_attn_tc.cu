@@ -26,6 +26,8 @@ namespace d2s {
 // warps [0, kSW): softmax/epilogue (TMEM lane quadrant = warp % 4; with kSW == 8 the two warps of a quadrant split the
 // key columns of every row); warp kSW: TMA + MMA issue
 constexpr int tc_threads(int ksw) { return 32 * (ksw + 1); }
+// a logit this many binades (powers of two, after scaling) above the row's exponent reference raises the reference
+constexpr float kMaxBinades = 100.0f;
 
 struct TcBars {
   uint64_t q_full[2], k_full[2], v_full, s_full, p_full, o_full, tmem_free;
@@ -39,7 +41,7 @@ template <int kNT, bool kPol, int kSW>
 __global__ void __launch_bounds__(tc_threads(kSW), kNT == 1 ? 4 : 2)
 attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                    const float* __restrict__ policy, int num_units, int T, int H, int Tkp, int kbufs, float scale,
-                   float eps, __nv_bfloat16* __restrict__ out, float* __restrict__ cls_row) {
+                   float eps, __nv_bfloat16* __restrict__ out, float* __restrict__ cls_row, float* __restrict__ stats) {
   constexpr int kTmemCols = kNT == 1 ? 128 : 256;
   // O accumulator columns: beyond the packed-P columns.  One softmax warp per row: P at [0, Tkp/2).  Two warps per row
   // (kSW == 8): the second column half writes its P over ITS OWN consumed S columns, at [16*ceil(n/2), ...) <= 192.
@@ -64,6 +66,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   float* vsum_s = cls_s + 256;                                // 64
   float* sum_s = vsum_s + 64;                                 // 2 x 128 (kSW == 8: partial row sums of the column halves)
   float* max_s = sum_s + 256;                                 // 2 x 128
+  float* ref_s = max_s + 256;                                 // 2 x 128 (kSW == 8: exponent reference of each column half)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t bytes_a = (uint32_t)rows_a * 128u, bytes_b = (uint32_t)rows_b * 128u;
@@ -218,12 +221,36 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         tc_fence_after();
         float sum = 0.f, mx_true = -INFINITY, mxk = 0.f;
         const bool want_cls = (cls_row != nullptr) && (i == 0);
+        // TMEM column of the packed-P chunk `c` of this warp (second column half: its own region, see kOCol)
+        auto pcol = [&](int c) -> uint32_t {
+          return (kSW == 8 && half == 1) ? (uint32_t)(ch_lo * 16 + (c - ch_lo) * 8) : (uint32_t)(c * 8);
+        };
+        // Multiply everything this thread has produced for chunks [ch_lo, upto) by f = 2^-d (exact: P is bf16, f a power of
+        // two).  Warp-uniform call (tcgen05.ld/st are .sync.aligned), per-lane f.
+        auto rescale_row = [&](int upto, float f, float& s0, float& s1, float& s2, float& s3) {
+          s0 *= f; s1 *= f; s2 *= f; s3 *= f;
+          tmem_st_wait();
+          for (int c = ch_lo; c < upto; ++c) {
+            uint32_t w[8];
+            tmem_ld8_nowait(lane_addr + pcol(c), w);
+            tmem_ld_wait();
+#pragma unroll
+            for (int q = 0; q < 8; ++q) w[q] = pack_bf16x2(bf16_lo(w[q]) * f, bf16_hi(w[q]) * f);
+            tmem_st8(lane_addr + pcol(c), w);
+          }
+          if (want_cls)
+            for (int j = ch_lo * 16; j < upto * 16; ++j) cls_s[j] *= f;
+        };
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
         if (warp_active) {
           // ONE pass over S (reading S twice -- row max, then exponentials -- lengthens the serial chain of the tile).
-          // Exponentials are taken against m' = max of the row's first 16 columns, not the row max: softmax is shift
-          // invariant and bf16 keeps fp32's exponent range, so P = 2^(s - m') is as accurate as 2^(s - max).  The true
-          // max is tracked on the side because the reference's eps terms are not shift invariant; they are rescaled by
-          // 2^(max - m') below, which restores the reference formula exactly.  Exponents are clamped at 2^120.
+          // Exponentials are taken against a reference m' = floor(k2 * max of 16 columns of the row), not the row max: softmax
+          // is shift invariant and bf16 keeps fp32's exponent range, so P = 2^(k2 s - m') is as accurate as 2^(k2 (s - max)).
+          // The true max is tracked on the side because the reference's eps terms are not shift invariant; they are rescaled
+          // by 2^(k2 max - m') below, which restores the reference formula exactly.  m' is an INTEGER number of binades: when a
+          // later chunk holds a logit more than kMaxBinades above it (never seen on trained ViTs, but nothing forbids it), the
+          // reference is raised by a whole number of binades and what was already produced is multiplied by the matching power
+          // of two -- exact, so the result does not depend on where the maximum sits in the row.
           // Reference chunk: chunk 0 with one warp per row.  With two warps per row both must derive the SAME m' from
           // columns neither of them overwrites with P before the other has read them: the last chunk of the first
           // half (the first half's P ends at column 8*ceil(n/2), below that chunk; the second half's P starts above it).
@@ -235,9 +262,8 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
 #pragma unroll
           for (int q = 1; q < 16; ++q)
             if (ch_ref * 16 + q < T) mx = fmaxf(mx, __uint_as_float(v[q]));
-          mxk = mx * k2;
+          mxk = floorf(mx * k2);
           mx_true = mx;
-          float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
           for (int ch = ch_lo; ch < ch_hi; ++ch) {
             if (ch != ch_ref || ch != ch_lo) {   // (the reference chunk is still in registers only if it comes first)
               tmem_ld16_nowait(lane_addr + (uint32_t)(ch * 16), v);
@@ -245,12 +271,22 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             }
             float a[16];
             const bool full = ch * 16 + 16 <= T;
+            // chunk maximum over the valid key columns (zero-filled columns past T must not raise the reference)
+            float cm = __uint_as_float(v[0]);
+#pragma unroll
+            for (int q = 1; q < 16; ++q)
+              if (full || ch * 16 + q < T) cm = fmaxf(cm, __uint_as_float(v[q]));
+            if (kPol) mx_true = fmaxf(mx_true, cm);
+            const float over = fmaf(cm, k2, -mxk);
+            if (__any_sync(0xffffffffu, over > kMaxBinades)) {       // rare: raise the reference, rescale what exists
+              const float d = over > kMaxBinades ? floorf(over) : 0.f;
+              rescale_row(ch, exp2_neg_int(d), s0, s1, s2, s3);
+              mxk += d;
+            }
 #pragma unroll
             for (int q = 0; q < 16; ++q) {
               const int j = ch * 16 + q;
-              const float sv = __uint_as_float(v[q]);
-              if (kPol && (full || j < T)) mx_true = fmaxf(mx_true, sv);
-              float e = ex2_approx(fminf(fmaf(sv, k2, -mxk), 120.0f));
+              float e = ex2_approx(fmaf(__uint_as_float(v[q]), k2, -mxk));
               if (kPol) e *= (j == i) ? 1.0f : pol_s[j];
               if (!full && j >= T) e = 0.f;
               a[q] = e;
@@ -264,26 +300,43 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             uint32_t packed[8];
 #pragma unroll
             for (int q = 0; q < 8; ++q) packed[q] = pack_bf16x2(a[2 * q], a[2 * q + 1]);
-            // P overlays S columns this warp has already consumed (second column half: its own region, see kOCol)
-            const uint32_t pcol = (kSW == 8 && half == 1) ? (uint32_t)(ch_lo * 16 + (ch - ch_lo) * 8) : (uint32_t)(ch * 8);
-            tmem_st8(lane_addr + pcol, packed);
+            // P overlays S columns this warp has already consumed
+            tmem_st8(lane_addr + pcol(ch), packed);
           }
-          sum = (s0 + s1) + (s2 + s3);
         }  // rows of an idle warp are never written out; whatever their P rows hold stays in those rows
+        if constexpr (kSW == 8) {
+          // The two column halves of a row exchange their partial sums, running maxima and exponent references through shared
+          // memory BEFORE P is published: both halves of a row must end on the same reference (one PV product reads both).
+          sum_s[half * kTileRows + r] = (s0 + s1) + (s2 + s3);
+          max_s[half * kTileRows + r] = mx_true;
+          ref_s[half * kTileRows + r] = mxk;
+          asm volatile("bar.sync 2, 256;" ::: "memory");
+          const float o_ref = ref_s[(half ^ 1) * kTileRows + r];
+          float o_sum = sum_s[(half ^ 1) * kTileRows + r];
+          if (__any_sync(0xffffffffu, warp_active && o_ref != mxk)) {   // rare: one half raised its reference
+            const float d = warp_active ? fmaxf(o_ref - mxk, 0.f) : 0.f;   // integer: both started from the same m'
+            if (warp_active) o_sum *= exp2_neg_int(fmaxf(mxk - o_ref, 0.f));
+            rescale_row(ch_hi, exp2_neg_int(d), s0, s1, s2, s3);
+            mxk += d;
+            // (the branch is taken by both warps of a row pair or by neither: the partner's CLS-row share is final after this)
+            asm volatile("bar.sync %0, 64;" ::"r"(3 + quad) : "memory");
+          }
+          sum = (s0 + s1) + (s2 + s3) + o_sum;
+          if (kPol) mx_true = fmaxf(mx_true, max_s[(half ^ 1) * kTileRows + r]);
+        } else {
+          sum = (s0 + s1) + (s2 + s3);
+        }
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         tc_fence_before();
         mbar_arrive(smem_u32(&bars->p_full));
-        if constexpr (kSW == 8) {
-          // the two column halves of a row exchange their partial sums (and running maxima) through shared memory
-          sum_s[half * kTileRows + r] = sum;
-          if (kPol) max_s[half * kTileRows + r] = mx_true;
-          asm volatile("bar.sync 2, 256;" ::: "memory");
-          sum += sum_s[(half ^ 1) * kTileRows + r];
-          if (kPol) mx_true = fmaxf(mx_true, max_s[(half ^ 1) * kTileRows + r]);
-        }
-        const float eps_scale = (kPol && warp_active) ? ex2_approx(fminf(fmaf(mx_true, k2, -mxk), 120.0f)) : 1.0f;
+        const float eps_scale = (kPol && warp_active) ? ex2_approx(fmaf(mx_true, k2, -mxk)) : 1.0f;   // <= 2^kMaxBinades
         const float den = sum + eps_den * eps_scale;
         const float c_eps_row = c_eps * eps_scale;
+        if (stats != nullptr && warp_active && i < T && (kSW == 4 || half == 0)) {
+          // saved for the backward (d2s_attn_policy_bwd): e_ij = 2^(k2 s_ij - m'_i) m_ij, P_ij = e_ij / den_i + c_i
+          const float inv = 1.0f / den;
+          reinterpret_cast<float4*>(stats)[(size_t)unit * T + i] = make_float4(mxk, inv, c_eps_row * inv, 0.0f);
+        }
         if (cls_row != nullptr && t == 0 && warp == 0) {
           // CLS row (query 0 = lane 0 of warp 0): probabilities of row 0, Attention.forward's second output
           __syncwarp();
@@ -399,12 +452,12 @@ static size_t tc_smem_bytes(int knt, int Tkp, int kbufs) {
   const int rows_a = knt == 1 ? Tkp : kTileRows, rows_b = knt == 1 ? 0 : Tkp - kTileRows;
   (void)rows_a;
   return 1024 + (size_t)(kTileRows + rows_b) * 128 + (size_t)(kbufs + 1) * Tkp * 128 + sizeof(TcBars) +
-         (256 + 256 + 64 + 256 + 256) * sizeof(float);
+         (256 + 256 + 64 + 256 + 256 + 256) * sizeof(float);
 }
 
 template <int kNT, bool kPol, int kSW>
 static int launch_tc(const CUtensorMap& map_a, const CUtensorMap& map_b, const float* policy, int units, int T, int H,
-                     int Tkp, float scale, float eps, void* out, float* cls_row, cudaStream_t stream) {
+                     int Tkp, float scale, float eps, void* out, float* cls_row, float* stats, cudaStream_t stream) {
   auto kern = attn_tc_fwd_kernel<kNT, kPol, kSW>;
   // two K buffers when they still leave room for the intended number of CTAs per SM
   const int per_sm = kNT == 1 ? 4 : 2;
@@ -419,7 +472,7 @@ static int launch_tc(const CUtensorMap& map_a, const CUtensorMap& map_b, const f
   }
   const int grid = units < per_sm * kNumSMs ? units : per_sm * kNumSMs;
   kern<<<grid, tc_threads(kSW), smem, stream>>>(map_a, map_b, policy, units, T, H, Tkp, kbufs, scale, eps,
-                                           (__nv_bfloat16*)out, cls_row);
+                                           (__nv_bfloat16*)out, cls_row, stats);
   count_launch();
   return check_launch("d2s_attn_policy_fwd(tcgen05)");
 }
@@ -429,14 +482,17 @@ static int launch_tc(const CUtensorMap& map_a, const CUtensorMap& map_b, const f
 using namespace d2s;
 
 extern "C" int d2s_attn_policy_fwd(const void* qkv, const float* policy, int dtype, int B, int T, int H, int hd,
-                                   float scale, float eps, void* out, float* cls_row, d2s_stream_t stream_) {
+                                   float scale, float eps, void* out, float* cls_row, float* stats, d2s_stream_t stream_) {
   D2S_REQUIRE(qkv && out, D2S_ERR_ARG, "attn_policy_fwd: null pointer");
   D2S_REQUIRE(dtype == D2S_F32 || dtype == D2S_BF16, D2S_ERR_ARG, "attn_policy_fwd: dtype %d unsupported", dtype);
   D2S_REQUIRE(B >= 0 && T >= 1 && H >= 1 && hd >= 1, D2S_ERR_ARG, "attn_policy_fwd: bad shape B=%d T=%d H=%d hd=%d", B, T, H, hd);
   D2S_REQUIRE((long long)B * H <= (1LL << 30), D2S_ERR_ARG, "attn_policy_fwd: B*H=%lld too large", (long long)B * H);
-  D2S_REQUIRE(aligned16(qkv) && aligned16(out), D2S_ERR_ALIGN, "attn_policy_fwd: qkv/out must be 16-byte aligned");
+  D2S_REQUIRE(aligned16(qkv) && aligned16(out) && aligned16(stats), D2S_ERR_ALIGN,
+              "attn_policy_fwd: qkv/out/stats must be 16-byte aligned");
+  D2S_REQUIRE(scale > 0.0f, D2S_ERR_ARG, "attn_policy_fwd: scale must be positive (got %g)", (double)scale);
   cudaStream_t stream = (cudaStream_t)stream_;
   if (dtype == D2S_F32 || force_simt()) {
+    D2S_REQUIRE(stats == nullptr, D2S_ERR_ARG, "attn_policy_fwd: row statistics are written by the bf16 tcgen05 kernel only");
     D2S_REQUIRE((long long)B * H <= 65535, D2S_ERR_ARG, "attn_policy_fwd(simt): B*H=%lld exceeds 65535", (long long)B * H);
     if (B == 0) return D2S_OK;
     return attn_simt_dispatch(qkv, policy, dtype, B, T, H, hd, scale, eps, out, cls_row, stream);
@@ -464,9 +520,9 @@ extern "C" int d2s_attn_policy_fwd(const void* qkv, const float* policy, int dty
   }
   const int units = B * H;
   if (T <= kTileRows) {
-    return policy ? launch_tc<1, true, 4>(map_a, map_b, policy, units, T, H, Tkp, scale, eps, out, cls_row, stream)
-                  : launch_tc<1, false, 4>(map_a, map_b, policy, units, T, H, Tkp, scale, eps, out, cls_row, stream);
+    return policy ? launch_tc<1, true, 4>(map_a, map_b, policy, units, T, H, Tkp, scale, eps, out, cls_row, stats, stream)
+                  : launch_tc<1, false, 4>(map_a, map_b, policy, units, T, H, Tkp, scale, eps, out, cls_row, stats, stream);
   }
-  return policy ? launch_tc<2, true, 4>(map_a, map_b, policy, units, T, H, Tkp, scale, eps, out, cls_row, stream)
-                : launch_tc<2, false, 8>(map_a, map_b, policy, units, T, H, Tkp, scale, eps, out, cls_row, stream);
+  return policy ? launch_tc<2, true, 4>(map_a, map_b, policy, units, T, H, Tkp, scale, eps, out, cls_row, stats, stream)
+                : launch_tc<2, false, 8>(map_a, map_b, policy, units, T, H, Tkp, scale, eps, out, cls_row, stats, stream);
 }

@@ -472,14 +472,60 @@ class _AttentionTrain(torch.autograd.Function):
         return dqkv, gpol, None, None, None, None
 
 
+class _AttentionFlash(torch.autograd.Function):
+    """Training attention as two tcgen05 kernels on the packed qkv tensor, differentiable in qkv and in the keep policy:
+    forward = the inference kernel, which also writes per-row softmax statistics (`d2s_attn_policy_fwd` with `stats`);
+    backward = `d2s_attn_policy_bwd`, which recomputes scores and probabilities on chip.  Saves qkv, the output and
+    (B,H,T,4) floats; no (B,H,T,T) tensor, no head-major copies, no library GEMM."""
+
+    @staticmethod
+    def forward(ctx, qkv, policy, H, scale, eps, want_cls):
+        qkv = qkv.contiguous()
+        B, T, C3 = qkv.shape
+        D = C3 // 3
+        dev = qkv.device
+        pol = _f32c(policy.reshape(B, T)) if policy is not None else None
+        out = torch.empty(B, T, D, dtype=qkv.dtype, device=dev)
+        cls_row = torch.empty(B, H, T, dtype=torch.float32, device=dev) if want_cls else None
+        stats = torch.empty(B, H, T, 4, dtype=torch.float32, device=dev)
+        _lib.call("d2s_attn_policy_fwd", _ptr(qkv), _ptr(pol), BF16, B, T, H, D // H, float(scale), float(eps), _ptr(out),
+                  _ptr(cls_row), _ptr(stats), _stream())
+        none = torch.empty(0, device=dev)
+        ctx.save_for_backward(qkv, out, stats, pol if pol is not None else none, cls_row if want_cls else none)
+        ctx.meta = (B, T, H, D // H, float(scale), pol is not None, want_cls,
+                    None if policy is None else (policy.shape, policy.dtype))
+        return out, (cls_row.to(qkv.dtype) if want_cls else None)
+
+    @staticmethod
+    def backward(ctx, gO, g_cls):
+        qkv, out, stats, pol, cls_row = ctx.saved_tensors
+        B, T, H, hd, scale, has_pol, want_cls, pol_meta = ctx.meta
+        g = gO.to(qkv.dtype).contiguous()
+        gc = _f32c(g_cls) if (want_cls and g_cls is not None) else None
+        dqkv = torch.empty_like(qkv)
+        gpol = torch.zeros(B, T, dtype=torch.float32, device=qkv.device) if has_pol else None
+        _lib.call("d2s_attn_policy_bwd", _ptr(qkv), _ptr(pol) if has_pol else None, _ptr(out), _ptr(g),
+                  _ptr(cls_row) if want_cls else None, _ptr(gc), _ptr(stats), B, T, H, hd, scale, _ptr(dqkv), _ptr(gpol), _stream())
+        if has_pol:
+            gpol = gpol.reshape(pol_meta[0]).to(pol_meta[1])
+        return dqkv, gpol, None, None, None, None
+
+
+_FLASH_TRAIN = os.environ.get("D2S_FLASH_TRAIN", "1") != "0"   # A/B switch: tcgen05 flash forward/backward for training attention
+FLASH_MAX_T = 208
+
+
 def attention_train(qkv, num_heads, policy=None, scale=None, eps=1e-6, want_cls_row=False):
     """Differentiable attention core of Attention.forward (vit_models/dynamic_vit.py:216-231) on the packed qkv (B,T,3*H*hd):
-    returns (out (B,T,H*hd), cls_row (B,H,T) | None).  bf16 CUDA tensors, T <= 256."""
+    returns (out (B,T,H*hd), cls_row (B,H,T) | None).  bf16 CUDA tensors, T <= 256.  hd == 64 and T <= 208 (every DeiT shape
+    at 224 px) run the tcgen05 flash kernels; the rest keeps the head-major GEMMs around the padded-row softmax kernels."""
     _check_cuda(qkv, policy)
     if qkv.dtype != torch.bfloat16 or qkv.shape[1] > 256:
         raise RuntimeError("attention_train: bf16 and T <= 256 only (other cases use softmax_with_policy around torch matmuls)")
     hd = qkv.shape[-1] // 3 // num_heads
     scale = hd ** -0.5 if scale is None else scale
+    if _FLASH_TRAIN and hd == 64 and qkv.shape[1] <= FLASH_MAX_T and scale > 0:
+        return _AttentionFlash.apply(qkv, policy, num_heads, float(scale), float(eps), bool(want_cls_row))
     return _AttentionTrain.apply(qkv, policy, num_heads, float(scale), float(eps), bool(want_cls_row))
 
 
@@ -497,7 +543,7 @@ def attention_core(qkv, num_heads, policy=None, scale=None, eps=1e-6, want_cls_r
     out = torch.empty(B, T, D, dtype=q.dtype, device=q.device)
     cls_row = torch.empty(B, num_heads, T, dtype=torch.float32, device=q.device) if want_cls_row else None
     _lib.call("d2s_attn_policy_fwd", _ptr(q), _ptr(pol), _dtype_code(q), B, T, num_heads, hd, float(scale), float(eps),
-              _ptr(out), _ptr(cls_row), _stream())
+              _ptr(out), _ptr(cls_row), None, _stream())
     return out, cls_row
 
 

@@ -163,9 +163,25 @@ int d2s_linear_wgrad_bf16(const void* dy, const void* x, int M, int N, int K, vo
  * qkv (B,T,3,H,hd) packed as produced by the qkv Linear; out (B,T,H*hd) ready for the proj Linear;
  * cls_row (B,H,T) f32 = probabilities of query row 0 (dynamic_vit.py:233-234) or NULL.
  * dtype BF16: tcgen05/TMEM tensor-core kernel (hd == 64, T <= 256).
- * dtype F32 : fp32 SIMT kernel used for 1e-4 parity runs (hd in {32,64}, T <= 256). */
+ * dtype F32 : fp32 SIMT kernel used for 1e-4 parity runs (hd in {32,64}, T <= 256).
+ * stats (B,H,T,4) f32 or NULL (BF16 only): per query row (m', 1/den, c/den, unused) with e_ij = 2^(k2 s_ij - m') m_ij,
+ * den = sum_j e_ij + eps', c = eps'/T (eps' = eps 2^(k2 max_j s_ij - m')): what d2s_attn_policy_bwd recomputes P from.
+ * scale > 0.  The exponent reference m' is raised (exactly, by whole binades) whenever a logit exceeds it by more than
+ * 100 binades, so the result does not depend on where a row's maximum sits. */
 int d2s_attn_policy_fwd(const void* qkv, const float* policy, int dtype, int B, int T, int H, int hd,
-                        float scale, float eps, void* out, float* cls_row, d2s_stream_t stream);
+                        float scale, float eps, void* out, float* cls_row, float* stats, d2s_stream_t stream);
+
+/* Backward of d2s_attn_policy_fwd (bf16, hd == 64, T <= 208): Attention.forward's core under autograd, differentiable in qkv AND
+ * in the keep policy (dynamic_vit.py:195-214, :218-231; default_dynamic_vit.py:185-199, :203-213), flash style -- scores and
+ * probabilities are recomputed on chip from qkv and the forward's row statistics, no (B,H,T,T) tensor is read or written.
+ *   qkv (B,T,3,H,64), out (B,T,H*64) = the forward's output, gout (B,T,H*64) = d loss / d out,
+ *   cls_row / g_cls (B,H,T) f32 or NULL: the forward's CLS-row output and its gradient (g_cls NULL: none),
+ *   stats (B,H,T,4) f32 as written by the forward (slot 3 is scratch: delta_i = gout_i . out_i is stored there),
+ *   dqkv (B,T,3,H,64) bf16 = d loss / d qkv (every element written), gpolicy (B,T) f32 ACCUMULATED into (caller zero-fills;
+ *   NULL iff policy is NULL).  The O(eps) gradient through the subtracted row maximum is not propagated. */
+int d2s_attn_policy_bwd(const void* qkv, const float* policy, const void* out, const void* gout, const float* cls_row,
+                        const float* g_cls, float* stats, int B, int T, int H, int hd, float scale, void* dqkv,
+                        float* gpolicy, d2s_stream_t stream);
 
 /* ---- predictor body (inference path of PredictorLG.forward, default_dynamic_vit.py:324-330; dynamic_vit.py:538-546)
  * d2s_pool_act: z (B,N,C) = in_conv's Linear output; local (B,N,C/2) = act(z[:,:,:C/2]);

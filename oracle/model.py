@@ -74,7 +74,7 @@ def variant_a_eval(sd, cfg, img):
     Returns dict(logits, kept=[(B,K_s) int64 per stage, stage-relative, score order], scores=[(B,N_s,2)])."""
     x = embed(sd, cfg, img)
     B = x.shape[0]
-    prev = torch.ones(B, INIT_N, 1, dtype=x.dtype)
+    prev = torch.ones(B, INIT_N, 1, dtype=x.dtype, device=x.device)
     kept_all, score_all = [], []
     p = 0
     for i in range(cfg.depth):
@@ -98,8 +98,8 @@ def variant_a_train(sd, cfg, img, gumbels):
     Returns dict(logits, features, final_decision (B,196,1), decisions=[(B,196)], scores)."""
     x = embed(sd, cfg, img)
     B = x.shape[0]
-    prev = torch.ones(B, INIT_N, 1, dtype=x.dtype)
-    policy = torch.ones(B, INIT_N + 1, 1, dtype=x.dtype)
+    prev = torch.ones(B, INIT_N, 1, dtype=x.dtype, device=x.device)
+    policy = torch.ones(B, INIT_N + 1, 1, dtype=x.dtype, device=x.device)
     decisions, score_all = [], []
     p = 0
     for i in range(cfg.depth):
@@ -107,7 +107,7 @@ def variant_a_train(sd, cfg, img, gumbels):
             logp = ops.predictor_a(sd, f"score_predictor.{p}", x[:, 1:], prev).reshape(B, -1, 2)
             hard, _ = ops.gumbel_keep_decision(logp, gumbels[p], prev)
             decisions.append(hard.reshape(B, INIT_N))
-            policy = torch.cat([torch.ones(B, 1, 1, dtype=hard.dtype), hard], dim=1)
+            policy = torch.cat([torch.ones(B, 1, 1, dtype=hard.dtype, device=hard.device), hard], dim=1)
             prev = hard
             score_all.append(logp)
             p += 1
@@ -151,7 +151,7 @@ def variant_b_threshold_train(sd, cfg, img):
     reference: `score` undefined at :936.)"""
     x = embed(sd, cfg, img)
     B = x.shape[0]
-    keep_mask = torch.ones(B, INIT_N + 1, dtype=x.dtype)
+    keep_mask = torch.ones(B, INIT_N + 1, dtype=x.dtype, device=x.device)
     logit = None
     p = 0
     for i in range(cfg.depth):
@@ -159,7 +159,7 @@ def variant_b_threshold_train(sd, cfg, img):
             logit, probs = ops.predictor_b(sd, f"score_predictor.{p}", x[:, 1:], cfg.small_predictor,
                                            cfg.predictor_bn, cfg.predictor_loss_type, True)
             m = ops.threshold_keep_mask(probs.detach(), cfg.patch_score_threshold)
-            keep_mask = torch.cat([torch.ones(B, 1, dtype=x.dtype), m.to(x.dtype)], dim=1)
+            keep_mask = torch.cat([torch.ones(B, 1, dtype=x.dtype, device=x.device), m.to(x.dtype)], dim=1)
             p += 1
         x = block(sd, cfg, i, x, policy=keep_mask.unsqueeze(-1))
     logits, feats = _head(sd, cfg, x)

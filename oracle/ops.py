@@ -67,7 +67,7 @@ def threshold_keep_mask(score: torch.Tensor, threshold: float) -> torch.Tensor:
 def batch_index_select(x: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
     """Per-image row gather (vit_models/default_dynamic_vit.py:37-53).  x (B,N,C) or (B,N); idx (B,K) int64."""
     if x.dim() == 3:
-        b = torch.arange(x.shape[0]).view(-1, 1)
+        b = torch.arange(x.shape[0], device=x.device).view(-1, 1)
         return x[b, idx]
     if x.dim() == 2:
         return torch.gather(x, 1, idx)
@@ -78,7 +78,7 @@ def gather_tokens_with_cls(x: torch.Tensor, kept: torch.Tensor) -> torch.Tensor:
     """x (B,T,D) incl. CLS at row 0, kept (B,K) spatial indices -> (B,K+1,D): CLS then kept+1
     (vit_models/dynamic_vit.py:907-912 / 954-960, default_dynamic_vit.py:464-466)."""
     B = x.shape[0]
-    rows = torch.cat([torch.zeros(B, 1, dtype=kept.dtype), kept + 1], dim=1)
+    rows = torch.cat([torch.zeros(B, 1, dtype=kept.dtype, device=kept.device), kept + 1], dim=1)
     return batch_index_select(x, rows)
 
 
@@ -86,9 +86,9 @@ def scatter_tokens_bwd(gout: torch.Tensor, kept: torch.Tensor, t_in: int) -> tor
     """Backward of gather_tokens_with_cls: (B,K+1,D) -> (B,t_in,D), zeros for dropped rows
     (autograd of torch.gather at vit_models/dynamic_vit.py:912; indices are unique per image)."""
     B, _, D = gout.shape
-    rows = torch.cat([torch.zeros(B, 1, dtype=kept.dtype), kept + 1], dim=1)
-    gx = torch.zeros(B, t_in, D, dtype=gout.dtype)
-    gx[torch.arange(B).view(-1, 1), rows] = gout
+    rows = torch.cat([torch.zeros(B, 1, dtype=kept.dtype, device=kept.device), kept + 1], dim=1)
+    gx = torch.zeros(B, t_in, D, dtype=gout.dtype, device=gout.device)
+    gx[torch.arange(B, device=gout.device).view(-1, 1), rows] = gout
     return gx
 
 
@@ -132,7 +132,7 @@ def softmax_with_policy(attn: torch.Tensor, policy: torch.Tensor, eps: float = 1
     """
     B, H, T, _ = attn.shape
     p = policy.reshape(B, 1, 1, T).float()
-    diag = torch.eye(T).view(1, 1, T, T)
+    diag = torch.eye(T, device=attn.device).view(1, 1, T, T)
     m = p + (1.0 - p) * diag
     e = torch.exp(attn.float() - attn.float().amax(dim=-1, keepdim=True)) * m
     out = (e + eps / T) / (e.sum(dim=-1, keepdim=True) + eps)

@@ -53,7 +53,7 @@ def test_argument_errors_precede_any_launch(d2s):
     assert lib.d2s_gather_tokens(p + 4, 0, 1, 4, 8, p, 2, 1, p, None) == 2            # misaligned -> D2S_ERR_ALIGN
     assert lib.d2s_ptopk_fwd(p, p, 1, 500, 10, 8, 0.05, p, p, None) == 1 and b"N=500" in lib.d2s_last_error()
     assert lib.d2s_ptopk_fwd(p, p, 1, 196, 98, 8, 0.0, p, p, None) == 1 and b"sigma" in lib.d2s_last_error()
-    assert lib.d2s_attn_policy_fwd(p, None, 1, 1, 8, 2, 48, 0.1, 1e-6, p, None, None) == 1
+    assert lib.d2s_attn_policy_fwd(p, None, 1, 1, 8, 2, 48, 0.1, 1e-6, p, None, None, None) == 1
     assert b"head dim" in lib.d2s_last_error()
     assert lib.d2s_softmax_policy_fwd(p, None, 0, 1, 1, 5000, 1e-6, p, None, None) == 1
     # the tcgen05 GEMM family and the training-attention helpers: shape / alignment contracts

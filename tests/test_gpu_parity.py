@@ -369,6 +369,89 @@ def test_attention_bf16_large_scores_and_full_batch(ops):
     torch.testing.assert_close(cls.sum(-1), torch.ones(B, H, device="cuda"), rtol=1e-3, atol=1e-3)
 
 
+@pytest.mark.parametrize("T,with_policy", [(197, False), (197, True), (138, True), (97, False), (97, True), (40, True)])
+def test_attention_bf16_logits_far_above_the_row_reference(ops, T, with_policy):
+    """The single-pass softmax of the tcgen05 kernel takes its exponent reference from 16 columns of the row.  Rows whose
+    maximum sits ~300 binades above those columns (logits of ~200 nats at columns 20 and T-27, ~50 nats inside the reference
+    columns) must come out like any other row: the kernel raises the reference by whole binades and rescales what it has
+    already produced, exactly.  Every second query is such a row, so lanes of one warp take both paths; at T = 197 without a
+    policy the two large keys fall into different column halves (two warps per row)."""
+    B, H, hd = 2, 6, 64
+    g = fx.gen(130 + T)
+    qkv = torch.randn(B, T, 3, H, hd, generator=g) * 0.5
+    u = torch.nn.functional.normalize(torch.randn(hd, generator=g), dim=0)
+    j1, j2 = 20, T - 13
+    qkv[:, 0::2, 0] += 40.0 * u
+    qkv[:, j1, 1] = 40.0 * u
+    qkv[:, j2, 1] = 40.2 * u
+    qkv[:, 5, 1] = 10.0 * u
+    qkv = qkv.reshape(B, T, 3 * H * hd).bfloat16()
+    pol = None
+    if with_policy:
+        pol = (torch.rand(B, T, generator=g) > 0.3).float()
+        pol[:, 0] = 1
+        pol[0, j1], pol[0, j2] = 1, 0          # image 0: the row maximum itself is masked out (the eps terms follow the true max)
+        pol[1, j1], pol[1, j2] = 1, 1
+    out, cls = ops.attention_core(cu(qkv), H, policy=None if pol is None else cu(pol), want_cls_row=True)
+    ro, rc = oo.attention_core(qkv.float().view(B, T, 3, H, hd), H, policy=pol)
+    s = torch.einsum("bihd,bjhd->bhij", qkv.float().view(B, T, 3, H, hd)[:, :, 0], qkv.float().view(B, T, 3, H, hd)[:, :, 1]) / 8
+    assert float((s[:, :, 0::2].amax(-1) - s[:, :, 0::2, :16].amax(-1)).min()) > 100       # the case is really exercised
+    assert bool(torch.isfinite(out).all())
+    torch.testing.assert_close(out.cpu().float(), ro, rtol=1e-2, atol=1e-2)
+    torch.testing.assert_close(cls.cpu(), rc, rtol=1e-2, atol=2e-4)
+
+
+@pytest.mark.parametrize("T,with_policy", [(197, True), (197, False), (138, True), (97, True), (16, False)])
+def test_attention_bf16_row_statistics(d2s, T, with_policy):
+    """`stats` of d2s_attn_policy_fwd: (m', 1/den, c/den) per query row reproduce the reference probabilities,
+    P_ij = 2^(k2 s_ij - m') m_ij / den + c / den  (what d2s_attn_policy_bwd recomputes P from)."""
+    B, H, hd = 2, 3, 64
+    qkv = (fx.randn(140 + T, B, T, 3 * H * hd) * 0.8).bfloat16()
+    pol = None
+    if with_policy:
+        pol = (torch.rand(B, T, generator=fx.gen(141 + T)) > 0.3).float()
+        pol[:, 0] = 1
+    q_d, out = cu(qkv), torch.empty(B, T, H * hd, dtype=torch.bfloat16, device="cuda")
+    stats = torch.full((B, H, T, 4), float("nan"), device="cuda")
+    pol_d = None if pol is None else cu(pol)
+    d2s._lib.call("d2s_attn_policy_fwd", q_d.data_ptr(), None if pol is None else pol_d.data_ptr(), 1, B, T, H, hd, hd ** -0.5, 1e-6,
+                  out.data_ptr(), None, stats.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    st = stats.cpu()
+    assert bool(torch.isfinite(st[..., :3]).all())
+    v = qkv.float().view(B, T, 3, H, hd)
+    s = torch.einsum("bihd,bjhd->bhij", v[:, :, 0], v[:, :, 1]) * hd ** -0.5
+    ref = oo.softmax_with_policy(s, pol.view(B, T, 1)) if pol is not None else torch.softmax(s, -1)
+    k2s = s * 1.4426950408889634
+    e = torch.exp2(k2s - st[..., 0:1])
+    if pol is not None:
+        e = e * (pol.view(B, 1, 1, T) + (1 - pol.view(B, 1, 1, T)) * torch.eye(T).view(1, 1, T, T))
+    torch.testing.assert_close(e * st[..., 1:2] + st[..., 2:3], ref, rtol=2e-4, atol=1e-7)
+    assert bool((st[..., 0] == st[..., 0].round()).all())            # the reference is a whole number of binades
+    assert float((k2s.amax(-1) - st[..., 0]).max()) <= 101.0         # and never more than ~100 binades below the row maximum
+
+
+def test_attention_train_full_batch_against_torch_autograd(ops):
+    """BASELINE configs[2] shape (B = 256 per GPU, T = 197, 6 heads): forward + backward of the tcgen05 training attention
+    against torch's fp32 autograd of the reference formulas on the same device; d policy sums 256 x 6 x 197 rows."""
+    B, T, H, hd = 256, 197, 6, 64
+    g = torch.Generator(device="cuda").manual_seed(5)
+    qkv = (torch.randn(B, T, 3 * H * hd, device="cuda", generator=g) * 0.7).bfloat16()
+    pol = (torch.rand(B, T, 1, device="cuda", generator=g) > 0.3).float()
+    pol[:, 0] = 1
+    go = (torch.randn(B, T, H * hd, device="cuda", generator=g) * 0.5).bfloat16()
+    q1, p1 = qkv.clone().requires_grad_(True), pol.clone().requires_grad_(True)
+    o1, _ = ops.attention_train(q1, H, policy=p1)
+    (o1.float() * go.float()).sum().backward()
+    q2, p2 = qkv.float().requires_grad_(True), pol.clone().requires_grad_(True)
+    o2, _ = oo.attention_core(q2.view(B, T, 3, H, hd), H, policy=p2)
+    (o2 * go.float()).sum().backward()
+    torch.testing.assert_close(o1.detach().float(), o2.detach(), rtol=2e-2, atol=2e-2)
+    assert float((q1.grad.float() - q2.grad).abs().max()) <= 3e-2 * float(q2.grad.abs().max())
+    assert float((q1.grad.float() - q2.grad).norm()) <= 1e-2 * float(q2.grad.norm())
+    assert float((p1.grad - p2.grad).abs().max()) <= 1e-2 * float(p2.grad.abs().max())
+    assert float((p1.grad - p2.grad).norm()) <= 5e-3 * float(p2.grad.norm())
+
+
 def test_attention_golden_module(d2s, ops):
     c = C["attn"]
     sd = fx.seeded_state_dict(c["shapes"], c["w_seed"])
@@ -703,10 +786,13 @@ def test_score_tail_a_gelu_on_load_and_prev_gather(ops):
     assert torch.equal(pk1.cpu(), torch.ones(B, K))
 
 
-@pytest.mark.parametrize("B,T,H,frac", [(3, 197, 6, False), (2, 138, 6, True), (2, 97, 6, True), (2, 64, 3, False), (1, 8, 2, True)])
+@pytest.mark.parametrize("B,T,H,frac", [(3, 197, 6, False), (2, 138, 6, True), (2, 97, 6, True), (2, 64, 3, False), (1, 8, 2, True),
+                                        (2, 208, 3, True), (1, 200, 2, False), (2, 129, 2, True), (2, 128, 2, False), (3, 1, 2, False),
+                                        (1, 250, 2, True)])
 def test_attention_train_fwd_bwd_vs_oracle_autograd(ops, B, T, H, frac):
-    """bf16 training attention (per-head strided GEMMs on the packed qkv + padded-row policy softmax kernels) against the
-    fp32 oracle's autograd on the same bf16-rounded inputs: output, CLS row, d qkv and d policy at bf16 tolerance."""
+    """bf16 training attention (T <= 208: the tcgen05 flash forward with row statistics + d2s_attn_policy_bwd; beyond: per-head
+    GEMMs on a head-major copy + padded-row policy softmax kernels) against the fp32 oracle's autograd on the same
+    bf16-rounded inputs: output, CLS row, d qkv and d policy at bf16 tolerance."""
     hd = 64
     qkv = (fx.randn(600 + T, B, T, 3 * H * hd) * 0.7).bfloat16()
     pol = torch.rand(B, T, 1, generator=fx.gen(601 + T)) if frac else (torch.rand(B, T, 1, generator=fx.gen(602 + T)) > 0.3).float()
