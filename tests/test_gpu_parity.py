@@ -813,7 +813,9 @@ def test_attention_train_fwd_bwd_vs_oracle_autograd(ops, B, T, H, frac):
     gq1, gq2 = q1.grad.cpu().float(), q2.grad
     assert float((gq1 - gq2).abs().max()) <= 3e-2 * float(gq2.abs().max()) + 1e-3
     gp1, gp2 = p1.grad.cpu().float(), p2.grad
-    assert float((gp1 - gp2).abs().max()) <= 3e-2 * float(gp2.abs().max()) + 1e-3
+    # d policy is accumulated in fp32 from fp32 scores: 1e-3 on the flash path (the GEMM path rounds dP and P to bf16 first)
+    ptol = 1e-3 if T <= ops.FLASH_MAX_T else 3e-2
+    assert float((gp1 - gp2).abs().max()) <= ptol * float(gp2.abs().max()) + 1e-5
     # no policy: plain softmax attention
     q3 = cu(qkv).requires_grad_(True)
     o3, none = ops.attention_train(q3, H)
