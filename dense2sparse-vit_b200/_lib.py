@@ -41,7 +41,6 @@ SIGNATURES = {
     "d2s_merge_heads_bf16": [_p, _i, _i, _i, _i, _i, _i, _p, _p],
     "d2s_colsum_bf16": [_p, ctypes.c_longlong, _i, _p, _p],
     "d2s_gelu_bwd_colsum_bf16": [_p, _p, ctypes.c_longlong, _i, _p, _p, _p],
-    "d2s_linear_wgrad_bf16": [_p, _p, _i, _i, _i, _p, _p, _p],
     "d2s_attn_policy_fwd": [_p, _p, _i, _i, _i, _i, _i, _f, _f, _p, _p, _p, _p],
     "d2s_attn_policy_bwd": [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _f, _p, _p, _p],
     "d2s_pool_act": [_p, _p, _i, _i, _i, _i, _i, _p, _p, _p],
@@ -53,7 +52,6 @@ SIGNATURES = {
     "d2s_layernorm_bwd": [_p, _i, _p, _i, _p, _p, ctypes.c_longlong, _i, _p, _p, _p, _p],
     "d2s_add_layernorm_fwd": [_p, _p, _i, _p, _p, ctypes.c_longlong, _i, _f, _p, _p, _i, _p, _p],
     "d2s_add_layernorm_bwd": [_p, _i, _p, _i, _p, _p, _p, ctypes.c_longlong, _i, _p, _p, _p, _p],
-    "d2s_linear_act_bf16": [_p, _p, _p, _i, _i, _i, _i, _p, _p],
     "d2s_linear_act_pair_bf16": [_p, _p, _p, _i, _i, _i, _i, _p, _p],
     "d2s_linear_residual_ln_bf16": [_p, _p, _p, _p, _p, _p, _f, _i, _i, _i, _p, _p, _p],
     "d2s_gather_layernorm": [_p, _p, _p, _p, _i, _i, _i, _i, _i, _f, _p, _p, _p],

@@ -401,13 +401,9 @@ static int launch_bwd(const CUtensorMap* maps, const float* policy, const float*
                       int Tp, float scale, void* dqkv, float* gpolicy, cudaStream_t stream) {
   auto kern = attn_tc_bwd_kernel<kNT, kPol>;
   const size_t smem = bwd_smem_bytes(kNT, Tp);
-  static bool smem_set = false;   // one per instantiation: opt in to the size the largest T of this variant needs
-  if (!smem_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)bwd_smem_bytes(kNT, kNT == 1 ? kTileRows : kBwdMaxT));
-    D2S_REQUIRE(e == cudaSuccess, D2S_ERR_CUDA, "attn_policy_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    smem_set = true;
-  }
+  static SmemOptIn opt;   // one per instantiation: opt in to the size the largest T of this variant needs
+  cudaError_t e = opt_in_smem(opt, kern, (int)bwd_smem_bytes(kNT, kNT == 1 ? kTileRows : kBwdMaxT));
+  D2S_REQUIRE(e == cudaSuccess, D2S_ERR_CUDA, "attn_policy_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   const int grid = units < kNumSMs ? units : kNumSMs;
   kern<<<grid, kBwdThreads, smem, stream>>>(maps[0], maps[1], maps[2], maps[3], policy, stats, g_cls, units, T, H, Tp, scale,
                                             (__nv_bfloat16*)dqkv, gpolicy);

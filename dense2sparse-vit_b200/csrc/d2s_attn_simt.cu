@@ -588,12 +588,9 @@ static int launch_attn_simt(const void* qkv, const float* policy, int B, int T, 
                                        (size_t)kAttnWarps * kQR * HD + (size_t)kAttnWarps * kQR * T);
   D2S_REQUIRE(smem <= 227 * 1024, D2S_ERR_ARG, "attn(simt): T=%d needs %zu B of shared memory", T, smem);
   auto kern = attn_simt_fwd_kernel<T_, HD>;
-  static bool smem_set = false;  // one flag per template instantiation
-  if (!smem_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    D2S_REQUIRE(e == cudaSuccess, D2S_ERR_CUDA, "attn(simt): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    smem_set = true;
-  }
+  static SmemOptIn opt;  // one per template instantiation
+  cudaError_t e = opt_in_smem(opt, kern, 227 * 1024);
+  D2S_REQUIRE(e == cudaSuccess, D2S_ERR_CUDA, "attn(simt): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   // enough CTAs to fill the machine: split the query rows when B*H is small
   int chunks = ceil_div(2 * kNumSMs, B * H);
   const int max_chunks = ceil_div(T, kAttnWarps * kQR);
@@ -705,12 +702,9 @@ extern "C" int d2s_softmax_policy_bwd_ld(const void* attn, const float* policy, 
   if (B == 0) return D2S_OK;
   dim3 grid(ceil_div(T, kRowsPerCta), B * H);
   const size_t smem = (size_t)2 * kRowsPerCta * ld * 2;   // scores block + gradient block (<= 64 KB at ld = 256)
-  static bool smem_set = false;
-  if (!smem_set) {
-    cudaError_t e = cudaFuncSetAttribute(softmax_policy_bwd_vec_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-    D2S_REQUIRE(e == cudaSuccess, D2S_ERR_CUDA, "softmax_policy_bwd_ld: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    smem_set = true;
-  }
+  static SmemOptIn opt;
+  cudaError_t e = opt_in_smem(opt, softmax_policy_bwd_vec_kernel<32>, 64 * 1024);
+  D2S_REQUIRE(e == cudaSuccess, D2S_ERR_CUDA, "softmax_policy_bwd_ld: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   if (ld <= 128)
     softmax_policy_bwd_vec_kernel<16><<<grid, kRowThreads, smem, (cudaStream_t)stream>>>(
         (const __nv_bfloat16*)attn, policy, (const __nv_bfloat16*)gout, stats, H, T, rows, ld, eps, (__nv_bfloat16*)gattn, gpolicy);

@@ -464,12 +464,9 @@ static int launch_tc(const CUtensorMap& map_a, const CUtensorMap& map_b, const f
   const size_t budget = (size_t)(228 * 1024) / per_sm - 1024;
   const int kbufs = tc_smem_bytes(kNT, Tkp, 2) <= budget ? 2 : 1;
   const size_t smem = tc_smem_bytes(kNT, Tkp, kbufs);
-  static size_t smem_set = 0;  // one per instantiation; the opt-in is sticky, only ever raised
-  if (smem > smem_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);
-    D2S_REQUIRE(e == cudaSuccess, D2S_ERR_CUDA, "attn_policy_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    smem_set = 113 * 1024;
-  }
+  static SmemOptIn opt;  // one per instantiation
+  cudaError_t e = opt_in_smem(opt, kern, 113 * 1024);
+  D2S_REQUIRE(e == cudaSuccess, D2S_ERR_CUDA, "attn_policy_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   const int grid = units < per_sm * kNumSMs ? units : per_sm * kNumSMs;
   kern<<<grid, tc_threads(kSW), smem, stream>>>(map_a, map_b, policy, units, T, H, Tkp, kbufs, scale, eps,
                                            (__nv_bfloat16*)out, cls_row, stats);

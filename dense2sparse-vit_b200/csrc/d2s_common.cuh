@@ -28,6 +28,19 @@ void count_launch(int n = 1);
     }                                           \
   } while (0)
 
+// The opt-in to more than 48 KB of dynamic shared memory is a per-DEVICE function attribute: remembered per call site and per
+// device ordinal, so that a process driving several GPUs (model on cuda:1 while cuda:0 is current elsewhere) sets it on each.
+struct SmemOptIn { unsigned long long done = 0; };
+template <typename K>
+static inline cudaError_t opt_in_smem(SmemOptIn& st, K kern, int bytes) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && ((st.done >> dev) & 1ull)) return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess && dev >= 0 && dev < 64) st.done |= 1ull << dev;
+  return e;
+}
+
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 static inline int  ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline size_t elem_size(int dtype) { return dtype == D2S_BF16 ? 2 : 4; }

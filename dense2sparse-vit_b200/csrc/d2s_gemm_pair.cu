@@ -447,12 +447,9 @@ static int gp_launch(const CUtensorMap& ma, const CUtensorMap& mw, const CUtenso
   const size_t smem = 1024 + (size_t)Cfg::STAGES * kStage + (size_t)Cfg::BLOCKS * kGpBlkBytes + sizeof(GpBars) +
                       (MODE == kGpModeLn ? (size_t)3 * Cfg::UN * NSUB * 4 + 4 * 128 * sizeof(float2) + 16 : (size_t)p.N * 4);
   D2S_REQUIRE(smem <= 227 * 1024, D2S_ERR_ARG, "%s: needs %zu B of shared memory", what, smem);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_pair_kernel<MODE, NSUB, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    D2S_REQUIRE(e == cudaSuccess, D2S_ERR_CUDA, "%s: cudaFuncSetAttribute: %s", what, cudaGetErrorString(e));
-    attr_set = true;
-  }
+  static SmemOptIn opt;
+  cudaError_t e = opt_in_smem(opt, gemm_pair_kernel<MODE, NSUB, ACT>, 227 * 1024);
+  D2S_REQUIRE(e == cudaSuccess, D2S_ERR_CUDA, "%s: cudaFuncSetAttribute: %s", what, cudaGetErrorString(e));
   const int pair_tiles = (p.M + 2 * kGpBM - 1) / (2 * kGpBM);
   const int pairs = pair_tiles < kNumSMs / 2 ? pair_tiles : kNumSMs / 2;
   gemm_pair_kernel<MODE, NSUB, ACT><<<2 * pairs, (2 + 4 * Cfg::PARTS) * 32, smem, stream>>>(ma, mw, mo, p);

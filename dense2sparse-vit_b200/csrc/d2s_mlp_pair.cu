@@ -521,12 +521,9 @@ extern "C" int d2s_mlp_residual_ln_bf16(const void* h, const void* w1, const voi
   const size_t smem = 1024 + (size_t)kMpKB * kMpA1Blk + 2 * (size_t)kMpPBlk + (size_t)kMpW1Slots * kMpW1Blk +
                       (size_t)kMpW2Slots * kMpW2Blk + sizeof(MpBars) + (size_t)HID * 4 + 2 * kMpD * 4 + (size_t)kMpOutWarps * 2048 + 32;
   D2S_REQUIRE(smem <= 227 * 1024, D2S_ERR_ARG, "mlp_residual_ln: needs %zu B of shared memory", smem);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(mlp_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    D2S_REQUIRE(e == cudaSuccess, D2S_ERR_CUDA, "mlp_residual_ln: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    attr_set = true;
-  }
+  static SmemOptIn opt;
+  cudaError_t e = opt_in_smem(opt, mlp_pair_kernel, 227 * 1024);
+  D2S_REQUIRE(e == cudaSuccess, D2S_ERR_CUDA, "mlp_residual_ln: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   const int pair_tiles = (M + 2 * kMpBM - 1) / (2 * kMpBM);
   const int pairs = pair_tiles < kNumSMs / 2 ? pair_tiles : kNumSMs / 2;
   mlp_pair_kernel<<<2 * pairs, kMpThreads, smem, (cudaStream_t)stream>>>(ma, mw1, mw2, p);

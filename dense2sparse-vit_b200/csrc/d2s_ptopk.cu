@@ -262,13 +262,9 @@ static int ptopk_launch(bool rng, const float* x, const float* noise, uint64_t s
     if (t < best - 1e-9) { best = t; G = g; }
   }
   auto kern = rng ? ptopk_fwd_kernel<true> : ptopk_fwd_kernel<false>;
-  static bool smem_set[2] = {false, false};
-  cudaError_t e;
-  if (!smem_set[rng ? 1 : 0]) {
-    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    D2S_REQUIRE(e == cudaSuccess, D2S_ERR_CUDA, "ptopk_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    smem_set[rng ? 1 : 0] = true;
-  }
+  static SmemOptIn opt[2];
+  cudaError_t e = opt_in_smem(opt[rng ? 1 : 0], kern, 227 * 1024);
+  D2S_REQUIRE(e == cudaSuccess, D2S_ERR_CUDA, "ptopk_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(G, B);
   cfg.blockDim = dim3(kPtThreads);

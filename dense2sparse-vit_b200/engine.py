@@ -33,6 +33,45 @@ def _needs_grad(*ts):
     return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in ts)
 
 
+def _d2s_float(t):
+    """The d2s kernels read float32 / bfloat16 and, under autocast, can only stand in for torch when the autocast dtype is bf16
+    (fp16 autocast -- the mode ddp_training.py:84-85,130 sets a GradScaler up for -- keeps torch's own modules)."""
+    if t.dtype not in (torch.float32, torch.bfloat16):
+        return False
+    return not torch.is_autocast_enabled("cuda") or torch.get_autocast_dtype("cuda") == torch.bfloat16
+
+
+def _ln_rows_ok(x):
+    """Row widths the LayerNorm-family kernels take: multiples of 8, up to 1536 (bf16) / 768 (fp32)."""
+    return x.shape[-1] % 8 == 0 and x.shape[-1] <= (1536 if x.dtype == torch.bfloat16 else 768)
+
+
+def _attn_kernel_ok(qkv, H):
+    """Shapes of d2s_attn_policy_fwd: bf16 -> tcgen05 kernel (hd 64), fp32 -> SIMT kernel (hd 32 / 64); T <= 256."""
+    hd = qkv.shape[-1] // 3 // H
+    if qkv.shape[1] > 256 or qkv.shape[-1] != 3 * H * hd:
+        return False
+    return (qkv.dtype == torch.bfloat16 and hd == 64) or (qkv.dtype == torch.float32 and hd in (32, 64))
+
+
+def _softmax_policy_torch(attn, policy, eps=1e-6):
+    """Attention.softmax_with_policy (dynamic_vit.py:195-214) in plain torch, for dtypes / shapes the kernels do not take:
+    keep mask p_j off the diagonal and 1 on it, fp32 exponentials of (attn - rowmax), eps/N added to every entry."""
+    B, H, N, _ = attn.shape
+    p = policy.reshape(B, 1, 1, N).to(torch.float32)
+    mask = p + (1.0 - p) * torch.eye(N, dtype=torch.float32, device=attn.device).view(1, 1, N, N)
+    e = (attn - attn.amax(dim=-1, keepdim=True)).to(torch.float32).exp() * mask
+    return ((e + eps / N) / (e.sum(dim=-1, keepdim=True) + eps)).type_as(attn)
+
+
+def softmax_with_policy(attn, policy, eps=1e-6):
+    """Attention.softmax_with_policy (dynamic_vit.py:195-214): the one-pass d2s kernel pair (forward, backward in both
+    arguments) for fp32 / bf16 CUDA tensors; other CUDA float types (fp16 autocast) take the torch restatement."""
+    if attn.is_cuda and attn.dtype not in (torch.float32, torch.bfloat16):
+        return _softmax_policy_torch(attn, policy, eps) if policy is not None else attn.softmax(dim=-1)
+    return ops.softmax_with_policy(attn, policy, eps)
+
+
 def patch_embed_forward(m, img):
     """Conv2d(kernel=stride=patch) as im2col + GEMM (dynamic_vit.py:286-303).  Avoids cuDNN's TF32 conv path so fp32
     runs stay within 1e-4 of the reference; the im2col is one d2s kernel when no gradient flows into the image."""
@@ -56,12 +95,18 @@ def attention_pre_proj(m, x, policy=None, return_cls_attn=False):
     H = m.num_heads
     qkv = ops.linear_train(m.qkv, x)
     if _needs_grad(qkv, policy) and qkv.is_cuda and qkv.dtype == torch.bfloat16 and T <= 256 and _TRAIN_ATTN:
-        # training, bf16: per-head strided GEMMs on the packed tensor around the padded-row policy softmax
+        # training, bf16: the tcgen05 flash forward / backward pair on the packed tensor (T <= 208, hd 64), else per-head GEMMs
+        # on a head-major copy around the padded-row policy softmax
         o, cls_attn = ops.attention_train(qkv, H, policy=policy, scale=m.scale, want_cls_row=return_cls_attn)
-    elif _needs_grad(qkv, policy):
+    elif _needs_grad(qkv, policy) or not qkv.is_cuda or not _attn_kernel_ok(qkv, H):
         q, k, v = qkv.reshape(B, T, 3, H, C // H).permute(2, 0, 3, 1, 4).unbind(0)
         attn = (q @ k.transpose(-2, -1)) * m.scale
-        attn = ops.softmax_with_policy(attn, policy)
+        if qkv.is_cuda:
+            attn = softmax_with_policy(attn, policy)
+        elif policy is None:
+            attn = attn.softmax(dim=-1)
+        else:                                  # CPU tensors (module construction / shape tests off the GPU)
+            attn = _softmax_policy_torch(attn, policy)
         o = (attn @ v).transpose(1, 2).reshape(B, T, C)
         cls_attn = attn[:, :, 0, :] if return_cls_attn else None
     else:
@@ -89,14 +134,14 @@ def _drop_off(d, training):
 def _fusable(m, x, *extra):
     """The carried-residual inference path applies when no gradient is needed and the norms are plain LayerNorms."""
     return (not _needs_grad(x, *extra, m.norm1.weight if hasattr(m.norm1, "weight") else None)
-            and x.is_cuda and _is_plain_ln(m.norm1) and _is_plain_ln(m.norm2)
+            and x.is_cuda and _d2s_float(x) and _ln_rows_ok(x) and _is_plain_ln(m.norm1) and _is_plain_ln(m.norm2)
             and isinstance(m.drop_path, torch.nn.Identity) and _drop_off(m.attn.proj_drop, m.training))
 
 
 def _train_fusable(m, x, y=None):
     """The training path with fused residual adds applies: CUDA, plain LayerNorms on rows the d2s LayerNorm kernels take, no
     stochastic depth, and a residual stream of one dtype."""
-    return (_FUSED_ADD_LN_TRAIN and x.is_cuda and x.dtype in (torch.float32, torch.bfloat16) and (y is None or y.dtype == x.dtype)
+    return (_FUSED_ADD_LN_TRAIN and x.is_cuda and _d2s_float(x) and (y is None or y.dtype == x.dtype)
             and _is_plain_ln(m.norm1) and _is_plain_ln(m.norm2) and x.shape[-1] % 8 == 0 and x.shape[-1] <= 768
             and isinstance(m.drop_path, torch.nn.Identity) and isinstance(m.mlp, torch.nn.Module))
 
@@ -110,9 +155,9 @@ def _mlp_is_plain(m, h):
 def mlp_hidden(m, h):
     """act(fc1(h)) of Mlp.forward (dynamic_vit.py:159-175) for inference: the tcgen05 GEMM with the exact-erf GELU in its
     epilogue when the shapes allow, else cuBLAS + the in-place d2s GELU kernel."""
-    if (_FUSED_FC1 and h.dtype == torch.bfloat16 and m.fc1.weight.dtype == torch.bfloat16 and m.fc1.out_features % 256 == 0
+    if (_FUSED_FC1 and _FUSED_PAIR and h.dtype == torch.bfloat16 and m.fc1.weight.dtype == torch.bfloat16 and m.fc1.out_features % 256 == 0
             and m.fc1.out_features <= 4096 and m.fc1.in_features % 64 == 0):
-        return ops.linear_act(h, m.fc1.weight, m.fc1.bias, ops.ACT_GELU, pair=_FUSED_PAIR)
+        return ops.linear_act(h, m.fc1.weight, m.fc1.bias, ops.ACT_GELU)
     u = m.fc1(h)
     ops.bias_act_(u, None, ops.ACT_GELU)
     return u
@@ -142,7 +187,7 @@ def _pair_ok(lin, a, x):
 def norm_forward(n, x):
     """A model LayerNorm on the training path: the d2s forward/backward pair when it applies (plain LayerNorm on a CUDA
     tensor whose rows are multiples of 8 elements), torch otherwise."""
-    if _is_plain_ln(n) and x.is_cuda and x.dtype in (torch.float32, torch.bfloat16) and x.shape[-1] % 8 == 0 \
+    if _is_plain_ln(n) and x.is_cuda and _d2s_float(x) and x.shape[-1] % 8 == 0 \
             and x.shape[-1] <= 768 and len(n.normalized_shape) == 1:
         return ops.layer_norm(x, n.weight, n.bias, n.eps)
     return n(x)
@@ -299,7 +344,8 @@ class _Stream:
 
     def normed(self, norm, row0=0, rows=None):
         """(x + y, norm((x + y)[:, row0:])) with the add folded in; leaves the stream holding the summed x."""
-        if _is_plain_ln(norm) and self.x.is_cuda and not _needs_grad(self.x, self.y, norm.weight):
+        if (_is_plain_ln(norm) and self.x.is_cuda and _d2s_float(self.x) and _ln_rows_ok(self.x)
+                and not _needs_grad(self.x, self.y, norm.weight)):
             return self._sum_norm(norm, row0)
         x = self.value()
         return x, norm(x[:, row0:])
@@ -307,7 +353,8 @@ class _Stream:
     def cls_normed(self, norm):
         """norm(x + y)[:, 0]: only the CLS row (what the eval heads consume)."""
         self._flush_gather()
-        if _is_plain_ln(norm) and self.x.is_cuda and not _needs_grad(self.x, self.y, norm.weight):
+        if (_is_plain_ln(norm) and self.x.is_cuda and _d2s_float(self.x) and _ln_rows_ok(self.x)
+                and not _needs_grad(self.x, self.y, norm.weight)):
             if self.mlp is not None:                     # the last MLP is only needed for the CLS rows
                 h, m = self.mlp
                 y0 = m.fc2(mlp_hidden(m, h[:, :1].contiguous()))
@@ -420,9 +467,9 @@ def _predictor_b_fusable(m, dtype):
 
 def _linear_act(x, lin, act):
     """act(lin(x)): the tcgen05 GEMM with the activation in its epilogue when the shape allows, else cuBLAS + in-place act."""
-    if (x.dtype == torch.bfloat16 and lin.weight.dtype == torch.bfloat16 and lin.out_features % 256 == 0
+    if (_FUSED_PAIR and x.dtype == torch.bfloat16 and lin.weight.dtype == torch.bfloat16 and lin.out_features % 256 == 0
             and lin.out_features <= 4096 and lin.in_features % 64 == 0):
-        return ops.linear_act(x, lin.weight, lin.bias, act, pair=_FUSED_PAIR)
+        return ops.linear_act(x, lin.weight, lin.bias, act)
     u = lin(x)
     return ops.bias_act_(u, None, act)
 
@@ -487,7 +534,7 @@ def _embed_stream(model, img):
 
 def _head(model, x):
     # training heads: the final norm keeps torch autocast's fp32 output (the token features go straight into the losses)
-    if _is_plain_ln(model.norm) and x.is_cuda and x.shape[-1] % 8 == 0 and x.shape[-1] <= 768 and x.dtype in (torch.float32, torch.bfloat16):
+    if _is_plain_ln(model.norm) and x.is_cuda and x.shape[-1] % 8 == 0 and x.shape[-1] <= 768 and _d2s_float(x):
         x = ops.layer_norm(x, model.norm.weight, model.norm.bias, model.norm.eps,
                            out_dtype=torch.float32 if torch.is_autocast_enabled("cuda") else None)
     else:
@@ -534,7 +581,8 @@ def variant_a_forward(model, img):
             else:
                 k = int(INIT_N * model.token_ratio[p_count])
                 ln = _pred_ln(pred)
-                if ln is not None and _predictor_a_fusable(pred) and not _needs_grad(st.x, st.y, ln.weight):
+                if (ln is not None and _predictor_a_fusable(pred) and st._probe().is_cuda and _d2s_float(st._probe())
+                        and not _needs_grad(st.x, st.y, ln.weight)):
                     # residual add folded into the predictor's LayerNorm over x[:, 1:]; fused predictor body
                     x, hn = st.normed(ln, row0=1)
                     _, keep_policy, prev_f32 = predictor_a_select(pred, hn, prev_f32, k)
@@ -583,7 +631,8 @@ def variant_b_forward(model, img, stacked_cls_attn_weights=None):
             pred = model.score_predictor[p_count]
             if thr is None:
                 ln = _pred_ln(pred)
-                if ln is not None and pred.topk_selection and not _needs_grad(st.x, st.y, ln.weight):
+                if (ln is not None and pred.topk_selection and st._probe().is_cuda and _d2s_float(st._probe())
+                        and not _needs_grad(st.x, st.y, ln.weight)):
                     x, hn = st.normed(ln, row0=1)
                     if _predictor_b_fusable(pred, hn.dtype):
                         pred_logits, pred_score, kept, dropped = predictor_b_select_fused(pred, hn, num_keep_node)
@@ -651,19 +700,33 @@ def _frozen_bf16_shadow(model, img):
     computes in bf16 anyway -- through a cast of every fp32 weight and bias on every call and, here, through the unfused
     fallbacks, because the fused inference kernels take bf16 weights.  Its weights cannot change between steps, so a bf16 copy
     is kept and the call runs on the fused inference path.  The copy is rebuilt when any parameter's storage or version counter
-    changes (load_state_dict, .to(), in-place edits).  Returns None when this does not apply."""
+    changes (load_state_dict, .to(), in-place edits through the tensor itself); invalidate_frozen_copies() drops it explicitly.
+    Numerics: torch autocast keeps the fp32 residual stream and fp32 LayerNorm / softmax of an fp32 module; the copy computes
+    like `model.to(bfloat16)` (bf16 residual stream).  Teacher logits / tokens / CLS rows agree with the per-call-cast path to
+    bf16 accuracy (3e-2 of the tensor's max, pinned by tests/test_gpu_models.py::test_frozen_teacher_under_autocast_...);
+    D2S_FROZEN_BF16=0 keeps torch's autocast numerics.  Returns None when this does not apply."""
     if not (_FROZEN_BF16 and img.is_cuda and not model.training and torch.is_autocast_enabled("cuda")
             and torch.get_autocast_dtype("cuda") == torch.bfloat16):
         return None
     params = list(model.parameters())
     if not params or any(p.requires_grad or p.dtype != torch.float32 or not p.is_cuda for p in params):
         return None
-    fp = hash(tuple((p.data_ptr(), p._version) for p in params))
+    # storage + version counter of every parameter and buffer.  Edits that bypass the version counter (`p.data.copy_()`, an EMA
+    # teacher updated through .data) are NOT seen: call invalidate_frozen_copies(model) after those, or set D2S_FROZEN_BF16=0.
+    fp = hash(tuple((p.data_ptr(), p._version) for p in params + list(model.buffers())))
     hit = _SHADOWS.get(model)
     if hit is None or hit[0] != fp:
         hit = (fp, copy.deepcopy(model).to(torch.bfloat16).eval())
         _SHADOWS[model] = hit
     return hit[1]
+
+
+def invalidate_frozen_copies(model=None):
+    """Drop the cached bf16 copy of `model` (all cached copies when None): the next call under bf16 autocast rebuilds it."""
+    if model is None:
+        _SHADOWS.clear()
+    else:
+        _SHADOWS.pop(model, None)
 
 
 def teacher_forward(model, img, with_cls_attn=True):

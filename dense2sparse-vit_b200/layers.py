@@ -53,7 +53,7 @@ class Attention(nn.Module):
         self.proj_drop = nn.Dropout(proj_drop)
 
     def softmax_with_policy(self, attn, policy, eps=1e-6):
-        return ops.softmax_with_policy(attn, policy, eps)
+        return engine.softmax_with_policy(attn, policy, eps)
 
     def forward(self, x, policy, return_cls_attn=False):
         return engine.attention_forward(self, x, policy, return_cls_attn)

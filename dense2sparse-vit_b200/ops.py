@@ -22,6 +22,20 @@ def _dtype_code(t: torch.Tensor) -> int:
     raise TypeError(f"d2s kernels take float32 or bfloat16 tensors, got {t.dtype}")
 
 
+def _copy_code(t: torch.Tensor) -> int:
+    """dtype code for the pure copy kernels (gather / scatter): only the element size matters."""
+    if t.element_size() == 2:
+        return BF16
+    if t.element_size() == 4:
+        return F32
+    raise TypeError(f"d2s gather/scatter kernels move 2- and 4-byte elements, got {t.dtype}")
+
+
+def _as_kernel_float(t):
+    """Tensors of other float types (fp16 under autocast) enter the fp32-math tail kernels as fp32."""
+    return t if t.dtype in (torch.float32, torch.bfloat16) else t.float()
+
+
 def _check_cuda(*ts):
     for t in ts:
         if t is not None and not t.is_cuda:
@@ -32,8 +46,21 @@ def _ptr(t):
     return None if t is None else t.data_ptr()
 
 
-def _stream():
-    return torch.cuda.current_stream().cuda_stream
+def _stream(t):
+    """(device, handle of torch's current stream ON THAT DEVICE) for the tensor a call works on."""
+    return t.device, torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _call(name, *args):
+    """One C-ABI call; the last argument comes from _stream(tensor).  The library launches (and sets function attributes, and
+    encodes tensor maps) on the CURRENT device: when the tensors live on another one (model.to('cuda:1') without set_device)
+    the call is made under a device guard, like torch's own ops."""
+    dev, stream = args[-1]
+    if dev.index is not None and dev.index != torch.cuda.current_device():
+        with torch.cuda.device(dev):
+            _lib.call(name, *args[:-1], stream)
+    else:
+        _lib.call(name, *args[:-1], stream)
 
 
 def _f32c(t):
@@ -54,7 +81,7 @@ def select_topk(score: torch.Tensor, k: int, order: int = ORDER_INDEX_ASC, want_
         raise RuntimeError(f"select_topk: K={k} outside [0, N={N}]")
     kept = torch.empty(B, k, dtype=torch.int64, device=s.device)
     dropped = torch.empty(B, N - k, dtype=torch.int64, device=s.device) if want_dropped else None
-    _lib.call("d2s_select_topk_f32", _ptr(s), B, N, k, order, _ptr(kept), _ptr(dropped), _stream())
+    _call("d2s_select_topk_f32", _ptr(s), B, N, k, order, _ptr(kept), _ptr(dropped), _stream(s))
     return kept, dropped
 
 
@@ -64,7 +91,7 @@ def score_tail_a(hidden, weight, bias, k=0, gumbel=None, prev=None, act_input=AC
     train (gumbel (B,N,2)): returns (logp, decision (B,N), ysoft (B,N))
     act_input=ACT_GELU: `hidden` is the previous Linear's raw output, the GELU is applied on load."""
     _check_cuda(hidden, weight, bias)
-    h = hidden.detach().contiguous()
+    h = _as_kernel_float(hidden.detach()).contiguous()
     B, N, C = h.shape
     w, b = _f32c(weight), _f32c(bias)
     logp = torch.empty(B, N, 2, dtype=torch.float32, device=h.device)
@@ -72,14 +99,14 @@ def score_tail_a(hidden, weight, bias, k=0, gumbel=None, prev=None, act_input=AC
     if gumbel is None:
         kept = torch.empty(B, k, dtype=torch.int64, device=h.device)
         prev_kept = torch.empty(B, k, dtype=torch.float32, device=h.device) if want_prev_kept else None
-        _lib.call("d2s_score_tail_a", _ptr(h), _dtype_code(h), B, N, C, _ptr(w), _ptr(b), k, None, _ptr(p),
-                  _ptr(logp), _ptr(kept), None, None, int(act_input), _ptr(prev_kept), _stream())
+        _call("d2s_score_tail_a", _ptr(h), _dtype_code(h), B, N, C, _ptr(w), _ptr(b), k, None, _ptr(p),
+                  _ptr(logp), _ptr(kept), None, None, int(act_input), _ptr(prev_kept), _stream(h))
         return (logp, kept, prev_kept) if want_prev_kept else (logp, kept)
     g = _f32c(gumbel)
     decision = torch.empty(B, N, dtype=torch.float32, device=h.device)
     ysoft = torch.empty(B, N, dtype=torch.float32, device=h.device)
-    _lib.call("d2s_score_tail_a", _ptr(h), _dtype_code(h), B, N, C, _ptr(w), _ptr(b), 0, _ptr(g), _ptr(p),
-              _ptr(logp), None, _ptr(decision), _ptr(ysoft), int(act_input), None, _stream())
+    _call("d2s_score_tail_a", _ptr(h), _dtype_code(h), B, N, C, _ptr(w), _ptr(b), 0, _ptr(g), _ptr(p),
+              _ptr(logp), None, _ptr(decision), _ptr(ysoft), int(act_input), None, _stream(h))
     return logp, decision, ysoft
 
 
@@ -87,7 +114,7 @@ def score_tail_b(hidden, ln_weight, ln_bias, weight, bias, k, ln_eps=1e-5, prob_
     """Variant B predictor tail ([LayerNorm]+Linear(C,1)+softmax|sigmoid) fused with the ascending-index
     top-k.  Returns (scores (B,N), probs (B,N), kept (B,k)|None, dropped (B,N-k)|None)."""
     _check_cuda(hidden, weight)
-    h = hidden.detach().contiguous()
+    h = _as_kernel_float(hidden.detach()).contiguous()
     B, N, C = h.shape
     lw, lb = _f32c(ln_weight), _f32c(ln_bias)
     w = _f32c(weight).reshape(-1)
@@ -96,8 +123,8 @@ def score_tail_b(hidden, ln_weight, ln_bias, weight, bias, k, ln_eps=1e-5, prob_
     probs = torch.empty(B, N, dtype=torch.float32, device=h.device)
     kept = torch.empty(B, k, dtype=torch.int64, device=h.device) if select else None
     dropped = torch.empty(B, N - k, dtype=torch.int64, device=h.device) if select else None
-    _lib.call("d2s_score_tail_b", _ptr(h), _dtype_code(h), B, N, C, _ptr(lw), _ptr(lb), float(ln_eps), _ptr(w),
-              _ptr(bz), prob_mode, k, _ptr(scores), _ptr(probs), _ptr(kept), _ptr(dropped), _stream())
+    _call("d2s_score_tail_b", _ptr(h), _dtype_code(h), B, N, C, _ptr(lw), _ptr(lb), float(ln_eps), _ptr(w),
+              _ptr(bz), prob_mode, k, _ptr(scores), _ptr(probs), _ptr(kept), _ptr(dropped), _stream(h))
     return scores, probs, kept, dropped
 
 
@@ -108,7 +135,7 @@ class _GumbelKeep(torch.autograd.Function):
         n = lp.numel() // 2
         pv = _f32c(prev.reshape(-1)) if prev is not None else None
         decision = torch.empty(lp.shape[:-1], dtype=torch.float32, device=lp.device)
-        _lib.call("d2s_gumbel_decision_f32", _ptr(lp), _ptr(g), _ptr(pv), n, _ptr(decision), None, _stream())
+        _call("d2s_gumbel_decision_f32", _ptr(lp), _ptr(g), _ptr(pv), n, _ptr(decision), None, _stream(lp))
         ctx.save_for_backward(lp, g, pv if pv is not None else torch.empty(0, device=lp.device))
         ctx.has_prev = pv is not None
         ctx.in_dtype = logp.dtype
@@ -123,8 +150,8 @@ class _GumbelKeep(torch.autograd.Function):
         glogp = torch.empty_like(lp)
         want_gprev = ctx.has_prev and ctx.needs_input_grad[2]
         gprev = torch.empty(n, dtype=torch.float32, device=lp.device) if want_gprev else None
-        _lib.call("d2s_gumbel_decision_bwd_f32", _ptr(g), _ptr(lp), _ptr(gm), _ptr(pv) if ctx.has_prev else None, n,
-                  _ptr(glogp), _ptr(gprev), _stream())
+        _call("d2s_gumbel_decision_bwd_f32", _ptr(g), _ptr(lp), _ptr(gm), _ptr(pv) if ctx.has_prev else None, n,
+                  _ptr(glogp), _ptr(gprev), _stream(g))
         if gprev is not None:
             gprev = gprev.reshape(ctx.prev_meta[0]).to(ctx.prev_meta[1])
         return glogp.to(ctx.in_dtype), None, gprev
@@ -149,7 +176,7 @@ class _GatherTokens(torch.autograd.Function):
         B, T, D = xc.shape
         K = ic.shape[1]
         out = torch.empty(B, K + (1 if prepend_cls else 0), D, dtype=xc.dtype, device=xc.device)
-        _lib.call("d2s_gather_tokens", _ptr(xc), _dtype_code(xc), B, T, D, _ptr(ic), K, int(prepend_cls), _ptr(out), _stream())
+        _call("d2s_gather_tokens", _ptr(xc), _copy_code(xc), B, T, D, _ptr(ic), K, int(prepend_cls), _ptr(out), _stream(xc))
         ctx.save_for_backward(ic)
         ctx.shape = (B, T, D, K, bool(prepend_cls))
         return out
@@ -160,16 +187,34 @@ class _GatherTokens(torch.autograd.Function):
         B, T, D, K, prepend_cls = ctx.shape
         g = gout.contiguous()
         gx = torch.empty(B, T, D, dtype=g.dtype, device=g.device)
-        _lib.call("d2s_scatter_tokens_bwd", _ptr(g), _dtype_code(g), B, T, D, _ptr(ic), K, int(prepend_cls), _ptr(gx), _stream())
+        _call("d2s_scatter_tokens_bwd", _ptr(g), _copy_code(g), B, T, D, _ptr(ic), K, int(prepend_cls), _ptr(gx), _stream(g))
         return gx, None, None
+
+
+_CHECK_INDICES = os.environ.get("D2S_CHECK_INDICES", "0") == "1"   # debug: validate gather indices (host sync)
+
+
+def _validate_indices(kept, n):
+    lo, hi = int(kept.min()), int(kept.max())
+    if lo < 0 or hi >= n:
+        raise IndexError(f"gather_tokens: index range [{lo}, {hi}] outside [0, {n})")
+    srt = torch.sort(kept, dim=1).values
+    if bool((srt[:, 1:] == srt[:, :-1]).any()):
+        raise ValueError("gather_tokens: duplicate indices in a row (the backward keeps one gradient per source row)")
 
 
 def gather_tokens(x, kept, prepend_cls=True):
     """x (B,T,D) with CLS at row 0, kept (B,K) spatial indices -> (B,K+1,D) = [CLS, x[kept+1]]
-    (vit_models/dynamic_vit.py:907-912).  Differentiable in x (backward = scatter + zero fill)."""
+    (vit_models/dynamic_vit.py:907-912).  Differentiable in x (backward = scatter + zero fill).
+    Contract: the indices of a row are UNIQUE and in range -- what every caller on the hot path passes (kept-token sets from
+    the selection kernels).  The backward writes each source row once (no atomics), so with duplicates it would keep one of
+    the gradients where torch.gather's backward sums them, and the forward clamps out-of-range indices where torch raises;
+    D2S_CHECK_INDICES=1 validates both on every call (with a host synchronisation)."""
     _check_cuda(x, kept)
     if kept.dtype != torch.int64:
         raise TypeError("indices must be int64")
+    if _CHECK_INDICES and kept.numel():
+        _validate_indices(kept, x.shape[1] - (1 if prepend_cls else 0))
     return _GatherTokens.apply(x, kept, prepend_cls)
 
 
@@ -178,8 +223,8 @@ def scatter_tokens_bwd(gout, kept, t_in, prepend_cls=True):
     g = gout.contiguous()
     B, _, D = g.shape
     gx = torch.empty(B, t_in, D, dtype=g.dtype, device=g.device)
-    _lib.call("d2s_scatter_tokens_bwd", _ptr(g), _dtype_code(g), B, t_in, D, _ptr(kept.contiguous()), kept.shape[1],
-              int(prepend_cls), _ptr(gx), _stream())
+    _call("d2s_scatter_tokens_bwd", _ptr(g), _copy_code(g), B, t_in, D, _ptr(kept.contiguous()), kept.shape[1],
+              int(prepend_cls), _ptr(gx), _stream(g))
     return gx
 
 
@@ -207,9 +252,9 @@ class _PerturbedTopK(torch.autograd.Function):
             nz = _f32c(noise)
             if tuple(nz.shape) != (B, num_samples, N):
                 raise ValueError(f"noise must be {(B, num_samples, N)}, got {tuple(nz.shape)}")
-            _lib.call("d2s_ptopk_fwd", _ptr(xc), _ptr(nz), B, N, k, num_samples, float(sigma), _ptr(ind), _ptr(egrad), _stream())
+            _call("d2s_ptopk_fwd", _ptr(xc), _ptr(nz), B, N, k, num_samples, float(sigma), _ptr(ind), _ptr(egrad), _stream(xc))
         else:
-            _lib.call("d2s_ptopk_fwd_rng", _ptr(xc), int(seed), B, N, k, num_samples, float(sigma), _ptr(ind), _ptr(egrad), _stream())
+            _call("d2s_ptopk_fwd_rng", _ptr(xc), int(seed), B, N, k, num_samples, float(sigma), _ptr(ind), _ptr(egrad), _stream(xc))
         ctx.save_for_backward(egrad)
         ctx.in_dtype = x.dtype
         return ind
@@ -220,7 +265,7 @@ class _PerturbedTopK(torch.autograd.Function):
         B, K, N = egrad.shape
         g = _f32c(gout)
         gx = torch.empty(B, N, dtype=torch.float32, device=g.device)
-        _lib.call("d2s_ptopk_bwd", _ptr(g), _ptr(egrad), B, N, K, _ptr(gx), _stream())
+        _call("d2s_ptopk_bwd", _ptr(g), _ptr(egrad), B, N, K, _ptr(gx), _stream(g))
         return gx.to(ctx.in_dtype), None, None, None, None, None
 
 
@@ -246,7 +291,7 @@ class _SoftmaxPolicy(torch.autograd.Function):
         pol = _f32c(policy.reshape(B, T)) if policy is not None else None
         out = torch.empty_like(a)
         stats = torch.empty(B, H, T, 2, dtype=torch.float32, device=a.device)
-        _lib.call("d2s_softmax_policy_fwd", _ptr(a), _ptr(pol), _dtype_code(a), B, H, T, float(eps), _ptr(out), _ptr(stats), _stream())
+        _call("d2s_softmax_policy_fwd", _ptr(a), _ptr(pol), _dtype_code(a), B, H, T, float(eps), _ptr(out), _ptr(stats), _stream(a))
         ctx.save_for_backward(a, stats, pol if pol is not None else torch.empty(0, device=a.device))
         ctx.meta = (B, H, T, float(eps), pol is not None, None if policy is None else (policy.shape, policy.dtype))
         return out
@@ -258,8 +303,8 @@ class _SoftmaxPolicy(torch.autograd.Function):
         g = gout.contiguous().to(a.dtype)
         gattn = torch.empty_like(a)
         gpol = torch.zeros(B, T, dtype=torch.float32, device=a.device) if has_pol else None
-        _lib.call("d2s_softmax_policy_bwd", _ptr(a), _ptr(pol) if has_pol else None, _ptr(g), _ptr(stats), _dtype_code(a),
-                  B, H, T, eps, _ptr(gattn), _ptr(gpol), _stream())
+        _call("d2s_softmax_policy_bwd", _ptr(a), _ptr(pol) if has_pol else None, _ptr(g), _ptr(stats), _dtype_code(a),
+                  B, H, T, eps, _ptr(gattn), _ptr(gpol), _stream(a))
         if has_pol:
             gpol = gpol.reshape(pol_meta[0]).to(pol_meta[1])
         return gattn, gpol, None
@@ -274,24 +319,6 @@ def softmax_with_policy(attn, policy, eps=1e-6):
 
 _FUSED_WGRAD = os.environ.get("D2S_FUSED_WGRAD", "1") != "0"   # A/B switch for ops.linear_train (d2s bias gradient)
 _FUSED_GELU_BWD = os.environ.get("D2S_FUSED_GELU_BWD", "1") != "0"   # A/B switch: fc1 -> GELU as one autograd node
-_WGRAD_LT = os.environ.get("D2S_WGRAD", "colsum") == "lt"       # dW + db in one cuBLASLt call instead of GEMM + d2s column sum
-
-
-def linear_wgrad(dy, x, want_bias=True):
-    """(dw, db) of y = x W^T + b from dy (M,N) and x (M,K), bf16: dw = dy^T x and db = column sums of dy in ONE cuBLASLt GEMM
-    with the bias-gradient epilogue (`d2s_linear_wgrad_bf16`); db is None when not wanted."""
-    _check_cuda(dy, x)
-    if dy.dtype != torch.bfloat16 or x.dtype != torch.bfloat16:
-        raise RuntimeError("linear_wgrad: bf16 only")
-    dy, x = dy.contiguous(), x.contiguous()
-    M, N = dy.shape
-    K = x.shape[1]
-    if x.shape[0] != M:
-        raise RuntimeError(f"linear_wgrad: dy {tuple(dy.shape)} and x {tuple(x.shape)} disagree on the row count")
-    dw = torch.empty(N, K, dtype=torch.bfloat16, device=dy.device)
-    db = torch.empty(N, dtype=torch.bfloat16, device=dy.device) if want_bias else None
-    _lib.call("d2s_linear_wgrad_bf16", _ptr(dy), _ptr(x), M, N, K, _ptr(dw), _ptr(db), _stream())
-    return dw, db
 
 
 def colsum(dy):
@@ -303,15 +330,14 @@ def colsum(dy):
     if dy.shape[0] == 0:
         return torch.zeros(dy.shape[1], dtype=torch.float32, device=dy.device)
     out = torch.empty(dy.shape[1], dtype=torch.float32, device=dy.device)
-    _lib.call("d2s_colsum_bf16", _ptr(dy), dy.shape[0], dy.shape[1], _ptr(out), _stream())
+    _call("d2s_colsum_bf16", _ptr(dy), dy.shape[0], dy.shape[1], _ptr(out), _stream(dy))
     return out
 
 
 class _LinearTrain(torch.autograd.Function):
     """nn.Linear on the bf16 training path (fp32 master weights under bf16 autocast, or a bf16 module).  Forward is the library
     GEMM torch would run on the bf16 casts; backward computes dx and dW with library GEMMs and the bias gradient with the d2s
-    column-sum kernel in fp32 (`_WGRAD_LT`: dW and db in one cuBLASLt call with the bias-gradient epilogue instead) --
-    torch.autograd's own column reduction of dy (61 launches, 3.7 ms of a 34 ms DeiT-S step) and the bf16 -> fp32 round trip of
+    column-sum kernel in fp32 -- torch.autograd's own column reduction of dy (61 launches, 3.7 ms of a 34 ms DeiT-S step) and the bf16 -> fp32 round trip of
     the bias gradient disappear."""
 
     @staticmethod
@@ -333,14 +359,10 @@ class _LinearTrain(torch.autograd.Function):
         gx = (gy2 @ wb).view(xb.shape).to(xd) if ctx.needs_input_grad[0] else None
         gw = gb = None
         want_b = bd is not None and ctx.needs_input_grad[2]
-        if _WGRAD_LT:
-            if ctx.needs_input_grad[1] or want_b:
-                gw, gb = linear_wgrad(gy2, xb.reshape(-1, K), want_bias=want_b)
-        else:
-            if ctx.needs_input_grad[1]:
-                gw = gy2.t() @ xb.reshape(-1, K)
-            if want_b:
-                gb = colsum(gy2)
+        if ctx.needs_input_grad[1]:
+            gw = gy2.t() @ xb.reshape(-1, K)
+        if want_b:
+            gb = colsum(gy2)
         return gx, None if gw is None else gw.to(wd), None if gb is None else gb.to(bd)
 
 
@@ -355,7 +377,7 @@ def gelu_bwd_colsum(u, ga, want_bias=True):
     du = torch.empty_like(u)
     db = torch.zeros(N, dtype=torch.float32, device=u.device) if want_bias else None
     if M > 0:
-        _lib.call("d2s_gelu_bwd_colsum_bf16", _ptr(u), _ptr(ga), M, N, _ptr(du), _ptr(db), _stream())
+        _call("d2s_gelu_bwd_colsum_bf16", _ptr(u), _ptr(ga), M, N, _ptr(du), _ptr(db), _stream(u))
     return du, db
 
 
@@ -398,7 +420,7 @@ def _linear_train_ok(lin, x):
 def linear_gelu_train(lin, act, x):
     """`act(lin(x))` under autograd: one node with the fused GELU-backward + bias-gradient kernel when `act` is the exact-erf
     nn.GELU and the bf16 training path applies, else `act(linear_train(lin, x))`."""
-    if (_FUSED_GELU_BWD and not _WGRAD_LT and _linear_train_ok(lin, x) and isinstance(act, torch.nn.GELU)
+    if (_FUSED_GELU_BWD and _linear_train_ok(lin, x) and isinstance(act, torch.nn.GELU)
             and getattr(act, "approximate", "none") == "none" and lin.out_features <= 8192):
         return _LinearGeluTrain.apply(x, lin.weight, lin.bias)
     return act(linear_train(lin, x))
@@ -430,16 +452,16 @@ class _AttentionTrain(torch.autograd.Function):
         Tp = (T + 7) // 8 * 8
         dev, dt = qkv.device, qkv.dtype
         qkvh = torch.empty(3, B * H, Tp, hd, dtype=dt, device=dev)
-        _lib.call("d2s_split_heads_bf16", _ptr(qkv), B, T, Tp, 3, H, hd, _ptr(qkvh), _stream())
+        _call("d2s_split_heads_bf16", _ptr(qkv), B, T, Tp, 3, H, hd, _ptr(qkvh), _stream(qkv))
         S = torch.empty(B * H, Tp, Tp, dtype=dt, device=dev)
         torch.baddbmm(S, qkvh[0], qkvh[1].transpose(1, 2), beta=0, alpha=scale, out=S)
         pol = _f32c(policy.reshape(B, T)) if policy is not None else None
         P = torch.empty_like(S)
         stats = torch.empty(B, H, T, 2, dtype=torch.float32, device=dev)
-        _lib.call("d2s_softmax_policy_fwd_ld", _ptr(S), _ptr(pol), B, H, T, Tp, Tp, float(eps), _ptr(P), _ptr(stats), _stream())
+        _call("d2s_softmax_policy_fwd_ld", _ptr(S), _ptr(pol), B, H, T, Tp, Tp, float(eps), _ptr(P), _ptr(stats), _stream(S))
         Oh = torch.bmm(P, qkvh[2])                                                    # (B*H, Tp, hd)
         O = torch.empty(B, T, D, dtype=dt, device=dev)
-        _lib.call("d2s_merge_heads_bf16", _ptr(Oh), B, T, Tp, 1, H, hd, _ptr(O), _stream())
+        _call("d2s_merge_heads_bf16", _ptr(Oh), B, T, Tp, 1, H, hd, _ptr(O), _stream(Oh))
         cls_attn = P.view(B, H, Tp, Tp)[:, :, 0, :T].clone() if want_cls else None
         ctx.save_for_backward(qkvh, S, P, stats, pol if pol is not None else torch.empty(0, device=dev))
         ctx.meta = (B, T, Tp, H, hd, float(scale), float(eps), pol is not None,
@@ -454,19 +476,19 @@ class _AttentionTrain(torch.autograd.Function):
         dev, dt = S.device, S.dtype
         g = gO.to(dt).contiguous()
         gOh = torch.empty(B * H, Tp, hd, dtype=dt, device=dev)
-        _lib.call("d2s_split_heads_bf16", _ptr(g), B, T, Tp, 1, H, hd, _ptr(gOh), _stream())
+        _call("d2s_split_heads_bf16", _ptr(g), B, T, Tp, 1, H, hd, _ptr(gOh), _stream(g))
         dqkvh = torch.empty(3, B * H, Tp, hd, dtype=dt, device=dev)
         torch.bmm(P.transpose(1, 2), gOh, out=dqkvh[2])                               # dV = P^T dO
         dP = torch.bmm(gOh, qkvh[2].transpose(1, 2))                                  # dP = dO V^T  (padding rows are zero)
         if g_cls is not None:
             dP.view(B, H, Tp, Tp)[:, :, 0, :T] += g_cls.to(dt)
         gpol = torch.zeros(B, T, dtype=torch.float32, device=dev) if has_pol else None
-        _lib.call("d2s_softmax_policy_bwd_ld", _ptr(S), _ptr(polp), _ptr(dP), _ptr(stats), B, H, T, Tp, Tp, eps, _ptr(dP),
-                  _ptr(gpol), _stream())
+        _call("d2s_softmax_policy_bwd_ld", _ptr(S), _ptr(polp), _ptr(dP), _ptr(stats), B, H, T, Tp, Tp, eps, _ptr(dP),
+                  _ptr(gpol), _stream(S))
         torch.baddbmm(dqkvh[0], dP, qkvh[1], beta=0, alpha=scale, out=dqkvh[0])                    # dQ = scale dS K
         torch.baddbmm(dqkvh[1], dP.transpose(1, 2), qkvh[0], beta=0, alpha=scale, out=dqkvh[1])    # dK = scale dS^T Q
         dqkv = torch.empty(B, T, 3 * H * hd, dtype=dt, device=dev)
-        _lib.call("d2s_merge_heads_bf16", _ptr(dqkvh), B, T, Tp, 3, H, hd, _ptr(dqkv), _stream())
+        _call("d2s_merge_heads_bf16", _ptr(dqkvh), B, T, Tp, 3, H, hd, _ptr(dqkv), _stream(dqkvh))
         if has_pol:
             gpol = gpol.reshape(pol_meta[0]).to(pol_meta[1])
         return dqkv, gpol, None, None, None, None
@@ -488,8 +510,8 @@ class _AttentionFlash(torch.autograd.Function):
         out = torch.empty(B, T, D, dtype=qkv.dtype, device=dev)
         cls_row = torch.empty(B, H, T, dtype=torch.float32, device=dev) if want_cls else None
         stats = torch.empty(B, H, T, 4, dtype=torch.float32, device=dev)
-        _lib.call("d2s_attn_policy_fwd", _ptr(qkv), _ptr(pol), BF16, B, T, H, D // H, float(scale), float(eps), _ptr(out),
-                  _ptr(cls_row), _ptr(stats), _stream())
+        _call("d2s_attn_policy_fwd", _ptr(qkv), _ptr(pol), BF16, B, T, H, D // H, float(scale), float(eps), _ptr(out),
+                  _ptr(cls_row), _ptr(stats), _stream(qkv))
         none = torch.empty(0, device=dev)
         ctx.save_for_backward(qkv, out, stats, pol if pol is not None else none, cls_row if want_cls else none)
         ctx.meta = (B, T, H, D // H, float(scale), pol is not None, want_cls,
@@ -504,8 +526,8 @@ class _AttentionFlash(torch.autograd.Function):
         gc = _f32c(g_cls) if (want_cls and g_cls is not None) else None
         dqkv = torch.empty_like(qkv)
         gpol = torch.zeros(B, T, dtype=torch.float32, device=qkv.device) if has_pol else None
-        _lib.call("d2s_attn_policy_bwd", _ptr(qkv), _ptr(pol) if has_pol else None, _ptr(out), _ptr(g),
-                  _ptr(cls_row) if want_cls else None, _ptr(gc), _ptr(stats), B, T, H, hd, scale, _ptr(dqkv), _ptr(gpol), _stream())
+        _call("d2s_attn_policy_bwd", _ptr(qkv), _ptr(pol) if has_pol else None, _ptr(out), _ptr(g),
+                  _ptr(cls_row) if want_cls else None, _ptr(gc), _ptr(stats), B, T, H, hd, scale, _ptr(dqkv), _ptr(gpol), _stream(qkv))
         if has_pol:
             gpol = gpol.reshape(pol_meta[0]).to(pol_meta[1])
         return dqkv, gpol, None, None, None, None
@@ -542,8 +564,8 @@ def attention_core(qkv, num_heads, policy=None, scale=None, eps=1e-6, want_cls_r
     pol = _f32c(policy.reshape(B, T)) if policy is not None else None
     out = torch.empty(B, T, D, dtype=q.dtype, device=q.device)
     cls_row = torch.empty(B, num_heads, T, dtype=torch.float32, device=q.device) if want_cls_row else None
-    _lib.call("d2s_attn_policy_fwd", _ptr(q), _ptr(pol), _dtype_code(q), B, T, num_heads, hd, float(scale), float(eps),
-              _ptr(out), _ptr(cls_row), None, _stream())
+    _call("d2s_attn_policy_fwd", _ptr(q), _ptr(pol), _dtype_code(q), B, T, num_heads, hd, float(scale), float(eps),
+              _ptr(out), _ptr(cls_row), None, _stream(q))
     return out, cls_row
 
 
@@ -565,8 +587,8 @@ def add_layernorm(x, y, weight, bias, eps, norm_row0=0, want_sum=True):
     need_sum = want_sum and (y is not None)
     out_sum = torch.empty(B, T, D, dtype=x.dtype, device=x.device) if need_sum else None
     out_norm = torch.empty(B, T - norm_row0, D, dtype=x.dtype, device=x.device)
-    _lib.call("d2s_add_layernorm", _ptr(x), _ptr(yc), _ptr(w), _ptr(b), _dtype_code(x), B, T, D, x.stride(0), x.stride(1),
-              float(eps), int(norm_row0), _ptr(out_sum), _ptr(out_norm), _stream())
+    _call("d2s_add_layernorm", _ptr(x), _ptr(yc), _ptr(w), _ptr(b), _dtype_code(x), B, T, D, x.stride(0), x.stride(1),
+              float(eps), int(norm_row0), _ptr(out_sum), _ptr(out_norm), _stream(x))
     if want_sum and y is None:
         out_sum = x
     return out_sum, out_norm
@@ -584,8 +606,8 @@ def gather_layernorm(x, kept, weight, bias, eps):
     w, b = weight.detach().to(xc.dtype).contiguous(), bias.detach().to(xc.dtype).contiguous()
     out_sum = torch.empty(B, K + 1, D, dtype=xc.dtype, device=xc.device)
     out_norm = torch.empty_like(out_sum)
-    _lib.call("d2s_gather_layernorm", _ptr(xc), _ptr(ic), _ptr(w), _ptr(b), _dtype_code(xc), B, T, D, K, float(eps),
-              _ptr(out_sum), _ptr(out_norm), _stream())
+    _call("d2s_gather_layernorm", _ptr(xc), _ptr(ic), _ptr(w), _ptr(b), _dtype_code(xc), B, T, D, K, float(eps),
+              _ptr(out_sum), _ptr(out_norm), _stream(xc))
     return out_sum, out_norm
 
 
@@ -602,7 +624,7 @@ def pool_act(z, policy=None, act=ACT_GELU):
     pol = _f32c(policy.reshape(B, N)) if policy is not None else None
     local = torch.empty(B, N, C // 2, dtype=zc.dtype, device=zc.device)
     pooled = torch.empty(B, C // 2, dtype=zc.dtype, device=zc.device)
-    _lib.call("d2s_pool_act", _ptr(zc), _ptr(pol), _dtype_code(zc), B, N, C, int(act), _ptr(local), _ptr(pooled), _stream())
+    _call("d2s_pool_act", _ptr(zc), _ptr(pol), _dtype_code(zc), B, N, C, int(act), _ptr(local), _ptr(pooled), _stream(zc))
     return local, pooled
 
 
@@ -617,7 +639,7 @@ def bias_act_(u, bias, act=ACT_GELU):
     per_image = bias is not None and bias.dim() == 2
     bc = None if bias is None else bias.detach().to(u.dtype).contiguous()
     n = u.shape[-2] if per_image else 0
-    _lib.call("d2s_bias_act", _ptr(u), _ptr(bc), _dtype_code(u), rows, n, C, int(act), _stream())
+    _call("d2s_bias_act", _ptr(u), _ptr(bc), _dtype_code(u), rows, n, C, int(act), _stream(u))
     return u
 
 
@@ -627,7 +649,7 @@ def pool_concat_(z):
     if not z.is_contiguous():
         raise ValueError("pool_concat_ works in place on a contiguous tensor")
     B, N, C = z.shape
-    _lib.call("d2s_pool_concat_inplace", _ptr(z), _dtype_code(z), B, N, C, _stream())
+    _call("d2s_pool_concat_inplace", _ptr(z), _dtype_code(z), B, N, C, _stream(z))
     return z
 
 
@@ -639,7 +661,7 @@ def assemble_tokens(patches, cls_token, pos_embed):
     cls = cls_token.detach().to(pc.dtype).reshape(D).contiguous()
     pos = pos_embed.detach().to(pc.dtype).reshape(N + 1, D).contiguous()
     out = torch.empty(B, N + 1, D, dtype=pc.dtype, device=pc.device)
-    _lib.call("d2s_assemble_tokens", _ptr(pc), _ptr(cls), _ptr(pos), _dtype_code(pc), B, N, D, _ptr(out), _stream())
+    _call("d2s_assemble_tokens", _ptr(pc), _ptr(cls), _ptr(pos), _dtype_code(pc), B, N, D, _ptr(out), _stream(pc))
     return out
 
 
@@ -654,8 +676,8 @@ def assemble_layernorm(patches, cls_token, pos_embed, weight, bias, eps):
     w, b = weight.detach().to(pc.dtype).contiguous(), bias.detach().to(pc.dtype).contiguous()
     out_sum = torch.empty(B, N + 1, D, dtype=pc.dtype, device=pc.device)
     out_norm = torch.empty_like(out_sum)
-    _lib.call("d2s_assemble_layernorm", _ptr(pc), _ptr(cls), _ptr(pos), _ptr(w), _ptr(b), _dtype_code(pc), B, N, D, float(eps),
-              _ptr(out_sum), _ptr(out_norm), _stream())
+    _call("d2s_assemble_layernorm", _ptr(pc), _ptr(cls), _ptr(pos), _ptr(w), _ptr(b), _dtype_code(pc), B, N, D, float(eps),
+              _ptr(out_sum), _ptr(out_norm), _stream(pc))
     return out_sum, out_norm
 
 
@@ -665,7 +687,7 @@ def patchify(img, ph, pw):
     x = img.detach().contiguous()
     B, C, Hh, Ww = x.shape
     out = torch.empty(B, (Hh // ph) * (Ww // pw), C * ph * pw, dtype=x.dtype, device=x.device)
-    _lib.call("d2s_patchify", _ptr(x), _dtype_code(x), B, C, Hh, Ww, int(ph), int(pw), _ptr(out), _stream())
+    _call("d2s_patchify", _ptr(x), _dtype_code(x), B, C, Hh, Ww, int(ph), int(pw), _ptr(out), _stream(x))
     return out
 
 
@@ -682,8 +704,8 @@ class _LayerNorm(torch.autograd.Function):
         w, b = _f32c(weight), _f32c(bias)
         h = torch.empty(xc.shape, dtype=out_dtype, device=xc.device)
         stats = torch.empty(rows, 2, dtype=torch.float32, device=xc.device)
-        _lib.call("d2s_layernorm_fwd", _ptr(xc), _dtype_code(xc), _ptr(w), _ptr(b), rows, D, float(eps), _ptr(h),
-                  _dtype_code(h), _ptr(stats), _stream())
+        _call("d2s_layernorm_fwd", _ptr(xc), _dtype_code(xc), _ptr(w), _ptr(b), rows, D, float(eps), _ptr(h),
+                  _dtype_code(h), _ptr(stats), _stream(xc))
         ctx.save_for_backward(xc, stats, w)
         ctx.meta = (weight.dtype, bias.dtype)
         return h
@@ -696,8 +718,8 @@ class _LayerNorm(torch.autograd.Function):
         g = dh.contiguous()
         dx = torch.empty_like(xc)
         dgb = torch.zeros(2, D, dtype=torch.float32, device=xc.device)
-        _lib.call("d2s_layernorm_bwd", _ptr(g), _dtype_code(g), _ptr(xc), _dtype_code(xc), _ptr(stats), _ptr(w), rows, D,
-                  _ptr(dx), _ptr(dgb[0]), _ptr(dgb[1]), _stream())
+        _call("d2s_layernorm_bwd", _ptr(g), _dtype_code(g), _ptr(xc), _dtype_code(xc), _ptr(stats), _ptr(w), rows, D,
+                  _ptr(dx), _ptr(dgb[0]), _ptr(dgb[1]), _stream(g))
         return dx, dgb[0].to(ctx.meta[0]), dgb[1].to(ctx.meta[1]), None, None
 
 
@@ -714,8 +736,8 @@ class _AddLayerNorm(torch.autograd.Function):
         s = torch.empty_like(xc)
         h = torch.empty(xc.shape, dtype=out_dtype, device=xc.device)
         stats = torch.empty(rows, 2, dtype=torch.float32, device=xc.device)
-        _lib.call("d2s_add_layernorm_fwd", _ptr(xc), _ptr(yc), _dtype_code(xc), _ptr(w), _ptr(b), rows, D, float(eps), _ptr(s),
-                  _ptr(h), _dtype_code(h), _ptr(stats), _stream())
+        _call("d2s_add_layernorm_fwd", _ptr(xc), _ptr(yc), _dtype_code(xc), _ptr(w), _ptr(b), rows, D, float(eps), _ptr(s),
+                  _ptr(h), _dtype_code(h), _ptr(stats), _stream(xc))
         ctx.save_for_backward(s, stats, w)
         ctx.meta = (weight.dtype, bias.dtype)
         return s, h
@@ -731,8 +753,8 @@ class _AddLayerNorm(torch.autograd.Function):
         ga = None if gs is None else gs.to(s.dtype).contiguous()
         dx = torch.empty_like(s)
         dgb = torch.zeros(2, D, dtype=torch.float32, device=s.device)
-        _lib.call("d2s_add_layernorm_bwd", _ptr(g), _dtype_code(g), _ptr(s), _dtype_code(s), _ptr(stats), _ptr(w), _ptr(ga), rows, D,
-                  _ptr(dx), _ptr(dgb[0]), _ptr(dgb[1]), _stream())
+        _call("d2s_add_layernorm_bwd", _ptr(g), _dtype_code(g), _ptr(s), _dtype_code(s), _ptr(stats), _ptr(w), _ptr(ga), rows, D,
+                  _ptr(dx), _ptr(dgb[0]), _ptr(dgb[1]), _stream(g))
         return dx, dx, dgb[0].to(ctx.meta[0]), dgb[1].to(ctx.meta[1]), None, None
 
 
@@ -756,8 +778,8 @@ def layer_norm(x, weight, bias, eps, out_dtype=None):
     return _LayerNorm.apply(x, weight, bias, eps, out_dtype)
 
 
-def linear_act(x, weight, bias, act=ACT_GELU, pair=False):
-    """act(x @ weight^T + bias) in one tcgen05 GEMM with the activation in the epilogue (bf16, inference only).
+def linear_act(x, weight, bias, act=ACT_GELU):
+    """act(x @ weight^T + bias) in one CTA-pair tcgen05 GEMM with the activation in the epilogue (bf16, inference only).
     x (..., K) contiguous, weight (N, K), N % 256 == 0, K % 64 == 0."""
     _check_cuda(x, weight, bias)
     if x.dtype != torch.bfloat16:
@@ -769,8 +791,7 @@ def linear_act(x, weight, bias, act=ACT_GELU, pair=False):
     M = xc.numel() // K
     N = w.shape[0]
     out = torch.empty(*xc.shape[:-1], N, dtype=torch.bfloat16, device=xc.device)
-    fn = "d2s_linear_act_pair_bf16" if pair else "d2s_linear_act_bf16"
-    _lib.call(fn, _ptr(xc), _ptr(w), _ptr(b), M, N, K, int(act), _ptr(out), _stream())
+    _call("d2s_linear_act_pair_bf16", _ptr(xc), _ptr(w), _ptr(b), M, N, K, int(act), _ptr(out), _stream(xc))
     return out
 
 
@@ -796,8 +817,8 @@ def linear_residual_ln(a, weight, bias, x, ln_weight=None, ln_bias=None, eps=1e-
         bt = ln_bias.detach().to(torch.bfloat16).contiguous()
     out_sum = torch.empty_like(xc)
     out_norm = torch.empty_like(xc) if want_norm else None
-    _lib.call("d2s_linear_residual_ln_bf16", _ptr(ac), _ptr(w), _ptr(b), _ptr(xc), _ptr(g), _ptr(bt), float(eps), M, N, K,
-              _ptr(out_sum), _ptr(out_norm), _stream())
+    _call("d2s_linear_residual_ln_bf16", _ptr(ac), _ptr(w), _ptr(b), _ptr(xc), _ptr(g), _ptr(bt), float(eps), M, N, K,
+              _ptr(out_sum), _ptr(out_norm), _stream(ac))
     return out_sum, out_norm
 
 
@@ -827,6 +848,6 @@ def mlp_residual_ln(h, w1, b1, w2, b2, x, ln_weight=None, ln_bias=None, eps=1e-5
     out_norm = None
     if want_norm:
         out_norm = torch.empty(xc.shape[0], T - norm_row0, D, dtype=xc.dtype, device=xc.device) if norm_row0 else torch.empty_like(xc)
-    _lib.call("d2s_mlp_residual_ln_bf16", _ptr(hc), _ptr(w1c), _ptr(bf(b1)), _ptr(w2c), _ptr(bf(b2)), _ptr(xc), _ptr(g), _ptr(bt),
-              float(eps), M, D, HID, T, int(norm_row0), _ptr(out_sum), _ptr(out_norm), _stream())
+    _call("d2s_mlp_residual_ln_bf16", _ptr(hc), _ptr(w1c), _ptr(bf(b1)), _ptr(w2c), _ptr(bf(b2)), _ptr(xc), _ptr(g), _ptr(bt),
+              float(eps), M, D, HID, T, int(norm_row0), _ptr(out_sum), _ptr(out_norm), _stream(hc))
     return out_sum, out_norm

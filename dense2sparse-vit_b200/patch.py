@@ -22,7 +22,7 @@ def install(dvit=None, ddvit=None, ptopk=None):
     """Patch whichever reference modules are given (already-imported module objects)."""
     if ddvit is not None:   # Variant A, vit_models/default_dynamic_vit.py
         _swap(ddvit, "batch_index_select", ops.batch_index_select)
-        _swap(ddvit.Attention, "softmax_with_policy", lambda self, attn, policy, eps=1e-6: ops.softmax_with_policy(attn, policy, eps))
+        _swap(ddvit.Attention, "softmax_with_policy", lambda self, attn, policy, eps=1e-6: engine.softmax_with_policy(attn, policy, eps))
         _swap(ddvit.Attention, "forward", lambda self, x, policy: engine.attention_forward(self, x, policy))
         _swap(ddvit.Block, "forward", lambda self, x, policy=None: engine.block_forward(self, x, policy))
         _swap(ddvit.PatchEmbed, "forward", lambda self, x: engine.patch_embed_forward(self, x))
@@ -32,7 +32,7 @@ def install(dvit=None, ddvit=None, ptopk=None):
               lambda self, x: engine.teacher_forward(self, x, with_cls_attn=False))
     if dvit is not None:    # Variant B, vit_models/dynamic_vit.py
         _swap(dvit, "batch_index_select", ops.batch_index_select)
-        _swap(dvit.Attention, "softmax_with_policy", lambda self, attn, policy, eps=1e-6: ops.softmax_with_policy(attn, policy, eps))
+        _swap(dvit.Attention, "softmax_with_policy", lambda self, attn, policy, eps=1e-6: engine.softmax_with_policy(attn, policy, eps))
         _swap(dvit.Attention, "forward",
               lambda self, x, policy, return_cls_attn=False: engine.attention_forward(self, x, policy, return_cls_attn))
         _swap(dvit.Block, "forward",

@@ -154,11 +154,6 @@ int d2s_colsum_bf16(const void* dy, long long M, int N, float* out, d2s_stream_t
  * du (M,N) = ga * gelu'(u) (exact-erf GELU), db (N) f32 = column sums of du (NULL: not wanted; overwritten otherwise). */
 int d2s_gelu_bwd_colsum_bf16(const void* u, const void* ga, long long M, int N, void* du, float* db, d2s_stream_t stream);
 
-/* Weight and bias gradient of a Linear layer (nn.Linear of Attention / Mlp / PredictorLG under autograd, dynamic_vit.py:159-236),
- * bf16: dw (N,K) = dy^T x, db (N) = column sums of dy (NULL: not wanted), from dy (M,N) and x (M,K).  ONE cuBLASLt GEMM with the
- * bias-gradient epilogue instead of torch.autograd's GEMM + separate column reduction.  N % 8 == 0, K % 8 == 0. */
-int d2s_linear_wgrad_bf16(const void* dy, const void* x, int M, int N, int K, void* dw, void* db, d2s_stream_t stream);
-
 /* Fused attention core of Attention.forward (dynamic_vit.py:218-234; default_dynamic_vit.py:203-213):
  * qkv (B,T,3,H,hd) packed as produced by the qkv Linear; out (B,T,H*hd) ready for the proj Linear;
  * cls_row (B,H,T) f32 = probabilities of query row 0 (dynamic_vit.py:233-234) or NULL.
@@ -230,11 +225,7 @@ int d2s_assemble_layernorm(const void* patches, const void* cls, const void* pos
 
 /* Linear + activation in one tcgen05 GEMM (fc1 + GELU of Mlp.forward, dynamic_vit.py:159-175), bf16 only:
  * out (M,N) = act(a (M,K) @ w (N,K)^T + bias (N)); fp32 accumulation; bias may be NULL.
- * N % 256 == 0 (N <= 4096), K % 64 == 0. */
-int d2s_linear_act_bf16(const void* a, const void* w, const void* bias, int M, int N, int K, int act, void* out,
-                        d2s_stream_t stream);
-
-/* The same contract on a CTA pair (tcgen05 cta_group::2, 256-row tiles, half of the weight tile per CTA). */
+ * N % 256 == 0 (N <= 4096), K % 64 == 0.  CTA pair (tcgen05 cta_group::2, 256-row tiles, half of the weight tile per CTA). */
 int d2s_linear_act_pair_bf16(const void* a, const void* w, const void* bias, int M, int N, int K, int act, void* out,
                              d2s_stream_t stream);
 

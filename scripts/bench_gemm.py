@@ -24,8 +24,8 @@ for T in (197, 138, 97, 68):
     fl = 2.0 * M * 4 * D * D
     a = t(ref); c = t(lambda: fc1(x))
     b1 = t(lambda: ops.linear_act(x, fc1.weight, fc1.bias, ops.ACT_GELU))
-    b2 = t(lambda: ops.linear_act(x, fc1.weight, fc1.bias, ops.ACT_GELU, pair=True))
-    b3 = t(lambda: ops.linear_act(x, fc1.weight, fc1.bias, ops.ACT_NONE, pair=True))
+    b2 = t(lambda: ops.linear_act(x, fc1.weight, fc1.bias, ops.ACT_GELU))
+    b3 = t(lambda: ops.linear_act(x, fc1.weight, fc1.bias, ops.ACT_NONE))
     print(f"T={T} fc1: cuBLAS+GELU {a:.1f} us | cuBLAS alone {c:.1f} us ({fl / c / 1e6:.0f} TF/s) | 1-CTA fused {b1:.1f} us ({fl / b1 / 1e6:.0f} TF/s)"
           f" | pair fused {b2:.1f} us ({fl / b2 / 1e6:.0f} TF/s) | pair no-act {b3:.1f} us")
     x3 = x.view(1024, T, D)

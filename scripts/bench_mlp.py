@@ -19,7 +19,7 @@ for T in (197, 138, 97, 68):
     fc2 = torch.nn.Linear(4 * D, D).cuda().bfloat16()
     ln = torch.nn.LayerNorm(D, eps=1e-6).cuda().bfloat16()
     def two():
-        u = ops.linear_act(h, fc1.weight, fc1.bias, ops.ACT_GELU, pair=True)
+        u = ops.linear_act(h, fc1.weight, fc1.bias, ops.ACT_GELU)
         return ops.linear_residual_ln(u, fc2.weight, fc2.bias, x, ln.weight, ln.bias, 1e-6)
     a = t(two)
     b = t(lambda: ops.mlp_residual_ln(h, fc1.weight, fc1.bias, fc2.weight, fc2.bias, x, ln.weight, ln.bias, 1e-6))

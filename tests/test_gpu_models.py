@@ -414,3 +414,217 @@ def test_fused_path_keeps_the_reference_token_sets_when_margins_allow(d2s, cuda_
         assert len(mine ^ theirs) <= 2 * near, (b, len(mine ^ theirs), near, float(margin[b]))
         if float(margin[b]) > 0.05:
             assert mine == theirs, (b, float(margin[b]))
+
+
+# ------------------------------------------------------------------------------------------ the benchmarked configuration
+DEIT_S = dict(patch_size=16, embed_dim=384, depth=12, num_heads=6, mlp_ratio=4, qkv_bias=True)
+BENCH_LOCS, BENCH_RATIOS = [3, 6, 9], [0.7, 0.7 ** 2, 0.7 ** 3]
+
+
+def _bench_model(d2s, variant, ratios=BENCH_RATIOS, num_classes=1000, seed=61, bn=False):
+    """The architecture bench.py times: full DeiT-S/16 (depth 12, 6 heads), pruning stages at blocks 3 / 6 / 9."""
+    if variant == "a":
+        m = d2s.variant_a.DefaultVisionTransformerDiffPruning(pruning_loc=BENCH_LOCS, token_ratio=ratios, distill=True,
+                                                              num_classes=num_classes, **DEIT_S)
+    else:
+        m = d2s.variant_b.VisionTransformerDiffPruning(pruning_loc=BENCH_LOCS, token_ratio=ratios, distill=True, topk_selection=True,
+                                                       predictor_loss_type="kl_div", predictor_bn=bn, num_classes=num_classes, **DEIT_S)
+    sd = fx.seeded_state_dict({k: tuple(v.shape) for k, v in m.state_dict().items()}, seed)
+    m.load_state_dict(sd)
+    return m, sd
+
+
+@pytest.mark.parametrize("variant", ["a", "b"])
+def test_bench_config_fp32_matches_the_oracle(d2s, cuda_dev, variant):
+    """Full DeiT-S (depth 12, stages at 3/6/9, ratios 0.7/0.49/0.343) in fp32 on the GPU against the CPU oracle (which equals
+    the unmodified reference at this configuration to 2e-6): kept-token sets of all three stages bit-exact, logits 1e-4."""
+    from oracle import model as om
+    m, sd = _bench_model(d2s, variant)
+    x = fx.randn(62, 4, 3, 224, 224)
+    cfg = om.VitCfg(embed_dim=384, depth=12, num_heads=6, num_classes=1000, pruning_loc=BENCH_LOCS, token_ratio=BENCH_RATIOS)
+    ref = om.variant_a_eval(sd, cfg, x) if variant == "a" else om.variant_b_forward(sd, cfg, x)
+    m = m.to(cuda_dev).eval()
+    with torch.no_grad():
+        out = m(x.to(cuda_dev))
+    logits = out if variant == "a" else out[0]
+    for s in range(3):
+        assert torch.equal(m.kept_token_indices[s].cpu(), ref["kept"][s]), f"stage {s}"
+    torch.testing.assert_close(logits.cpu(), ref["logits"], rtol=1e-4, atol=2e-5)
+    if variant == "b":
+        for i in (0, 5, 11):
+            torch.testing.assert_close(out[1][i].cpu(), ref["cls_attns"][i], rtol=1e-4, atol=1e-7)
+
+
+def test_bench_config_bf16_graph_at_batch_1024(d2s, cuda_dev):
+    """BASELINE configs[1] exactly as bench.py runs it -- bf16, batch 1024, the whole forward replayed from a CUDA graph
+    (runner.InferenceRunner) -- against the fp32 GPU path on IDENTICAL (bf16-representable) weights and images.
+      * keep ratio 1.0 (every kernel runs, no token can change sides): logits within 1e-2 relative (L2 over the batch; the
+        largest single deviation over 1024 x 1000 logits is a tail statistic and is held to 3e-2 of max |logit|);
+      * real ratios: the kept sets of stage 1 agree wherever the fp32 score margin at the cut exceeds bf16 noise, and images whose
+        three kept sets all agree have logits within the same bound."""
+    B = 1024
+    g = torch.Generator(device=cuda_dev).manual_seed(63)
+    x = torch.randn(B, 3, 224, 224, device=cuda_dev, generator=g).bfloat16()
+
+    def run32(model):
+        outs, kept = [], [[], [], []]
+        with torch.no_grad():
+            for i in range(0, B, 128):
+                outs.append(model(x[i:i + 128].float()))
+                for s in range(3):
+                    kept[s].append(model.kept_token_indices[s])
+        return torch.cat(outs), [torch.cat(k) for k in kept]
+
+    for ratios in ([1.0, 1.0, 1.0], BENCH_RATIOS):
+        m, sd = _bench_model(d2s, "a", ratios)
+        sdr = {k: (v.bfloat16().float() if v.is_floating_point() else v) for k, v in sd.items()}
+        m.load_state_dict(sdr)
+        m32 = m.to(cuda_dev).eval()
+        l32, k32 = run32(m32)
+        s32 = None
+        if ratios[0] < 1.0:
+            # fp32 stage-1 scores: margin of every image at the cut
+            from oracle import ops as oo_
+            with torch.no_grad():
+                xs = x[:128].float()
+                st = d2s.engine._embed_stream(m32, xs)
+                for blk in m32.blocks[:3]:
+                    st.block(blk)
+                xx = st.value()
+                s32 = d2s.engine.predictor_a_forward(m32.score_predictor[0], xx[:, 1:], torch.ones(128, 196, 1, device=cuda_dev))[:, :, 0]
+        runner = d2s.runner.InferenceRunner(m32, B, cuda_dev, dtype=torch.bfloat16, use_graph=True, warmup=1)
+        l16 = runner(x).float().clone()
+        k16 = [k.clone() for k in runner.model.kept_token_indices]
+        torch.cuda.synchronize()
+        assert runner.graph is not None
+        scale = float(l32.abs().max())
+        if ratios[0] == 1.0:
+            assert float((l16 - l32).norm() / l32.norm()) <= 1e-2
+            assert float((l16 - l32).abs().max()) <= 3e-2 * scale
+        else:
+            same = torch.ones(B, dtype=torch.bool, device=cuda_dev)
+            for s in range(3):
+                same &= (torch.sort(k16[s], 1).values == torch.sort(k32[s], 1).values).all(1)
+            assert int(same.sum()) >= 16, "too few images without a flipped token to compare logits on"
+            d = (l16 - l32)[same]
+            assert float(d.norm() / l32[same].norm()) <= 1e-2
+            assert float(d.abs().max()) <= 3e-2 * scale
+            K = k32[0].shape[1]
+            srt = torch.sort(s32, dim=-1, descending=True).values
+            margin = srt[:, K - 1] - srt[:, K]
+            for b in range(128):
+                mine, theirs = set(k16[0][b].tolist()), set(k32[0][b].tolist())
+                near = int(((s32[b] - srt[b, K - 1]).abs() < 0.05).sum())
+                assert len(mine ^ theirs) <= 2 * near, (b, len(mine ^ theirs), near)
+                if float(margin[b]) > 0.05:
+                    assert mine == theirs, (b, float(margin[b]))
+        del runner
+
+
+@pytest.mark.parametrize("small", [False, True])
+def test_variant_b_batchnorm_predictors_on_the_gpu(d2s, cuda_dev, small):
+    """The BatchNorm predictor architectures of Variant B (dynamic_vit.py:350-367, :389-406, :439-479; predictor_bn=True) on
+    the GPU against the oracle: eval (running statistics) with bit-exact kept sets and 1e-4 logits, and the training-mode
+    forward (per-batch statistics, as the reference: no SyncBN)."""
+    from oracle import model as om
+    kw = dict(patch_size=16, embed_dim=128, depth=4, num_heads=2, num_classes=16, mlp_ratio=4, qkv_bias=True)
+    m = d2s.variant_b.VisionTransformerDiffPruning(pruning_loc=[1, 2], token_ratio=[0.7, 0.49], distill=True, topk_selection=True,
+                                                   predictor_loss_type="kl_div", predictor_bn=True, small_predictor=small, **kw)
+    sd = fx.seeded_state_dict({k: tuple(v.shape) for k, v in m.state_dict().items()}, 71)
+    m.load_state_dict(sd)
+    x = fx.randn(72, 4, 3, 224, 224)
+    cfg = om.VitCfg(embed_dim=128, depth=4, num_heads=2, num_classes=16, pruning_loc=[1, 2], token_ratio=[0.7, 0.49],
+                    small_predictor=small, predictor_bn=True)
+    m = m.to(cuda_dev).eval()
+    ref = om.variant_b_forward(sd, cfg, x)
+    with torch.no_grad():
+        logits, cls_attns, pred_logits, kept = m(x.to(cuda_dev))
+    for s in range(2):
+        assert torch.equal(kept[s].cpu(), ref["kept"][s])
+        torch.testing.assert_close(pred_logits[s].cpu(), ref["pred_logits"][s], rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(logits.cpu(), ref["logits"], rtol=1e-4, atol=2e-5)
+    m.train()
+    reft = om.variant_b_forward(sd, cfg, x, training=True)
+    lt, feats, plt, keptt = m(x.to(cuda_dev))
+    for s in range(2):
+        assert torch.equal(keptt[s].cpu(), reft["kept"][s])
+    torch.testing.assert_close(lt.detach().cpu(), reft["logits"], rtol=1e-4, atol=2e-5)
+
+
+# ------------------------------------------------------------------------------------------ robustness (dtype / shape / device)
+def test_fp16_autocast_training_step_falls_back_to_torch(d2s, cuda_dev):
+    """fp16 autocast (the GradScaler mode of ddp_training.py:84-85,130): the d2s kernels take fp32 / bf16 only, so the step must
+    run on torch's own modules instead of raising, and agree with the fp32 step."""
+    x = fx.randn(80, 2, 3, 224, 224).to(cuda_dev)
+    m, _ = _deit_s_width_models(d2s, cuda_dev, "a", [0.7, 0.49])
+    m.train()
+    m._d2s_gumbels = [fx.randn(81 + i, 2, 196, 2).to(cuda_dev) for i in range(2)]
+    outs = {}
+    for name, ctx in (("fp32", torch.autocast("cuda", enabled=False)), ("fp16", torch.autocast("cuda", dtype=torch.float16))):
+        m.zero_grad()
+        with ctx:
+            logits, feats, final_dec, decs = m(x)
+        logits.float().square().mean().backward()
+        outs[name] = (logits.detach().float(), m.head.weight.grad.detach().clone())
+    assert float((outs["fp16"][0] - outs["fp32"][0]).abs().max()) <= 2e-2 * float(outs["fp32"][0].abs().max())
+    assert bool(torch.isfinite(outs["fp16"][1]).all())
+    mb, _ = _deit_s_width_models(d2s, cuda_dev, "b", [0.7, 0.49])
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
+        lb = mb(x)[0]
+    assert bool(torch.isfinite(lb).all())
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16, torch.float32])
+def test_shapes_outside_the_kernels_fall_back(d2s, cuda_dev, dtype):
+    """Head dim 48 (no attention kernel), an fp16 model (no kernel dtype) and width 100 (rows not multiples of 8): the forward
+    must still run -- on torch -- and match the oracle to the dtype's accuracy."""
+    from oracle import model as om
+    x = fx.randn(85, 2, 3, 224, 224)
+    for ed, heads in ((96, 2), (100, 2)):
+        kw = dict(patch_size=16, embed_dim=ed, depth=2, num_heads=heads, num_classes=16, mlp_ratio=4, qkv_bias=True)
+        m = d2s.variant_a.DefaultVisionTransformerDiffPruning(pruning_loc=[1], token_ratio=[1.0], distill=True, **kw)
+        sd = fx.seeded_state_dict({k: tuple(v.shape) for k, v in m.state_dict().items()}, 86)
+        m.load_state_dict(sd)
+        ref = om.variant_a_eval(sd, om.VitCfg(embed_dim=ed, depth=2, num_heads=heads, num_classes=16, pruning_loc=[1],
+                                              token_ratio=[1.0]), x)["logits"]
+        m = m.to(cuda_dev).eval().to(dtype)
+        with torch.no_grad():
+            out = m(x.to(cuda_dev, dtype))
+        tol = 1e-4 if dtype == torch.float32 else 3e-2
+        assert float((out.float().cpu() - ref).abs().max()) <= tol * float(ref.abs().max())
+
+
+def test_ops_follow_the_tensors_device(d2s):
+    """A model on cuda:1 while cuda:0 is the current device (model.to('cuda:1') without set_device): every op must launch on
+    the tensors' device, like torch's own ops."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from oracle import model as om
+    dev1 = torch.device("cuda:1")
+    torch.cuda.set_device(0)
+    m, sd = _deit_s_width_models(d2s, dev1, "a", [0.7, 0.49])
+    x = fx.randn(90, 2, 3, 224, 224)
+    cfg = om.VitCfg(embed_dim=384, depth=4, num_heads=6, num_classes=16, pruning_loc=[1, 2], token_ratio=[0.7, 0.49])
+    ref = om.variant_a_eval(sd, cfg, x)
+    with torch.no_grad():
+        out = m(x.to(dev1))
+        out16 = m.to(torch.bfloat16)(x.to(dev1, torch.bfloat16))
+    assert torch.cuda.current_device() == 0 and out.device == dev1
+    assert m.kept_token_indices[0].device == dev1
+    torch.testing.assert_close(out.cpu(), ref["logits"], rtol=1e-4, atol=2e-5)
+    assert float((out16.float().cpu() - ref["logits"]).abs().max()) <= 0.2 * float(ref["logits"].abs().max())
+    q = torch.randn(2, 197, 3 * 384, device=dev1, dtype=torch.bfloat16, requires_grad=True)
+    o, _ = d2s.ops.attention_train(q, 6)
+    o.float().sum().backward()
+    assert bool(torch.isfinite(q.grad).all()) and q.grad.device == dev1
+
+
+def test_gather_index_contract_check(d2s, cuda_dev, monkeypatch):
+    monkeypatch.setattr(d2s.ops, "_CHECK_INDICES", True)
+    x = torch.randn(2, 10, 8, device=cuda_dev)
+    good = torch.tensor([[0, 3, 5], [1, 2, 8]], device=cuda_dev)
+    d2s.ops.gather_tokens(x, good)
+    with pytest.raises(ValueError, match="duplicate"):
+        d2s.ops.gather_tokens(x, torch.tensor([[0, 3, 3], [1, 2, 8]], device=cuda_dev))
+    with pytest.raises(IndexError):
+        d2s.ops.gather_tokens(x, torch.tensor([[0, 3, 9], [1, 2, 8]], device=cuda_dev))

@@ -649,42 +649,28 @@ def test_gelu_inplace_matches_exact_erf(ops):
     assert float((outb.cpu().float() != refb.bfloat16().float())[core].float().mean()) < 1e-4
 
 
-@pytest.mark.parametrize("M,N,K,act", [(1000, 1536, 384, 1), (128, 256, 64, 1), (77, 512, 128, 0), (3 * 197, 1536, 384, 2),
-                                       (20000, 1536, 384, 1), (513, 3072, 768, 1)])
-def test_linear_act_gemm(ops, M, N, K, act):
-    x = (fx.randn(200 + M % 97, M, K) * 1.0).bfloat16()
-    w = (fx.randn(201 + N % 89, N, K) / K ** 0.5).bfloat16()
-    b = (fx.randn(202, N) * 0.2).bfloat16()
-    out = ops.linear_act(cu(x), cu(w), cu(b), act)
-    ref = torch.nn.functional.linear(x.float(), w.float(), b.float())       # fp32 accumulate of the same bf16 operands
-    ref = torch.nn.functional.gelu(ref) if act == 1 else (torch.relu(ref) if act == 2 else ref)
-    torch.testing.assert_close(out.cpu().float(), ref, rtol=1e-2, atol=1e-2)
-    assert out.shape == (M, N) and out.dtype == torch.bfloat16
-
-
 @pytest.mark.parametrize("M,N,K,act", [(1000, 1536, 384, 1), (256, 256, 64, 1), (77, 512, 128, 0), (3 * 197, 1536, 384, 2),
-                                       (20000, 1536, 384, 1), (513, 3072, 768, 1), (129, 256, 64, 0)])
+                                       (20000, 1536, 384, 1), (513, 3072, 768, 1), (129, 256, 64, 0), (128, 256, 64, 1)])
 def test_linear_act_pair_gemm(ops, M, N, K, act):
     """CTA-pair (cta_group::2) variant of the fc1 GEMM: same contract, ragged row tails in either CTA of the pair."""
     x = (fx.randn(210 + M % 97, M, K) * 1.0).bfloat16()
     w = (fx.randn(211 + N % 89, N, K) / K ** 0.5).bfloat16()
     b = (fx.randn(212, N) * 0.2).bfloat16()
-    out = ops.linear_act(cu(x), cu(w), cu(b), act, pair=True)
+    out = ops.linear_act(cu(x), cu(w), cu(b), act)
     ref = torch.nn.functional.linear(x.float(), w.float(), b.float())
     ref = torch.nn.functional.gelu(ref) if act == 1 else (torch.relu(ref) if act == 2 else ref)
     torch.testing.assert_close(out.cpu().float(), ref, rtol=1e-2, atol=1e-2)
     assert out.shape == (M, N) and out.dtype == torch.bfloat16
 
 
-@pytest.mark.parametrize("pair", [False, True])
-def test_gelu_epilogue_is_erf_gelu_to_one_bf16_ulp(ops, pair):
+def test_gelu_epilogue_is_erf_gelu_to_one_bf16_ulp(ops):
     """The epilogue's GELU (erfcx polynomial x one ex2) against float64 erf GELU of the exact pre-activation: identity
     weights make the accumulator exact, so any deviation is the activation's.  <= 1 bf16 ulp down to x = -5.6 (the
     negative tail included: |GELU| ~ 6e-8 there); below that the polynomial's argument is clamped and only |err| < 1e-8 holds."""
     K = N = 256
     xs = torch.linspace(-6.0, 6.0, 512 * K).reshape(512, K).bfloat16()
     w = torch.eye(N, K).bfloat16()
-    out = ops.linear_act(cu(xs), cu(w), None, 1, pair=pair).cpu().double()
+    out = ops.linear_act(cu(xs), cu(w), None, 1).cpu().double()
     x64 = xs.double()
     ref = 0.5 * x64 * torch.special.erfc(-x64 / 2 ** 0.5)
     ulp = torch.maximum(ref.abs(), torch.tensor(1e-30, dtype=torch.float64)) * 2.0 ** -8
@@ -826,21 +812,6 @@ def test_attention_train_fwd_bwd_vs_oracle_autograd(ops, B, T, H, frac):
     assert none is None
     torch.testing.assert_close(o3.detach().cpu().float(), o4.detach(), **tol)
     assert float((q3.grad.cpu().float() - q4.grad).abs().max()) <= 3e-2 * float(q4.grad.abs().max()) + 1e-3
-
-
-@pytest.mark.parametrize("M,N,K", [(197 * 8, 1152, 384), (50432, 1536, 384), (138 * 5, 384, 1536), (40, 8, 8), (1, 384, 384)])
-def test_linear_wgrad_matches_autograd(ops, M, N, K):
-    """dw = dy^T x and db = sum_m dy in one cuBLASLt GEMM (bias-gradient epilogue) against fp32 sums of the same bf16 inputs."""
-    dy = (fx.randn(800 + N, M, N) * 0.5).bfloat16()
-    x = fx.randn(801 + K, M, K).bfloat16()
-    dw, db = ops.linear_wgrad(cu(dy), cu(x))
-    rw = dy.float().t() @ x.float()
-    rb = dy.float().sum(0)
-    assert float((dw.cpu().float() - rw).abs().max()) <= 8e-3 * float(rw.abs().max()) + 1e-3
-    assert float((db.cpu().float() - rb).abs().max()) <= 8e-3 * float(rb.abs().max()) + 1e-3
-    dw2, none = ops.linear_wgrad(cu(dy), cu(x), want_bias=False)
-    assert none is None
-    assert float((dw2.cpu().float() - rw).abs().max()) <= 8e-3 * float(rw.abs().max()) + 1e-3
 
 
 @pytest.mark.parametrize("M,N", [(50432, 1536), (50432, 384), (197 * 7, 1152), (3, 8), (1, 2048), (0, 384)])
