@@ -388,10 +388,15 @@ def predictor_a_hidden(m, x, policy, normed=None):
     return h
 
 
+def _tail_ok(h):
+    """Hidden widths the fused tail kernels take (d2s_score_tail_a / _b): multiples of 8 in [8, 1024], on CUDA."""
+    return h.is_cuda and h.shape[-1] % 8 == 0 and 8 <= h.shape[-1] <= 1024
+
+
 def predictor_a_forward(m, x, policy):
     h = predictor_a_hidden(m, x, policy)
     lin = m.out_conv[4]
-    if _needs_grad(h, lin.weight):
+    if _needs_grad(h, lin.weight) or not _tail_ok(h):
         return m.out_conv[5](lin(h))
     logp, _ = ops.score_tail_a(h, lin.weight, lin.bias, k=0)
     return logp.to(x.dtype)
@@ -403,7 +408,8 @@ def _predictor_a_fusable(m):
     return (len(ic) == 3 and len(oc) == 6 and _is_plain_ln(ic[0]) and isinstance(ic[1], L) and isinstance(ic[2], G)
             and isinstance(oc[0], L) and isinstance(oc[1], G) and isinstance(oc[2], L) and isinstance(oc[3], G)
             and isinstance(oc[4], L) and getattr(ic[2], "approximate", "none") == "none"
-            and oc[0].in_features == ic[1].out_features and ic[1].out_features % 16 == 0)
+            and oc[0].in_features == ic[1].out_features and ic[1].out_features % 16 == 0
+            and oc[4].in_features % 8 == 0 and 8 <= oc[4].in_features <= 1024)
 
 
 def predictor_a_select(m, normed, prev, k):
@@ -462,7 +468,8 @@ def _predictor_b_fusable(m, dtype):
     for i in range(0, len(oc) - 3, 3):
         if not (_ln_ok(oc[i], dtype) and isinstance(oc[i + 1], torch.nn.Linear) and _act_code(oc[i + 2]) is not None):
             return False
-    return _is_plain_ln(oc[-3]) and isinstance(oc[-2], torch.nn.Linear) and oc[-2].out_features == 1
+    return (_is_plain_ln(oc[-3]) and isinstance(oc[-2], torch.nn.Linear) and oc[-2].out_features == 1
+            and oc[-2].in_features % 8 == 0 and 8 <= oc[-2].in_features <= 1024 and ic[1].out_features % 16 == 0)
 
 
 def _linear_act(x, lin, act):
@@ -497,7 +504,7 @@ def predictor_b_forward(m, x, policy=None, current_sigma=0.0005, cls_attn=None, 
         return None
     h, norm, lin = predictor_b_hidden(m, x, normed)
     prob_mode = ops.PROB_SOFTMAX if m.loss_type in ["kl_div", "mse"] else ops.PROB_SIGMOID
-    if _needs_grad(h, lin.weight):
+    if _needs_grad(h, lin.weight) or not _tail_ok(h):
         scores = lin(norm_forward(norm, h)).flatten(-2, -1)
         probs = F.softmax(scores, dim=-1) if prob_mode == ops.PROB_SOFTMAX else torch.sigmoid(scores)
         if k_select is None:
@@ -593,7 +600,11 @@ def variant_a_forward(model, img):
                         prev_decision = prev_f32.unsqueeze(-1).to(dt)
                     h = predictor_a_hidden(pred, x[:, 1:], prev_decision)
                     lin = pred.out_conv[4]
-                    _, keep_policy = ops.score_tail_a(h, lin.weight, lin.bias, k=k)
+                    if _tail_ok(h):
+                        _, keep_policy = ops.score_tail_a(h, lin.weight, lin.bias, k=k)
+                    else:                                # widths outside the tail kernel: torch tail, d2s selection
+                        logp = pred.out_conv[5](lin(h))
+                        keep_policy, _ = ops.select_topk(logp[:, :, 0], k, ops.ORDER_SCORE_DESC, want_dropped=False)
                     prev_decision = ops.batch_index_select(prev_decision, keep_policy)
                     prev_f32 = prev_decision.reshape(B, -1).float()
                 model.kept_token_indices.append(keep_policy)
