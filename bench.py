@@ -1,17 +1,25 @@
 #!/usr/bin/env python
 """Throughput of the token-sparsification hot path inside DynamicViT DeiT-S/16, keep rate 0.7, 224 px.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl d2s|reference] [--batch B]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl d2s|reference] [--batch B] [--legs a,b,...]
 
-A "step" is one inference pass of the pruned model over one batch of synthetic images (BASELINE.json
-configs[1]: batch 1024 per GPU, bf16).  N > 1 = one process per GPU (torchrun), the batch dimension is sharded
-with no data-path collective (weak scaling: every rank owns its own 1024 images).  Rank 0 prints ONE JSON line.
+A "step" is one inference pass of the pruned model over one batch of synthetic images (BASELINE.json configs[1]: batch 1024
+per GPU, bf16).  N > 1 = one process per GPU (torchrun); the batch dimension is sharded with no data-path collective (weak
+scaling: every rank owns its own 1024 images).  Rank 0 prints ONE JSON line.
 
-  value        images/s, inputs resident in HBM, CUDA-graph replay of the whole forward, CUDA-event timed
-  e2e          images/s through the public API with pinned HOST images in and HOST logits out every step
-  roofline     the dominant d2s kernel (policy attention), timed alone with CUDA events at the step's shapes
-  cpu_baseline the CPU restatement of the reference forward (oracle/), timed on this box's host cores
-  --impl reference   times that CPU forward alone (the reference is pure PyTorch-on-CPU)
+  value          images/s, inputs resident in HBM, CUDA-graph replay of the whole forward, CUDA-event timed, max over ranks
+  e2e            images/s through the public API with pinned HOST images in and HOST logits out every step
+  parity_checked the gate run before any timing: 8 images through the fp32 GPU path and the bf16 path against the CPU oracle
+  roofline       the step's dominant d2s kernel (the one-kernel MLP, tensor-bound), aggregated over its launches per step
+  kernels        every d2s kernel of the step timed alone inside a CUDA graph (no host launch time), rotating buffers > L2
+  train          BASELINE configs[2]: Variant A training step (student fwd+bwd, frozen teacher, distillation losses, AdamW),
+                 bf16 autocast, batch 256 per GPU; N > 1: one NCCL all-reduce of the flat gradient buffer per step
+  ptopk          BASELINE configs[3]: PerturbedTopK forward + backward (N=196, k=98, 500 samples), B in {1, 8, 64, 256}
+  sweep          BASELINE configs[4]: select / gather / scatter, D in {384, 768}, bf16 and fp32, keep 0.3-0.9, B 64-4096
+  h2d_only       the host->device copy of the e2e leg alone (its ceiling), at N ranks
+  gpu_eager_baseline  the oracle's restatement of the reference forward executed by torch eager on the same GPU in bf16
+  cpu_baseline   the CPU restatement of the reference forward (oracle/), timed on this box's host cores
+  --impl reference   times that CPU forward alone (the reference is pure PyTorch)
 """
 import argparse
 import json
@@ -31,6 +39,10 @@ UNIT = "images/s"
 LOCS, RATIOS = [3, 6, 9], [0.7, 0.7 ** 2, 0.7 ** 3]   # upstream DynamicViT convention (SURVEY.md 8d cfg 1/2)
 DEIT_S = dict(patch_size=16, embed_dim=384, depth=12, num_heads=6, mlp_ratio=4, qkv_bias=True)
 GFLOP_PER_IMG = 5.96                                    # SURVEY.md 8d, Variant A 3 stages
+TRAIN_GFLOP_PER_IMG = 36.8                              # 3 x 9.2 (student fwd+bwd at T=197) + 9.2 (teacher fwd)
+ALL_LEGS = ("parity", "infer", "e2e", "h2d", "train", "kernels", "ptopk", "sweep", "eager", "cpu")
+W_SEED = 61                                             # seeded weights (tests/golden/fixtures.py): well-spread predictor scores
+L2_BYTES = 126e6
 
 
 def parse():
@@ -40,9 +52,12 @@ def parse():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="d2s", choices=["d2s", "reference"])
     ap.add_argument("--batch", type=int, default=1024, help="images per GPU per step")
+    ap.add_argument("--train-batch", type=int, default=256, help="images per GPU per training step (BASELINE configs[2])")
+    ap.add_argument("--train-steps", type=int, default=10)
     ap.add_argument("--cpu-batch", type=int, default=8, help="images per CPU step (BASELINE configs[0])")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true", help="omit the cpu_baseline leg (debugging only)")
+    ap.add_argument("--legs", default=",".join(ALL_LEGS), help="comma-separated subset of: " + ", ".join(ALL_LEGS))
     return ap.parse_args()
 
 
@@ -56,6 +71,14 @@ def peaks():
     return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback")
 
 
+def seeded_weights(model):
+    """Random weights with non-degenerate predictor scores, a pure function of the architecture (fixtures.seeded_state_dict)."""
+    import fixtures as fx
+    sd = fx.seeded_state_dict({k: tuple(v.shape) for k, v in model.state_dict().items()}, W_SEED)
+    model.load_state_dict(sd)
+    return sd
+
+
 # ---------------------------------------------------------------------------------------------------
 # CPU arm: the oracle's restatement of DefaultVisionTransformerDiffPruning.forward (eval), all host threads
 # ---------------------------------------------------------------------------------------------------
@@ -63,9 +86,8 @@ def cpu_forward_setup(batch):
     import torch
     from oracle import model as om           # bench.py's cpu legs are allowed to execute oracle/
     import d2s
-    torch.manual_seed(0)
     m = d2s.pkg.variant_a.DefaultVisionTransformerDiffPruning(pruning_loc=LOCS, token_ratio=RATIOS, distill=True, **DEIT_S)
-    sd = {k: v.detach().float() for k, v in m.state_dict().items()}
+    sd = {k: v.detach().float() for k, v in seeded_weights(m).items()}
     cfg = om.VitCfg(embed_dim=384, depth=12, num_heads=6, pruning_loc=LOCS, token_ratio=RATIOS)
     img = torch.randn(batch, 3, 224, 224, generator=torch.Generator().manual_seed(42))
     return om, sd, cfg, img
@@ -113,7 +135,7 @@ def run_reference(args):
 
 
 # ---------------------------------------------------------------------------------------------------
-# GPU arm
+# GPU arm: helpers
 # ---------------------------------------------------------------------------------------------------
 class ClockSampler:
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -157,103 +179,188 @@ class ClockSampler:
                 "reasons": sorted(reasons)}
 
 
-def time_kernel(fn, iters, torch):
-    """Average duration (ms) of `fn` over `iters` back-to-back launches on the current stream (CUDA events)."""
-    for _ in range(3):
-        fn()
-    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+def time_graphed(calls, torch, launches=24, replays=5):
+    """Average GPU duration (ms) of one kernel launch.  `calls` is a list of closures doing the SAME launch on different
+    argument sets (rotating buffers: their combined footprint should exceed the L2); `launches` of them are captured
+    round-robin into one CUDA graph, so no host launch time sits between kernels; the graph is replayed `replays` times between
+    two CUDA events on the replaying stream."""
+    reps = max(1, launches // len(calls))
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for c in calls:
+            c()
+    torch.cuda.current_stream().wait_stream(side)
     torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        for _ in range(reps):
+            for c in calls:
+                c()
+    graph.replay()
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s.record()
-    for _ in range(iters):
-        fn()
+    for _ in range(replays):
+        graph.replay()
     e.record()
     torch.cuda.synchronize()
-    return s.elapsed_time(e) / iters
+    ms = s.elapsed_time(e) / (replays * reps * len(calls))
+    del graph
+    return ms
 
 
+def nsets_for(bytes_per_call):
+    """How many rotating argument sets make the working set larger than twice the L2 (at most 8, at least 1)."""
+    return int(max(1, min(8, -(-2 * L2_BYTES // max(1.0, float(bytes_per_call))))))
+
+
+def row(kernel, shape, ms, algo_bytes, launches_per_step=None, flops=None):
+    r = dict(kernel=kernel, shape=shape, us=ms * 1e3, algo_bytes=algo_bytes, gbs=algo_bytes / ms / 1e6)
+    if launches_per_step is not None:
+        r["launches_per_step"] = launches_per_step
+    if flops is not None:
+        r["tflops"] = flops / ms / 1e9
+    return r
+
+
+# ---------------------------------------------------------------------------------------------------
+# parity gate
+# ---------------------------------------------------------------------------------------------------
+def parity_gate(pkg, model16, sd, dev, torch):
+    """8 images, before anything is timed: (1) the fp32 GPU path against the CPU oracle on the same weights -- kept-token sets
+    bit-exact at all three stages, logits 1e-4; (2) the bf16 model that is about to be timed against the fp32 oracle on the
+    bf16-ROUNDED weights and images -- tokens may only change sides where the fp32 score is within bf16 noise of the cut."""
+    import copy
+    from oracle import model as om
+    cfg = om.VitCfg(embed_dim=384, depth=12, num_heads=6, pruning_loc=LOCS, token_ratio=RATIOS)
+    img = torch.randn(8, 3, 224, 224, generator=torch.Generator().manual_seed(7)).bfloat16().float()
+    sd32 = {k: v.detach().float() for k, v in sd.items()}
+    ref = om.variant_a_eval(sd32, cfg, img)
+    m32 = pkg.variant_a.DefaultVisionTransformerDiffPruning(pruning_loc=LOCS, token_ratio=RATIOS, distill=True, **DEIT_S)
+    m32.load_state_dict(sd32)
+    m32 = m32.to(dev).eval()
+    with torch.no_grad():
+        l32 = m32(img.to(dev)).cpu()
+    kept_exact = all(torch.equal(m32.kept_token_indices[s].cpu(), ref["kept"][s]) for s in range(3))
+    rel32 = float((l32 - ref["logits"]).abs().max() / ref["logits"].abs().max())
+    del m32
+    sdr = {k: (v.bfloat16().float() if v.is_floating_point() else v) for k, v in sd32.items()}
+    refr = om.variant_a_eval(sdr, cfg, img)
+    with torch.no_grad():
+        l16 = model16(img.to(dev, torch.bfloat16)).float().cpu()
+    k16 = model16.kept_token_indices[0].cpu()
+    s32 = refr["scores"][0][:, :, 0]
+    K = k16.shape[1]
+    srt = torch.sort(s32, dim=-1, descending=True).values
+    near = ((s32 - srt[:, K - 1:K]).abs() < 0.05).sum(1)
+    a, b = torch.zeros(8, 196, dtype=torch.bool), torch.zeros(8, 196, dtype=torch.bool)
+    a.scatter_(1, k16, True)
+    b.scatter_(1, refr["kept"][0], True)
+    flips = (a ^ b).sum(1)
+    margin_ok = bool((flips <= 2 * near).all()) and bool((flips[(srt[:, K - 1] - srt[:, K]) > 0.05] == 0).all())
+    out = {"images": 8, "oracle": "oracle.model.variant_a_eval (CPU fp32; equals the unmodified reference to 2e-6 at this config)",
+           "fp32_kept_sets_bit_exact": kept_exact, "fp32_logits_max_rel": rel32,
+           "bf16_stage1_flipped_tokens": int(flips.sum()), "bf16_flips_within_fp32_score_margin": margin_ok,
+           "bf16_logits_rel_l2_incl_flips": float((l16 - refr["logits"]).norm() / refr["logits"].norm()),
+           "ok": bool(kept_exact and rel32 <= 1e-4 and margin_ok and bool(torch.isfinite(l16).all()))}
+    if not out["ok"]:
+        raise SystemExit("bench.py: parity gate failed, nothing is timed: " + json.dumps(out))
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# per-kernel breakdown (graph-timed)
+# ---------------------------------------------------------------------------------------------------
 def kernel_breakdown(ops, B, dev, torch, pk):
     """Time every d2s kernel of one forward alone, at the shapes the step launches them with.
     Returns (rows, roofline dict for the dominant kernel)."""
     D, H, hd, N0 = 384, 6, 64, 196
     e = 2  # bf16
     rows = []
-    # token count per layer: blocks 0-2: 197; 3-5: 138; 6-8: 97; 9-11: 68
+    bf = torch.bfloat16
     Ks = [int(N0 * r) for r in RATIOS]
-    Ts = [N0 + 1] + [k + 1 for k in Ks]
-    attn_ms, attn_bytes, attn_flops = 0.0, 0.0, 0.0
-    pair_ms, pair_bytes, pair_flops, pair_n = 0.0, 0.0, 0.0, 0
-    mlp_ms, mlp_bytes, mlp_flops, mlp_n = 0.0, 0.0, 0.0, 0
-    for T in Ts:
-        qkv = torch.randn(B, T, 3 * D, device=dev, dtype=torch.bfloat16)
-        ms = time_kernel(lambda: ops.attention_core(qkv, H), 20, torch)
-        by = B * (e * 4 * T * D)                      # q,k,v in + out, bf16 (SURVEY.md 8d row 4)
+    Ts = [N0 + 1] + [k + 1 for k in Ks]                   # tokens per block group: 197, 138, 97, 68
+    agg = {k: dict(ms=0.0, by=0.0, fl=0.0, n=0) for k in ("attn", "pair", "mlp")}
+
+    def acc(key, ms, by, fl, n):
+        a = agg[key]
+        a["ms"] += n * ms; a["by"] += n * by; a["fl"] += n * fl; a["n"] += n
+
+    gw, gb = torch.ones(D, device=dev, dtype=bf), torch.zeros(D, device=dev, dtype=bf)
+    wp = torch.randn(D, D, device=dev, dtype=bf) * 0.05
+    w1 = torch.randn(4 * D, D, device=dev, dtype=bf) * 0.05
+    w2 = torch.randn(D, 4 * D, device=dev, dtype=bf) * 0.02
+    b1 = torch.zeros(4 * D, device=dev, dtype=bf)
+    for gi, T in enumerate(Ts):
+        by_attn = B * (e * 4 * T * D)                      # q,k,v in + out, bf16 (SURVEY.md 8d row 4)
+        ns = nsets_for(by_attn)
+        qkvs = [torch.randn(B, T, 3 * D, device=dev, dtype=bf) for _ in range(ns)]
+        ms = time_graphed([lambda q=q: ops.attention_core(q, H) for q in qkvs], torch, launches=12)
         fl = B * 4.0 * H * T * T * hd
-        rows.append(dict(kernel="attn_policy_fwd(tcgen05)", shape=f"B={B},T={T},H={H},hd={hd}", launches_per_step=3,
-                         ms=ms, algo_bytes=by, gbs=by / ms / 1e6, tflops=fl / ms / 1e9))
-        attn_ms += 3 * ms; attn_bytes += 3 * by; attn_flops += 3 * fl
-        del qkv
-        # the other per-block d2s kernels at this token count: the CTA-pair GEMMs (proj / fc2 + residual + next LayerNorm,
-        # fc1 + GELU) and the stand-alone add + LayerNorm that is left at the pruning stages and the first block
-        xr = torch.randn(B, T, D, device=dev, dtype=torch.bfloat16)
-        yr = torch.randn(B, T, D, device=dev, dtype=torch.bfloat16)
-        gw, gb = torch.ones(D, device=dev, dtype=torch.bfloat16), torch.zeros(D, device=dev, dtype=torch.bfloat16)
-        wp = torch.randn(D, D, device=dev, dtype=torch.bfloat16) * 0.05
-        w1 = torch.randn(4 * D, D, device=dev, dtype=torch.bfloat16) * 0.05
-        w2 = torch.randn(D, 4 * D, device=dev, dtype=torch.bfloat16) * 0.02
-        b1 = torch.zeros(4 * D, device=dev, dtype=torch.bfloat16)
-        ur = torch.randn(B, T, 4 * D, device=dev, dtype=torch.bfloat16)
-        gi = Ts.index(T)
-        # launches per step in this token-count group of 3 blocks (engine._Stream): proj+LN 3; fc2+LN 2; the third fc2 feeds the
-        # predictor's LayerNorm over x[:, 1:] (groups 0-2: fc2 + residual only, then add_layernorm) or the CLS head (group 3)
-        ms = time_kernel(lambda: ops.linear_residual_ln(yr, wp, gb, xr, gw, gb, 1e-6), 10, torch)
+        rows.append(row("attn_policy_fwd(tcgen05)", f"B={B},T={T},H={H},hd={hd}", ms, by_attn, 3, fl))
+        acc("attn", ms, by_attn, fl, 3)
+        del qkvs
+        xs = [(torch.randn(B, T, D, device=dev, dtype=bf), torch.randn(B, T, D, device=dev, dtype=bf)) for _ in range(2)]
         by, fl = B * T * e * 4 * D, 2.0 * B * T * D * D
-        rows.append(dict(kernel="linear_residual_ln(proj+add+LN, tcgen05 pair)", shape=f"M={B * T},N={D},K={D}", launches_per_step=3,
-                         ms=ms, algo_bytes=by, gbs=by / ms / 1e6, tflops=fl / ms / 1e9))
-        pair_ms += 3 * ms; pair_bytes += 3 * by; pair_flops += 3 * fl; pair_n += 3
+        ms = time_graphed([lambda x=x, y=y: ops.linear_residual_ln(y, wp, gb, x, gw, gb, 1e-6) for x, y in xs], torch, launches=12)
+        rows.append(row("linear_residual_ln(proj+add+LN, tcgen05 pair)", f"M={B * T},N={D},K={D}", ms, by, 3, fl))
+        acc("pair", ms, by, fl, 3)
         # the MLP branch in one kernel (fc1 + GELU + fc2 + residual + next LayerNorm): the step's dominant kernel, tensor-bound
         # (4.7 MFLOP per token against 3 KB of HBM traffic)
-        ms = time_kernel(lambda: ops.mlp_residual_ln(xr, w1, b1, w2, gb, yr, gw, gb, 1e-6), 10, torch)
         by, fl = B * T * e * 4 * D, 4.0 * B * T * D * 4 * D
-        rows.append(dict(kernel="mlp_residual_ln(fc1+GELU+fc2+add+LN, tcgen05 pair)", shape=f"M={B * T},D={D},HID={4 * D}", launches_per_step=2,
-                         ms=ms, algo_bytes=by, gbs=by / ms / 1e6, tflops=fl / ms / 1e9))
-        mlp_ms += 2 * ms; mlp_bytes += 2 * by; mlp_flops += 2 * fl; mlp_n += 2
+        ms = time_graphed([lambda x=x, y=y: ops.mlp_residual_ln(x, w1, b1, w2, gb, y, gw, gb, 1e-6) for x, y in xs], torch, launches=8)
+        rows.append(row("mlp_residual_ln(fc1+GELU+fc2+add+LN, tcgen05 pair)", f"M={B * T},D={D},HID={4 * D}", ms, by, 2, fl))
+        acc("mlp", ms, by, fl, 2)
         if gi < 3:   # the block in front of a pruning stage: the LayerNorm is the predictor's, over x[:, 1:]
-            ms = time_kernel(lambda: ops.mlp_residual_ln(xr, w1, b1, w2, gb, yr, gw, gb, 1e-6, norm_row0=1), 10, torch)
+            ms = time_graphed([lambda x=x, y=y: ops.mlp_residual_ln(x, w1, b1, w2, gb, y, gw, gb, 1e-6, norm_row0=1) for x, y in xs],
+                              torch, launches=8)
             by = B * e * D * (3 * T + T - 1)
-            rows.append(dict(kernel="mlp_residual_ln(fc1+GELU+fc2+add+LN over x[:,1:], tcgen05 pair)", shape=f"M={B * T},D={D},HID={4 * D}",
-                             launches_per_step=1, ms=ms, algo_bytes=by, gbs=by / ms / 1e6, tflops=fl / ms / 1e9))
-            mlp_ms += ms; mlp_bytes += by; mlp_flops += fl; mlp_n += 1
-        if gi == 0:   # the first block's norm1 is the only stand-alone LayerNorm over all tokens left in the step
-            ms = time_kernel(lambda: ops.add_layernorm(xr, None, gw, gb, 1e-6), 20, torch)
-            by = B * T * D * e * 2
-            rows.append(dict(kernel="add_layernorm(no branch)", shape=f"B={B},T={T},D={D}", launches_per_step=1, ms=ms,
-                             algo_bytes=by, gbs=by / ms / 1e6))
-        del xr, yr, w1, w2, ur, wp
+            rows.append(row("mlp_residual_ln(... LN over x[:,1:])", f"M={B * T},D={D},HID={4 * D}", ms, by, 1, fl))
+            acc("mlp", ms, by, fl, 1)
+        if gi == 0:  # the first block's norm1: token assembly fused with the LayerNorm
+            pos, cls = torch.randn(1, T, D, device=dev, dtype=bf), torch.randn(1, 1, D, device=dev, dtype=bf)
+            ps = [torch.randn(B, T - 1, D, device=dev, dtype=bf) for _ in range(2)]
+            ms = time_graphed([lambda p=p: ops.assemble_layernorm(p, cls, pos, gw, gb, 1e-6) for p in ps], torch, launches=12)
+            rows.append(row("assemble_layernorm(token assembly + norm1)", f"B={B},T={T},D={D}", ms, B * T * D * e * 3, 1))
+            imgs = [torch.randn(B, 3, 224, 224, device=dev, dtype=bf) for _ in range(2)]
+            ms = time_graphed([lambda i=i: ops.patchify(i, 16, 16) for i in imgs], torch, launches=12)
+            rows.append(row("patchify(im2col)", f"B={B},3x224x224", ms, B * 3 * 224 * 224 * e * 2, 1))
+            del imgs, ps
+        del xs
     n_in = N0
     for s, K in enumerate(Ks):
         T_in = n_in + 1
-        x = torch.randn(B, T_in, D, device=dev, dtype=torch.bfloat16)
-        sc = torch.rand(B, n_in, device=dev)
-        kept, _ = ops.select_topk(sc, K, ops.ORDER_SCORE_DESC, want_dropped=False)
-        gw2, gb2 = torch.ones(D, device=dev, dtype=torch.bfloat16), torch.zeros(D, device=dev, dtype=torch.bfloat16)
-        ms = time_kernel(lambda: ops.gather_layernorm(x, kept, gw2, gb2, 1e-6), 50, torch)
         by = B * (3 * e * D * (K + 1) + 8 * (K + 1))
-        rows.append(dict(kernel="gather_layernorm(kept-token gather + norm1)", shape=f"B={B},T={T_in},D={D},K={K}", launches_per_step=1, ms=ms,
-                         algo_bytes=by, gbs=by / ms / 1e6))
-        hid = torch.randn(B, n_in, D // 4, device=dev, dtype=torch.bfloat16)
-        W = torch.randn(2, D // 4, device=dev) * 0.1
-        bias = torch.zeros(2, device=dev)
-        ms = time_kernel(lambda: ops.score_tail_a(hid, W, bias, k=K), 50, torch)
-        by = B * (e * n_in * (D // 4) + 8 * n_in + 8 * K)
-        rows.append(dict(kernel="score_tail_a(+select)", shape=f"B={B},N={n_in},C={D // 4},K={K}", launches_per_step=1,
-                         ms=ms, algo_bytes=by, gbs=by / ms / 1e6))
-        pd = torch.ones(B, n_in, 1, device=dev, dtype=torch.bfloat16)
-        ms = time_kernel(lambda: ops.batch_index_select(pd, kept), 50, torch)
-        rows.append(dict(kernel="batch_index_select(prev_decision)", shape=f"B={B},N={n_in},K={K}", launches_per_step=1,
-                         ms=ms, algo_bytes=B * (2 * e * K + 8 * K), gbs=B * (2 * e * K + 8 * K) / ms / 1e6))
+        ns = nsets_for(by)
+        sets = []
+        for _ in range(ns):
+            x = torch.randn(B, T_in, D, device=dev, dtype=bf)
+            kept, _ = ops.select_topk(torch.rand(B, n_in, device=dev), K, ops.ORDER_SCORE_DESC, want_dropped=False)
+            sets.append((x, kept))
+        ms = time_graphed([lambda x=x, k=k: ops.gather_layernorm(x, k, gw, gb, 1e-6) for x, k in sets], torch)
+        rows.append(row("gather_layernorm(kept-token gather + norm1)", f"B={B},T={T_in},D={D},K={K}", ms, by, 1))
+        del sets
+        # the fused predictor tail: GELU on load of the (B,N,D/4) hidden activations, Linear(D/4,2), log-softmax, top-K in score order,
+        # previous decisions gathered (what engine.predictor_a_select launches)
+        by = B * (e * n_in * (D // 4) + 8 * n_in + 8 * K + 4 * K + (4 * n_in if s else 0))
+        ns = nsets_for(by)
+        W, bias = torch.randn(2, D // 4, device=dev) * 0.1, torch.zeros(2, device=dev)
+        hids = [torch.randn(B, n_in, D // 4, device=dev, dtype=bf) for _ in range(ns)]
+        prev = (torch.rand(B, n_in, device=dev) > 0.1).float() if s else None
+        ms = time_graphed([lambda h=h: ops.score_tail_a(h, W, bias, k=K, prev=prev, act_input=ops.ACT_GELU, want_prev_kept=True)
+                           for h in hids], torch)
+        rows.append(row("score_tail_a(GELU + Linear + log-softmax + top-K + prev gather)", f"B={B},N={n_in},C={D // 4},K={K}", ms, by, 1))
+        zs = [torch.randn(B, n_in, D, device=dev, dtype=bf) for _ in range(nsets_for(B * n_in * D * e * 1.5))]
+        ms = time_graphed([lambda z=z: ops.pool_act(z, prev, ops.ACT_GELU) for z in zs], torch)
+        rows.append(row("pool_act(GELU + policy-weighted mean pool)", f"B={B},N={n_in},C={D}", ms, B * n_in * D * e * 1.5, 1))
+        us = [torch.randn(B, n_in, D // 2, device=dev, dtype=bf) for _ in range(nsets_for(B * n_in * D * e))]
+        pim = torch.randn(B, D // 2, device=dev, dtype=bf)
+        ms = time_graphed([lambda u=u: ops.bias_act_(u, pim, ops.ACT_GELU) for u in us], torch)
+        rows.append(row("bias_act(per-image bias + GELU, in place)", f"B={B},N={n_in},C={D // 2}", ms, B * n_in * D * e, 1))
         n_in = K
-        del x, sc, hid
-    # dominant kernel of the step (profiles/: ~37 % of the serialised step): the one-kernel MLP.  Tensor-bound: 4 * D * 4D flops
+        del hids, zs, us
+    # dominant kernel of the step (profiles/: ~38 % of the serialised step): the one-kernel MLP.  Tensor-bound: 4 * D * 4D flops
     # per token against 4 * D * 2 bytes of HBM traffic (the hidden activations stay on chip).  Aggregated over its launches at
     # the four token counts; peak = the measured burst bf16 GEMM rate (the kernel is timed alone).
     traffic = None
@@ -263,23 +370,209 @@ def kernel_breakdown(ops, B, dev, torch, pk):
             traffic = tj["dram_bytes_per_step"] / tj["launches_per_step"]
     except (OSError, KeyError, ValueError):
         pass
-    roof = {"kernel": f"mlp_pair_kernel (fc1 + GELU + fc2 + residual + LayerNorm, {mlp_n} launches/step, T=197/138/97/68)",
-            "bound": "tensor", "achieved": mlp_flops / mlp_ms / 1e9, "peak": pk["tf_burst"], "unit": "TFLOP/s",
-            "frac": mlp_flops / mlp_ms / 1e9 / pk["tf_burst"], "traffic": traffic, "peak_source": pk["source"],
-            "flops_per_launch": mlp_flops / mlp_n, "algo_bytes_per_launch": mlp_bytes / mlp_n, "ms_per_launch": mlp_ms / mlp_n,
-            "ms_per_step_in_kernel": mlp_ms,
-            "frac_of_sustained_peak": mlp_flops / mlp_ms / 1e9 / pk["tf_sustained"],
-            "hbm": {"achieved": mlp_bytes / mlp_ms / 1e6, "peak": pk["hbm"], "unit": "GB/s", "frac": mlp_bytes / mlp_ms / 1e6 / pk["hbm"]},
-            "proj_ln": {"kernel": f"gemm_pair_kernel<LN> (proj + residual + LayerNorm, {pair_n} launches/step)", "bound": "hbm",
-                        "achieved": pair_bytes / pair_ms / 1e6, "frac": pair_bytes / pair_ms / 1e6 / pk["hbm"],
-                        "ms_per_step_in_kernel": pair_ms},
-            "attention": {"kernel": "attn_tc_fwd_kernel (12 launches/step)", "bound": "hbm",
-                          "achieved": attn_bytes / attn_ms / 1e6, "frac": attn_bytes / attn_ms / 1e6 / pk["hbm"],
-                          "ms_per_step_in_kernel": attn_ms,
-                          "tensor": {"achieved": attn_flops / attn_ms / 1e9, "frac": attn_flops / attn_ms / 1e9 / pk["tf_burst"]}}}
+    m, p, a = agg["mlp"], agg["pair"], agg["attn"]
+    roof = {"kernel": f"mlp_pair_kernel (fc1 + GELU + fc2 + residual + LayerNorm, {m['n']} launches/step, T=197/138/97/68)",
+            "bound": "tensor", "achieved": m["fl"] / m["ms"] / 1e9, "peak": pk["tf_burst"], "unit": "TFLOP/s",
+            "frac": m["fl"] / m["ms"] / 1e9 / pk["tf_burst"], "traffic": traffic, "peak_source": pk["source"],
+            "flops_per_launch": m["fl"] / m["n"], "algo_bytes_per_launch": m["by"] / m["n"], "ms_per_launch": m["ms"] / m["n"],
+            "ms_per_step_in_kernel": m["ms"],
+            "frac_of_sustained_peak": m["fl"] / m["ms"] / 1e9 / pk["tf_sustained"],
+            "hbm": {"achieved": m["by"] / m["ms"] / 1e6, "peak": pk["hbm"], "unit": "GB/s", "frac": m["by"] / m["ms"] / 1e6 / pk["hbm"]},
+            "proj_ln": {"kernel": f"gemm_pair_kernel<LN> (proj + residual + LayerNorm, {p['n']} launches/step)", "bound": "hbm",
+                        "achieved": p["by"] / p["ms"] / 1e6, "frac": p["by"] / p["ms"] / 1e6 / pk["hbm"],
+                        "ms_per_step_in_kernel": p["ms"]},
+            "attention": {"kernel": f"attn_tc_fwd_kernel ({a['n']} launches/step)", "bound": "hbm",
+                          "achieved": a["by"] / a["ms"] / 1e6, "frac": a["by"] / a["ms"] / 1e6 / pk["hbm"],
+                          "ms_per_step_in_kernel": a["ms"],
+                          "tensor": {"achieved": a["fl"] / a["ms"] / 1e9, "frac": a["fl"] / a["ms"] / 1e9 / pk["tf_burst"]}},
+            "timing": "each kernel alone, launches captured in a CUDA graph (no host launch time), rotating argument sets > 2x L2"}
     return rows, roof
 
 
+# ---------------------------------------------------------------------------------------------------
+# BASELINE configs[3]: PerturbedTopK, configs[4]: select / gather sweep
+# ---------------------------------------------------------------------------------------------------
+def ptopk_leg(ops, dev, torch, pk):
+    N, K, S = 196, 98, 500
+    out = []
+    for B in (1, 8, 64, 256):
+        nsets = nsets_for(B * 4 * S * N)
+        xs = [torch.softmax(torch.randn(B, N, device=dev), -1) for _ in range(nsets)]
+        noises = [torch.randn(B, S, N, device=dev) for _ in range(nsets)]
+        ind = torch.empty(B, K, N, device=dev)
+        eg = torch.empty(B, K, N, device=dev)
+        gx = torch.empty(B, N, device=dev)
+        go = torch.randn(B, K, N, device=dev)
+        call = ops._lib.call
+        st = lambda: torch.cuda.current_stream().cuda_stream   # noqa: E731
+        f_ms = time_graphed([lambda x=x, nz=nz: call("d2s_ptopk_fwd", x.data_ptr(), nz.data_ptr(), B, N, K, S, 0.05, ind.data_ptr(),
+                                                     eg.data_ptr(), st()) for x, nz in zip(xs, noises)], torch)
+        r_ms = time_graphed([lambda x=x: call("d2s_ptopk_fwd_rng", x.data_ptr(), 7, B, N, K, S, 0.05, ind.data_ptr(), eg.data_ptr(), st())
+                             for x in xs], torch)
+        b_ms = time_graphed([lambda: call("d2s_ptopk_bwd", go.data_ptr(), eg.data_ptr(), B, N, K, gx.data_ptr(), st())], torch)
+        f_by, b_by = B * (4 * N + 4 * S * N + 8 * K * N), B * (8 * K * N + 4 * N)
+        out.append({"B": B, "fwd_us": f_ms * 1e3, "fwd_gbs": f_by / f_ms / 1e6, "fwd_frac_hbm": f_by / f_ms / 1e6 / pk["hbm"],
+                    "fwd_rng_us": r_ms * 1e3, "bwd_us": b_ms * 1e3, "bwd_gbs": b_by / b_ms / 1e6,
+                    "fwd_bwd_us": (f_ms + b_ms) * 1e3, "selections_per_s": B * S / f_ms * 1e3,
+                    "reference_materialises_bytes": B * S * K * N * (4 + 8)})
+        del xs, noises
+    return {"config": "PerturbedTopK N=196 (DeiT-B/16 spatial tokens), k=98, num_samples=500, sigma=0.05, injected noise; fwd also "
+                      "writes the backward's expected-gradient tensor; algorithmic bytes per SURVEY.md 8d row (2)", "rows": out}
+
+
+def sweep_leg(ops, dev, torch, pk):
+    N = 196
+    rows = []
+    for B in (64, 1024, 4096):
+        for ratio in (0.3, 0.7, 0.9):
+            K = int(N * ratio)
+            scs = [torch.rand(B, N, device=dev) for _ in range(nsets_for(B * 12 * N))]
+            ms = time_graphed([lambda s=s: ops.select_topk(s, K, ops.ORDER_INDEX_ASC) for s in scs], torch)
+            rows.append(row("select_topk(index asc, +dropped)", f"B={B},N={N},K={K}", ms, B * (4 * N + 8 * N)))
+            kept, _ = ops.select_topk(scs[0], K, ops.ORDER_INDEX_ASC)
+            for D in (384, 768):
+                for dt, e, name in ((torch.bfloat16, 2, "bf16"), (torch.float32, 4, "f32")):
+                    if B == 4096 and ratio != 0.7:
+                        continue                      # the largest batch at the headline keep rate only
+                    by_f = B * (2 * e * D * (K + 1) + 8 * (K + 1))
+                    xs = [torch.randn(B, N + 1, D, device=dev, dtype=dt) for _ in range(nsets_for(by_f))]
+                    ms = time_graphed([lambda x=x: ops.gather_tokens(x, kept) for x in xs], torch, launches=16)
+                    rows.append(row("gather_tokens fwd", f"B={B},T={N + 1},D={D},K={K},{name}", ms, by_f))
+                    del xs
+                    by_b = B * (e * D * ((K + 1) + (N + 1)) + 8 * (K + 1))
+                    gs = [torch.randn(B, K + 1, D, device=dev, dtype=dt) for _ in range(nsets_for(by_b))]
+                    ms = time_graphed([lambda g=g: ops.scatter_tokens_bwd(g, kept, N + 1) for g in gs], torch, launches=16)
+                    rows.append(row("scatter_tokens bwd", f"B={B},T={N + 1},D={D},K={K},{name}", ms, by_b))
+                    del gs
+    for r in rows:
+        r["frac_hbm"] = r["gbs"] / pk["hbm"]
+    return {"config": "N=196; D in {384,768}; keep 0.3/0.7/0.9; B in {64,1024,4096}; bf16 and fp32; HBM fraction of the measured peak",
+            "rows": rows}
+
+
+# ---------------------------------------------------------------------------------------------------
+# BASELINE configs[2]: training step
+# ---------------------------------------------------------------------------------------------------
+def train_leg(pkg, args, dev, rank, world, torch, dist, pk):
+    B = args.train_batch
+    torch.manual_seed(0)
+    student = pkg.variant_a.DefaultVisionTransformerDiffPruning(pruning_loc=LOCS, token_ratio=RATIOS, distill=True, **DEIT_S)
+    seeded_weights(student)
+    student = student.to(dev).train()
+    teacher = pkg.variant_a.DefaultVisionTransformerTeacher(**DEIT_S).to(dev).eval()
+    for p in teacher.parameters():
+        p.requires_grad_(False)
+    crit = pkg.losses.DistillDiffPruningLoss(teacher, keep_ratio=RATIOS)
+    opt = torch.optim.AdamW(student.parameters(), lr=5e-4, weight_decay=0.05, capturable=True)
+    grads = pkg.runner.FlatGrads(student.parameters())
+    g = torch.Generator(device=dev).manual_seed(42 + rank)
+    x = torch.randn(B, 3, 224, 224, device=dev, generator=g)
+    y = torch.randint(0, 1000, (B,), device=dev, generator=g)
+
+    def fwd_loss(xx, yy):
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            return crit(xx, student(xx), yy)[0]
+
+    n0 = pkg._lib.launch_count()
+    run = pkg.runner.TrainStepRunner(fwd_loss, opt, x, y, warmup=2, use_graph=not args.no_graph, grads=grads)
+    per_step = (pkg._lib.launch_count() - n0) // (3 if not args.no_graph else 2)
+    W, K = 3, args.train_steps
+    for _ in range(W):
+        run()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        loss = run()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.barrier()
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    # host -> device fed variant of the same step: pinned fp32 images + labels copied in every step (the e2e form)
+    hx, hy = x.cpu().pin_memory(), y.cpu().pin_memory()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        loss = run(hx, hy)
+    lv = float(loss.detach())               # device -> host read of the step's result
+    e2e_s = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.barrier()
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    t = float(ms.item()) / K
+    val = world * B / (t / 1e3)
+    grad_bytes = grads.flat.numel() * 4
+    out = {"metric": "training images/sec DynamicViT (Variant A, 3 stages @3,6,9) DeiT-S kr=0.7 @224", "value": val, "unit": UNIT,
+           "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": t, "batch_per_gpu": B, "dtype": "bf16 autocast, fp32 master weights",
+           "workload": "student fwd+bwd (Gumbel keep decisions, policy attention at T=197) + frozen DeiT-S teacher fwd + "
+                       "DistillDiffPruningLoss (cls + ratio + cls-KL + token-KL) + AdamW",
+           "cuda_graph": not args.no_graph, "d2s_launches_per_step": int(per_step), "final_loss": lv,
+           "e2e": {"value": world * B * K / float(e2e_s.item()), "unit": UNIT, "h2d_bytes_per_step": hx.numel() * 4 + hy.numel() * 8,
+                   "d2h_bytes_per_step": 4},
+           "collective": (f"one NCCL all-reduce of the flat fp32 gradient buffer ({grad_bytes / 1e6:.1f} MB) per step, captured in the "
+                          f"step's CUDA graph between backward and AdamW" if world > 1 else "none (single GPU)"),
+           "allreduce_floor_ms": (2 * (world - 1) / world * grad_bytes / 725e9 * 1e3) if world > 1 else 0.0,
+           "limiter": "tensor + HBM bound single-GPU step; the all-reduce is not overlapped with backward (it is ~1-2 % of the step)",
+           "tensor_frac_of_sustained_peak": val / world * TRAIN_GFLOP_PER_IMG / 1e3 / pk["tf_sustained"]}
+    del run, student, teacher, opt, grads
+    torch.cuda.empty_cache()
+    return out
+
+
+def gpu_eager_leg(sd, dev, B, torch):
+    """The oracle's restatement of the reference forward (plain torch ops: F.linear / matmul / softmax / sort / gather -- what
+    `reference_model.to(bfloat16).cuda()` executes) run by torch eager on this GPU at the benchmarked batch and dtype."""
+    from oracle import model as om
+    cfg = om.VitCfg(embed_dim=384, depth=12, num_heads=6, pruning_loc=LOCS, token_ratio=RATIOS)
+    sd16 = {k: (v.to(dev, torch.bfloat16) if v.is_floating_point() else v.to(dev)) for k, v in sd.items()}
+    x = torch.randn(B, 3, 224, 224, device=dev).bfloat16()
+    with torch.no_grad():
+        for _ in range(2):
+            om.variant_a_eval(sd16, cfg, x)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        n = 5
+        for _ in range(n):
+            om.variant_a_eval(sd16, cfg, x)
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    return {"value": B / (ms / 1e3), "unit": UNIT, "ms_per_step": ms, "kind": "port",
+            "what": f"oracle.model.variant_a_eval on cuda tensors, torch eager (cuBLAS / ATen kernels), bf16, batch {B}, inputs resident"}
+
+
+def h2d_leg(dev, B, world, torch, dist):
+    host = [torch.zeros(B, 3, 224, 224, dtype=torch.bfloat16).pin_memory() for _ in range(2)]
+    dst = [torch.empty(B, 3, 224, 224, dtype=torch.bfloat16, device=dev) for _ in range(2)]
+    for i in range(2):
+        dst[i].copy_(host[i], non_blocking=True)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n = 8
+    e0.record()
+    for i in range(n):
+        dst[i & 1].copy_(host[i & 1], non_blocking=True)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1) / n], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    nbytes = host[0].numel() * 2
+    return {"bytes_per_step": nbytes, "ms_max_over_ranks": float(ms), "gbs_per_gpu": nbytes / float(ms) / 1e6,
+            "img_s_ceiling": world * B / (float(ms) / 1e3),
+            "what": "pinned bf16 image batch -> device, nothing else running, every rank at once (the e2e leg's copy ceiling)"}
+
+
+# ---------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------
 def run_gpu(args):
     import torch
     import torch.distributed as dist
@@ -288,6 +581,9 @@ def run_gpu(args):
     rank = int(os.environ.get("RANK", 0))
     local = int(os.environ.get("LOCAL_RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
+    legs = set(args.legs.split(","))
+    if args.skip_cpu:
+        legs.discard("cpu")
     if not torch.cuda.is_available():
         raise SystemExit("bench.py (d2s arm) needs a CUDA device: there is no CPU fallback")
     torch.cuda.set_device(local)
@@ -298,23 +594,30 @@ def run_gpu(args):
     pk = peaks()
     B, K, W = args.batch, args.steps, max(args.warmup, 3)
 
-    torch.manual_seed(0)
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
     model = pkg.variant_a.DefaultVisionTransformerDiffPruning(pruning_loc=LOCS, token_ratio=RATIOS, distill=True, **DEIT_S)
+    sd = seeded_weights(model)
     runner = pkg.runner.InferenceRunner(model, B, dev, dtype=torch.bfloat16, use_graph=not args.no_graph, warmup=2)
+    line = {"metric": METRIC, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic"}
+
+    # ---- parity gate: nothing is timed unless the path about to be timed reproduces the oracle ----------------------
+    if "parity" in legs and rank == 0:
+        line["parity_checked"] = parity_gate(pkg, runner.model, sd, dev, torch)
+    barrier()
+
     # kernels per forward: count one eager forward through the C ABI (the graph replays exactly these)
     n0 = pkg._lib.launch_count()
     with torch.no_grad():
         runner.model(runner.static_in)
     torch.cuda.synchronize()
     launches_per_step = pkg._lib.launch_count() - n0
-
     g = torch.Generator(device=dev).manual_seed(42 + rank)
     runner.static_in.copy_(torch.randn(runner.static_in.shape, device=dev, generator=g).to(torch.bfloat16))
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
 
     # ---- value: inputs resident in HBM ------------------------------------------------------------
     for _ in range(W):
@@ -337,28 +640,39 @@ def run_gpu(args):
     logits_ok = bool(torch.isfinite(runner.logits.float()).all())
 
     # ---- e2e: pinned host images -> device -> forward -> host logits, every step -----------------------
-    host = [torch.randn(B, 3, 224, 224, generator=torch.Generator().manual_seed(100 + i)).to(torch.bfloat16).pin_memory()
-            for i in range(2)]
-    h2d = host[0].numel() * host[0].element_size()
-    d2h = runner.logits.numel() * runner.logits.element_size()
-    for i in range(2):
-        runner.step_prefetched(runner.prefetch(host[i & 1]))
-    barrier()
-    t0 = time.perf_counter()
-    slot = runner.prefetch(host[0])
-    out_host = None
-    for i in range(K):
-        # start the next step's copy before this step's compute is enqueued: the copy overlaps the compute
-        nxt = runner.prefetch(host[(i + 1) & 1]) if i + 1 < K else None
-        out_host = runner.step_prefetched(slot)
-        slot = nxt
-    torch.cuda.synchronize()
-    e2e_s = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
-    barrier()
-    if world > 1:
-        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    e2e_val = world * B * K / float(e2e_s.item())
-    e2e_ok = bool(torch.isfinite(out_host.float()).all())
+    e2e = None
+    if "e2e" in legs:
+        host = [torch.randn(B, 3, 224, 224, generator=torch.Generator().manual_seed(100 + i)).to(torch.bfloat16).pin_memory()
+                for i in range(2)]
+        h2d = host[0].numel() * host[0].element_size()
+        d2h = runner.logits.numel() * runner.logits.element_size()
+        for i in range(2):
+            runner.step_prefetched(runner.prefetch(host[i & 1]))
+        barrier()
+        t0 = time.perf_counter()
+        slot = runner.prefetch(host[0])
+        out_host = None
+        for i in range(K):
+            # start the next step's copy before this step's compute is enqueued: the copy overlaps the compute
+            nxt = runner.prefetch(host[(i + 1) & 1]) if i + 1 < K else None
+            out_host = runner.step_prefetched(slot)
+            slot = nxt
+        torch.cuda.synchronize()
+        e2e_s = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+        barrier()
+        if world > 1:
+            dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+        logits_ok = logits_ok and bool(torch.isfinite(out_host.float()).all())
+        e2e = {"value": world * B * K / float(e2e_s.item()), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "note": "pinned bf16 host images, double-buffered H2D on a copy stream overlapping the previous step, "
+                       "host logits read back every step; wall clock between device synchronisations"}
+        del host
+    h2d_only = h2d_leg(dev, B, world, torch, dist) if "h2d" in legs else None
+    del runner
+    torch.cuda.empty_cache()
+
+    # ---- training step (all ranks: the gradient all-reduce is the path's one collective) -----------------------------
+    train = train_leg(pkg, args, dev, rank, world, torch, dist, pk) if "train" in legs else None
 
     if rank != 0:
         if world > 1:
@@ -366,34 +680,41 @@ def run_gpu(args):
             dist.destroy_process_group()
         return
 
-    # ---- rank 0: per-kernel breakdown, roofline, cpu baseline ----------------------------------------
-    time.sleep(2.0)   # kernels are timed alone against the BURST peaks: let the clocks recover from the sustained loop
-    rows, roof = kernel_breakdown(pkg.ops, B, dev, torch, pk)
-    own_ms = sum(r["ms"] * r["launches_per_step"] for r in rows)
-    line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-        "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "bf16", "data": "synthetic",
+    # ---- rank 0: per-kernel breakdown, roofline, kernel-family legs, baselines ----------------------------------------
+    line.update({
+        "value": value, "ms_per_step": total_ms / K,
         "config": {"workload": "DynamicViT DeiT-S/16 keep_rate=0.7 (3 stages @3,6,9; ratios 0.7/0.49/0.343) inference, "
-                               "224px, batch 1024 per GPU, bf16, random-init weights",
+                               "224px, batch 1024 per GPU, bf16, random (seeded) weights",
                    "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world} (batch-sharded, no collective)",
                    "cuda_graph": not args.no_graph,
                    "l2": "inputs larger than L2: 308 MB of images and >1 GB of activations per step vs 126 MB L2",
-                   "outputs_finite": logits_ok and e2e_ok},
-        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "note": "pinned bf16 host images, double-buffered H2D on a copy stream overlapping the previous step, "
-                        "host logits read back every step; wall clock between device synchronisations"},
-        "gpu_launches": int(launches_per_step * K),
-        "d2s_launches_per_step": int(launches_per_step),
-        "clocks": clocks,
-        "roofline": roof,
+                   "outputs_finite": logits_ok},
+        "gpu_launches": int(launches_per_step * K), "d2s_launches_per_step": int(launches_per_step), "clocks": clocks,
         "model_tensor_frac": {"gflop_per_img": GFLOP_PER_IMG, "achieved_tflops": value / world * GFLOP_PER_IMG / 1e3,
                               "peak": pk["tf_sustained"], "frac": value / world * GFLOP_PER_IMG / 1e3 / pk["tf_sustained"],
-                              "peak_source": pk["source"] + " (sustained)"},
-        "d2s_kernel_ms_per_step": own_ms, "d2s_kernel_share_of_step": own_ms / (total_ms / K),
-        "kernels": rows,
-    }
-    if not args.skip_cpu:
+                              "peak_source": pk["source"] + " (sustained)"}})
+    if e2e is not None:
+        line["e2e"] = e2e
+    if h2d_only is not None:
+        line["h2d_only"] = h2d_only
+    if train is not None:
+        line["train"] = train
+    time.sleep(2.0)   # kernels are timed alone against the BURST peaks: let the clocks recover from the sustained loops
+    if "kernels" in legs:
+        rows, roof = kernel_breakdown(pkg.ops, B, dev, torch, pk)
+        own_ms = sum(r["us"] * 1e-3 * r["launches_per_step"] for r in rows)
+        line.update({"roofline": roof, "d2s_kernel_ms_per_step": own_ms, "d2s_kernel_share_of_step": own_ms / (total_ms / K),
+                     "kernels": rows})
+        torch.cuda.empty_cache()
+    if "ptopk" in legs:
+        line["ptopk"] = ptopk_leg(pkg.ops, dev, torch, pk)
+    if "sweep" in legs:
+        line["sweep"] = sweep_leg(pkg.ops, dev, torch, pk)
+        torch.cuda.empty_cache()
+    if "eager" in legs:
+        line["gpu_eager_baseline"] = gpu_eager_leg(sd, dev, B, torch)
+        torch.cuda.empty_cache()
+    if "cpu" in legs:
         c = time_cpu(args.cpu_batch, steps=40, warmup=1, budget_s=15.0)
         line["cpu_baseline"] = {
             "value": c["img_s"], "unit": UNIT, "cores": c["cores"], "kind": "port",
