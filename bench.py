@@ -242,7 +242,19 @@ def parity_gate(pkg, model16, sd, dev, torch):
     m32 = m32.to(dev).eval()
     with torch.no_grad():
         l32 = m32(img.to(dev)).cpu()
-    kept_exact = all(torch.equal(m32.kept_token_indices[s].cpu(), ref["kept"][s]) for s in range(3))
+    # Variant A keeps the tokens in descending-score order and indexes every stage relative to the previous stage's order.  Two
+    # kept tokens whose fp32 scores differ by less than the CPU/GPU rounding difference (~1e-6) may swap places (attention is
+    # permutation equivariant: nothing downstream changes), which shifts the stage-relative indices of the next stage.  What
+    # must be bit-identical is the set of ORIGINAL token ids kept at every stage.
+    def original_ids(kept_list):
+        ids, out = None, []
+        for k in kept_list:
+            ids = k if ids is None else torch.gather(ids, 1, k)
+            out.append(torch.sort(ids, 1).values)
+        return out
+    mine, theirs = original_ids([k.cpu() for k in m32.kept_token_indices]), original_ids(ref["kept"])
+    kept_exact = all(torch.equal(a, b) for a, b in zip(mine, theirs))
+    order_same = all(torch.equal(m32.kept_token_indices[s].cpu(), ref["kept"][s]) for s in range(3))
     rel32 = float((l32 - ref["logits"]).abs().max() / ref["logits"].abs().max())
     del m32
     sdr = {k: (v.bfloat16().float() if v.is_floating_point() else v) for k, v in sd32.items()}
@@ -260,7 +272,7 @@ def parity_gate(pkg, model16, sd, dev, torch):
     flips = (a ^ b).sum(1)
     margin_ok = bool((flips <= 2 * near).all()) and bool((flips[(srt[:, K - 1] - srt[:, K]) > 0.05] == 0).all())
     out = {"images": 8, "oracle": "oracle.model.variant_a_eval (CPU fp32; equals the unmodified reference to 2e-6 at this config)",
-           "fp32_kept_sets_bit_exact": kept_exact, "fp32_logits_max_rel": rel32,
+           "fp32_kept_token_sets_bit_exact": kept_exact, "fp32_kept_order_identical": order_same, "fp32_logits_max_rel": rel32,
            "bf16_stage1_flipped_tokens": int(flips.sum()), "bf16_flips_within_fp32_score_margin": margin_ok,
            "bf16_logits_rel_l2_incl_flips": float((l16 - refr["logits"]).norm() / refr["logits"].norm()),
            "ok": bool(kept_exact and rel32 <= 1e-4 and margin_ok and bool(torch.isfinite(l16).all()))}

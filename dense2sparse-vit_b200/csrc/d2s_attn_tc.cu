@@ -28,6 +28,7 @@ namespace d2s {
 constexpr int tc_threads(int ksw) { return 32 * (ksw + 1); }
 // a logit this many binades (powers of two, after scaling) above the row's exponent reference raises the reference
 constexpr float kMaxBinades = 100.0f;
+constexpr float kBigSum = 1.2676506e30f;   // 2^100: a 16-column partial sum beyond it triggers the check of the chunk maximum
 
 struct TcBars {
   uint64_t q_full[2], k_full[2], v_full, s_full, p_full, o_full, tmem_free;
@@ -271,28 +272,41 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             }
             float a[16];
             const bool full = ch * 16 + 16 <= T;
-            // chunk maximum over the valid key columns (zero-filled columns past T must not raise the reference)
-            float cm = __uint_as_float(v[0]);
+            // exponentials against the current reference; the chunk's own partial sums double as the overflow detector (a sum
+            // beyond 2^kMaxBinades, inf or NaN), so the common path carries no dependence on a row maximum
+            auto exps = [&]() {
 #pragma unroll
-            for (int q = 1; q < 16; ++q)
-              if (full || ch * 16 + q < T) cm = fmaxf(cm, __uint_as_float(v[q]));
-            if (kPol) mx_true = fmaxf(mx_true, cm);
-            const float over = fmaf(cm, k2, -mxk);
-            if (__any_sync(0xffffffffu, over > kMaxBinades)) {       // rare: raise the reference, rescale what exists
+              for (int q = 0; q < 16; ++q) {
+                const int j = ch * 16 + q;
+                float e = ex2_approx(fmaf(__uint_as_float(v[q]), k2, -mxk));
+                if (kPol) e *= (j == i) ? 1.0f : pol_s[j];
+                if (!full && j >= T) e = 0.f;
+                a[q] = e;
+              }
+            };
+            exps();
+            float c0 = (a[0] + a[4]) + (a[8] + a[12]), c1 = (a[1] + a[5]) + (a[9] + a[13]);
+            float c2 = (a[2] + a[6]) + (a[10] + a[14]), c3 = (a[3] + a[7]) + (a[11] + a[15]);
+            if (kPol) {
+              // the true row maximum (masked keys included: the reference's eps terms follow it); off the critical path
+#pragma unroll
+              for (int q = 0; q < 16; ++q)
+                if (full || ch * 16 + q < T) mx_true = fmaxf(mx_true, __uint_as_float(v[q]));
+            }
+            if (__any_sync(0xffffffffu, !((c0 + c1) + (c2 + c3) <= kBigSum))) {   // rare: raise the reference, rescale what exists
+              float cm = __uint_as_float(v[0]);     // chunk maximum over the valid key columns (zero-filled columns past T excluded)
+#pragma unroll
+              for (int q = 1; q < 16; ++q)
+                if (full || ch * 16 + q < T) cm = fmaxf(cm, __uint_as_float(v[q]));
+              const float over = fmaf(cm, k2, -mxk);
               const float d = over > kMaxBinades ? floorf(over) : 0.f;
               rescale_row(ch, exp2_neg_int(d), s0, s1, s2, s3);
               mxk += d;
+              exps();
+              c0 = (a[0] + a[4]) + (a[8] + a[12]); c1 = (a[1] + a[5]) + (a[9] + a[13]);
+              c2 = (a[2] + a[6]) + (a[10] + a[14]); c3 = (a[3] + a[7]) + (a[11] + a[15]);
             }
-#pragma unroll
-            for (int q = 0; q < 16; ++q) {
-              const int j = ch * 16 + q;
-              float e = ex2_approx(fmaf(__uint_as_float(v[q]), k2, -mxk));
-              if (kPol) e *= (j == i) ? 1.0f : pol_s[j];
-              if (!full && j >= T) e = 0.f;
-              a[q] = e;
-            }
-#pragma unroll
-            for (int q = 0; q < 16; q += 4) { s0 += a[q]; s1 += a[q + 1]; s2 += a[q + 2]; s3 += a[q + 3]; }
+            s0 += c0; s1 += c1; s2 += c2; s3 += c3;
             if (want_cls) {
 #pragma unroll
               for (int q = 0; q < 16; ++q) cls_s[ch * 16 + q] = a[q];
@@ -303,6 +317,16 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             // P overlays S columns this warp has already consumed
             tmem_st8(lane_addr + pcol(ch), packed);
           }
+          if (kPol) {
+            // a MASKED key far above every kept one never shows in the sums: the reference still subtracts it (its row then
+            // degenerates to the eps terms), so the reference is raised for it as well
+            const float over = fmaf(mx_true, k2, -mxk);
+            if (__any_sync(0xffffffffu, over > kMaxBinades)) {
+              const float d = over > kMaxBinades ? floorf(over) : 0.f;
+              rescale_row(ch_hi, exp2_neg_int(d), s0, s1, s2, s3);
+              mxk += d;
+            }
+          }
         }  // rows of an idle warp are never written out; whatever their P rows hold stays in those rows
         if constexpr (kSW == 8) {
           // The two column halves of a row exchange their partial sums, running maxima and exponent references through shared
@@ -310,7 +334,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
           sum_s[half * kTileRows + r] = (s0 + s1) + (s2 + s3);
           max_s[half * kTileRows + r] = mx_true;
           ref_s[half * kTileRows + r] = mxk;
-          asm volatile("bar.sync 2, 256;" ::: "memory");
+          asm volatile("bar.sync %0, 64;" ::"r"(3 + quad) : "memory");        // the two warps of this row quadrant
           const float o_ref = ref_s[(half ^ 1) * kTileRows + r];
           float o_sum = sum_s[(half ^ 1) * kTileRows + r];
           if (__any_sync(0xffffffffu, warp_active && o_ref != mxk)) {   // rare: one half raised its reference
@@ -319,7 +343,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             rescale_row(ch_hi, exp2_neg_int(d), s0, s1, s2, s3);
             mxk += d;
             // (the branch is taken by both warps of a row pair or by neither: the partner's CLS-row share is final after this)
-            asm volatile("bar.sync %0, 64;" ::"r"(3 + quad) : "memory");
+            asm volatile("bar.sync %0, 64;" ::"r"(7 + quad) : "memory");
           }
           sum = (s0 + s1) + (s2 + s3) + o_sum;
           if (kPol) mx_true = fmaxf(mx_true, max_s[(half ^ 1) * kTileRows + r]);
