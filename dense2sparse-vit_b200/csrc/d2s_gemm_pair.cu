@@ -78,6 +78,7 @@ struct GpParams {
   const __nv_bfloat16* x;       // MODE_LN: residual input (M,N)
   __nv_bfloat16* out_sum;       // MODE_LN: x' (M,N)
   __nv_bfloat16* out_norm;      // MODE_LN: LayerNorm(x') (M,N) or NULL
+  __nv_bfloat16* pre;           // MODE_ACT: the pre-activation A @ W^T + bias (M,N) as a second output, or NULL
   float eps;
   int M, N, K, act, want_ln;
   long long* trace;             // D2S_GEMM_TRACE: device buffer for per-warp clock64 phase totals (profiling only)
@@ -229,11 +230,22 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             tmem_ld_wait();
             GP_TRACE(2)
             uint32_t o[16];
+            // training: the Linear's own output is a second result (GELU' needs it); one 64-byte row segment per thread,
+            // straight from registers (no room for a second staging block next to a 4-stage operand ring)
+            const bool want_pre = p.pre != nullptr;
+            const bool row_ok = row0 + r < p.M;
+            uint4* pre_row = reinterpret_cast<uint4*>(p.pre + (size_t)(row_ok ? row0 + r : 0) * p.N + col0 + c * 32);
+            uint32_t pw[4];
 #pragma unroll
             for (int q = 0; q < 16; ++q) {
               const float2 bq = *reinterpret_cast<const float2*>(&bias_s[col0 + c * 32 + 2 * q]);
               uint64_t xp = f2_add(f2_pack(__uint_as_float(v[2 * q]), __uint_as_float(v[2 * q + 1])), f2_pack(bq.x, bq.y));
               float x0, x1;
+              if (want_pre) {
+                f2_unpack(xp, x0, x1);
+                pw[q & 3] = pack_bf16x2(x0, x1);
+                if ((q & 3) == 3 && row_ok) pre_row[q >> 2] = make_uint4(pw[0], pw[1], pw[2], pw[3]);
+              }
               if (ACT == D2S_ACT_GELU) xp = gelu_erf_pair(xp);
               f2_unpack(xp, x0, x1);
               if (ACT == D2S_ACT_RELU) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
@@ -462,20 +474,22 @@ static int gp_launch(const CUtensorMap& ma, const CUtensorMap& mw, const CUtenso
 using namespace d2s;
 
 extern "C" int d2s_linear_act_pair_bf16(const void* a, const void* w, const void* bias, int M, int N, int K, int act, void* out,
-                                        d2s_stream_t stream) {
+                                        void* pre, d2s_stream_t stream) {
   const char* what = "d2s_linear_act_pair_bf16";
   D2S_REQUIRE(a && w && out, D2S_ERR_ARG, "linear_act_pair: null pointer");
   D2S_REQUIRE(M >= 0 && N >= 256 && N % 256 == 0 && N <= 4096 && K >= kGpBK && K % kGpBK == 0, D2S_ERR_ARG,
               "linear_act_pair: need N %% 256 == 0 (N <= 4096) and K %% %d == 0 (got M=%d N=%d K=%d)", kGpBK, M, N, K);
   D2S_REQUIRE(act >= D2S_ACT_NONE && act <= D2S_ACT_RELU, D2S_ERR_ARG, "linear_act_pair: bad activation %d", act);
-  D2S_REQUIRE(aligned16(a) && aligned16(w) && aligned16(out), D2S_ERR_ALIGN, "linear_act_pair: pointers must be 16-byte aligned");
+  D2S_REQUIRE(aligned16(a) && aligned16(w) && aligned16(out) && aligned16(pre), D2S_ERR_ALIGN,
+              "linear_act_pair: pointers must be 16-byte aligned");
   if (M == 0) return D2S_OK;
   CUtensorMap ma, mw, mo;
   int rc;
   if ((rc = gp_map_2d(&ma, a, K, M, kGpBK, kGpBM, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, what))) return rc;
   if ((rc = gp_map_2d(&mw, w, K, N, kGpBK, 128, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, what))) return rc;
   if ((rc = gp_map_2d(&mo, out, N, M, 64, kGpBM, CU_TENSOR_MAP_L2_PROMOTION_NONE, what))) return rc;
-  GpParams p{(const __nv_bfloat16*)bias, nullptr, nullptr, nullptr, nullptr, nullptr, 0.f, M, N, K, act, 0, gp_trace(), gp_debug()};
+  GpParams p{(const __nv_bfloat16*)bias, nullptr, nullptr, nullptr, nullptr, nullptr, (__nv_bfloat16*)pre, 0.f, M, N, K, act, 0,
+             gp_trace(), gp_debug()};
   if (act == D2S_ACT_GELU) return gp_launch<kGpModeAct, 1, D2S_ACT_GELU>(ma, mw, mo, p, (cudaStream_t)stream, what);
   if (act == D2S_ACT_RELU) return gp_launch<kGpModeAct, 1, D2S_ACT_RELU>(ma, mw, mo, p, (cudaStream_t)stream, what);
   return gp_launch<kGpModeAct, 1, D2S_ACT_NONE>(ma, mw, mo, p, (cudaStream_t)stream, what);
@@ -498,7 +512,7 @@ extern "C" int d2s_linear_residual_ln_bf16(const void* a, const void* w, const v
   if ((rc = gp_map_2d(&ma, a, K, M, kGpBK, kGpBM, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, what))) return rc;
   if ((rc = gp_map_2d(&mw, w, K, N, kGpBK, 96, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, what))) return rc;
   GpParams p{(const __nv_bfloat16*)bias, (const __nv_bfloat16*)gamma, (const __nv_bfloat16*)beta, (const __nv_bfloat16*)x,
-             (__nv_bfloat16*)out_sum, (__nv_bfloat16*)out_norm, eps, M, N, K, 0, out_norm ? 1 : 0, gp_trace(), gp_debug()};
+             (__nv_bfloat16*)out_sum, (__nv_bfloat16*)out_norm, nullptr, eps, M, N, K, 0, out_norm ? 1 : 0, gp_trace(), gp_debug()};
   if (N == 384) return gp_launch<kGpModeLn, 2, 0>(ma, mw, ma, p, (cudaStream_t)stream, what);
   return gp_launch<kGpModeLn, 1, 0>(ma, mw, ma, p, (cudaStream_t)stream, what);
 }

@@ -369,23 +369,37 @@ class _Stream:
 
 
 def _seq_forward(layers, h):
-    """A predictor nn.Sequential on the training path: its LayerNorms run on the d2s forward/backward kernels."""
-    for layer in layers:
-        h = norm_forward(layer, h) if isinstance(layer, torch.nn.LayerNorm) else layer(h)
+    """A predictor nn.Sequential on the training path: LayerNorms on the d2s forward/backward kernels, Linear layers through
+    ops.linear_train (bias gradient by the column-sum kernel, fp32 weight gradient straight from the GEMM) and Linear -> GELU
+    pairs as one autograd node (ops.linear_gelu_train).  Each falls back to the module itself when it does not apply."""
+    layers = list(layers)
+    i = 0
+    while i < len(layers):
+        layer = layers[i]
+        if isinstance(layer, torch.nn.LayerNorm):
+            h = norm_forward(layer, h)
+        elif isinstance(layer, torch.nn.Linear) and h.is_cuda:
+            nxt = layers[i + 1] if i + 1 < len(layers) else None
+            if isinstance(nxt, torch.nn.GELU):
+                h = ops.linear_gelu_train(layer, nxt, h)
+                i += 1
+            else:
+                h = ops.linear_train(layer, h)
+        else:
+            h = layer(h)
+        i += 1
     return h
 
 
 # ---- Variant A predictor (default_dynamic_vit.py:304-330) ------------------------------------------
 def predictor_a_hidden(m, x, policy, normed=None):
     """`normed`: in_conv's LayerNorm already applied (by the fused add+LayerNorm kernel)."""
-    h = _seq_forward(m.in_conv, x) if normed is None else m.in_conv[2](m.in_conv[1](normed))
+    h = _seq_forward(m.in_conv, x) if normed is None else _seq_forward(list(m.in_conv)[1:], normed)
     B, N, C = h.shape
     half = C // 2
     pooled = (h[:, :, half:] * policy).sum(dim=1, keepdim=True) / torch.sum(policy, dim=1, keepdim=True)
     h = torch.cat([h[:, :, :half], pooled.expand(B, N, half)], dim=-1)
-    for layer in list(m.out_conv)[:4]:      # Linear, GELU, Linear, GELU
-        h = layer(h)
-    return h
+    return _seq_forward(list(m.out_conv)[:4], h)      # Linear, GELU, Linear, GELU
 
 
 def _tail_ok(h):

@@ -319,6 +319,7 @@ def softmax_with_policy(attn, policy, eps=1e-6):
 
 _FUSED_WGRAD = os.environ.get("D2S_FUSED_WGRAD", "1") != "0"   # A/B switch for ops.linear_train (d2s bias gradient)
 _FUSED_GELU_BWD = os.environ.get("D2S_FUSED_GELU_BWD", "1") != "0"   # A/B switch: fc1 -> GELU as one autograd node
+_FUSED_GELU_FWD = os.environ.get("D2S_FUSED_GELU_FWD", "1") != "0"   # A/B switch: its forward as one tcgen05 GEMM (GELU + pre-activation out)
 
 
 def colsum(dy):
@@ -332,6 +333,26 @@ def colsum(dy):
     out = torch.empty(dy.shape[1], dtype=torch.float32, device=dy.device)
     _call("d2s_colsum_bf16", _ptr(dy), dy.shape[0], dy.shape[1], _ptr(out), _stream(dy))
     return out
+
+
+def _wgrad(dy, x, dtype):
+    """dW = dy^T x for bf16 (M,N) x (M,K) operands in the parameter's dtype: with fp32 master weights the library GEMM writes
+    its fp32 accumulator out directly (no bf16 rounding of the weight gradient, no separate cast pass)."""
+    if dtype == torch.float32 and _MM_OUT_DTYPE:
+        return torch.mm(dy.t(), x, out_dtype=torch.float32)
+    return (dy.t() @ x).to(dtype)
+
+
+def _probe_mm_out_dtype():
+    try:
+        torch.mm(torch.zeros(8, 8, dtype=torch.bfloat16, device="meta"), torch.zeros(8, 8, dtype=torch.bfloat16, device="meta"),
+                 out_dtype=torch.float32)
+        return True
+    except (TypeError, RuntimeError, NotImplementedError):
+        return False
+
+
+_MM_OUT_DTYPE = _probe_mm_out_dtype()
 
 
 class _LinearTrain(torch.autograd.Function):
@@ -360,10 +381,10 @@ class _LinearTrain(torch.autograd.Function):
         gw = gb = None
         want_b = bd is not None and ctx.needs_input_grad[2]
         if ctx.needs_input_grad[1]:
-            gw = gy2.t() @ xb.reshape(-1, K)
+            gw = _wgrad(gy2, xb.reshape(-1, K), wd)
         if want_b:
             gb = colsum(gy2)
-        return gx, None if gw is None else gw.to(wd), None if gb is None else gb.to(bd)
+        return gx, gw, None if gb is None else gb.to(bd)
 
 
 def gelu_bwd_colsum(u, ga, want_bias=True):
@@ -389,10 +410,16 @@ class _LinearGeluTrain(torch.autograd.Function):
     def forward(ctx, x, w, b):
         xb, wb = x.to(torch.bfloat16), w.to(torch.bfloat16)
         bb = None if b is None else b.to(torch.bfloat16)
-        u = F.linear(xb, wb, bb)
+        if _FUSED_GELU_FWD and wb.shape[0] % 256 == 0 and wb.shape[0] <= 4096 and wb.shape[1] % 64 == 0:
+            # one tcgen05 GEMM writes both the Linear's output (kept for GELU') and its GELU: torch's separate GELU pass
+            # (read + write of the (M, 4D) hidden tensor) disappears
+            a, u = linear_act(xb, wb, bb, ACT_GELU, want_pre=True)
+        else:
+            u = F.linear(xb, wb, bb)
+            a = F.gelu(u)
         ctx.save_for_backward(xb, wb, u)
         ctx.meta = (x.dtype, w.dtype, None if b is None else b.dtype)
-        return F.gelu(u)
+        return a
 
     @staticmethod
     def backward(ctx, ga):
@@ -405,7 +432,7 @@ class _LinearGeluTrain(torch.autograd.Function):
         want_b = bd is not None and ctx.needs_input_grad[2]
         du, gb = gelu_bwd_colsum(u.reshape(-1, N), ga2, want_bias=want_b)
         gx = (du @ wb).view(xb.shape).to(xd) if ctx.needs_input_grad[0] else None
-        gw = (du.t() @ xb.reshape(-1, K)).to(wd) if ctx.needs_input_grad[1] else None
+        gw = _wgrad(du, xb.reshape(-1, K), wd) if ctx.needs_input_grad[1] else None
         return gx, gw, None if gb is None else gb.to(bd)
 
 
@@ -778,9 +805,10 @@ def layer_norm(x, weight, bias, eps, out_dtype=None):
     return _LayerNorm.apply(x, weight, bias, eps, out_dtype)
 
 
-def linear_act(x, weight, bias, act=ACT_GELU):
-    """act(x @ weight^T + bias) in one CTA-pair tcgen05 GEMM with the activation in the epilogue (bf16, inference only).
-    x (..., K) contiguous, weight (N, K), N % 256 == 0, K % 64 == 0."""
+def linear_act(x, weight, bias, act=ACT_GELU, want_pre=False):
+    """act(x @ weight^T + bias) in one CTA-pair tcgen05 GEMM with the activation in the epilogue (bf16, no autograd).
+    x (..., K) contiguous, weight (N, K), N % 256 == 0, K % 64 == 0.  want_pre: returns (act(u), u) with u the Linear's own
+    output as a second result of the same kernel."""
     _check_cuda(x, weight, bias)
     if x.dtype != torch.bfloat16:
         raise TypeError("linear_act is a bf16 kernel")
@@ -791,8 +819,9 @@ def linear_act(x, weight, bias, act=ACT_GELU):
     M = xc.numel() // K
     N = w.shape[0]
     out = torch.empty(*xc.shape[:-1], N, dtype=torch.bfloat16, device=xc.device)
-    _call("d2s_linear_act_pair_bf16", _ptr(xc), _ptr(w), _ptr(b), M, N, K, int(act), _ptr(out), _stream(xc))
-    return out
+    pre = torch.empty_like(out) if want_pre else None
+    _call("d2s_linear_act_pair_bf16", _ptr(xc), _ptr(w), _ptr(b), M, N, K, int(act), _ptr(out), _ptr(pre), _stream(xc))
+    return (out, pre) if want_pre else out
 
 
 def linear_residual_ln(a, weight, bias, x, ln_weight=None, ln_bias=None, eps=1e-5, want_norm=True):

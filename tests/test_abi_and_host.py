@@ -60,8 +60,8 @@ def test_argument_errors_precede_any_launch(d2s):
     assert lib.d2s_linear_residual_ln_bf16(p, p, p, p, p, p, 1e-6, 256, 768, 384, p, p, None) == 1 and b"N in {192, 384}" in lib.d2s_last_error()
     assert lib.d2s_linear_residual_ln_bf16(p, p, p, p, None, None, 1e-6, 256, 384, 384, p, p, None) == 1 and b"gamma" in lib.d2s_last_error()
     assert lib.d2s_linear_residual_ln_bf16(p, p, p, p, p, p, 1e-6, 256, 384, 100, p, p, None) == 1 and b"K %" in lib.d2s_last_error()
-    assert lib.d2s_linear_act_pair_bf16(p, p, p, 256, 300, 384, 1, p, None) == 1 and b"N % 256" in lib.d2s_last_error()
-    assert lib.d2s_linear_act_pair_bf16(p + 8, p, p, 256, 256, 384, 1, p, None) == 2
+    assert lib.d2s_linear_act_pair_bf16(p, p, p, 256, 300, 384, 1, p, None, None) == 1 and b"N % 256" in lib.d2s_last_error()
+    assert lib.d2s_linear_act_pair_bf16(p + 8, p, p, 256, 256, 384, 1, p, None, None) == 2
     assert lib.d2s_mlp_residual_ln_bf16(p, p, p, p, p, p, p, p, 1e-6, 256, 768, 3072, 1, 0, p, p, None) == 1 and b"D == 384" in lib.d2s_last_error()
     assert lib.d2s_mlp_residual_ln_bf16(p, p, p, p, p, p, p, p, 1e-6, 256, 384, 1000, 1, 0, p, p, None) == 1 and b"HID" in lib.d2s_last_error()
     assert lib.d2s_mlp_residual_ln_bf16(None, p, p, p, p, p, p, p, 1e-6, 256, 384, 1536, 1, 0, p, p, None) == 1 and b"null" in lib.d2s_last_error()
