@@ -870,7 +870,7 @@ def test_linear_gelu_train_matches_modules_under_autocast(ops):
     # the fused forward applies GELU to the fp32 accumulator (torch: to the bf16-rounded Linear output): within one bf16 ulp
     assert y1.dtype == torch.bfloat16
     torch.testing.assert_close(y1.float(), y2.float(), rtol=2 ** -7, atol=2e-3)
-    assert float((y1 != y2).float().mean()) < 0.2
+    assert float((y1 != y2).float().mean()) < 0.35     # single vs double rounding: a quarter of the results move by one ulp
     (y1.float() * up).sum().backward()
     (y2.float() * up).sum().backward()
     for a, b in ((x1.grad, x2.grad), (lin.weight.grad, lin2.weight.grad), (lin.bias.grad, lin2.bias.grad)):
