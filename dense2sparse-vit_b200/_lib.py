@@ -24,6 +24,7 @@ _u64 = ctypes.c_uint64
 # name -> argtypes; every entry point returns int (0 == ok).  Keep in sync with include/d2s.h.
 SIGNATURES = {
     "d2s_select_topk_f32": [_p, _i, _i, _i, _i, _p, _p, _p],
+    "d2s_threshold_select_f32": [_p, _i, _i, _f, _p, _p, _p, _p],
     "d2s_score_tail_a": [_p, _i, _i, _i, _i, _p, _p, _i, _p, _p, _p, _p, _p, _p, _i, _p, _p],
     "d2s_score_tail_b": [_p, _i, _i, _i, _i, _p, _p, _f, _p, _p, _i, _i, _p, _p, _p, _p, _p],
     "d2s_gumbel_decision_f32": [_p, _p, _p, _i64, _p, _p, _p],

@@ -123,6 +123,87 @@ select_topk_kernel(const float* __restrict__ score, int N, int K, int order,
                      dropped ? dropped + (size_t)b * (N - K) : nullptr);
 }
 
+// ---- dynamic keep-ratio ("threshold") selection: the prefix-sum form of kernel (1) -------------------------------------------
+// Reference: vit_models/dynamic_vit.py:880-890 (training) / :935-945 (inference): ascending sort of the keep probabilities,
+// cumulative sum, keep the tokens whose cumulative mass exceeds the threshold, scatter the flags back to token order.
+// One CTA per image: ascending stable rank by counting (same keys as the top-K select), the sorted values land in shared
+// memory, ONE thread runs the prefix sum in index order with a double accumulator rounded to float per prefix -- exactly
+// torch's CPU cumsum (acc_type<float> = double), the oracle's arithmetic -- and every token reads the prefix at its own rank.
+// Outputs: mask (B,N) uint8 0/1 (a torch.bool tensor's storage), count (B) int32 = kept tokens per image, kept (B,N) int64 =
+// the kept token indices in ascending order followed by -1 padding (the index list a varlen gather consumes); NULL to skip.
+__global__ void __launch_bounds__(kSelThreads)
+threshold_select_kernel(const float* __restrict__ score, int N, float threshold, uint8_t* __restrict__ mask,
+                        int* __restrict__ count, int64_t* __restrict__ kept) {
+  __shared__ SelSmem s;
+  __shared__ float sorted_s[kSelMaxN];
+  __shared__ int total_s;
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float myv[kSelEPT];
+  uint32_t mykey[kSelEPT];
+#pragma unroll
+  for (int e = 0; e < kSelEPT; ++e) {
+    const int i = e * kSelThreads + tid;
+    myv[e] = (i < N) ? score[(size_t)b * N + i] : 0.f;
+    mykey[e] = float_to_ordered(myv[e]);
+    if (i < N) s.key[i] = mykey[e];
+  }
+  __syncthreads();
+  int rank[kSelEPT];
+#pragma unroll
+  for (int e = 0; e < kSelEPT; ++e) rank[e] = 0;
+  const int nchunks = (N + kSelThreads - 1) / kSelThreads;
+  for (int j = 0; j < N; ++j) {
+    const uint32_t kj = s.key[j];  // broadcast read
+#pragma unroll
+    for (int e = 0; e < kSelEPT; ++e)
+      if (e < nchunks) rank[e] += (kj < mykey[e]) || (kj == mykey[e] && j < e * kSelThreads + tid);
+  }
+#pragma unroll
+  for (int e = 0; e < kSelEPT; ++e)
+    if (e * kSelThreads + tid < N) sorted_s[rank[e]] = myv[e];
+  __syncthreads();
+  if (tid == 0) {
+    double acc = 0.0;
+    for (int r = 0; r < N; ++r) {
+      acc += (double)sorted_s[r];
+      sorted_s[r] = (float)acc;
+    }
+  }
+  __syncthreads();
+  unsigned ball[kSelEPT];
+#pragma unroll
+  for (int e = 0; e < kSelEPT; ++e) {
+    const int i = e * kSelThreads + tid;
+    const bool keep = (i < N) && (sorted_s[rank[e]] > threshold);
+    if (i < N && mask) mask[(size_t)b * N + i] = keep ? 1 : 0;
+    ball[e] = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0) s.warp_cnt[e][warp] = __popc(ball[e]);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int t = 0;
+    for (int e = 0; e < nchunks; ++e)
+      for (int w = 0; w < kSelWarps; ++w) t += s.warp_cnt[e][w];
+    total_s = t;
+    if (count) count[b] = t;
+  }
+  if (kept == nullptr) return;
+  __syncthreads();
+#pragma unroll
+  for (int e = 0; e < kSelEPT; ++e) {
+    const int i = e * kSelThreads + tid;
+    if (i >= N) continue;
+    int before = 0;
+    for (int ee = 0; ee <= e; ++ee) {
+      const int wend = (ee == e) ? warp : kSelWarps;
+      for (int w = 0; w < wend; ++w) before += s.warp_cnt[ee][w];
+    }
+    before += __popc(ball[e] & ((1u << lane) - 1u));
+    if ((ball[e] >> lane) & 1u) kept[(size_t)b * N + before] = i;
+    else kept[(size_t)b * N + total_s + (i - before)] = -1;      // padding behind the kept list
+  }
+}
+
 // ---- per-token dot products of the tails ---------------------------------------------------------
 // One thread per token walks its C-element row with 16-byte loads (the row is contiguous; the warp's
 // lines are all used and stay in L1 between consecutive loads).  Weights are broadcast from smem.
@@ -421,6 +502,16 @@ extern "C" int d2s_select_topk_f32(const float* score, int B, int N, int K, int 
   select_topk_kernel<<<B, kSelThreads, 0, (cudaStream_t)stream>>>(score, N, K, order, kept, dropped);
   count_launch();
   return check_launch("d2s_select_topk_f32");
+}
+
+extern "C" int d2s_threshold_select_f32(const float* score, int B, int N, float threshold, uint8_t* mask, int* count,
+                                       int64_t* kept, d2s_stream_t stream) {
+  D2S_REQUIRE(score && (mask || kept || count), D2S_ERR_ARG, "threshold_select: null pointer");
+  D2S_REQUIRE(B >= 0 && N >= 1 && N <= kSelMaxN, D2S_ERR_ARG, "threshold_select: N=%d outside [1,%d]", N, kSelMaxN);
+  if (B == 0) return D2S_OK;
+  threshold_select_kernel<<<B, kSelThreads, 0, (cudaStream_t)stream>>>(score, N, threshold, mask, count, kept);
+  count_launch();
+  return check_launch("d2s_threshold_select_f32");
 }
 
 static int check_tail(const void* hidden, int dtype, int B, int N, int C, int K) {

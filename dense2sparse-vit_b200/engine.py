@@ -26,6 +26,7 @@ _FROZEN_BF16 = os.environ.get("D2S_FROZEN_BF16", "1") != "0"   # A/B switch: cac
 _FUSED_ADD_LN_TRAIN = os.environ.get("D2S_FUSED_ADD_LN_TRAIN", "1") != "0"   # A/B switch: residual adds folded into LayerNorm fwd/bwd
 _FUSED_MLP = os.environ.get("D2S_FUSED_MLP", "1") != "0"      # A/B switch for the one-kernel MLP (ops.mlp_residual_ln)
 _FUSED_PAIR = os.environ.get("D2S_FUSED_PAIR", "1") != "0"  # A/B switch for the CTA-pair GEMMs (fc1 pair; proj/fc2 + add + LN)
+_THRESHOLD_INFERENCE = os.environ.get("D2S_THRESHOLD_INFERENCE", "0") == "1"   # opt-in: what dynamic_vit.py:935-949 intends
 INIT_N = 14 * 14  # the reference hard-codes 196 spatial tokens (dynamic_vit.py:828, default_dynamic_vit.py:446)
 
 
@@ -673,24 +674,51 @@ def variant_b_forward(model, img, stacked_cls_attn_weights=None):
                 cls_attn = st.block(blk, return_cls_attn=True)
                 model.cls_attns.append(cls_attn[:, :, 1:])
             elif model.training:
-                # dynamic keep ratio: cumulative-score threshold -> 0/1 policy (dynamic_vit.py:880-894)
+                # dynamic keep ratio: cumulative-score threshold -> 0/1 policy (dynamic_vit.py:880-894); sort + cumsum +
+                # compare + scatter are one d2s kernel (ops.threshold_select)
                 x = st.value()
                 pred_logits, pred_score = predictor_b_forward(pred, x[:, 1:])
-                val, idx = torch.sort(pred_score.detach().clone())
-                th = torch.cumsum(val, dim=-1) > thr
-                model.keep_ratios = torch.sum(th, dim=1).detach().clone() / N
+                if pred_score.is_cuda:
+                    spatial_mask, kept_count = ops.threshold_select(pred_score.detach(), thr)
+                    model.keep_ratios = kept_count.to(torch.float32) / N
+                else:
+                    val, idx = torch.sort(pred_score.detach().clone(), stable=True)
+                    th = torch.cumsum(val, dim=-1) > thr
+                    model.keep_ratios = torch.sum(th, dim=1).detach().clone() / N
+                    spatial_mask = torch.zeros((B, N), device=dev, dtype=torch.bool).scatter(1, idx, th)
                 model.min_keep_ratio = torch.min(model.keep_ratios).item()
                 model.avg_keep_ratio = torch.mean(model.keep_ratios).item()
                 model.max_keep_ratio = torch.max(model.keep_ratios).item()
-                spatial_mask = torch.zeros((B, N), device=dev, dtype=torch.bool).scatter(1, idx, th)
                 model.kept_token_indices.append(spatial_mask.unsqueeze(-1).repeat(1, 1, D).flatten())
                 model.dropped_token_indices.append(~spatial_mask.unsqueeze(-1).repeat(1, 1, D).flatten())
                 keep_mask = torch.cat((torch.ones(B, 1, dtype=dt, device=dev), spatial_mask), dim=1).float()
                 st.block(blk, policy=keep_mask.unsqueeze(-1))
+            elif _THRESHOLD_INFERENCE or getattr(model, "d2s_threshold_inference", False):
+                # OPT-IN.  The reference's inference branch of this mode cannot run (dynamic_vit.py:936 reads `score`, which
+                # is only assigned in a comment at :933, and :947 indexes with a float mask).  What it evidently intends -- the
+                # same cumulative-score threshold on pred_score, then a variable-length removal of the dropped tokens, batch
+                # size 1 by design (mask_predictor.py:249-254) -- runs here as: prefix-sum select kernel -> kept index list,
+                # one host read of the kept count (the output shape depends on it, as in the reference's boolean indexing),
+                # gather of CLS + kept tokens fused with the block's norm1.
+                x = st.value()
+                pred_logits, pred_score = predictor_b_forward(pred, x[:, 1:])
+                spatial_mask, kept_count, kept_pad = ops.threshold_select(pred_score.detach(), thr, want_indices=True)
+                counts = kept_count.tolist()
+                if len(set(counts)) != 1:
+                    raise RuntimeError(f"patch_score_threshold inference: images keep different token counts {counts}; like the "
+                                       "reference's x.flatten()[mask].reshape(B, -1, D) this mode is for batch size 1")
+                model.keep_ratios = kept_count.to(torch.float32) / N
+                model.min_keep_ratio = model.avg_keep_ratio = model.max_keep_ratio = counts[0] / N
+                kept = kept_pad[:, :counts[0]].contiguous()
+                model.kept_token_indices.append(kept)
+                model.pred_logits.append(pred_logits)
+                st.gather(x, kept)
+                st.block(blk)
             else:
                 # the reference's inference branch of this mode reads an undefined name (dynamic_vit.py:936)
                 raise NotImplementedError("patch_score_threshold inference is undefined in the reference "
-                                          "(vit_models/dynamic_vit.py:936 uses `score` before assignment)")
+                                          "(vit_models/dynamic_vit.py:936 uses `score` before assignment); "
+                                          "set model.d2s_threshold_inference = True (or D2S_THRESHOLD_INFERENCE=1) for the intended behaviour")
             p_count += 1
         else:
             if model.training and thr is not None:

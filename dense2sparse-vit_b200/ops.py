@@ -85,6 +85,20 @@ def select_topk(score: torch.Tensor, k: int, order: int = ORDER_INDEX_ASC, want_
     return kept, dropped
 
 
+def threshold_select(score, threshold, want_indices=False):
+    """Dynamic keep-ratio selection (vit_models/dynamic_vit.py:880-890, :935-945): tokens whose cumulative ascending-sorted
+    score mass exceeds `threshold` are kept.  score (B,N) -> (mask (B,N) bool, count (B) int32[, kept (B,N) int64: the kept
+    indices in ascending order, then -1 padding])."""
+    _check_cuda(score)
+    s = _f32c(score)
+    B, N = s.shape
+    mask = torch.empty(B, N, dtype=torch.bool, device=s.device)
+    count = torch.empty(B, dtype=torch.int32, device=s.device)
+    kept = torch.empty(B, N, dtype=torch.int64, device=s.device) if want_indices else None
+    _call("d2s_threshold_select_f32", _ptr(s), B, N, float(threshold), _ptr(mask), _ptr(count), _ptr(kept), _stream(s))
+    return (mask, count, kept) if want_indices else (mask, count)
+
+
 def score_tail_a(hidden, weight, bias, k=0, gumbel=None, prev=None, act_input=ACT_NONE, want_prev_kept=False):
     """Variant A predictor tail (Linear(C,2)+LogSoftmax) fused with selection or the Gumbel decision.
     eval  (gumbel None): returns (logp (B,N,2), kept (B,k) int64 in descending-score order[, prev_kept (B,k) f32])

@@ -53,6 +53,15 @@ uint64_t d2s_launch_count(void);
 int d2s_select_topk_f32(const float* score, int B, int N, int K, int order,
                         int64_t* kept, int64_t* dropped, d2s_stream_t stream);
 
+/* Dynamic keep-ratio selection (the prefix-sum form of the select): replaces sort / cumsum / compare / scatter at
+ * vit_models/dynamic_vit.py:880-890 (training) and :935-945 (inference).  score (B,N) f32 keep probabilities; a token is
+ * kept iff the cumulative sum of the ascending-sorted scores (stable: equal scores in index order; double accumulator rounded
+ * to f32 per prefix, as torch's CPU cumsum) at its rank exceeds `threshold`.  mask (B,N) uint8 0/1, count (B) int32 kept
+ * tokens per image, kept (B,N) int64 kept indices ascending then -1 padding (what a variable-length gather consumes); any of
+ * the three may be NULL. */
+int d2s_threshold_select_f32(const float* score, int B, int N, float threshold, uint8_t* mask, int* count, int64_t* kept,
+                             d2s_stream_t stream);
+
 /* ---- (1b) fused predictor tails -----------------------------------------------------------------
  * Variant A tail: Linear(C,2)+LogSoftmax (default_dynamic_vit.py:319-320), then either
  *   eval : top-K of logp[:,:,0] in descending-score order (default_dynamic_vit.py:461-463)  -> kept

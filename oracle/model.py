@@ -166,6 +166,29 @@ def variant_b_threshold_train(sd, cfg, img):
     return dict(logits=logits, features=feats, pred_logits=logit, keep_mask=keep_mask[:, 1:])
 
 
+def variant_b_threshold_eval_intended(sd, cfg, img):
+    """What the inference branch of the dynamic keep-ratio mode evidently intends (vit_models/dynamic_vit.py:935-949): the
+    lines themselves cannot execute (`score` is never assigned, :936; a float mask is used as an index, :947), so nothing can
+    be pinned against the reference here -- PARITY UNPINNED for this function.  Intent, restated: the cumulative-score
+    threshold of the training branch on the eval predictor scores, then the dropped tokens are removed (variable length:
+    one image per batch, mask_predictor.py:249-254); the pruning block and the later ones run without a policy."""
+    assert img.shape[0] == 1, "variable-length pruning: one image per batch"
+    x = embed(sd, cfg, img)
+    kept_all, p = [], 0
+    for i in range(cfg.depth):
+        if i in cfg.pruning_loc:
+            _, probs = ops.predictor_b(sd, f"score_predictor.{p}", x[:, 1:], cfg.small_predictor, cfg.predictor_bn,
+                                       cfg.predictor_loss_type, False)
+            m = ops.threshold_keep_mask(probs, cfg.patch_score_threshold)
+            kept = torch.nonzero(m[0]).flatten().unsqueeze(0)
+            x = ops.gather_tokens_with_cls(x, kept)
+            kept_all.append(kept)
+            p += 1
+        x = block(sd, cfg, i, x)
+    logits, feats = _head(sd, cfg, x)
+    return dict(logits=logits, features=feats, kept=kept_all)
+
+
 def teacher_forward(sd, cfg, img, want_cls_attn=True):
     """Unpruned ViT teacher (vit_models/dynamic_vit.py:1150-1176; default_dynamic_vit.py:581-598).
     Returns (logits, tokens (B,196,D), cls_attn (B,depth,H,197) or None)."""

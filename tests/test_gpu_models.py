@@ -161,6 +161,33 @@ def test_variant_b_threshold_train(d2s, cuda_dev, img):
             model(img)
 
 
+def test_variant_b_threshold_inference_opt_in(d2s, cuda_dev, img):
+    """The opt-in inference form of the dynamic keep-ratio mode (prefix-sum select kernel + variable-length gather, one image
+    per batch) against the oracle's restatement of what dynamic_vit.py:935-949 intends."""
+    from oracle import model as om
+    m = META["Bthr"]
+    model = _load(d2s.variant_b.VisionTransformerDiffPruning(
+        pruning_loc=m["locs"], token_ratio=m["ratios"], distill=True, topk_selection=True, predictor_loss_type="kl_div",
+        patch_score_threshold=m["threshold"], small_predictor=True, **COMMON), m, cuda_dev).eval()
+    model.d2s_threshold_inference = True
+    sd = fx.seeded_state_dict(m["shapes"], m["w_seed"])
+    cfg = om.VitCfg(embed_dim=C["embed_dim"], depth=C["depth"], num_heads=C["num_heads"], num_classes=C["num_classes"],
+                    pruning_loc=m["locs"], token_ratio=m["ratios"], small_predictor=True, patch_score_threshold=m["threshold"])
+    counts = []
+    for b in range(img.shape[0]):
+        ref = om.variant_b_threshold_eval_intended(sd, cfg, img[b:b + 1].cpu())
+        with torch.no_grad():
+            logits = model(img[b:b + 1])[0]
+        for s in range(len(m["locs"])):
+            assert torch.equal(model.kept_token_indices[s].cpu(), ref["kept"][s])
+        torch.testing.assert_close(logits.cpu(), ref["logits"], **FP32)
+        counts.append(int(model.kept_token_indices[0].shape[1]))
+    assert 0 < min(counts) and max(counts) < 196 and model.max_keep_ratio == counts[-1] / 196
+    if len(set(counts)) > 1:
+        with pytest.raises(RuntimeError, match="batch size 1"), torch.no_grad():
+            model(img)
+
+
 def test_teachers(d2s, cuda_dev, img):
     m = META["T"]
     tb = _load(d2s.variant_b.VisionTransformerTeacher(**COMMON), m, cuda_dev).eval()

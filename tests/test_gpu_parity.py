@@ -76,6 +76,27 @@ def test_select_full_size_properties(ops):
 
 
 # ------------------------------------------------------------------------------------------ gather
+@pytest.mark.parametrize("B,N", [(64, 196), (3, 137), (2, 1000), (5, 5), (1, 1)])
+def test_threshold_select_bit_exact(ops, B, N):
+    """d2s_threshold_select_f32 (the prefix-sum form of the select, dynamic_vit.py:880-890) against the oracle: keep masks,
+    per-image counts and the ascending kept-index lists bit-exact, with tied scores and every threshold regime
+    (nothing kept ... everything kept)."""
+    g = fx.gen(40 + N)
+    p = torch.softmax(torch.randn(B, N, generator=g) * 2.0, dim=-1)
+    p[:, : N // 4] = p[:, N // 2: N // 2 + N // 4].clone() if N >= 4 else p[:, : N // 4]      # exact ties
+    for thr in (-1.0, 0.0, 0.05, 0.3, 0.9, 0.999999, 1.5):
+        mask, count, kept = ops.threshold_select(cu(p), thr, want_indices=True)
+        ref = oo.threshold_keep_mask(p, thr)
+        assert torch.equal(mask.cpu(), ref), thr
+        assert torch.equal(count.cpu().long(), ref.sum(1)), thr
+        for b in range(B):
+            k = int(ref[b].sum())
+            assert torch.equal(kept[b, :k].cpu(), torch.nonzero(ref[b]).flatten())
+            assert bool((kept[b, k:] == -1).all())
+        m2, c2 = ops.threshold_select(cu(p), thr)
+        assert torch.equal(m2, mask) and torch.equal(c2, count)
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("B,T,D,K", [(3, 197, 384, 137), (2, 138, 384, 96), (2, 97, 768, 67), (1, 197, 768, 176),
                                      (5, 197, 384, 58), (2, 10, 8, 4), (2, 197, 384, 0), (1, 2, 384, 1)])
