@@ -682,6 +682,34 @@ def run_gpu(args):
     h2d_only = h2d_leg(dev, B, world, torch, dist) if "h2d" in legs else None
     del runner
     torch.cuda.empty_cache()
+    # the same end-to-end step fed with RAW uint8 pixels (normalisation inside the im2col kernel): half the bytes over PCIe
+    e2e_u8 = None
+    if "e2e" in legs:
+        model_u8 = pkg.variant_a.DefaultVisionTransformerDiffPruning(pruning_loc=LOCS, token_ratio=RATIOS, distill=True, **DEIT_S)
+        model_u8.load_state_dict(sd)
+        ru = pkg.runner.InferenceRunner(model_u8, B, dev, dtype=torch.bfloat16, use_graph=not args.no_graph, warmup=2, uint8_input=True)
+        host8 = [torch.randint(0, 256, (B, 3, 224, 224), generator=torch.Generator().manual_seed(200 + i), dtype=torch.uint8).pin_memory()
+                 for i in range(2)]
+        for i in range(2):
+            ru.step_prefetched(ru.prefetch(host8[i & 1]))
+        barrier()
+        t0 = time.perf_counter()
+        slot = ru.prefetch(host8[0])
+        for i in range(K):
+            nxt = ru.prefetch(host8[(i + 1) & 1]) if i + 1 < K else None
+            out_host = ru.step_prefetched(slot)
+            slot = nxt
+        torch.cuda.synchronize()
+        u8_s = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+        barrier()
+        if world > 1:
+            dist.all_reduce(u8_s, op=dist.ReduceOp.MAX)
+        e2e_u8 = {"value": world * B * K / float(u8_s.item()), "unit": UNIT, "h2d_bytes_per_step": host8[0].numel(),
+                  "d2h_bytes_per_step": ru.logits.numel() * ru.logits.element_size(), "outputs_finite": bool(torch.isfinite(out_host.float()).all()),
+                  "note": "pinned uint8 host images (raw pixels); ToTensor + Normalize run inside the patch-embedding im2col kernel, "
+                          "bit-identical to host-side normalisation (tests/test_gpu_models.py::test_runner_uint8_input_...)"}
+        del ru, model_u8, host8
+    torch.cuda.empty_cache()
 
     # ---- training step (all ranks: the gradient all-reduce is the path's one collective) -----------------------------
     train = train_leg(pkg, args, dev, rank, world, torch, dist, pk) if "train" in legs else None
@@ -707,6 +735,8 @@ def run_gpu(args):
                               "peak_source": pk["source"] + " (sustained)"}})
     if e2e is not None:
         line["e2e"] = e2e
+    if e2e_u8 is not None:
+        line["e2e_uint8"] = e2e_u8
     if h2d_only is not None:
         line["h2d_only"] = h2d_only
     if train is not None:

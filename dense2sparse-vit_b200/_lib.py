@@ -49,6 +49,7 @@ SIGNATURES = {
     "d2s_pool_concat_inplace": [_p, _i, _i, _i, _i, _p],
     "d2s_assemble_tokens": [_p, _p, _p, _i, _i, _i, _i, _p, _p],
     "d2s_patchify": [_p, _i, _i, _i, _i, _i, _i, _i, _p, _p],
+    "d2s_patchify_u8": [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p],
     "d2s_layernorm_fwd": [_p, _i, _p, _p, ctypes.c_longlong, _i, _f, _p, _i, _p, _p],
     "d2s_layernorm_bwd": [_p, _i, _p, _i, _p, _p, ctypes.c_longlong, _i, _p, _p, _p, _p],
     "d2s_add_layernorm_fwd": [_p, _p, _i, _p, _p, ctypes.c_longlong, _i, _f, _p, _p, _i, _p, _p],

@@ -90,9 +90,80 @@ patchify_band_kernel(const int4* __restrict__ img, int C, int Hh, int Ww, int ph
   }
 }
 
+// uint8 images: the host side of the end-to-end path ships raw pixels (half the bytes of bf16, a quarter of fp32 over PCIe) and
+// torchvision's ToTensor + Normalize -- x / 255, then (x - mean[c]) / std[c], both in fp32 -- run here.  Each CTA first builds the
+// 256-entry table of that expression per channel with the SAME two IEEE operations (division by 255, subtraction, division; no
+// FMA contraction, no reciprocal), rounded to the output type, so every pixel is bit-identical to the torch pipeline at the cost
+// of one shared-memory lookup; then the band is transposed to patch rows as in patchify_band_kernel.
+template <typename OutT>
+__global__ void __launch_bounds__(256)
+patchify_u8_band_kernel(const uint8_t* __restrict__ img, const float* __restrict__ mean, const float* __restrict__ stdv, int C,
+                        int Hh, int Ww, int ph, int pw, OutT* __restrict__ out) {
+  extern __shared__ int4 band_raw[];                   // [C * ph][W] bytes, then the table
+  uint8_t* band = reinterpret_cast<uint8_t*>(band_raw);
+  OutT* lut = reinterpret_cast<OutT*>(band + (size_t)C * ph * Ww);      // [C][256]
+  const int gh = Hh / ph, gw = Ww / pw;
+  const int b = blockIdx.x / gh, gy = blockIdx.x - b * gh;
+  for (int i = threadIdx.x; i < C * 256; i += blockDim.x) {
+    const int c = i >> 8;
+    const float x = __fdiv_rn((float)(i & 255), 255.0f);
+    const float v = __fdiv_rn(__fsub_rn(x, mean[c]), stdv[c]);
+    if (sizeof(OutT) == 2) reinterpret_cast<__nv_bfloat16*>(lut)[i] = __float2bfloat16_rn(v);
+    else reinterpret_cast<float*>(lut)[i] = v;
+  }
+  const int wv = Ww / 16;                              // 16-byte vectors per image row
+  const int nvec = C * ph * wv;
+  for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
+    const int r = i / wv, xv = i - r * wv;             // r = c * ph + py
+    const int c = r / ph, py = r - c * ph;
+    band_raw[i] = ld_stream16(img + (((size_t)(b * C + c) * Hh + (size_t)(gy * ph + py)) * Ww + (size_t)xv * 16));
+  }
+  __syncthreads();
+  constexpr int VE = 16 / sizeof(OutT);                // output elements per 16-byte store
+  const int pwv = pw / VE;                             // vectors per patch row
+  const int vpp = C * ph * pwv;                        // vectors per patch (= per output row)
+  const int nout = gw * vpp;
+  int4* dst = reinterpret_cast<int4*>(out) + (size_t)blockIdx.x * nout;
+  for (int j = threadIdx.x; j < nout; j += blockDim.x) {
+    const int gx = j / vpp, kv = j - gx * vpp;
+    const int r = kv / pwv, pxv = kv - r * pwv;        // r = c * ph + py
+    const int c = r / ph;
+    const uint8_t* px = band + (size_t)r * Ww + gx * pw + pxv * VE;
+    const OutT* t = lut + c * 256;
+    OutT v[VE];
+#pragma unroll
+    for (int q = 0; q < VE; ++q) v[q] = t[px[q]];
+    dst[j] = *reinterpret_cast<const int4*>(v);
+  }
+}
+
 }  // namespace d2s
 
 using namespace d2s;
+
+extern "C" int d2s_patchify_u8(const void* img, const float* mean, const float* stdv, int out_dtype, int B, int C, int Hh, int Ww,
+                               int ph, int pw, void* out, d2s_stream_t stream) {
+  D2S_REQUIRE(img && mean && stdv && out, D2S_ERR_ARG, "patchify_u8: null pointer");
+  D2S_REQUIRE(out_dtype == D2S_F32 || out_dtype == D2S_BF16, D2S_ERR_ARG, "patchify_u8: output dtype %d unsupported", out_dtype);
+  const int ve = out_dtype == D2S_BF16 ? 8 : 4;
+  D2S_REQUIRE(B >= 0 && C >= 1 && C <= 4 && ph >= 1 && pw >= ve && Hh % ph == 0 && Ww % pw == 0 && pw % ve == 0 && Ww % 16 == 0,
+              D2S_ERR_ARG, "patchify_u8: bad shape B=%d C=%d H=%d W=%d patch=%dx%d (C <= 4, W %% 16 == 0, patch width %% %d == 0)", B,
+              C, Hh, Ww, ph, pw, ve);
+  const size_t smem = (size_t)C * ph * Ww + (size_t)C * 256 * (out_dtype == D2S_BF16 ? 2 : 4);
+  D2S_REQUIRE(smem <= 48 * 1024 && (long long)B * (Hh / ph) <= 0x7fffffffLL, D2S_ERR_ARG,
+              "patchify_u8: a band of C*ph image rows must fit 48 KB of shared memory (needs %zu B)", smem);
+  D2S_REQUIRE(aligned16(img) && aligned16(out), D2S_ERR_ALIGN, "patchify_u8: pointers must be 16-byte aligned");
+  if (B == 0) return D2S_OK;
+  const unsigned grid = (unsigned)((long long)B * (Hh / ph));
+  if (out_dtype == D2S_BF16)
+    patchify_u8_band_kernel<__nv_bfloat16><<<grid, 256, smem, (cudaStream_t)stream>>>((const uint8_t*)img, mean, stdv, C, Hh, Ww, ph,
+                                                                                      pw, (__nv_bfloat16*)out);
+  else
+    patchify_u8_band_kernel<float><<<grid, 256, smem, (cudaStream_t)stream>>>((const uint8_t*)img, mean, stdv, C, Hh, Ww, ph, pw,
+                                                                              (float*)out);
+  count_launch();
+  return check_launch("d2s_patchify_u8");
+}
 
 extern "C" int d2s_patchify(const void* img, int dtype, int B, int C, int Hh, int Ww, int ph, int pw, void* out,
                             d2s_stream_t stream) {

@@ -82,6 +82,16 @@ def patch_embed_forward(m, img):
         f"Input image size ({Hh}*{Ww}) doesn't match model ({m.img_size[0]}*{m.img_size[1]})."
     gh, gw = Hh // ph, Ww // pw
     w = m.proj.weight
+    if img.dtype == torch.uint8:
+        # raw pixels (runner.InferenceRunner(..., uint8_input=True)): ToTensor + Normalize fused into the im2col kernel
+        norm = getattr(m, "d2s_input_norm", None)
+        if norm is None:
+            raise RuntimeError("uint8 images need the normalisation constants: set patch_embed.d2s_input_norm = (mean, std)")
+        if img.is_cuda and w.dtype in (torch.float32, torch.bfloat16) and pw % 8 == 0 and Ww % 16 == 0 and C <= 4:
+            patches = ops.patchify_u8(img, ph, pw, norm[0], norm[1], out_dtype=w.dtype)
+            return F.linear(patches, w.view(w.shape[0], -1), m.proj.bias)
+        mean, std = (t.to(img.device, torch.float32).view(1, C, 1, 1) for t in norm)
+        img = (img.to(torch.float32).div(255.0) - mean) / std
     img = img.to(w.dtype)
     if img.is_cuda and not _needs_grad(img) and img.dtype in (torch.float32, torch.bfloat16) and pw % 8 == 0 and Ww % 8 == 0:
         patches = ops.patchify(img, ph, pw)

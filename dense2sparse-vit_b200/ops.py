@@ -732,6 +732,23 @@ def patchify(img, ph, pw):
     return out
 
 
+def patchify_u8(img, ph, pw, mean, std, out_dtype=torch.bfloat16):
+    """Raw uint8 images (B,C,H,W) -> normalised patches (B, (H/ph)*(W/pw), C*ph*pw) of `out_dtype`: torchvision's ToTensor +
+    Normalize ((x / 255 - mean[c]) / std[c], fp32) and the im2col of PatchEmbed in one pass, bit-identical to doing them with
+    torch.  mean, std: per-channel fp32 tensors."""
+    _check_cuda(img, mean, std)
+    if img.dtype != torch.uint8:
+        raise TypeError("patchify_u8 takes uint8 images")
+    x = img.detach().contiguous()
+    B, C, Hh, Ww = x.shape
+    m, s = _f32c(mean).reshape(-1), _f32c(std).reshape(-1)
+    if m.numel() != C or s.numel() != C:
+        raise ValueError(f"patchify_u8: mean / std must have {C} entries")
+    out = torch.empty(B, (Hh // ph) * (Ww // pw), C * ph * pw, dtype=out_dtype, device=x.device)
+    _call("d2s_patchify_u8", _ptr(x), _ptr(m), _ptr(s), _dtype_code(out), B, C, Hh, Ww, int(ph), int(pw), _ptr(out), _stream(x))
+    return out
+
+
 # ----------------------------------------------------------------------------------------------
 # LayerNorm with autograd (training path)
 # ----------------------------------------------------------------------------------------------

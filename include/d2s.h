@@ -209,6 +209,12 @@ int d2s_assemble_tokens(const void* patches, const void* cls, const void* pos, i
  * img (B,C,H,W) -> out (B, (H/ph)*(W/pw), C*ph*pw) with k = (c, py, px); pw must be a multiple of 8 (bf16) / 4 (f32). */
 int d2s_patchify(const void* img, int dtype, int B, int C, int H, int W, int ph, int pw, void* out, d2s_stream_t stream);
 
+/* The same im2col from RAW uint8 images (the host side of the end-to-end path: half the PCIe bytes of bf16): ToTensor + Normalize
+ * -- x / 255, then (x - mean[c]) / std[c] in fp32, rounded to out_dtype -- applied on the fly, bit-identical to the torch
+ * pipeline (per-channel 256-entry table built with the same IEEE operations).  mean, std (C) f32; C <= 4, W % 16 == 0. */
+int d2s_patchify_u8(const void* img, const float* mean, const float* std, int out_dtype, int B, int C, int H, int W, int ph, int pw,
+                    void* out, d2s_stream_t stream);
+
 /* ---- residual add + LayerNorm ("next" row of the scope table: Block.forward) -----------------------------
  * Inference path of x = x + branch; h = norm(x) (dynamic_vit.py:263-283; default_dynamic_vit.py:234-237) and of the
  * predictors' leading LayerNorm over x[:, 1:] (dynamic_vit.py:409, :491; default_dynamic_vit.py:308) in one pass:

@@ -220,6 +220,27 @@ def test_cuda_graph_runner_matches_eager(d2s, cuda_dev, img):
     assert torch.equal(hl, eager.cpu())
 
 
+def test_runner_uint8_input_equals_host_side_normalisation(d2s, cuda_dev):
+    """InferenceRunner(uint8_input=True): raw pixels in, ToTensor + Normalize inside the im2col kernel -- the same logits, bit
+    for bit, as normalising on the host (what the reference's data loaders do) and feeding floats; also through the pinned-host
+    pipeline."""
+    import copy
+    m, _ = _deit_s_width_models(d2s, cuda_dev, "a", [0.7, 0.49])
+    u8 = torch.randint(0, 256, (6, 3, 224, 224), generator=fx.gen(95), dtype=torch.uint8)
+    mean = torch.tensor(d2s.runner.InferenceRunner.IMAGENET_MEAN).view(1, 3, 1, 1)
+    std = torch.tensor(d2s.runner.InferenceRunner.IMAGENET_STD).view(1, 3, 1, 1)
+    xf = ((u8.float().div(255.0) - mean) / std).to(torch.bfloat16)
+    rf = d2s.runner.InferenceRunner(copy.deepcopy(m), 6, cuda_dev, dtype=torch.bfloat16, use_graph=True, warmup=1)
+    ru = d2s.runner.InferenceRunner(copy.deepcopy(m), 6, cuda_dev, dtype=torch.bfloat16, use_graph=True, warmup=1, uint8_input=True)
+    a = rf(xf.to(cuda_dev)).clone()
+    b = ru(u8.to(cuda_dev)).clone()
+    torch.cuda.synchronize()
+    assert torch.equal(a, b)
+    hl = ru.step_prefetched(ru.prefetch(u8.pin_memory()))
+    torch.cuda.synchronize()
+    assert torch.equal(hl, a.cpu())
+
+
 def test_smoke_entry():
     import __graft_entry__ as ge
     ge.smoke()

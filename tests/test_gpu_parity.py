@@ -655,6 +655,19 @@ def test_patchify_bit_exact(ops, dtype):
     assert torch.equal(ops.patchify(cu(img3), 16, 16).cpu(), ref3)
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("B,C,H,W,p", [(3, 3, 224, 224, 16), (2, 1, 32, 64, 8), (1, 3, 48, 32, 16)])
+def test_patchify_u8_is_totensor_normalize_im2col_bit_exact(ops, dtype, B, C, H, W, p):
+    """Raw uint8 pixels -> normalised patches: bit-identical to torch's x / 255, (x - mean) / std in fp32, cast, im2col."""
+    u8 = torch.randint(0, 256, (B, C, H, W), generator=fx.gen(330 + H), dtype=torch.uint8)
+    u8[0, 0, 0, :16] = torch.arange(240, 256, dtype=torch.uint8)
+    mean, std = torch.tensor([0.485, 0.456, 0.406][:C]), torch.tensor([0.229, 0.224, 0.225][:C])
+    out = ops.patchify_u8(cu(u8), p, p, cu(mean), cu(std), out_dtype=dtype)
+    x = ((u8.float().div(255.0) - mean.view(1, C, 1, 1)) / std.view(1, C, 1, 1)).to(dtype)
+    ref = x.view(B, C, H // p, p, W // p, p).permute(0, 2, 4, 1, 3, 5).reshape(B, (H // p) * (W // p), C * p * p)
+    assert torch.equal(out.cpu(), ref)
+
+
 def test_gelu_inplace_matches_exact_erf(ops):
     u = (fx.randn(182, 64, 197, 1536) * 2.0)
     ref = torch.nn.functional.gelu(u)
