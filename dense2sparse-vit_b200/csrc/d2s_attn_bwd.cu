@@ -38,7 +38,7 @@ constexpr uint32_t kColS = 0, kColDP = 208, kColDV = 104, kColDK = 312, kColDQ =
 constexpr int kBwdThreads = 160;
 
 struct BwdBars {
-  uint64_t qdo_full, k_full, v_full, sdp_full, pds_full, acc_full, acc_free, dq_full, dq_free;
+  uint64_t qdo_full, k_full[2], v_full, sdp_full, pds_full, acc_full, acc_free, dq_full, dq_free;
   uint32_t tmem_base;
   uint32_t pad;
 };
@@ -85,18 +85,21 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_qa, const __grid_cons
   const int rows_b = kNT == 1 ? 0 : Tp - kTileRows;      // rows of the second box, and of key tile 1
   unsigned char* q_s = tiles;                                      // Tp x 128 B (Tp is a multiple of 16: whole 1024-byte atoms)
   unsigned char* do_s = q_s + (size_t)Tp * 128;                    // Tp x 128 B
-  unsigned char* k_s = do_s + (size_t)Tp * 128;                    // 128 x 128 B      (key tile jb)
-  unsigned char* v_s = k_s + kTileBytes;                           // 128 x 128 B
+  unsigned char* k_s = do_s + (size_t)Tp * 128;                    // 2 x 128 x 128 B  (key tile jb; double-buffered: K lives until the dQ MMAs)
+  unsigned char* v_s = k_s + 2 * kTileBytes;                       // 128 x 128 B
   unsigned char* ds_s = v_s + kTileBytes;                          // 2 kNT blocks of [128 key rows x 64 queries]: dS^T
   float* stash = reinterpret_cast<float*>(ds_s + (size_t)2 * kNT * kTileBytes);   // kNT == 2: Tp x 64 fp32 (dQ of key tile 0)
-  float4* sts = reinterpret_cast<float4*>(stash + (kNT == 2 ? (size_t)Tp * kTcHD : 0));   // 256 x (m', 1/den, -delta/den, c/den)
+  // per-query statistics, two queries per entry for the packed fp32x2 arithmetic of the pass:
+  //   sts[2 p] = (-m'_i, -m'_i+1, 1/den_i, 1/den_i+1)      sts[2 p + 1] = (-delta_i/den_i, -delta_i+1/den_i+1, c_i/den_i, c_i+1/den_i+1),  i = 2 p
+  float4* sts = reinterpret_cast<float4*>(stash + (kNT == 2 ? (size_t)Tp * kTcHD : 0));   // 256 floats x 4
   float* pol_s = reinterpret_cast<float*>(sts + 256);              // 256
   BwdBars* bars = reinterpret_cast<BwdBars*>(pol_s + 256);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
     mbar_init(smem_u32(&bars->qdo_full), 1);
-    mbar_init(smem_u32(&bars->k_full), 1);
+    mbar_init(smem_u32(&bars->k_full[0]), 1);
+    mbar_init(smem_u32(&bars->k_full[1]), 1);
     mbar_init(smem_u32(&bars->v_full), 1);
     mbar_init(smem_u32(&bars->sdp_full), 1);
     mbar_init(smem_u32(&bars->pds_full), 128);
@@ -123,7 +126,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_qa, const __grid_cons
     const uint32_t idesc_kv = make_idesc(128, kTcHD, 1);        // dV, dK: A from TMEM, B MN-major
     const uint32_t idesc_q = make_idesc(128, kTcHD, 1, 1);      // dQ: A and B MN-major
     const uint64_t qd = make_desc_sw128(smem_u32(q_s), 16, 1024), gd = make_desc_sw128(smem_u32(do_s), 16, 1024);
-    const uint64_t kd = make_desc_sw128(smem_u32(k_s), 16, 1024), vd = make_desc_sw128(smem_u32(v_s), 16, 1024);
+    const uint64_t kd0 = make_desc_sw128(smem_u32(k_s), 16, 1024), vd = make_desc_sw128(smem_u32(v_s), 16, 1024);
     const uint32_t bytes_a = (uint32_t)rows_a * 128u, bytes_b = (uint32_t)rows_b * 128u;
     auto load_qdo = [&](int unit) {     // all Tp query rows of Q and dO
       const uint32_t bar = smem_u32(&bars->qdo_full);
@@ -149,7 +152,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_qa, const __grid_cons
     int unit = blockIdx.x;
     if (unit < num_units) {
       load_qdo(unit);
-      load_tile(k_s, 1, unit, 0, smem_u32(&bars->k_full));
+      load_tile(k_s, 1, unit, 0, smem_u32(&bars->k_full[0]));
       load_tile(v_s, 2, unit, 0, smem_u32(&bars->v_full));
     }
     uint32_t iter = 0, dqn = 0, un = 0;     // (unit, key tile) iterations, dQ tiles and units processed by this CTA: parity sources
@@ -160,8 +163,15 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_qa, const __grid_cons
         const bool last_jb = jb == kNT - 1;
         const int n_unit = last_jb ? next : unit, n_jb = last_jb ? 0 : jb + 1;     // the (unit, key tile) after this one
         const bool has_n = n_unit < num_units;
+        const uint32_t kb = iter & 1;                                              // K buffer of this iteration
+        const uint64_t kd = kd0 + (uint64_t)(kb * (kTileBytes >> 4));
+        if (has_n) {
+          // the other K buffer was last read by the dQ MMAs of the previous iteration: refill it a whole iteration ahead
+          if (iter > 0) mbar_wait(smem_u32(&bars->dq_full), (dqn - 1) & 1);
+          load_tile(k_s + (kb ^ 1) * kTileBytes, 1, n_unit, n_jb, smem_u32(&bars->k_full[kb ^ 1]));
+        }
         if (jb == 0) mbar_wait(smem_u32(&bars->qdo_full), un & 1);
-        mbar_wait(smem_u32(&bars->k_full), iter & 1);
+        mbar_wait(smem_u32(&bars->k_full[kb]), (iter >> 1) & 1);
         mbar_wait(smem_u32(&bars->v_full), iter & 1);
         if (iter > 0) mbar_wait(smem_u32(&bars->acc_free), (iter - 1) & 1);        // dV / dK of the previous tile are drained
         tc_fence_after();
@@ -213,10 +223,6 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_qa, const __grid_cons
           mbar_wait(smem_u32(&bars->acc_full), iter & 1);                          // Q and dO are dead
           load_qdo(n_unit);
         }
-        if (has_n) {
-          mbar_wait(smem_u32(&bars->dq_full), (dqn - 1) & 1);                      // K tile is dead
-          load_tile(k_s, 1, n_unit, n_jb, smem_u32(&bars->k_full));
-        }
       }
     }
   } else {
@@ -233,9 +239,10 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_qa, const __grid_cons
         float4 st = make_float4(0.f, 0.f, 0.f, 0.f);      // queries past T: P = 0, g = 0
         if (i < T) {
           const float4 raw4 = reinterpret_cast<const float4*>(stats)[(size_t)unit * T + i];
-          st = make_float4(raw4.x, raw4.y, -raw4.w * raw4.y, raw4.z);
+          st = make_float4(-raw4.x, raw4.y, -raw4.w * raw4.y, raw4.z);
         }
-        sts[i] = st;
+        float* e0 = reinterpret_cast<float*>(sts + (i & ~1)) + (i & 1);
+        e0[0] = st.x; e0[2] = st.y; e0[4] = st.z; e0[6] = st.w;
         if (kPol) pol_s[i] = i < T ? policy[(size_t)b * T + i] : 0.0f;
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -250,11 +257,18 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_qa, const __grid_cons
         mbar_wait(smem_u32(&bars->sdp_full), iter & 1);
         tc_fence_after();
         if (warp_active) {
+          uint32_t nsv[16], ndv[16];
+          tmem_ld16_nowait(lane_addr + kColS, nsv);
+          tmem_ld16_nowait(lane_addr + kColDP, ndv);
           for (int c = 0; c < nchunks; ++c) {
             uint32_t sv[16], dv[16];
-            tmem_ld16_nowait(lane_addr + kColS + (uint32_t)(c * 16), sv);
-            tmem_ld16_nowait(lane_addr + kColDP + (uint32_t)(c * 16), dv);
             tmem_ld_wait();
+#pragma unroll
+            for (int q = 0; q < 16; ++q) { sv[q] = nsv[q]; dv[q] = ndv[q]; }
+            if (c + 1 < nchunks) {           // the next chunk's S^T / dP^T columns travel while this one is processed
+              tmem_ld16_nowait(lane_addr + kColS + (uint32_t)((c + 1) * 16), nsv);
+              tmem_ld16_nowait(lane_addr + kColDP + (uint32_t)((c + 1) * 16), ndv);
+            }
             if (c == 0) dv[0] = __float_as_uint(__uint_as_float(dv[0]) + gc);       // d loss / d P[0, j] (CLS-row output)
             // the diagonal (mask 1 whatever the policy) lies in one chunk per thread: warp-uniform split of the two forms
             const bool diag_chunk = kPol && (c * 16 < jb * kTileRows + quad * 32 + 32) && (c * 16 + 16 > jb * kTileRows + quad * 32);
@@ -263,27 +277,34 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_qa, const __grid_cons
 #pragma unroll
               for (int q = 0; q < 16; ++q) {
                 const int i = c * 16 + q;
-                const float4 st = sts[i];
-                const float et = ex2_approx(fmaf(__uint_as_float(sv[q]), k2, -st.x));
-                const float g = fmaf(__uint_as_float(dv[q]), st.y, st.z);
+                const float* st = reinterpret_cast<const float*>(sts + (i & ~1)) + (i & 1);     // (-m', 1/den, -delta/den, c/den) at +0,2,4,6
+                const float et = ex2_approx(fmaf(__uint_as_float(sv[q]), k2, st[0]));
+                const float g = fmaf(__uint_as_float(dv[q]), st[2], st[4]);
                 const float e = (i == j) ? et : et * pj;
-                pv[q] = fmaf(e, st.y, st.w);
+                pv[q] = fmaf(e, st[2], st[6]);
                 dsv[q] = g * e;
                 const float u = (i == j) ? 0.f : g * et;
                 if (q & 1) dpol1 += u; else dpol0 += u;
               }
             } else {
+              // two queries per step on the packed fp32x2 pipe (FFMA2 / FMUL2 / FADD2): 7 arithmetic issue slots per pair
+              const uint64_t k22 = f2_bcast(k2), pj2 = f2_bcast(pj);
+              uint64_t dacc = f2_pack(dpol0, dpol1);
 #pragma unroll
-              for (int q = 0; q < 16; ++q) {
-                const float4 st = sts[c * 16 + q];
-                const float et = ex2_approx(fmaf(__uint_as_float(sv[q]), k2, -st.x));
-                const float g = fmaf(__uint_as_float(dv[q]), st.y, st.z);
-                const float u = g * et;
-                const float e = kPol ? et * pj : et;
-                pv[q] = fmaf(e, st.y, st.w);
-                dsv[q] = kPol ? u * pj : u;
-                if (kPol) { if (q & 1) dpol1 += u; else dpol0 += u; }
+              for (int q = 0; q < 16; q += 2) {
+                const float4 sa = sts[c * 16 + q], sb = sts[c * 16 + q + 1];
+                const uint64_t a2 = f2_pack(sa.z, sa.w);
+                float x0, x1;
+                f2_unpack(f2_fma(f2_pack(__uint_as_float(sv[q]), __uint_as_float(sv[q + 1])), k22, f2_pack(sa.x, sa.y)), x0, x1);
+                const uint64_t et2 = f2_pack(ex2_approx(x0), ex2_approx(x1));
+                const uint64_t g2 = f2_fma(f2_pack(__uint_as_float(dv[q]), __uint_as_float(dv[q + 1])), a2, f2_pack(sb.x, sb.y));
+                const uint64_t u2 = f2_mul(g2, et2);
+                const uint64_t e2 = kPol ? f2_mul(et2, pj2) : et2;
+                f2_unpack(f2_fma(e2, a2, f2_pack(sb.z, sb.w)), pv[q], pv[q + 1]);
+                f2_unpack(kPol ? f2_mul(u2, pj2) : u2, dsv[q], dsv[q + 1]);
+                if (kPol) dacc = f2_add(dacc, u2);
               }
+              if (kPol) f2_unpack(dacc, dpol0, dpol1);
             }
             uint32_t pp[8], dd[8];
 #pragma unroll
@@ -392,7 +413,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_qa, const __grid_cons
 }
 
 static size_t bwd_smem_bytes(int knt, int Tp) {
-  return 1024 + (size_t)2 * Tp * 128 + (size_t)(2 + 2 * knt) * kTileBytes + (knt == 2 ? (size_t)Tp * kTcHD * 4 : 0) + 256 * 16 +
+  return 1024 + (size_t)2 * Tp * 128 + (size_t)(3 + 2 * knt) * kTileBytes + (knt == 2 ? (size_t)Tp * kTcHD * 4 : 0) + 256 * 16 +
          256 * 4 + sizeof(BwdBars);
 }
 

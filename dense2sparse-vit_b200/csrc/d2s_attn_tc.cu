@@ -68,6 +68,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   float* sum_s = vsum_s + 64;                                 // 2 x 128 (kSW == 8: partial row sums of the column halves)
   float* max_s = sum_s + 256;                                 // 2 x 128
   float* ref_s = max_s + 256;                                 // 2 x 128 (kSW == 8: exponent reference of each column half)
+  float* vpart_s = ref_s + 256;                               // 4 x 64 partial column sums of V
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t bytes_a = (uint32_t)rows_a * 128u, bytes_b = (uint32_t)rows_b * 128u;
@@ -195,18 +196,49 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     const float eps_den = kPol ? eps : 0.0f;
     const int nchunks = Tkp / 16;
     uint32_t g = 0;
+    constexpr int kPolPer = 256 / (32 * kSW);                     // policy elements per softmax thread (256-entry row buffer)
+    float pol_next[kPolPer];
     for (uint32_t it = 0, unit = blockIdx.x; (int)unit < num_units; unit += gridDim.x, ++it) {
       const int b = unit / H, h = unit % H;
       if (kPol) {
-        // per-unit policy row and column sums of V (for the eps/T term): sum_j V[j][d]
+        // per-unit policy row and column sums of V (for the eps/T term): sum_j V[j][d].  The policy row of THIS unit was fetched
+        // into registers while the previous unit was being processed (its global-memory latency is off the critical path); the
+        // column sums are split over all softmax threads (row groups x 64 columns) and combined through shared memory.
         asm volatile("bar.sync 1, %0;" ::"n"(32 * kSW) : "memory");  // previous unit's readers of pol_s / vsum_s are done
-        for (int j = tid; j < 256; j += 32 * kSW) pol_s[j] = (j < T) ? policy[(size_t)b * T + j] : 0.0f;
+        if (it == 0) {
+#pragma unroll
+          for (int q = 0; q < kPolPer; ++q) {
+            const int j = tid + q * 32 * kSW;
+            pol_next[q] = (j < T) ? policy[(size_t)b * T + j] : 0.0f;
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < kPolPer; ++q) pol_s[tid + q * 32 * kSW] = pol_next[q];
+        {
+          const int nb = (int)(unit + gridDim.x) / H;             // next unit's image (clamped: the values are unused past the end)
+          const int nbc = nb < (num_units / H) ? nb : b;
+#pragma unroll
+          for (int q = 0; q < kPolPer; ++q) {
+            const int j = tid + q * 32 * kSW;
+            pol_next[q] = (j < T) ? policy[(size_t)nbc * T + j] : 0.0f;
+          }
+        }
         mbar_wait(smem_u32(&bars->v_full), it & 1);
-        if (tid < kTcHD) {
+        {
+          constexpr int kGroups = 32 * kSW / kTcHD;               // row groups: 2 (four softmax warps) or 4 (eight)
+          const int col = tid & (kTcHD - 1), grp = tid >> 6;
+          const int cchunk = col >> 3, within = col & 7;
           float acc = 0.f;
-          const int cchunk = tid >> 3, within = tid & 7;
-          for (int j = 0; j < T; ++j)
+          for (int j = grp; j < T; j += kGroups)
             acc += __bfloat162float(*(reinterpret_cast<const __nv_bfloat16*>(v_s + sw128_off(j, cchunk)) + within));
+          vpart_s[grp * kTcHD + col] = acc;
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * kSW) : "memory");
+        if (tid < kTcHD) {
+          constexpr int kGroups = 32 * kSW / kTcHD;
+          float acc = vpart_s[tid];
+#pragma unroll
+          for (int gq = 1; gq < kGroups; ++gq) acc += vpart_s[gq * kTcHD + tid];
           vsum_s[tid] = acc;
         }
         asm volatile("bar.sync 1, %0;" ::"n"(32 * kSW) : "memory");
@@ -274,13 +306,28 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             const bool full = ch * 16 + 16 <= T;
             // exponentials against the current reference; the chunk's own partial sums double as the overflow detector (a sum
             // beyond 2^kMaxBinades, inf or NaN), so the common path carries no dependence on a row maximum
+            // the diagonal (mask 1 whatever the policy) lies in the chunks that overlap this warp's 32 query rows: a warp-uniform
+            // split, so that every other chunk is a plain multiply by the policy (fetched as four 16-byte broadcasts)
+            const bool diag_chunk = kPol && ch * 16 < t * kTileRows + quad * 32 + 32 && ch * 16 + 16 > t * kTileRows + quad * 32;
             auto exps = [&]() {
+              float pj[16];
+              if (kPol) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  const float4 p4 = *reinterpret_cast<const float4*>(&pol_s[ch * 16 + 4 * q]);
+                  pj[4 * q] = p4.x; pj[4 * q + 1] = p4.y; pj[4 * q + 2] = p4.z; pj[4 * q + 3] = p4.w;
+                }
+                if (diag_chunk) {
+#pragma unroll
+                  for (int q = 0; q < 16; ++q)
+                    if (ch * 16 + q == i) pj[q] = 1.0f;
+                }
+              }
 #pragma unroll
               for (int q = 0; q < 16; ++q) {
-                const int j = ch * 16 + q;
                 float e = ex2_approx(fmaf(__uint_as_float(v[q]), k2, -mxk));
-                if (kPol) e *= (j == i) ? 1.0f : pol_s[j];
-                if (!full && j >= T) e = 0.f;
+                if (kPol) e *= pj[q];                       // columns past T: the policy buffer holds zeros there
+                else if (!full && ch * 16 + q >= T) e = 0.f;
                 a[q] = e;
               }
             };
@@ -289,9 +336,18 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             float c2 = (a[2] + a[6]) + (a[10] + a[14]), c3 = (a[3] + a[7]) + (a[11] + a[15]);
             if (kPol) {
               // the true row maximum (masked keys included: the reference's eps terms follow it); off the critical path
+              if (full) {
+                const float m0 = fmax3(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]));
+                const float m1 = fmax3(__uint_as_float(v[3]), __uint_as_float(v[4]), __uint_as_float(v[5]));
+                const float m2 = fmax3(__uint_as_float(v[6]), __uint_as_float(v[7]), __uint_as_float(v[8]));
+                const float m3 = fmax3(__uint_as_float(v[9]), __uint_as_float(v[10]), __uint_as_float(v[11]));
+                const float m4 = fmax3(__uint_as_float(v[12]), __uint_as_float(v[13]), __uint_as_float(v[14]));
+                mx_true = fmax3(mx_true, fmax3(m0, m1, m2), fmax3(m3, m4, __uint_as_float(v[15])));
+              } else {
 #pragma unroll
-              for (int q = 0; q < 16; ++q)
-                if (full || ch * 16 + q < T) mx_true = fmaxf(mx_true, __uint_as_float(v[q]));
+                for (int q = 0; q < 16; ++q)
+                  if (ch * 16 + q < T) mx_true = fmaxf(mx_true, __uint_as_float(v[q]));
+              }
             }
             if (__any_sync(0xffffffffu, !((c0 + c1) + (c2 + c3) <= kBigSum))) {   // rare: raise the reference, rescale what exists
               float cm = __uint_as_float(v[0]);     // chunk maximum over the valid key columns (zero-filled columns past T excluded)
@@ -459,6 +515,7 @@ typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void
                              const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                              CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static EncodeFn encode_fn() {
+  bind_primary_context();
   static EncodeFn fn = nullptr;
   static bool tried = false;
   if (!tried) {
@@ -476,7 +533,7 @@ static size_t tc_smem_bytes(int knt, int Tkp, int kbufs) {
   const int rows_a = knt == 1 ? Tkp : kTileRows, rows_b = knt == 1 ? 0 : Tkp - kTileRows;
   (void)rows_a;
   return 1024 + (size_t)(kTileRows + rows_b) * 128 + (size_t)(kbufs + 1) * Tkp * 128 + sizeof(TcBars) +
-         (256 + 256 + 64 + 256 + 256 + 256) * sizeof(float);
+         (256 + 256 + 64 + 256 + 256 + 256 + 256) * sizeof(float);
 }
 
 template <int kNT, bool kPol, int kSW>
@@ -544,6 +601,8 @@ extern "C" int d2s_attn_policy_fwd(const void* qkv, const float* policy, int dty
     return policy ? launch_tc<1, true, 4>(map_a, map_b, policy, units, T, H, Tkp, scale, eps, out, cls_row, stats, stream)
                   : launch_tc<1, false, 4>(map_a, map_b, policy, units, T, H, Tkp, scale, eps, out, cls_row, stats, stream);
   }
-  return policy ? launch_tc<2, true, 4>(map_a, map_b, policy, units, T, H, Tkp, scale, eps, out, cls_row, stats, stream)
+  static const bool pol8 = []() { const char* e = getenv("D2S_ATTN_POL_SW"); return !(e && e[0] == '4'); }();
+  if (policy && !pol8) return launch_tc<2, true, 4>(map_a, map_b, policy, units, T, H, Tkp, scale, eps, out, cls_row, stats, stream);
+  return policy ? launch_tc<2, true, 8>(map_a, map_b, policy, units, T, H, Tkp, scale, eps, out, cls_row, stats, stream)
                 : launch_tc<2, false, 8>(map_a, map_b, policy, units, T, H, Tkp, scale, eps, out, cls_row, stats, stream);
 }

@@ -146,6 +146,11 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));  // first source -> upper half
   return r;
 }
+__device__ __forceinline__ float fmax3(float a, float b, float c) {      // FMNMX3: one issue slot for a three-way maximum
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -297,7 +302,19 @@ __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v 
 typedef CUresult (*GgEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+// cuTensorMapEncodeTiled is a DRIVER call: it needs the device's primary context current on the calling thread.  A thread whose
+// first CUDA activity is one of these entry points (autograd's backward thread when the node is the only one of the graph)
+// has none yet -- the encode then fails with CUDA_ERROR_INVALID_CONTEXT (201).  One runtime call binds it.
+static inline void bind_primary_context() {
+  static thread_local bool bound = false;
+  if (!bound) {
+    cudaFree(nullptr);
+    bound = true;
+  }
+}
+
 static inline GgEncodeFn gg_encode_fn() {
+  bind_primary_context();
   static GgEncodeFn fn = nullptr;
   static bool tried = false;
   if (!tried) {
