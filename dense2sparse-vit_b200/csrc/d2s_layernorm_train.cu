@@ -135,6 +135,20 @@ ln_bwd_kernel(const TH* __restrict__ dh, const TX* __restrict__ x, const float* 
     const float mean = ok ? stats[row * 2] : 0.f, rstd = ok ? stats[row * 2 + 1] : 0.f;
     float xh[kVPL][8], gg[kVPL][8];
     float s1 = 0.f, s2 = 0.f;
+    // the residual-stream gradient is fetched together with x and dh (raw 16-byte words, unpacked at the end): issued only
+    // where it is consumed, behind the two row reductions, it exposed a second full memory latency per 8-row pass
+    int4 ga_raw[kVPL][sizeof(TX) == 2 ? 1 : 2];
+    if (gadd) {
+#pragma unroll
+      for (int k = 0; k < kVPL; ++k) {
+        const int vi = sub + 16 * k;
+        if (ok && vi < nvec) {
+          const int4* gp = reinterpret_cast<const int4*>(gadd + row * D + vi * 8);
+          ga_raw[k][0] = gp[0];
+          if (sizeof(TX) == 4) ga_raw[k][sizeof(TX) == 2 ? 0 : 1] = gp[1];
+        }
+      }
+    }
 #pragma unroll
     for (int k = 0; k < kVPL; ++k) {
       const int vi = sub + 16 * k;
@@ -168,7 +182,7 @@ ln_bwd_kernel(const TH* __restrict__ dh, const TX* __restrict__ x, const float* 
           for (int q = 0; q < 8; ++q) o[q] = rstd * (gg[k][q] - s1 - xh[k][q] * s2);
           if (gadd) {   // gradient that reaches x directly (the residual stream's), accumulated here instead of by a torch add
             float ga[8];
-            TV<TX>::load(gadd + row * D + vi * 8, ga);
+            TV<TX>::load(reinterpret_cast<const TX*>(&ga_raw[k][0]), ga);
 #pragma unroll
             for (int q = 0; q < 8; ++q) o[q] += ga[q];
           }
