@@ -477,6 +477,7 @@ def train_leg(pkg, args, dev, rank, world, torch, dist, pk):
     crit = pkg.losses.DistillDiffPruningLoss(teacher, keep_ratio=RATIOS)
     opt = torch.optim.AdamW(student.parameters(), lr=5e-4, weight_decay=0.05, capturable=True)
     grads = pkg.runner.FlatGrads(student.parameters())
+    wcache = pkg.ops.BF16WeightCache(student.parameters())
     g = torch.Generator(device=dev).manual_seed(42 + rank)
     x = torch.randn(B, 3, 224, 224, device=dev, generator=g)
     y = torch.randint(0, 1000, (B,), device=dev, generator=g)
@@ -486,7 +487,7 @@ def train_leg(pkg, args, dev, rank, world, torch, dist, pk):
             return crit(xx, student(xx), yy)[0]
 
     n0 = pkg._lib.launch_count()
-    run = pkg.runner.TrainStepRunner(fwd_loss, opt, x, y, warmup=2, use_graph=not args.no_graph, grads=grads)
+    run = pkg.runner.TrainStepRunner(fwd_loss, opt, x, y, warmup=2, use_graph=not args.no_graph, grads=grads, weight_cache=wcache)
     per_step = (pkg._lib.launch_count() - n0) // (3 if not args.no_graph else 2)
     W, K = 3, args.train_steps
     for _ in range(W):
@@ -530,7 +531,8 @@ def train_leg(pkg, args, dev, rank, world, torch, dist, pk):
            "allreduce_floor_ms": (2 * (world - 1) / world * grad_bytes / 725e9 * 1e3) if world > 1 else 0.0,
            "limiter": "tensor + HBM bound single-GPU step; the all-reduce is not overlapped with backward (it is ~1-2 % of the step)",
            "tensor_frac_of_sustained_peak": val / world * TRAIN_GFLOP_PER_IMG / 1e3 / pk["tf_sustained"]}
-    del run, student, teacher, opt, grads
+    wcache.close()
+    del run, student, teacher, opt, grads, wcache
     torch.cuda.empty_cache()
     return out
 

@@ -234,8 +234,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             // straight from registers (no room for a second staging block next to a 4-stage operand ring)
             const bool want_pre = p.pre != nullptr;
             const bool row_ok = row0 + r < p.M;
-            uint4* pre_row = reinterpret_cast<uint4*>(p.pre + (size_t)(row_ok ? row0 + r : 0) * p.N + col0 + c * 32);
-            uint32_t pw[4];
+            __nv_bfloat16* pre_row = p.pre + (size_t)(row_ok ? row0 + r : 0) * p.N + col0 + c * 32;
+            uint32_t pw[8];
 #pragma unroll
             for (int q = 0; q < 16; ++q) {
               const float2 bq = *reinterpret_cast<const float2*>(&bias_s[col0 + c * 32 + 2 * q]);
@@ -243,8 +243,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
               float x0, x1;
               if (want_pre) {
                 f2_unpack(xp, x0, x1);
-                pw[q & 3] = pack_bf16x2(x0, x1);
-                if ((q & 3) == 3 && row_ok) pre_row[q >> 2] = make_uint4(pw[0], pw[1], pw[2], pw[3]);
+                pw[q & 7] = pack_bf16x2(x0, x1);
+                if ((q & 7) == 7 && row_ok) st_global_v8(pre_row + (q >> 3) * 16, pw);     // whole 32-byte sectors
               }
               if (ACT == D2S_ACT_GELU) xp = gelu_erf_pair(xp);
               f2_unpack(xp, x0, x1);

@@ -349,6 +349,44 @@ def colsum(dy):
     return out
 
 
+class BF16WeightCache:
+    """bf16 copies of a model's fp32 master parameters, refreshed ONCE per step by one multi-tensor copy instead of one cast
+    kernel per Linear weight and bias per forward (141 launches, 0.5 ms of a DeiT-S training step).  The training-path Linear
+    ops (linear_train / linear_gelu_train) pick the copy up when one is registered for the parameter; whoever owns the step
+    (runner.TrainStepRunner) calls refresh() after every optimizer update -- between refreshes the copies are what the forward
+    sees, so a refresh must follow every change of the master weights."""
+
+    _active = {}          # id(parameter) -> bf16 copy
+
+    def __init__(self, params):
+        self.src = [p for p in params if p.dtype == torch.float32 and p.is_cuda]
+        self.dst = [torch.empty_like(p, dtype=torch.bfloat16) for p in self.src]
+        for p, d in zip(self.src, self.dst):
+            BF16WeightCache._active[id(p)] = (p, d)
+        self.refresh()
+
+    def refresh(self):
+        with torch.no_grad():
+            torch._foreach_copy_(self.dst, self.src)
+
+    def close(self):
+        for p in self.src:
+            BF16WeightCache._active.pop(id(p), None)
+
+    @staticmethod
+    def lookup(p):
+        hit = BF16WeightCache._active.get(id(p))
+        return hit[1] if hit is not None and hit[0] is p else None
+
+
+def _bf16_of(p):
+    """The bf16 form of a Linear weight / bias for the forward: the per-step cached copy when one is registered, else a cast."""
+    if p is None:
+        return None
+    c = BF16WeightCache.lookup(p)
+    return c if c is not None else p.to(torch.bfloat16)
+
+
 def _wgrad(dy, x, dtype):
     """dW = dy^T x for bf16 (M,N) x (M,K) operands in the parameter's dtype: with fp32 master weights the library GEMM writes
     its fp32 accumulator out directly (no bf16 rounding of the weight gradient, no separate cast pass)."""
@@ -377,8 +415,8 @@ class _LinearTrain(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, w, b):
-        xb, wb = x.to(torch.bfloat16), w.to(torch.bfloat16)
-        bb = None if b is None else b.to(torch.bfloat16)
+        xb, wb = x.to(torch.bfloat16), _bf16_of(w)
+        bb = _bf16_of(b)
         ctx.save_for_backward(xb, wb)
         ctx.meta = (x.dtype, w.dtype, None if b is None else b.dtype)
         return F.linear(xb, wb, bb)
@@ -422,8 +460,8 @@ class _LinearGeluTrain(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, w, b):
-        xb, wb = x.to(torch.bfloat16), w.to(torch.bfloat16)
-        bb = None if b is None else b.to(torch.bfloat16)
+        xb, wb = x.to(torch.bfloat16), _bf16_of(w)
+        bb = _bf16_of(b)
         if _FUSED_GELU_FWD and wb.shape[0] % 256 == 0 and wb.shape[0] <= 4096 and wb.shape[1] % 64 == 0:
             # one tcgen05 GEMM writes both the Linear's output (kept for GELU') and its GELU: torch's separate GELU pass
             # (read + write of the (M, 4D) hidden tensor) disappears

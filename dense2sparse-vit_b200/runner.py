@@ -174,8 +174,10 @@ class TrainStepRunner:
     capturable=True.  `grads` (a FlatGrads over the optimizer's parameters) makes the step data-parallel: one NCCL all-reduce of
     the flat gradient buffer is captured between backward and the optimizer step (one process per GPU, torchrun)."""
 
-    def __init__(self, step_fn, optimizer, x, y, warmup=3, use_graph=True, grads=None):
-        self.step_fn, self.opt, self.grads = step_fn, optimizer, grads
+    def __init__(self, step_fn, optimizer, x, y, warmup=3, use_graph=True, grads=None, weight_cache=None):
+        """weight_cache: an ops.BF16WeightCache over the trained parameters -- refreshed right after every optimizer step
+        (inside the captured graph), so the forward's Linear layers read per-step bf16 copies instead of casting every weight."""
+        self.step_fn, self.opt, self.grads, self.weight_cache = step_fn, optimizer, grads, weight_cache
         self.static_x, self.static_y = x.clone(), y.clone()
         self.graph, self.loss = None, None
         dev = x.device
@@ -201,6 +203,8 @@ class TrainStepRunner:
         if self.grads is not None:
             self.grads.all_reduce()
         self.opt.step()
+        if self.weight_cache is not None:
+            self.weight_cache.refresh()
 
     def _eager(self):
         if self.grads is None:

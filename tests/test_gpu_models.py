@@ -423,20 +423,30 @@ def test_graphed_training_step_matches_eager(d2s, cuda_dev):
         p.requires_grad_(False)
     gumbels = [fx.randn(51 + i, 4, 196, 2).to(cuda_dev) for i in range(2)]
     losses = {}
-    for mode in ("eager", "graph"):
+    for mode in ("eager", "graph", "graph_flat"):
         m = copy.deepcopy(base).train()
         m._d2s_gumbels = gumbels
         crit = d2s.losses.DistillDiffPruningLoss(teacher, keep_ratio=[0.7, 0.49])
         opt = torch.optim.AdamW(m.parameters(), lr=1e-4, weight_decay=0.05, capturable=True)
+        # graph_flat: what bench.py's training leg runs -- gradients as views of one flat buffer (the data-parallel all-reduce
+        # target) and per-step bf16 weight copies refreshed by one multi-tensor copy after the optimizer step
+        grads = d2s.runner.FlatGrads(m.parameters()) if mode == "graph_flat" else None
+        cache = d2s.ops.BF16WeightCache(m.parameters()) if mode == "graph_flat" else None
 
         def fwd_loss(xx, yy, m=m, crit=crit):
             with torch.autocast("cuda", dtype=torch.bfloat16):
                 return crit(xx, m(xx), yy)[0]
-        run = d2s.runner.TrainStepRunner(fwd_loss, opt, x, y, warmup=2, use_graph=mode == "graph")
-        assert (run.graph is not None) == (mode == "graph")
+        run = d2s.runner.TrainStepRunner(fwd_loss, opt, x, y, warmup=2, use_graph=mode != "eager", grads=grads, weight_cache=cache)
+        assert (run.graph is not None) == (mode != "eager")
         losses[mode] = [float(run()) for _ in range(4)]
-    for a, b in zip(losses["eager"], losses["graph"]):
-        assert abs(a - b) <= 2e-2 * abs(a) + 1e-3, losses
+        if cache is not None:
+            for p_, d_ in zip(cache.src, cache.dst):
+                assert torch.equal(d_, p_.detach().to(torch.bfloat16))          # the copies follow the optimizer
+            cache.close()
+            assert d2s.ops.BF16WeightCache.lookup(cache.src[0]) is None
+    for mode in ("graph", "graph_flat"):
+        for a, b in zip(losses["eager"], losses[mode]):
+            assert abs(a - b) <= 2e-2 * abs(a) + 1e-3, losses
     assert losses["graph"][-1] != losses["graph"][0]          # the replays really update the weights
 
 
