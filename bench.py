@@ -57,6 +57,7 @@ def parse():
     ap.add_argument("--train-steps", type=int, default=10)
     ap.add_argument("--cpu-batch", type=int, default=8, help="images per CPU step (BASELINE configs[0])")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--torch-adamw", action="store_true", help="training leg: torch.optim.AdamW(capturable) instead of runner.FlatAdamW")
     ap.add_argument("--skip-cpu", action="store_true", help="omit the cpu_baseline leg (debugging only)")
     ap.add_argument("--legs", default=",".join(ALL_LEGS), help="comma-separated subset of: " + ", ".join(ALL_LEGS))
     return ap.parse_args()
@@ -476,9 +477,13 @@ def train_leg(pkg, args, dev, rank, world, torch, dist, pk):
     for p in teacher.parameters():
         p.requires_grad_(False)
     crit = pkg.losses.DistillDiffPruningLoss(teacher, keep_ratio=RATIOS)
-    opt = torch.optim.AdamW(student.parameters(), lr=5e-4, weight_decay=0.05, capturable=True)
-    grads = pkg.runner.FlatGrads(student.parameters())
-    wcache = pkg.ops.BF16WeightCache(student.parameters())
+    if args.torch_adamw:
+        opt = torch.optim.AdamW(student.parameters(), lr=5e-4, weight_decay=0.05, capturable=True)
+        grads = pkg.runner.FlatGrads(student.parameters())
+        wcache = pkg.ops.BF16WeightCache(student.parameters())
+    else:            # AdamW as one d2s kernel over flat (parameter, gradient, moment) buffers; it also writes the bf16 weight copies
+        opt = pkg.runner.FlatAdamW(student.parameters(), lr=5e-4, weight_decay=0.05)
+        grads, wcache = opt.grads, opt.weight_cache
     g = torch.Generator(device=dev).manual_seed(42 + rank)
     x = torch.randn(B, 3, 224, 224, device=dev, generator=g)
     y = torch.randint(0, 1000, (B,), device=dev, generator=g)
@@ -530,9 +535,11 @@ def train_leg(pkg, args, dev, rank, world, torch, dist, pk):
            "collective": (f"one NCCL all-reduce of the flat fp32 gradient buffer ({grad_bytes / 1e6:.1f} MB) per step, captured in the "
                           f"step's CUDA graph between backward and AdamW" if world > 1 else "none (single GPU)"),
            "allreduce_floor_ms": (2 * (world - 1) / world * grad_bytes / 725e9 * 1e3) if world > 1 else 0.0,
+           "optimizer": "torch.optim.AdamW(capturable)" if args.torch_adamw else "runner.FlatAdamW (d2s_adamw_flat_f32: one launch, also writes the bf16 weight copies)",
            "limiter": "tensor + HBM bound single-GPU step; the all-reduce is not overlapped with backward (it is ~1-2 % of the step)",
            "tensor_frac_of_sustained_peak": val / world * TRAIN_GFLOP_PER_IMG / 1e3 / pk["tf_sustained"]}
     wcache.close()
+    grads.close()
     del run, student, teacher, opt, grads, wcache
     torch.cuda.empty_cache()
     return out

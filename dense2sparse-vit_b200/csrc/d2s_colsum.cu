@@ -48,13 +48,15 @@ colsum_bf16_kernel(const __nv_bfloat16* __restrict__ dy, long long M, int N, int
 
 using namespace d2s;
 
-extern "C" int d2s_colsum_bf16(const void* dy, long long M, int N, float* out, d2s_stream_t stream) {
+static int colsum_entry(const void* dy, long long M, int N, float* out, bool zero_first, d2s_stream_t stream) {
   D2S_REQUIRE(dy && out, D2S_ERR_ARG, "colsum: null pointer");
   D2S_REQUIRE(M >= 0 && N >= 8 && N % 8 == 0 && N <= 8192, D2S_ERR_ARG, "colsum: bad shape M=%lld N=%d (N %% 8 == 0, N <= 8192)", M, N);
   D2S_REQUIRE(aligned16(dy), D2S_ERR_ALIGN, "colsum: dy must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
-  cudaError_t e = cudaMemsetAsync(out, 0, (size_t)N * sizeof(float), st);
-  D2S_REQUIRE(e == cudaSuccess, D2S_ERR_CUDA, "colsum: memset: %s", cudaGetErrorString(e));
+  if (zero_first) {
+    cudaError_t e = cudaMemsetAsync(out, 0, (size_t)N * sizeof(float), st);
+    D2S_REQUIRE(e == cudaSuccess, D2S_ERR_CUDA, "colsum: memset: %s", cudaGetErrorString(e));
+  }
   if (M == 0) return D2S_OK;
   const int nx = N / 8;
   int ny = 1024 / nx;                      // row slots per CTA
@@ -69,6 +71,15 @@ extern "C" int d2s_colsum_bf16(const void* dy, long long M, int N, float* out, d
   colsum_bf16_kernel<<<(unsigned)grid, dim3(nx, ny), smem, st>>>((const __nv_bfloat16*)dy, M, N, (int)rows_per_cta, out);
   count_launch();
   return check_launch("d2s_colsum_bf16");
+}
+
+extern "C" int d2s_colsum_bf16(const void* dy, long long M, int N, float* out, d2s_stream_t stream) {
+  return colsum_entry(dy, M, N, out, true, stream);
+}
+
+// out += column sums: the form that lands a bias gradient straight in the parameter's (zeroed once per step) gradient slot
+extern "C" int d2s_colsum_acc_bf16(const void* dy, long long M, int N, float* out, d2s_stream_t stream) {
+  return colsum_entry(dy, M, N, out, false, stream);
 }
 
 // GELU backward fused with the bias gradient of the Linear in front of it (Mlp.forward, dynamic_vit.py:170-172: fc1 -> GELU):
@@ -154,13 +165,14 @@ gelu_bwd_colsum_kernel(const __nv_bfloat16* __restrict__ u, const __nv_bfloat16*
 
 }  // namespace d2s
 
-extern "C" int d2s_gelu_bwd_colsum_bf16(const void* u, const void* ga, long long M, int N, void* du, float* db, d2s_stream_t stream) {
+static int gelu_bwd_colsum_entry(const void* u, const void* ga, long long M, int N, void* du, float* db, bool zero_first,
+                                 d2s_stream_t stream) {
   D2S_REQUIRE(u && ga && du, D2S_ERR_ARG, "gelu_bwd_colsum: null pointer");
   D2S_REQUIRE(M >= 0 && N >= 8 && N % 8 == 0 && N <= 8192, D2S_ERR_ARG, "gelu_bwd_colsum: bad shape M=%lld N=%d (N %% 8 == 0, N <= 8192)",
               M, N);
   D2S_REQUIRE(aligned16(u) && aligned16(ga) && aligned16(du), D2S_ERR_ALIGN, "gelu_bwd_colsum: pointers must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
-  if (db) {
+  if (db && zero_first) {
     cudaError_t e = cudaMemsetAsync(db, 0, (size_t)N * sizeof(float), st);
     D2S_REQUIRE(e == cudaSuccess, D2S_ERR_CUDA, "gelu_bwd_colsum: memset: %s", cudaGetErrorString(e));
   }
@@ -178,4 +190,12 @@ extern "C" int d2s_gelu_bwd_colsum_bf16(const void* u, const void* ga, long long
                                                                          (int)rows_per_cta, (__nv_bfloat16*)du, db);
   d2s::count_launch();
   return d2s::check_launch("d2s_gelu_bwd_colsum_bf16");
+}
+
+extern "C" int d2s_gelu_bwd_colsum_bf16(const void* u, const void* ga, long long M, int N, void* du, float* db, d2s_stream_t stream) {
+  return gelu_bwd_colsum_entry(u, ga, M, N, du, db, true, stream);
+}
+
+extern "C" int d2s_gelu_bwd_colsum_acc_bf16(const void* u, const void* ga, long long M, int N, void* du, float* db, d2s_stream_t stream) {
+  return gelu_bwd_colsum_entry(u, ga, M, N, du, db, false, stream);
 }

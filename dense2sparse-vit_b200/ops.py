@@ -349,6 +349,84 @@ def colsum(dy):
     return out
 
 
+# ---- gradient slots: parameter gradients written where they live ------------------------------------------------
+# autograd hands a parameter gradient to an AccumulateGrad node, which adds it into an existing .grad with one more elementwise
+# launch per parameter (~200 launches, ~0.5 ms of a DeiT-S training step, plus a second pass over every weight gradient).  When
+# the gradients live in a runner.FlatGrads buffer the training-path nodes below write them there directly -- dW as the output of
+# the library GEMM, bias / LayerNorm gradients by kernels that accumulate into the slot -- and return None to autograd (the
+# "main_grad" arrangement of large-model trainers).  A slot is fp32, zeroed once per step by FlatGrads.zero(), which also re-arms
+# the "first write overwrites" flag of every slot; a parameter used twice in one backward accumulates on its second write.
+_GRAD_SLOTS = {}          # id(parameter) -> [weakref(parameter), first_write_pending]
+
+
+def register_grad_slots(params):
+    import weakref
+    for p in params:
+        _GRAD_SLOTS[id(p)] = [weakref.ref(p), True]
+
+
+def unregister_grad_slots(params):
+    for p in params:
+        _GRAD_SLOTS.pop(id(p), None)
+
+
+def reset_grad_slots(params):
+    for p in params:
+        e = _GRAD_SLOTS.get(id(p))
+        if e is not None:
+            e[1] = True
+
+
+def _grad_slot(p):
+    """(slot tensor, entry) when `p`'s gradient is to be written in place, else (None, None)."""
+    if p is None:
+        return None, None
+    e = _GRAD_SLOTS.get(id(p))
+    if e is None or e[0]() is not p:
+        return None, None
+    g = p.grad
+    if g is None or g.dtype != torch.float32 or not g.is_contiguous() or not g.is_cuda:
+        return None, None
+    return g, e
+
+
+def _wgrad_into(p, dy, x):
+    """dW = dy^T x landed in `p`'s gradient slot; False when `p` has none (the caller returns the gradient to autograd)."""
+    slot, e = _grad_slot(p)
+    if slot is None or not _MM_OUT:
+        return False
+    if e[1]:
+        torch.mm(dy.t(), x, out_dtype=torch.float32, out=slot)
+        e[1] = False
+    else:
+        slot.add_(torch.mm(dy.t(), x, out_dtype=torch.float32))
+    return True
+
+
+def _bias_grad_into(p, dy):
+    slot, e = _grad_slot(p)
+    if slot is None or dy.shape[0] == 0:
+        return False
+    _call("d2s_colsum_acc_bf16", _ptr(dy), dy.shape[0], dy.shape[1], _ptr(slot), _stream(dy))
+    e[1] = False
+    return True
+
+
+def adamw_flat(p, g, m, v, shadow, begin, end, lr, step, beta1, beta2, eps, weight_decay, grad_scale=1.0):
+    """One AdamW update of elements [begin, end) of the flat fp32 buffers (p, g, m, v) (`d2s_adamw_flat_f32`): lr and step are
+    1-element fp32 CUDA tensors; shadow (bf16, same layout) or None receives the updated parameters."""
+    _check_cuda(p, g, m, v, lr, step)
+    for t in (p, g, m, v, lr, step):
+        if t.dtype != torch.float32 or not t.is_contiguous():
+            raise TypeError("adamw_flat: contiguous fp32 tensors are expected")
+    if not (p.numel() == g.numel() == m.numel() == v.numel()) or not 0 <= begin <= end <= p.numel():
+        raise RuntimeError("adamw_flat: the flat buffers must have one size and [begin, end) must lie inside it")
+    if shadow is not None and (shadow.dtype != torch.bfloat16 or shadow.numel() != p.numel() or not shadow.is_contiguous()):
+        raise TypeError("adamw_flat: shadow must be a contiguous bf16 tensor of the parameters' size")
+    _call("d2s_adamw_flat_f32", _ptr(p), _ptr(g), _ptr(m), _ptr(v), _ptr(shadow), int(begin), int(end), _ptr(lr), _ptr(step),
+          float(beta1), float(beta2), float(eps), float(weight_decay), float(grad_scale), _stream(p))
+
+
 class BF16WeightCache:
     """bf16 copies of a model's fp32 master parameters, refreshed ONCE per step by one multi-tensor copy instead of one cast
     kernel per Linear weight and bias per forward (141 launches, 0.5 ms of a DeiT-S training step).  The training-path Linear
@@ -358,14 +436,23 @@ class BF16WeightCache:
 
     _active = {}          # id(parameter) -> bf16 copy
 
-    def __init__(self, params):
-        self.src = [p for p in params if p.dtype == torch.float32 and p.is_cuda]
-        self.dst = [torch.empty_like(p, dtype=torch.bfloat16) for p in self.src]
+    def __init__(self, params, copies=None):
+        """copies: bf16 tensors somebody else keeps current (runner.FlatAdamW's kernel writes them with the update), one per
+        parameter; refresh() is then a no-op."""
+        params = list(params)
+        if copies is not None:
+            self.src, self.dst, self.external = params, list(copies), True
+        else:
+            self.src = [p for p in params if p.dtype == torch.float32 and p.is_cuda]
+            self.dst = [torch.empty_like(p, dtype=torch.bfloat16) for p in self.src]
+            self.external = False
         for p, d in zip(self.src, self.dst):
             BF16WeightCache._active[id(p)] = (p, d)
         self.refresh()
 
     def refresh(self):
+        if self.external:
+            return
         with torch.no_grad():
             torch._foreach_copy_(self.dst, self.src)
 
@@ -407,6 +494,18 @@ def _probe_mm_out_dtype():
 _MM_OUT_DTYPE = _probe_mm_out_dtype()
 
 
+def _probe_mm_out():
+    try:
+        a = torch.zeros(8, 8, dtype=torch.bfloat16, device="meta")
+        torch.mm(a, a, out_dtype=torch.float32, out=torch.zeros(8, 8, dtype=torch.float32, device="meta"))
+        return True
+    except (TypeError, RuntimeError, NotImplementedError):
+        return False
+
+
+_MM_OUT = _MM_OUT_DTYPE and _probe_mm_out() and os.environ.get("D2S_DIRECT_GRADS", "1") != "0"
+
+
 class _LinearTrain(torch.autograd.Function):
     """nn.Linear on the bf16 training path (fp32 master weights under bf16 autocast, or a bf16 module).  Forward is the library
     GEMM torch would run on the bf16 casts; backward computes dx and dW with library GEMMs and the bias gradient with the d2s
@@ -419,6 +518,7 @@ class _LinearTrain(torch.autograd.Function):
         bb = _bf16_of(b)
         ctx.save_for_backward(xb, wb)
         ctx.meta = (x.dtype, w.dtype, None if b is None else b.dtype)
+        ctx.params = (w, b)
         return F.linear(xb, wb, bb)
 
     @staticmethod
@@ -432,14 +532,15 @@ class _LinearTrain(torch.autograd.Function):
         gx = (gy2 @ wb).view(xb.shape).to(xd) if ctx.needs_input_grad[0] else None
         gw = gb = None
         want_b = bd is not None and ctx.needs_input_grad[2]
-        if ctx.needs_input_grad[1]:
+        w_p, b_p = ctx.params
+        if ctx.needs_input_grad[1] and not _wgrad_into(w_p, gy2, xb.reshape(-1, K)):
             gw = _wgrad(gy2, xb.reshape(-1, K), wd)
-        if want_b:
+        if want_b and not _bias_grad_into(b_p, gy2):
             gb = colsum(gy2)
         return gx, gw, None if gb is None else gb.to(bd)
 
 
-def gelu_bwd_colsum(u, ga, want_bias=True):
+def gelu_bwd_colsum(u, ga, want_bias=True, db_into=None):
     """(du, db) = (ga * gelu'(u), column sums of du in fp32) for 2-D bf16 u, ga: the exact-erf GELU backward fused with the bias
     gradient of the Linear that produced u (`d2s_gelu_bwd_colsum_bf16`)."""
     _check_cuda(u, ga)
@@ -448,6 +549,10 @@ def gelu_bwd_colsum(u, ga, want_bias=True):
     u, ga = u.contiguous(), ga.contiguous()
     M, N = u.shape
     du = torch.empty_like(u)
+    if db_into is not None:           # an fp32 (N,) gradient slot: accumulated into, nothing returned for it
+        if M > 0:
+            _call("d2s_gelu_bwd_colsum_acc_bf16", _ptr(u), _ptr(ga), M, N, _ptr(du), _ptr(db_into), _stream(u))
+        return du, None
     db = torch.zeros(N, dtype=torch.float32, device=u.device) if want_bias else None
     if M > 0:
         _call("d2s_gelu_bwd_colsum_bf16", _ptr(u), _ptr(ga), M, N, _ptr(du), _ptr(db), _stream(u))
@@ -471,6 +576,7 @@ class _LinearGeluTrain(torch.autograd.Function):
             a = F.gelu(u)
         ctx.save_for_backward(xb, wb, u)
         ctx.meta = (x.dtype, w.dtype, None if b is None else b.dtype)
+        ctx.params = (w, b)
         return a
 
     @staticmethod
@@ -482,9 +588,15 @@ class _LinearGeluTrain(torch.autograd.Function):
         if ga2.dtype != torch.bfloat16 or not ga2.is_contiguous():
             ga2 = ga2.to(torch.bfloat16).contiguous()
         want_b = bd is not None and ctx.needs_input_grad[2]
-        du, gb = gelu_bwd_colsum(u.reshape(-1, N), ga2, want_bias=want_b)
+        w_p, b_p = ctx.params
+        slot, e = _grad_slot(b_p) if want_b else (None, None)
+        du, gb = gelu_bwd_colsum(u.reshape(-1, N), ga2, want_bias=want_b, db_into=slot)
+        if e is not None:
+            e[1] = False
         gx = (du @ wb).view(xb.shape).to(xd) if ctx.needs_input_grad[0] else None
-        gw = _wgrad(du, xb.reshape(-1, K), wd) if ctx.needs_input_grad[1] else None
+        gw = None
+        if ctx.needs_input_grad[1] and not _wgrad_into(w_p, du, xb.reshape(-1, K)):
+            gw = _wgrad(du, xb.reshape(-1, K), wd)
         return gx, gw, None if gb is None else gb.to(bd)
 
 
@@ -791,6 +903,18 @@ def patchify_u8(img, ph, pw, mean, std, out_dtype=torch.bfloat16):
 # LayerNorm with autograd (training path)
 # ----------------------------------------------------------------------------------------------
 
+def _ln_grad_targets(ctx, D, dev):
+    """Where the LayerNorm backward accumulates (dgamma, dbeta): the parameters' gradient slots when both have one (nothing is
+    returned to autograd then), else a fresh zeroed pair."""
+    weight, bias = ctx.params
+    (sw, ew), (sb, eb) = _grad_slot(weight), _grad_slot(bias)
+    if sw is not None and sb is not None:
+        ew[1] = eb[1] = False
+        return sw, sb, True
+    dgb = torch.zeros(2, D, dtype=torch.float32, device=dev)
+    return dgb[0], dgb[1], False
+
+
 class _LayerNorm(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, eps, out_dtype):
@@ -804,6 +928,7 @@ class _LayerNorm(torch.autograd.Function):
                   _dtype_code(h), _ptr(stats), _stream(xc))
         ctx.save_for_backward(xc, stats, w)
         ctx.meta = (weight.dtype, bias.dtype)
+        ctx.params = (weight, bias)
         return h
 
     @staticmethod
@@ -813,10 +938,12 @@ class _LayerNorm(torch.autograd.Function):
         rows = xc.numel() // D
         g = dh.contiguous()
         dx = torch.empty_like(xc)
-        dgb = torch.zeros(2, D, dtype=torch.float32, device=xc.device)
+        dg, db, direct = _ln_grad_targets(ctx, D, xc.device)
         _call("d2s_layernorm_bwd", _ptr(g), _dtype_code(g), _ptr(xc), _dtype_code(xc), _ptr(stats), _ptr(w), rows, D,
-                  _ptr(dx), _ptr(dgb[0]), _ptr(dgb[1]), _stream(g))
-        return dx, dgb[0].to(ctx.meta[0]), dgb[1].to(ctx.meta[1]), None, None
+                  _ptr(dx), _ptr(dg), _ptr(db), _stream(g))
+        if direct:
+            return dx, None, None, None, None
+        return dx, dg.to(ctx.meta[0]), db.to(ctx.meta[1]), None, None
 
 
 class _AddLayerNorm(torch.autograd.Function):
@@ -836,6 +963,7 @@ class _AddLayerNorm(torch.autograd.Function):
                   _ptr(h), _dtype_code(h), _ptr(stats), _stream(xc))
         ctx.save_for_backward(s, stats, w)
         ctx.meta = (weight.dtype, bias.dtype)
+        ctx.params = (weight, bias)
         return s, h
 
     @staticmethod
@@ -848,10 +976,12 @@ class _AddLayerNorm(torch.autograd.Function):
         g = gh.contiguous()
         ga = None if gs is None else gs.to(s.dtype).contiguous()
         dx = torch.empty_like(s)
-        dgb = torch.zeros(2, D, dtype=torch.float32, device=s.device)
+        dg, db, direct = _ln_grad_targets(ctx, D, s.device)
         _call("d2s_add_layernorm_bwd", _ptr(g), _dtype_code(g), _ptr(s), _dtype_code(s), _ptr(stats), _ptr(w), _ptr(ga), rows, D,
-                  _ptr(dx), _ptr(dgb[0]), _ptr(dgb[1]), _stream(g))
-        return dx, dx, dgb[0].to(ctx.meta[0]), dgb[1].to(ctx.meta[1]), None, None
+                  _ptr(dx), _ptr(dg), _ptr(db), _stream(g))
+        if direct:
+            return dx, dx, None, None, None, None
+        return dx, dx, dg.to(ctx.meta[0]), db.to(ctx.meta[1]), None, None
 
 
 def add_layer_norm_train(x, y, weight, bias, eps, out_dtype=None):

@@ -158,10 +158,27 @@ int d2s_merge_heads_bf16(const void* src, int B, int T, int Tp, int G, int H, in
 /* Column sums of a bf16 matrix in fp32: out[n] = sum_m dy[m, n] (out is overwritten): the bias gradient of an nn.Linear
  * under autograd (dynamic_vit.py:159-236).  N % 8 == 0, N <= 8192. */
 int d2s_colsum_bf16(const void* dy, long long M, int N, float* out, d2s_stream_t stream);
+/* Same, ACCUMULATING: out[n] += sum_m dy[m, n] -- lands the bias gradient straight in the parameter's gradient slot (what
+ * autograd's AccumulateGrad node does with a second pass, torch/csrc/autograd/functions/accumulate_grad.h). */
+int d2s_colsum_acc_bf16(const void* dy, long long M, int N, float* out, d2s_stream_t stream);
 
 /* GELU backward fused with the bias gradient of the Linear in front of it (Mlp.forward, dynamic_vit.py:170-172), bf16:
  * du (M,N) = ga * gelu'(u) (exact-erf GELU), db (N) f32 = column sums of du (NULL: not wanted; overwritten otherwise). */
 int d2s_gelu_bwd_colsum_bf16(const void* u, const void* ga, long long M, int N, void* du, float* db, d2s_stream_t stream);
+/* Same with db ACCUMULATED into (db += column sums of du). */
+int d2s_gelu_bwd_colsum_acc_bf16(const void* u, const void* ga, long long M, int N, void* du, float* db, d2s_stream_t stream);
+
+/* AdamW over the slice [begin, end) of flat fp32 buffers p (parameters), g (gradients), m, v (moments), all of one layout:
+ * the optimizer.step() of the training loop (train.py:63-66; the reference builds torch/timm AdamW in mask_predictor.py and
+ * ddp_training.py), decoupled weight decay, bias correction from the step count:
+ *   g' = g * grad_scale;  p *= 1 - lr*wd;  m += (g'-m)(1-beta1);  v = v*beta2 + (1-beta2) g'^2;
+ *   p -= lr/(1-beta1^t) * m / (sqrt(v)/sqrt(1-beta2^t) + eps)
+ * lr and t (the 1-based step count, as a float) are read from DEVICE memory so a captured CUDA graph serves every step.
+ * shadow_bf16 (same layout, NULL: none) receives the updated parameters rounded to bf16 -- the copy the next forward's GEMMs
+ * read.  One launch per parameter group (its own lr pointer / weight decay). */
+int d2s_adamw_flat_f32(float* p, const float* g, float* m, float* v, void* shadow_bf16, long long begin, long long end,
+                       const float* lr, const float* step, float beta1, float beta2, float eps, float weight_decay,
+                       float grad_scale, d2s_stream_t stream);
 
 /* Fused attention core of Attention.forward (dynamic_vit.py:218-234; default_dynamic_vit.py:203-213):
  * qkv (B,T,3,H,hd) packed as produced by the qkv Linear; out (B,T,H*hd) ready for the proj Linear;

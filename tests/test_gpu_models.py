@@ -449,15 +449,21 @@ def test_graphed_training_step_matches_eager(d2s, cuda_dev):
         p.requires_grad_(False)
     gumbels = [fx.randn(51 + i, 4, 196, 2).to(cuda_dev) for i in range(2)]
     losses = {}
-    for mode in ("eager", "graph", "graph_flat"):
+    for mode in ("eager", "graph", "graph_flat", "graph_flat_adamw"):
         m = copy.deepcopy(base).train()
         m._d2s_gumbels = gumbels
         crit = d2s.losses.DistillDiffPruningLoss(teacher, keep_ratio=[0.7, 0.49])
-        opt = torch.optim.AdamW(m.parameters(), lr=1e-4, weight_decay=0.05, capturable=True)
-        # graph_flat: what bench.py's training leg runs -- gradients as views of one flat buffer (the data-parallel all-reduce
-        # target) and per-step bf16 weight copies refreshed by one multi-tensor copy after the optimizer step
-        grads = d2s.runner.FlatGrads(m.parameters()) if mode == "graph_flat" else None
-        cache = d2s.ops.BF16WeightCache(m.parameters()) if mode == "graph_flat" else None
+        # graph_flat: gradients as views of one flat buffer (the data-parallel all-reduce target, written in place by the d2s
+        # training nodes) and per-step bf16 weight copies refreshed by one multi-tensor copy after torch's AdamW
+        # graph_flat_adamw: what bench.py's training leg runs -- the flat d2s AdamW kernel, which owns the flat gradients and
+        # writes the bf16 weight copies itself
+        if mode == "graph_flat_adamw":
+            opt = d2s.runner.FlatAdamW(m.parameters(), lr=1e-4, weight_decay=0.05)
+            grads, cache = opt.grads, opt.weight_cache
+        else:
+            opt = torch.optim.AdamW(m.parameters(), lr=1e-4, weight_decay=0.05, capturable=True)
+            grads = d2s.runner.FlatGrads(m.parameters()) if mode == "graph_flat" else None
+            cache = d2s.ops.BF16WeightCache(m.parameters()) if mode == "graph_flat" else None
 
         def fwd_loss(xx, yy, m=m, crit=crit):
             with torch.autocast("cuda", dtype=torch.bfloat16):
@@ -470,10 +476,85 @@ def test_graphed_training_step_matches_eager(d2s, cuda_dev):
                 assert torch.equal(d_, p_.detach().to(torch.bfloat16))          # the copies follow the optimizer
             cache.close()
             assert d2s.ops.BF16WeightCache.lookup(cache.src[0]) is None
-    for mode in ("graph", "graph_flat"):
+        if grads is not None:
+            grads.close()
+    for mode in ("graph", "graph_flat", "graph_flat_adamw"):
         for a, b in zip(losses["eager"], losses[mode]):
             assert abs(a - b) <= 2e-2 * abs(a) + 1e-3, losses
     assert losses["graph"][-1] != losses["graph"][0]          # the replays really update the weights
+
+
+def test_flat_adamw_follows_torch_adamw(d2s, cuda_dev):
+    """runner.FlatAdamW (one d2s kernel per parameter group over flat buffers) against torch.optim.AdamW on the same parameters
+    and gradients: two groups with their own lr / weight decay, sizes that are not multiples of the vector width, an lr change
+    between steps; the bf16 copies equal the rounded parameters; parameters keep their identity (re-pointed, not replaced)."""
+    shapes = [(37, 5), (1,), (384,), (129, 64), (3,), (1000, 7)]
+    mine = [torch.nn.Parameter(fx.randn(300 + i, *sh).to(cuda_dev)) for i, sh in enumerate(shapes)]
+    ref = [torch.nn.Parameter(p.detach().clone()) for p in mine]
+    groups = lambda ps: [dict(params=ps[:3], lr=3e-3, weight_decay=0.0), dict(params=ps[3:], lr=1e-3, weight_decay=0.1)]
+    opt = d2s.runner.FlatAdamW(groups(mine), betas=(0.9, 0.98), eps=1e-8)
+    topt = torch.optim.AdamW(groups(ref), betas=(0.9, 0.98), eps=1e-8)
+    assert all(p.data_ptr() % 16 == 0 for p in mine) and opt.weight_cache is not None
+    for step in range(6):
+        if step == 3:
+            for o in (opt, topt):
+                o.param_groups[1]["lr"] = 5e-4
+        opt.zero_grad()
+        for i, (p, q) in enumerate(zip(mine, ref)):
+            g = fx.randn(400 + 10 * step + i, *p.shape).to(cuda_dev) * (0.1 + i)
+            p.grad.add_(g)                      # into the flat slot, as autograd's accumulate does
+            q.grad = g.clone()
+        opt.step()
+        topt.step()
+        for p, q in zip(mine, ref):
+            torch.testing.assert_close(p.detach(), q.detach(), rtol=2e-6, atol=2e-7)
+            assert torch.equal(d2s.ops.BF16WeightCache.lookup(p), p.detach().to(torch.bfloat16))
+    assert float(opt.step_t) == 6.0
+    opt.close()
+    assert d2s.ops.BF16WeightCache.lookup(mine[0]) is None
+
+
+def test_gradient_slots_receive_what_autograd_would_accumulate(d2s, cuda_dev):
+    """With runner.FlatGrads the d2s training nodes (Linear, Linear + GELU, LayerNorm, add + LayerNorm) write their parameter
+    gradients straight into the flat buffer and return nothing to autograd; the buffer must hold what autograd's own accumulate
+    pass leaves in .grad -- also for a second backward without zero() in between (accumulation) and for a parameter used
+    twice in one graph."""
+    import copy
+    torch.manual_seed(5)
+    D = 128
+    net = torch.nn.ModuleDict(dict(ln1=torch.nn.LayerNorm(D), fc1=torch.nn.Linear(D, 256), act=torch.nn.GELU(),
+                                   fc2=torch.nn.Linear(256, D), ln2=torch.nn.LayerNorm(D), head=torch.nn.Linear(D, 16))).to(cuda_dev)
+    x = fx.randn(71, 6, 50, D).to(cuda_dev)
+
+    def loss_of(n):
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            h = d2s.ops.layer_norm(x, n["ln1"].weight, n["ln1"].bias, 1e-5)
+            a = d2s.ops.linear_gelu_train(n["fc1"], n["act"], h)
+            y = d2s.ops.linear_train(n["fc2"], a)
+            s, h2 = d2s.ops.add_layer_norm_train(x.to(y.dtype), y, n["ln2"].weight, n["ln2"].bias, 1e-5)
+            o = d2s.ops.linear_train(n["head"], h2) + d2s.ops.linear_train(n["head"], s)      # head used twice
+            return (o.float() ** 2).mean() + s.float().mean()
+    ref = copy.deepcopy(net)
+    for _ in range(2):                                        # two backward passes accumulate
+        loss_of(ref).backward()
+    fg = d2s.runner.FlatGrads(net.parameters())
+    views = [p.grad for p in net.parameters()]
+    for _ in range(2):
+        loss_of(net).backward()
+    for (name, p), q, v in zip(net.named_parameters(), ref.parameters(), views):
+        assert p.grad is v, name                              # still the flat view
+        torch.testing.assert_close(p.grad, q.grad, rtol=2e-3, atol=2e-5 * float(q.grad.abs().max()) + 1e-7, msg=name)
+    fg.zero()
+    assert float(fg.flat.abs().max()) == 0.0
+    loss_of(net).backward()                                   # after zero(): one pass worth again
+    one = copy.deepcopy(net)
+    for p in one.parameters():
+        p.grad = None
+    d2s.ops.unregister_grad_slots(list(net.parameters()))
+    loss_of(one).backward()
+    for (name, p), q in zip(net.named_parameters(), one.parameters()):
+        torch.testing.assert_close(p.grad, q.grad, rtol=2e-3, atol=2e-5 * float(q.grad.abs().max()) + 1e-7, msg=name)
+    fg.close()
 
 
 def test_fused_path_keeps_the_reference_token_sets_when_margins_allow(d2s, cuda_dev):
