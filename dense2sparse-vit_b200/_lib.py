@@ -50,11 +50,15 @@ SIGNATURES = {
     "d2s_pool_act": [_p, _p, _i, _i, _i, _i, _i, _p, _p, _p],
     "d2s_bias_act": [_p, _p, _i, ctypes.c_longlong, _i, _i, _i, _p],
     "d2s_pool_concat_inplace": [_p, _i, _i, _i, _i, _p],
+    "d2s_pool_concat_fwd": [_p, _p, _i, _i, _i, _i, _p, _p, _p, _p],
+    "d2s_pool_concat_bwd": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p],
     "d2s_assemble_tokens": [_p, _p, _p, _i, _i, _i, _i, _p, _p],
     "d2s_patchify": [_p, _i, _i, _i, _i, _i, _i, _i, _p, _p],
     "d2s_patchify_u8": [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p],
     "d2s_layernorm_fwd": [_p, _i, _p, _p, ctypes.c_longlong, _i, _f, _p, _i, _p, _p],
     "d2s_layernorm_bwd": [_p, _i, _p, _i, _p, _p, ctypes.c_longlong, _i, _p, _p, _p, _p],
+    "d2s_layernorm_seg_fwd": [_p, _i, _p, _p, ctypes.c_longlong, _i, _i, _i, _f, _p, _i, _p, _p],
+    "d2s_layernorm_seg_bwd": [_p, _i, _p, _i, _p, _p, ctypes.c_longlong, _i, _i, _i, _p, _p, _p, _p],
     "d2s_add_layernorm_fwd": [_p, _p, _i, _p, _p, ctypes.c_longlong, _i, _f, _p, _p, _i, _p, _p],
     "d2s_add_layernorm_bwd": [_p, _i, _p, _i, _p, _p, _p, ctypes.c_longlong, _i, _p, _p, _p, _p],
     "d2s_linear_act_pair_bf16": [_p, _p, _p, _i, _i, _i, _i, _p, _p, _p],

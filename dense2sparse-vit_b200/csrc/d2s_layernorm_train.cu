@@ -48,6 +48,12 @@ template <> struct TV<float> {   // 8 floats = two 16-byte vectors, so both dtyp
   __device__ static float round(float f) { return f; }
 };
 
+// LayerNorm over rows `skip`.. of every (seg + skip)-row segment of x (the predictors normalise x[:, 1:], default_dynamic_vit.py
+// :461 / dynamic_vit.py:846): dense row r of the output <-> row r + (r / seg + 1) * skip of x.  seg == 0: identity.
+__device__ __forceinline__ long long seg_row(long long row, int seg, int skip) {
+  return seg > 0 ? row + (row / seg + 1) * skip : row;
+}
+
 __device__ __forceinline__ float hw_sum(float v) {
 #pragma unroll
   for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -59,10 +65,11 @@ template <typename TX, typename TH, int kVPL>
 __global__ void __launch_bounds__(kLtThreads)
 ln_fwd_kernel(const TX* __restrict__ x, const TX* __restrict__ res, const float* __restrict__ gamma,
               const float* __restrict__ beta, long long rows, int D, float eps, TX* __restrict__ out_sum, TH* __restrict__ h,
-              float* __restrict__ stats) {
+              float* __restrict__ stats, int seg, int skip) {
   const int sub = threadIdx.x & 15;
   const long long row = (long long)blockIdx.x * kLtRowsPerIter + (threadIdx.x >> 4);
   const bool ok = row < rows;
+  const long long xrow = seg_row(row, seg, skip);      // x / res / out_sum live in the segmented layout, h and stats are dense
   const int nvec = D / 8;
   float v[kVPL][8];
   float sum = 0.f;
@@ -70,13 +77,13 @@ ln_fwd_kernel(const TX* __restrict__ x, const TX* __restrict__ res, const float*
   for (int k = 0; k < kVPL; ++k) {
     const int vi = sub + 16 * k;
     if (ok && vi < nvec) {
-      TV<TX>::load(x + row * D + vi * 8, v[k]);
+      TV<TX>::load(x + xrow * D + vi * 8, v[k]);
       if (res) {   // residual add folded in: s = x + res rounded to the stream's dtype (what torch's add would store), kept
         float r[8];
-        TV<TX>::load(res + row * D + vi * 8, r);
+        TV<TX>::load(res + xrow * D + vi * 8, r);
 #pragma unroll
         for (int q = 0; q < 8; ++q) v[k][q] = TV<TX>::round(v[k][q] + r[q]);
-        TV<TX>::store(out_sum + row * D + vi * 8, v[k]);
+        TV<TX>::store(out_sum + xrow * D + vi * 8, v[k]);
       }
 #pragma unroll
       for (int q = 0; q < 8; ++q) sum += v[k][q];
@@ -115,7 +122,7 @@ template <typename TX, typename TH, int kVPL>
 __global__ void __launch_bounds__(kLtBwdThreads)
 ln_bwd_kernel(const TH* __restrict__ dh, const TX* __restrict__ x, const float* __restrict__ stats,
               const float* __restrict__ gamma, const TX* __restrict__ gadd, long long rows, int D, TX* __restrict__ dx,
-              float* __restrict__ dgamma, float* __restrict__ dbeta) {
+              float* __restrict__ dgamma, float* __restrict__ dbeta, int seg, int skip) {
   extern __shared__ float red[];   // (half-warps per CTA) x D partial column sums
   const int sub = threadIdx.x & 15;
   const int nvec = D / 8;
@@ -133,6 +140,7 @@ ln_bwd_kernel(const TH* __restrict__ dh, const TX* __restrict__ x, const float* 
     const long long row = row0 + (threadIdx.x >> 4);
     const bool ok = row < row_end;
     const float mean = ok ? stats[row * 2] : 0.f, rstd = ok ? stats[row * 2 + 1] : 0.f;
+    const long long xrow = seg_row(row, seg, skip);    // x / gadd / dx: segmented layout; dh and stats: dense
     float xh[kVPL][8], gg[kVPL][8];
     float s1 = 0.f, s2 = 0.f;
     // the residual-stream gradient is fetched together with x and dh (raw 16-byte words, unpacked at the end): issued only
@@ -143,7 +151,7 @@ ln_bwd_kernel(const TH* __restrict__ dh, const TX* __restrict__ x, const float* 
       for (int k = 0; k < kVPL; ++k) {
         const int vi = sub + 16 * k;
         if (ok && vi < nvec) {
-          const int4* gp = reinterpret_cast<const int4*>(gadd + row * D + vi * 8);
+          const int4* gp = reinterpret_cast<const int4*>(gadd + xrow * D + vi * 8);
           ga_raw[k][0] = gp[0];
           if (sizeof(TX) == 4) ga_raw[k][sizeof(TX) == 2 ? 0 : 1] = gp[1];
         }
@@ -154,7 +162,7 @@ ln_bwd_kernel(const TH* __restrict__ dh, const TX* __restrict__ x, const float* 
       const int vi = sub + 16 * k;
       if (ok && vi < nvec) {
         float xv[8], dv[8];
-        TV<TX>::load(x + row * D + vi * 8, xv);
+        TV<TX>::load(x + xrow * D + vi * 8, xv);
         TV<TH>::load(dh + row * D + vi * 8, dv);
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
@@ -186,7 +194,19 @@ ln_bwd_kernel(const TH* __restrict__ dh, const TX* __restrict__ x, const float* 
 #pragma unroll
             for (int q = 0; q < 8; ++q) o[q] += ga[q];
           }
-          TV<TX>::store(dx + row * D + vi * 8, o);
+          TV<TX>::store(dx + xrow * D + vi * 8, o);
+          if (seg > 0 && row % seg == 0) {     // the rows the LayerNorm skipped receive no gradient from it: zero (or gadd's)
+#pragma unroll
+            for (int s = 1; s <= skip; ++s) {
+              float z[8];
+              if (gadd) TV<TX>::load(gadd + (xrow - s) * D + vi * 8, z);
+              else {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) z[q] = 0.f;
+              }
+              TV<TX>::store(dx + (xrow - s) * D + vi * 8, z);
+            }
+          }
         }
       }
     }
@@ -218,22 +238,22 @@ ln_bwd_kernel(const TH* __restrict__ dh, const TX* __restrict__ x, const float* 
 
 template <typename TX, typename TH>
 static int ln_fwd_launch(const void* x, const void* res, const float* gamma, const float* beta, long long rows, int D, float eps,
-                         void* out_sum, void* h, float* stats, cudaStream_t st) {
+                         void* out_sum, void* h, float* stats, int seg, int skip, cudaStream_t st) {
   const int vpl = ceil_div(D / 8, 16);
   const unsigned grid = (unsigned)((rows + kLtRowsPerIter - 1) / kLtRowsPerIter);
-  if (vpl <= 3) ln_fwd_kernel<TX, TH, 3><<<grid, kLtThreads, 0, st>>>((const TX*)x, (const TX*)res, gamma, beta, rows, D, eps, (TX*)out_sum, (TH*)h, stats);
-  else          ln_fwd_kernel<TX, TH, 6><<<grid, kLtThreads, 0, st>>>((const TX*)x, (const TX*)res, gamma, beta, rows, D, eps, (TX*)out_sum, (TH*)h, stats);
+  if (vpl <= 3) ln_fwd_kernel<TX, TH, 3><<<grid, kLtThreads, 0, st>>>((const TX*)x, (const TX*)res, gamma, beta, rows, D, eps, (TX*)out_sum, (TH*)h, stats, seg, skip);
+  else          ln_fwd_kernel<TX, TH, 6><<<grid, kLtThreads, 0, st>>>((const TX*)x, (const TX*)res, gamma, beta, rows, D, eps, (TX*)out_sum, (TH*)h, stats, seg, skip);
   count_launch();
   return check_launch("d2s_layernorm_fwd");
 }
 template <typename TX, typename TH>
 static int ln_bwd_launch(const void* dh, const void* x, const float* stats, const float* gamma, const void* gadd, long long rows,
-                         int D, void* dx, float* dgamma, float* dbeta, cudaStream_t st) {
+                         int D, void* dx, float* dgamma, float* dbeta, int seg, int skip, cudaStream_t st) {
   const int vpl = ceil_div(D / 8, 16);
   const unsigned grid = (unsigned)((rows + kLtRowsPerCta - 1) / kLtRowsPerCta);
   const size_t smem = (size_t)kLtBwdRowsPerIter * D * sizeof(float);
-  if (vpl <= 3) ln_bwd_kernel<TX, TH, 3><<<grid, kLtBwdThreads, smem, st>>>((const TH*)dh, (const TX*)x, stats, gamma, (const TX*)gadd, rows, D, (TX*)dx, dgamma, dbeta);
-  else          ln_bwd_kernel<TX, TH, 6><<<grid, kLtBwdThreads, smem, st>>>((const TH*)dh, (const TX*)x, stats, gamma, (const TX*)gadd, rows, D, (TX*)dx, dgamma, dbeta);
+  if (vpl <= 3) ln_bwd_kernel<TX, TH, 3><<<grid, kLtBwdThreads, smem, st>>>((const TH*)dh, (const TX*)x, stats, gamma, (const TX*)gadd, rows, D, (TX*)dx, dgamma, dbeta, seg, skip);
+  else          ln_bwd_kernel<TX, TH, 6><<<grid, kLtBwdThreads, smem, st>>>((const TH*)dh, (const TX*)x, stats, gamma, (const TX*)gadd, rows, D, (TX*)dx, dgamma, dbeta, seg, skip);
   count_launch();
   return check_launch("d2s_layernorm_bwd");
 }
@@ -249,44 +269,65 @@ static int ln_check(const char* what, long long rows, int D, int dx, int dh) {
 using namespace d2s;
 
 static int ln_fwd_entry(const char* what, const void* x, const void* res, int x_dtype, const float* gamma, const float* beta,
-                        long long rows, int D, float eps, void* out_sum, void* h, int h_dtype, float* stats, d2s_stream_t stream) {
+                        long long rows, int D, float eps, void* out_sum, void* h, int h_dtype, float* stats, int seg, int skip,
+                        d2s_stream_t stream) {
   D2S_REQUIRE(x && gamma && beta && h && stats && (!res || out_sum), D2S_ERR_ARG, "%s: null pointer", what);
+  D2S_REQUIRE(seg >= 0 && skip >= 0 && (seg == 0 || rows % seg == 0), D2S_ERR_ARG, "%s: rows=%lld must be whole segments of %d rows", what,
+              rows, seg);
   int rc = ln_check(what, rows, D, x_dtype, h_dtype);
   if (rc) return rc;
   D2S_REQUIRE(aligned16(x) && aligned16(h) && aligned16(gamma) && aligned16(beta) && (!res || (aligned16(res) && aligned16(out_sum))),
               D2S_ERR_ALIGN, "%s: 16-byte alignment", what);
   if (rows == 0) return D2S_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  if (x_dtype == D2S_F32 && h_dtype == D2S_BF16) return ln_fwd_launch<float, __nv_bfloat16>(x, res, gamma, beta, rows, D, eps, out_sum, h, stats, st);
-  if (x_dtype == D2S_F32 && h_dtype == D2S_F32) return ln_fwd_launch<float, float>(x, res, gamma, beta, rows, D, eps, out_sum, h, stats, st);
-  if (x_dtype == D2S_BF16 && h_dtype == D2S_BF16) return ln_fwd_launch<__nv_bfloat16, __nv_bfloat16>(x, res, gamma, beta, rows, D, eps, out_sum, h, stats, st);
-  return ln_fwd_launch<__nv_bfloat16, float>(x, res, gamma, beta, rows, D, eps, out_sum, h, stats, st);
+  if (x_dtype == D2S_F32 && h_dtype == D2S_BF16) return ln_fwd_launch<float, __nv_bfloat16>(x, res, gamma, beta, rows, D, eps, out_sum, h, stats, seg, skip, st);
+  if (x_dtype == D2S_F32 && h_dtype == D2S_F32) return ln_fwd_launch<float, float>(x, res, gamma, beta, rows, D, eps, out_sum, h, stats, seg, skip, st);
+  if (x_dtype == D2S_BF16 && h_dtype == D2S_BF16) return ln_fwd_launch<__nv_bfloat16, __nv_bfloat16>(x, res, gamma, beta, rows, D, eps, out_sum, h, stats, seg, skip, st);
+  return ln_fwd_launch<__nv_bfloat16, float>(x, res, gamma, beta, rows, D, eps, out_sum, h, stats, seg, skip, st);
 }
 
 static int ln_bwd_entry(const char* what, const void* dh, int h_dtype, const void* x, int x_dtype, const float* stats,
                         const float* gamma, const void* gadd, long long rows, int D, void* dx, float* dgamma, float* dbeta,
-                        d2s_stream_t stream) {
+                        int seg, int skip, d2s_stream_t stream) {
   D2S_REQUIRE(dh && x && stats && gamma && dx && dgamma && dbeta, D2S_ERR_ARG, "%s: null pointer", what);
+  D2S_REQUIRE(seg >= 0 && skip >= 0, D2S_ERR_ARG, "%s: bad segments", what);
+  D2S_REQUIRE(seg == 0 || rows % seg == 0, D2S_ERR_ARG, "%s: rows=%lld must be whole segments of %d rows", what, rows, seg);
   int rc = ln_check(what, rows, D, x_dtype, h_dtype);
   if (rc) return rc;
   D2S_REQUIRE(aligned16(dh) && aligned16(x) && aligned16(dx) && aligned16(gamma) && (!gadd || aligned16(gadd)), D2S_ERR_ALIGN,
               "%s: 16-byte alignment", what);
   if (rows == 0) return D2S_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  if (x_dtype == D2S_F32 && h_dtype == D2S_BF16) return ln_bwd_launch<float, __nv_bfloat16>(dh, x, stats, gamma, gadd, rows, D, dx, dgamma, dbeta, st);
-  if (x_dtype == D2S_F32 && h_dtype == D2S_F32) return ln_bwd_launch<float, float>(dh, x, stats, gamma, gadd, rows, D, dx, dgamma, dbeta, st);
-  if (x_dtype == D2S_BF16 && h_dtype == D2S_BF16) return ln_bwd_launch<__nv_bfloat16, __nv_bfloat16>(dh, x, stats, gamma, gadd, rows, D, dx, dgamma, dbeta, st);
-  return ln_bwd_launch<__nv_bfloat16, float>(dh, x, stats, gamma, gadd, rows, D, dx, dgamma, dbeta, st);
+  if (x_dtype == D2S_F32 && h_dtype == D2S_BF16) return ln_bwd_launch<float, __nv_bfloat16>(dh, x, stats, gamma, gadd, rows, D, dx, dgamma, dbeta, seg, skip, st);
+  if (x_dtype == D2S_F32 && h_dtype == D2S_F32) return ln_bwd_launch<float, float>(dh, x, stats, gamma, gadd, rows, D, dx, dgamma, dbeta, seg, skip, st);
+  if (x_dtype == D2S_BF16 && h_dtype == D2S_BF16) return ln_bwd_launch<__nv_bfloat16, __nv_bfloat16>(dh, x, stats, gamma, gadd, rows, D, dx, dgamma, dbeta, seg, skip, st);
+  return ln_bwd_launch<__nv_bfloat16, float>(dh, x, stats, gamma, gadd, rows, D, dx, dgamma, dbeta, seg, skip, st);
 }
 
 extern "C" int d2s_layernorm_fwd(const void* x, int x_dtype, const float* gamma, const float* beta, long long rows, int D,
                                  float eps, void* h, int h_dtype, float* stats, d2s_stream_t stream) {
-  return ln_fwd_entry("layernorm_fwd", x, nullptr, x_dtype, gamma, beta, rows, D, eps, nullptr, h, h_dtype, stats, stream);
+  return ln_fwd_entry("layernorm_fwd", x, nullptr, x_dtype, gamma, beta, rows, D, eps, nullptr, h, h_dtype, stats, 0, 0, stream);
+}
+
+// The same over rows `skip`.. of every (seg + skip)-row segment of x (LayerNorm(x[:, 1:]) without the slice copy): h and stats
+// are dense over the rows = n_segments * seg normalised rows.
+extern "C" int d2s_layernorm_seg_fwd(const void* x, int x_dtype, const float* gamma, const float* beta, long long rows, int D,
+                                     int seg, int skip, float eps, void* h, int h_dtype, float* stats, d2s_stream_t stream) {
+  D2S_REQUIRE(seg > 0, D2S_ERR_ARG, "layernorm_seg_fwd: seg=%d must be positive", seg);
+  return ln_fwd_entry("layernorm_seg_fwd", x, nullptr, x_dtype, gamma, beta, rows, D, eps, nullptr, h, h_dtype, stats, seg, skip, stream);
 }
 
 extern "C" int d2s_layernorm_bwd(const void* dh, int h_dtype, const void* x, int x_dtype, const float* stats, const float* gamma,
                                  long long rows, int D, void* dx, float* dgamma, float* dbeta, d2s_stream_t stream) {
-  return ln_bwd_entry("layernorm_bwd", dh, h_dtype, x, x_dtype, stats, gamma, nullptr, rows, D, dx, dgamma, dbeta, stream);
+  return ln_bwd_entry("layernorm_bwd", dh, h_dtype, x, x_dtype, stats, gamma, nullptr, rows, D, dx, dgamma, dbeta, 0, 0, stream);
+}
+
+// Backward of d2s_layernorm_seg_fwd: dx has x's segmented layout; the skipped rows of every segment are written as zeros.
+extern "C" int d2s_layernorm_seg_bwd(const void* dh, int h_dtype, const void* x, int x_dtype, const float* stats, const float* gamma,
+                                     long long rows, int D, int seg, int skip, void* dx, float* dgamma, float* dbeta,
+                                     d2s_stream_t stream) {
+  D2S_REQUIRE(seg > 0, D2S_ERR_ARG, "layernorm_seg_bwd: seg=%d must be positive", seg);
+  return ln_bwd_entry("layernorm_seg_bwd", dh, h_dtype, x, x_dtype, stats, gamma, nullptr, rows, D, dx, dgamma, dbeta, seg, skip, stream);
 }
 
 // Residual add folded into the LayerNorm that follows it, with autograd (Block.forward, dynamic_vit.py:276-283: x = x + branch;
@@ -297,11 +338,11 @@ extern "C" int d2s_add_layernorm_fwd(const void* x, const void* res, int x_dtype
                                      long long rows, int D, float eps, void* out_sum, void* h, int h_dtype, float* stats,
                                      d2s_stream_t stream) {
   D2S_REQUIRE(res && out_sum, D2S_ERR_ARG, "add_layernorm_fwd: null pointer");
-  return ln_fwd_entry("add_layernorm_fwd", x, res, x_dtype, gamma, beta, rows, D, eps, out_sum, h, h_dtype, stats, stream);
+  return ln_fwd_entry("add_layernorm_fwd", x, res, x_dtype, gamma, beta, rows, D, eps, out_sum, h, h_dtype, stats, 0, 0, stream);
 }
 
 extern "C" int d2s_add_layernorm_bwd(const void* dh, int h_dtype, const void* xsum, int x_dtype, const float* stats,
                                      const float* gamma, const void* gsum, long long rows, int D, void* dx, float* dgamma,
                                      float* dbeta, d2s_stream_t stream) {
-  return ln_bwd_entry("add_layernorm_bwd", dh, h_dtype, xsum, x_dtype, stats, gamma, gsum, rows, D, dx, dgamma, dbeta, stream);
+  return ln_bwd_entry("add_layernorm_bwd", dh, h_dtype, xsum, x_dtype, stats, gamma, gsum, rows, D, dx, dgamma, dbeta, 0, 0, stream);
 }

@@ -260,6 +260,183 @@ act_flat_kernel(T_* __restrict__ u, long long nvec_total, int act) {
   }
 }
 
+
+// ---- training form of the predictors' local / global split (PredictorLG.forward, default_dynamic_vit.py:326-329 with the keep
+// policy, dynamic_vit.py:541-545 with a plain mean) as one kernel each way instead of slice, multiply, sum, divide, expand, cat
+// and their six autograd nodes:
+//     out[b, n, :half] = h[b, n, :half]            pooled[b, c] = sum_n w[b, n] h[b, n, half + c] / sum_n w[b, n]
+//     out[b, n, half + c] = pooled[b, c]           (w = policy, or 1 when policy is NULL)
+// backward, with G[b, c] = sum_n dout[b, n, half + c] and S = sum_n w[b, n]:
+//     dh[b, n, :half] = dout[b, n, :half]          dh[b, n, half + c] = w[b, n] G[b, c] / S
+//     dpolicy[b, n] = sum_c (h[b, n, half + c] - pooled[b, c]) G[b, c] / S
+// One CTA per image; a warp owns a row at a time (lane l: 16-byte vectors l, l + 32, .. of the half row), so the per-row dot
+// product of the backward is a warp reduction.  Sums in fp32, one rounding at the end.
+constexpr int kPtWarps = 8;
+constexpr int kPtMaxK = 3;          // half-row vectors per lane: C/2 <= 3 * 32 * (8 | 4) elements
+
+template <typename T_>
+__global__ void __launch_bounds__(kPtWarps * 32)
+pool_concat_fwd_kernel(const T_* __restrict__ h, const float* __restrict__ policy, int N, int C, T_* __restrict__ out,
+                       float* __restrict__ pooled, float* __restrict__ wsum) {
+  constexpr int VE = PVec<T_>::kElems;
+  extern __shared__ float pt_red[];          // kPtWarps x half partial sums, then the pooled row in slot 0
+  __shared__ float ws_red[kPtWarps];
+  const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int half = C / 2, hvec = half / VE;
+  const T_* hb = h + (size_t)b * N * C;
+  T_* ob = out + (size_t)b * N * C;
+  float acc[kPtMaxK][8];
+#pragma unroll
+  for (int k = 0; k < kPtMaxK; ++k)
+#pragma unroll
+    for (int q = 0; q < 8; ++q) acc[k][q] = 0.f;
+  float ws = 0.f;
+  for (int n = warp; n < N; n += kPtWarps) {
+    const float w = policy ? policy[(size_t)b * N + n] : 1.f;
+    ws += w;
+#pragma unroll
+    for (int k = 0; k < kPtMaxK; ++k) {
+      const int v = lane + 32 * k;
+      if (v < hvec) {
+        const int4 loc = *reinterpret_cast<const int4*>(hb + (size_t)n * C + (size_t)v * VE);
+        const int4 glo = *reinterpret_cast<const int4*>(hb + (size_t)n * C + half + (size_t)v * VE);
+        *reinterpret_cast<int4*>(ob + (size_t)n * C + (size_t)v * VE) = loc;
+        float x[8];
+        PVec<T_>::unpack(glo, x);
+#pragma unroll
+        for (int q = 0; q < VE; ++q) acc[k][q] = fmaf(w, x[q], acc[k][q]);
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < kPtMaxK; ++k) {
+    const int v = lane + 32 * k;
+    if (v < hvec) {
+#pragma unroll
+      for (int q = 0; q < VE; ++q) pt_red[(size_t)warp * half + (size_t)v * VE + q] = acc[k][q];
+    }
+  }
+  if (lane == 0) ws_red[warp] = ws;          // every lane of a warp holds the same row-weight sum
+  __syncthreads();
+  float S = 0.f;
+#pragma unroll
+  for (int w = 0; w < kPtWarps; ++w) S += ws_red[w];
+  __syncthreads();
+  for (int c = threadIdx.x; c < half; c += kPtWarps * 32) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < kPtWarps; ++w) t += pt_red[(size_t)w * half + c];
+    t /= S;
+    pooled[(size_t)b * half + c] = t;
+    pt_red[(size_t)kPtWarps * half + c] = t;
+  }
+  if (threadIdx.x == 0) wsum[b] = S;
+  __syncthreads();
+  int4 packed[kPtMaxK];
+#pragma unroll
+  for (int k = 0; k < kPtMaxK; ++k) {
+    const int v = lane + 32 * k;
+    if (v < hvec) {
+      float m[8];
+#pragma unroll
+      for (int q = 0; q < VE; ++q) m[q] = pt_red[(size_t)kPtWarps * half + (size_t)v * VE + q];
+      packed[k] = PVec<T_>::pack(m);
+    }
+  }
+  for (int n = warp; n < N; n += kPtWarps)
+#pragma unroll
+    for (int k = 0; k < kPtMaxK; ++k) {
+      const int v = lane + 32 * k;
+      if (v < hvec) *reinterpret_cast<int4*>(ob + (size_t)n * C + half + (size_t)v * VE) = packed[k];
+    }
+}
+
+template <typename T_>
+__global__ void __launch_bounds__(kPtWarps * 32)
+pool_concat_bwd_kernel(const T_* __restrict__ dout, const T_* __restrict__ h, const float* __restrict__ policy,
+                       const float* __restrict__ pooled, const float* __restrict__ wsum, int N, int C, T_* __restrict__ dh,
+                       float* __restrict__ dpolicy) {
+  constexpr int VE = PVec<T_>::kElems;
+  extern __shared__ float pt_red[];          // kPtWarps x half partial sums, then G / S in slot kPtWarps
+  const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int half = C / 2, hvec = half / VE;
+  const T_* gb = dout + (size_t)b * N * C;
+  const T_* hb = h + (size_t)b * N * C;
+  T_* db = dh + (size_t)b * N * C;
+  float acc[kPtMaxK][8];
+#pragma unroll
+  for (int k = 0; k < kPtMaxK; ++k)
+#pragma unroll
+    for (int q = 0; q < 8; ++q) acc[k][q] = 0.f;
+  for (int n = warp; n < N; n += kPtWarps) {
+#pragma unroll
+    for (int k = 0; k < kPtMaxK; ++k) {
+      const int v = lane + 32 * k;
+      if (v < hvec) {
+        const int4 loc = *reinterpret_cast<const int4*>(gb + (size_t)n * C + (size_t)v * VE);
+        const int4 glo = *reinterpret_cast<const int4*>(gb + (size_t)n * C + half + (size_t)v * VE);
+        *reinterpret_cast<int4*>(db + (size_t)n * C + (size_t)v * VE) = loc;
+        float x[8];
+        PVec<T_>::unpack(glo, x);
+#pragma unroll
+        for (int q = 0; q < VE; ++q) acc[k][q] += x[q];
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < kPtMaxK; ++k) {
+    const int v = lane + 32 * k;
+    if (v < hvec) {
+#pragma unroll
+      for (int q = 0; q < VE; ++q) pt_red[(size_t)warp * half + (size_t)v * VE + q] = acc[k][q];
+    }
+  }
+  __syncthreads();
+  const float invS = 1.f / wsum[b];
+  for (int c = threadIdx.x; c < half; c += kPtWarps * 32) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < kPtWarps; ++w) t += pt_red[(size_t)w * half + c];
+    pt_red[(size_t)kPtWarps * half + c] = t * invS;                       // G / S
+  }
+  __syncthreads();
+  float gs[kPtMaxK][8], pm[kPtMaxK][8];
+#pragma unroll
+  for (int k = 0; k < kPtMaxK; ++k) {
+    const int v = lane + 32 * k;
+#pragma unroll
+    for (int q = 0; q < VE; ++q) {
+      gs[k][q] = v < hvec ? pt_red[(size_t)kPtWarps * half + (size_t)v * VE + q] : 0.f;
+      pm[k][q] = v < hvec ? pooled[(size_t)b * half + (size_t)v * VE + q] : 0.f;
+    }
+  }
+  for (int n = warp; n < N; n += kPtWarps) {
+    const float w = policy ? policy[(size_t)b * N + n] : 1.f;
+    float dot = 0.f;
+#pragma unroll
+    for (int k = 0; k < kPtMaxK; ++k) {
+      const int v = lane + 32 * k;
+      if (v < hvec) {
+        float o[8];
+#pragma unroll
+        for (int q = 0; q < VE; ++q) o[q] = w * gs[k][q];
+        *reinterpret_cast<int4*>(db + (size_t)n * C + half + (size_t)v * VE) = PVec<T_>::pack(o);
+        if (dpolicy) {
+          float x[8];
+          PVec<T_>::unpack(*reinterpret_cast<const int4*>(hb + (size_t)n * C + half + (size_t)v * VE), x);
+#pragma unroll
+          for (int q = 0; q < VE; ++q) dot = fmaf(x[q] - pm[k][q], gs[k][q], dot);
+        }
+      }
+    }
+    if (dpolicy) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+      if (lane == 0) dpolicy[(size_t)b * N + n] = dot;
+    }
+  }
+}
+
 }  // namespace d2s
 
 using namespace d2s;
@@ -331,4 +508,49 @@ extern "C" int d2s_bias_act(void* u, const void* bias, int dtype, long long rows
   }
   count_launch();
   return check_launch("d2s_bias_act");
+}
+
+static int pool_concat_check(const char* what, int dtype, int B, int N, int C) {
+  D2S_REQUIRE(dtype == D2S_F32 || dtype == D2S_BF16, D2S_ERR_ARG, "%s: dtype %d unsupported", what, dtype);
+  const int ve = dtype == D2S_BF16 ? 8 : 4;
+  D2S_REQUIRE(B >= 0 && N >= 1 && C >= 2 * ve && C % (2 * ve) == 0 && C / 2 / ve <= 32 * kPtMaxK, D2S_ERR_ARG,
+              "%s: bad shape B=%d N=%d C=%d (C/2 a multiple of %d, at most %d)", what, B, N, C, ve, 32 * kPtMaxK * ve);
+  return D2S_OK;
+}
+
+extern "C" int d2s_pool_concat_fwd(const void* h, const float* policy, int dtype, int B, int N, int C, void* out, float* pooled,
+                                   float* wsum, d2s_stream_t stream) {
+  D2S_REQUIRE(h && out && pooled && wsum, D2S_ERR_ARG, "pool_concat_fwd: null pointer");
+  int rc = pool_concat_check("pool_concat_fwd", dtype, B, N, C);
+  if (rc) return rc;
+  D2S_REQUIRE(aligned16(h) && aligned16(out), D2S_ERR_ALIGN, "pool_concat_fwd: h/out must be 16-byte aligned");
+  if (B == 0) return D2S_OK;
+  const size_t smem = ((size_t)kPtWarps + 1) * (C / 2) * sizeof(float);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == D2S_BF16)
+    pool_concat_fwd_kernel<__nv_bfloat16><<<B, kPtWarps * 32, smem, st>>>((const __nv_bfloat16*)h, policy, N, C, (__nv_bfloat16*)out, pooled, wsum);
+  else
+    pool_concat_fwd_kernel<float><<<B, kPtWarps * 32, smem, st>>>((const float*)h, policy, N, C, (float*)out, pooled, wsum);
+  count_launch();
+  return check_launch("d2s_pool_concat_fwd");
+}
+
+extern "C" int d2s_pool_concat_bwd(const void* dout, const void* h, const float* policy, const float* pooled, const float* wsum,
+                                   int dtype, int B, int N, int C, void* dh, float* dpolicy, d2s_stream_t stream) {
+  D2S_REQUIRE(dout && h && pooled && wsum && dh, D2S_ERR_ARG, "pool_concat_bwd: null pointer");
+  D2S_REQUIRE(!dpolicy || policy, D2S_ERR_ARG, "pool_concat_bwd: dpolicy without a policy");
+  int rc = pool_concat_check("pool_concat_bwd", dtype, B, N, C);
+  if (rc) return rc;
+  D2S_REQUIRE(aligned16(dout) && aligned16(h) && aligned16(dh), D2S_ERR_ALIGN, "pool_concat_bwd: dout/h/dh must be 16-byte aligned");
+  if (B == 0) return D2S_OK;
+  const size_t smem = ((size_t)kPtWarps + 1) * (C / 2) * sizeof(float);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == D2S_BF16)
+    pool_concat_bwd_kernel<__nv_bfloat16><<<B, kPtWarps * 32, smem, st>>>((const __nv_bfloat16*)dout, (const __nv_bfloat16*)h, policy, pooled,
+                                                                         wsum, N, C, (__nv_bfloat16*)dh, dpolicy);
+  else
+    pool_concat_bwd_kernel<float><<<B, kPtWarps * 32, smem, st>>>((const float*)dout, (const float*)h, policy, pooled, wsum, N, C,
+                                                                  (float*)dh, dpolicy);
+  count_launch();
+  return check_launch("d2s_pool_concat_bwd");
 }

@@ -26,6 +26,7 @@ _FROZEN_BF16 = os.environ.get("D2S_FROZEN_BF16", "1") != "0"   # A/B switch: cac
 _FUSED_ADD_LN_TRAIN = os.environ.get("D2S_FUSED_ADD_LN_TRAIN", "1") != "0"   # A/B switch: residual adds folded into LayerNorm fwd/bwd
 _FUSED_MLP = os.environ.get("D2S_FUSED_MLP", "1") != "0"      # A/B switch for the one-kernel MLP (ops.mlp_residual_ln)
 _FUSED_PAIR = os.environ.get("D2S_FUSED_PAIR", "1") != "0"  # A/B switch for the CTA-pair GEMMs (fc1 pair; proj/fc2 + add + LN)
+_POOL_TRAIN = os.environ.get("D2S_POOL_TRAIN", "1") != "0"  # A/B switch: the predictors' local/global split as one kernel each way
 _THRESHOLD_INFERENCE = os.environ.get("D2S_THRESHOLD_INFERENCE", "0") == "1"   # opt-in: what dynamic_vit.py:935-949 intends
 INIT_N = 14 * 14  # the reference hard-codes 196 spatial tokens (dynamic_vit.py:828, default_dynamic_vit.py:446)
 
@@ -195,13 +196,13 @@ def _pair_ok(lin, a, x):
             and x.shape[-1] == lin.out_features and a.shape[:-1] == x.shape[:-1])
 
 
-def norm_forward(n, x):
+def norm_forward(n, x, row0=0):
     """A model LayerNorm on the training path: the d2s forward/backward pair when it applies (plain LayerNorm on a CUDA
-    tensor whose rows are multiples of 8 elements), torch otherwise."""
+    tensor whose rows are multiples of 8 elements), torch otherwise.  row0: normalise x[:, row0:] (read in place by the kernel)."""
     if _is_plain_ln(n) and x.is_cuda and _d2s_float(x) and x.shape[-1] % 8 == 0 \
             and x.shape[-1] <= 768 and len(n.normalized_shape) == 1:
-        return ops.layer_norm(x, n.weight, n.bias, n.eps)
-    return n(x)
+        return ops.layer_norm(x, n.weight, n.bias, n.eps, row0=row0)
+    return n(x[:, row0:] if row0 else x)
 
 
 def block_forward(m, x, policy=None, return_cls_attn=False):
@@ -379,12 +380,19 @@ class _Stream:
         return norm(self.value())[:, 0]
 
 
-def _seq_forward(layers, h):
+def _seq_forward(layers, h, row0=0):
     """A predictor nn.Sequential on the training path: LayerNorms on the d2s forward/backward kernels, Linear layers through
     ops.linear_train (bias gradient by the column-sum kernel, fp32 weight gradient straight from the GEMM) and Linear -> GELU
-    pairs as one autograd node (ops.linear_gelu_train).  Each falls back to the module itself when it does not apply."""
+    pairs as one autograd node (ops.linear_gelu_train).  Each falls back to the module itself when it does not apply.
+    row0: the sequence is applied to h[:, row0:]; a leading LayerNorm reads those rows in place instead of a slice copy."""
     layers = list(layers)
     i = 0
+    if row0:
+        if layers and isinstance(layers[0], torch.nn.LayerNorm):
+            h = norm_forward(layers[0], h, row0=row0)
+            i = 1
+        else:
+            h = h[:, row0:]
     while i < len(layers):
         layer = layers[i]
         if isinstance(layer, torch.nn.LayerNorm):
@@ -403,13 +411,16 @@ def _seq_forward(layers, h):
 
 
 # ---- Variant A predictor (default_dynamic_vit.py:304-330) ------------------------------------------
-def predictor_a_hidden(m, x, policy, normed=None):
-    """`normed`: in_conv's LayerNorm already applied (by the fused add+LayerNorm kernel)."""
-    h = _seq_forward(m.in_conv, x) if normed is None else _seq_forward(list(m.in_conv)[1:], normed)
+def predictor_a_hidden(m, x, policy, normed=None, row0=0):
+    """`normed`: in_conv's LayerNorm already applied (by the fused add+LayerNorm kernel).  row0: the predictor sees x[:, row0:]."""
+    h = _seq_forward(m.in_conv, x, row0=row0) if normed is None else _seq_forward(list(m.in_conv)[1:], normed)
     B, N, C = h.shape
     half = C // 2
-    pooled = (h[:, :, half:] * policy).sum(dim=1, keepdim=True) / torch.sum(policy, dim=1, keepdim=True)
-    h = torch.cat([h[:, :, :half], pooled.expand(B, N, half)], dim=-1)
+    if _POOL_TRAIN and ops.pool_concat_train_ok(h) and policy is not None and policy.is_cuda:
+        h = ops.pool_concat_train(h, policy)          # slice, multiply, sum, divide, expand, cat: one kernel each way
+    else:
+        pooled = (h[:, :, half:] * policy).sum(dim=1, keepdim=True) / torch.sum(policy, dim=1, keepdim=True)
+        h = torch.cat([h[:, :, :half], pooled.expand(B, N, half)], dim=-1)
     return _seq_forward(list(m.out_conv)[:4], h)      # Linear, GELU, Linear, GELU
 
 
@@ -418,8 +429,8 @@ def _tail_ok(h):
     return h.is_cuda and h.shape[-1] % 8 == 0 and 8 <= h.shape[-1] <= 1024
 
 
-def predictor_a_forward(m, x, policy):
-    h = predictor_a_hidden(m, x, policy)
+def predictor_a_forward(m, x, policy, row0=0):
+    h = predictor_a_hidden(m, x, policy, row0=row0)
     lin = m.out_conv[4]
     if _needs_grad(h, lin.weight) or not _tail_ok(h):
         return m.out_conv[5](lin(h))
@@ -466,8 +477,11 @@ def predictor_b_hidden(m, x, normed=None):
     h = _seq_forward(m.in_conv, x) if normed is None else m.in_conv[2](m.in_conv[1](normed))
     B, N, C = h.shape
     half = C // 2
-    pooled = torch.mean(h[:, :, half:], dim=1, keepdim=True)
-    h = torch.cat([h[:, :, :half], pooled.expand(B, N, half)], dim=-1)
+    if _POOL_TRAIN and ops.pool_concat_train_ok(h) and torch.is_grad_enabled() and h.requires_grad:
+        h = ops.pool_concat_train(h)
+    else:
+        pooled = torch.mean(h[:, :, half:], dim=1, keepdim=True)
+        h = torch.cat([h[:, :, :half], pooled.expand(B, N, half)], dim=-1)
     body, norm, lin = _predictor_b_tail_parts(m)
     return _seq_forward(body, h), norm, lin
 
@@ -603,7 +617,7 @@ def variant_a_forward(model, img):
             pred = model.score_predictor[p_count]
             if model.training:
                 x = st.value()
-                pred_score = predictor_a_forward(pred, x[:, 1:], prev_decision).reshape(B, -1, 2)
+                pred_score = predictor_a_forward(pred, x, prev_decision, row0=1).reshape(B, -1, 2)
                 g = injected[p_count] if injected is not None else draw_gumbel(pred_score)
                 hard = ops.gumbel_keep_decision(pred_score, g, prev_decision)
                 out_pred_prob.append(hard.reshape(B, INIT_N))

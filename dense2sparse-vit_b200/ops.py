@@ -834,6 +834,50 @@ def bias_act_(u, bias, act=ACT_GELU):
     return u
 
 
+class _PoolConcat(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, h, policy):
+        hc = h.contiguous()
+        B, N, C = hc.shape
+        pol = None if policy is None else _f32c(policy.reshape(B, N))
+        out = torch.empty_like(hc)
+        pooled = torch.empty(B, C // 2, dtype=torch.float32, device=hc.device)
+        wsum = torch.empty(B, dtype=torch.float32, device=hc.device)
+        _call("d2s_pool_concat_fwd", _ptr(hc), _ptr(pol), _dtype_code(hc), B, N, C, _ptr(out), _ptr(pooled), _ptr(wsum), _stream(hc))
+        ctx.save_for_backward(hc, pooled, wsum, pol if pol is not None else torch.empty(0, device=hc.device))
+        ctx.meta = (pol is not None, None if policy is None else (policy.shape, policy.dtype))
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        hc, pooled, wsum, pol = ctx.saved_tensors
+        has_pol, pol_meta = ctx.meta
+        B, N, C = hc.shape
+        g = gout.to(hc.dtype).contiguous()
+        dh = torch.empty_like(hc)
+        want_dp = has_pol and ctx.needs_input_grad[1]
+        dpol = torch.empty(B, N, dtype=torch.float32, device=hc.device) if want_dp else None
+        _call("d2s_pool_concat_bwd", _ptr(g), _ptr(hc), _ptr(pol if has_pol else None), _ptr(pooled), _ptr(wsum), _dtype_code(hc),
+              B, N, C, _ptr(dh), _ptr(dpol), _stream(g))
+        return dh, None if dpol is None else dpol.view(pol_meta[0]).to(pol_meta[1])
+
+
+def pool_concat_train(h, policy=None):
+    """cat(h[..., :C/2], weighted mean over tokens of h[..., C/2:] broadcast to every token) for h (B,N,C) f32|bf16 with
+    autograd in h and policy (B,N,1) or None (plain mean): the local / global split of PredictorLG.forward
+    (default_dynamic_vit.py:326-329, dynamic_vit.py:541-545) as one kernel forward and one backward."""
+    _check_cuda(h, policy)
+    if h.dim() != 3 or h.dtype not in (torch.float32, torch.bfloat16):
+        raise RuntimeError("pool_concat_train: a (B,N,C) f32 | bf16 tensor is expected")
+    return _PoolConcat.apply(h, policy)
+
+
+def pool_concat_train_ok(h):
+    ve = 8 if h.dtype == torch.bfloat16 else 4
+    return (h.is_cuda and h.dim() == 3 and h.dtype in (torch.float32, torch.bfloat16) and h.shape[-1] % (2 * ve) == 0
+            and h.shape[-1] // 2 // ve <= 96 and h.shape[1] >= 1)
+
+
 def pool_concat_(z):
     """In place: z (B,N,C) <- cat(z[..., :C/2], mean over tokens of z[..., C/2:] broadcast) (dynamic_vit.py:539-545)."""
     _check_cuda(z)
@@ -917,33 +961,51 @@ def _ln_grad_targets(ctx, D, dev):
 
 class _LayerNorm(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, eps, out_dtype):
+    def forward(ctx, x, weight, bias, eps, out_dtype, row0):
         xc = x.contiguous()
         D = xc.shape[-1]
-        rows = xc.numel() // D
         w, b = _f32c(weight), _f32c(bias)
-        h = torch.empty(xc.shape, dtype=out_dtype, device=xc.device)
-        stats = torch.empty(rows, 2, dtype=torch.float32, device=xc.device)
-        _call("d2s_layernorm_fwd", _ptr(xc), _dtype_code(xc), _ptr(w), _ptr(b), rows, D, float(eps), _ptr(h),
-                  _dtype_code(h), _ptr(stats), _stream(xc))
+        if row0:                                     # LayerNorm(x[:, row0:]) of a (B, T, D) tensor without the slice copy
+            B, T = xc.shape[0], xc.shape[1]
+            seg = T - row0
+            rows = B * seg
+            h = torch.empty(B, seg, D, dtype=out_dtype, device=xc.device)
+            stats = torch.empty(rows, 2, dtype=torch.float32, device=xc.device)
+            if rows:
+                _call("d2s_layernorm_seg_fwd", _ptr(xc), _dtype_code(xc), _ptr(w), _ptr(b), rows, D, seg, row0, float(eps), _ptr(h),
+                      _dtype_code(h), _ptr(stats), _stream(xc))
+        else:
+            rows = xc.numel() // D
+            seg = 0
+            h = torch.empty(xc.shape, dtype=out_dtype, device=xc.device)
+            stats = torch.empty(rows, 2, dtype=torch.float32, device=xc.device)
+            _call("d2s_layernorm_fwd", _ptr(xc), _dtype_code(xc), _ptr(w), _ptr(b), rows, D, float(eps), _ptr(h),
+                      _dtype_code(h), _ptr(stats), _stream(xc))
         ctx.save_for_backward(xc, stats, w)
-        ctx.meta = (weight.dtype, bias.dtype)
+        ctx.meta = (weight.dtype, bias.dtype, rows, seg, row0)
         ctx.params = (weight, bias)
         return h
 
     @staticmethod
     def backward(ctx, dh):
         xc, stats, w = ctx.saved_tensors
+        _, _, rows, seg, row0 = ctx.meta
         D = xc.shape[-1]
-        rows = xc.numel() // D
         g = dh.contiguous()
         dx = torch.empty_like(xc)
         dg, db, direct = _ln_grad_targets(ctx, D, xc.device)
-        _call("d2s_layernorm_bwd", _ptr(g), _dtype_code(g), _ptr(xc), _dtype_code(xc), _ptr(stats), _ptr(w), rows, D,
-                  _ptr(dx), _ptr(dg), _ptr(db), _stream(g))
+        if seg:
+            if rows:
+                _call("d2s_layernorm_seg_bwd", _ptr(g), _dtype_code(g), _ptr(xc), _dtype_code(xc), _ptr(stats), _ptr(w), rows, D, seg,
+                      row0, _ptr(dx), _ptr(dg), _ptr(db), _stream(g))
+            else:
+                dx.zero_()
+        else:
+            _call("d2s_layernorm_bwd", _ptr(g), _dtype_code(g), _ptr(xc), _dtype_code(xc), _ptr(stats), _ptr(w), rows, D,
+                      _ptr(dx), _ptr(dg), _ptr(db), _stream(g))
         if direct:
-            return dx, None, None, None, None
-        return dx, dg.to(ctx.meta[0]), db.to(ctx.meta[1]), None, None
+            return dx, None, None, None, None, None
+        return dx, dg.to(ctx.meta[0]), db.to(ctx.meta[1]), None, None, None
 
 
 class _AddLayerNorm(torch.autograd.Function):
@@ -995,13 +1057,17 @@ def add_layer_norm_train(x, y, weight, bias, eps, out_dtype=None):
     return _AddLayerNorm.apply(x, y, weight, bias, eps, out_dtype)
 
 
-def layer_norm(x, weight, bias, eps, out_dtype=None):
+def layer_norm(x, weight, bias, eps, out_dtype=None, row0=0):
     """LayerNorm over the last dim with autograd: x f32|bf16 -> out_dtype (default: bf16 under CUDA autocast, else
-    x.dtype), statistics in fp32.  One streaming kernel forward, one backward (dx + dgamma + dbeta)."""
+    x.dtype), statistics in fp32.  One streaming kernel forward, one backward (dx + dgamma + dbeta).
+    row0 > 0: x is (B, T, D) and the result is LayerNorm(x[:, row0:]) (B, T - row0, D) -- the predictors' input norm over the
+    patch tokens -- read in place (no slice copy; the backward writes the full (B, T, D) gradient, zeros in the skipped rows)."""
     _check_cuda(x, weight, bias)
     if out_dtype is None:
         out_dtype = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else x.dtype
-    return _LayerNorm.apply(x, weight, bias, eps, out_dtype)
+    if row0 and (x.dim() != 3 or not 0 < row0 < x.shape[1]):
+        raise RuntimeError(f"layer_norm: row0={row0} needs a (B, T, D) input with T > row0, got {tuple(x.shape)}")
+    return _LayerNorm.apply(x, weight, bias, eps, out_dtype, int(row0))
 
 
 def linear_act(x, weight, bias, act=ACT_GELU, want_pre=False):

@@ -217,6 +217,17 @@ int d2s_bias_act(void* u, const void* bias, int dtype, long long rows, int N, in
 /* Variant B's concat (dynamic_vit.py:539-545) in place: z (B,N,C) <- cat(z[:,:,:C/2], mean_n(z[:,:,C/2:]).expand). */
 int d2s_pool_concat_inplace(void* z, int dtype, int B, int N, int C, d2s_stream_t stream);
 
+/* Training form of the same local / global split, with autograd in h and in the keep policy (PredictorLG.forward,
+ * default_dynamic_vit.py:326-329: policy-weighted mean; dynamic_vit.py:541-545: plain mean, policy NULL), f32 | bf16:
+ *   out[b,n,:C/2] = h[b,n,:C/2];  pooled[b,c] = sum_n w[b,n] h[b,n,C/2+c] / sum_n w[b,n];  out[b,n,C/2+c] = pooled[b,c]
+ * pooled (B,C/2) f32 and wsum (B) f32 are saved for the backward, which returns dh (B,N,C) and, when dpolicy is not NULL,
+ * dpolicy (B,N) f32 = sum_c (h[b,n,C/2+c] - pooled[b,c]) G[b,c] / wsum[b] with G = column sums of dout's global half.
+ * policy (B,N) f32.  C/2 a multiple of the 16-byte vector, C/2 <= 768 (bf16) | 384 (f32). */
+int d2s_pool_concat_fwd(const void* h, const float* policy, int dtype, int B, int N, int C, void* out, float* pooled,
+                        float* wsum, d2s_stream_t stream);
+int d2s_pool_concat_bwd(const void* dout, const void* h, const float* policy, const float* pooled, const float* wsum,
+                        int dtype, int B, int N, int C, void* dh, float* dpolicy, d2s_stream_t stream);
+
 /* ---- token assembly (dynamic_vit.py:816-824; default_dynamic_vit.py:437-442) -----------------------------------
  * out (B,N+1,D) = cat(cls (D) broadcast, patches (B,N,D)) + pos (N+1,D), one pass instead of concat + add. */
 int d2s_assemble_tokens(const void* patches, const void* cls, const void* pos, int dtype, int B, int N, int D,
@@ -292,6 +303,15 @@ int d2s_layernorm_fwd(const void* x, int x_dtype, const float* gamma, const floa
                       float eps, void* h, int h_dtype, float* stats, d2s_stream_t stream);
 int d2s_layernorm_bwd(const void* dh, int h_dtype, const void* x, int x_dtype, const float* stats, const float* gamma,
                       long long rows, int D, void* dx, float* dgamma, float* dbeta, d2s_stream_t stream);
+
+/* The same over the rows `skip`.. of every (seg + skip)-row segment of x -- LayerNorm(x[:, 1:]) as the predictors apply it
+ * (default_dynamic_vit.py:461 -> :313, dynamic_vit.py:846 -> :386) without the slice copy: x holds rows/seg segments of
+ * seg + skip rows, h and stats are dense over the `rows` normalised rows (rows % seg == 0).  Backward writes dx in x's layout,
+ * zeros in the skipped rows. */
+int d2s_layernorm_seg_fwd(const void* x, int x_dtype, const float* gamma, const float* beta, long long rows, int D, int seg,
+                          int skip, float eps, void* h, int h_dtype, float* stats, d2s_stream_t stream);
+int d2s_layernorm_seg_bwd(const void* dh, int h_dtype, const void* x, int x_dtype, const float* stats, const float* gamma,
+                          long long rows, int D, int seg, int skip, void* dx, float* dgamma, float* dbeta, d2s_stream_t stream);
 
 /* The residual add folded into the LayerNorm that follows it, training path (Block.forward, dynamic_vit.py:276-283:
  * x = x + branch; norm(x)): forward writes out_sum = x + res (dtype of x) and h = LayerNorm(out_sum) (+ stats); backward

@@ -29,9 +29,8 @@ teacher = pkg.variant_a.DefaultVisionTransformerTeacher(**bench.DEIT_S).to(dev).
 for p in teacher.parameters():
     p.requires_grad_(False)
 crit = pkg.losses.DistillDiffPruningLoss(teacher, keep_ratio=bench.RATIOS)
-opt = torch.optim.AdamW(student.parameters(), lr=5e-4, weight_decay=0.05, capturable=True)
-grads = pkg.runner.FlatGrads(student.parameters())
-wcache = pkg.ops.BF16WeightCache(student.parameters())
+opt = pkg.runner.FlatAdamW(student.parameters(), lr=5e-4, weight_decay=0.05)
+grads, wcache = opt.grads, opt.weight_cache
 x = torch.randn(args.batch, 3, 224, 224, device=dev)
 y = torch.randint(0, 1000, (args.batch,), device=dev)
 
@@ -45,9 +44,26 @@ run = pkg.runner.TrainStepRunner(fwd_loss, opt, x, y, warmup=2, use_graph=False,
 for _ in range(2):
     run()
 torch.cuda.synchronize()
-with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], record_shapes=True) as prof:
+with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], record_shapes=True, with_stack=True) as prof:
     run()
     torch.cuda.synchronize()
 print(prof.key_averages(group_by_input_shape=True).table(sort_by="self_cuda_time_total", row_limit=args.rows, max_name_column_width=60,
                                                          max_shapes_column_width=90))
 print(prof.key_averages().table(sort_by="self_cuda_time_total", row_limit=args.rows, max_name_column_width=110))
+# aten ops with device time, grouped by the innermost repo frame that issued them
+import collections
+by_site = collections.defaultdict(lambda: [0.0, 0])
+for ev in prof.events():
+    if not ev.name.startswith("aten::") or ev.self_device_time_total <= 0:
+        continue
+    site = "?"
+    for fr in (ev.stack or []):
+        if "/root/repo/" in fr or "dense2sparse" in fr:
+            site = fr.split("/")[-1]
+            break
+    k = (ev.name, site, str(ev.input_shapes)[:70])
+    by_site[k][0] += ev.self_device_time_total
+    by_site[k][1] += 1
+print("\n==== aten ops by call site (self device us, calls) ====")
+for k, (t, n) in sorted(by_site.items(), key=lambda kv: -kv[1][0])[:90]:
+    print(f"{t:9.1f} {n:4d}  {k[0]:28s} {k[1]:60s} {k[2]}")

@@ -963,3 +963,66 @@ def test_errors_are_loud(ops):
         torch.stack([xh[0, [0, 1, 3]], xh[1, [0, 2, 4]]]).tolist()))
     with pytest.raises(RuntimeError, match="head dim"):
         ops.attention_core(torch.zeros(1, 8, 3 * 2 * 48, dtype=torch.bfloat16).cuda(), 2)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("B,N,C,with_policy", [(3, 196, 384, True), (2, 137, 384, False), (2, 5, 16, True), (1, 1, 1536, True),
+                                                (4, 196, 768, True)])
+def test_pool_concat_train_matches_the_torch_composition(ops, B, N, C, with_policy, dtype):
+    """d2s_pool_concat_fwd/bwd against the reference's slice / multiply / sum / divide / expand / cat (default_dynamic_vit.py
+    :326-329; plain mean: dynamic_vit.py:541-545) under torch autograd in fp32."""
+    if dtype == torch.float32 and C // 2 > 384:
+        pytest.skip("f32 rows up to C/2 = 384")
+    h = fx.randn(900 + N, B, N, C).to(dtype)
+    pol = (torch.rand(B, N, 1, generator=fx.gen(901 + N)) > 0.4).float() * (0.5 + torch.rand(B, N, 1, generator=fx.gen(902))) if with_policy else None
+    if pol is not None:
+        pol[:, 0] = 1.0
+    go = fx.randn(903 + N, B, N, C).to(dtype)
+    hr = h.float().clone().requires_grad_(True)
+    pr = None if pol is None else pol.clone().requires_grad_(True)
+    half = C // 2
+    if pr is not None:
+        pooled = (hr[:, :, half:] * pr).sum(dim=1, keepdim=True) / pr.sum(dim=1, keepdim=True)
+    else:
+        pooled = hr[:, :, half:].mean(dim=1, keepdim=True)
+    ref = torch.cat([hr[:, :, :half], pooled.expand(B, N, half)], dim=-1)
+    (ref * go.float()).sum().backward()
+    hd = cu(h).requires_grad_(True)
+    pd = None if pol is None else cu(pol).requires_grad_(True)
+    out = ops.pool_concat_train(hd, pd)
+    assert out.dtype == dtype and out.shape == (B, N, C)
+    (out.float() * cu(go).float()).sum().backward()
+    tol = dict(rtol=1e-5, atol=1e-5) if dtype == torch.float32 else dict(rtol=1e-2, atol=1e-2)
+    assert torch.equal(out[:, :, :half].cpu(), h[:, :, :half])                       # the local half is a copy
+    torch.testing.assert_close(out.float().cpu(), ref.detach(), **tol)
+    assert torch.equal(hd.grad[:, :, :half].cpu(), go[:, :, :half])
+    gscale = float(hr.grad.abs().max())
+    torch.testing.assert_close(hd.grad.float().cpu(), hr.grad, rtol=tol["rtol"], atol=tol["atol"] * max(1.0, gscale))
+    if pol is not None:
+        pscale = float(pr.grad.abs().max())
+        torch.testing.assert_close(pd.grad.cpu(), pr.grad, rtol=1e-4 if dtype == torch.float32 else 2e-2,
+                                   atol=(1e-5 if dtype == torch.float32 else 2e-2) * max(1.0, pscale))
+
+
+@pytest.mark.parametrize("dtype,out_dtype", [(torch.float32, torch.float32), (torch.bfloat16, torch.bfloat16), (torch.float32, torch.bfloat16)])
+@pytest.mark.parametrize("B,T,D,row0", [(3, 197, 384, 1), (2, 9, 64, 1), (2, 10, 768, 2), (1, 2, 8, 1)])
+def test_layer_norm_over_a_row_slice_reads_in_place(ops, B, T, D, row0, dtype, out_dtype):
+    """ops.layer_norm(x, row0=r) == layer_norm(x[:, r:]) forward and backward (d2s_layernorm_seg_fwd/bwd): the gradient has
+    x's full shape with zeros in the skipped rows, dgamma / dbeta as usual."""
+    x = fx.randn(910 + T, B, T, D).to(dtype)
+    w, b = 1.0 + 0.1 * fx.randn(911, D), 0.1 * fx.randn(912, D)
+    go = fx.randn(913 + T, B, T - row0, D).to(out_dtype)
+    xr, wr, br = x.float().clone().requires_grad_(True), w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    ref = torch.nn.functional.layer_norm(xr[:, row0:], (D,), wr, br, 1e-5)
+    (ref * go.float()).sum().backward()
+    xd, wd, bd = cu(x).requires_grad_(True), cu(w).requires_grad_(True), cu(b).requires_grad_(True)
+    out = ops.layer_norm(xd, wd, bd, 1e-5, out_dtype=out_dtype, row0=row0)
+    assert out.shape == (B, T - row0, D) and out.dtype == out_dtype and out.is_contiguous()
+    (out.float() * cu(go).float()).sum().backward()
+    lo = dtype == torch.bfloat16 or out_dtype == torch.bfloat16
+    tol = dict(rtol=2e-2, atol=2e-2) if lo else dict(rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(out.float().cpu(), ref.detach(), **tol)
+    assert xd.grad.shape == x.shape and float(xd.grad[:, :row0].abs().max()) == 0.0
+    torch.testing.assert_close(xd.grad.float().cpu(), xr.grad, rtol=tol["rtol"], atol=tol["atol"] * max(1.0, float(xr.grad.abs().max())))
+    torch.testing.assert_close(wd.grad.cpu(), wr.grad, rtol=tol["rtol"], atol=tol["atol"] * max(1.0, float(wr.grad.abs().max())))
+    torch.testing.assert_close(bd.grad.cpu(), br.grad, rtol=tol["rtol"], atol=tol["atol"] * max(1.0, float(br.grad.abs().max())))
