@@ -44,6 +44,7 @@ SIGNATURES = {
     "d2s_gelu_bwd_colsum_bf16": [_p, _p, ctypes.c_longlong, _i, _p, _p, _p],
     "d2s_colsum_acc_bf16": [_p, ctypes.c_longlong, _i, _p, _p],
     "d2s_gelu_bwd_colsum_acc_bf16": [_p, _p, ctypes.c_longlong, _i, _p, _p, _p],
+    "d2s_token_kl_fwd": [_p, _i, ctypes.c_longlong, _p, _i, ctypes.c_longlong, _i, _i, _i, _p, _p, _p],
     "d2s_adamw_flat_f32": [_p, _p, _p, _p, _p, ctypes.c_longlong, ctypes.c_longlong, _p, _p, _f, _f, _f, _f, _f, _p],
     "d2s_attn_policy_fwd": [_p, _p, _i, _i, _i, _i, _i, _f, _f, _p, _p, _p, _p],
     "d2s_attn_policy_bwd": [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _f, _p, _p, _p],

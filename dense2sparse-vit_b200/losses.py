@@ -12,6 +12,19 @@ import torch
 import torch.nn.functional as F
 
 
+def _token_kl_rows(token_s, token_t):
+    """KL(softmax(token_t) || softmax(token_s)) per token row, (B*N,) f32: F.kl_div(log_softmax(s), log_softmax(t),
+    log_target=True) summed over the channels (losses.py:220-225).  One d2s pass over both tensors when it applies (CUDA,
+    row-dense f32 | bf16 (B,N,C), C % 8 == 0, C <= 1024), torch's composition otherwise."""
+    from . import ops
+    B, N, C = token_s.shape
+    if token_s.is_cuda and ops.token_kl_ok(token_s, token_t):
+        return ops.token_kl_rows(token_s, token_t)
+    lp = F.log_softmax(token_s.reshape(B * N, C).float(), dim=-1)
+    lt = F.log_softmax(token_t.reshape(B * N, C).float(), dim=-1)
+    return (lt.exp() * (lt - lp)).sum(dim=-1)
+
+
 class DistillDiffPruningLoss(torch.nn.Module):
     def __init__(self, teacher_model, base_criterion=None, ratio_weight=2.0, distill_weight=0.5, clf_weight=1.0,
                  keep_ratio=(0.7, 0.49, 0.343), print_mode=False):
@@ -38,9 +51,7 @@ class DistillDiffPruningLoss(torch.nn.Module):
         # indexing, no host synchronisation -- the whole training step can be captured in a CUDA graph (runner.TrainStepRunner).
         B, N, C = token_pred.shape
         keep = (mask.reshape(B * N) > 0.5).float()
-        lp = F.log_softmax(token_pred.reshape(B * N, C).float(), dim=-1)
-        lt = F.log_softmax(token_t.reshape(B * N, C).float(), dim=-1)
-        kl_rows = (lt.exp() * (lt - lp)).sum(dim=-1)
+        kl_rows = _token_kl_rows(token_pred, token_t)
         token_kl = (kl_rows * keep).sum() / keep.sum().clamp_min(1.0)
         loss = (self.clf_weight * cls_loss + self.ratio_weight * ratio_loss / max(1, len(out_pred_score))
                 + self.distill_weight * (cls_kl + token_kl))
@@ -144,10 +155,14 @@ class BackboneLoss(torch.nn.Module):
         B, N, C = token_t.size()
         # teacher tokens of the kept positions: the LAST stage's indices into the full-length sequence (losses.py:212)
         token_t = ops.gather_tokens(token_t.detach(), kept_token_idx[-1], prepend_cls=False)
-        token_s = token_s.reshape(-1, C).float()
-        token_t = token_t.reshape(-1, C).float()
-        token_kl_loss = F.kl_div(F.log_softmax(token_s, dim=-1), F.log_softmax(token_t, dim=-1), reduction="batchmean",
-                                 log_target=True)
+        if token_s.dim() == 3 and token_s.shape == token_t.shape:
+            rows = token_s.shape[0] * token_s.shape[1]
+            token_kl_loss = _token_kl_rows(token_s, token_t).sum() / rows           # "batchmean" over the kept rows
+        else:
+            token_s = token_s.reshape(-1, C).float()
+            token_t = token_t.reshape(-1, C).float()
+            token_kl_loss = F.kl_div(F.log_softmax(token_s, dim=-1), F.log_softmax(token_t, dim=-1), reduction="batchmean",
+                                     log_target=True)
         backbone_loss = cls_loss + cls_kl_loss + token_kl_loss
         self.running_loss += backbone_loss.detach().item()
         self.running_cls_loss += cls_loss.detach().item()

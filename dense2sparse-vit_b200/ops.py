@@ -878,6 +878,47 @@ def pool_concat_train_ok(h):
             and h.shape[-1] // 2 // ve <= 96 and h.shape[1] >= 1)
 
 
+def _rows_view_ok(t):
+    """(B,N,C) f32 | bf16 CUDA tensor whose tokens are dense rows (strides (bs, C, 1)): contiguous, or a row slice x[:, r:]."""
+    return (t.dim() == 3 and t.is_cuda and t.dtype in (torch.float32, torch.bfloat16) and t.stride(2) == 1 and t.stride(1) == t.shape[2]
+            and t.stride(0) >= t.shape[1] * t.shape[2] and t.stride(0) % 8 == 0 and t.data_ptr() % 16 == 0)
+
+
+def token_kl_ok(s, t):
+    return (_rows_view_ok(s) and _rows_view_ok(t) and s.shape == t.shape and s.shape[2] % 8 == 0 and s.shape[2] <= 1024
+            and s.shape[1] >= 1)
+
+
+class _TokenKL(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, s, t):
+        B, N, C = s.shape
+        kl = torch.empty(B * N, dtype=torch.float32, device=s.device)
+        diff = torch.empty(B * N, C, dtype=torch.float32, device=s.device)
+        _call("d2s_token_kl_fwd", _ptr(s), _dtype_code(s), s.stride(0), _ptr(t), _dtype_code(t), t.stride(0), B, N, C, _ptr(kl),
+              _ptr(diff), _stream(s))
+        ctx.save_for_backward(diff)
+        ctx.meta = (s.shape, s.dtype)
+        return kl
+
+    @staticmethod
+    def backward(ctx, g):
+        (diff,) = ctx.saved_tensors
+        shape, dt = ctx.meta
+        return (diff * g.reshape(-1, 1)).view(shape).to(dt), None
+
+
+def token_kl_rows(s, t):
+    """Per-token KL(softmax(t) || softmax(s)) over the channels, (B*N,) f32, differentiable in s (t is a constant target):
+    F.kl_div(F.log_softmax(s), F.log_softmax(t), log_target=True, reduction='none').sum(-1) of losses.py:220-225 as one pass
+    (`d2s_token_kl_fwd`); s and t may be x[:, 1:] views."""
+    _check_cuda(s, t)
+    if not token_kl_ok(s, t):
+        raise RuntimeError(f"token_kl_rows: (B,N,C) f32 | bf16 row-dense tensors of one shape with C % 8 == 0, C <= 1024 are expected, got "
+                           f"{tuple(s.shape)} {s.dtype} strides {s.stride()} and {tuple(t.shape)} {t.dtype} strides {t.stride()}")
+    return _TokenKL.apply(s, t.detach())
+
+
 def pool_concat_(z):
     """In place: z (B,N,C) <- cat(z[..., :C/2], mean over tokens of z[..., C/2:] broadcast) (dynamic_vit.py:539-545)."""
     _check_cuda(z)

@@ -168,6 +168,14 @@ int d2s_gelu_bwd_colsum_bf16(const void* u, const void* ga, long long M, int N, 
 /* Same with db ACCUMULATED into (db += column sums of du). */
 int d2s_gelu_bwd_colsum_acc_bf16(const void* u, const void* ga, long long M, int N, void* du, float* db, d2s_stream_t stream);
 
+/* Token distillation rows: kl_rows[b*N+n] = KL(softmax(t[b,n,:]) || softmax(s[b,n,:])) over the C channels -- the
+ * F.kl_div(F.log_softmax(token_s), F.log_softmax(token_t), log_target=True) of BackboneLoss (losses.py:220-225) before its
+ * batchmean -- and diff (B*N, C) f32 = softmax(s) - softmax(t), the gradient of kl_rows in s (the backward is a row scaling).
+ * s, t: (B,N,C) f32 | bf16 with element strides (batch_stride, C, 1), so x[:, 1:] views are read in place.
+ * C % 8 == 0, C <= 1024. */
+int d2s_token_kl_fwd(const void* s, int s_dtype, long long s_batch_stride, const void* t, int t_dtype, long long t_batch_stride,
+                     int B, int N, int C, float* kl_rows, float* diff, d2s_stream_t stream);
+
 /* AdamW over the slice [begin, end) of flat fp32 buffers p (parameters), g (gradients), m, v (moments), all of one layout:
  * the optimizer.step() of the training loop (train.py:63-66; the reference builds torch/timm AdamW in mask_predictor.py and
  * ddp_training.py), decoupled weight decay, bias correction from the step count:

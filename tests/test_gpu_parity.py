@@ -1026,3 +1026,29 @@ def test_layer_norm_over_a_row_slice_reads_in_place(ops, B, T, D, row0, dtype, o
     torch.testing.assert_close(xd.grad.float().cpu(), xr.grad, rtol=tol["rtol"], atol=tol["atol"] * max(1.0, float(xr.grad.abs().max())))
     torch.testing.assert_close(wd.grad.cpu(), wr.grad, rtol=tol["rtol"], atol=tol["atol"] * max(1.0, float(wr.grad.abs().max())))
     torch.testing.assert_close(bd.grad.cpu(), br.grad, rtol=tol["rtol"], atol=tol["atol"] * max(1.0, float(br.grad.abs().max())))
+
+
+@pytest.mark.parametrize("sdt,tdt", [(torch.float32, torch.float32), (torch.float32, torch.bfloat16), (torch.bfloat16, torch.bfloat16)])
+@pytest.mark.parametrize("B,N,C,sliced", [(3, 196, 384, True), (2, 67, 384, False), (2, 5, 8, True), (1, 3, 1024, False), (2, 9, 768, True)])
+def test_token_kl_rows_match_f_kl_div(ops, B, N, C, sliced, sdt, tdt):
+    """d2s_token_kl_fwd against F.kl_div(F.log_softmax(s), F.log_softmax(t), log_target=True) (losses.py:220-225), value and
+    gradient in s; inputs as x[:, 1:] views (read in place) or dense."""
+    full_s = (fx.randn(920 + N, B, N + 1, C) * 2.0).to(sdt)
+    full_t = (fx.randn(921 + N, B, N + 1, C) * 2.0).to(tdt)
+    w = torch.rand(B * N, generator=fx.gen(922))
+    sr = full_s.float().clone().requires_grad_(True)
+    ref_rows = torch.nn.functional.kl_div(torch.log_softmax(sr[:, 1:].reshape(-1, C), -1), torch.log_softmax(full_t.float()[:, 1:].reshape(-1, C), -1),
+                                          reduction="none", log_target=True).sum(-1)
+    (ref_rows * w).sum().backward()
+    sd = cu(full_s.detach().clone()).requires_grad_(True)
+    td = cu(full_t)
+    s_in, t_in = (sd[:, 1:], td[:, 1:]) if sliced else (sd[:, 1:].contiguous(), td[:, 1:].contiguous())
+    assert ops.token_kl_ok(s_in, t_in)
+    rows = ops.token_kl_rows(s_in, t_in)
+    assert rows.shape == (B * N,) and rows.dtype == torch.float32
+    (rows * cu(w)).sum().backward()
+    torch.testing.assert_close(rows.detach().cpu(), ref_rows.detach(), rtol=1e-5, atol=1e-6)
+    g = sd.grad.float().cpu()
+    assert float(g[:, 0].abs().max()) == 0.0
+    tol = 1e-6 if sdt == torch.float32 else 4e-3 * float(sr.grad.abs().max())
+    torch.testing.assert_close(g, sr.grad, rtol=1e-4 if sdt == torch.float32 else 1e-2, atol=tol)
