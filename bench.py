@@ -39,9 +39,10 @@ METRIC = "images/sec DynamicViT DeiT-S kr=0.7 @224"
 UNIT = "images/s"
 LOCS, RATIOS = [3, 6, 9], [0.7, 0.7 ** 2, 0.7 ** 3]   # upstream DynamicViT convention (SURVEY.md 8d cfg 1/2)
 DEIT_S = dict(patch_size=16, embed_dim=384, depth=12, num_heads=6, mlp_ratio=4, qkv_bias=True)
+DEIT_B = dict(patch_size=16, embed_dim=768, depth=12, num_heads=12, mlp_ratio=4, qkv_bias=True)     # BASELINE configs[3] / [4] widths
 GFLOP_PER_IMG = 5.96                                    # SURVEY.md 8d, Variant A 3 stages
 TRAIN_GFLOP_PER_IMG = 36.8                              # 3 x 9.2 (student fwd+bwd at T=197) + 9.2 (teacher fwd)
-ALL_LEGS = ("parity", "infer", "e2e", "h2d", "train", "kernels", "ptopk", "sweep", "eager", "cpu")
+ALL_LEGS = ("parity", "infer", "e2e", "h2d", "train", "kernels", "ptopk", "sweep", "base", "eager", "cpu")
 W_SEED = 61                                             # seeded weights (tests/golden/fixtures.py): well-spread predictor scores
 L2_BYTES = 126e6
 
@@ -545,6 +546,46 @@ def train_leg(pkg, args, dev, rank, world, torch, dist, pk):
     return out
 
 
+def base_leg(pkg, dev, torch, pk, no_graph=False):
+    """DeiT-B widths (D = 768, 12 heads, hidden 3072; dynamic_vit.py:1301-1303) through the same inference path: attention on
+    the tcgen05 kernel, proj / fc2 + residual + LayerNorm as the CTA-pair GEMM with the row kept in two 384-column halves,
+    fc1 + GELU as the CTA-pair GEMM; qkv stays the library GEMM and the hidden activations make an HBM round trip (the
+    128 x 768 fp32 fc2 accumulator does not fit next to the hidden chunks in TMEM)."""
+    B = 512
+    model = pkg.variant_a.DefaultVisionTransformerDiffPruning(pruning_loc=LOCS, token_ratio=RATIOS, distill=True, **DEIT_B)
+    seeded_weights(model)
+    runner = pkg.runner.InferenceRunner(model, B, dev, dtype=torch.bfloat16, use_graph=not no_graph, warmup=2)
+    n0 = pkg._lib.launch_count()
+    with torch.no_grad():
+        runner.model(runner.static_in)
+    torch.cuda.synchronize()
+    launches = pkg._lib.launch_count() - n0
+    g = torch.Generator(device=dev).manual_seed(7)
+    runner.static_in.copy_(torch.randn(runner.static_in.shape, device=dev, generator=g).to(runner.static_in.dtype))
+    for _ in range(3):
+        runner.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    K = 10
+    e0.record()
+    for _ in range(K):
+        runner.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    out = runner.logits
+    ms = e0.elapsed_time(e1) / K
+    gflop = 4.0 * GFLOP_PER_IMG * 0.985      # widths x2 -> GEMM FLOPs x4; the attention part (score / PV) grows x2 only
+    val = B / (ms / 1e3)
+    res = {"metric": "images/sec DynamicViT DeiT-B kr=0.7 @224", "value": val, "unit": UNIT, "ms_per_step": ms, "batch": B,
+           "dtype": "bf16", "cuda_graph": not no_graph, "d2s_launches_per_step": int(launches), "outputs_finite": bool(torch.isfinite(out.float()).all()),
+           "model_tensor_frac": {"gflop_per_img": gflop, "achieved_tflops": val * gflop / 1e3, "peak": pk["tf_sustained"],
+                                 "frac": val * gflop / 1e3 / pk["tf_sustained"]},
+           "path": "attn_tc_fwd + gemm_pair<LN> (N = 768: two halves) + gemm_pair<ACT> (fc1 + GELU); qkv on the library GEMM"}
+    del runner, model
+    torch.cuda.empty_cache()
+    return res
+
+
 def gpu_eager_leg(sd, dev, B, torch):
     """The oracle's restatement of the reference forward (plain torch ops: F.linear / matmul / softmax / sort / gather -- what
     `reference_model.to(bfloat16).cuda()` executes) run by torch eager on this GPU at the benchmarked batch and dtype."""
@@ -766,6 +807,8 @@ def run_gpu(args):
         line["ptopk"] = ptopk_leg(pkg.ops, dev, torch, pk)
     if "sweep" in legs:
         line["sweep"] = sweep_leg(pkg.ops, dev, torch, pk)
+    if "base" in legs and rank == 0:
+        line["arch_base"] = base_leg(pkg, dev, torch, pk, args.no_graph)
         torch.cuda.empty_cache()
     if "eager" in legs:
         line["gpu_eager_baseline"] = gpu_eager_leg(sd, dev, B, torch)

@@ -19,7 +19,8 @@
 //              both CTAs and publishes the accumulator to both epilogues
 //   warps 2-17 epilogue (both CTAs), four warps per TMEM lane quadrant splitting the columns
 //
-// MODE_LN keeps the whole 128 x D row tile (D = 192 or 384 <= 512 TMEM columns) in the CTA, so the LayerNorm of the
+// MODE_LN keeps the whole 128 x D row tile (D = 192 or 384 <= 512 TMEM columns; D = 768 as two 384-column halves accumulated
+// one after the other, the first normalised from its own freshly written x' lines) in the CTA, so the LayerNorm of the
 // freshly produced residual stream is computed in the same kernel.  Each epilogue thread owns one row and half of its
 // columns and keeps them in registers: the residual rows are fetched with coalesced loads while the MMAs still run and
 // transposed to one-row-per-lane through a 4 KB per-warp buffer; pass 1 reads the accumulator, forms x' and the fp32
@@ -104,8 +105,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   unsigned char* ring = smem_dyn + padb;
   unsigned char* blocks = ring + STAGES * kStage;               // MODE_ACT: store staging; MODE_LN: x / x' / h tile
   GpBars* bars = reinterpret_cast<GpBars*>(blocks + Cfg::BLOCKS * kGpBlkBytes);
-  float* bias_s = reinterpret_cast<float*>(bars + 1);           // N floats (MODE_ACT) / 3 x TN floats (MODE_LN)
-  float2* red_s = reinterpret_cast<float2*>(bias_s + (MODE == kGpModeLn ? 3 * TN : p.N));   // MODE_LN: [PARTS][128] partial stats
+  float* bias_s = reinterpret_cast<float*>(bars + 1);           // N floats (MODE_ACT) / 3 x N floats (MODE_LN)
+  float2* red_s = reinterpret_cast<float2*>(bias_s + (MODE == kGpModeLn ? 3 * p.N : p.N));   // MODE_LN: [PARTS][128] partial stats
   volatile uint32_t* sel_s = reinterpret_cast<volatile uint32_t*>(red_s + 4 * 128);           // MODE_LN: byte-permute selectors
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -125,10 +126,10 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
   }
   if (MODE == kGpModeLn) {
-    for (int i = tid; i < TN; i += kThreads) {
+    for (int i = tid; i < p.N; i += kThreads) {
       bias_s[i] = p.bias ? __bfloat162float(p.bias[i]) : 0.f;
-      bias_s[TN + i] = p.gamma ? __bfloat162float(p.gamma[i]) : 1.f;
-      bias_s[2 * TN + i] = p.beta ? __bfloat162float(p.beta[i]) : 0.f;
+      bias_s[p.N + i] = p.gamma ? __bfloat162float(p.gamma[i]) : 1.f;
+      bias_s[2 * p.N + i] = p.beta ? __bfloat162float(p.beta[i]) : 0.f;
     }
   } else {
     for (int i = tid; i < p.N; i += kThreads) bias_s[i] = p.bias ? __bfloat162float(p.bias[i]) : 0.f;
@@ -271,122 +272,132 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       }
       GP_TRACE_DUMP(5, tile)
     } else {
-      // ---- MODE_LN: n_tiles == 1, TN == N.  This thread owns row r and the 64-column blocks b = PARTS bi + part (whole
-      // 128-byte lines), and keeps its x / x' values in registers (BPT x 32 packed bf16 pairs). ----
+      // ---- MODE_LN: rows of N = n_tiles x TN columns (n_tiles = 1: D = 192 / 384; n_tiles = 2: D = 768, whose 128 x 768 fp32
+      // row tile does not fit the 512 TMEM columns: the two 384-column halves are accumulated one after the other).  This
+      // thread owns row r and the 64-column blocks b = PARTS bi + part of the current half (whole 128-byte lines), and keeps
+      // its x / x' values in registers (BPT x 32 packed bf16 pairs); the row statistics run on across the halves.  After the
+      // last half the registers hold that half's x'; earlier halves are normalised from the x' lines this warp itself wrote
+      // a moment ago (L2 hits), in the coalesced layout, with mean / rstd fetched from the owning lane by shuffle. ----
       constexpr int NBLK = TN / 64, BPT = NBLK / PARTS;
       static_assert(MODE != kGpModeLn || NBLK % PARTS == 0, "column blocks must split evenly over the epilogue warps");
-      const float* gamma_s = bias_s + TN;
-      const float* beta_s = bias_s + 2 * TN;
+      const int ldn = p.N;
+      const float* gamma_s = bias_s + ldn;
+      const float* beta_s = bias_s + 2 * ldn;
       unsigned char* buf = blocks + ew * 4096;                  // per-warp [32 rows x 128 B] transposition buffer
       const int crow = lane >> 3, cseg = lane & 7;              // coalesced pattern: 8 lanes x 16 B cover one row's 128-byte line
       const uint32_t co_off = (uint32_t)crow * 128, co_seg = (uint32_t)cseg;
       const uint32_t own_off = (uint32_t)lane * 128, own_sw = (uint32_t)lane & 7u;
       GP_TRACE_DECL(7)
-      for (int pt = pair; pt < pair_tiles; pt += num_pairs, ++tile) {
+      for (int pt = pair; pt < pair_tiles; pt += num_pairs) {
         const int row0 = pt * 2 * kGpBM + (int)rank * kGpBM + quad * 32;     // first row of this warp
-        // ---- residual rows: coalesced loads (issued before the accumulator is awaited), transposed to one row per lane ----
         uint32_t xr[BPT][32];      // this thread's values, 2 bf16 per word: first in the coalesced layout, then its own row
-        // element offset of (row0 + crow, column part*64 + cseg*8); block bi / row group i add compile-time constants
-        const size_t goff = (size_t)(row0 + crow) * TN + part * 64 + cseg * 8;
+        // element offset of (row0 + crow, column part*64 + cseg*8); half nt / block bi / row group i add on top
+        const size_t goff = (size_t)(row0 + crow) * ldn + part * 64 + cseg * 8;
         const int rows_left = p.M - row0 - crow;                  // row group i is in range iff 4 i < rows_left
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          // rows past M re-read the last valid row (their results are never stored): no predicated loads, no zero fills
-          const int grow = min(row0 + crow + 4 * i, p.M - 1);
-          const __nv_bfloat16* xp = p.x + (size_t)grow * TN + part * 64 + cseg * 8;
-#pragma unroll
-          for (int bi = 0; bi < BPT; ++bi) {
-            const uint4 t = ld_nc16(xp + bi * (PARTS * 64));
-            xr[bi][4 * i] = t.x; xr[bi][4 * i + 1] = t.y; xr[bi][4 * i + 2] = t.z; xr[bi][4 * i + 3] = t.w;
-          }
-        }
-#pragma unroll
-        for (int bi = 0; bi < BPT; ++bi) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i)    // row 4 i + crow: (row & 7) = ((4 i) & 7) + crow
-            *reinterpret_cast<uint4*>(buf + co_off + i * 512 + ((co_seg ^ (uint32_t)((4 * i + crow) & 7)) << 4)) =
-                make_uint4(xr[bi][4 * i], xr[bi][4 * i + 1], xr[bi][4 * i + 2], xr[bi][4 * i + 3]);
-          __syncwarp();
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const uint4 t = *reinterpret_cast<const uint4*>(buf + own_off + (((uint32_t)q ^ own_sw) << 4));
-            xr[bi][4 * q] = t.x; xr[bi][4 * q + 1] = t.y; xr[bi][4 * q + 2] = t.z; xr[bi][4 * q + 3] = t.w;
-          }
-          __syncwarp();
-        }
-        GP_TRACE(0)
-        mbar_wait(smem_u32(&bars->tmem_full[0]), tile & 1);
-        tc_fence_after();
-        GP_TRACE(1)
-        // ---- pass 1: x' = bf16(x + bf16(acc + bias)) in registers, fp32 sum / sum of squares of the rounded values ----
         uint64_t acc_s = f2_bcast(0.f), acc_q = f2_bcast(0.f);
-#pragma unroll
-        for (int bi = 0; bi < BPT; ++bi) {
-          const int col0 = (PARTS * bi + part) * 64;
-#pragma unroll
-          for (int hh = 0; hh < 4; ++hh) {
-            uint32_t v[16];
-            tmem_ld16_nowait(lane_addr + col0 + hh * 16, v);
-            tmem_ld_wait();
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              const float2 bq = *reinterpret_cast<const float2*>(&bias_s[col0 + hh * 16 + 2 * q]);
-              float y0, y1;
-              f2_unpack(f2_add(f2_pack(__uint_as_float(v[2 * q]), __uint_as_float(v[2 * q + 1])), f2_pack(bq.x, bq.y)), y0, y1);
-              const uint32_t yb = pack_bf16x2(y0, y1);                  // the Linear's bf16 output
-              // the residual add's bf16 output, x + y rounded once (add.rn.bf16x2).  Working on the packed words also keeps
-              // ptxas from unpacking the whole row to fp32 ahead of the accumulator wait (2x the live registers -> spills).
-              const uint32_t sb = add_bf16x2(xr[bi][hh * 8 + q], yb);
-              xr[bi][hh * 8 + q] = sb;
-              const uint64_t sv = f2_pack(bf16_lo(sb), bf16_hi(sb));
-              acc_s = f2_add(acc_s, sv);
-              acc_q = f2_fma(sv, sv, acc_q);
-            }
-          }
-        }
-        // accumulator drained: the next tile's MMAs may start
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(mapa(smem_u32(&bars->tmem_empty[0]), 0));
-        GP_TRACE(2)
-        {
-          float s0, s1, q0, q1;
-          f2_unpack(acc_s, s0, s1);
-          f2_unpack(acc_q, q0, q1);
-          red_s[part * 128 + r] = make_float2(s0 + s1, q0 + q1);
-        }
-        // ---- x' out: one row per lane -> coalesced 128-byte lines ----
-#pragma unroll
-        for (int bi = 0; bi < BPT; ++bi) {
-#pragma unroll
-          for (int q = 0; q < 8; ++q)
-            *reinterpret_cast<uint4*>(buf + own_off + (((uint32_t)q ^ own_sw) << 4)) =
-                make_uint4(xr[bi][4 * q], xr[bi][4 * q + 1], xr[bi][4 * q + 2], xr[bi][4 * q + 3]);
-          __syncwarp();
+        for (int nt = 0; nt < n_tiles; ++nt, ++tile) {
+          const int cb = nt * TN;                                 // first column of this half
+          // ---- residual rows: coalesced loads (issued before the accumulator is awaited), transposed to one row per lane ----
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const uint4 val = *reinterpret_cast<const uint4*>(buf + co_off + i * 512 + ((co_seg ^ (uint32_t)((4 * i + crow) & 7)) << 4));
-            if (4 * i < rows_left) *reinterpret_cast<uint4*>(p.out_sum + goff + 4 * i * TN + bi * (PARTS * 64)) = val;
+            // rows past M re-read the last valid row (their results are never stored): no predicated loads, no zero fills
+            const int grow = min(row0 + crow + 4 * i, p.M - 1);
+            const __nv_bfloat16* xp = p.x + (size_t)grow * ldn + cb + part * 64 + cseg * 8;
+#pragma unroll
+            for (int bi = 0; bi < BPT; ++bi) {
+              const uint4 t = ld_nc16(xp + bi * (PARTS * 64));
+              xr[bi][4 * i] = t.x; xr[bi][4 * i + 1] = t.y; xr[bi][4 * i + 2] = t.z; xr[bi][4 * i + 3] = t.w;
+            }
           }
+#pragma unroll
+          for (int bi = 0; bi < BPT; ++bi) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)    // row 4 i + crow: (row & 7) = ((4 i) & 7) + crow
+              *reinterpret_cast<uint4*>(buf + co_off + i * 512 + ((co_seg ^ (uint32_t)((4 * i + crow) & 7)) << 4)) =
+                  make_uint4(xr[bi][4 * i], xr[bi][4 * i + 1], xr[bi][4 * i + 2], xr[bi][4 * i + 3]);
+            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const uint4 t = *reinterpret_cast<const uint4*>(buf + own_off + (((uint32_t)q ^ own_sw) << 4));
+              xr[bi][4 * q] = t.x; xr[bi][4 * q + 1] = t.y; xr[bi][4 * q + 2] = t.z; xr[bi][4 * q + 3] = t.w;
+            }
+            __syncwarp();
+          }
+          GP_TRACE(0)
+          mbar_wait(smem_u32(&bars->tmem_full[0]), tile & 1);
+          tc_fence_after();
+          GP_TRACE(1)
+          // ---- pass 1: x' = bf16(x + bf16(acc + bias)) in registers, fp32 sum / sum of squares of the rounded values ----
+#pragma unroll
+          for (int bi = 0; bi < BPT; ++bi) {
+            const int col0 = (PARTS * bi + part) * 64;
+#pragma unroll
+            for (int hh = 0; hh < 4; ++hh) {
+              uint32_t v[16];
+              tmem_ld16_nowait(lane_addr + col0 + hh * 16, v);
+              tmem_ld_wait();
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                const float2 bq = *reinterpret_cast<const float2*>(&bias_s[cb + col0 + hh * 16 + 2 * q]);
+                float y0, y1;
+                f2_unpack(f2_add(f2_pack(__uint_as_float(v[2 * q]), __uint_as_float(v[2 * q + 1])), f2_pack(bq.x, bq.y)), y0, y1);
+                const uint32_t yb = pack_bf16x2(y0, y1);                  // the Linear's bf16 output
+                // the residual add's bf16 output, x + y rounded once (add.rn.bf16x2).  Working on the packed words also keeps
+                // ptxas from unpacking the whole row to fp32 ahead of the accumulator wait (2x the live registers -> spills).
+                const uint32_t sb = add_bf16x2(xr[bi][hh * 8 + q], yb);
+                xr[bi][hh * 8 + q] = sb;
+                const uint64_t sv = f2_pack(bf16_lo(sb), bf16_hi(sb));
+                acc_s = f2_add(acc_s, sv);
+                acc_q = f2_fma(sv, sv, acc_q);
+              }
+            }
+          }
+          // accumulator drained: the next half's / tile's MMAs may start
+          tc_fence_before();
           __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(mapa(smem_u32(&bars->tmem_empty[0]), 0));
+          GP_TRACE(2)
+          // ---- x' out: one row per lane -> coalesced 128-byte lines ----
+#pragma unroll
+          for (int bi = 0; bi < BPT; ++bi) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              *reinterpret_cast<uint4*>(buf + own_off + (((uint32_t)q ^ own_sw) << 4)) =
+                  make_uint4(xr[bi][4 * q], xr[bi][4 * q + 1], xr[bi][4 * q + 2], xr[bi][4 * q + 3]);
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const uint4 val = *reinterpret_cast<const uint4*>(buf + co_off + i * 512 + ((co_seg ^ (uint32_t)((4 * i + crow) & 7)) << 4));
+              if (4 * i < rows_left) *reinterpret_cast<uint4*>(p.out_sum + goff + (size_t)4 * i * ldn + cb + bi * (PARTS * 64)) = val;
+            }
+            __syncwarp();
+          }
+          GP_TRACE(3)
         }
-        GP_TRACE(3)
         if (p.want_ln) {
+          {
+            float s0, s1, q0, q1;
+            f2_unpack(acc_s, s0, s1);
+            f2_unpack(acc_q, q0, q1);
+            red_s[part * 128 + r] = make_float2(s0 + s1, q0 + q1);
+          }
           asm volatile("bar.sync %0, %1;" ::"r"(1 + quad), "n"(32 * PARTS) : "memory");     // the warps of this lane quadrant
           float sum = 0.f, sq = 0.f;
 #pragma unroll
           for (int k = 0; k < PARTS; ++k) { const float2 t = red_s[k * 128 + r]; sum += t.x; sq += t.y; }
-          const float mean = sum * (1.0f / TN);
-          const float var = fmaxf(sq * (1.0f / TN) - mean * mean, 0.f);
+          const float inv_n = 1.0f / (float)ldn;
+          const float mean = sum * inv_n;
+          const float var = fmaxf(sq * inv_n - mean * mean, 0.f);
           const float rstd = rsqrtf(var + p.eps);
           const uint64_t sc = f2_bcast(rstd), sh = f2_bcast(-mean * rstd);
           const uint32_t sel_lo = sel_s[0], sel_hi = sel_s[1];
           asm volatile("bar.sync %0, %1;" ::"r"(1 + quad), "n"(32 * PARTS) : "memory");     // red_s may be rewritten by the next tile
           GP_TRACE(4)
-          // ---- pass 2: h = (x' - mean) * rstd * gamma + beta, then out like x' ----
+          // ---- pass 2: h = (x' - mean) * rstd * gamma + beta for the half in registers (the last one), then out like x' ----
+          const int cb_last = (n_tiles - 1) * TN;
 #pragma unroll
           for (int bi = 0; bi < BPT; ++bi) {
-            const int col0 = (PARTS * bi + part) * 64;
+            const int col0 = cb_last + (PARTS * bi + part) * 64;
 #pragma unroll
             for (int q = 0; q < 32; ++q) {
               const float2 g = *reinterpret_cast<const float2*>(&gamma_s[col0 + 2 * q]);
@@ -407,9 +418,35 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const uint4 val = *reinterpret_cast<const uint4*>(buf + co_off + i * 512 + ((co_seg ^ (uint32_t)((4 * i + crow) & 7)) << 4));
-              if (4 * i < rows_left) *reinterpret_cast<uint4*>(p.out_norm + goff + 4 * i * TN + bi * (PARTS * 64)) = val;
+              if (4 * i < rows_left) *reinterpret_cast<uint4*>(p.out_norm + goff + (size_t)4 * i * ldn + cb_last + bi * (PARTS * 64)) = val;
             }
             __syncwarp();
+          }
+          // ---- earlier halves: x' back from the lines this warp stored above (each lane re-reads exactly the 16-byte pieces
+          // it wrote itself), normalised in the coalesced layout ----
+          for (int nt = 0; nt + 1 < n_tiles; ++nt) {
+            const int cb = nt * TN;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float m_i = __shfl_sync(0xffffffffu, mean, 4 * i + crow), r_i = __shfl_sync(0xffffffffu, rstd, 4 * i + crow);
+              if (4 * i < rows_left) {
+#pragma unroll
+                for (int bi = 0; bi < BPT; ++bi) {
+                  const size_t off = goff + (size_t)4 * i * ldn + cb + bi * (PARTS * 64);
+                  const uint4 t = *reinterpret_cast<const uint4*>(p.out_sum + off);
+                  const int col = cb + (PARTS * bi + part) * 64 + cseg * 8;
+                  const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+                  uint32_t o[4];
+#pragma unroll
+                  for (int q = 0; q < 4; ++q) {
+                    const float2 g = *reinterpret_cast<const float2*>(&gamma_s[col + 2 * q]);
+                    const float2 bt = *reinterpret_cast<const float2*>(&beta_s[col + 2 * q]);
+                    o[q] = pack_bf16x2(fmaf((bf16_lo(w[q]) - m_i) * r_i, g.x, bt.x), fmaf((bf16_hi(w[q]) - m_i) * r_i, g.y, bt.y));
+                  }
+                  *reinterpret_cast<uint4*>(p.out_norm + off) = make_uint4(o[0], o[1], o[2], o[3]);
+                }
+              }
+            }
           }
           GP_TRACE(5)
         }
@@ -457,7 +494,7 @@ static int gp_launch(const CUtensorMap& ma, const CUtensorMap& mw, const CUtenso
   using Cfg = GpCfg<MODE, NSUB>;
   constexpr uint32_t kStage = kGpABytes + NSUB * (Cfg::UN / 2) * 128;
   const size_t smem = 1024 + (size_t)Cfg::STAGES * kStage + (size_t)Cfg::BLOCKS * kGpBlkBytes + sizeof(GpBars) +
-                      (MODE == kGpModeLn ? (size_t)3 * Cfg::UN * NSUB * 4 + 4 * 128 * sizeof(float2) + 16 : (size_t)p.N * 4);
+                      (MODE == kGpModeLn ? (size_t)3 * p.N * 4 + 4 * 128 * sizeof(float2) + 16 : (size_t)p.N * 4);
   D2S_REQUIRE(smem <= 227 * 1024, D2S_ERR_ARG, "%s: needs %zu B of shared memory", what, smem);
   static SmemOptIn opt;
   cudaError_t e = opt_in_smem(opt, gemm_pair_kernel<MODE, NSUB, ACT>, 227 * 1024);
@@ -500,9 +537,9 @@ extern "C" int d2s_linear_residual_ln_bf16(const void* a, const void* w, const v
                                            d2s_stream_t stream) {
   const char* what = "d2s_linear_residual_ln_bf16";
   D2S_REQUIRE(a && w && x && out_sum, D2S_ERR_ARG, "linear_residual_ln: null pointer");
-  D2S_REQUIRE(M >= 0 && (N == 192 || N == 384) && K >= kGpBK && K % kGpBK == 0, D2S_ERR_ARG,
-              "linear_residual_ln: need N in {192, 384} (one CTA holds whole rows in TMEM) and K %% %d == 0 (got M=%d N=%d K=%d)",
-              kGpBK, M, N, K);
+  D2S_REQUIRE(M >= 0 && (N == 192 || N == 384 || N == 768) && K >= kGpBK && K % kGpBK == 0, D2S_ERR_ARG,
+              "linear_residual_ln: need N in {192, 384, 768} (a CTA keeps whole rows: in TMEM, or in two 384-column halves) and "
+              "K %% %d == 0 (got M=%d N=%d K=%d)", kGpBK, M, N, K);
   D2S_REQUIRE(!out_norm || (gamma && beta), D2S_ERR_ARG, "linear_residual_ln: out_norm needs gamma and beta");
   D2S_REQUIRE(aligned16(a) && aligned16(w) && aligned16(x) && aligned16(out_sum) && aligned16(out_norm), D2S_ERR_ALIGN,
               "linear_residual_ln: pointers must be 16-byte aligned");
@@ -513,6 +550,6 @@ extern "C" int d2s_linear_residual_ln_bf16(const void* a, const void* w, const v
   if ((rc = gp_map_2d(&mw, w, K, N, kGpBK, 96, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, what))) return rc;
   GpParams p{(const __nv_bfloat16*)bias, (const __nv_bfloat16*)gamma, (const __nv_bfloat16*)beta, (const __nv_bfloat16*)x,
              (__nv_bfloat16*)out_sum, (__nv_bfloat16*)out_norm, nullptr, eps, M, N, K, 0, out_norm ? 1 : 0, gp_trace(), gp_debug()};
-  if (N == 384) return gp_launch<kGpModeLn, 2, 0>(ma, mw, ma, p, (cudaStream_t)stream, what);
+  if (N != 192) return gp_launch<kGpModeLn, 2, 0>(ma, mw, ma, p, (cudaStream_t)stream, what);      // 384, or 768 as two halves
   return gp_launch<kGpModeLn, 1, 0>(ma, mw, ma, p, (cudaStream_t)stream, what);
 }

@@ -190,9 +190,10 @@ def _mlp_fused_ok(m, h, x):
 
 
 def _pair_ok(lin, a, x):
-    """The CTA-pair GEMM with residual + LayerNorm epilogue applies: bf16, whole rows (D in {192, 384}) fit one CTA's TMEM."""
+    """The CTA-pair GEMM with residual + LayerNorm epilogue applies: bf16, whole rows stay in one CTA (D in {192, 384}: in its
+    TMEM; D = 768, DeiT-B: as two 384-column halves)."""
     return (_FUSED_PAIR and isinstance(lin, torch.nn.Linear) and a.dtype == torch.bfloat16 and x.dtype == torch.bfloat16
-            and lin.weight.dtype == torch.bfloat16 and lin.out_features in (192, 384) and lin.in_features % 64 == 0
+            and lin.weight.dtype == torch.bfloat16 and lin.out_features in (192, 384, 768) and lin.in_features % 64 == 0
             and x.shape[-1] == lin.out_features and a.shape[:-1] == x.shape[:-1])
 
 

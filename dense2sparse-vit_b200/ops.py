@@ -1133,7 +1133,7 @@ def linear_act(x, weight, bias, act=ACT_GELU, want_pre=False):
 def linear_residual_ln(a, weight, bias, x, ln_weight=None, ln_bias=None, eps=1e-5, want_norm=True):
     """(x', h) with x' = x + (a @ weight^T + bias) and h = LayerNorm(x') * ln_weight + ln_bias (h None when
     want_norm is False): attn.proj / mlp.fc2 + residual add + the next LayerNorm of Block.forward
-    (vit_models/dynamic_vit.py:263-283) in one CTA-pair tcgen05 GEMM.  bf16, inference only; N in {192, 384}."""
+    (vit_models/dynamic_vit.py:263-283) in one CTA-pair tcgen05 GEMM.  bf16, inference only; N in {192, 384, 768}."""
     _check_cuda(a, weight, bias, x, ln_weight, ln_bias)
     if a.dtype != torch.bfloat16 or x.dtype != torch.bfloat16:
         raise TypeError("linear_residual_ln is a bf16 kernel")

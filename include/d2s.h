@@ -286,7 +286,8 @@ int d2s_linear_act_pair_bf16(const void* a, const void* w, const void* bias, int
  *   y = bf16(a (M,K) @ w (N,K)^T + bias (N));  out_sum (M,N) = bf16(x (M,N) + y);
  *   out_norm (M,N) = LayerNorm(out_sum) * gamma + beta (statistics in fp32), or skipped when out_norm is NULL.
  * Roundings are the reference's (Linear output, residual sum, LayerNorm output each rounded to bf16).
- * N in {192, 384} (a CTA keeps whole rows in TMEM), K % 64 == 0; x may alias out_sum. */
+ * N in {192, 384} (a CTA keeps whole rows in TMEM) or 768 (DeiT-B: two 384-column halves accumulated one after the other, the
+ * row statistics carried across), K % 64 == 0; x may alias out_sum. */
 int d2s_linear_residual_ln_bf16(const void* a, const void* w, const void* bias, const void* x, const void* gamma,
                                 const void* beta, float eps, int M, int N, int K, void* out_sum, void* out_norm,
                                 d2s_stream_t stream);

@@ -57,7 +57,7 @@ def test_argument_errors_precede_any_launch(d2s):
     assert b"head dim" in lib.d2s_last_error()
     assert lib.d2s_softmax_policy_fwd(p, None, 0, 1, 1, 5000, 1e-6, p, None, None) == 1
     # the tcgen05 GEMM family and the training-attention helpers: shape / alignment contracts
-    assert lib.d2s_linear_residual_ln_bf16(p, p, p, p, p, p, 1e-6, 256, 768, 384, p, p, None) == 1 and b"N in {192, 384}" in lib.d2s_last_error()
+    assert lib.d2s_linear_residual_ln_bf16(p, p, p, p, p, p, 1e-6, 256, 576, 384, p, p, None) == 1 and b"N in {192, 384, 768}" in lib.d2s_last_error()
     assert lib.d2s_linear_residual_ln_bf16(p, p, p, p, None, None, 1e-6, 256, 384, 384, p, p, None) == 1 and b"gamma" in lib.d2s_last_error()
     assert lib.d2s_linear_residual_ln_bf16(p, p, p, p, p, p, 1e-6, 256, 384, 100, p, p, None) == 1 and b"K %" in lib.d2s_last_error()
     assert lib.d2s_linear_act_pair_bf16(p, p, p, 256, 300, 384, 1, p, None, None) == 1 and b"N % 256" in lib.d2s_last_error()

@@ -484,6 +484,46 @@ def test_graphed_training_step_matches_eager(d2s, cuda_dev):
     assert losses["graph"][-1] != losses["graph"][0]          # the replays really update the weights
 
 
+def test_deit_b_widths_run_the_fused_pair_gemms(d2s, cuda_dev):
+    """D = 768 (DeiT-B, dynamic_vit.py:1301-1303): proj / fc2 + residual + LayerNorm go through d2s_linear_residual_ln_bf16 with
+    the row kept as two 384-column halves, fc1 + GELU through the CTA-pair GEMM; at keep ratio 1.0 (no token can flip) the bf16
+    logits match the fp32 oracle on identical (bf16-rounded) inputs to 1e-2 (L2) / 2e-2 (max)."""
+    from oracle import model as om
+    kw = dict(patch_size=16, embed_dim=768, depth=3, num_heads=12, num_classes=16, mlp_ratio=4, qkv_bias=True)
+    m = d2s.variant_a.DefaultVisionTransformerDiffPruning(pruning_loc=[1, 2], token_ratio=[1.0, 1.0], distill=True, **kw)
+    sd = fx.seeded_state_dict({k: tuple(v.shape) for k, v in m.state_dict().items()}, 131)
+    sd = {k: (v.bfloat16().float() if v.is_floating_point() else v) for k, v in sd.items()}
+    m.load_state_dict(sd)
+    m = m.to(cuda_dev).eval().to(torch.bfloat16)
+    x = fx.randn(132, 3, 3, 224, 224).bfloat16()
+    calls = []
+    orig = d2s.ops.linear_residual_ln
+    d2s.ops.linear_residual_ln = lambda *a, **k: (calls.append(a[1].shape), orig(*a, **k))[1]
+    try:
+        with torch.no_grad():
+            lg = m(x.to(cuda_dev))
+    finally:
+        d2s.ops.linear_residual_ln = orig
+    assert calls and all(sh[0] == 768 for sh in calls), calls             # the fused kernel really ran, at N = 768
+    assert any(sh[1] == 3072 for sh in calls) and any(sh[1] == 768 for sh in calls)
+    cfg = om.VitCfg(embed_dim=768, depth=3, num_heads=12, num_classes=16, pruning_loc=[1, 2], token_ratio=[1.0, 1.0])
+    ref = om.variant_a_eval(sd, cfg, x.float())["logits"]
+    l2, mx = _bf16_err(lg, ref)
+    assert l2 < 1e-2 and mx < 2e-2, (l2, mx)
+    # real ratios: runs, finite, and selects the oracle's first-stage tokens up to near-ties
+    m2 = d2s.variant_a.DefaultVisionTransformerDiffPruning(pruning_loc=[1, 2], token_ratio=[0.7, 0.49], distill=True, **kw)
+    m2.load_state_dict(sd)
+    m2 = m2.to(cuda_dev).eval().to(torch.bfloat16)
+    with torch.no_grad():
+        lg2 = m2(x.to(cuda_dev))
+    assert bool(torch.isfinite(lg2.float()).all())
+    cfg2 = om.VitCfg(embed_dim=768, depth=3, num_heads=12, num_classes=16, pruning_loc=[1, 2], token_ratio=[0.7, 0.49])
+    ref2 = om.variant_a_eval(sd, cfg2, x.float())
+    a, b = m2.kept_token_indices[0].cpu(), ref2["kept"][0]
+    for r in range(a.shape[0]):
+        assert len(set(a[r].tolist()) & set(b[r].tolist())) >= 0.93 * a.shape[1]
+
+
 def test_flat_adamw_follows_torch_adamw(d2s, cuda_dev):
     """runner.FlatAdamW (one d2s kernel per parameter group over flat buffers) against torch.optim.AdamW on the same parameters
     and gradients: two groups with their own lr / weight decay, sizes that are not multiples of the vector width, an lr change

@@ -733,7 +733,8 @@ def _residual_ln_reference(a, w, b, x, g, bt, eps):
 
 
 @pytest.mark.parametrize("M,N,K", [(256, 384, 384), (1000, 384, 384), (77, 384, 1536), (3 * 197, 384, 1536), (20000, 384, 384),
-                                   (130, 192, 192), (1000, 192, 768), (5 * 138, 384, 64)])
+                                   (130, 192, 192), (1000, 192, 768), (5 * 138, 384, 64),
+                                   (256, 768, 768), (1000, 768, 768), (77, 768, 3072), (3 * 197, 768, 3072), (20000, 768, 768), (5 * 138, 768, 64)])
 def test_linear_residual_ln(ops, M, N, K):
     """proj / fc2 + residual + next LayerNorm (dynamic_vit.py:263-283) in one kernel vs the three separate bf16 ops."""
     a = fx.randn(300 + M % 91, M, K).bfloat16()
