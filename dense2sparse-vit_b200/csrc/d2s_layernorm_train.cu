@@ -117,57 +117,91 @@ ln_fwd_kernel(const TX* __restrict__ x, const TX* __restrict__ res, const float*
   }
 }
 
+// 16-byte asynchronous global -> shared copies (LDGSTS): the bytes in flight no longer sit in registers
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int kN> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(kN) : "memory"); }
+
 // dx = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dh * gamma;  dgamma += dh * xhat;  dbeta += dh
-template <typename TX, typename TH, int kVPL>
+// The inputs of a pass (8 rows: x, dh and the residual-stream gradient) travel through a kStages-deep ring of THREAD-PRIVATE
+// shared-memory slots filled by cp.async: every thread copies exactly the 16-byte pieces it will read itself, so the ring needs
+// no barrier (cp.async.wait_group orders a thread's own copies), and two passes of loads are in flight per thread without
+// costing registers.  With the loads held in registers (167 per thread, 3 CTAs of 128 threads per SM) the kernel had 18 KB in
+// flight per SM and ran at 2-3.4 TB/s.
+template <typename TX, typename TH, int kVPL, int kStages>
 __global__ void __launch_bounds__(kLtBwdThreads)
 ln_bwd_kernel(const TH* __restrict__ dh, const TX* __restrict__ x, const float* __restrict__ stats,
               const float* __restrict__ gamma, const TX* __restrict__ gadd, long long rows, int D, TX* __restrict__ dx,
-              float* __restrict__ dgamma, float* __restrict__ dbeta, int seg, int skip) {
-  extern __shared__ float red[];   // (half-warps per CTA) x D partial column sums
+              float* __restrict__ dgamma, float* __restrict__ dbeta, int seg, int skip, int rows_per_cta) {
+  extern __shared__ __align__(16) unsigned char ln_smem[];
+  float* red = reinterpret_cast<float*>(ln_smem);   // (half-warps per CTA) x D partial column sums
+  constexpr int kXB = 8 * (int)sizeof(TX), kHB = 8 * (int)sizeof(TH);          // bytes of one 8-element piece
+  constexpr int kStageBytes = kLtBwdThreads * kVPL * (2 * kXB + kHB);
+  unsigned char* ring = ln_smem + (size_t)kLtBwdRowsPerIter * D * sizeof(float);
+  // slot of (stage, tensor, k) for this thread: consecutive threads -> consecutive 16-byte words (conflict-free)
+  auto slot_x = [&](int st, int k) { return ring + (size_t)st * kStageBytes + (size_t)(k * kLtBwdThreads + threadIdx.x) * kXB; };
+  auto slot_g = [&](int st, int k) { return ring + (size_t)st * kStageBytes + (size_t)kLtBwdThreads * kVPL * kXB + (size_t)(k * kLtBwdThreads + threadIdx.x) * kXB; };
+  auto slot_h = [&](int st, int k) { return ring + (size_t)st * kStageBytes + (size_t)kLtBwdThreads * kVPL * 2 * kXB + (size_t)(k * kLtBwdThreads + threadIdx.x) * kHB; };
   const int sub = threadIdx.x & 15;
   const int nvec = D / 8;
-  float g[kVPL][8];
-#pragma unroll
-  for (int k = 0; k < kVPL; ++k)
-    if (sub + 16 * k < nvec) TV<float>::load(gamma + (sub + 16 * k) * 8, g[k]);
   float ag[kVPL][8], ab[kVPL][8];
 #pragma unroll
   for (int k = 0; k < kVPL; ++k)
 #pragma unroll
     for (int q = 0; q < 8; ++q) { ag[k][q] = 0.f; ab[k][q] = 0.f; }
-  const long long row_end = min(rows, ((long long)blockIdx.x + 1) * kLtRowsPerCta);
-  for (long long row0 = (long long)blockIdx.x * kLtRowsPerCta; row0 < row_end; row0 += kLtBwdRowsPerIter) {
-    const long long row = row0 + (threadIdx.x >> 4);
-    const bool ok = row < row_end;
-    const float mean = ok ? stats[row * 2] : 0.f, rstd = ok ? stats[row * 2 + 1] : 0.f;
-    const long long xrow = seg_row(row, seg, skip);    // x / gadd / dx: segmented layout; dh and stats: dense
-    float xh[kVPL][8], gg[kVPL][8];
-    float s1 = 0.f, s2 = 0.f;
-    // the residual-stream gradient is fetched together with x and dh (raw 16-byte words, unpacked at the end): issued only
-    // where it is consumed, behind the two row reductions, it exposed a second full memory latency per 8-row pass
-    int4 ga_raw[kVPL][sizeof(TX) == 2 ? 1 : 2];
-    if (gadd) {
+  const long long row_begin = (long long)blockIdx.x * rows_per_cta;
+  const long long row_end = min(rows, row_begin + rows_per_cta);
+  const int iters = (int)((row_end - row_begin + kLtBwdRowsPerIter - 1) / kLtBwdRowsPerIter);
+  auto issue = [&](int it) {
+    if (it < iters) {
+      const long long row = row_begin + (long long)it * kLtBwdRowsPerIter + (threadIdx.x >> 4);
+      if (row < row_end) {
+        const long long xrow = seg_row(row, seg, skip);    // x / gadd / dx: segmented layout; dh and stats: dense
+        const int st = it % kStages;
 #pragma unroll
-      for (int k = 0; k < kVPL; ++k) {
-        const int vi = sub + 16 * k;
-        if (ok && vi < nvec) {
-          const int4* gp = reinterpret_cast<const int4*>(gadd + xrow * D + vi * 8);
-          ga_raw[k][0] = gp[0];
-          if (sizeof(TX) == 4) ga_raw[k][sizeof(TX) == 2 ? 0 : 1] = gp[1];
+        for (int k = 0; k < kVPL; ++k) {
+          const int vi = sub + 16 * k;
+          if (vi < nvec) {
+#pragma unroll
+            for (int c = 0; c < kXB / 16; ++c) cp_async16(slot_x(st, k) + 16 * c, reinterpret_cast<const unsigned char*>(x + xrow * D + vi * 8) + 16 * c);
+#pragma unroll
+            for (int c = 0; c < kHB / 16; ++c) cp_async16(slot_h(st, k) + 16 * c, reinterpret_cast<const unsigned char*>(dh + row * D + vi * 8) + 16 * c);
+            if (gadd) {
+#pragma unroll
+              for (int c = 0; c < kXB / 16; ++c) cp_async16(slot_g(st, k) + 16 * c, reinterpret_cast<const unsigned char*>(gadd + xrow * D + vi * 8) + 16 * c);
+            }
+          }
         }
       }
     }
+    cp_async_commit();          // one group per pass, also when empty: the wait below counts groups
+  };
+#pragma unroll
+  for (int p = 0; p < kStages - 1; ++p) issue(p);
+  for (int it = 0; it < iters; ++it) {
+    issue(it + kStages - 1);
+    cp_async_wait<kStages - 1>();                          // this thread's copies of pass `it` have landed
+    const int st = it % kStages;
+    const long long row = row_begin + (long long)it * kLtBwdRowsPerIter + (threadIdx.x >> 4);
+    const bool ok = row < row_end;
+    const float mean = ok ? stats[row * 2] : 0.f, rstd = ok ? stats[row * 2 + 1] : 0.f;
+    const long long xrow = seg_row(row, seg, skip);
+    float xh[kVPL][8], gg[kVPL][8];
+    float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int k = 0; k < kVPL; ++k) {
       const int vi = sub + 16 * k;
       if (ok && vi < nvec) {
-        float xv[8], dv[8];
-        TV<TX>::load(x + xrow * D + vi * 8, xv);
-        TV<TH>::load(dh + row * D + vi * 8, dv);
+        float xv[8], dv[8], g[8];
+        TV<TX>::load(reinterpret_cast<const TX*>(slot_x(st, k)), xv);
+        TV<TH>::load(reinterpret_cast<const TH*>(slot_h(st, k)), dv);
+        TV<float>::load(gamma + vi * 8, g);
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
           xh[k][q] = (xv[q] - mean) * rstd;
-          gg[k][q] = dv[q] * g[k][q];
+          gg[k][q] = dv[q] * g[q];
           s1 += gg[k][q];
           s2 = fmaf(gg[k][q], xh[k][q], s2);
           ag[k][q] = fmaf(dv[q], xh[k][q], ag[k][q]);
@@ -190,7 +224,7 @@ ln_bwd_kernel(const TH* __restrict__ dh, const TX* __restrict__ x, const float* 
           for (int q = 0; q < 8; ++q) o[q] = rstd * (gg[k][q] - s1 - xh[k][q] * s2);
           if (gadd) {   // gradient that reaches x directly (the residual stream's), accumulated here instead of by a torch add
             float ga[8];
-            TV<TX>::load(reinterpret_cast<const TX*>(&ga_raw[k][0]), ga);
+            TV<TX>::load(reinterpret_cast<const TX*>(slot_g(st, k)), ga);
 #pragma unroll
             for (int q = 0; q < 8; ++q) o[q] += ga[q];
           }
@@ -246,16 +280,37 @@ static int ln_fwd_launch(const void* x, const void* res, const float* gamma, con
   count_launch();
   return check_launch("d2s_layernorm_fwd");
 }
+template <typename TX, typename TH, int kVPL, int kStages>
+static int ln_bwd_launch_cfg(const void* dh, const void* x, const float* stats, const float* gamma, const void* gadd, long long rows,
+                             int D, void* dx, float* dgamma, float* dbeta, int seg, int skip, cudaStream_t st) {
+  const size_t smem = (size_t)kLtBwdRowsPerIter * D * sizeof(float) +
+                      (size_t)kStages * kLtBwdThreads * kVPL * (2 * 8 * sizeof(TX) + 8 * sizeof(TH));
+  // one wave of equally loaded CTAs: as many as fit the GPU at once (shared memory bound), each walking a contiguous row block
+  // of at least kLtRowsPerCta rows in 8-row passes and flushing its column sums once (2 D atomics per CTA)
+  const int per_sm = (int)((227 * 1024) / (smem + 1024));
+  const long long slots = (long long)kNumSMs * (per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm));
+  long long rpc = (rows + slots - 1) / slots;
+  rpc = (rpc + kLtBwdRowsPerIter - 1) / kLtBwdRowsPerIter * kLtBwdRowsPerIter;
+  if (rpc < kLtRowsPerCta) rpc = kLtRowsPerCta;
+  const unsigned grid = (unsigned)((rows + rpc - 1) / rpc);
+  static SmemOptIn opt;
+  cudaError_t e = opt_in_smem(opt, ln_bwd_kernel<TX, TH, kVPL, kStages>, smem);
+  D2S_REQUIRE(e == cudaSuccess, D2S_ERR_CUDA, "layernorm_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+  ln_bwd_kernel<TX, TH, kVPL, kStages><<<grid, kLtBwdThreads, smem, st>>>((const TH*)dh, (const TX*)x, stats, gamma, (const TX*)gadd, rows, D,
+                                                                           (TX*)dx, dgamma, dbeta, seg, skip, (int)rpc);
+  count_launch();
+  return check_launch("d2s_layernorm_bwd");
+}
 template <typename TX, typename TH>
 static int ln_bwd_launch(const void* dh, const void* x, const float* stats, const float* gamma, const void* gadd, long long rows,
                          int D, void* dx, float* dgamma, float* dbeta, int seg, int skip, cudaStream_t st) {
+  // ring depth: three passes (two in flight) where three CTAs still fit an SM, else two
   const int vpl = ceil_div(D / 8, 16);
-  const unsigned grid = (unsigned)((rows + kLtRowsPerCta - 1) / kLtRowsPerCta);
-  const size_t smem = (size_t)kLtBwdRowsPerIter * D * sizeof(float);
-  if (vpl <= 3) ln_bwd_kernel<TX, TH, 3><<<grid, kLtBwdThreads, smem, st>>>((const TH*)dh, (const TX*)x, stats, gamma, (const TX*)gadd, rows, D, (TX*)dx, dgamma, dbeta, seg, skip);
-  else          ln_bwd_kernel<TX, TH, 6><<<grid, kLtBwdThreads, smem, st>>>((const TH*)dh, (const TX*)x, stats, gamma, (const TX*)gadd, rows, D, (TX*)dx, dgamma, dbeta, seg, skip);
-  count_launch();
-  return check_launch("d2s_layernorm_bwd");
+  if (vpl <= 3) {
+    if (sizeof(TX) == 2) return ln_bwd_launch_cfg<TX, TH, 3, 3>(dh, x, stats, gamma, gadd, rows, D, dx, dgamma, dbeta, seg, skip, st);
+    return ln_bwd_launch_cfg<TX, TH, 3, 2>(dh, x, stats, gamma, gadd, rows, D, dx, dgamma, dbeta, seg, skip, st);
+  }
+  return ln_bwd_launch_cfg<TX, TH, 6, 2>(dh, x, stats, gamma, gadd, rows, D, dx, dgamma, dbeta, seg, skip, st);
 }
 
 static int ln_check(const char* what, long long rows, int D, int dx, int dh) {

@@ -33,7 +33,7 @@ template <> struct KlRow<__nv_bfloat16> {
   }
 };
 
-template <typename TS, typename TT>
+template <typename TS, typename TT, int kK>
 __global__ void __launch_bounds__(kKlWarps * 32)
 token_kl_fwd_kernel(const TS* __restrict__ s, long long s_bstride, const TT* __restrict__ t, long long t_bstride, long long rows,
                     int N, int C, float* __restrict__ kl, float* __restrict__ diff) {
@@ -45,10 +45,10 @@ token_kl_fwd_kernel(const TS* __restrict__ s, long long s_bstride, const TT* __r
   const TS* sp = s + b * s_bstride + (long long)n * C;
   const TT* tp = t + b * t_bstride + (long long)n * C;
   const int nchunk = C / 8;
-  float sv[kKlMaxK][8], tv[kKlMaxK][8];
+  float sv[kK][8], tv[kK][8];
   float ms = -INFINITY, mt = -INFINITY;
 #pragma unroll
-  for (int k = 0; k < kKlMaxK; ++k) {
+  for (int k = 0; k < kK; ++k) {
     const int j = lane + 32 * k;
     if (j < nchunk) {
       KlRow<TS>::load8(sp + j * 8, sv[k]);
@@ -59,33 +59,41 @@ token_kl_fwd_kernel(const TS* __restrict__ s, long long s_bstride, const TT* __r
   }
   ms = warp_max(ms);
   mt = warp_max(mt);
+  // one exponential per element and tensor: e = exp(x - max) is kept and reused for the probabilities; the log-probabilities are
+  // (x - max) - log(sum e), so the row needs two logarithms in all.  lds = (s - ms) - (t - mt) overwrites sv.
   float es = 0.f, et = 0.f;
 #pragma unroll
-  for (int k = 0; k < kKlMaxK; ++k)
+  for (int k = 0; k < kK; ++k)
     if (lane + 32 * k < nchunk) {
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
-        sv[k][q] -= ms;
-        tv[k][q] -= mt;
-        es += expf(sv[k][q]);
-        et += expf(tv[k][q]);
+        const float ds = sv[k][q] - ms, dt = tv[k][q] - mt;
+        const float xs = __expf(ds), xt = __expf(dt);
+        es += xs;
+        et += xt;
+        sv[k][q] = xs;
+        tv[k][q] = xt;
       }
     }
   es = warp_sum(es);
   et = warp_sum(et);
-  const float ls = logf(es), lt = logf(et);
+  // kl = sum_c pt (lpt - lps),  lpt - lps = (t - mt) - (s - ms) - (log et - log es) = log(xt / xs) - log(et / es): computed from
+  // the differences of the shifted logits, which are reloaded (L1 hits) rather than kept in a third register array
+  const float inv_s = 1.f / es, inv_t = 1.f / et;
+  const float lratio = (mt + logf(et)) - (ms + logf(es));         // log-partition difference: lpt - lps = (t - s) - lratio
   float acc = 0.f;
 #pragma unroll
-  for (int k = 0; k < kKlMaxK; ++k) {
+  for (int k = 0; k < kK; ++k) {
     const int j = lane + 32 * k;
     if (j < nchunk) {
-      float d[8];
+      float s0[8], t0[8], d[8];
+      KlRow<TS>::load8(sp + j * 8, s0);
+      KlRow<TT>::load8(tp + j * 8, t0);
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
-        const float lps = sv[k][q] - ls, lpt = tv[k][q] - lt;
-        const float pt = expf(lpt);
-        acc = fmaf(pt, lpt - lps, acc);
-        d[q] = expf(lps) - pt;
+        const float pt = tv[k][q] * inv_t;
+        acc = fmaf(pt, (t0[q] - s0[q]) - lratio, acc);
+        d[q] = fmaf(sv[k][q], inv_s, -pt);
       }
       float* dp = diff + r * C + j * 8;
       *reinterpret_cast<float4*>(dp) = make_float4(d[0], d[1], d[2], d[3]);
@@ -100,7 +108,10 @@ template <typename TS, typename TT>
 static int token_kl_launch(const void* s, long long sb, const void* t, long long tb, long long rows, int N, int C, float* kl, float* diff,
                            cudaStream_t st) {
   const long long grid = (rows + kKlWarps - 1) / kKlWarps;
-  token_kl_fwd_kernel<TS, TT><<<(unsigned)grid, kKlWarps * 32, 0, st>>>((const TS*)s, sb, (const TT*)t, tb, rows, N, C, kl, diff);
+  if (C <= 512)
+    token_kl_fwd_kernel<TS, TT, 2><<<(unsigned)grid, kKlWarps * 32, 0, st>>>((const TS*)s, sb, (const TT*)t, tb, rows, N, C, kl, diff);
+  else
+    token_kl_fwd_kernel<TS, TT, kKlMaxK><<<(unsigned)grid, kKlWarps * 32, 0, st>>>((const TS*)s, sb, (const TT*)t, tb, rows, N, C, kl, diff);
   count_launch();
   return check_launch("d2s_token_kl_fwd");
 }
