@@ -30,6 +30,19 @@ constexpr int tc_threads(int ksw) { return 32 * (ksw + 1); }
 constexpr float kMaxBinades = 100.0f;
 constexpr float kBigSum = 1.2676506e30f;   // 2^100: a 16-column partial sum beyond it triggers the check of the chunk maximum
 
+// clock64 wait / phase totals per CTA (profiling builds only: D2S_NVCC_EXTRA=-DD2S_ATTN_TRACE_BUILD; scripts/bench_attn_trace.py)
+#ifdef D2S_ATTN_TRACE_BUILD
+__device__ long long d2s_tc_trace_buf[1024 * 16];
+#define TC_TRACE_DECL long long tr[8] = {}; long long tr_t = clock64(); const long long tr_begin = tr_t;
+#define TC_TRACE(i) { const long long tr_n = clock64(); tr[i] += tr_n - tr_t; tr_t = tr_n; }
+#define TC_TRACE_DUMP(slot) if (lane == 0 && blockIdx.x < 1024) { long long* dst = d2s_tc_trace_buf + (size_t)blockIdx.x * 16 + (slot) * 8; \
+    for (int i = 0; i < 7; ++i) dst[i] = tr[i]; dst[7] = clock64() - tr_begin; }
+#else
+#define TC_TRACE_DECL
+#define TC_TRACE(i)
+#define TC_TRACE_DUMP(slot)
+#endif
+
 struct TcBars {
   uint64_t q_full[2], k_full[2], v_full, s_full, p_full, o_full, tmem_free;
   uint32_t tmem_base;
@@ -135,6 +148,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         issue_v(unit);
       }
       uint32_t g = 0;  // tiles processed by this CTA: parity source for the per-tile barriers
+      TC_TRACE_DECL
       for (uint32_t it = 0; unit < num_units; unit += gridDim.x, ++it) {
         const int next = unit + gridDim.x;
         const bool has_next = next < num_units;
@@ -145,9 +159,13 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         const uint64_t kd = make_desc_sw128(smem_u32(k_s0 + (size_t)kb * Tkp * 128), 16, 1024);
 #pragma unroll
         for (int t = 0; t < kNT; ++t, ++g) {
+          TC_TRACE(6)
           if (t == 0) mbar_wait(smem_u32(&bars->k_full[kb]), k_parity);
+          TC_TRACE(0)
           mbar_wait(smem_u32(&bars->q_full[t]), it & 1);
+          TC_TRACE(1)
           if (g > 0) mbar_wait(smem_u32(&bars->tmem_free), (g - 1) & 1);
+          TC_TRACE(2)
           tc_fence_after();
           const uint64_t qd = make_desc_sw128(smem_u32(q_s[t]), 16, 1024);
           if (elect_one()) {
@@ -159,12 +177,16 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
           }
           __syncwarp();
           const bool last = t == kNT - 1;
+          TC_TRACE(6)
           mbar_wait(smem_u32(&bars->p_full), g & 1);   // softmax done => this tile's S-MMA has completed as well
+          TC_TRACE(3)
           if (has_next) {
             issue_q(next, t);                          // this Q tile is dead: refill it during PV / epilogue / softmax
             if (last && kbufs == 1) issue_k(next, it + 1);
           }
+          TC_TRACE(6)
           if (t == 0) mbar_wait(smem_u32(&bars->v_full), it & 1);
+          TC_TRACE(4)
           tc_fence_after();
           // fully unrolled issue (T <= 256 => at most 16 K-steps); descriptors advance by constants
           const int split = kSW == 8 ? (ksteps + 1) / 2 : 16;   // first K-step whose P lives in the second half's region
@@ -180,11 +202,15 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
           }
           __syncwarp();
           if (last && has_next) {
+            TC_TRACE(6)
             mbar_wait(smem_u32(&bars->o_full), g & 1);  // V is dead once the PV-MMA has completed
+            TC_TRACE(5)
             issue_v(next);
           }
         }
       }
+      TC_TRACE(6)
+      TC_TRACE_DUMP(0)
     }
   } else {
     // ===================================== softmax / epilogue warps =====================================
@@ -198,6 +224,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     uint32_t g = 0;
     constexpr int kPolPer = 256 / (32 * kSW);                     // policy elements per softmax thread (256-entry row buffer)
     float pol_next[kPolPer];
+    TC_TRACE_DECL
     for (uint32_t it = 0, unit = blockIdx.x; (int)unit < num_units; unit += gridDim.x, ++it) {
       const int b = unit / H, h = unit % H;
       if (kPol) {
@@ -250,7 +277,9 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         // key columns of this warp: all of them (kSW == 4) or one half, split at a 16-column chunk boundary
         const int ch_lo = (kSW == 8 && half == 1) ? (nchunks + 1) / 2 : 0;
         const int ch_hi = (kSW == 8 && half == 0) ? (nchunks + 1) / 2 : nchunks;
+        TC_TRACE(6)
         mbar_wait(smem_u32(&bars->s_full), g & 1);
+        TC_TRACE(0)
         tc_fence_after();
         float sum = 0.f, mx_true = -INFINITY, mxk = 0.f;
         const bool want_cls = (cls_row != nullptr) && (i == 0);
@@ -298,10 +327,12 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
           mxk = floorf(mx * k2);
           mx_true = mx;
           for (int ch = ch_lo; ch < ch_hi; ++ch) {
+            TC_TRACE(6)
             if (ch != ch_ref || ch != ch_lo) {   // (the reference chunk is still in registers only if it comes first)
               tmem_ld16_nowait(lane_addr + (uint32_t)(ch * 16), v);
               tmem_ld_wait();
             }
+            TC_TRACE(1)
             float a[16];
             const bool full = ch * 16 + 16 <= T;
             // exponentials against the current reference; the chunk's own partial sums double as the overflow detector (a sum
@@ -367,11 +398,13 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
 #pragma unroll
               for (int q = 0; q < 16; ++q) cls_s[ch * 16 + q] = a[q];
             }
+            TC_TRACE(5)
             uint32_t packed[8];
 #pragma unroll
             for (int q = 0; q < 8; ++q) packed[q] = pack_bf16x2(a[2 * q], a[2 * q + 1]);
             // P overlays S columns this warp has already consumed
             tmem_st8(lane_addr + pcol(ch), packed);
+            TC_TRACE(2)
           }
           if (kPol) {
             // a MASKED key far above every kept one never shows in the sums: the reference still subtracts it (its row then
@@ -406,9 +439,11 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         } else {
           sum = (s0 + s1) + (s2 + s3);
         }
+        TC_TRACE(6)
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         tc_fence_before();
         mbar_arrive(smem_u32(&bars->p_full));
+        TC_TRACE(2)
         const float eps_scale = (kPol && warp_active) ? ex2_approx(fmaf(mx_true, k2, -mxk)) : 1.0f;   // <= 2^kMaxBinades
         const float den = sum + eps_den * eps_scale;
         const float c_eps_row = c_eps * eps_scale;
@@ -428,7 +463,9 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         // ---- epilogue: this warp's share of the 64 output columns -------------------------------------------
         constexpr int kOC = kSW == 8 ? 32 : 64;            // output columns per warp
         const int oc0 = kSW == 8 ? half * 32 : 0;
+        TC_TRACE(6)
         mbar_wait(smem_u32(&bars->o_full), g & 1);
+        TC_TRACE(3)
         tc_fence_after();
         if constexpr (kNT == 2) {
           uint32_t ow[kOC / 2];   // packed bf16
@@ -487,8 +524,10 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
           tc_fence_before();
           mbar_arrive(smem_u32(&bars->tmem_free));
         }
+        TC_TRACE(4)
       }
     }
+    if (warp == 0) { TC_TRACE_DUMP(1) }
   }
   tc_fence_before();
   __syncthreads();
@@ -558,6 +597,13 @@ static int launch_tc(const CUtensorMap& map_a, const CUtensorMap& map_b, const f
 }  // namespace d2s
 
 using namespace d2s;
+
+#ifdef D2S_ATTN_TRACE_BUILD
+extern "C" int d2s_debug_attn_trace(long long* host_out, int n_ctas) {   // profiling builds only; not part of include/d2s.h
+  cudaDeviceSynchronize();
+  return (int)cudaMemcpyFromSymbol(host_out, d2s_tc_trace_buf, (size_t)n_ctas * 16 * sizeof(long long));
+}
+#endif
 
 extern "C" int d2s_attn_policy_fwd(const void* qkv, const float* policy, int dtype, int B, int T, int H, int hd,
                                    float scale, float eps, void* out, float* cls_row, float* stats, d2s_stream_t stream_) {
