@@ -293,8 +293,11 @@ static int ln_bwd_launch_cfg(const void* dh, const void* x, const float* stats, 
   rpc = (rpc + kLtBwdRowsPerIter - 1) / kLtBwdRowsPerIter * kLtBwdRowsPerIter;
   if (rpc < kLtRowsPerCta) rpc = kLtRowsPerCta;
   const unsigned grid = (unsigned)((rows + rpc - 1) / rpc);
+  // opt in once per device for the largest row this instantiation takes (D <= 128 kVPL): the memo does not know about D
+  constexpr size_t kSmemMax = (size_t)kLtBwdRowsPerIter * (128 * kVPL) * sizeof(float) +
+                              (size_t)kStages * kLtBwdThreads * kVPL * (2 * 8 * sizeof(TX) + 8 * sizeof(TH));
   static SmemOptIn opt;
-  cudaError_t e = opt_in_smem(opt, ln_bwd_kernel<TX, TH, kVPL, kStages>, smem);
+  cudaError_t e = opt_in_smem(opt, ln_bwd_kernel<TX, TH, kVPL, kStages>, (int)kSmemMax);
   D2S_REQUIRE(e == cudaSuccess, D2S_ERR_CUDA, "layernorm_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   ln_bwd_kernel<TX, TH, kVPL, kStages><<<grid, kLtBwdThreads, smem, st>>>((const TH*)dh, (const TX*)x, stats, gamma, (const TX*)gadd, rows, D,
                                                                            (TX*)dx, dgamma, dbeta, seg, skip, (int)rpc);
