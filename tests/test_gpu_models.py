@@ -552,6 +552,19 @@ def test_flat_adamw_follows_torch_adamw(d2s, cuda_dev):
     assert float(opt.step_t) == 6.0
     opt.close()
     assert d2s.ops.BF16WeightCache.lookup(mine[0]) is None
+    # grad_scale (the 1 / world of the data-parallel mean, folded into the kernel): same as scaling the gradients first
+    n = 1000
+    p1, g = fx.randn(500, n).to(cuda_dev), fx.randn(501, n).to(cuda_dev)
+    p2 = p1.clone()
+    m1, v1, m2, v2 = (torch.zeros(n, device=cuda_dev) for _ in range(4))
+    lr, st = torch.full((1,), 1e-3, device=cuda_dev), torch.ones(1, device=cuda_dev)
+    d2s.ops.adamw_flat(p1, g, m1, v1, None, 0, n, lr, st, 0.9, 0.999, 1e-8, 0.01, grad_scale=0.125)
+    d2s.ops.adamw_flat(p2, g * 0.125, m2, v2, None, 0, n, lr, st, 0.9, 0.999, 1e-8, 0.01)
+    assert torch.equal(p1, p2) and torch.equal(m1, m2) and torch.equal(v1, v2)
+    # a sub-range leaves everything outside it untouched (parameter groups are ranges of one buffer), unaligned ends included
+    p3, before = p2.clone(), p2.clone()
+    d2s.ops.adamw_flat(p3, g, m2, v2, None, 13, 770, lr, st, 0.9, 0.999, 1e-8, 0.01)
+    assert torch.equal(p3[:13], before[:13]) and torch.equal(p3[770:], before[770:]) and not torch.equal(p3[13:770], before[13:770])
 
 
 def test_gradient_slots_receive_what_autograd_would_accumulate(d2s, cuda_dev):
