@@ -108,6 +108,8 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = bars->tmem_base;
+  pdl_wait();       // set-up above overlaps the previous kernel's tail (d2s_common.cuh, launch_pdl); qkv / policy are read below
+  pdl_trigger();
 
   if (warp_uniform(warp) == kSW) {
     {
@@ -588,8 +590,9 @@ static int launch_tc(const CUtensorMap& map_a, const CUtensorMap& map_b, const f
   cudaError_t e = opt_in_smem(opt, kern, 113 * 1024);
   D2S_REQUIRE(e == cudaSuccess, D2S_ERR_CUDA, "attn_policy_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   const int grid = units < per_sm * kNumSMs ? units : per_sm * kNumSMs;
-  kern<<<grid, tc_threads(kSW), smem, stream>>>(map_a, map_b, policy, units, T, H, Tkp, kbufs, scale, eps,
-                                           (__nv_bfloat16*)out, cls_row, stats);
+  e = launch_pdl(kern, dim3(grid), dim3(tc_threads(kSW)), smem, stream, map_a, map_b, policy, units, T, H, Tkp, kbufs, scale, eps,
+                 (__nv_bfloat16*)out, cls_row, stats);
+  D2S_REQUIRE(e == cudaSuccess, D2S_ERR_CUDA, "attn_policy_fwd: launch: %s", cudaGetErrorString(e));
   count_launch();
   return check_launch("d2s_attn_policy_fwd(tcgen05)");
 }

@@ -125,6 +125,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)), "n"(512) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
   }
+  pdl_wait();       // everything above overlaps the previous kernel's tail; nothing below may run before its writes are visible
+  pdl_trigger();
   if (MODE == kGpModeLn) {
     for (int i = tid; i < p.N; i += kThreads) {
       bias_s[i] = p.bias ? __bfloat162float(p.bias[i]) : 0.f;
@@ -501,7 +503,8 @@ static int gp_launch(const CUtensorMap& ma, const CUtensorMap& mw, const CUtenso
   D2S_REQUIRE(e == cudaSuccess, D2S_ERR_CUDA, "%s: cudaFuncSetAttribute: %s", what, cudaGetErrorString(e));
   const int pair_tiles = (p.M + 2 * kGpBM - 1) / (2 * kGpBM);
   const int pairs = pair_tiles < kNumSMs / 2 ? pair_tiles : kNumSMs / 2;
-  gemm_pair_kernel<MODE, NSUB, ACT><<<2 * pairs, (2 + 4 * Cfg::PARTS) * 32, smem, stream>>>(ma, mw, mo, p);
+  e = launch_pdl(gemm_pair_kernel<MODE, NSUB, ACT>, dim3(2 * pairs), dim3((2 + 4 * Cfg::PARTS) * 32), smem, stream, ma, mw, mo, p);
+  D2S_REQUIRE(e == cudaSuccess, D2S_ERR_CUDA, "%s: launch: %s", what, cudaGetErrorString(e));
   count_launch();
   return check_launch(what);
 }

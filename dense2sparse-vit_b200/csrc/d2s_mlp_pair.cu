@@ -122,6 +122,8 @@ mlp_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)), "n"(512) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
   }
+  pdl_wait();       // barrier set-up and the TMEM allocation overlap the previous kernel's tail (d2s_common.cuh, launch_pdl)
+  pdl_trigger();
   for (int i = tid; i < p.HID; i += kMpThreads) b1_s[i] = p.b1 ? __bfloat162float(p.b1[i]) : 0.f;
   for (int i = tid; i < TN; i += kMpThreads) {
     b2_s[i] = p.b2 ? __bfloat162float(p.b2[i]) : 0.f;
@@ -526,7 +528,8 @@ extern "C" int d2s_mlp_residual_ln_bf16(const void* h, const void* w1, const voi
   D2S_REQUIRE(e == cudaSuccess, D2S_ERR_CUDA, "mlp_residual_ln: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   const int pair_tiles = (M + 2 * kMpBM - 1) / (2 * kMpBM);
   const int pairs = pair_tiles < kNumSMs / 2 ? pair_tiles : kNumSMs / 2;
-  mlp_pair_kernel<<<2 * pairs, kMpThreads, smem, (cudaStream_t)stream>>>(ma, mw1, mw2, p);
+  e = launch_pdl(mlp_pair_kernel, dim3(2 * pairs), dim3(kMpThreads), smem, (cudaStream_t)stream, ma, mw1, mw2, p);
+  D2S_REQUIRE(e == cudaSuccess, D2S_ERR_CUDA, "mlp_residual_ln: launch: %s", cudaGetErrorString(e));
   count_launch();
   return check_launch(what);
 }
