@@ -58,6 +58,7 @@ def parse():
     ap.add_argument("--train-steps", type=int, default=10)
     ap.add_argument("--cpu-batch", type=int, default=8, help="images per CPU step (BASELINE configs[0])")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--teacher-stream", type=int, default=1, help="training leg: run the frozen teacher on a second stream (1) or inline (0)")
     ap.add_argument("--torch-adamw", action="store_true", help="training leg: torch.optim.AdamW(capturable) instead of runner.FlatAdamW")
     ap.add_argument("--skip-cpu", action="store_true", help="omit the cpu_baseline leg (debugging only)")
     ap.add_argument("--legs", default=",".join(ALL_LEGS), help="comma-separated subset of: " + ", ".join(ALL_LEGS))
@@ -489,8 +490,12 @@ def train_leg(pkg, args, dev, rank, world, torch, dist, pk):
     x = torch.randn(B, 3, 224, 224, device=dev, generator=g)
     y = torch.randint(0, 1000, (B,), device=dev, generator=g)
 
+    tstream = torch.cuda.Stream(device=dev) if args.teacher_stream else None
+
     def fwd_loss(xx, yy):
         with torch.autocast("cuda", dtype=torch.bfloat16):
+            if tstream is not None:          # the frozen teacher's forward on a second stream, concurrent with the student's
+                crit.start_teacher(xx, tstream)
             return crit(xx, student(xx), yy)[0]
 
     n0 = pkg._lib.launch_count()
@@ -536,6 +541,7 @@ def train_leg(pkg, args, dev, rank, world, torch, dist, pk):
            "collective": (f"one NCCL all-reduce of the flat fp32 gradient buffer ({grad_bytes / 1e6:.1f} MB) per step, captured in the "
                           f"step's CUDA graph between backward and AdamW" if world > 1 else "none (single GPU)"),
            "allreduce_floor_ms": (2 * (world - 1) / world * grad_bytes / 725e9 * 1e3) if world > 1 else 0.0,
+           "teacher": "second stream, concurrent with the student forward (forks from and rejoins the captured stream)" if args.teacher_stream else "inline",
            "optimizer": "torch.optim.AdamW(capturable)" if args.torch_adamw else "runner.FlatAdamW (d2s_adamw_flat_f32: one launch, also writes the bf16 weight copies)",
            "limiter": "tensor + HBM bound single-GPU step; the all-reduce is not overlapped with backward (it is ~1-2 % of the step)",
            "tensor_frac_of_sustained_peak": val / world * TRAIN_GFLOP_PER_IMG / 1e3 / pk["tf_sustained"]}

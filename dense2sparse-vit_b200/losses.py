@@ -34,6 +34,26 @@ class DistillDiffPruningLoss(torch.nn.Module):
         self.ratio_weight, self.distill_weight, self.clf_weight = ratio_weight, distill_weight, clf_weight
         self.keep_ratio = list(keep_ratio)
         self.print_mode = print_mode
+        self._pending = None
+
+    def start_teacher(self, inputs, stream):
+        """Launch the frozen teacher's forward on `stream` NOW (typically right before the student's forward on the current
+        stream): the two forwards are independent, so their kernels interleave and each fills the other's launch and tail gaps;
+        forward() on the same `inputs` then joins the stream and uses the outputs instead of running the teacher itself.
+        Works under CUDA-graph capture (the side stream forks from and rejoins the capturing stream)."""
+        cur = torch.cuda.current_stream(inputs.device)
+        stream.wait_stream(cur)
+        with torch.cuda.stream(stream), torch.no_grad():
+            out = self.teacher_model(inputs)[:2]
+        self._pending = (inputs, out, stream)
+
+    def _teacher_outputs(self, inputs):
+        pending, self._pending = self._pending, None
+        if pending is not None and pending[0] is inputs:
+            torch.cuda.current_stream(inputs.device).wait_stream(pending[2])
+            return pending[1]
+        with torch.no_grad():
+            return self.teacher_model(inputs)[:2]
 
     def forward(self, inputs, outputs, labels):
         pred, token_pred, mask, out_pred_score = outputs
@@ -42,8 +62,7 @@ class DistillDiffPruningLoss(torch.nn.Module):
         for i, score in enumerate(out_pred_score):
             ratio_loss = ratio_loss + ((score.float().mean(dim=1) - self.keep_ratio[i]) ** 2).mean()
         cls_loss = self.base_criterion(pred.float(), labels)
-        with torch.no_grad():
-            cls_t, token_t = self.teacher_model(inputs)[:2]
+        cls_t, token_t = self._teacher_outputs(inputs)
         cls_kl = F.kl_div(F.log_softmax(pred.float(), dim=-1), F.log_softmax(cls_t.float(), dim=-1),
                           reduction="batchmean", log_target=True)
         # token distillation over the KEPT tokens: KL(teacher || student) per token row, "batchmean" over the kept rows.  Written

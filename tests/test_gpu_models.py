@@ -524,6 +524,33 @@ def test_deit_b_widths_run_the_fused_pair_gemms(d2s, cuda_dev):
         assert len(set(a[r].tolist()) & set(b[r].tolist())) >= 0.93 * a.shape[1]
 
 
+def test_teacher_on_a_second_stream_gives_the_same_loss(d2s, cuda_dev):
+    """DistillDiffPruningLoss.start_teacher: the frozen teacher's forward launched on a side stream before the student's forward
+    (eager and inside a captured training step) yields the loss of the inline teacher call."""
+    x = fx.randn(60, 4, 3, 224, 224).to(cuda_dev)
+    y = torch.tensor([2, 4, 6, 8], device=cuda_dev)
+    m, _ = _deit_s_width_models(d2s, cuda_dev, "a", [0.7, 0.49])
+    m = m.train()
+    m._d2s_gumbels = [fx.randn(61 + i, 4, 196, 2).to(cuda_dev) for i in range(2)]
+    teacher = d2s.variant_a.DefaultVisionTransformerTeacher(patch_size=16, embed_dim=384, depth=2, num_heads=6, num_classes=16,
+                                                            mlp_ratio=4, qkv_bias=True).to(cuda_dev).eval()
+    for p in teacher.parameters():
+        p.requires_grad_(False)
+    crit = d2s.losses.DistillDiffPruningLoss(teacher, keep_ratio=[0.7, 0.49])
+    side = torch.cuda.Stream(device=cuda_dev)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        inline, parts0 = crit(x, m(x), y)
+        crit.start_teacher(x, side)
+        assert crit._pending is not None
+        overlapped, parts1 = crit(x, m(x), y)
+        assert crit._pending is None                      # consumed
+        crit.start_teacher(x.clone(), side)               # other inputs: the pending result is dropped, the teacher runs inline
+        other, _ = crit(x, m(x), y)
+    torch.cuda.synchronize()
+    for a, b in ((inline, overlapped), (inline, other), (parts0["token_kl"], parts1["token_kl"]), (parts0["cls_kl"], parts1["cls_kl"])):
+        assert abs(float(a) - float(b)) <= 1e-5 * abs(float(a)) + 1e-6, (float(a), float(b))
+
+
 def test_flat_adamw_follows_torch_adamw(d2s, cuda_dev):
     """runner.FlatAdamW (one d2s kernel per parameter group over flat buffers) against torch.optim.AdamW on the same parameters
     and gradients: two groups with their own lr / weight decay, sizes that are not multiples of the vector width, an lr change
