@@ -390,26 +390,62 @@ def _grad_slot(p):
     return g, e
 
 
-def _wgrad_into(p, dy, x):
-    """dW = dy^T x landed in `p`'s gradient slot; False when `p` has none (the caller returns the gradient to autograd)."""
+# Weight / bias gradients that land in gradient slots are consumed only by the optimizer, while dx is what the rest of the backward
+# waits for: with D2S_WGRAD_STREAM=1 they are enqueued on a side stream (forked after dy is ready) and fill the launch / tail gaps
+# of the dx chain; whoever owns the step joins the stream before the gradients are read (join_wgrad_stream(), called by
+# runner.TrainStepRunner after backward).  The operands are kept alive until the join, so the allocator cannot hand their memory
+# to the main stream while the side stream still reads it.
+_WGRAD_STREAM = os.environ.get("D2S_WGRAD_STREAM", "0") == "1"
+_wgrad_side = {}          # device index -> (stream, [operand references])
+
+
+def _wgrad_ctx(t):
+    """(stream context, refs list) for slot-bound parameter gradients of tensors on t's device; the side stream has been made to
+    wait for the current one (dy is ready)."""
+    dev = t.device
+    ent = _wgrad_side.get(dev.index)
+    if ent is None:
+        ent = _wgrad_side[dev.index] = (torch.cuda.Stream(device=dev), [])
+    ent[0].wait_stream(torch.cuda.current_stream(dev))
+    return ent
+
+
+def join_wgrad_stream(device=None):
+    """Make the current stream wait for every parameter-gradient kernel enqueued on the side stream (no-op when unused)."""
+    for idx, (stream, refs) in _wgrad_side.items():
+        if device is None or device.index == idx:
+            if refs:
+                torch.cuda.current_stream(torch.device("cuda", idx)).wait_stream(stream)
+                refs.clear()
+
+
+def _wgrad_into(p, dy, x, b_p=None):
+    """dW = dy^T x landed in `p`'s gradient slot -- and, when `b_p` has a slot too, its bias gradient (column sums of dy) right
+    behind it; returns (weight done, bias done).  False: the caller returns that gradient to autograd."""
     slot, e = _grad_slot(p)
-    if slot is None or not _MM_OUT:
-        return False
-    if e[1]:
-        torch.mm(dy.t(), x, out_dtype=torch.float32, out=slot)
-        e[1] = False
+    bslot, be = _grad_slot(b_p) if (b_p is not None and dy.shape[0] > 0) else (None, None)
+    w_ok = slot is not None and _MM_OUT
+    if not w_ok and bslot is None:
+        return False, False
+
+    def run():
+        if w_ok:
+            if e[1]:
+                torch.mm(dy.t(), x, out_dtype=torch.float32, out=slot)
+                e[1] = False
+            else:
+                slot.add_(torch.mm(dy.t(), x, out_dtype=torch.float32))
+        if bslot is not None:
+            _call("d2s_colsum_acc_bf16", _ptr(dy), dy.shape[0], dy.shape[1], _ptr(bslot), _stream(dy))
+            be[1] = False
+    if _WGRAD_STREAM and dy.is_cuda:
+        stream, refs = _wgrad_ctx(dy)
+        refs.append((dy, x))
+        with torch.cuda.stream(stream):
+            run()
     else:
-        slot.add_(torch.mm(dy.t(), x, out_dtype=torch.float32))
-    return True
-
-
-def _bias_grad_into(p, dy):
-    slot, e = _grad_slot(p)
-    if slot is None or dy.shape[0] == 0:
-        return False
-    _call("d2s_colsum_acc_bf16", _ptr(dy), dy.shape[0], dy.shape[1], _ptr(slot), _stream(dy))
-    e[1] = False
-    return True
+        run()
+    return w_ok, bslot is not None
 
 
 def adamw_flat(p, g, m, v, shadow, begin, end, lr, step, beta1, beta2, eps, weight_decay, grad_scale=1.0):
@@ -533,9 +569,10 @@ class _LinearTrain(torch.autograd.Function):
         gw = gb = None
         want_b = bd is not None and ctx.needs_input_grad[2]
         w_p, b_p = ctx.params
-        if ctx.needs_input_grad[1] and not _wgrad_into(w_p, gy2, xb.reshape(-1, K)):
+        w_done, b_done = _wgrad_into(w_p if ctx.needs_input_grad[1] else None, gy2, xb.reshape(-1, K), b_p if want_b else None)
+        if ctx.needs_input_grad[1] and not w_done:
             gw = _wgrad(gy2, xb.reshape(-1, K), wd)
-        if want_b and not _bias_grad_into(b_p, gy2):
+        if want_b and not b_done:
             gb = colsum(gy2)
         return gx, gw, None if gb is None else gb.to(bd)
 
@@ -595,7 +632,7 @@ class _LinearGeluTrain(torch.autograd.Function):
             e[1] = False
         gx = (du @ wb).view(xb.shape).to(xd) if ctx.needs_input_grad[0] else None
         gw = None
-        if ctx.needs_input_grad[1] and not _wgrad_into(w_p, du, xb.reshape(-1, K)):
+        if ctx.needs_input_grad[1] and not _wgrad_into(w_p, du, xb.reshape(-1, K))[0]:
             gw = _wgrad(du, xb.reshape(-1, K), wd)
         return gx, gw, None if gb is None else gb.to(bd)
 

@@ -300,6 +300,7 @@ class TrainStepRunner:
             self.grads.zero()
         self.loss = self.step_fn(self.static_x, self.static_y)
         self.loss.backward()
+        ops.join_wgrad_stream()                      # parameter gradients enqueued on the side stream (D2S_WGRAD_STREAM=1)
         if self.grads is not None:
             self.grads.all_reduce()
         self.opt.step()
