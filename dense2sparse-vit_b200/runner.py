@@ -257,6 +257,24 @@ class FlatAdamW(torch.optim.Optimizer):
             ops.adamw_flat(self.flat_p, self.grads.flat, self.exp_avg, self.exp_avg_sq, self.shadow, begin, end, g["_lr_dev"],
                            self.step_t, b1, b2, g["eps"], g["weight_decay"], scale)
 
+    # ---- checkpoint / resume (the moments live in flat buffers, not in torch's per-parameter `state`) ----
+    def state_dict(self):
+        groups = [{k: v for k, v in g.items() if k != "params" and not k.startswith("_")} for g in self.param_groups]
+        return {"step": float(self.step_t.item()), "exp_avg": self.exp_avg.detach().clone(), "exp_avg_sq": self.exp_avg_sq.detach().clone(),
+                "param_groups": groups, "numel": [p.numel() for g in self.param_groups for p in g["params"]]}
+
+    def load_state_dict(self, sd):
+        numel = [p.numel() for g in self.param_groups for p in g["params"]]
+        if list(sd["numel"]) != numel or sd["exp_avg"].numel() != self.exp_avg.numel():
+            raise ValueError("FlatAdamW.load_state_dict: the checkpoint was written for a different parameter list")
+        with torch.no_grad():
+            self.exp_avg.copy_(sd["exp_avg"])
+            self.exp_avg_sq.copy_(sd["exp_avg_sq"])
+            self.step_t.fill_(float(sd["step"]))
+        for g, saved in zip(self.param_groups, sd["param_groups"]):
+            g.update(saved)
+        self.sync_hyper()
+
     def close(self):
         self.grads.close()
         if self.weight_cache is not None:

@@ -579,6 +579,33 @@ def test_flat_adamw_follows_torch_adamw(d2s, cuda_dev):
     assert float(opt.step_t) == 6.0
     opt.close()
     assert d2s.ops.BF16WeightCache.lookup(mine[0]) is None
+    # checkpoint / resume: a second optimizer over equal parameters continues bit-identically from the saved state
+    ps_a = [torch.nn.Parameter(fx.randn(600 + i, *sh).to(cuda_dev)) for i, sh in enumerate(shapes[:3])]
+    ps_b = [torch.nn.Parameter(p.detach().clone()) for p in ps_a]
+    oa = d2s.runner.FlatAdamW(ps_a, lr=2e-3, weight_decay=0.05)
+    gs = [[fx.randn(700 + 10 * st_ + i, *p.shape).to(cuda_dev) for i, p in enumerate(ps_a)] for st_ in range(4)]
+    for st_ in range(2):
+        oa.zero_grad()
+        for p, g_ in zip(ps_a, gs[st_]):
+            p.grad.add_(g_)
+        oa.step()
+    ckpt = oa.state_dict()
+    ob = d2s.runner.FlatAdamW(ps_b, lr=1.0, weight_decay=0.0)           # wrong hyper-parameters on purpose: the checkpoint's win
+    with torch.no_grad():
+        for p, q in zip(ps_b, ps_a):
+            p.copy_(q)
+    ob.load_state_dict(ckpt)
+    assert ob.param_groups[0]["lr"] == 2e-3 and ob.param_groups[0]["weight_decay"] == 0.05 and float(ob.step_t) == 2.0
+    for st_ in range(2, 4):
+        for o, ps in ((oa, ps_a), (ob, ps_b)):
+            o.zero_grad()
+            for p, g_ in zip(ps, gs[st_]):
+                p.grad.add_(g_)
+            o.step()
+    for p, q in zip(ps_a, ps_b):
+        assert torch.equal(p.detach(), q.detach())
+    oa.close()
+    ob.close()
     # grad_scale (the 1 / world of the data-parallel mean, folded into the kernel): same as scaling the gradients first
     n = 1000
     p1, g = fx.randn(500, n).to(cuda_dev), fx.randn(501, n).to(cuda_dev)
