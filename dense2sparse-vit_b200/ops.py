@@ -459,6 +459,8 @@ def adamw_flat(p, g, m, v, shadow, begin, end, lr, step, beta1, beta2, eps, weig
         raise RuntimeError("adamw_flat: the flat buffers must have one size and [begin, end) must lie inside it")
     if shadow is not None and (shadow.dtype != torch.bfloat16 or shadow.numel() != p.numel() or not shadow.is_contiguous()):
         raise TypeError("adamw_flat: shadow must be a contiguous bf16 tensor of the parameters' size")
+    if begin == end:
+        return
     _call("d2s_adamw_flat_f32", _ptr(p), _ptr(g), _ptr(m), _ptr(v), _ptr(shadow), int(begin), int(end), _ptr(lr), _ptr(step),
           float(beta1), float(beta2), float(eps), float(weight_decay), float(grad_scale), _stream(p))
 
@@ -880,7 +882,8 @@ class _PoolConcat(torch.autograd.Function):
         out = torch.empty_like(hc)
         pooled = torch.empty(B, C // 2, dtype=torch.float32, device=hc.device)
         wsum = torch.empty(B, dtype=torch.float32, device=hc.device)
-        _call("d2s_pool_concat_fwd", _ptr(hc), _ptr(pol), _dtype_code(hc), B, N, C, _ptr(out), _ptr(pooled), _ptr(wsum), _stream(hc))
+        if B > 0:
+            _call("d2s_pool_concat_fwd", _ptr(hc), _ptr(pol), _dtype_code(hc), B, N, C, _ptr(out), _ptr(pooled), _ptr(wsum), _stream(hc))
         ctx.save_for_backward(hc, pooled, wsum, pol if pol is not None else torch.empty(0, device=hc.device))
         ctx.meta = (pol is not None, None if policy is None else (policy.shape, policy.dtype))
         return out
@@ -894,8 +897,9 @@ class _PoolConcat(torch.autograd.Function):
         dh = torch.empty_like(hc)
         want_dp = has_pol and ctx.needs_input_grad[1]
         dpol = torch.empty(B, N, dtype=torch.float32, device=hc.device) if want_dp else None
-        _call("d2s_pool_concat_bwd", _ptr(g), _ptr(hc), _ptr(pol if has_pol else None), _ptr(pooled), _ptr(wsum), _dtype_code(hc),
-              B, N, C, _ptr(dh), _ptr(dpol), _stream(g))
+        if B > 0:
+            _call("d2s_pool_concat_bwd", _ptr(g), _ptr(hc), _ptr(pol if has_pol else None), _ptr(pooled), _ptr(wsum), _dtype_code(hc),
+                  B, N, C, _ptr(dh), _ptr(dpol), _stream(g))
         return dh, None if dpol is None else dpol.view(pol_meta[0]).to(pol_meta[1])
 
 
@@ -932,8 +936,9 @@ class _TokenKL(torch.autograd.Function):
         B, N, C = s.shape
         kl = torch.empty(B * N, dtype=torch.float32, device=s.device)
         diff = torch.empty(B * N, C, dtype=torch.float32, device=s.device)
-        _call("d2s_token_kl_fwd", _ptr(s), _dtype_code(s), s.stride(0), _ptr(t), _dtype_code(t), t.stride(0), B, N, C, _ptr(kl),
-              _ptr(diff), _stream(s))
+        if B > 0:
+            _call("d2s_token_kl_fwd", _ptr(s), _dtype_code(s), s.stride(0), _ptr(t), _dtype_code(t), t.stride(0), B, N, C, _ptr(kl),
+                  _ptr(diff), _stream(s))
         ctx.save_for_backward(diff)
         ctx.meta = (s.shape, s.dtype)
         return kl

@@ -1053,3 +1053,25 @@ def test_token_kl_rows_match_f_kl_div(ops, B, N, C, sliced, sdt, tdt):
     assert float(g[:, 0].abs().max()) == 0.0
     tol = 1e-6 if sdt == torch.float32 else 4e-3 * float(sr.grad.abs().max())
     torch.testing.assert_close(g, sr.grad, rtol=1e-4 if sdt == torch.float32 else 1e-2, atol=tol)
+
+
+def test_round2_training_ops_take_empty_inputs(ops):
+    """B = 0 / empty ranges return without a launch (the C ABI reports shape errors, not empty work)."""
+    dev = torch.device("cuda")
+    h = torch.zeros(0, 196, 384, device=dev, dtype=torch.bfloat16)
+    assert ops.pool_concat_train(h, torch.zeros(0, 196, 1, device=dev)).shape == (0, 196, 384)
+    s = torch.zeros(0, 197, 384, device=dev)
+    assert ops.token_kl_rows(s[:, 1:], s[:, 1:]).shape == (0,)
+    w, b = torch.ones(384, device=dev), torch.zeros(384, device=dev)
+    assert ops.layer_norm(torch.zeros(0, 197, 384, device=dev), w, b, 1e-5, row0=1).shape == (0, 196, 384)
+    p = torch.ones(16, device=dev)
+    g, m, v = torch.ones(16, device=dev), torch.zeros(16, device=dev), torch.zeros(16, device=dev)
+    lr, st = torch.full((1,), 1e-3, device=dev), torch.ones(1, device=dev)
+    ops.adamw_flat(p, g, m, v, None, 5, 5, lr, st, 0.9, 0.999, 1e-8, 0.0)
+    assert torch.equal(p, torch.ones(16, device=dev)) and float(m.abs().max()) == 0.0
+    with pytest.raises(RuntimeError):
+        ops.adamw_flat(p, g, m, v, None, 0, 17, lr, st, 0.9, 0.999, 1e-8, 0.0)          # range outside the buffers
+    with pytest.raises(RuntimeError):
+        ops.token_kl_rows(torch.zeros(2, 4, 12, device=dev), torch.zeros(2, 4, 12, device=dev))   # C % 8 != 0
+    with pytest.raises(RuntimeError):
+        ops.pool_concat_train(torch.zeros(2, 4, 12, device=dev, dtype=torch.float64))
