@@ -129,7 +129,8 @@ template <int kN> __device__ __forceinline__ void cp_async_wait() { asm volatile
 // shared-memory slots filled by cp.async: every thread copies exactly the 16-byte pieces it will read itself, so the ring needs
 // no barrier (cp.async.wait_group orders a thread's own copies), and two passes of loads are in flight per thread without
 // costing registers.  With the loads held in registers (167 per thread, 3 CTAs of 128 threads per SM) the kernel had 18 KB in
-// flight per SM and ran at 2-3.4 TB/s.
+// flight per SM and ran at 2-3.4 TB/s.  The ring also lets the second half of a pass re-read the row instead of holding it in
+// registers across the reductions: 96 registers, four CTAs per SM.
 template <typename TX, typename TH, int kVPL, int kStages>
 __global__ void __launch_bounds__(kLtBwdThreads)
 ln_bwd_kernel(const TH* __restrict__ dh, const TX* __restrict__ x, const float* __restrict__ stats,
@@ -188,7 +189,9 @@ ln_bwd_kernel(const TH* __restrict__ dh, const TX* __restrict__ x, const float* 
     const bool ok = row < row_end;
     const float mean = ok ? stats[row * 2] : 0.f, rstd = ok ? stats[row * 2 + 1] : 0.f;
     const long long xrow = seg_row(row, seg, skip);
-    float xh[kVPL][8], gg[kVPL][8];
+    // pass A: row sums and the column accumulators.  Nothing of the row is kept in registers across the two half-warp reductions:
+    // pass B re-reads x and dh from this thread's ring slots (shared memory) and recomputes xhat and g -- 48 registers less, which
+    // is what lets a fourth CTA onto the SM (the kernel is latency-bound at three CTAs of four warps).
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int k = 0; k < kVPL; ++k) {
@@ -200,16 +203,12 @@ ln_bwd_kernel(const TH* __restrict__ dh, const TX* __restrict__ x, const float* 
         TV<float>::load(gamma + vi * 8, g);
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-          xh[k][q] = (xv[q] - mean) * rstd;
-          gg[k][q] = dv[q] * g[q];
-          s1 += gg[k][q];
-          s2 = fmaf(gg[k][q], xh[k][q], s2);
-          ag[k][q] = fmaf(dv[q], xh[k][q], ag[k][q]);
+          const float xh = (xv[q] - mean) * rstd, gq = dv[q] * g[q];
+          s1 += gq;
+          s2 = fmaf(gq, xh, s2);
+          ag[k][q] = fmaf(dv[q], xh, ag[k][q]);
           ab[k][q] += dv[q];
         }
-      } else {
-#pragma unroll
-        for (int q = 0; q < 8; ++q) { xh[k][q] = 0.f; gg[k][q] = 0.f; }
       }
     }
     s1 = hw_sum(s1) / (float)D;
@@ -219,9 +218,12 @@ ln_bwd_kernel(const TH* __restrict__ dh, const TX* __restrict__ x, const float* 
       for (int k = 0; k < kVPL; ++k) {
         const int vi = sub + 16 * k;
         if (vi < nvec) {
-          float o[8];
+          float xv[8], dv[8], g[8], o[8];
+          TV<TX>::load(reinterpret_cast<const TX*>(slot_x(st, k)), xv);
+          TV<TH>::load(reinterpret_cast<const TH*>(slot_h(st, k)), dv);
+          TV<float>::load(gamma + vi * 8, g);
 #pragma unroll
-          for (int q = 0; q < 8; ++q) o[q] = rstd * (gg[k][q] - s1 - xh[k][q] * s2);
+          for (int q = 0; q < 8; ++q) o[q] = rstd * (dv[q] * g[q] - s1 - (xv[q] - mean) * rstd * s2);
           if (gadd) {   // gradient that reaches x directly (the residual stream's), accumulated here instead of by a torch add
             float ga[8];
             TV<TX>::load(reinterpret_cast<const TX*>(slot_g(st, k)), ga);
@@ -291,7 +293,7 @@ static int ln_bwd_launch_cfg(const void* dh, const void* x, const float* stats, 
   const long long slots = (long long)kNumSMs * (per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm));
   long long rpc = (rows + slots - 1) / slots;
   rpc = (rpc + kLtBwdRowsPerIter - 1) / kLtBwdRowsPerIter * kLtBwdRowsPerIter;
-  if (rpc < kLtRowsPerCta) rpc = kLtRowsPerCta;
+  if (rpc < kLtRowsPerCta / 2) rpc = kLtRowsPerCta / 2;           // at least 64 rows per 2 D column atomics
   const unsigned grid = (unsigned)((rows + rpc - 1) / rpc);
   // opt in once per device for the largest row this instantiation takes (D <= 128 kVPL): the memo does not know about D
   constexpr size_t kSmemMax = (size_t)kLtBwdRowsPerIter * (128 * kVPL) * sizeof(float) +
@@ -307,12 +309,9 @@ static int ln_bwd_launch_cfg(const void* dh, const void* x, const float* stats, 
 template <typename TX, typename TH>
 static int ln_bwd_launch(const void* dh, const void* x, const float* stats, const float* gamma, const void* gadd, long long rows,
                          int D, void* dx, float* dgamma, float* dbeta, int seg, int skip, cudaStream_t st) {
-  // ring depth: three passes (two in flight) where three CTAs still fit an SM, else two
+  // ring depth: two passes (one in flight while one is consumed); four CTAs of four warps then fit an SM for bf16 rows up to 384
   const int vpl = ceil_div(D / 8, 16);
-  if (vpl <= 3) {
-    if (sizeof(TX) == 2) return ln_bwd_launch_cfg<TX, TH, 3, 3>(dh, x, stats, gamma, gadd, rows, D, dx, dgamma, dbeta, seg, skip, st);
-    return ln_bwd_launch_cfg<TX, TH, 3, 2>(dh, x, stats, gamma, gadd, rows, D, dx, dgamma, dbeta, seg, skip, st);
-  }
+  if (vpl <= 3) return ln_bwd_launch_cfg<TX, TH, 3, 2>(dh, x, stats, gamma, gadd, rows, D, dx, dgamma, dbeta, seg, skip, st);
   return ln_bwd_launch_cfg<TX, TH, 6, 2>(dh, x, stats, gamma, gadd, rows, D, dx, dgamma, dbeta, seg, skip, st);
 }
 
