@@ -521,8 +521,11 @@ def train_leg(pkg, args, dev, rank, world, torch, dist, pk):
     hx, hy = x.cpu().pin_memory(), y.cpu().pin_memory()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    for _ in range(K):
-        loss = run(hx, hy)
+    run.prefetch(hx, hy)                    # the copy of step k + 1 runs on a copy stream under step k
+    for k in range(K):
+        loss = run.step_prefetched()
+        if k + 1 < K:
+            run.prefetch(hx, hy)
     lv = float(loss.detach())               # device -> host read of the step's result
     e2e_s = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
     if world > 1:

@@ -331,6 +331,30 @@ class TrainStepRunner:
         self._body()
         return self.loss
 
+    # ---- pipelined input: the next batch's host -> device copy runs on a copy stream while the current step computes --------
+    def prefetch(self, x_host, y_host):
+        """Start copying a LATER step's batch (pinned host tensors) into a device staging buffer on the copy stream."""
+        dev = self.static_x.device
+        if getattr(self, "_stage", None) is None:
+            self._stage = (torch.empty_like(self.static_x), torch.empty_like(self.static_y))
+            self._copy_stream = torch.cuda.Stream(device=dev)
+            self._ready, self._taken = torch.cuda.Event(), torch.cuda.Event()
+            self._taken.record(torch.cuda.current_stream(dev))
+        self._copy_stream.wait_event(self._taken)             # the previous staged batch has been moved into the step's inputs
+        with torch.cuda.stream(self._copy_stream):
+            self._stage[0].copy_(x_host, non_blocking=True)
+            self._stage[1].copy_(y_host, non_blocking=True)
+            self._ready.record(self._copy_stream)
+
+    def step_prefetched(self):
+        """One optimisation step on the batch staged by prefetch(): a device-to-device move into the graph's inputs, then the step."""
+        cur = torch.cuda.current_stream(self.static_x.device)
+        cur.wait_event(self._ready)
+        self.static_x.copy_(self._stage[0], non_blocking=True)
+        self.static_y.copy_(self._stage[1], non_blocking=True)
+        self._taken.record(cur)
+        return self()
+
     def __call__(self, x=None, y=None):
         """One optimisation step on (x, y) (default: the tensors already in place); returns the (static) loss tensor."""
         if x is not None:

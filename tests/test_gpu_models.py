@@ -471,6 +471,14 @@ def test_graphed_training_step_matches_eager(d2s, cuda_dev):
         run = d2s.runner.TrainStepRunner(fwd_loss, opt, x, y, warmup=2, use_graph=mode != "eager", grads=grads, weight_cache=cache)
         assert (run.graph is not None) == (mode != "eager")
         losses[mode] = [float(run()) for _ in range(4)]
+        if mode == "graph_flat_adamw":          # pipelined input: the staged batch lands in the graph's inputs before the replay
+            hx, hy = (x + 1.0).cpu().pin_memory(), y.cpu().pin_memory()
+            run.prefetch(hx, hy)
+            l5 = float(run.step_prefetched())
+            assert torch.equal(run.static_x.cpu(), hx) and torch.equal(run.static_y.cpu(), hy) and l5 == l5
+            run.prefetch(x.cpu().pin_memory(), hy)
+            run.step_prefetched()
+            assert torch.equal(run.static_x, x)
         if cache is not None:
             for p_, d_ in zip(cache.src, cache.dst):
                 assert torch.equal(d_, p_.detach().to(torch.bfloat16))          # the copies follow the optimizer
