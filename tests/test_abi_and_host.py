@@ -178,8 +178,28 @@ full, _ = oo.select_topk(score, K, oo.ORDER_INDEX_ASC)
 ok = torch.equal(torch.cat([torch.as_tensor(p) for p in parts]), full)
 ms = torch.tensor([10.0 + rank])                              # max-over-ranks timing reduction used by bench.py
 dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+# training's one collective: runner.FlatGrads -- every gradient a view of one flat buffer, one all-reduce, mean over the ranks
+torch.manual_seed(7)
+net = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Tanh(), torch.nn.Linear(5, 3))
+xs, ys = fx.randn(11, GB, 6), fx.randn(12, GB, 3)
+ref_net = __import__("copy").deepcopy(net)
+((ref_net(xs) - ys) ** 2).mean(dim=1).mean().backward()          # the global-batch gradient, computed in one process
+fg = d2s.runner.FlatGrads(net.parameters())
+views = [p.grad for p in net.parameters()]
+fg.zero()
+((net(xs[lo:hi]) - ys[lo:hi]) ** 2).mean(dim=1).mean().backward()  # equal shard sizes: mean of shard means = global mean
+fg.all_reduce()
+grads_ok = all(p.grad is v for p, v in zip(net.parameters(), views)) and all(
+    torch.allclose(p.grad, q.grad, rtol=1e-5, atol=1e-7) for p, q in zip(net.parameters(), ref_net.parameters()))
+offs, total = d2s.runner.flat_layout(list(net.parameters()))
+layout_ok = all(o % 8 == 0 for o in offs) and total == fg.flat.numel() and offs == fg.offsets
+fs = d2s.runner.FlatGrads(__import__("copy").deepcopy(net).parameters(), average=False)   # sum: the optimizer folds 1/world in
+fs.flat.fill_(float(rank + 1))
+fs.all_reduce()
+sum_ok = bool((fs.flat == 3.0).all())
 if rank == 0:
-    print(json.dumps({"ok": bool(ok), "max_ms": float(ms), "world": world, "env": d2s.runner.dist_env()}))
+    print(json.dumps({"ok": bool(ok), "max_ms": float(ms), "world": world, "env": d2s.runner.dist_env(),
+                      "grads_ok": bool(grads_ok), "layout_ok": bool(layout_ok), "sum_ok": sum_ok}))
 dist.destroy_process_group()
 '''
 
@@ -200,6 +220,8 @@ def test_two_rank_gloo_sharding(tmp_path):
     line = [ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1]
     out = json.loads(line)
     assert out["ok"] and out["max_ms"] == 11.0 and out["world"] == 2 and out["env"] == [0, 0, 2]
+    # the gradient all-reduce of the training path (runner.FlatGrads): mean over the ranks == the global-batch gradient
+    assert out["grads_ok"] and out["layout_ok"] and out["sum_ok"]
 
 
 def test_bench_reference_arm_contract_two_ranks():
