@@ -13,10 +13,12 @@ scaling: every rank owns its own 1024 images).  Rank 0 prints ONE JSON line.
   parity_checked the gate run before any timing: 8 images through the fp32 GPU path and the bf16 path against the CPU oracle
   roofline       the step's dominant d2s kernel (the one-kernel MLP, tensor-bound), aggregated over its launches per step
   kernels        every d2s kernel of the step timed alone inside a CUDA graph (no host launch time), rotating buffers > L2
-  train          BASELINE configs[2]: Variant A training step (student fwd+bwd, frozen teacher, distillation losses, AdamW),
-                 bf16 autocast, batch 256 per GPU; N > 1: one NCCL all-reduce of the flat gradient buffer per step
+  train          BASELINE configs[2]: Variant A training step (student fwd+bwd, frozen teacher on a second stream, distillation
+                 losses, AdamW as one flat kernel), bf16 autocast, batch 256 per GPU, whole step one CUDA graph; N > 1: one NCCL
+                 all-reduce of the flat gradient buffer per step; train.e2e: pinned host batch copied in under the previous step
   ptopk          BASELINE configs[3]: PerturbedTopK forward + backward (N=196, k=98, 500 samples), B in {1, 8, 64, 256}
   sweep          BASELINE configs[4]: select / gather / scatter, D in {384, 768}, bf16 and fp32, keep 0.3-0.9, B 64-4096
+  arch_base      the same inference path at DeiT-B widths (D = 768, 12 heads, hidden 3072), batch 512
   h2d_only       the host->device copy of the e2e leg alone (its ceiling), at N ranks
   gpu_eager_baseline  the oracle's restatement of the reference forward executed by torch eager on the same GPU in bf16
   cpu_baseline   the CPU restatement of the reference forward (oracle/), timed on this box's host cores
