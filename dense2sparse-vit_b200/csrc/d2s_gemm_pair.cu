@@ -40,7 +40,7 @@ constexpr uint32_t kGpBlkBytes = 128 * 128;      // one staged 128 x 64 bf16 blo
 
 enum { kGpModeAct = 0, kGpModeLn = 1 };
 
-// clock64 phase totals per epilogue warp (profiling builds only: -DD2S_GEMM_TRACE_BUILD; see scripts/bench_gemm_trace*.py)
+// clock64 phase totals per epilogue warp (profiling builds only: D2S_NVCC_EXTRA=-DD2S_GEMM_TRACE_BUILD; buffer named by D2S_GEMM_TRACE)
 #ifdef D2S_GEMM_TRACE_BUILD
 #define GP_TRACE_DECL(n) long long tr[n] = {}; long long tr_t = clock64();
 #define GP_TRACE(i) { const long long tr_n = clock64(); tr[i] += tr_n - tr_t; tr_t = tr_n; }

@@ -23,7 +23,7 @@
 //               measured slower -- the stage is bound by the sub-partitions' issue / MUFU slots, not by per-warp latency)
 //   warps 12-15 output: residual add + LayerNorm of the finished row tile, overlapped with the next tile's GEMMs
 // Build options for experiments: -DMP_W1 / -DMP_W2 (weight ring depths, default 5 / 3), -DMP_E1W (8 | 16), -DD2S_GEMM_TRACE_BUILD
-// (clock64 totals of the issuers' barrier waits, scripts/bench_mlp_trace.py).
+// (clock64 totals of the issuers' barrier waits into MpParams::trace, a device buffer named by the D2S_GEMM_TRACE environment variable).
 #include <stdlib.h>
 #include "d2s_tc.cuh"
 
@@ -49,7 +49,7 @@ constexpr int kMpE1Parts = kMpE1Warps / 4;          // E1 warps per TMEM lane qu
 constexpr int kMpE1Cols = kMpCH / kMpE1Parts;       // hidden columns of a chunk per E1 warp (64 or 32)
 constexpr uint32_t kMpAccCols = 384, kMpSCols = 128;
 
-// clock64 totals of the issuing warps' waits (profiling builds only: -DD2S_GEMM_TRACE_BUILD, scripts/bench_mlp_trace.py)
+// clock64 totals of the issuing warps' waits (profiling builds only: D2S_NVCC_EXTRA=-DD2S_GEMM_TRACE_BUILD)
 #ifdef D2S_GEMM_TRACE_BUILD
 #define MP_TRACE_DECL long long tr[8] = {}; long long tr_t = clock64();
 #define MP_TRACE(i) { const long long tr_n = clock64(); tr[i] += tr_n - tr_t; tr_t = tr_n; }
