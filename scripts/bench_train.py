@@ -24,6 +24,7 @@ ap.add_argument("--warmup", type=int, default=3)
 ap.add_argument("--variant", default="a", choices=["a", "b"],
                 help="a: DynamicViT (3 stages, Gumbel decisions, DistillDiffPruningLoss); b: Dense2Sparse (1 stage @3, top-k, MaskLoss + BackboneLoss, train.py:40-53)")
 ap.add_argument("--graph", action="store_true", help="capture the whole step (forward, loss, backward, AdamW) in a CUDA graph (Variant A, one GPU)")
+ap.add_argument("--flat-adamw", action="store_true", help="runner.FlatAdamW (one d2s kernel, gradients written into its flat buffer) instead of torch.optim.AdamW; single GPU")
 ap.add_argument("--freeze-backbone", action="store_true", help="train the predictors only (mask_predictor.py:219-225)")
 args = ap.parse_args()
 pkg = d2s.pkg
@@ -57,7 +58,10 @@ else:
     backbone_loss_fn = pkg.losses.BackboneLoss(types.SimpleNamespace(mixup=0.0, patch_score_threshold=None))
 metrics = {}
 use_graph = args.graph and args.variant == "a" and world == 1
-opt = torch.optim.AdamW([p for p in student.parameters() if p.requires_grad], lr=5e-4, weight_decay=0.05, capturable=use_graph)
+if args.flat_adamw and world == 1:
+    opt = pkg.runner.FlatAdamW([p for p in student.parameters() if p.requires_grad], lr=5e-4, weight_decay=0.05)
+else:
+    opt = torch.optim.AdamW([p for p in student.parameters() if p.requires_grad], lr=5e-4, weight_decay=0.05, capturable=use_graph)
 g = torch.Generator(device=dev).manual_seed(42 + rank)
 x = torch.randn(args.batch, 3, 224, 224, device=dev, generator=g)
 y = torch.randint(0, 1000, (args.batch,), device=dev, generator=g)
@@ -85,7 +89,8 @@ if use_graph:
         with torch.autocast("cuda", dtype=torch.bfloat16):
             return crit(xx, model(xx), yy)[0]
     n_cap = pkg._lib.launch_count()
-    graphed = pkg.runner.TrainStepRunner(fwd_loss, opt, x, y, warmup=max(1, args.warmup))
+    graphed = pkg.runner.TrainStepRunner(fwd_loss, opt, x, y, warmup=max(1, args.warmup), grads=getattr(opt, "grads", None),
+                                         weight_cache=getattr(opt, "weight_cache", None))
     per_step_captured = (pkg._lib.launch_count() - n_cap) // (max(1, args.warmup) + 1)   # eager warm-ups + the capture pass
     step = graphed
 
@@ -119,6 +124,7 @@ if rank == 0:
                       "d2s_launches_per_step": int(per_step),
                       "config": {"workload": "student fwd+bwd + frozen teacher fwd + AdamW, " + ("ratio/distill losses" if args.variant == "a" else "MaskLoss(kl_div) + BackboneLoss"),
                                  "batch_per_gpu": args.batch, "freeze_backbone": args.freeze_backbone,
-                                 "parallelism": f"DDP x{world} (NCCL gradient all-reduce)" if world > 1 else "single GPU", "cuda_graph": bool(use_graph)}}))
+                                 "parallelism": f"DDP x{world} (NCCL gradient all-reduce)" if world > 1 else "single GPU", "cuda_graph": bool(use_graph),
+                                 "optimizer": type(opt).__name__}}))
 if world > 1:
     dist.destroy_process_group()
