@@ -19,6 +19,7 @@ scaling: every rank owns its own 1024 images).  Rank 0 prints ONE JSON line.
   ptopk          BASELINE configs[3]: PerturbedTopK forward + backward (N=196, k=98, 500 samples), B in {1, 8, 64, 256}
   sweep          BASELINE configs[4]: select / gather / scatter, D in {384, 768}, bf16 and fp32, keep 0.3-0.9, B 64-4096
   arch_base      the same inference path at DeiT-B widths (D = 768, 12 heads, hidden 3072), batch 512
+  variant_b      Dense2Sparse (Variant B): inference at batch 1024 and the reference's train.py loop (MaskLoss + BackboneLoss) at 256
   h2d_only       the host->device copy of the e2e leg alone (its ceiling), at N ranks
   gpu_eager_baseline  the oracle's restatement of the reference forward executed by torch eager on the same GPU in bf16
   cpu_baseline   the CPU restatement of the reference forward (oracle/), timed on this box's host cores
@@ -44,7 +45,7 @@ DEIT_S = dict(patch_size=16, embed_dim=384, depth=12, num_heads=6, mlp_ratio=4, 
 DEIT_B = dict(patch_size=16, embed_dim=768, depth=12, num_heads=12, mlp_ratio=4, qkv_bias=True)     # BASELINE configs[3] / [4] widths
 GFLOP_PER_IMG = 5.96                                    # SURVEY.md 8d, Variant A 3 stages
 TRAIN_GFLOP_PER_IMG = 36.8                              # 3 x 9.2 (student fwd+bwd at T=197) + 9.2 (teacher fwd)
-ALL_LEGS = ("parity", "infer", "e2e", "h2d", "train", "kernels", "ptopk", "sweep", "base", "eager", "cpu")
+ALL_LEGS = ("parity", "infer", "e2e", "h2d", "train", "kernels", "ptopk", "sweep", "base", "variant_b", "eager", "cpu")
 W_SEED = 61                                             # seeded weights (tests/golden/fixtures.py): well-spread predictor scores
 L2_BYTES = 126e6
 
@@ -597,6 +598,82 @@ def base_leg(pkg, dev, torch, pk, no_graph=False):
     return res
 
 
+def variant_b_leg(pkg, dev, torch, no_graph=False):
+    """Dense2Sparse (Variant B, dynamic_vit.py:814-1015): one pruning stage at block 3, keep ratio 0.7, top-k selection, the
+    large LayerNorm predictor, CLS-attention rows collected in every block.  Inference at batch 1024 (CUDA graph) and the
+    reference's training loop (train.py:40-66: student + teacher with CLS attention, MaskLoss + BackboneLoss, AdamW) at batch
+    256, eager -- the losses keep host-side running metrics."""
+    import types
+    kw = dict(pruning_loc=[3], token_ratio=[0.7], distill=True, topk_selection=True, predictor_loss_type="kl_div", **DEIT_S)
+    model = pkg.variant_b.VisionTransformerDiffPruning(**kw)
+    seeded_weights(model)
+    B = 1024
+    runner = pkg.runner.InferenceRunner(model, B, dev, dtype=torch.bfloat16, use_graph=not no_graph, warmup=2)
+    g = torch.Generator(device=dev).manual_seed(11)
+    runner.static_in.copy_(torch.randn(runner.static_in.shape, device=dev, generator=g).to(runner.static_in.dtype))
+    for _ in range(3):
+        runner.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    K = 10
+    e0.record()
+    for _ in range(K):
+        runner.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    ms_inf = e0.elapsed_time(e1) / K
+    finite = bool(torch.isfinite(runner.logits.float()).all())
+    del runner, model
+    torch.cuda.empty_cache()
+    # ---- training loop of train.py
+    Bt = 256
+    torch.manual_seed(0)
+    student = pkg.variant_b.VisionTransformerDiffPruning(**kw)
+    seeded_weights(student)
+    student = student.to(dev).train()
+    teacher = pkg.variant_b.VisionTransformerTeacher(**DEIT_S).to(dev).eval()
+    for p in teacher.parameters():
+        p.requires_grad_(False)
+    mask_loss = pkg.losses.MaskLoss(types.SimpleNamespace(keep_ratios=[0.7], mask_loss_type="kl_div", batch_size=Bt, device=dev), "train")
+    backbone_loss = pkg.losses.BackboneLoss(types.SimpleNamespace(mixup=0.0, patch_score_threshold=None))
+    opt = pkg.runner.FlatAdamW(student.parameters(), lr=5e-4, weight_decay=0.05)
+    x = torch.randn(Bt, 3, 224, 224, device=dev, generator=g)
+    y = torch.randint(0, 1000, (Bt,), device=dev, generator=g)
+    metrics = {}
+
+    def step():
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            with torch.no_grad():
+                logits_t, token_t, cls_attn = teacher(x)
+            logits_s, token_s, pred_logits, kept = student(x)
+            loss = mask_loss(pred_logits, cls_attn, kept, metrics) + backbone_loss(logits_s, token_s, logits_t, token_t, kept, y, metrics)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        return loss
+    for _ in range(3):
+        loss = step()
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(K):
+        loss = step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms_tr = e0.elapsed_time(e1) / K
+    out = {"inference": {"metric": "images/sec Dense2Sparse (Variant B) DeiT-S 1 stage@3 kr=0.7 @224", "value": B / (ms_inf / 1e3), "unit": UNIT,
+                         "ms_per_step": ms_inf, "batch": B, "dtype": "bf16", "cuda_graph": not no_graph, "outputs_finite": finite,
+                         "outputs": "logits + 12 CLS-attention rows + predictor logits + kept indices"},
+           "train": {"metric": "training images/sec Dense2Sparse (Variant B) DeiT-S 1 stage@3 kr=0.7 @224", "value": Bt / (ms_tr / 1e3), "unit": UNIT,
+                     "ms_per_step": ms_tr, "batch": Bt, "dtype": "bf16 autocast, fp32 master weights", "cuda_graph": False,
+                     "final_loss": float(loss.detach()),
+                     "workload": "train.py:40-66: student fwd+bwd + frozen teacher fwd (CLS attention rows) + MaskLoss(kl_div) + BackboneLoss + "
+                                 "runner.FlatAdamW, eager (the losses keep host-side running metrics)"}}
+    opt.close()
+    del student, teacher, opt
+    torch.cuda.empty_cache()
+    return out
+
+
 def gpu_eager_leg(sd, dev, B, torch):
     """The oracle's restatement of the reference forward (plain torch ops: F.linear / matmul / softmax / sort / gather -- what
     `reference_model.to(bfloat16).cuda()` executes) run by torch eager on this GPU at the benchmarked batch and dtype."""
@@ -820,6 +897,8 @@ def run_gpu(args):
         line["sweep"] = sweep_leg(pkg.ops, dev, torch, pk)
     if "base" in legs and rank == 0:
         line["arch_base"] = base_leg(pkg, dev, torch, pk, args.no_graph)
+    if "variant_b" in legs and rank == 0:
+        line["variant_b"] = variant_b_leg(pkg, dev, torch, args.no_graph)
         torch.cuda.empty_cache()
     if "eager" in legs:
         line["gpu_eager_baseline"] = gpu_eager_leg(sd, dev, B, torch)
