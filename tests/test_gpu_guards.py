@@ -184,3 +184,86 @@ def test_layernorm_train_kernels_and_colsum_stay_in_bounds(d2s, rows, D):
         if gd not in (x, y):
             assert bool(torch.isfinite(gd.t.float()).all()), f"{name}: element left unwritten or fed by an out-of-bounds read"
     torch.testing.assert_close(cs.t, x.t.float().sum(0), rtol=1e-3, atol=1e-2)
+
+
+@pytest.mark.parametrize("B,N,C", [(3, 196, 384), (2, 137, 384), (1, 5, 16), (5, 67, 768)])
+def test_predictor_split_and_token_kl_stay_in_bounds(d2s, B, N, C):
+    """d2s_pool_concat_fwd/bwd, d2s_token_kl_fwd (with x[:, 1:]-style batch strides) and d2s_layernorm_seg_fwd/bwd."""
+    lib = d2s._lib
+    g = torch.Generator(device="cuda").manual_seed(N + C)
+    bf = torch.bfloat16
+    h = Guarded((B, N, C), bf, torch.randn(B, N, C, device="cuda", generator=g).bfloat16(), poison_after=True)
+    go = Guarded((B, N, C), bf, torch.randn(B, N, C, device="cuda", generator=g).bfloat16(), poison_after=True)
+    pol = Guarded((B, N), torch.float32, (torch.rand(B, N, device="cuda", generator=g) > 0.3).float() + 0.5, poison_after=True)
+    # token KL inputs: (B, N+1, C) tensors read from row 1 on (batch stride (N+1)*C)
+    s = Guarded((B, N + 1, C), torch.float32, torch.randn(B, N + 1, C, device="cuda", generator=g), poison_after=True)
+    t = Guarded((B, N + 1, C), bf, torch.randn(B, N + 1, C, device="cuda", generator=g).bfloat16(), poison_after=True)
+    w = torch.ones(C, device="cuda")
+    bb = torch.zeros(C, device="cuda")
+    for _ in range(2):
+        out, pooled, wsum = Guarded((B, N, C), bf), Guarded((B, C // 2), torch.float32), Guarded((B,), torch.float32)
+        dh, dpol = Guarded((B, N, C), bf), Guarded((B, N), torch.float32)
+        lib.call("d2s_pool_concat_fwd", h.ptr, pol.ptr, 1, B, N, C, out.ptr, pooled.ptr, wsum.ptr, _stream())
+        lib.call("d2s_pool_concat_bwd", go.ptr, h.ptr, pol.ptr, pooled.ptr, wsum.ptr, 1, B, N, C, dh.ptr, dpol.ptr, _stream())
+        kl, diff = Guarded((B * N,), torch.float32), Guarded((B * N, C), torch.float32)
+        lib.call("d2s_token_kl_fwd", s.t[:, 1:].data_ptr(), 0, (N + 1) * C, t.t[:, 1:].data_ptr(), 1, (N + 1) * C, B, N, C, kl.ptr, diff.ptr,
+                 _stream())
+        hn, stats = Guarded((B, N, C), bf), Guarded((B * N, 2), torch.float32)
+        dx = Guarded((B, N + 1, C), torch.float32)
+        dgb = Guarded((2, C), torch.float32, torch.zeros(2, C, device="cuda"))
+        if C <= 768:
+            lib.call("d2s_layernorm_seg_fwd", s.ptr, 0, w.data_ptr(), bb.data_ptr(), B * N, C, N, 1, 1e-6, hn.ptr, 1, stats.ptr, _stream())
+            lib.call("d2s_layernorm_seg_bwd", go.ptr, 1, s.ptr, 0, stats.ptr, w.data_ptr(), B * N, C, N, 1, dx.ptr, dgb.t[0].data_ptr(),
+                     dgb.t[1].data_ptr(), _stream())
+        torch.cuda.synchronize()
+        named = [("out", out), ("pooled", pooled), ("wsum", wsum), ("dh", dh), ("dpolicy", dpol), ("kl", kl), ("diff", diff), ("hn", hn),
+                 ("stats", stats), ("dx", dx), ("dgamma/dbeta", dgb)]
+        for name, gd in named + [("h", h), ("gout", go), ("policy", pol), ("s", s), ("t", t)]:
+            assert gd.ok(), f"{name}: guard zone overwritten"
+        for name, gd in named:
+            assert bool(torch.isfinite(gd.t.float()).all()), f"{name}: element left unwritten or fed by an out-of-bounds read"
+        assert float(dx.t[:, 0].abs().max()) == 0.0                      # the skipped rows' gradient is written as zeros
+
+
+@pytest.mark.parametrize("n,begin,end", [(1000, 0, 1000), (1003, 13, 771), (4096, 8, 4088), (17, 1, 16)])
+def test_adamw_flat_touches_only_its_range(d2s, n, begin, end):
+    lib = d2s._lib
+    g = torch.Generator(device="cuda").manual_seed(n)
+    p0 = torch.randn(n, device="cuda", generator=g)
+    p, m, v = Guarded((n,), torch.float32, p0), Guarded((n,), torch.float32, torch.zeros(n, device="cuda")), Guarded((n,), torch.float32, torch.zeros(n, device="cuda"))
+    gr = Guarded((n,), torch.float32, torch.randn(n, device="cuda", generator=g), poison_after=True)
+    sh = Guarded((n,), torch.bfloat16, torch.zeros(n, device="cuda").bfloat16())
+    lr, st = torch.full((1,), 1e-3, device="cuda"), torch.ones(1, device="cuda")
+    lib.call("d2s_adamw_flat_f32", p.ptr, gr.ptr, m.ptr, v.ptr, sh.ptr, begin, end, lr.data_ptr(), st.data_ptr(), 0.9, 0.999, 1e-8, 0.05, 1.0,
+             _stream())
+    torch.cuda.synchronize()
+    for name, gd in (("p", p), ("m", m), ("v", v), ("shadow", sh), ("g", gr)):
+        assert gd.ok(), f"{name}: guard zone overwritten"
+    inside = torch.zeros(n, dtype=torch.bool, device="cuda")
+    inside[begin:end] = True
+    assert torch.equal(p.t[~inside], p0[~inside]) and float(m.t[~inside].abs().max() if (~inside).any() else 0.0) == 0.0
+    assert bool((p.t[inside] != p0[inside]).all()) and bool(torch.isfinite(p.t).all())
+    assert torch.equal(sh.t[inside], p.t[inside].bfloat16()) and float(sh.t[~inside].float().abs().max() if (~inside).any() else 0.0) == 0.0
+
+
+@pytest.mark.parametrize("M,K", [(300, 768), (77, 3072), (1000, 64)])
+def test_linear_residual_ln_at_768_columns_stays_in_bounds(d2s, M, K):
+    lib = d2s._lib
+    N = 768
+    g = torch.Generator(device="cuda").manual_seed(M + K)
+    bf = torch.bfloat16
+    a = Guarded((M, K), bf, torch.randn(M, K, device="cuda", generator=g).bfloat16(), poison_after=True)
+    w = Guarded((N, K), bf, (torch.randn(N, K, device="cuda", generator=g) / K ** 0.5).bfloat16(), poison_after=True)
+    x = Guarded((M, N), bf, torch.randn(M, N, device="cuda", generator=g).bfloat16(), poison_after=True)
+    bias, gam, bet = (torch.randn(N, device="cuda", generator=g).bfloat16() for _ in range(3))
+    outs = []
+    for _ in range(2):
+        s_, h_ = Guarded((M, N), bf), Guarded((M, N), bf)
+        lib.call("d2s_linear_residual_ln_bf16", a.ptr, w.ptr, bias.data_ptr(), x.ptr, gam.data_ptr(), bet.data_ptr(), 1e-6, M, N, K, s_.ptr,
+                 h_.ptr, _stream())
+        torch.cuda.synchronize()
+        for name, gd in (("out_sum", s_), ("out_norm", h_), ("a", a), ("w", w), ("x", x)):
+            assert gd.ok(), f"{name}: guard zone overwritten"
+        assert bool(torch.isfinite(s_.t.float()).all()) and bool(torch.isfinite(h_.t.float()).all())
+        outs.append((s_.t.clone(), h_.t.clone()))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])      # deterministic
