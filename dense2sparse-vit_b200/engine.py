@@ -26,6 +26,7 @@ _FROZEN_BF16 = os.environ.get("D2S_FROZEN_BF16", "1") != "0"   # A/B switch: cac
 _FUSED_ADD_LN_TRAIN = os.environ.get("D2S_FUSED_ADD_LN_TRAIN", "1") != "0"   # A/B switch: residual adds folded into LayerNorm fwd/bwd
 _FUSED_MLP = os.environ.get("D2S_FUSED_MLP", "1") != "0"      # A/B switch for the one-kernel MLP (ops.mlp_residual_ln)
 _FUSED_PAIR = os.environ.get("D2S_FUSED_PAIR", "1") != "0"  # A/B switch for the CTA-pair GEMMs (fc1 pair; proj/fc2 + add + LN)
+_PRED_FUSED = os.environ.get("D2S_PRED_FUSED", "1") != "0"  # A/B switch: second half of the Variant A predictor + selection as one tcgen05 kernel (inference, D = 384)
 _POOL_TRAIN = os.environ.get("D2S_POOL_TRAIN", "1") != "0"  # A/B switch: the predictors' local/global split as one kernel each way
 _THRESHOLD_INFERENCE = os.environ.get("D2S_THRESHOLD_INFERENCE", "0") == "1"   # opt-in: what dynamic_vit.py:935-949 intends
 INIT_N = 14 * 14  # the reference hard-codes 196 spatial tokens (dynamic_vit.py:828, default_dynamic_vit.py:446)
@@ -460,6 +461,11 @@ def predictor_a_select(m, normed, prev, k):
     half = l0.in_features // 2
     # Linear(cat(local, pooled)) = local @ W[:, :half]^T + (pooled @ W[:, half:]^T + b)
     per_image = F.linear(pooled, l0.weight[:, half:], l0.bias)   # (B, D/2)
+    l2, lin = m.out_conv[2], m.out_conv[4]
+    if (_PRED_FUSED and l0.bias is not None and l2.bias is not None and lin.bias is not None
+            and ops.predictor_a_tail_ok(local, l0.weight, l2.weight, lin.weight)):
+        # split Linear + GELU, Linear + GELU, Linear(., 2), log-softmax and the selection as one tcgen05 kernel
+        return ops.predictor_a_tail(local, per_image, l0.weight, l2.weight, l2.bias, lin.weight, lin.bias, k, prev=prev)
     u = F.linear(local, l0.weight[:, :half])
     ops.bias_act_(u, per_image, ops.ACT_GELU)
     z2 = m.out_conv[2](u)                                        # Linear(D/2, D/4) + bias; its GELU is applied by the tail

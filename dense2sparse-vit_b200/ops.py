@@ -107,7 +107,7 @@ def score_tail_a(hidden, weight, bias, k=0, gumbel=None, prev=None, act_input=AC
     _check_cuda(hidden, weight, bias)
     h = _as_kernel_float(hidden.detach()).contiguous()
     B, N, C = h.shape
-    w, b = _f32c(weight), _f32c(bias)
+    w, b = _f32c_param(weight), _f32c_param(bias)
     logp = torch.empty(B, N, 2, dtype=torch.float32, device=h.device)
     p = _f32c(prev.reshape(B, N)) if prev is not None else None
     if gumbel is None:
@@ -871,6 +871,67 @@ def bias_act_(u, bias, act=ACT_GELU):
     n = u.shape[-2] if per_image else 0
     _call("d2s_bias_act", _ptr(u), _ptr(bc), _dtype_code(u), rows, n, C, int(act), _stream(u))
     return u
+
+
+_F32_PARAM_CACHE = {}
+
+
+def _f32c_param(t):
+    """fp32 contiguous copy of a (small) parameter, cached while the parameter's storage and version counter stand: the tail
+    kernels take their last Linear in fp32, and converting it on every call costs two serialised copy kernels per stage."""
+    if t is None:
+        return None
+    if t.dtype == torch.float32 and t.is_contiguous():
+        return t.detach()
+    key = (t.data_ptr(), t._version, t.dtype, tuple(t.shape), t.device)
+    hit = _F32_PARAM_CACHE.get(id(t))
+    if hit is not None and hit[0] == key:
+        return hit[1]
+    if len(_F32_PARAM_CACHE) > 256:
+        _F32_PARAM_CACHE.clear()
+    c = t.detach().to(torch.float32).contiguous()
+    _F32_PARAM_CACHE[id(t)] = (key, c)
+    return c
+
+
+PRED_TAIL_H = 192
+PRED_TAIL_MAX_N = 256
+
+
+def predictor_a_tail_ok(local, w2, w3, w4):
+    """Shapes / dtypes d2s_predictor_a_tail_bf16 takes: bf16, D/2 = 192 with the D -> D/2 -> D/4 -> 2 stack, N <= 256."""
+    H = PRED_TAIL_H
+    return (local.is_cuda and local.dtype == torch.bfloat16 and local.dim() == 3 and local.shape[-1] == H
+            and 1 <= local.shape[1] <= PRED_TAIL_MAX_N
+            and all(w.dtype == torch.bfloat16 and w.is_contiguous() for w in (w2, w3))
+            and tuple(w2.shape) == (H, 2 * H) and tuple(w3.shape) == (H // 2, H) and tuple(w4.shape) == (2, H // 2))
+
+
+def predictor_a_tail(local, per_image, w2, w3, b3, w4, b4, k, prev=None, want_prev_kept=True):
+    """Second half of Variant A's PredictorLG.forward + the stage's selection (vit_models/default_dynamic_vit.py:329-330,
+    :461-467) as ONE tcgen05 kernel: local (B,N,192) bf16 from pool_act, per_image (B,192) = pooled @ W2[:, 192:]^T + b2,
+    prev (B,N) f32 keep decisions or None.
+    Returns (logp (B,N,2) f32, kept (B,k) int64 in descending-score order[, prev_kept (B,k) f32])."""
+    _check_cuda(local, per_image, w2, w3, w4)
+    h = local.detach().contiguous()
+    pl = per_image.detach().to(torch.bfloat16).contiguous()
+    B, N, H = h.shape
+    if not 0 <= k <= N:
+        raise RuntimeError(f"predictor_a_tail: K={k} outside [0, N={N}]")
+    dev = h.device
+    logp = torch.empty(B, N, 2, dtype=torch.float32, device=dev)
+    kept = torch.empty(B, k, dtype=torch.int64, device=dev)
+    prev_kept = torch.empty(B, k, dtype=torch.float32, device=dev) if want_prev_kept else None
+    if tuple(pl.shape) != (B, H):
+        raise RuntimeError(f"predictor_a_tail: per_image must be ({B}, {H}), got {tuple(pl.shape)}")
+    if B == 0:
+        return (logp, kept, prev_kept) if want_prev_kept else (logp, kept)
+    p = _f32c(prev.reshape(B, N)) if prev is not None else None
+    b3c = b3.detach().to(torch.bfloat16).contiguous()
+    w4f, b4f = _f32c_param(w4), _f32c_param(b4)
+    _call("d2s_predictor_a_tail_bf16", _ptr(h), _ptr(pl), _ptr(w2.detach()), _ptr(w3.detach()), _ptr(b3c),
+          _ptr(w4f), _ptr(b4f), _ptr(p), B, N, H, k, _ptr(logp), _ptr(kept), _ptr(prev_kept), _stream(h))
+    return (logp, kept, prev_kept) if want_prev_kept else (logp, kept)
 
 
 class _PoolConcat(torch.autograd.Function):

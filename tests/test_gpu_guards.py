@@ -225,6 +225,39 @@ def test_predictor_split_and_token_kl_stay_in_bounds(d2s, B, N, C):
         assert float(dx.t[:, 0].abs().max()) == 0.0                      # the skipped rows' gradient is written as zeros
 
 
+@pytest.mark.parametrize("B,N,K", [(3, 196, 137), (2, 137, 96), (5, 96, 67), (1, 129, 1), (2, 7, 7), (150, 131, 60)])
+def test_predictor_tail_kernel_stays_in_bounds(d2s, B, N, K):
+    """d2s_predictor_a_tail_bf16: TMA tiles whose second box is nearly empty, rows past N of the last tile, the in-place u tile,
+    the double-buffered key / bias rows (B > 148: several images per CTA)."""
+    lib = d2s._lib
+    H = 192
+    g = torch.Generator(device="cuda").manual_seed(N + K)
+    bf = torch.bfloat16
+    rnd = lambda *s, sc=1.0: torch.randn(*s, device="cuda", generator=g) * sc
+    local = Guarded((B, N, H), bf, rnd(B, N, H, sc=0.6).bfloat16(), poison_after=True)
+    per_image = Guarded((B, H), bf, rnd(B, H, sc=0.3).bfloat16(), poison_after=True)
+    w2 = Guarded((H, 2 * H), bf, rnd(H, 2 * H, sc=0.08).bfloat16(), poison_after=True)
+    w3 = Guarded((H // 2, H), bf, rnd(H // 2, H, sc=0.1).bfloat16(), poison_after=True)
+    b3 = Guarded((H // 2,), bf, rnd(H // 2, sc=0.1).bfloat16(), poison_after=True)
+    w4 = Guarded((2, H // 2), torch.float32, rnd(2, H // 2, sc=0.3), poison_after=True)
+    b4 = Guarded((2,), torch.float32, rnd(2, sc=0.1), poison_after=True)
+    prev = Guarded((B, N), torch.float32, (torch.rand(B, N, device="cuda", generator=g) > 0.3).float(), poison_after=True)
+    outs = []
+    for _ in range(2):
+        logp, kept, pk = Guarded((B, N, 2), torch.float32), Guarded((B, K), torch.int64), Guarded((B, K), torch.float32)
+        lib.call("d2s_predictor_a_tail_bf16", local.ptr, per_image.ptr, w2.ptr, w3.ptr, b3.ptr, w4.ptr, b4.ptr, prev.ptr, B, N, H, K,
+                 logp.ptr, kept.ptr, pk.ptr, _stream())
+        torch.cuda.synchronize()
+        for name, gd in [("logp", logp), ("kept", kept), ("prev_kept", pk), ("local", local), ("per_image", per_image), ("w2", w2),
+                         ("w3", w3), ("b3", b3), ("w4", w4), ("b4", b4), ("prev", prev)]:
+            assert gd.ok(), f"{name}: guard zone overwritten"
+        assert bool(torch.isfinite(logp.t).all()) and bool(torch.isfinite(pk.t).all()), "element left unwritten or fed by an out-of-bounds read"
+        assert int(kept.t.min()) >= 0 and int(kept.t.max()) < N
+        assert all(len(set(row.tolist())) == K for row in kept.t.cpu()[:8])
+        outs.append((logp.t.clone(), kept.t.clone(), pk.t.clone()))
+    assert all(torch.equal(a, b) for a, b in zip(outs[0], outs[1])), "run-to-run difference"
+
+
 @pytest.mark.parametrize("n,begin,end", [(1000, 0, 1000), (1003, 13, 771), (4096, 8, 4088), (17, 1, 16)])
 def test_adamw_flat_touches_only_its_range(d2s, n, begin, end):
     lib = d2s._lib

@@ -820,6 +820,89 @@ def test_score_tail_a_gelu_on_load_and_prev_gather(ops):
     assert torch.equal(pk1.cpu(), torch.ones(B, K))
 
 
+def _tail_inputs(B, N, seed, with_prev=True):
+    H = 192
+    local = (0.6 * fx.randn(seed, B, N, H)).bfloat16()
+    per_image = (0.3 * fx.randn(seed + 1, B, H)).bfloat16()
+    w2 = fx.randn(seed + 2, H, 2 * H, scale=0.08).bfloat16()
+    w3, b3 = fx.randn(seed + 3, H // 2, H, scale=0.1).bfloat16(), fx.randn(seed + 4, H // 2, scale=0.1).bfloat16()
+    w4, b4 = fx.randn(seed + 5, 2, H // 2, scale=0.3), fx.randn(seed + 6, 2, scale=0.1)
+    prev = (torch.rand(B, N, generator=fx.gen(seed + 7)) > 0.25).float() if with_prev else None
+    return local, per_image, w2, w3, b3, w4, b4, prev
+
+
+def _tail_reference(local, per_image, w2, w3, b3, w4, b4):
+    """out_conv of PredictorLG (default_dynamic_vit.py:315-320) on cat(local, pooled.expand) with the first Linear split as
+    local @ W[:, :H]^T + per_image, in fp32 from the same bf16 operands."""
+    F = torch.nn.functional
+    H = local.shape[-1]
+    u = F.gelu(local.float() @ w2.float()[:, :H].t() + per_image.float()[:, None, :])
+    v = F.gelu(u @ w3.float().t() + b3.float())
+    return F.log_softmax(v @ w4.t() + b4, dim=-1)
+
+
+@pytest.mark.parametrize("B,N,K", [(3, 196, 137), (5, 137, 96), (4, 96, 67), (2, 128, 64), (2, 129, 70), (1, 17, 5), (1, 1, 1),
+                                   (2, 256, 200), (3, 200, 0), (2, 64, 64), (300, 196, 137)])
+def test_predictor_a_tail_kernel(ops, B, N, K):
+    """d2s_predictor_a_tail_bf16 (second / third Linear + GELUs + Linear(., 2) + log-softmax + selection as one tcgen05 kernel)
+    against an fp32 evaluation of the same bf16 operands at bf16 tolerance (three chained bf16 roundings: 3e-2 on log-probs of
+    magnitude ~1), the kept list bit-exact against the stable descending sort of the kernel's OWN scores, prev gathered exactly."""
+    local, per_image, w2, w3, b3, w4, b4, prev = _tail_inputs(B, N, 900 + N)
+    logp, kept, pk = ops.predictor_a_tail(cu(local), cu(per_image), cu(w2), cu(w3), cu(b3), cu(w4), cu(b4), K, prev=cu(prev))
+    ref = _tail_reference(local, per_image, w2, w3, b3, w4, b4)
+    assert logp.shape == (B, N, 2) and kept.shape == (B, K) and pk.shape == (B, K)
+    torch.testing.assert_close(logp.cpu(), ref, rtol=3e-2, atol=3e-2)
+    rk, _ = oo.select_topk(logp.cpu()[:, :, 0], K, oo.ORDER_SCORE_DESC)
+    assert torch.equal(kept.cpu(), rk)
+    assert torch.equal(pk.cpu(), oo.batch_index_select(prev, kept.cpu()))
+    # deterministic, and prev = None gathers ones
+    logp2, kept2, pk1 = ops.predictor_a_tail(cu(local), cu(per_image), cu(w2), cu(w3), cu(b3), cu(w4), cu(b4), K)
+    assert torch.equal(logp2, logp) and torch.equal(kept2, kept)
+    assert torch.equal(pk1.cpu(), torch.ones(B, K))
+
+
+def test_predictor_a_tail_matches_the_unfused_path(d2s, ops):
+    """engine.predictor_a_select with the tail kernel against the same call on the library GEMMs + bias_act + score_tail_a: same
+    roundings (every Linear / GELU output in bf16), so the log-probs agree to a few bf16 ulps of the hidden activations and the
+    kept sets differ only where two scores are closer than that."""
+    eng = d2s.engine
+    torch.manual_seed(5)
+    pred = d2s.variant_a.PredictorLG(384).cuda()
+    for p in pred.parameters():
+        torch.nn.init.normal_(p, std=0.08 if p.dim() > 1 else 0.05)
+    pred = pred.to(torch.bfloat16).eval()
+    B, N, K = 6, 196, 137
+    normed = cu(fx.randn(77, B, N, 384)).bfloat16()
+    prev = cu((torch.rand(B, N, generator=fx.gen(78)) > 0.3).float())
+    old = eng._PRED_FUSED
+    try:
+        with torch.no_grad():
+            eng._PRED_FUSED = False
+            lp_u, kept_u, pk_u = eng.predictor_a_select(pred, normed, prev, K)
+            eng._PRED_FUSED = True
+            n0 = d2s._lib.launch_count()
+            lp_f, kept_f, pk_f = eng.predictor_a_select(pred, normed, prev, K)
+            assert d2s._lib.launch_count() - n0 == 2          # pool_act + the tail kernel
+    finally:
+        eng._PRED_FUSED = old
+    torch.testing.assert_close(lp_f, lp_u, rtol=2e-2, atol=2e-2)
+    same = sum(len(set(a.tolist()) & set(b.tolist())) for a, b in zip(kept_u.cpu(), kept_f.cpu()))
+    assert same >= 0.98 * B * K
+    assert torch.equal(pk_f, torch.gather(prev, 1, kept_f))
+
+
+def test_predictor_a_tail_rejects_what_it_cannot_take(ops):
+    local, per_image, w2, w3, b3, w4, b4, prev = _tail_inputs(2, 50, 950)
+    with pytest.raises(RuntimeError):
+        ops.predictor_a_tail(cu(local), cu(per_image), cu(w2), cu(w3), cu(b3), cu(w4), cu(b4), 51)          # K > N
+    with pytest.raises(RuntimeError):
+        ops.predictor_a_tail(cu(local), cu(per_image[:1]), cu(w2), cu(w3), cu(b3), cu(w4), cu(b4), 10)     # per_image rows
+    assert not ops.predictor_a_tail_ok(cu(local).float(), cu(w2), cu(w3), cu(w4))                           # fp32 stays unfused
+    assert not ops.predictor_a_tail_ok(cu(local)[:, :, :96], cu(w2), cu(w3), cu(w4))                        # other widths too
+    empty = ops.predictor_a_tail(cu(local)[:0], cu(per_image)[:0], cu(w2), cu(w3), cu(b3), cu(w4), cu(b4), 10)
+    assert empty[0].shape == (0, 50, 2) and empty[1].shape == (0, 10)
+
+
 @pytest.mark.parametrize("B,T,H,frac", [(3, 197, 6, False), (2, 138, 6, True), (2, 97, 6, True), (2, 64, 3, False), (1, 8, 2, True),
                                         (2, 208, 3, True), (1, 200, 2, False), (2, 129, 2, True), (2, 128, 2, False), (3, 1, 2, False),
                                         (1, 250, 2, True)])
