@@ -360,25 +360,24 @@ def kernel_breakdown(ops, B, dev, torch, pk):
         ms = time_graphed([lambda x=x, k=k: ops.gather_layernorm(x, k, gw, gb, 1e-6) for x, k in sets], torch)
         rows.append(row("gather_layernorm(kept-token gather + norm1)", f"B={B},T={T_in},D={D},K={K}", ms, by, 1))
         del sets
-        # the fused predictor tail: GELU on load of the (B,N,D/4) hidden activations, Linear(D/4,2), log-softmax, top-K in score order,
-        # previous decisions gathered (what engine.predictor_a_select launches)
-        by = B * (e * n_in * (D // 4) + 8 * n_in + 8 * K + 4 * K + (4 * n_in if s else 0))
-        ns = nsets_for(by)
-        W, bias = torch.randn(2, D // 4, device=dev) * 0.1, torch.zeros(2, device=dev)
-        hids = [torch.randn(B, n_in, D // 4, device=dev, dtype=bf) for _ in range(ns)]
+        # second half of the predictor + selection as one tcgen05 kernel (what engine.predictor_a_select launches after the first
+        # Linear and pool_act): reads local (B,N,D/2) and the per-image bias rows, writes log-probs, kept indices, gathered decisions
         prev = (torch.rand(B, n_in, device=dev) > 0.1).float() if s else None
-        ms = time_graphed([lambda h=h: ops.score_tail_a(h, W, bias, k=K, prev=prev, act_input=ops.ACT_GELU, want_prev_kept=True)
-                           for h in hids], torch)
-        rows.append(row("score_tail_a(GELU + Linear + log-softmax + top-K + prev gather)", f"B={B},N={n_in},C={D // 4},K={K}", ms, by, 1))
+        H2 = D // 2
+        by = B * (e * n_in * H2 + e * H2 + 8 * n_in + 8 * K + 4 * K + (4 * n_in if s else 0))
+        w2, w3, b3 = (torch.randn(H2, D, device=dev) * 0.05).to(bf), (torch.randn(H2 // 2, H2, device=dev) * 0.07).to(bf), torch.zeros(H2 // 2, device=dev, dtype=bf)
+        W, bias = torch.randn(2, D // 4, device=dev) * 0.1, torch.zeros(2, device=dev)
+        pim = torch.randn(B, H2, device=dev, dtype=bf) * 0.3
+        locs = [torch.randn(B, n_in, H2, device=dev, dtype=bf) * 0.5 for _ in range(nsets_for(by))]
+        if ops.predictor_a_tail_ok(locs[0], w2, w3, W):
+            ms = time_graphed([lambda h=h: ops.predictor_a_tail(h, pim, w2, w3, b3, W, bias, K, prev=prev) for h in locs], torch)
+            rows.append(row("predictor_a_tail(Linear+GELU x2 + Linear + log-softmax + top-K + prev gather, tcgen05)",
+                            f"B={B},N={n_in},C={H2},K={K}", ms, by, 1))
         zs = [torch.randn(B, n_in, D, device=dev, dtype=bf) for _ in range(nsets_for(B * n_in * D * e * 1.5))]
         ms = time_graphed([lambda z=z: ops.pool_act(z, prev, ops.ACT_GELU) for z in zs], torch)
         rows.append(row("pool_act(GELU + policy-weighted mean pool)", f"B={B},N={n_in},C={D}", ms, B * n_in * D * e * 1.5, 1))
-        us = [torch.randn(B, n_in, D // 2, device=dev, dtype=bf) for _ in range(nsets_for(B * n_in * D * e))]
-        pim = torch.randn(B, D // 2, device=dev, dtype=bf)
-        ms = time_graphed([lambda u=u: ops.bias_act_(u, pim, ops.ACT_GELU) for u in us], torch)
-        rows.append(row("bias_act(per-image bias + GELU, in place)", f"B={B},N={n_in},C={D // 2}", ms, B * n_in * D * e, 1))
         n_in = K
-        del hids, zs, us
+        del locs, zs
     # dominant kernel of the step (profiles/: ~38 % of the serialised step): the one-kernel MLP.  Tensor-bound: 4 * D * 4D flops
     # per token against 4 * D * 2 bytes of HBM traffic (the hidden activations stay on chip).  Aggregated over its launches at
     # the four token counts; peak = the measured burst bf16 GEMM rate (the kernel is timed alone).
