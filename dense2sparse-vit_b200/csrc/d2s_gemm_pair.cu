@@ -38,7 +38,7 @@ constexpr int kGpBM = 128, kGpBK = 64, kGpMaxThreads = 576;   // warp 0 TMA, war
 constexpr uint32_t kGpABytes = kGpBM * 128;      // 128 rows x 64 bf16
 constexpr uint32_t kGpBlkBytes = 128 * 128;      // one staged 128 x 64 bf16 block (SWIZZLE_128B)
 
-enum { kGpModeAct = 0, kGpModeLn = 1 };
+enum { kGpModeAct = 0, kGpModeLn = 1, kGpModeAct192 = 2 };   // Act192: MODE_ACT with 192-column tiles (N % 192 == 0, e.g. N = 384)
 
 // clock64 phase totals per epilogue warp (profiling builds only: D2S_NVCC_EXTRA=-DD2S_GEMM_TRACE_BUILD; buffer named by D2S_GEMM_TRACE)
 #ifdef D2S_GEMM_TRACE_BUILD
@@ -56,6 +56,10 @@ template <int MODE, int NSUB> struct GpCfg;
 template <> struct GpCfg<kGpModeAct, 1> {        // fc1: 256-column tiles, accumulator double-buffered
   static constexpr int UN = 256, NSUB = 1, ACC = 2, STAGES = 4, BLOCKS = 4;      // BLOCKS: staging blocks of 16 KB
   static constexpr int PARTS = 4, MAXREG = 96;     // epilogue warps per TMEM lane quadrant; 2 + 16 warps -> 20 allocated -> 102 regs
+};
+template <> struct GpCfg<kGpModeAct192, 1> {     // Linear(D, D) + GELU of the predictors (N = 384): 192-column tiles, accumulator double-buffered
+  static constexpr int UN = 192, NSUB = 1, ACC = 2, STAGES = 4, BLOCKS = 3;
+  static constexpr int PARTS = 3, MAXREG = 128;
 };
 template <> struct GpCfg<kGpModeLn, 2> {         // D = 384: two N = 192 MMAs per k-step, one accumulator
   static constexpr int UN = 192, NSUB = 2, ACC = 1, STAGES = 4, BLOCKS = 3;
@@ -207,8 +211,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16);
     uint32_t tile = 0;
 
-    if (MODE == kGpModeAct) {
-      // part p owns the 64-column block p of every 256-column tile: one staging block, one TMA store per tile
+    if (MODE != kGpModeLn) {
+      // part p owns the 64-column block p of every 256- (192-) column tile: one staging block, one TMA store per tile
       GP_TRACE_DECL(5)
       const bool issuer = (ew & 3) == 0 && lane == 0;
       unsigned char* blk = blocks + (size_t)part * kGpBlkBytes;
@@ -517,8 +521,9 @@ extern "C" int d2s_linear_act_pair_bf16(const void* a, const void* w, const void
                                         void* pre, d2s_stream_t stream) {
   const char* what = "d2s_linear_act_pair_bf16";
   D2S_REQUIRE(a && w && out, D2S_ERR_ARG, "linear_act_pair: null pointer");
-  D2S_REQUIRE(M >= 0 && N >= 256 && N % 256 == 0 && N <= 4096 && K >= kGpBK && K % kGpBK == 0, D2S_ERR_ARG,
-              "linear_act_pair: need N %% 256 == 0 (N <= 4096) and K %% %d == 0 (got M=%d N=%d K=%d)", kGpBK, M, N, K);
+  const bool t192 = N % 256 != 0;                  // 192-column tiles for widths like 384
+  D2S_REQUIRE(M >= 0 && N >= 192 && (N % 256 == 0 || N % 192 == 0) && N <= 4096 && K >= kGpBK && K % kGpBK == 0, D2S_ERR_ARG,
+              "linear_act_pair: need N %% 256 == 0 or N %% 192 == 0 (N <= 4096) and K %% %d == 0 (got M=%d N=%d K=%d)", kGpBK, M, N, K);
   D2S_REQUIRE(act >= D2S_ACT_NONE && act <= D2S_ACT_RELU, D2S_ERR_ARG, "linear_act_pair: bad activation %d", act);
   D2S_REQUIRE(aligned16(a) && aligned16(w) && aligned16(out) && aligned16(pre), D2S_ERR_ALIGN,
               "linear_act_pair: pointers must be 16-byte aligned");
@@ -526,10 +531,15 @@ extern "C" int d2s_linear_act_pair_bf16(const void* a, const void* w, const void
   CUtensorMap ma, mw, mo;
   int rc;
   if ((rc = gp_map_2d(&ma, a, K, M, kGpBK, kGpBM, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, what))) return rc;
-  if ((rc = gp_map_2d(&mw, w, K, N, kGpBK, 128, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, what))) return rc;
+  if ((rc = gp_map_2d(&mw, w, K, N, kGpBK, t192 ? 96 : 128, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, what))) return rc;
   if ((rc = gp_map_2d(&mo, out, N, M, 64, kGpBM, CU_TENSOR_MAP_L2_PROMOTION_NONE, what))) return rc;
   GpParams p{(const __nv_bfloat16*)bias, nullptr, nullptr, nullptr, nullptr, nullptr, (__nv_bfloat16*)pre, 0.f, M, N, K, act, 0,
              gp_trace(), gp_debug()};
+  if (t192) {
+    if (act == D2S_ACT_GELU) return gp_launch<kGpModeAct192, 1, D2S_ACT_GELU>(ma, mw, mo, p, (cudaStream_t)stream, what);
+    if (act == D2S_ACT_RELU) return gp_launch<kGpModeAct192, 1, D2S_ACT_RELU>(ma, mw, mo, p, (cudaStream_t)stream, what);
+    return gp_launch<kGpModeAct192, 1, D2S_ACT_NONE>(ma, mw, mo, p, (cudaStream_t)stream, what);
+  }
   if (act == D2S_ACT_GELU) return gp_launch<kGpModeAct, 1, D2S_ACT_GELU>(ma, mw, mo, p, (cudaStream_t)stream, what);
   if (act == D2S_ACT_RELU) return gp_launch<kGpModeAct, 1, D2S_ACT_RELU>(ma, mw, mo, p, (cudaStream_t)stream, what);
   return gp_launch<kGpModeAct, 1, D2S_ACT_NONE>(ma, mw, mo, p, (cudaStream_t)stream, what);

@@ -92,8 +92,12 @@ pool_act_kernel(const T_* __restrict__ z, const float* __restrict__ policy, int 
   extern __shared__ float red[];  // groups x (C/2) partial sums, then groups partial policy sums
   const int b = blockIdx.x;
   const int nvec = C / VE, half_vec = nvec / 2, half = C / 2;
-  const int groups = kPoolThreads / nvec;  // host guarantees nvec <= kPoolThreads
-  const int v = threadIdx.x % nvec, g = threadIdx.x / nvec;
+  // local == NULL: only the pooled global half is wanted (z is already activated and its local half is consumed in place
+  // by the next kernel): the threads cover the upper half of the row only, twice as many token groups
+  const bool only_pool = local == nullptr;
+  const int tv = only_pool ? half_vec : nvec;          // 16-byte vectors per token row handled here
+  const int groups = kPoolThreads / tv;                // host guarantees nvec <= kPoolThreads
+  const int v = (only_pool ? half_vec : 0) + threadIdx.x % tv, g = threadIdx.x / tv;
   float acc[8];
 #pragma unroll
   for (int q = 0; q < 8; ++q) acc[q] = 0.f;
@@ -443,7 +447,7 @@ using namespace d2s;
 
 extern "C" int d2s_pool_act(const void* z, const float* policy, int dtype, int B, int N, int C, int act, void* local,
                             void* pooled, d2s_stream_t stream) {
-  D2S_REQUIRE(z && local && pooled, D2S_ERR_ARG, "pool_act: null pointer");
+  D2S_REQUIRE(z && pooled, D2S_ERR_ARG, "pool_act: null pointer");
   D2S_REQUIRE(dtype == D2S_F32 || dtype == D2S_BF16, D2S_ERR_ARG, "pool_act: dtype %d unsupported", dtype);
   const int ve = dtype == D2S_BF16 ? 8 : 4;
   D2S_REQUIRE(B >= 0 && N >= 1 && C >= 2 * ve && C % (2 * ve) == 0 && C / ve <= kPoolThreads, D2S_ERR_ARG,
@@ -451,7 +455,7 @@ extern "C" int d2s_pool_act(const void* z, const float* policy, int dtype, int B
   D2S_REQUIRE(act >= D2S_ACT_NONE && act <= D2S_ACT_RELU, D2S_ERR_ARG, "pool_act: bad activation %d", act);
   D2S_REQUIRE(aligned16(z) && aligned16(local), D2S_ERR_ALIGN, "pool_act: z/local must be 16-byte aligned");
   if (B == 0) return D2S_OK;
-  const int groups = kPoolThreads / (C / ve);
+  const int groups = kPoolThreads / (local ? C / ve : C / ve / 2);
   const size_t smem = ((size_t)groups * (C / 2) + groups) * sizeof(float);
   if (dtype == D2S_BF16)
     pool_act_kernel<__nv_bfloat16><<<B, kPoolThreads, smem, (cudaStream_t)stream>>>(

@@ -5,7 +5,8 @@
 //   v  = GELU(Linear(D/2, D/4)(u))                                          out_conv[2:4]
 //   logp = LogSoftmax(Linear(D/4, 2)(v));  kept = argsort(logp[:, :, 0], descending)[:, :K]        out_conv[4:6], :461-465
 //
-// local (B,N,D/2) = GELU(in_conv)(x)[:, :, :D/2] comes from d2s_pool_act; the per-image term pooled @ W2[:, D/2:]^T + b2 (B,D/2)
+// local (B,N,D/2) = GELU(in_conv)(x)[:, :, :D/2] -- dense from d2s_pool_act, or the first D/2 columns of the (B,N,D) output of the
+// Linear + GELU GEMM read in place through the tensor map's row stride --; the per-image term pooled @ W2[:, D/2:]^T + b2 (B,D/2)
 // from one small library GEMM over d2s_pool_act's pooled rows.
 // Before: two library GEMMs + bias_act + the score-tail kernel (6 launches, (B,N,D/2) written and read twice and (B,N,D/4) once).  Here `local` is read once and only (B,N,2) + (B,K) are written; u and v live in TMEM / shared memory.
 //
@@ -370,14 +371,15 @@ static int pf_map(CUtensorMap* map, const void* base, int rank, const cuuint64_t
 
 using namespace d2s;
 
-extern "C" int d2s_predictor_a_tail_bf16(const void* local, const void* per_image, const void* w2, const void* w3, const void* b3,
-                                         const float* w4, const float* b4, const float* prev, int B, int N, int H, int K,
-                                         float* logp, int64_t* kept, float* prev_kept, d2s_stream_t stream) {
+extern "C" int d2s_predictor_a_tail_bf16(const void* local, int ld, const void* per_image, const void* w2, const void* w3,
+                                         const void* b3, const float* w4, const float* b4, const float* prev, int B, int N, int H,
+                                         int K, float* logp, int64_t* kept, float* prev_kept, d2s_stream_t stream) {
   const char* what = "d2s_predictor_a_tail_bf16";
   D2S_REQUIRE(local && per_image && w2 && w3 && b3 && w4 && b4 && logp && (kept || K == 0), D2S_ERR_ARG, "predictor_a_tail: null pointer");
   D2S_REQUIRE(H == kPfH, D2S_ERR_ARG, "predictor_a_tail: H=%d unsupported (the kernel is built for D/2 = %d)", H, kPfH);
   D2S_REQUIRE(B >= 0 && N >= 1 && N <= kPfMaxN, D2S_ERR_ARG, "predictor_a_tail: N=%d outside [1,%d]", N, kPfMaxN);
   D2S_REQUIRE(K >= 0 && K <= N, D2S_ERR_ARG, "predictor_a_tail: K=%d outside [0,N=%d]", K, N);
+  D2S_REQUIRE(ld >= H && ld % 8 == 0, D2S_ERR_ARG, "predictor_a_tail: row stride ld=%d must be a multiple of 8 elements, at least H=%d", ld, H);
   D2S_REQUIRE(aligned16(local) && aligned16(per_image) && aligned16(w2) && aligned16(w3) && aligned16(logp), D2S_ERR_ALIGN,
               "predictor_a_tail: local / per_image / weights / logp must be 16-byte aligned");
   if (B == 0) return D2S_OK;
@@ -385,7 +387,7 @@ extern "C" int d2s_predictor_a_tail_bf16(const void* local, const void* per_imag
   int rc;
   {
     const cuuint64_t gdim[3] = {(cuuint64_t)H, (cuuint64_t)N, (cuuint64_t)B};
-    const cuuint64_t gstr[2] = {(cuuint64_t)H * 2, (cuuint64_t)N * H * 2};
+    const cuuint64_t gstr[2] = {(cuuint64_t)ld * 2, (cuuint64_t)N * ld * 2};
     const cuuint32_t box[3] = {64, 128, 1};
     if ((rc = pf_map(&mx, local, 3, gdim, gstr, box, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, what))) return rc;
   }

@@ -455,15 +455,22 @@ def predictor_a_select(m, normed, prev, k):
     GELU / multiply / reduce / expand / concat passes: `normed` = in_conv's LayerNorm output (from the fused
     add+LayerNorm), `prev` (B,N) fp32 keep decisions of the previous stage or None (all ones).
     Returns (log-probs (B,N,2) fp32, kept (B,k) int64 in descending-score order, prev gathered at kept (B,k) fp32)."""
-    z = m.in_conv[1](normed)                                     # Linear(D,D) + bias (cuBLAS)
-    local, pooled = ops.pool_act(z, prev, ops.ACT_GELU)          # GELU + policy-weighted mean pool, one pass
-    l0 = m.out_conv[0]
+    l1, l0, l2, lin = m.in_conv[1], m.out_conv[0], m.out_conv[2], m.out_conv[4]
     half = l0.in_features // 2
+    tail_ok = _PRED_FUSED and l0.bias is not None and l2.bias is not None and lin.bias is not None
+    if (tail_ok and _FUSED_PAIR and normed.dtype == torch.bfloat16 and l1.weight.dtype == torch.bfloat16
+            and l1.out_features % 192 == 0 and l1.in_features % 64 == 0
+            and ops.predictor_a_tail_ok(normed[:, :, :half], l0.weight, l2.weight, lin.weight)):
+        # Linear(D,D) + GELU as one tcgen05 GEMM; its local half is read in place by the tail kernel, its global half only pooled
+        g = ops.linear_act(normed, l1.weight, l1.bias, ops.ACT_GELU)
+        _, pooled = ops.pool_act(g, prev, ops.ACT_NONE, want_local=False)
+        per_image = F.linear(pooled, l0.weight[:, half:], l0.bias)
+        return ops.predictor_a_tail(g[:, :, :half], per_image, l0.weight, l2.weight, l2.bias, lin.weight, lin.bias, k, prev=prev)
+    z = l1(normed)                                               # Linear(D,D) + bias (cuBLAS)
+    local, pooled = ops.pool_act(z, prev, ops.ACT_GELU)          # GELU + policy-weighted mean pool, one pass
     # Linear(cat(local, pooled)) = local @ W[:, :half]^T + (pooled @ W[:, half:]^T + b)
     per_image = F.linear(pooled, l0.weight[:, half:], l0.bias)   # (B, D/2)
-    l2, lin = m.out_conv[2], m.out_conv[4]
-    if (_PRED_FUSED and l0.bias is not None and l2.bias is not None and lin.bias is not None
-            and ops.predictor_a_tail_ok(local, l0.weight, l2.weight, lin.weight)):
+    if tail_ok and ops.predictor_a_tail_ok(local, l0.weight, l2.weight, lin.weight):
         # split Linear + GELU, Linear + GELU, Linear(., 2), log-softmax and the selection as one tcgen05 kernel
         return ops.predictor_a_tail(local, per_image, l0.weight, l2.weight, l2.bias, lin.weight, lin.bias, k, prev=prev)
     u = F.linear(local, l0.weight[:, :half])

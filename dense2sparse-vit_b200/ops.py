@@ -5,6 +5,7 @@ caching allocator; nothing synchronises with the host.  Inputs must be CUDA tens
 fallback (the CPU restatement lives in oracle/ and is test infrastructure only).
 """
 import os
+import weakref
 
 import torch
 import torch.nn.functional as F
@@ -845,14 +846,15 @@ def gather_layernorm(x, kept, weight, bias, eps):
 # predictor body (inference)
 # ----------------------------------------------------------------------------------------------
 
-def pool_act(z, policy=None, act=ACT_GELU):
+def pool_act(z, policy=None, act=ACT_GELU, want_local=True):
     """z (B,N,C) -> (local (B,N,C/2) = act(z[..., :C/2]), pooled (B,C/2) = policy-weighted mean over tokens of
-    act(z[..., C/2:])) in one pass (vit_models/default_dynamic_vit.py:325-328; dynamic_vit.py:538-542)."""
+    act(z[..., C/2:])) in one pass (vit_models/default_dynamic_vit.py:325-328; dynamic_vit.py:538-542).
+    want_local=False: (None, pooled) -- z is already activated and its local half is consumed in place by the next kernel."""
     _check_cuda(z, policy)
     zc = z.detach().contiguous()
     B, N, C = zc.shape
     pol = _f32c(policy.reshape(B, N)) if policy is not None else None
-    local = torch.empty(B, N, C // 2, dtype=zc.dtype, device=zc.device)
+    local = torch.empty(B, N, C // 2, dtype=zc.dtype, device=zc.device) if want_local else None
     pooled = torch.empty(B, C // 2, dtype=zc.dtype, device=zc.device)
     _call("d2s_pool_act", _ptr(zc), _ptr(pol), _dtype_code(zc), B, N, C, int(act), _ptr(local), _ptr(pooled), _stream(zc))
     return local, pooled
@@ -877,20 +879,25 @@ _F32_PARAM_CACHE = {}
 
 
 def _f32c_param(t):
-    """fp32 contiguous copy of a (small) parameter, cached while the parameter's storage and version counter stand: the tail
-    kernels take their last Linear in fp32, and converting it on every call costs two serialised copy kernels per stage."""
+    """fp32 contiguous copy of a (small) parameter, cached while THIS tensor object, its storage and its version counter stand:
+    the tail kernels take their last Linear in fp32, and converting it on every call costs two serialised copy kernels per
+    stage.  The entry holds a weak reference to the tensor it was made from: a new tensor that happens to reuse the id, the
+    address and the version of a dead one is a miss."""
     if t is None:
         return None
     if t.dtype == torch.float32 and t.is_contiguous():
         return t.detach()
     key = (t.data_ptr(), t._version, t.dtype, tuple(t.shape), t.device)
     hit = _F32_PARAM_CACHE.get(id(t))
-    if hit is not None and hit[0] == key:
-        return hit[1]
+    if hit is not None and hit[0]() is t and hit[1] == key:
+        return hit[2]
     if len(_F32_PARAM_CACHE) > 256:
-        _F32_PARAM_CACHE.clear()
+        for k in [k for k, v in _F32_PARAM_CACHE.items() if v[0]() is None]:
+            del _F32_PARAM_CACHE[k]
+        if len(_F32_PARAM_CACHE) > 256:
+            _F32_PARAM_CACHE.clear()
     c = t.detach().to(torch.float32).contiguous()
-    _F32_PARAM_CACHE[id(t)] = (key, c)
+    _F32_PARAM_CACHE[id(t)] = (weakref.ref(t), key, c)
     return c
 
 
@@ -913,9 +920,14 @@ def predictor_a_tail(local, per_image, w2, w3, b3, w4, b4, k, prev=None, want_pr
     prev (B,N) f32 keep decisions or None.
     Returns (logp (B,N,2) f32, kept (B,k) int64 in descending-score order[, prev_kept (B,k) f32])."""
     _check_cuda(local, per_image, w2, w3, w4)
-    h = local.detach().contiguous()
-    pl = per_image.detach().to(torch.bfloat16).contiguous()
+    h = local.detach()
     B, N, H = h.shape
+    # a column slice of a wider contiguous (B, N, ld) tensor is read in place through the tensor map's row stride
+    if not (h.stride(2) == 1 and h.stride(1) % 8 == 0 and h.stride(1) >= H and (B <= 1 or h.stride(0) == N * h.stride(1))
+            and h.data_ptr() % 16 == 0):
+        h = h.contiguous()
+    ld = h.stride(1) if N > 1 else H
+    pl = per_image.detach().to(torch.bfloat16).contiguous()
     if not 0 <= k <= N:
         raise RuntimeError(f"predictor_a_tail: K={k} outside [0, N={N}]")
     dev = h.device
@@ -929,7 +941,7 @@ def predictor_a_tail(local, per_image, w2, w3, b3, w4, b4, k, prev=None, want_pr
     p = _f32c(prev.reshape(B, N)) if prev is not None else None
     b3c = b3.detach().to(torch.bfloat16).contiguous()
     w4f, b4f = _f32c_param(w4), _f32c_param(b4)
-    _call("d2s_predictor_a_tail_bf16", _ptr(h), _ptr(pl), _ptr(w2.detach()), _ptr(w3.detach()), _ptr(b3c),
+    _call("d2s_predictor_a_tail_bf16", _ptr(h), int(ld), _ptr(pl), _ptr(w2.detach()), _ptr(w3.detach()), _ptr(b3c),
           _ptr(w4f), _ptr(b4f), _ptr(p), B, N, H, k, _ptr(logp), _ptr(kept), _ptr(prev_kept), _stream(h))
     return (logp, kept, prev_kept) if want_prev_kept else (logp, kept)
 
@@ -1216,7 +1228,7 @@ def layer_norm(x, weight, bias, eps, out_dtype=None, row0=0):
 
 def linear_act(x, weight, bias, act=ACT_GELU, want_pre=False):
     """act(x @ weight^T + bias) in one CTA-pair tcgen05 GEMM with the activation in the epilogue (bf16, no autograd).
-    x (..., K) contiguous, weight (N, K), N % 256 == 0, K % 64 == 0.  want_pre: returns (act(u), u) with u the Linear's own
+    x (..., K) contiguous, weight (N, K), N % 256 == 0 or N % 192 == 0 (256- or 192-column tiles), K % 64 == 0.  want_pre: returns (act(u), u) with u the Linear's own
     output as a second result of the same kernel."""
     _check_cuda(x, weight, bias)
     if x.dtype != torch.bfloat16:

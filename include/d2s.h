@@ -215,6 +215,7 @@ int d2s_attn_policy_bwd(const void* qkv, const float* policy, const void* out, c
 /* ---- predictor body (inference path of PredictorLG.forward, default_dynamic_vit.py:324-330; dynamic_vit.py:538-546)
  * d2s_pool_act: z (B,N,C) = in_conv's Linear output; local (B,N,C/2) = act(z[:,:,:C/2]);
  *   pooled (B,C/2) = sum_n act(z[b,n,C/2:]) * policy[b,n] / sum_n policy[b,n]   (policy (B,N) f32; NULL => mean).
+ *   local NULL: only pooled is produced (z already activated, its local half consumed in place by the next kernel).
  * d2s_bias_act: u (rows,C) = act(u + bias[row / N]) in place; bias (rows/N, C) (N == 0: one shared row; NULL: none)
  *   -- the per-image term pooled @ W_global^T + b of the split Linear that replaces cat + Linear (:329,
  *   out_conv[0]); with bias NULL it is the in-place activation of Mlp.forward (dynamic_vit.py:170-171).
@@ -226,12 +227,13 @@ int d2s_bias_act(void* u, const void* bias, int dtype, long long rows, int N, in
  * default_dynamic_vit.py:329-330 = out_conv on cat(local, pooled.expand), fused with the stage's selection, :461-467):
  * Linear(D,D/2) + GELU (split as local @ W2[:, :D/2]^T + per_image, per_image = pooled @ W2[:, D/2:]^T + b2), Linear(D/2,D/4) +
  * GELU, Linear(D/4,2), LogSoftmax and the stable descending top-K -- replaces two library GEMMs, d2s_bias_act and d2s_score_tail_a.
- *   local (B,N,H) bf16 as written by d2s_pool_act (H = D/2 = 192), per_image (B,H) bf16; w2 (H,2H) (only its first H columns
+ *   local (B,N,H) bf16 (H = D/2 = 192) with a row stride of ld elements (ld = H: dense, as written by d2s_pool_act; ld = 2H: the
+ *   first half of every row of the (B,N,D) Linear + GELU output, read in place), per_image (B,H) bf16; w2 (H,2H) (only its first H columns
  *   are read), w3 (H/2,H) bf16 row-major as nn.Linear stores them, b3 bf16; w4 (2,H/2), b4 (2) f32; prev (B,N) f32 keep
  *   decisions or NULL (all ones);
  *   logp (B,N,2) f32, kept (B,K) int64 in descending-score order (ties: lower index first), prev_kept (B,K) f32 =
  *   prev gathered at kept (NULL to skip).  N <= 256.  The hidden activations never touch HBM. */
-int d2s_predictor_a_tail_bf16(const void* local, const void* per_image, const void* w2, const void* w3, const void* b3,
+int d2s_predictor_a_tail_bf16(const void* local, int ld, const void* per_image, const void* w2, const void* w3, const void* b3,
                               const float* w4, const float* b4, const float* prev, int B, int N, int H, int K,
                               float* logp, int64_t* kept, float* prev_kept, d2s_stream_t stream);
 /* Variant B's concat (dynamic_vit.py:539-545) in place: z (B,N,C) <- cat(z[:,:,:C/2], mean_n(z[:,:,C/2:]).expand). */
@@ -288,7 +290,7 @@ int d2s_assemble_layernorm(const void* patches, const void* cls, const void* pos
 
 /* Linear + activation in one tcgen05 GEMM (fc1 + GELU of Mlp.forward, dynamic_vit.py:159-175), bf16 only:
  * out (M,N) = act(a (M,K) @ w (N,K)^T + bias (N)); fp32 accumulation; bias may be NULL.
- * N % 256 == 0 (N <= 4096), K % 64 == 0.  CTA pair (tcgen05 cta_group::2, 256-row tiles, half of the weight tile per CTA).
+ * N % 256 == 0 or N % 192 == 0 (256- or 192-column tiles; N <= 4096), K % 64 == 0.  CTA pair (tcgen05 cta_group::2, 256-row tiles, half of the weight tile per CTA).
  * pre (M,N) or NULL: also write the pre-activation a @ w^T + bias (training: GELU' needs it; saves torch's separate GELU pass). */
 int d2s_linear_act_pair_bf16(const void* a, const void* w, const void* bias, int M, int N, int K, int act, void* out,
                              void* pre, d2s_stream_t stream);

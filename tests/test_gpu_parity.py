@@ -607,6 +607,36 @@ def test_pool_act(ops, dtype, B, N, Cc, with_policy):
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("B,N,Cc", [(3, 196, 384), (2, 137, 768), (1, 5, 64)])
+def test_pool_act_pooled_only(ops, dtype, B, N, Cc):
+    """want_local=False (an already activated tensor whose local half is read in place by the next kernel): the pooled rows are
+    BIT-identical to the two-output call's, nothing else is written."""
+    z = (fx.randn(160 + Cc, B, N, Cc) * 1.5).to(dtype)
+    pol = (torch.rand(B, N, generator=fx.gen(161)) > 0.3).float()
+    pol[:, 0] = 1
+    for act in (ops.ACT_NONE, ops.ACT_GELU):
+        _, p_both = ops.pool_act(cu(z), cu(pol), act)
+        none, p_only = ops.pool_act(cu(z), cu(pol), act, want_local=False)
+        assert none is None
+        torch.testing.assert_close(p_only, p_both, rtol=2e-3, atol=2e-3)      # (the token groups sum in a different order)
+    _, rp = oo.pool_act(z, pol, "gelu")
+    tol = dict(rtol=1e-5, atol=1e-6) if dtype == torch.float32 else dict(rtol=1e-2, atol=1e-2)
+    torch.testing.assert_close(p_only.cpu().float(), rp.float(), **tol)
+
+
+def test_predictor_a_tail_reads_a_column_slice_in_place(ops):
+    """local given as the first 192 columns of a (B, N, 384) tensor (the Linear + GELU GEMM's output): identical results to the
+    dense copy, no copy made (the tensor map carries the row stride)."""
+    B, N, K = 5, 196, 137
+    local, per_image, w2, w3, b3, w4, b4, prev = _tail_inputs(B, N, 990)
+    wide = torch.cat([local, torch.full_like(local, float("nan"))], dim=-1)      # whatever sits in the other half is never read
+    wide_c = cu(wide)
+    a = ops.predictor_a_tail(wide_c[:, :, :192], cu(per_image), cu(w2), cu(w3), cu(b3), cu(w4), cu(b4), K, prev=cu(prev))
+    b = ops.predictor_a_tail(cu(local), cu(per_image), cu(w2), cu(w3), cu(b3), cu(w4), cu(b4), K, prev=cu(prev))
+    assert all(torch.equal(x, y) for x, y in zip(a, b))
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_bias_act_and_split_linear_identity(ops, dtype):
     B, N, Cc = 4, 196, 192
     u = fx.randn(150, B, N, Cc).to(dtype)
@@ -684,7 +714,9 @@ def test_gelu_inplace_matches_exact_erf(ops):
 
 
 @pytest.mark.parametrize("M,N,K,act", [(1000, 1536, 384, 1), (256, 256, 64, 1), (77, 512, 128, 0), (3 * 197, 1536, 384, 2),
-                                       (20000, 1536, 384, 1), (513, 3072, 768, 1), (129, 256, 64, 0), (128, 256, 64, 1)])
+                                       (20000, 1536, 384, 1), (513, 3072, 768, 1), (129, 256, 64, 0), (128, 256, 64, 1),
+                                       (1000, 384, 384, 1), (3 * 196 + 5, 384, 384, 1), (257, 192, 64, 0), (20000, 384, 384, 2),
+                                       (300, 576, 128, 1)])
 def test_linear_act_pair_gemm(ops, M, N, K, act):
     """CTA-pair (cta_group::2) variant of the fc1 GEMM: same contract, ragged row tails in either CTA of the pair."""
     x = (fx.randn(210 + M % 97, M, K) * 1.0).bfloat16()
@@ -697,7 +729,7 @@ def test_linear_act_pair_gemm(ops, M, N, K, act):
     assert out.shape == (M, N) and out.dtype == torch.bfloat16
 
 
-@pytest.mark.parametrize("M,N,K", [(1000, 1536, 384), (50432, 1536, 384), (77, 256, 64)])
+@pytest.mark.parametrize("M,N,K", [(1000, 1536, 384), (50432, 1536, 384), (77, 256, 64), (777, 384, 384)])
 def test_linear_act_pair_gemm_second_output(ops, M, N, K):
     """Training forward of fc1 -> GELU: the same GEMM also writes the Linear's own output (GELU' needs it)."""
     x = (fx.randn(220 + M % 97, M, K) * 1.0).bfloat16()
@@ -882,7 +914,7 @@ def test_predictor_a_tail_matches_the_unfused_path(d2s, ops):
             eng._PRED_FUSED = True
             n0 = d2s._lib.launch_count()
             lp_f, kept_f, pk_f = eng.predictor_a_select(pred, normed, prev, K)
-            assert d2s._lib.launch_count() - n0 == 2          # pool_act + the tail kernel
+            assert d2s._lib.launch_count() - n0 == 3          # Linear + GELU GEMM, pool_act (pooled only), the tail kernel
     finally:
         eng._PRED_FUSED = old
     torch.testing.assert_close(lp_f, lp_u, rtol=2e-2, atol=2e-2)
@@ -1158,3 +1190,19 @@ def test_round2_training_ops_take_empty_inputs(ops):
         ops.token_kl_rows(torch.zeros(2, 4, 12, device=dev), torch.zeros(2, 4, 12, device=dev))   # C % 8 != 0
     with pytest.raises(RuntimeError):
         ops.pool_concat_train(torch.zeros(2, 4, 12, device=dev, dtype=torch.float64))
+
+
+def test_cached_fp32_parameter_copies_follow_the_parameter(ops):
+    """ops._f32c_param (fp32 copies of the tail's last Linear, cached across calls): in-place updates, dtype casts of the
+    module and a NEW tensor that reuses a dead one's address must all be seen."""
+    lin = torch.nn.Linear(96, 2).cuda().to(torch.bfloat16)
+    a = ops._f32c_param(lin.weight)
+    assert ops._f32c_param(lin.weight) is a                                  # cached
+    with torch.no_grad():
+        lin.weight.mul_(2.0)
+    b = ops._f32c_param(lin.weight)
+    assert torch.equal(b, lin.weight.float()) and not torch.equal(a, b)
+    for i in range(20):                                                      # same shape, freed and reallocated: never stale
+        w = (torch.full((2, 96), float(i), device="cuda")).to(torch.bfloat16)
+        assert float(ops._f32c_param(w)[0, 0]) == float(i)
+        del w
