@@ -57,9 +57,9 @@ template <> struct GpCfg<kGpModeAct, 1> {        // fc1: 256-column tiles, accum
   static constexpr int UN = 256, NSUB = 1, ACC = 2, STAGES = 4, BLOCKS = 4;      // BLOCKS: staging blocks of 16 KB
   static constexpr int PARTS = 4, MAXREG = 96;     // epilogue warps per TMEM lane quadrant; 2 + 16 warps -> 20 allocated -> 102 regs
 };
-template <> struct GpCfg<kGpModeAct192, 1> {     // Linear(D, D) + GELU of the predictors (N = 384): 192-column tiles, accumulator double-buffered
-  static constexpr int UN = 192, NSUB = 1, ACC = 2, STAGES = 4, BLOCKS = 3;
-  static constexpr int PARTS = 3, MAXREG = 128;
+template <> struct GpCfg<kGpModeAct192, 1> {     // qkv (N = 1152) and the predictors' Linear(D, D) + GELU (N = 384): 192-column tiles,
+  static constexpr int UN = 192, NSUB = 1, ACC = 2, STAGES = 6, BLOCKS = 3;      // accumulator double-buffered.  6 x 28 KB of ring =
+  static constexpr int PARTS = 3, MAXREG = 128;    // 96 KB of RESIDENT A rows + 6 x 12 KB of W ring when K <= 384 (p.ares)
 };
 template <> struct GpCfg<kGpModeLn, 2> {         // D = 384: two N = 192 MMAs per k-step, one accumulator
   static constexpr int UN = 192, NSUB = 2, ACC = 1, STAGES = 4, BLOCKS = 3;
@@ -71,7 +71,7 @@ template <> struct GpCfg<kGpModeLn, 1> {         // D = 192
 };
 
 struct GpBars {
-  uint64_t full[4], empty[4], tmem_full[2], tmem_empty[2];
+  uint64_t full[6], empty[6], tmem_full[2], tmem_empty[2], a_full[6], a_empty[6];
   uint32_t tmem_base;
   uint32_t pad;
 };
@@ -88,6 +88,8 @@ struct GpParams {
   int M, N, K, act, want_ln;
   long long* trace;             // D2S_GEMM_TRACE: device buffer for per-warp clock64 phase totals (profiling only)
   int dbg;                      // profiling switches (D2S_GEMM_DEBUG): 1 no output stores, 2 no epilogue body, 8 no operand loads
+  int ares;                     // MODE_ACT192, K <= 384: the row tile's A rows stay resident across its column tiles
+  int groups;                   // MODE_ACT*: a row tile's column tiles are split into `groups` work units (last-wave quantisation); 1 otherwise
 };
 
 template <int MODE, int NSUB_, int ACT>
@@ -118,9 +120,11 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
   const int pair_tiles = (p.M + 2 * kGpBM - 1) / (2 * kGpBM);
   const int n_tiles = p.N / TN, k_blocks = p.K / kGpBK;
+  const int G = MODE == kGpModeLn ? 1 : p.groups, npg = n_tiles / G, units = pair_tiles * G;   // work unit = (row tile, group of npg column tiles)
 
   if (tid == 0) {
     for (int i = 0; i < STAGES; ++i) { mbar_init(smem_u32(&bars->full[i]), 1); mbar_init(smem_u32(&bars->empty[i]), 1); }
+    for (int i = 0; i < 6; ++i) { mbar_init(smem_u32(&bars->a_full[i]), 1); mbar_init(smem_u32(&bars->a_empty[i]), 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&bars->tmem_full[i]), 1); mbar_init(smem_u32(&bars->tmem_empty[i]), 8 * PARTS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     if (MODE == kGpModeLn) { sel_s[0] = 0x1044u; sel_s[1] = 0x3244u; }   // {0, 0, b0, b1} and {0, 0, b2, b3}
@@ -150,9 +154,35 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     if (lane == 0) {
       // ======================================= TMA producer (both CTAs) =======================================
       uint32_t it = 0;
-      for (int pt = pair; pt < pair_tiles; pt += num_pairs) {
+      if (MODE == kGpModeAct192 && p.ares) {
+        // A resident: the row tile's k-blocks are loaded ONCE (each as soon as the previous tile's last column tile has read
+        // it) and every column tile streams only its W blocks: per row tile 96 + n_tiles x 72 KB through the SM's L2 port
+        // instead of n_tiles x 168 KB
+        unsigned char* wring = ring + 6 * kGpABytes;
+        uint32_t at = 0;
+        for (int un = pair; un < units; un += num_pairs, ++at) {
+          const int pt = un / G, nt0 = (un - pt * G) * npg;
+          const int row0 = pt * 2 * kGpBM + (int)rank * kGpBM;
+          for (int kb = 0; kb < k_blocks; ++kb) {
+            mbar_wait(smem_u32(&bars->a_empty[kb]), (at & 1) ^ 1);
+            const uint32_t af = smem_u32(&bars->a_full[kb]);
+            if (rank == 0) mbar_expect_tx(af, 2 * kGpABytes);
+            tma_load_2d_pair(smem_u32(ring + kb * kGpABytes), &map_a, kb * kGpBK, row0, mapa(af, 0));
+          }
+          for (int nt = nt0; nt < nt0 + npg; ++nt)
+            for (int kb = 0; kb < k_blocks; ++kb, ++it) {
+              const uint32_t s = it % STAGES, n = it / STAGES;
+              mbar_wait(smem_u32(&bars->empty[s]), (n & 1) ^ 1);
+              const uint32_t full_local = smem_u32(&bars->full[s]);
+              if (rank == 0) mbar_expect_tx(full_local, 2 * kBSub);
+              tma_load_2d_pair(smem_u32(wring + s * kBSub), &map_w, kb * kGpBK, nt * TN + (int)rank * (UN / 2), mapa(full_local, 0));
+            }
+        }
+      } else
+      for (int un = pair; un < units; un += num_pairs) {
+        const int pt = un / G, nt0 = (un - pt * G) * npg;
         const int row0 = pt * 2 * kGpBM + (int)rank * kGpBM;
-        for (int nt = 0; nt < n_tiles; ++nt)
+        for (int nt = nt0; nt < nt0 + npg; ++nt)
           for (int kb = 0; kb < k_blocks; ++kb, ++it) {
             const uint32_t s = it % STAGES, n = it / STAGES;
             mbar_wait(smem_u32(&bars->empty[s]), (n & 1) ^ 1);
@@ -173,27 +203,31 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       // ===== MMA issuer (leader): the whole warp runs the loop warp-uniformly, one elected lane issues (see elect_one) =====
       const uint32_t idesc = make_idesc(2 * kGpBM, UN, 0);
       uint32_t it = 0, tile = 0;
-      for (int pt = pair; pt < pair_tiles; pt += num_pairs)
-        for (int nt = 0; nt < n_tiles; ++nt, ++tile) {
+      for (int un = pair; un < units; un += num_pairs)
+        for (int nt = 0; nt < npg; ++nt, ++tile) {                       // (the issuer only needs the position inside the unit)
           const uint32_t as = tile % ACC, an = tile / ACC;
           mbar_wait(smem_u32(&bars->tmem_empty[as]), (an & 1) ^ 1);      // both epilogues have drained this accumulator
           tc_fence_after();
           const uint32_t d = tmem + as * kAccCols;
+          const bool ares = MODE == kGpModeAct192 && p.ares;
+          const uint32_t at = tile / (uint32_t)npg;                // work units done by this pair
           for (int kb = 0; kb < k_blocks; ++kb, ++it) {
             const uint32_t s = it % STAGES, n = it / STAGES;
+            if (ares && nt == 0) mbar_wait(smem_u32(&bars->a_full[kb]), at & 1);
             mbar_wait(smem_u32(&bars->full[s]), n & 1);
             tc_fence_after();
-            const uint64_t ad = make_desc_sw128(smem_u32(ring + s * kStage), 16, 1024);
+            const uint64_t ad = make_desc_sw128(smem_u32(ares ? ring + kb * kGpABytes : ring + s * kStage), 16, 1024);
             if (elect_one()) {
 #pragma unroll
               for (int j = 0; j < NSUB; ++j) {
-                const uint64_t bd = make_desc_sw128(smem_u32(ring + s * kStage + kGpABytes + j * kBSub), 16, 1024);
+                const uint64_t bd = make_desc_sw128(smem_u32(ares ? ring + 6 * kGpABytes + s * kBSub : ring + s * kStage + kGpABytes + j * kBSub), 16, 1024);
                 if (kb == 0) mma2_ss_imm<false>(d + j * UN, ad, bd, idesc); else mma2_ss_imm<true>(d + j * UN, ad, bd, idesc);
                 mma2_ss_imm<true>(d + j * UN, ad + 2, bd + 2, idesc);
                 mma2_ss_imm<true>(d + j * UN, ad + 4, bd + 4, idesc);
                 mma2_ss_imm<true>(d + j * UN, ad + 6, bd + 6, idesc);
               }
               mma2_commit_both(smem_u32(&bars->empty[s]));               // ring slot free in both CTAs once these retire
+              if (ares && nt == npg - 1) mma2_commit_both(smem_u32(&bars->a_empty[kb]));   // the unit's last reader of this A block
             }
             __syncwarp();
           }
@@ -216,9 +250,10 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       GP_TRACE_DECL(5)
       const bool issuer = (ew & 3) == 0 && lane == 0;
       unsigned char* blk = blocks + (size_t)part * kGpBlkBytes;
-      for (int pt = pair; pt < pair_tiles; pt += num_pairs) {
+      for (int un = pair; un < units; un += num_pairs) {
+        const int pt = un / G, nt0 = (un - pt * G) * npg;
         const int row0 = pt * 2 * kGpBM + (int)rank * kGpBM;
-        for (int nt = 0; nt < n_tiles; ++nt, ++tile) {
+        for (int nt = nt0; nt < nt0 + npg; ++nt, ++tile) {
           const uint32_t as = tile % ACC, an = tile / ACC;
           mbar_wait(smem_u32(&bars->tmem_full[as]), an & 1);
           tc_fence_after();
@@ -506,7 +541,8 @@ static int gp_launch(const CUtensorMap& ma, const CUtensorMap& mw, const CUtenso
   cudaError_t e = opt_in_smem(opt, gemm_pair_kernel<MODE, NSUB, ACT>, 227 * 1024);
   D2S_REQUIRE(e == cudaSuccess, D2S_ERR_CUDA, "%s: cudaFuncSetAttribute: %s", what, cudaGetErrorString(e));
   const int pair_tiles = (p.M + 2 * kGpBM - 1) / (2 * kGpBM);
-  const int pairs = pair_tiles < kNumSMs / 2 ? pair_tiles : kNumSMs / 2;
+  const int units = pair_tiles * (MODE == kGpModeLn ? 1 : p.groups);
+  const int pairs = units < kNumSMs / 2 ? units : kNumSMs / 2;
   e = launch_pdl(gemm_pair_kernel<MODE, NSUB, ACT>, dim3(2 * pairs), dim3((2 + 4 * Cfg::PARTS) * 32), smem, stream, ma, mw, mo, p);
   D2S_REQUIRE(e == cudaSuccess, D2S_ERR_CUDA, "%s: launch: %s", what, cudaGetErrorString(e));
   count_launch();
@@ -533,8 +569,22 @@ extern "C" int d2s_linear_act_pair_bf16(const void* a, const void* w, const void
   if ((rc = gp_map_2d(&ma, a, K, M, kGpBK, kGpBM, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, what))) return rc;
   if ((rc = gp_map_2d(&mw, w, K, N, kGpBK, t192 ? 96 : 128, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, what))) return rc;
   if ((rc = gp_map_2d(&mo, out, N, M, 64, kGpBM, CU_TENSOR_MAP_L2_PROMOTION_NONE, what))) return rc;
+  static const bool ares_on = []() { const char* e = getenv("D2S_GEMM_ARES"); return !(e && e[0] == '0'); }();
+  // Split a row tile's column tiles into G work units when that shortens the last wave: time per CTA pair ~
+  // ceil(row tiles * G / pairs) units of (column tiles per unit + 0.25) -- each unit (re)loads the A rows, partly exposed.
+  const int n_tiles = N / (t192 ? 192 : 256), pair_tiles = (M + 2 * kGpBM - 1) / (2 * kGpBM), np = kNumSMs / 2;
+  int groups = 1;
+  {
+    static const bool grp_on = []() { const char* e = getenv("D2S_GEMM_GROUPS"); return !(e && e[0] == '0'); }();
+    double best = (double)((pair_tiles + np - 1) / np) * (n_tiles + 0.25);
+    for (int g = 2; g <= n_tiles && grp_on; ++g) {
+      if (n_tiles % g) continue;
+      const double r = (double)((pair_tiles * g + np - 1) / np) * (n_tiles / g + 0.25);
+      if (r < best * 0.99) { best = r; groups = g; }
+    }
+  }
   GpParams p{(const __nv_bfloat16*)bias, nullptr, nullptr, nullptr, nullptr, nullptr, (__nv_bfloat16*)pre, 0.f, M, N, K, act, 0,
-             gp_trace(), gp_debug()};
+             gp_trace(), gp_debug(), (t192 && K <= 6 * kGpBK && ares_on) ? 1 : 0, groups};
   if (t192) {
     if (act == D2S_ACT_GELU) return gp_launch<kGpModeAct192, 1, D2S_ACT_GELU>(ma, mw, mo, p, (cudaStream_t)stream, what);
     if (act == D2S_ACT_RELU) return gp_launch<kGpModeAct192, 1, D2S_ACT_RELU>(ma, mw, mo, p, (cudaStream_t)stream, what);
@@ -562,7 +612,7 @@ extern "C" int d2s_linear_residual_ln_bf16(const void* a, const void* w, const v
   if ((rc = gp_map_2d(&ma, a, K, M, kGpBK, kGpBM, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, what))) return rc;
   if ((rc = gp_map_2d(&mw, w, K, N, kGpBK, 96, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, what))) return rc;
   GpParams p{(const __nv_bfloat16*)bias, (const __nv_bfloat16*)gamma, (const __nv_bfloat16*)beta, (const __nv_bfloat16*)x,
-             (__nv_bfloat16*)out_sum, (__nv_bfloat16*)out_norm, nullptr, eps, M, N, K, 0, out_norm ? 1 : 0, gp_trace(), gp_debug()};
+             (__nv_bfloat16*)out_sum, (__nv_bfloat16*)out_norm, nullptr, eps, M, N, K, 0, out_norm ? 1 : 0, gp_trace(), gp_debug(), 0, 1};
   if (N != 192) return gp_launch<kGpModeLn, 2, 0>(ma, mw, ma, p, (cudaStream_t)stream, what);      // 384, or 768 as two halves
   return gp_launch<kGpModeLn, 1, 0>(ma, mw, ma, p, (cudaStream_t)stream, what);
 }

@@ -26,6 +26,7 @@ _FROZEN_BF16 = os.environ.get("D2S_FROZEN_BF16", "1") != "0"   # A/B switch: cac
 _FUSED_ADD_LN_TRAIN = os.environ.get("D2S_FUSED_ADD_LN_TRAIN", "1") != "0"   # A/B switch: residual adds folded into LayerNorm fwd/bwd
 _FUSED_MLP = os.environ.get("D2S_FUSED_MLP", "1") != "0"      # A/B switch for the one-kernel MLP (ops.mlp_residual_ln)
 _FUSED_PAIR = os.environ.get("D2S_FUSED_PAIR", "1") != "0"  # A/B switch for the CTA-pair GEMMs (fc1 pair; proj/fc2 + add + LN)
+_QKV_PAIR = os.environ.get("D2S_QKV_PAIR", "1") != "0"     # A/B switch: inference qkv projection on the CTA-pair tcgen05 GEMM (else the library GEMM)
 _PRED_FUSED = os.environ.get("D2S_PRED_FUSED", "1") != "0"  # A/B switch: second half of the Variant A predictor + selection as one tcgen05 kernel (inference, D = 384)
 _POOL_TRAIN = os.environ.get("D2S_POOL_TRAIN", "1") != "0"  # A/B switch: the predictors' local/global split as one kernel each way
 _THRESHOLD_INFERENCE = os.environ.get("D2S_THRESHOLD_INFERENCE", "0") == "1"   # opt-in: what dynamic_vit.py:935-949 intends
@@ -106,7 +107,15 @@ def attention_pre_proj(m, x, policy=None, return_cls_attn=False):
     """Attention.forward up to (not including) the output projection (dynamic_vit.py:216-231): (o (B,T,C), cls_attn)."""
     B, T, C = x.shape
     H = m.num_heads
-    qkv = ops.linear_train(m.qkv, x)
+    lin = m.qkv
+    if (_QKV_PAIR and _FUSED_PAIR and x.is_cuda and x.dtype == torch.bfloat16 and lin.weight.dtype == torch.bfloat16
+            and not _needs_grad(x, lin.weight, lin.bias) and lin.in_features % 64 == 0 and lin.in_features <= 384
+            and lin.out_features % 192 == 0 and lin.out_features % 256 != 0):
+        # inference, D <= 384: the CTA-pair tcgen05 GEMM with 192-column tiles and the row tile's input rows resident in shared
+        # memory -- bit-identical to the library GEMM and as fast (both are bound by the 3 x (B,T,D) write stream)
+        qkv = ops.linear_act(x, lin.weight, lin.bias, ops.ACT_NONE)
+    else:
+        qkv = ops.linear_train(lin, x)
     if _needs_grad(qkv, policy) and qkv.is_cuda and qkv.dtype == torch.bfloat16 and T <= 256 and _TRAIN_ATTN:
         # training, bf16: the tcgen05 flash forward / backward pair on the packed tensor (T <= 208, hd 64), else per-head GEMMs
         # on a head-major copy around the padded-row policy softmax
