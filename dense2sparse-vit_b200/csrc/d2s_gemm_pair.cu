@@ -84,6 +84,7 @@ struct GpParams {
   __nv_bfloat16* out_sum;       // MODE_LN: x' (M,N)
   __nv_bfloat16* out_norm;      // MODE_LN: LayerNorm(x') (M,N) or NULL
   __nv_bfloat16* pre;           // MODE_ACT: the pre-activation A @ W^T + bias (M,N) as a second output, or NULL
+  float2* stats;                // MODE_LN: per-row (mean, rstd) of x' (M), or NULL -- lets the consumer apply the LayerNorm itself
   float eps;
   int M, N, K, act, want_ln;
   long long* trace;             // D2S_GEMM_TRACE: device buffer for per-warp clock64 phase totals (profiling only)
@@ -433,7 +434,9 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           const uint64_t sc = f2_bcast(rstd), sh = f2_bcast(-mean * rstd);
           const uint32_t sel_lo = sel_s[0], sel_hi = sel_s[1];
           asm volatile("bar.sync %0, %1;" ::"r"(1 + quad), "n"(32 * PARTS) : "memory");     // red_s may be rewritten by the next tile
+          if (p.stats != nullptr && part == 0 && row0 + lane < p.M) p.stats[row0 + lane] = make_float2(mean, rstd);
           GP_TRACE(4)
+          if (p.out_norm != nullptr) {
           // ---- pass 2: h = (x' - mean) * rstd * gamma + beta for the half in registers (the last one), then out like x' ----
           const int cb_last = (n_tiles - 1) * TN;
 #pragma unroll
@@ -488,6 +491,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 }
               }
             }
+          }
           }
           GP_TRACE(5)
         }
@@ -583,7 +587,7 @@ extern "C" int d2s_linear_act_pair_bf16(const void* a, const void* w, const void
       if (r < best * 0.99) { best = r; groups = g; }
     }
   }
-  GpParams p{(const __nv_bfloat16*)bias, nullptr, nullptr, nullptr, nullptr, nullptr, (__nv_bfloat16*)pre, 0.f, M, N, K, act, 0,
+  GpParams p{(const __nv_bfloat16*)bias, nullptr, nullptr, nullptr, nullptr, nullptr, (__nv_bfloat16*)pre, nullptr, 0.f, M, N, K, act, 0,
              gp_trace(), gp_debug(), (t192 && K <= 6 * kGpBK && ares_on) ? 1 : 0, groups};
   if (t192) {
     if (act == D2S_ACT_GELU) return gp_launch<kGpModeAct192, 1, D2S_ACT_GELU>(ma, mw, mo, p, (cudaStream_t)stream, what);
@@ -595,10 +599,9 @@ extern "C" int d2s_linear_act_pair_bf16(const void* a, const void* w, const void
   return gp_launch<kGpModeAct, 1, D2S_ACT_NONE>(ma, mw, mo, p, (cudaStream_t)stream, what);
 }
 
-extern "C" int d2s_linear_residual_ln_bf16(const void* a, const void* w, const void* bias, const void* x, const void* gamma,
-                                           const void* beta, float eps, int M, int N, int K, void* out_sum, void* out_norm,
-                                           d2s_stream_t stream) {
-  const char* what = "d2s_linear_residual_ln_bf16";
+static int gp_linear_residual(const char* what, const void* a, const void* w, const void* bias, const void* x, const void* gamma,
+                              const void* beta, float eps, int M, int N, int K, void* out_sum, void* out_norm, float* stats,
+                              d2s_stream_t stream) {
   D2S_REQUIRE(a && w && x && out_sum, D2S_ERR_ARG, "linear_residual_ln: null pointer");
   D2S_REQUIRE(M >= 0 && (N == 192 || N == 384 || N == 768) && K >= kGpBK && K % kGpBK == 0, D2S_ERR_ARG,
               "linear_residual_ln: need N in {192, 384, 768} (a CTA keeps whole rows: in TMEM, or in two 384-column halves) and "
@@ -612,7 +615,21 @@ extern "C" int d2s_linear_residual_ln_bf16(const void* a, const void* w, const v
   if ((rc = gp_map_2d(&ma, a, K, M, kGpBK, kGpBM, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, what))) return rc;
   if ((rc = gp_map_2d(&mw, w, K, N, kGpBK, 96, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, what))) return rc;
   GpParams p{(const __nv_bfloat16*)bias, (const __nv_bfloat16*)gamma, (const __nv_bfloat16*)beta, (const __nv_bfloat16*)x,
-             (__nv_bfloat16*)out_sum, (__nv_bfloat16*)out_norm, nullptr, eps, M, N, K, 0, out_norm ? 1 : 0, gp_trace(), gp_debug(), 0, 1};
+             (__nv_bfloat16*)out_sum, (__nv_bfloat16*)out_norm, nullptr, reinterpret_cast<float2*>(stats), eps, M, N, K, 0,
+             (out_norm || stats) ? 1 : 0, gp_trace(), gp_debug(), 0, 1};
   if (N != 192) return gp_launch<kGpModeLn, 2, 0>(ma, mw, ma, p, (cudaStream_t)stream, what);      // 384, or 768 as two halves
   return gp_launch<kGpModeLn, 1, 0>(ma, mw, ma, p, (cudaStream_t)stream, what);
+}
+
+extern "C" int d2s_linear_residual_ln_bf16(const void* a, const void* w, const void* bias, const void* x, const void* gamma,
+                                           const void* beta, float eps, int M, int N, int K, void* out_sum, void* out_norm,
+                                           d2s_stream_t stream) {
+  return gp_linear_residual("d2s_linear_residual_ln_bf16", a, w, bias, x, gamma, beta, eps, M, N, K, out_sum, out_norm, nullptr, stream);
+}
+
+extern "C" int d2s_linear_residual_stats_bf16(const void* a, const void* w, const void* bias, const void* x, float eps, int M, int N,
+                                              int K, void* out_sum, float* stats, d2s_stream_t stream) {
+  D2S_REQUIRE(stats != nullptr && (reinterpret_cast<uintptr_t>(stats) & 7u) == 0, D2S_ERR_ARG,
+              "linear_residual_stats: stats must be a non-null, 8-byte aligned (M,2) f32 buffer");
+  return gp_linear_residual("d2s_linear_residual_stats_bf16", a, w, bias, x, nullptr, nullptr, eps, M, N, K, out_sum, nullptr, stats, stream);
 }

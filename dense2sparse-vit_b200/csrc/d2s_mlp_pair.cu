@@ -64,6 +64,7 @@ constexpr uint32_t kMpAccCols = 384, kMpSCols = 128;
 struct MpBars {
   uint64_t a1_full[kMpKB], a1_empty[kMpKB], w1_full[kMpW1Slots], w1_empty[kMpW1Slots], w2_full[kMpW2Slots], w2_empty[kMpW2Slots];
   uint64_t s_full, s_empty, p_full, p_empty, acc_full, acc_empty;
+  uint64_t a1_ready[kMpKB];      // in_stats: the k-block of H has been normalised in place by both CTAs' E1 warps (leader's copy counts)
   uint32_t tmem_base, pad;
 };
 static_assert(sizeof(MpBars) % 8 == 0, "MpBars");
@@ -75,6 +76,10 @@ struct MpParams {
   float eps;
   int M, HID, want_ln;
   int T, ln_row0;               // LayerNorm output skips the first ln_row0 tokens of every T-token image (predictor norm over x[:, 1:])
+  // LayerNorm of the INPUT applied on the fly (the producer wrote x' and per-row (mean, rstd) instead of a normalised copy):
+  // map_a then covers x' itself, which is also the residual input x
+  const float2* in_stats;
+  const __nv_bfloat16 *in_gamma, *in_beta;
 };
 
 #if MP_E1W == 8
@@ -96,8 +101,9 @@ mlp_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   float* b1_s = reinterpret_cast<float*>(bars + 1);                       // HID
   float* b2_s = b1_s + p.HID;                                             // 384: b2
   uint32_t* gb_s = reinterpret_cast<uint32_t*>(b2_s + TN);                // 384: (gamma, beta) as bf16 pairs
+  uint32_t* gbin_s = gb_s + TN;                                           // 384: (gamma, beta) of the input LayerNorm (in_stats)
   unsigned char* out_s = reinterpret_cast<unsigned char*>(                  // 4 x 2 KB transposition buffers of the output warps
-      (reinterpret_cast<uintptr_t>(gb_s + TN) + 15) & ~(uintptr_t)15);
+      (reinterpret_cast<uintptr_t>(gbin_s + TN) + 15) & ~(uintptr_t)15);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t rank = cluster_ctarank();
@@ -107,7 +113,11 @@ mlp_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   const int nch = p.HID / kMpCH;
 
   if (tid == 0) {
-    for (int i = 0; i < kMpKB; ++i) { mbar_init(smem_u32(&bars->a1_full[i]), 1); mbar_init(smem_u32(&bars->a1_empty[i]), 1); }
+    for (int i = 0; i < kMpKB; ++i) {
+      mbar_init(smem_u32(&bars->a1_full[i]), 1);
+      mbar_init(smem_u32(&bars->a1_empty[i]), 1);
+      mbar_init(smem_u32(&bars->a1_ready[i]), 2 * kMpE1Warps);
+    }
     for (int i = 0; i < kMpW1Slots; ++i) { mbar_init(smem_u32(&bars->w1_full[i]), 1); mbar_init(smem_u32(&bars->w1_empty[i]), 1); }
     for (int i = 0; i < kMpW2Slots; ++i) { mbar_init(smem_u32(&bars->w2_full[i]), 1); mbar_init(smem_u32(&bars->w2_empty[i]), 1); }
     mbar_init(smem_u32(&bars->s_full), 1);
@@ -129,6 +139,7 @@ mlp_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     b2_s[i] = p.b2 ? __bfloat162float(p.b2[i]) : 0.f;
     const __nv_bfloat16 gm = p.gamma ? p.gamma[i] : __float2bfloat16_rn(1.f), bt = p.beta ? p.beta[i] : __float2bfloat16_rn(0.f);
     gb_s[i] = (uint32_t)__bfloat16_as_ushort(gm) | ((uint32_t)__bfloat16_as_ushort(bt) << 16);
+    if (p.in_stats) gbin_s[i] = (uint32_t)__bfloat16_as_ushort(p.in_gamma[i]) | ((uint32_t)__bfloat16_as_ushort(p.in_beta[i]) << 16);
   }
   tc_fence_before();
   __syncthreads();
@@ -161,8 +172,13 @@ mlp_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             if (j == 0) {   // the row tile's activations: resident for all chunks, refilled k-block by k-block
               mbar_wait(smem_u32(&bars->a1_empty[kb]), (tile_i & 1) ^ 1);
               const uint32_t fl = smem_u32(&bars->a1_full[kb]);
-              if (rank == 0) mbar_expect_tx(fl, 2 * kMpA1Blk);
-              tma_load_2d_pair(smem_u32(a1_s + kb * kMpA1Blk), &map_a, kb * 64, row0, mapa(fl, 0));
+              if (p.in_stats) {   // each CTA's own barrier: its E1 warps normalise the block before the pair's MMAs read it
+                mbar_expect_tx(fl, kMpA1Blk);
+                tma_load_2d(smem_u32(a1_s + kb * kMpA1Blk), &map_a, kb * 64, row0, fl);
+              } else {
+                if (rank == 0) mbar_expect_tx(fl, 2 * kMpA1Blk);
+                tma_load_2d_pair(smem_u32(a1_s + kb * kMpA1Blk), &map_a, kb * 64, row0, mapa(fl, 0));
+              }
             }
             const uint32_t s = w1_it % kMpW1Slots, n = w1_it / kMpW1Slots;
             mbar_wait(smem_u32(&bars->w1_empty[s]), (n & 1) ^ 1);
@@ -203,7 +219,7 @@ mlp_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
           MP_TRACE(1)
           const uint32_t d = tmem + kMpAccCols;
           for (int kb = 0; kb < kMpKB; ++kb, ++w1_it) {
-            if (j == 0) mbar_wait(smem_u32(&bars->a1_full[kb]), tile_i & 1);
+            if (j == 0) mbar_wait(smem_u32(p.in_stats ? &bars->a1_ready[kb] : &bars->a1_full[kb]), tile_i & 1);
             MP_TRACE(2)
             const uint32_t s = w1_it % kMpW1Slots, n = w1_it / kMpW1Slots;
             mbar_wait(smem_u32(&bars->w1_full[s]), n & 1);
@@ -282,10 +298,50 @@ mlp_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     unsigned char* blk = p_s + (part * kMpE1Cols / 64) * kMpPBlk;
     const int kc0 = (part * kMpE1Cols % 64) / 8;
     uint32_t c = 0;
-    for (int pt = pair; pt < pair_tiles; pt += num_pairs)
+    // in_stats: H arrives as the raw residual stream x'; this thread normalises its row's share of every k-block in place,
+    // h = bf16(((x - mean) * rstd) * gamma + beta) with the producer's statistics -- the arithmetic of the pair GEMM's own
+    // LayerNorm pass, so the A operand is bit-identical to the normalised copy that is no longer written.  Done for the NEXT row
+    // tile inside the last chunk of the current one (its H blocks land as soon as G1 of that chunk has retired), so that G1(0) of
+    // the next tile still runs under this tile's last GELU.
+    auto normalize_tile = [&](int pt_n, uint32_t ti) {
+      const int row = pt_n * 2 * kMpBM + (int)rank * kMpBM + r;
+      const float2 st = row < p.M ? p.in_stats[row] : make_float2(0.f, 0.f);
+      const uint64_t sc = f2_bcast(st.y), sh = f2_bcast(-st.x * st.y);
+      constexpr int kCh = 8 / kMpE1Parts;                     // 16-byte chunks of a k-block row per E1 warp
+#pragma unroll 1
+      for (int kb = 0; kb < kMpKB; ++kb) {
+        mbar_wait(smem_u32(&bars->a1_full[kb]), ti & 1);
+        unsigned char* hb = a1_s + kb * kMpA1Blk;
+#pragma unroll
+        for (int k = 0; k < kCh; ++k) {
+          const int ch = part * kCh + k;
+          uint4* ptr = reinterpret_cast<uint4*>(hb + sw128_off(r, ch));
+          const uint4 t = *ptr;
+          const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+          uint32_t o[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint2 gb = *reinterpret_cast<const uint2*>(&gbin_s[kb * 64 + ch * 8 + 2 * q]);
+            float h0, h1;
+            f2_unpack(f2_fma(f2_fma(f2_pack(bf16_lo(w[q]), bf16_hi(w[q])), sc, sh), f2_pack(bf16_lo(gb.x), bf16_lo(gb.y)),
+                             f2_pack(bf16_hi(gb.x), bf16_hi(gb.y))), h0, h1);
+            o[q] = pack_bf16x2(h0, h1);
+          }
+          *ptr = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(mapa(smem_u32(&bars->a1_ready[kb]), 0));
+      }
+    };
+    uint32_t tile_i = 0;
+    if (p.in_stats && pair < pair_tiles) normalize_tile(pair, 0);
+    for (int pt = pair; pt < pair_tiles; pt += num_pairs, ++tile_i)
       for (int j = 0; j < nch; ++j, ++c) {
         mbar_wait(smem_u32(&bars->s_full), c & 1);
         tc_fence_after();
+        // (before S_j is pulled into registers: G1(0) of the next tile needs the normalised blocks as much as the free S buffer)
+        if (p.in_stats && j == nch - 1 && pt + num_pairs < pair_tiles) normalize_tile(pt + num_pairs, tile_i + 1);
         // all columns first: S_j is then in registers and G1(j + 1) may overwrite it while the GELU below runs (with the
         // second half loaded after the first half's GELU, s_empty went out ~1 k cycles later and G1 waited for it)
         uint32_t va[32], vb[32];
@@ -498,10 +554,11 @@ static int mp_map_2d(CUtensorMap* map, const void* base, uint64_t inner, uint64_
 
 using namespace d2s;
 
-extern "C" int d2s_mlp_residual_ln_bf16(const void* h, const void* w1, const void* b1, const void* w2, const void* b2,
-                                        const void* x, const void* gamma, const void* beta, float eps, int M, int D, int HID,
-                                        int T, int norm_row0, void* out_sum, void* out_norm, d2s_stream_t stream) {
-  const char* what = "d2s_mlp_residual_ln_bf16";
+static_assert(kMpW1Slots >= kMpKB - 1, "in_stats: the H blocks of a tile are issued interleaved with the first chunk's W1 blocks");
+
+static int mp_launch(const char* what, const void* h, const float* in_stats, const void* in_gamma, const void* in_beta, const void* w1,
+                     const void* b1, const void* w2, const void* b2, const void* x, const void* gamma, const void* beta, float eps,
+                     int M, int D, int HID, int T, int norm_row0, void* out_sum, void* out_norm, d2s_stream_t stream) {
   D2S_REQUIRE(h && w1 && w2 && x && out_sum, D2S_ERR_ARG, "mlp_residual_ln: null pointer");
   D2S_REQUIRE(M >= 0 && D == kMpD && HID >= kMpCH && HID % kMpCH == 0 && HID <= 2048, D2S_ERR_ARG,
               "mlp_residual_ln: need D == %d and HID %% %d == 0, %d <= HID <= 2048 (got M=%d D=%d HID=%d)", kMpD, kMpCH, kMpCH, M,
@@ -519,9 +576,10 @@ extern "C" int d2s_mlp_residual_ln_bf16(const void* h, const void* w1, const voi
   if ((rc = mp_map_2d(&mw2, w2, HID, D, 64, 96, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, what))) return rc;
   const char* tr_env = getenv("D2S_GEMM_TRACE");
   MpParams p{tr_env ? reinterpret_cast<long long*>(strtoull(tr_env, nullptr, 10)) : nullptr, (const __nv_bfloat16*)b1, (const __nv_bfloat16*)b2, (const __nv_bfloat16*)gamma, (const __nv_bfloat16*)beta,
-             (const __nv_bfloat16*)x, (__nv_bfloat16*)out_sum, (__nv_bfloat16*)out_norm, eps, M, HID, out_norm ? 1 : 0, T, norm_row0};
+             (const __nv_bfloat16*)x, (__nv_bfloat16*)out_sum, (__nv_bfloat16*)out_norm, eps, M, HID, out_norm ? 1 : 0, T, norm_row0,
+             reinterpret_cast<const float2*>(in_stats), (const __nv_bfloat16*)in_gamma, (const __nv_bfloat16*)in_beta};
   const size_t smem = 1024 + (size_t)kMpKB * kMpA1Blk + 2 * (size_t)kMpPBlk + (size_t)kMpW1Slots * kMpW1Blk +
-                      (size_t)kMpW2Slots * kMpW2Blk + sizeof(MpBars) + (size_t)HID * 4 + 2 * kMpD * 4 + (size_t)kMpOutWarps * 2048 + 32;
+                      (size_t)kMpW2Slots * kMpW2Blk + sizeof(MpBars) + (size_t)HID * 4 + 3 * kMpD * 4 + (size_t)kMpOutWarps * 2048 + 32;
   D2S_REQUIRE(smem <= 227 * 1024, D2S_ERR_ARG, "mlp_residual_ln: needs %zu B of shared memory", smem);
   static SmemOptIn opt;
   cudaError_t e = opt_in_smem(opt, mlp_pair_kernel, 227 * 1024);
@@ -532,4 +590,21 @@ extern "C" int d2s_mlp_residual_ln_bf16(const void* h, const void* w1, const voi
   D2S_REQUIRE(e == cudaSuccess, D2S_ERR_CUDA, "mlp_residual_ln: launch: %s", cudaGetErrorString(e));
   count_launch();
   return check_launch(what);
+}
+
+extern "C" int d2s_mlp_residual_ln_bf16(const void* h, const void* w1, const void* b1, const void* w2, const void* b2,
+                                        const void* x, const void* gamma, const void* beta, float eps, int M, int D, int HID,
+                                        int T, int norm_row0, void* out_sum, void* out_norm, d2s_stream_t stream) {
+  return mp_launch("d2s_mlp_residual_ln_bf16", h, nullptr, nullptr, nullptr, w1, b1, w2, b2, x, gamma, beta, eps, M, D, HID, T, norm_row0,
+                   out_sum, out_norm, stream);
+}
+
+extern "C" int d2s_mlp_lnin_residual_ln_bf16(const void* x, const float* in_stats, const void* in_gamma, const void* in_beta,
+                                             const void* w1, const void* b1, const void* w2, const void* b2, const void* gamma,
+                                             const void* beta, float eps, int M, int D, int HID, int T, int norm_row0, void* out_sum,
+                                             void* out_norm, d2s_stream_t stream) {
+  D2S_REQUIRE(in_stats && in_gamma && in_beta && (reinterpret_cast<uintptr_t>(in_stats) & 7u) == 0, D2S_ERR_ARG,
+              "mlp_lnin_residual_ln: in_stats (M,2) f32 (8-byte aligned), in_gamma and in_beta are required");
+  return mp_launch("d2s_mlp_lnin_residual_ln_bf16", x, in_stats, in_gamma, in_beta, w1, b1, w2, b2, x, gamma, beta, eps, M, D, HID, T,
+                   norm_row0, out_sum, out_norm, stream);
 }

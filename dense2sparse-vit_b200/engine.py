@@ -26,6 +26,7 @@ _FROZEN_BF16 = os.environ.get("D2S_FROZEN_BF16", "1") != "0"   # A/B switch: cac
 _FUSED_ADD_LN_TRAIN = os.environ.get("D2S_FUSED_ADD_LN_TRAIN", "1") != "0"   # A/B switch: residual adds folded into LayerNorm fwd/bwd
 _FUSED_MLP = os.environ.get("D2S_FUSED_MLP", "1") != "0"      # A/B switch for the one-kernel MLP (ops.mlp_residual_ln)
 _FUSED_PAIR = os.environ.get("D2S_FUSED_PAIR", "1") != "0"  # A/B switch for the CTA-pair GEMMs (fc1 pair; proj/fc2 + add + LN)
+_LAZY_NORM2 = os.environ.get("D2S_LAZY_NORM2", "1") != "0"  # A/B switch: norm2 applied inside the one-kernel MLP from per-row statistics (no normalised copy)
 _QKV_PAIR = os.environ.get("D2S_QKV_PAIR", "1") != "0"     # A/B switch: inference qkv projection on the CTA-pair tcgen05 GEMM (else the library GEMM)
 _PRED_FUSED = os.environ.get("D2S_PRED_FUSED", "1") != "0"  # A/B switch: second half of the Variant A predictor + selection as one tcgen05 kernel (inference, D = 384)
 _POOL_TRAIN = os.environ.get("D2S_POOL_TRAIN", "1") != "0"  # A/B switch: the predictors' local/global split as one kernel each way
@@ -232,6 +233,29 @@ def block_forward(m, x, policy=None, return_cls_attn=False):
     return x + m.drop_path(m.mlp(norm_forward(m.norm2, x)))
 
 
+class _LazyNorm:
+    """norm(x) that has not been materialised: x is the summed residual stream, `stats` (M,2) f32 its per-row (mean, rstd) as the
+    kernel that produced x wrote them (ops.linear_residual_ln(want_stats=True)).  The one-kernel MLP applies the LayerNorm to
+    its input tile in shared memory (ops.mlp_residual_ln(in_stats=...)): the normalised copy -- a quarter of the proj + residual +
+    LayerNorm kernel's traffic -- is never written or read.  Any other consumer materialises what it needs."""
+
+    def __init__(self, x, stats, norm):
+        self.x, self.stats, self.norm = x, stats, norm
+        self.dtype, self.shape, self.is_cuda, self.requires_grad = x.dtype, x.shape, x.is_cuda, False
+
+    def value(self):
+        n = self.norm
+        return ops.add_layernorm(self.x, None, n.weight, n.bias, n.eps, want_sum=False)[1]
+
+    def cls_rows(self):
+        n = self.norm
+        return ops.add_layernorm(self.x[:, :1], None, n.weight, n.bias, n.eps, want_sum=False)[1]
+
+
+def _norm_value(h):
+    return h.value() if isinstance(h, _LazyNorm) else h
+
+
 class _Stream:
     """Residual stream of the model-level inference loops: x plus a pending branch (x + branch is the value the reference
     holds in `x`).  The branch is either a tensor y or a deferred Linear `lin = (a, module)` (attn.proj / mlp.fc2), so
@@ -279,7 +303,7 @@ class _Stream:
         self._flush_gather()
         if self.mlp is not None:                       # deferred whole MLP (h, module): its fc2 becomes the deferred Linear
             h, m = self.mlp
-            self.lin, self.mlp = (mlp_hidden(m, h), m.fc2), None
+            self.lin, self.mlp = (mlp_hidden(m, _norm_value(h)), m.fc2), None
         if self.lin is not None:
             a, lin = self.lin
             self.y, self.lin = lin(a), None
@@ -290,8 +314,10 @@ class _Stream:
             self.x, self.y = self.x + self.y, None
         return self.x
 
-    def _sum_norm(self, norm, row0=0):
-        """(x + branch, norm((x + branch)[:, row0:])); leaves the stream holding the summed x."""
+    def _sum_norm(self, norm, row0=0, lazy=False):
+        """(x + branch, norm((x + branch)[:, row0:])); leaves the stream holding the summed x.
+        lazy: the caller's only consumer of the norm is the one-kernel MLP; when the branch is a deferred Linear the second result
+        is then a _LazyNorm (statistics instead of the normalised tensor)."""
         if self._asm is not None and row0 == 0 and self.y is None and self.lin is None and self.mlp is None and self.gidx is None:
             (patches, cls, pos), self._asm = self._asm, None
             self._x, h = ops.assemble_layernorm(patches, cls, pos, norm.weight, norm.bias, norm.eps)
@@ -306,13 +332,21 @@ class _Stream:
             h, m = self.mlp
             if _mlp_fused_ok(m, h, self.x):
                 self.mlp = None
-                self.x, hn = ops.mlp_residual_ln(h, m.fc1.weight, m.fc1.bias, m.fc2.weight, m.fc2.bias, self.x,
-                                                 norm.weight, norm.bias, norm.eps, norm_row0=row0)
+                if isinstance(h, _LazyNorm) and h.x is self.x:      # norm2 applied inside the kernel, from its statistics
+                    self.x, hn = ops.mlp_residual_ln(None, m.fc1.weight, m.fc1.bias, m.fc2.weight, m.fc2.bias, self.x,
+                                                     norm.weight, norm.bias, norm.eps, norm_row0=row0, in_stats=h.stats,
+                                                     in_ln_weight=h.norm.weight, in_ln_bias=h.norm.bias)
+                else:
+                    self.x, hn = ops.mlp_residual_ln(_norm_value(h), m.fc1.weight, m.fc1.bias, m.fc2.weight, m.fc2.bias, self.x,
+                                                     norm.weight, norm.bias, norm.eps, norm_row0=row0)
                 return self.x, hn
             else:
-                self.lin, self.mlp = (mlp_hidden(m, h), m.fc2), None
+                self.lin, self.mlp = (mlp_hidden(m, _norm_value(h)), m.fc2), None
         if self.lin is not None and _pair_ok(self.lin[1], self.lin[0], self.x):
             (a, lin), self.lin = self.lin, None
+            if row0 == 0 and lazy:
+                self.x, st = ops.linear_residual_ln(a, lin.weight, lin.bias, self.x, eps=norm.eps, want_norm=False, want_stats=True)
+                return self.x, _LazyNorm(self.x, st, norm)
             if row0 == 0:
                 self.x, h = ops.linear_residual_ln(a, lin.weight, lin.bias, self.x, norm.weight, norm.bias, norm.eps)
                 return self.x, h
@@ -350,11 +384,14 @@ class _Stream:
             _, h = self._sum_norm(blk.norm1)
             o, cls_attn = attention_pre_proj(blk.attn, h, policy, return_cls_attn)
             self.lin = (o, blk.attn.proj)
-            _, h = self._sum_norm(blk.norm2)
+            # norm2 is only ever read by this block's MLP: when that MLP runs as the one kernel, hand it the statistics
+            lazy = (_LAZY_NORM2 and _mlp_is_plain(blk.mlp, o) and _mlp_fused_ok(blk.mlp, o, o) and o.shape[-1] == 384
+                    and _is_plain_ln(blk.norm2) and blk.norm2.weight.dtype == torch.bfloat16)
+            _, h = self._sum_norm(blk.norm2, lazy=lazy)
             if _mlp_is_plain(blk.mlp, h):
                 self.mlp = (h, blk.mlp)                  # deferred: fused with the residual add and the next LayerNorm
             else:
-                self.y = blk.mlp(h)
+                self.y = blk.mlp(_norm_value(h))
             return cls_attn
         if _train_fusable(blk, self.x, self.y):
             return self._block_train(blk, policy, return_cls_attn)
@@ -380,7 +417,8 @@ class _Stream:
                 and not _needs_grad(self.x, self.y, norm.weight)):
             if self.mlp is not None:                     # the last MLP is only needed for the CLS rows
                 h, m = self.mlp
-                y0 = m.fc2(mlp_hidden(m, h[:, :1].contiguous()))
+                h0 = h.cls_rows() if isinstance(h, _LazyNorm) else h[:, :1].contiguous()
+                y0 = m.fc2(mlp_hidden(m, h0))
             elif self.lin is not None:                   # the last fc2 is only needed for the CLS rows
                 a, lin = self.lin
                 y0 = lin(a[:, :1])

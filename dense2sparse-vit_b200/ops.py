@@ -1245,10 +1245,12 @@ def linear_act(x, weight, bias, act=ACT_GELU, want_pre=False):
     return (out, pre) if want_pre else out
 
 
-def linear_residual_ln(a, weight, bias, x, ln_weight=None, ln_bias=None, eps=1e-5, want_norm=True):
+def linear_residual_ln(a, weight, bias, x, ln_weight=None, ln_bias=None, eps=1e-5, want_norm=True, want_stats=False):
     """(x', h) with x' = x + (a @ weight^T + bias) and h = LayerNorm(x') * ln_weight + ln_bias (h None when
     want_norm is False): attn.proj / mlp.fc2 + residual add + the next LayerNorm of Block.forward
-    (vit_models/dynamic_vit.py:263-283) in one CTA-pair tcgen05 GEMM.  bf16, inference only; N in {192, 384, 768}."""
+    (vit_models/dynamic_vit.py:263-283) in one CTA-pair tcgen05 GEMM.  bf16, inference only; N in {192, 384, 768}.
+    want_stats (with want_norm=False): returns (x', stats) with stats (M,2) f32 = per-row (mean, rstd) of x' for `eps`: the
+    consumer (mlp_residual_ln(in_stats=...)) applies the LayerNorm itself and the normalised copy is never written."""
     _check_cuda(a, weight, bias, x, ln_weight, ln_bias)
     if a.dtype != torch.bfloat16 or x.dtype != torch.bfloat16:
         raise TypeError("linear_residual_ln is a bf16 kernel")
@@ -1266,18 +1268,31 @@ def linear_residual_ln(a, weight, bias, x, ln_weight=None, ln_bias=None, eps=1e-
         g = ln_weight.detach().to(torch.bfloat16).contiguous()
         bt = ln_bias.detach().to(torch.bfloat16).contiguous()
     out_sum = torch.empty_like(xc)
+    if want_stats:
+        if want_norm:
+            raise RuntimeError("linear_residual_ln: want_stats replaces the normalised output (want_norm=False)")
+        stats = torch.empty(M, 2, dtype=torch.float32, device=xc.device)
+        if M:
+            _call("d2s_linear_residual_stats_bf16", _ptr(ac), _ptr(w), _ptr(b), _ptr(xc), float(eps), M, N, K, _ptr(out_sum),
+                  _ptr(stats), _stream(ac))
+        return out_sum, stats
     out_norm = torch.empty_like(xc) if want_norm else None
     _call("d2s_linear_residual_ln_bf16", _ptr(ac), _ptr(w), _ptr(b), _ptr(xc), _ptr(g), _ptr(bt), float(eps), M, N, K,
               _ptr(out_sum), _ptr(out_norm), _stream(ac))
     return out_sum, out_norm
 
 
-def mlp_residual_ln(h, w1, b1, w2, b2, x, ln_weight=None, ln_bias=None, eps=1e-5, want_norm=True, norm_row0=0):
+def mlp_residual_ln(h, w1, b1, w2, b2, x, ln_weight=None, ln_bias=None, eps=1e-5, want_norm=True, norm_row0=0,
+                    in_stats=None, in_ln_weight=None, in_ln_bias=None):
     """(x', hn) with x' = x + fc2(GELU(fc1(h))) and hn = LayerNorm(x') * ln_weight + ln_bias (None when want_norm is False):
     the MLP branch of Block.forward with its residual add and the next LayerNorm (vit_models/dynamic_vit.py:159-175, :263-283)
     in ONE CTA-pair tcgen05 kernel; the hidden activations stay on chip.  bf16, inference only, D == 384.
-    norm_row0 > 0 (x of shape (B,T,D)): hn = LayerNorm(x'[:, norm_row0:]) of shape (B, T-norm_row0, D)."""
-    _check_cuda(h, w1, b1, w2, b2, x, ln_weight, ln_bias)
+    norm_row0 > 0 (x of shape (B,T,D)): hn = LayerNorm(x'[:, norm_row0:]) of shape (B, T-norm_row0, D).
+    in_stats (M,2) f32 with in_ln_weight / in_ln_bias: h is None and the MLP's input is LayerNorm(x) formed on the fly from the
+    per-row (mean, rstd) that linear_residual_ln(want_stats=True) wrote next to x."""
+    if in_stats is not None:
+        h = x
+    _check_cuda(h, w1, b1, w2, b2, x, ln_weight, ln_bias, in_stats, in_ln_weight, in_ln_bias)
     if h.dtype != torch.bfloat16 or x.dtype != torch.bfloat16:
         raise TypeError("mlp_residual_ln is a bf16 kernel")
     hc, xc = h.detach().contiguous(), x.detach().contiguous()
@@ -1298,6 +1313,14 @@ def mlp_residual_ln(h, w1, b1, w2, b2, x, ln_weight=None, ln_bias=None, eps=1e-5
     out_norm = None
     if want_norm:
         out_norm = torch.empty(xc.shape[0], T - norm_row0, D, dtype=xc.dtype, device=xc.device) if norm_row0 else torch.empty_like(xc)
+    if in_stats is not None:
+        st = in_stats.detach().contiguous()
+        if st.dtype != torch.float32 or st.numel() != 2 * M:
+            raise RuntimeError(f"mlp_residual_ln: in_stats must be ({M}, 2) float32")
+        _call("d2s_mlp_lnin_residual_ln_bf16", _ptr(xc), _ptr(st), _ptr(bf(in_ln_weight)), _ptr(bf(in_ln_bias)), _ptr(w1c),
+              _ptr(bf(b1)), _ptr(w2c), _ptr(bf(b2)), _ptr(g), _ptr(bt), float(eps), M, D, HID, T, int(norm_row0), _ptr(out_sum),
+              _ptr(out_norm), _stream(xc))
+        return out_sum, out_norm
     _call("d2s_mlp_residual_ln_bf16", _ptr(hc), _ptr(w1c), _ptr(bf(b1)), _ptr(w2c), _ptr(bf(b2)), _ptr(xc), _ptr(g), _ptr(bt),
               float(eps), M, D, HID, T, int(norm_row0), _ptr(out_sum), _ptr(out_norm), _stream(hc))
     return out_sum, out_norm

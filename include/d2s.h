@@ -305,6 +305,11 @@ int d2s_linear_act_pair_bf16(const void* a, const void* w, const void* bias, int
 int d2s_linear_residual_ln_bf16(const void* a, const void* w, const void* bias, const void* x, const void* gamma,
                                 const void* beta, float eps, int M, int N, int K, void* out_sum, void* out_norm,
                                 d2s_stream_t stream);
+/* The same without the normalised output: out_sum = x + bf16(a @ w^T + bias) and stats (M,2) f32 = per-row (mean, rstd) of out_sum
+ * (rstd = rsqrt(var + eps)); the consumer (d2s_mlp_lnin_residual_ln_bf16) applies the LayerNorm itself, which saves writing and
+ * re-reading the (M,N) normalised copy. */
+int d2s_linear_residual_stats_bf16(const void* a, const void* w, const void* bias, const void* x, float eps, int M, int N, int K,
+                                   void* out_sum, float* stats, d2s_stream_t stream);
 
 /* The whole MLP branch of Block.forward in one kernel (dynamic_vit.py:159-175, :263-283), bf16, D == 384:
  *   u = GELU(h (M,D) @ w1 (HID,D)^T + b1);  out_sum (M,D) = bf16(x + bf16(u @ w2 (D,HID)^T + b2));
@@ -317,6 +322,13 @@ int d2s_linear_residual_ln_bf16(const void* a, const void* w, const void* bias, 
 int d2s_mlp_residual_ln_bf16(const void* h, const void* w1, const void* b1, const void* w2, const void* b2, const void* x,
                              const void* gamma, const void* beta, float eps, int M, int D, int HID, int T, int norm_row0,
                              void* out_sum, void* out_norm, d2s_stream_t stream);
+/* The same with the LayerNorm of the MLP's INPUT applied on the fly (Block.forward's norm2, dynamic_vit.py:281): x (M,D) is the
+ * residual stream itself, in_stats (M,2) f32 its per-row (mean, rstd) as written by d2s_linear_residual_stats_bf16, in_gamma /
+ * in_beta (D) bf16 that LayerNorm's affine; h = bf16((x - mean) * rstd * gamma + beta) is formed in shared memory (the arithmetic of
+ * d2s_linear_residual_ln_bf16's own LayerNorm pass: bit-identical A operand) and never written to HBM.  x is also the residual input. */
+int d2s_mlp_lnin_residual_ln_bf16(const void* x, const float* in_stats, const void* in_gamma, const void* in_beta, const void* w1,
+                                  const void* b1, const void* w2, const void* b2, const void* gamma, const void* beta, float eps,
+                                  int M, int D, int HID, int T, int norm_row0, void* out_sum, void* out_norm, d2s_stream_t stream);
 
 /* LayerNorm forward / backward for the training path (norm1 / norm2 / predictor norms of Block.forward,
  * dynamic_vit.py:263-283) with mixed dtypes for bf16 autocast: x (rows,D) f32|bf16 -> h (rows,D) f32|bf16,

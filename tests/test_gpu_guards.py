@@ -107,9 +107,21 @@ def test_gemm_family_stays_in_bounds(d2s, M):
                  f_sum.ptr, f_norm.ptr, _stream())
         act, pre = Guarded((M, HID), torch.bfloat16), Guarded((M, HID), torch.bfloat16)
         lib.call("d2s_linear_act_pair_bf16", h.ptr, w1.data_ptr(), b1.data_ptr(), M, HID, D, 1, act.ptr, pre.ptr, _stream())
+        # 192-column tiles with resident input rows (qkv: N = 1152; the predictors' Linear + GELU: N = 384)
+        wq, bq = rn(3 * D, D, k=0.05), rn(3 * D, k=0.1)
+        qkv, g384 = Guarded((M, 3 * D), torch.bfloat16), Guarded((M, D), torch.bfloat16)
+        lib.call("d2s_linear_act_pair_bf16", h.ptr, wq.data_ptr(), bq.data_ptr(), M, 3 * D, D, 0, qkv.ptr, None, _stream())
+        lib.call("d2s_linear_act_pair_bf16", h.ptr, wp.data_ptr(), b2.data_ptr(), M, D, D, 1, g384.ptr, None, _stream())
+        # statistics instead of the normalised copy, and the MLP kernel that applies the LayerNorm to its input tile itself
+        s_sum, s_st = Guarded((M, D), torch.bfloat16), Guarded((M, 2), torch.float32)
+        lib.call("d2s_linear_residual_stats_bf16", h.ptr, wp.data_ptr(), b2.data_ptr(), x.ptr, 1e-6, M, D, D, s_sum.ptr, s_st.ptr, _stream())
+        l_sum, l_norm = Guarded((M, D), torch.bfloat16), Guarded((M, D), torch.bfloat16)
+        lib.call("d2s_mlp_lnin_residual_ln_bf16", s_sum.ptr, s_st.ptr, gam.data_ptr(), bet.data_ptr(), w1.data_ptr(), b1.data_ptr(),
+                 w2.data_ptr(), b2.data_ptr(), gam.data_ptr(), bet.data_ptr(), 1e-6, M, D, HID, 1, 0, l_sum.ptr, l_norm.ptr, _stream())
         torch.cuda.synchronize()
         for name, gd in (("mlp sum", o_sum), ("mlp norm", o_norm), ("proj sum", p_sum), ("proj norm", p_norm), ("fc2 sum", f_sum),
-                         ("fc2 norm", f_norm), ("act", act), ("pre", pre), ("h", h), ("x", x), ("a4", a4)):
+                         ("fc2 norm", f_norm), ("act", act), ("pre", pre), ("qkv", qkv), ("linear + gelu 384", g384), ("stats sum", s_sum),
+                         ("stats", s_st), ("lnin sum", l_sum), ("lnin norm", l_norm), ("h", h), ("x", x), ("a4", a4)):
             assert gd.ok(), f"{name}: guard zone overwritten"
             if gd not in (h, x, a4):
                 assert bool(torch.isfinite(gd.t.float()).all()), f"{name}: element left unwritten or fed by an out-of-bounds read"

@@ -1206,3 +1206,46 @@ def test_cached_fp32_parameter_copies_follow_the_parameter(ops):
         w = (torch.full((2, 96), float(i), device="cuda")).to(torch.bfloat16)
         assert float(ops._f32c_param(w)[0, 0]) == float(i)
         del w
+
+
+@pytest.mark.parametrize("B,T,row0", [(3, 197, 0), (2, 138, 1), (7, 97, 0), (1, 1, 0), (5, 68, 0), (40, 197, 1), (300, 97, 0)])
+def test_mlp_kernel_applies_its_input_layernorm_from_row_statistics(ops, B, T, row0):
+    """proj + residual with per-row (mean, rstd) instead of the normalised copy (d2s_linear_residual_stats_bf16) followed by the
+    one-kernel MLP that normalises its input tile in shared memory (d2s_mlp_lnin_residual_ln_bf16): BIT-identical to the pair that
+    materialises LayerNorm(x') in between (same arithmetic, same roundings), statistics equal to the fp32 row statistics of x'."""
+    D, HID = 384, 1536
+    bf = torch.bfloat16
+    r = lambda seed, *s, sc=1.0: cu(fx.randn(seed, *s) * sc).to(bf)
+    Wp, bp = r(1, D, D, sc=D ** -0.5), r(2, D, sc=0.1)
+    W1, b1, W2, b2 = r(3, HID, D, sc=D ** -0.5), r(4, HID, sc=0.1), r(5, D, HID, sc=HID ** -0.5), r(6, D, sc=0.1)
+    g2, bt2 = (1 + 0.2 * cu(fx.randn(7, D))).to(bf), r(8, D, sc=0.2)
+    g1, bt1 = (1 + 0.2 * cu(fx.randn(9, D))).to(bf), r(10, D, sc=0.2)
+    a, x = r(11 + T, B, T, D), r(12 + T, B, T, D, sc=2.0)
+    x = x + 3.0 * (torch.arange(D, device="cuda") % 7 == 0).to(bf)            # a few channels with a large mean
+    xs0, hn = ops.linear_residual_ln(a, Wp, bp, x, g2, bt2, 1e-6)
+    ref = ops.mlp_residual_ln(hn, W1, b1, W2, b2, xs0, g1, bt1, 1e-6, norm_row0=row0)
+    xs1, st = ops.linear_residual_ln(a, Wp, bp, x, eps=1e-6, want_norm=False, want_stats=True)
+    assert torch.equal(xs1, xs0) and st.shape == (B * T, 2)
+    xf = xs1.float().reshape(B * T, D)
+    torch.testing.assert_close(st[:, 0], xf.mean(-1), rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(st[:, 1], torch.rsqrt(xf.var(-1, unbiased=False) + 1e-6), rtol=1e-3, atol=1e-4)
+    out = ops.mlp_residual_ln(None, W1, b1, W2, b2, xs1, g1, bt1, 1e-6, norm_row0=row0, in_stats=st, in_ln_weight=g2, in_ln_bias=bt2)
+    assert torch.equal(out[0], ref[0]) and torch.equal(out[1], ref[1])
+
+
+def test_lazy_norm2_is_invisible_at_model_level(d2s, monkeypatch):
+    """engine: norm2 handed to the one-kernel MLP as statistics (D2S_LAZY_NORM2) against the same forward with the normalised
+    copy: identical logits and kept sets (the kernels are bit-identical; the CLS-only last MLP normalises its rows itself)."""
+    torch.manual_seed(3)
+    m = d2s.variant_a.DefaultVisionTransformerDiffPruning(patch_size=16, embed_dim=384, depth=6, num_heads=6, num_classes=32, mlp_ratio=4,
+                                                          qkv_bias=True, pruning_loc=[2, 4], token_ratio=[0.7, 0.49], distill=True)
+    m = m.cuda().eval().to(torch.bfloat16)
+    img = cu(fx.randn(55, 5, 3, 224, 224)).bfloat16()
+    with torch.no_grad():
+        monkeypatch.setattr(d2s.engine, "_LAZY_NORM2", True)
+        a = m(img)
+        ka = [k.clone() for k in m.kept_token_indices]
+        monkeypatch.setattr(d2s.engine, "_LAZY_NORM2", False)
+        b = m(img)
+        kb = m.kept_token_indices
+    assert torch.equal(a, b) and all(torch.equal(p, q) for p, q in zip(ka, kb))
