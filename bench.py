@@ -321,22 +321,34 @@ def kernel_breakdown(ops, B, dev, torch, pk):
         acc("attn", ms, by_attn, fl, 3)
         del qkvs
         xs = [(torch.randn(B, T, D, device=dev, dtype=bf), torch.randn(B, T, D, device=dev, dtype=bf)) for _ in range(2)]
-        by, fl = B * T * e * 4 * D, 2.0 * B * T * D * D
-        ms = time_graphed([lambda x=x, y=y: ops.linear_residual_ln(y, wp, gb, x, gw, gb, 1e-6) for x, y in xs], torch, launches=12)
-        rows.append(row("linear_residual_ln(proj+add+LN, tcgen05 pair)", f"M={B * T},N={D},K={D}", ms, by, 3, fl))
+        # qkv projection on the CTA-pair GEMM (192-column tiles, input rows resident): write-bound, 3 of its 4 (B,T,D) units are stores
+        wq, bq = torch.randn(3 * D, D, device=dev, dtype=bf) * 0.05, torch.zeros(3 * D, device=dev, dtype=bf)
+        by, fl = B * T * e * 4 * D, 2.0 * B * T * D * 3 * D
+        ms = time_graphed([lambda x=x: ops.linear_act(x, wq, bq, ops.ACT_NONE) for x, _ in xs], torch, launches=12)
+        rows.append(row("linear_act(qkv projection, tcgen05 pair, 192-column tiles)", f"M={B * T},N={3 * D},K={D}", ms, by, 3, fl))
+        # attn.proj + residual; norm2 is NOT materialised: the kernel writes x' and per-row (mean, rstd), the MLP kernel applies the norm
+        by, fl = B * T * (e * 3 * D + 8), 2.0 * B * T * D * D
+        ms = time_graphed([lambda x=x, y=y: ops.linear_residual_ln(y, wp, gb, x, eps=1e-6, want_norm=False, want_stats=True) for x, y in xs],
+                          torch, launches=12)
+        rows.append(row("linear_residual_ln(proj+add+row statistics, tcgen05 pair)", f"M={B * T},N={D},K={D}", ms, by, 3, fl))
         acc("pair", ms, by, fl, 3)
-        # the MLP branch in one kernel (fc1 + GELU + fc2 + residual + next LayerNorm): the step's dominant kernel, tensor-bound
-        # (4.7 MFLOP per token against 3 KB of HBM traffic)
-        by, fl = B * T * e * 4 * D, 4.0 * B * T * D * 4 * D
-        ms = time_graphed([lambda x=x, y=y: ops.mlp_residual_ln(x, w1, b1, w2, gb, y, gw, gb, 1e-6) for x, y in xs], torch, launches=8)
-        rows.append(row("mlp_residual_ln(fc1+GELU+fc2+add+LN, tcgen05 pair)", f"M={B * T},D={D},HID={4 * D}", ms, by, 2, fl))
+        # the MLP branch in one kernel (norm2 on its input tile + fc1 + GELU + fc2 + residual + next LayerNorm): the step's dominant
+        # kernel, tensor-bound (4.7 MFLOP per token against 2.3 KB of HBM traffic: x' in (also the residual), x'' and hn out)
+        sts = [torch.stack([x.float().mean(-1), torch.rsqrt(x.float().var(-1, unbiased=False) + 1e-6)], -1).reshape(-1, 2).contiguous()
+               for x, _ in xs]
+        by, fl = B * T * (e * 3 * D + 8), 4.0 * B * T * D * 4 * D
+        ms = time_graphed([lambda x=x, st=st: ops.mlp_residual_ln(None, w1, b1, w2, gb, x, gw, gb, 1e-6, in_stats=st, in_ln_weight=gw,
+                                                                  in_ln_bias=gb) for (x, _), st in zip(xs, sts)], torch, launches=8)
+        rows.append(row("mlp_residual_ln(norm2+fc1+GELU+fc2+add+LN, tcgen05 pair)", f"M={B * T},D={D},HID={4 * D}", ms, by, 2, fl))
         acc("mlp", ms, by, fl, 2)
         if gi < 3:   # the block in front of a pruning stage: the LayerNorm is the predictor's, over x[:, 1:]
-            ms = time_graphed([lambda x=x, y=y: ops.mlp_residual_ln(x, w1, b1, w2, gb, y, gw, gb, 1e-6, norm_row0=1) for x, y in xs],
+            ms = time_graphed([lambda x=x, st=st: ops.mlp_residual_ln(None, w1, b1, w2, gb, x, gw, gb, 1e-6, norm_row0=1, in_stats=st,
+                                                                      in_ln_weight=gw, in_ln_bias=gb) for (x, _), st in zip(xs, sts)],
                               torch, launches=8)
-            by = B * e * D * (3 * T + T - 1)
+            by = B * (e * D * (2 * T + T - 1) + 8 * T)
             rows.append(row("mlp_residual_ln(... LN over x[:,1:])", f"M={B * T},D={D},HID={4 * D}", ms, by, 1, fl))
             acc("mlp", ms, by, fl, 1)
+        del sts
         if gi == 0:  # the first block's norm1: token assembly fused with the LayerNorm
             pos, cls = torch.randn(1, T, D, device=dev, dtype=bf), torch.randn(1, 1, D, device=dev, dtype=bf)
             ps = [torch.randn(B, T - 1, D, device=dev, dtype=bf) for _ in range(2)]
@@ -389,14 +401,14 @@ def kernel_breakdown(ops, B, dev, torch, pk):
     except (OSError, KeyError, ValueError):
         pass
     m, p, a = agg["mlp"], agg["pair"], agg["attn"]
-    roof = {"kernel": f"mlp_pair_kernel (fc1 + GELU + fc2 + residual + LayerNorm, {m['n']} launches/step, T=197/138/97/68)",
+    roof = {"kernel": f"mlp_pair_kernel (norm2 + fc1 + GELU + fc2 + residual + LayerNorm, {m['n']} launches/step, T=197/138/97/68)",
             "bound": "tensor", "achieved": m["fl"] / m["ms"] / 1e9, "peak": pk["tf_burst"], "unit": "TFLOP/s",
             "frac": m["fl"] / m["ms"] / 1e9 / pk["tf_burst"], "traffic": traffic, "peak_source": pk["source"],
             "flops_per_launch": m["fl"] / m["n"], "algo_bytes_per_launch": m["by"] / m["n"], "ms_per_launch": m["ms"] / m["n"],
             "ms_per_step_in_kernel": m["ms"],
             "frac_of_sustained_peak": m["fl"] / m["ms"] / 1e9 / pk["tf_sustained"],
             "hbm": {"achieved": m["by"] / m["ms"] / 1e6, "peak": pk["hbm"], "unit": "GB/s", "frac": m["by"] / m["ms"] / 1e6 / pk["hbm"]},
-            "proj_ln": {"kernel": f"gemm_pair_kernel<LN> (proj + residual + LayerNorm, {p['n']} launches/step)", "bound": "hbm",
+            "proj_ln": {"kernel": f"gemm_pair_kernel<LN> (proj + residual + row statistics, {p['n']} launches/step)", "bound": "hbm",
                         "achieved": p["by"] / p["ms"] / 1e6, "frac": p["by"] / p["ms"] / 1e6 / pk["hbm"],
                         "ms_per_step_in_kernel": p["ms"]},
             "attention": {"kernel": f"attn_tc_fwd_kernel ({a['n']} launches/step)", "bound": "hbm",
