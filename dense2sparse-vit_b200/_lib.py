@@ -64,12 +64,13 @@ SIGNATURES = {
     "d2s_add_layernorm_fwd": [_p, _p, _i, _p, _p, ctypes.c_longlong, _i, _f, _p, _p, _i, _p, _p],
     "d2s_add_layernorm_bwd": [_p, _i, _p, _i, _p, _p, _p, ctypes.c_longlong, _i, _p, _p, _p, _p],
     "d2s_linear_act_pair_bf16": [_p, _p, _p, _i, _i, _i, _i, _p, _p, _p],
+    "d2s_linear_lnin_act_pair_bf16": [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p],
     "d2s_linear_residual_ln_bf16": [_p, _p, _p, _p, _p, _p, _f, _i, _i, _i, _p, _p, _p],
     "d2s_linear_residual_stats_bf16": [_p, _p, _p, _p, _f, _i, _i, _i, _p, _p, _p],
     "d2s_gather_layernorm": [_p, _p, _p, _p, _i, _i, _i, _i, _i, _f, _p, _p, _p],
     "d2s_assemble_layernorm": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _f, _p, _p, _p],
     "d2s_mlp_residual_ln_bf16": [_p, _p, _p, _p, _p, _p, _p, _p, _f, _i, _i, _i, _i, _i, _p, _p, _p],
-    "d2s_mlp_lnin_residual_ln_bf16": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _f, _i, _i, _i, _i, _i, _p, _p, _p],
+    "d2s_mlp_lnin_residual_ln_bf16": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _f, _i, _i, _i, _i, _i, _p, _p, _p, _p],
     "d2s_add_layernorm": [_p, _p, _p, _p, _i, _i, _i, _i, ctypes.c_longlong, ctypes.c_longlong, _f, _i, _p, _p, _p],
 }
 INFO_SYMBOLS = ["d2s_last_error", "d2s_version", "d2s_launch_count"]

@@ -71,7 +71,7 @@ template <> struct GpCfg<kGpModeLn, 1> {         // D = 192
 };
 
 struct GpBars {
-  uint64_t full[6], empty[6], tmem_full[2], tmem_empty[2], a_full[6], a_empty[6];
+  uint64_t full[6], empty[6], tmem_full[2], tmem_empty[2], a_full[6], a_empty[6], a_ready[6];
   uint32_t tmem_base;
   uint32_t pad;
 };
@@ -91,6 +91,9 @@ struct GpParams {
   int dbg;                      // profiling switches (D2S_GEMM_DEBUG): 1 no output stores, 2 no epilogue body, 8 no operand loads
   int ares;                     // MODE_ACT192, K <= 384: the row tile's A rows stay resident across its column tiles
   int groups;                   // MODE_ACT*: a row tile's column tiles are split into `groups` work units (last-wave quantisation); 1 otherwise
+  // MODE_ACT192 + ares: LayerNorm of the INPUT rows applied on the fly (A is the raw residual stream, in_stats its per-row (mean, rstd))
+  const float2* in_stats;
+  const __nv_bfloat16 *in_gamma, *in_beta;
 };
 
 template <int MODE, int NSUB_, int ACT>
@@ -115,6 +118,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   float* bias_s = reinterpret_cast<float*>(bars + 1);           // N floats (MODE_ACT) / 3 x N floats (MODE_LN)
   float2* red_s = reinterpret_cast<float2*>(bias_s + (MODE == kGpModeLn ? 3 * p.N : p.N));   // MODE_LN: [PARTS][128] partial stats
   volatile uint32_t* sel_s = reinterpret_cast<volatile uint32_t*>(red_s + 4 * 128);           // MODE_LN: byte-permute selectors
+  uint32_t* gbin_s = reinterpret_cast<uint32_t*>(bias_s + p.N);                               // MODE_ACT192, in_stats: K x (gamma, beta) as bf16 pairs
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t rank = cluster_ctarank();
@@ -125,7 +129,11 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 
   if (tid == 0) {
     for (int i = 0; i < STAGES; ++i) { mbar_init(smem_u32(&bars->full[i]), 1); mbar_init(smem_u32(&bars->empty[i]), 1); }
-    for (int i = 0; i < 6; ++i) { mbar_init(smem_u32(&bars->a_full[i]), 1); mbar_init(smem_u32(&bars->a_empty[i]), 1); }
+    for (int i = 0; i < 6; ++i) {
+      mbar_init(smem_u32(&bars->a_full[i]), 1);
+      mbar_init(smem_u32(&bars->a_empty[i]), 1);
+      mbar_init(smem_u32(&bars->a_ready[i]), 2 * 4 * PARTS);      // in_stats: every epilogue warp of both CTAs has normalised its share
+    }
     for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&bars->tmem_full[i]), 1); mbar_init(smem_u32(&bars->tmem_empty[i]), 8 * PARTS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     if (MODE == kGpModeLn) { sel_s[0] = 0x1044u; sel_s[1] = 0x3244u; }   // {0, 0, b0, b1} and {0, 0, b2, b3}
@@ -144,6 +152,9 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     }
   } else {
     for (int i = tid; i < p.N; i += kThreads) bias_s[i] = p.bias ? __bfloat162float(p.bias[i]) : 0.f;
+    if (MODE == kGpModeAct192 && p.in_stats)
+      for (int i = tid; i < p.K; i += kThreads)
+        gbin_s[i] = (uint32_t)__bfloat16_as_ushort(p.in_gamma[i]) | ((uint32_t)__bfloat16_as_ushort(p.in_beta[i]) << 16);
   }
   tc_fence_before();
   __syncthreads();
@@ -167,8 +178,13 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           for (int kb = 0; kb < k_blocks; ++kb) {
             mbar_wait(smem_u32(&bars->a_empty[kb]), (at & 1) ^ 1);
             const uint32_t af = smem_u32(&bars->a_full[kb]);
-            if (rank == 0) mbar_expect_tx(af, 2 * kGpABytes);
-            tma_load_2d_pair(smem_u32(ring + kb * kGpABytes), &map_a, kb * kGpBK, row0, mapa(af, 0));
+            if (p.in_stats) {     // each CTA's own barrier: its epilogue warps normalise the block before the pair's MMAs read it
+              mbar_expect_tx(af, kGpABytes);
+              tma_load_2d(smem_u32(ring + kb * kGpABytes), &map_a, kb * kGpBK, row0, af);
+            } else {
+              if (rank == 0) mbar_expect_tx(af, 2 * kGpABytes);
+              tma_load_2d_pair(smem_u32(ring + kb * kGpABytes), &map_a, kb * kGpBK, row0, mapa(af, 0));
+            }
           }
           for (int nt = nt0; nt < nt0 + npg; ++nt)
             for (int kb = 0; kb < k_blocks; ++kb, ++it) {
@@ -214,7 +230,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           const uint32_t at = tile / (uint32_t)npg;                // work units done by this pair
           for (int kb = 0; kb < k_blocks; ++kb, ++it) {
             const uint32_t s = it % STAGES, n = it / STAGES;
-            if (ares && nt == 0) mbar_wait(smem_u32(&bars->a_full[kb]), at & 1);
+            if (ares && nt == 0) mbar_wait(smem_u32(p.in_stats ? &bars->a_ready[kb] : &bars->a_full[kb]), at & 1);
             mbar_wait(smem_u32(&bars->full[s]), n & 1);
             tc_fence_after();
             const uint64_t ad = make_desc_sw128(smem_u32(ares ? ring + kb * kGpABytes : ring + s * kStage), 16, 1024);
@@ -251,10 +267,47 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       GP_TRACE_DECL(5)
       const bool issuer = (ew & 3) == 0 && lane == 0;
       unsigned char* blk = blocks + (size_t)part * kGpBlkBytes;
-      for (int un = pair; un < units; un += num_pairs) {
+      // in_stats (A resident): the unit's input rows arrive as the raw residual stream; this thread normalises its row's share of
+      // every k-block in place, h = bf16(((x - mean) * rstd) * gamma + beta) -- the arithmetic of the LayerNorm pass of MODE_LN, so
+      // the operand is bit-identical to the normalised copy the producer no longer writes.  The NEXT unit's blocks are handled in
+      // front of the current unit's last column tile (they land as soon as that tile's MMAs have retired); the kernel is bound
+      // by its stores, so the MMA pipe's short wait for a_ready is hidden.
+      const bool lnin = MODE == kGpModeAct192 && p.ares && p.in_stats != nullptr;
+      auto normalize_unit = [&](int un_n, uint32_t at_n) {
+        const int row = (un_n / G) * 2 * kGpBM + (int)rank * kGpBM + r;
+        const float2 st = row < p.M ? p.in_stats[row] : make_float2(0.f, 0.f);
+        const uint64_t sc = f2_bcast(st.y), sh = f2_bcast(-st.x * st.y);
+#pragma unroll 1
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(smem_u32(&bars->a_full[kb]), at_n & 1);
+          unsigned char* hb = ring + kb * kGpABytes;
+          for (int ch = part; ch < 8; ch += PARTS) {
+            uint4* ptr = reinterpret_cast<uint4*>(hb + sw128_off(r, ch));
+            const uint4 t = *ptr;
+            const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+            uint32_t o[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const uint2 gb = *reinterpret_cast<const uint2*>(&gbin_s[kb * 64 + ch * 8 + 2 * q]);
+              float h0, h1;
+              f2_unpack(f2_fma(f2_fma(f2_pack(bf16_lo(w[q]), bf16_hi(w[q])), sc, sh), f2_pack(bf16_lo(gb.x), bf16_lo(gb.y)),
+                               f2_pack(bf16_hi(gb.x), bf16_hi(gb.y))), h0, h1);
+              o[q] = pack_bf16x2(h0, h1);
+            }
+            *ptr = make_uint4(o[0], o[1], o[2], o[3]);
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(mapa(smem_u32(&bars->a_ready[kb]), 0));
+        }
+      };
+      uint32_t at = 0;
+      if (lnin && pair < units) normalize_unit(pair, 0);
+      for (int un = pair; un < units; un += num_pairs, ++at) {
         const int pt = un / G, nt0 = (un - pt * G) * npg;
         const int row0 = pt * 2 * kGpBM + (int)rank * kGpBM;
         for (int nt = nt0; nt < nt0 + npg; ++nt, ++tile) {
+          if (lnin && nt == nt0 + npg - 1 && un + num_pairs < units) normalize_unit(un + num_pairs, at + 1);
           const uint32_t as = tile % ACC, an = tile / ACC;
           mbar_wait(smem_u32(&bars->tmem_full[as]), an & 1);
           tc_fence_after();
@@ -539,7 +592,7 @@ static int gp_launch(const CUtensorMap& ma, const CUtensorMap& mw, const CUtenso
   using Cfg = GpCfg<MODE, NSUB>;
   constexpr uint32_t kStage = kGpABytes + NSUB * (Cfg::UN / 2) * 128;
   const size_t smem = 1024 + (size_t)Cfg::STAGES * kStage + (size_t)Cfg::BLOCKS * kGpBlkBytes + sizeof(GpBars) +
-                      (MODE == kGpModeLn ? (size_t)3 * p.N * 4 + 4 * 128 * sizeof(float2) + 16 : (size_t)p.N * 4);
+                      (MODE == kGpModeLn ? (size_t)3 * p.N * 4 + 4 * 128 * sizeof(float2) + 16 : (size_t)p.N * 4 + (size_t)p.K * 4);
   D2S_REQUIRE(smem <= 227 * 1024, D2S_ERR_ARG, "%s: needs %zu B of shared memory", what, smem);
   static SmemOptIn opt;
   cudaError_t e = opt_in_smem(opt, gemm_pair_kernel<MODE, NSUB, ACT>, 227 * 1024);
@@ -557,9 +610,8 @@ static int gp_launch(const CUtensorMap& ma, const CUtensorMap& mw, const CUtenso
 
 using namespace d2s;
 
-extern "C" int d2s_linear_act_pair_bf16(const void* a, const void* w, const void* bias, int M, int N, int K, int act, void* out,
-                                        void* pre, d2s_stream_t stream) {
-  const char* what = "d2s_linear_act_pair_bf16";
+static int gp_linear_act(const char* what, const void* a, const float* in_stats, const void* in_gamma, const void* in_beta,
+                         const void* w, const void* bias, int M, int N, int K, int act, void* out, void* pre, d2s_stream_t stream) {
   D2S_REQUIRE(a && w && out, D2S_ERR_ARG, "linear_act_pair: null pointer");
   const bool t192 = N % 256 != 0;                  // 192-column tiles for widths like 384
   D2S_REQUIRE(M >= 0 && N >= 192 && (N % 256 == 0 || N % 192 == 0) && N <= 4096 && K >= kGpBK && K % kGpBK == 0, D2S_ERR_ARG,
@@ -588,7 +640,10 @@ extern "C" int d2s_linear_act_pair_bf16(const void* a, const void* w, const void
     }
   }
   GpParams p{(const __nv_bfloat16*)bias, nullptr, nullptr, nullptr, nullptr, nullptr, (__nv_bfloat16*)pre, nullptr, 0.f, M, N, K, act, 0,
-             gp_trace(), gp_debug(), (t192 && K <= 6 * kGpBK && ares_on) ? 1 : 0, groups};
+             gp_trace(), gp_debug(), (t192 && K <= 6 * kGpBK && (ares_on || in_stats)) ? 1 : 0, groups,
+             reinterpret_cast<const float2*>(in_stats), (const __nv_bfloat16*)in_gamma, (const __nv_bfloat16*)in_beta};
+  D2S_REQUIRE(!in_stats || p.ares, D2S_ERR_ARG, "%s: the on-the-fly input LayerNorm needs N %% 192 == 0 (N %% 256 != 0) and K <= %d", what,
+              6 * kGpBK);
   if (t192) {
     if (act == D2S_ACT_GELU) return gp_launch<kGpModeAct192, 1, D2S_ACT_GELU>(ma, mw, mo, p, (cudaStream_t)stream, what);
     if (act == D2S_ACT_RELU) return gp_launch<kGpModeAct192, 1, D2S_ACT_RELU>(ma, mw, mo, p, (cudaStream_t)stream, what);
@@ -616,7 +671,7 @@ static int gp_linear_residual(const char* what, const void* a, const void* w, co
   if ((rc = gp_map_2d(&mw, w, K, N, kGpBK, 96, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, what))) return rc;
   GpParams p{(const __nv_bfloat16*)bias, (const __nv_bfloat16*)gamma, (const __nv_bfloat16*)beta, (const __nv_bfloat16*)x,
              (__nv_bfloat16*)out_sum, (__nv_bfloat16*)out_norm, nullptr, reinterpret_cast<float2*>(stats), eps, M, N, K, 0,
-             (out_norm || stats) ? 1 : 0, gp_trace(), gp_debug(), 0, 1};
+             (out_norm || stats) ? 1 : 0, gp_trace(), gp_debug(), 0, 1, nullptr, nullptr, nullptr};
   if (N != 192) return gp_launch<kGpModeLn, 2, 0>(ma, mw, ma, p, (cudaStream_t)stream, what);      // 384, or 768 as two halves
   return gp_launch<kGpModeLn, 1, 0>(ma, mw, ma, p, (cudaStream_t)stream, what);
 }
@@ -632,4 +687,17 @@ extern "C" int d2s_linear_residual_stats_bf16(const void* a, const void* w, cons
   D2S_REQUIRE(stats != nullptr && (reinterpret_cast<uintptr_t>(stats) & 7u) == 0, D2S_ERR_ARG,
               "linear_residual_stats: stats must be a non-null, 8-byte aligned (M,2) f32 buffer");
   return gp_linear_residual("d2s_linear_residual_stats_bf16", a, w, bias, x, nullptr, nullptr, eps, M, N, K, out_sum, nullptr, stats, stream);
+}
+
+extern "C" int d2s_linear_act_pair_bf16(const void* a, const void* w, const void* bias, int M, int N, int K, int act, void* out,
+                                        void* pre, d2s_stream_t stream) {
+  return gp_linear_act("d2s_linear_act_pair_bf16", a, nullptr, nullptr, nullptr, w, bias, M, N, K, act, out, pre, stream);
+}
+
+extern "C" int d2s_linear_lnin_act_pair_bf16(const void* x, const float* in_stats, const void* in_gamma, const void* in_beta,
+                                             const void* w, const void* bias, int M, int N, int K, int act, void* out,
+                                             d2s_stream_t stream) {
+  D2S_REQUIRE(in_stats && in_gamma && in_beta && (reinterpret_cast<uintptr_t>(in_stats) & 7u) == 0, D2S_ERR_ARG,
+              "linear_lnin_act_pair: in_stats (M,2) f32 (8-byte aligned), in_gamma and in_beta are required");
+  return gp_linear_act("d2s_linear_lnin_act_pair_bf16", x, in_stats, in_gamma, in_beta, w, bias, M, N, K, act, out, nullptr, stream);
 }

@@ -80,6 +80,7 @@ struct MpParams {
   // map_a then covers x' itself, which is also the residual input x
   const float2* in_stats;
   const __nv_bfloat16 *in_gamma, *in_beta;
+  float2* out_stats;            // per-row (mean, rstd) of x' (M) for a consumer that applies the next LayerNorm itself, or NULL
 };
 
 #if MP_E1W == 8
@@ -464,13 +465,15 @@ mlp_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa(smem_u32(&bars->acc_empty), 0));     // the next tile's G2(0) may start
-      if (p.want_ln) {
+      if (p.want_ln || p.out_stats != nullptr) {
         float s0, s1, q0, q1;
         f2_unpack(acc_s, s0, s1);
         f2_unpack(acc_q, q0, q1);
         const float mean = (s0 + s1) * (1.0f / TN);
         const float var = fmaxf((q0 + q1) * (1.0f / TN) - mean * mean, 0.f);
         const float rstd = rsqrtf(var + p.eps);
+        if (p.out_stats != nullptr && row0 + lane < p.M) p.out_stats[row0 + lane] = make_float2(mean, rstd);   // (this thread's row)
+        if (!p.want_ln) continue;
         const uint64_t sc = f2_bcast(rstd), sh = f2_bcast(-mean * rstd);
         // ---- pass 2: hn = (x' - mean) * rstd * gamma + beta; x' comes back from L2 (this warp wrote it above) ----
         // hn row of global row g = (image b, token t): b * (T - ln_row0) + t - ln_row0, tokens t < ln_row0 are not written
@@ -558,7 +561,7 @@ static_assert(kMpW1Slots >= kMpKB - 1, "in_stats: the H blocks of a tile are iss
 
 static int mp_launch(const char* what, const void* h, const float* in_stats, const void* in_gamma, const void* in_beta, const void* w1,
                      const void* b1, const void* w2, const void* b2, const void* x, const void* gamma, const void* beta, float eps,
-                     int M, int D, int HID, int T, int norm_row0, void* out_sum, void* out_norm, d2s_stream_t stream) {
+                     int M, int D, int HID, int T, int norm_row0, void* out_sum, void* out_norm, float* out_stats, d2s_stream_t stream) {
   D2S_REQUIRE(h && w1 && w2 && x && out_sum, D2S_ERR_ARG, "mlp_residual_ln: null pointer");
   D2S_REQUIRE(M >= 0 && D == kMpD && HID >= kMpCH && HID % kMpCH == 0 && HID <= 2048, D2S_ERR_ARG,
               "mlp_residual_ln: need D == %d and HID %% %d == 0, %d <= HID <= 2048 (got M=%d D=%d HID=%d)", kMpD, kMpCH, kMpCH, M,
@@ -577,7 +580,8 @@ static int mp_launch(const char* what, const void* h, const float* in_stats, con
   const char* tr_env = getenv("D2S_GEMM_TRACE");
   MpParams p{tr_env ? reinterpret_cast<long long*>(strtoull(tr_env, nullptr, 10)) : nullptr, (const __nv_bfloat16*)b1, (const __nv_bfloat16*)b2, (const __nv_bfloat16*)gamma, (const __nv_bfloat16*)beta,
              (const __nv_bfloat16*)x, (__nv_bfloat16*)out_sum, (__nv_bfloat16*)out_norm, eps, M, HID, out_norm ? 1 : 0, T, norm_row0,
-             reinterpret_cast<const float2*>(in_stats), (const __nv_bfloat16*)in_gamma, (const __nv_bfloat16*)in_beta};
+             reinterpret_cast<const float2*>(in_stats), (const __nv_bfloat16*)in_gamma, (const __nv_bfloat16*)in_beta,
+             reinterpret_cast<float2*>(out_stats)};
   const size_t smem = 1024 + (size_t)kMpKB * kMpA1Blk + 2 * (size_t)kMpPBlk + (size_t)kMpW1Slots * kMpW1Blk +
                       (size_t)kMpW2Slots * kMpW2Blk + sizeof(MpBars) + (size_t)HID * 4 + 3 * kMpD * 4 + (size_t)kMpOutWarps * 2048 + 32;
   D2S_REQUIRE(smem <= 227 * 1024, D2S_ERR_ARG, "mlp_residual_ln: needs %zu B of shared memory", smem);
@@ -596,15 +600,16 @@ extern "C" int d2s_mlp_residual_ln_bf16(const void* h, const void* w1, const voi
                                         const void* x, const void* gamma, const void* beta, float eps, int M, int D, int HID,
                                         int T, int norm_row0, void* out_sum, void* out_norm, d2s_stream_t stream) {
   return mp_launch("d2s_mlp_residual_ln_bf16", h, nullptr, nullptr, nullptr, w1, b1, w2, b2, x, gamma, beta, eps, M, D, HID, T, norm_row0,
-                   out_sum, out_norm, stream);
+                   out_sum, out_norm, nullptr, stream);
 }
 
 extern "C" int d2s_mlp_lnin_residual_ln_bf16(const void* x, const float* in_stats, const void* in_gamma, const void* in_beta,
                                              const void* w1, const void* b1, const void* w2, const void* b2, const void* gamma,
                                              const void* beta, float eps, int M, int D, int HID, int T, int norm_row0, void* out_sum,
-                                             void* out_norm, d2s_stream_t stream) {
+                                             void* out_norm, float* out_stats, d2s_stream_t stream) {
+  D2S_REQUIRE((reinterpret_cast<uintptr_t>(out_stats) & 7u) == 0, D2S_ERR_ALIGN, "mlp_lnin_residual_ln: out_stats must be 8-byte aligned");
   D2S_REQUIRE(in_stats && in_gamma && in_beta && (reinterpret_cast<uintptr_t>(in_stats) & 7u) == 0, D2S_ERR_ARG,
               "mlp_lnin_residual_ln: in_stats (M,2) f32 (8-byte aligned), in_gamma and in_beta are required");
   return mp_launch("d2s_mlp_lnin_residual_ln_bf16", x, in_stats, in_gamma, in_beta, w1, b1, w2, b2, x, gamma, beta, eps, M, D, HID, T,
-                   norm_row0, out_sum, out_norm, stream);
+                   norm_row0, out_sum, out_norm, out_stats, stream);
 }

@@ -26,6 +26,7 @@ _FROZEN_BF16 = os.environ.get("D2S_FROZEN_BF16", "1") != "0"   # A/B switch: cac
 _FUSED_ADD_LN_TRAIN = os.environ.get("D2S_FUSED_ADD_LN_TRAIN", "1") != "0"   # A/B switch: residual adds folded into LayerNorm fwd/bwd
 _FUSED_MLP = os.environ.get("D2S_FUSED_MLP", "1") != "0"      # A/B switch for the one-kernel MLP (ops.mlp_residual_ln)
 _FUSED_PAIR = os.environ.get("D2S_FUSED_PAIR", "1") != "0"  # A/B switch for the CTA-pair GEMMs (fc1 pair; proj/fc2 + add + LN)
+_LAZY_NORM1 = os.environ.get("D2S_LAZY_NORM1", "1") != "0"  # A/B switch: norm1 applied inside the qkv GEMM from the MLP kernel's row statistics
 _LAZY_NORM2 = os.environ.get("D2S_LAZY_NORM2", "1") != "0"  # A/B switch: norm2 applied inside the one-kernel MLP from per-row statistics (no normalised copy)
 _QKV_PAIR = os.environ.get("D2S_QKV_PAIR", "1") != "0"     # A/B switch: inference qkv projection on the CTA-pair tcgen05 GEMM (else the library GEMM)
 _PRED_FUSED = os.environ.get("D2S_PRED_FUSED", "1") != "0"  # A/B switch: second half of the Variant A predictor + selection as one tcgen05 kernel (inference, D = 384)
@@ -104,14 +105,28 @@ def patch_embed_forward(m, img):
     return F.linear(patches, w.view(w.shape[0], -1), m.proj.bias)
 
 
+def _qkv_pair_ok(lin, x):
+    """The qkv projection runs on the CTA-pair tcgen05 GEMM with 192-column tiles and resident input rows: inference, bf16, D <= 384."""
+    return (_QKV_PAIR and _FUSED_PAIR and x.is_cuda and x.dtype == torch.bfloat16 and lin.weight.dtype == torch.bfloat16
+            and not _needs_grad(x, lin.weight, lin.bias) and lin.in_features % 64 == 0 and lin.in_features <= 384
+            and lin.out_features % 192 == 0 and lin.out_features % 256 != 0)
+
+
 def attention_pre_proj(m, x, policy=None, return_cls_attn=False):
     """Attention.forward up to (not including) the output projection (dynamic_vit.py:216-231): (o (B,T,C), cls_attn)."""
     B, T, C = x.shape
     H = m.num_heads
     lin = m.qkv
-    if (_QKV_PAIR and _FUSED_PAIR and x.is_cuda and x.dtype == torch.bfloat16 and lin.weight.dtype == torch.bfloat16
-            and not _needs_grad(x, lin.weight, lin.bias) and lin.in_features % 64 == 0 and lin.in_features <= 384
-            and lin.out_features % 192 == 0 and lin.out_features % 256 != 0):
+    if isinstance(x, _LazyNorm):
+        if _qkv_pair_ok(lin, x):
+            # norm1 was not materialised: the qkv GEMM normalises its resident input rows from the producer's row statistics
+            qkv = ops.linear_act(x.x, lin.weight, lin.bias, ops.ACT_NONE, in_stats=x.stats, in_ln_weight=x.norm.weight,
+                                 in_ln_bias=x.norm.bias)
+        else:
+            x = x.value()
+    if isinstance(x, _LazyNorm):
+        pass
+    elif _qkv_pair_ok(lin, x):
         # inference, D <= 384: the CTA-pair tcgen05 GEMM with 192-column tiles and the row tile's input rows resident in shared
         # memory -- bit-identical to the library GEMM and as fast (both are bound by the 3 x (B,T,D) write stream)
         qkv = ops.linear_act(x, lin.weight, lin.bias, ops.ACT_NONE)
@@ -332,6 +347,12 @@ class _Stream:
             h, m = self.mlp
             if _mlp_fused_ok(m, h, self.x):
                 self.mlp = None
+                if isinstance(h, _LazyNorm) and h.x is self.x and lazy and row0 == 0:
+                    # ... and the NEXT norm handed on as statistics too (its only reader is the qkv GEMM)
+                    self.x, st = ops.mlp_residual_ln(None, m.fc1.weight, m.fc1.bias, m.fc2.weight, m.fc2.bias, self.x, eps=norm.eps,
+                                                     want_norm=False, in_stats=h.stats, in_ln_weight=h.norm.weight,
+                                                     in_ln_bias=h.norm.bias, want_stats=True)
+                    return self.x, _LazyNorm(self.x, st, norm)
                 if isinstance(h, _LazyNorm) and h.x is self.x:      # norm2 applied inside the kernel, from its statistics
                     self.x, hn = ops.mlp_residual_ln(None, m.fc1.weight, m.fc1.bias, m.fc2.weight, m.fc2.bias, self.x,
                                                      norm.weight, norm.bias, norm.eps, norm_row0=row0, in_stats=h.stats,
@@ -381,7 +402,10 @@ class _Stream:
         if not _fusable(blk, self._probe(), policy):
             self._flush_gather()
         if _fusable(blk, self._probe(), policy):
-            _, h = self._sum_norm(blk.norm1)
+            # norm1 is only ever read by this block's qkv projection
+            lazy1 = (_LAZY_NORM1 and _is_plain_ln(blk.norm1) and blk.norm1.weight.dtype == torch.bfloat16
+                     and _qkv_pair_ok(blk.attn.qkv, self._probe()))
+            _, h = self._sum_norm(blk.norm1, lazy=lazy1)
             o, cls_attn = attention_pre_proj(blk.attn, h, policy, return_cls_attn)
             self.lin = (o, blk.attn.proj)
             # norm2 is only ever read by this block's MLP: when that MLP runs as the one kernel, hand it the statistics

@@ -1226,7 +1226,7 @@ def layer_norm(x, weight, bias, eps, out_dtype=None, row0=0):
     return _LayerNorm.apply(x, weight, bias, eps, out_dtype, int(row0))
 
 
-def linear_act(x, weight, bias, act=ACT_GELU, want_pre=False):
+def linear_act(x, weight, bias, act=ACT_GELU, want_pre=False, in_stats=None, in_ln_weight=None, in_ln_bias=None):
     """act(x @ weight^T + bias) in one CTA-pair tcgen05 GEMM with the activation in the epilogue (bf16, no autograd).
     x (..., K) contiguous, weight (N, K), N % 256 == 0 or N % 192 == 0 (256- or 192-column tiles), K % 64 == 0.  want_pre: returns (act(u), u) with u the Linear's own
     output as a second result of the same kernel."""
@@ -1240,6 +1240,17 @@ def linear_act(x, weight, bias, act=ACT_GELU, want_pre=False):
     M = xc.numel() // K
     N = w.shape[0]
     out = torch.empty(*xc.shape[:-1], N, dtype=torch.bfloat16, device=xc.device)
+    if in_stats is not None:
+        # x is the raw residual stream: LayerNorm(x) (in_ln_weight / in_ln_bias, statistics from the producer) is formed in the
+        # kernel's resident input tile (N % 192 == 0, K <= 384)
+        st = in_stats.detach().contiguous()
+        if want_pre or st.dtype != torch.float32 or st.numel() != 2 * M:
+            raise RuntimeError(f"linear_act: in_stats must be ({M}, 2) float32 (and no second output)")
+        gi, bi = (t.detach().to(torch.bfloat16).contiguous() for t in (in_ln_weight, in_ln_bias))
+        if M:
+            _call("d2s_linear_lnin_act_pair_bf16", _ptr(xc), _ptr(st), _ptr(gi), _ptr(bi), _ptr(w), _ptr(b), M, N, K, int(act),
+                  _ptr(out), _stream(xc))
+        return out
     pre = torch.empty_like(out) if want_pre else None
     _call("d2s_linear_act_pair_bf16", _ptr(xc), _ptr(w), _ptr(b), M, N, K, int(act), _ptr(out), _ptr(pre), _stream(xc))
     return (out, pre) if want_pre else out
@@ -1283,13 +1294,15 @@ def linear_residual_ln(a, weight, bias, x, ln_weight=None, ln_bias=None, eps=1e-
 
 
 def mlp_residual_ln(h, w1, b1, w2, b2, x, ln_weight=None, ln_bias=None, eps=1e-5, want_norm=True, norm_row0=0,
-                    in_stats=None, in_ln_weight=None, in_ln_bias=None):
+                    in_stats=None, in_ln_weight=None, in_ln_bias=None, want_stats=False):
     """(x', hn) with x' = x + fc2(GELU(fc1(h))) and hn = LayerNorm(x') * ln_weight + ln_bias (None when want_norm is False):
     the MLP branch of Block.forward with its residual add and the next LayerNorm (vit_models/dynamic_vit.py:159-175, :263-283)
     in ONE CTA-pair tcgen05 kernel; the hidden activations stay on chip.  bf16, inference only, D == 384.
     norm_row0 > 0 (x of shape (B,T,D)): hn = LayerNorm(x'[:, norm_row0:]) of shape (B, T-norm_row0, D).
     in_stats (M,2) f32 with in_ln_weight / in_ln_bias: h is None and the MLP's input is LayerNorm(x) formed on the fly from the
-    per-row (mean, rstd) that linear_residual_ln(want_stats=True) wrote next to x."""
+    per-row (mean, rstd) that linear_residual_ln(want_stats=True) wrote next to x.
+    want_stats (with in_stats, want_norm=False): returns (x', stats (M,2) f32 = per-row (mean, rstd) of x' for `eps`) -- the next
+    LayerNorm is then applied by its consumer (linear_act(in_stats=...): the next block's qkv projection)."""
     if in_stats is not None:
         h = x
     _check_cuda(h, w1, b1, w2, b2, x, ln_weight, ln_bias, in_stats, in_ln_weight, in_ln_bias)
@@ -1317,10 +1330,13 @@ def mlp_residual_ln(h, w1, b1, w2, b2, x, ln_weight=None, ln_bias=None, eps=1e-5
         st = in_stats.detach().contiguous()
         if st.dtype != torch.float32 or st.numel() != 2 * M:
             raise RuntimeError(f"mlp_residual_ln: in_stats must be ({M}, 2) float32")
+        out_stats = torch.empty(M, 2, dtype=torch.float32, device=xc.device) if want_stats else None
         _call("d2s_mlp_lnin_residual_ln_bf16", _ptr(xc), _ptr(st), _ptr(bf(in_ln_weight)), _ptr(bf(in_ln_bias)), _ptr(w1c),
               _ptr(bf(b1)), _ptr(w2c), _ptr(bf(b2)), _ptr(g), _ptr(bt), float(eps), M, D, HID, T, int(norm_row0), _ptr(out_sum),
-              _ptr(out_norm), _stream(xc))
-        return out_sum, out_norm
+              _ptr(out_norm), _ptr(out_stats), _stream(xc))
+        return (out_sum, out_stats) if want_stats else (out_sum, out_norm)
+    if want_stats:
+        raise RuntimeError("mlp_residual_ln: want_stats is an output of the in_stats form of the kernel")
     _call("d2s_mlp_residual_ln_bf16", _ptr(hc), _ptr(w1c), _ptr(bf(b1)), _ptr(w2c), _ptr(bf(b2)), _ptr(xc), _ptr(g), _ptr(bt),
               float(eps), M, D, HID, T, int(norm_row0), _ptr(out_sum), _ptr(out_norm), _stream(hc))
     return out_sum, out_norm

@@ -294,6 +294,12 @@ int d2s_assemble_layernorm(const void* patches, const void* cls, const void* pos
  * pre (M,N) or NULL: also write the pre-activation a @ w^T + bias (training: GELU' needs it; saves torch's separate GELU pass). */
 int d2s_linear_act_pair_bf16(const void* a, const void* w, const void* bias, int M, int N, int K, int act, void* out,
                              void* pre, d2s_stream_t stream);
+/* The same with the LayerNorm of the INPUT rows applied on the fly (Block.forward's norm1 in front of attn.qkv, dynamic_vit.py:277;
+ * N % 192 == 0, N % 256 != 0, K <= 384): x (M,K) is the residual stream, in_stats (M,2) f32 its per-row (mean, rstd) as written by
+ * d2s_mlp_lnin_residual_ln_bf16 (out_stats), in_gamma / in_beta (K) bf16; the row tile is normalised in shared memory (bit-identical
+ * to the normalised copy) before the MMAs read it. */
+int d2s_linear_lnin_act_pair_bf16(const void* x, const float* in_stats, const void* in_gamma, const void* in_beta, const void* w,
+                                  const void* bias, int M, int N, int K, int act, void* out, d2s_stream_t stream);
 
 /* Linear + residual add + LayerNorm in one tcgen05 GEMM: attn.proj / mlp.fc2 of Block.forward together with the
  * residual add and the NEXT LayerNorm (dynamic_vit.py:263-283: x = x + attn(norm1(x)); x = x + mlp(norm2(x))), bf16 only:
@@ -325,10 +331,13 @@ int d2s_mlp_residual_ln_bf16(const void* h, const void* w1, const void* b1, cons
 /* The same with the LayerNorm of the MLP's INPUT applied on the fly (Block.forward's norm2, dynamic_vit.py:281): x (M,D) is the
  * residual stream itself, in_stats (M,2) f32 its per-row (mean, rstd) as written by d2s_linear_residual_stats_bf16, in_gamma /
  * in_beta (D) bf16 that LayerNorm's affine; h = bf16((x - mean) * rstd * gamma + beta) is formed in shared memory (the arithmetic of
- * d2s_linear_residual_ln_bf16's own LayerNorm pass: bit-identical A operand) and never written to HBM.  x is also the residual input. */
+ * d2s_linear_residual_ln_bf16's own LayerNorm pass: bit-identical A operand) and never written to HBM.  x is also the residual input.
+ * out_stats (M,2) f32 or NULL: per-row (mean, rstd) of out_sum for `eps`, for a consumer that applies the NEXT LayerNorm itself
+ * (d2s_linear_lnin_act_pair_bf16: the next block's qkv projection); out_norm may then be NULL. */
 int d2s_mlp_lnin_residual_ln_bf16(const void* x, const float* in_stats, const void* in_gamma, const void* in_beta, const void* w1,
                                   const void* b1, const void* w2, const void* b2, const void* gamma, const void* beta, float eps,
-                                  int M, int D, int HID, int T, int norm_row0, void* out_sum, void* out_norm, d2s_stream_t stream);
+                                  int M, int D, int HID, int T, int norm_row0, void* out_sum, void* out_norm, float* out_stats,
+                                  d2s_stream_t stream);
 
 /* LayerNorm forward / backward for the training path (norm1 / norm2 / predictor norms of Block.forward,
  * dynamic_vit.py:263-283) with mixed dtypes for bf16 autocast: x (rows,D) f32|bf16 -> h (rows,D) f32|bf16,

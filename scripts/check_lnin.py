@@ -59,4 +59,33 @@ if "--time" in sys.argv:
     for T in (197, 138, 97, 68):
         xs = [(r(1024, T, D), r(1024, T, D)) for _ in range(3)]
         print(f"T={T}: proj+LN -> MLP {timed(old, xs):.1f} us | proj+stats -> MLP with the LayerNorm inside {timed(new, xs):.1f} us")
-sys.exit(0 if ok else 1)
+
+
+# ---- norm1: MLP kernel writes row statistics, the next qkv projection normalises its resident input rows itself ----
+def chain_old(a, x):
+    xs, st = ops.linear_residual_ln(a, Wp, bp, x, eps=1e-6, want_norm=False, want_stats=True)
+    x2, hn = ops.mlp_residual_ln(None, W1, b1, W2, b2, xs, g1, bt1, 1e-6, in_stats=st, in_ln_weight=g2, in_ln_bias=bt2)
+    return x2, ops.linear_act(hn, Wq, bq, ops.ACT_NONE)
+
+
+def chain_new(a, x):
+    xs, st = ops.linear_residual_ln(a, Wp, bp, x, eps=1e-6, want_norm=False, want_stats=True)
+    x2, st2 = ops.mlp_residual_ln(None, W1, b1, W2, b2, xs, None, None, 1e-6, want_norm=False, in_stats=st, in_ln_weight=g2,
+                                  in_ln_bias=bt2, want_stats=True)
+    return x2, ops.linear_act(x2, Wq, bq, ops.ACT_NONE, in_stats=st2, in_ln_weight=g1, in_ln_bias=bt1)
+
+
+Wq, bq = r(3 * D, D, sc=D ** -0.5), r(3 * D, sc=0.1)
+ok2 = True
+for (B, T) in [(3, 197), (2, 138), (7, 97), (1, 1), (5, 68), (64, 197), (300, 97), (1024, 68)]:
+    a, x = r(B, T, D), r(B, T, D, sc=2.0)
+    o, n = chain_old(a, x), chain_new(a, x)
+    same = all(torch.equal(p, q) for p, q in zip(o, n))
+    print(f"norm1 chain B={B} T={T}: identical {same}")
+    ok2 &= same
+print("OK" if ok2 else "MISMATCH")
+if "--time" in sys.argv:
+    for T in (197, 138, 97, 68):
+        xs = [(r(1024, T, D), r(1024, T, D)) for _ in range(3)]
+        print(f"T={T}: proj -> MLP -> qkv with hn materialised {timed(chain_old, xs):.1f} us | with row statistics {timed(chain_new, xs):.1f} us")
+sys.exit(0 if (ok and ok2) else 1)

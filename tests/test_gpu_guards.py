@@ -115,13 +115,17 @@ def test_gemm_family_stays_in_bounds(d2s, M):
         # statistics instead of the normalised copy, and the MLP kernel that applies the LayerNorm to its input tile itself
         s_sum, s_st = Guarded((M, D), torch.bfloat16), Guarded((M, 2), torch.float32)
         lib.call("d2s_linear_residual_stats_bf16", h.ptr, wp.data_ptr(), b2.data_ptr(), x.ptr, 1e-6, M, D, D, s_sum.ptr, s_st.ptr, _stream())
-        l_sum, l_norm = Guarded((M, D), torch.bfloat16), Guarded((M, D), torch.bfloat16)
+        l_sum, l_norm, l_st = Guarded((M, D), torch.bfloat16), Guarded((M, D), torch.bfloat16), Guarded((M, 2), torch.float32)
         lib.call("d2s_mlp_lnin_residual_ln_bf16", s_sum.ptr, s_st.ptr, gam.data_ptr(), bet.data_ptr(), w1.data_ptr(), b1.data_ptr(),
-                 w2.data_ptr(), b2.data_ptr(), gam.data_ptr(), bet.data_ptr(), 1e-6, M, D, HID, 1, 0, l_sum.ptr, l_norm.ptr, _stream())
+                 w2.data_ptr(), b2.data_ptr(), gam.data_ptr(), bet.data_ptr(), 1e-6, M, D, HID, 1, 0, l_sum.ptr, l_norm.ptr, l_st.ptr, _stream())
+        q2 = Guarded((M, 3 * D), torch.bfloat16)      # the next block's qkv projection normalising its input rows from those statistics
+        lib.call("d2s_linear_lnin_act_pair_bf16", l_sum.ptr, l_st.ptr, gam.data_ptr(), bet.data_ptr(), wq.data_ptr(), bq.data_ptr(), M, 3 * D, D,
+                 0, q2.ptr, _stream())
         torch.cuda.synchronize()
         for name, gd in (("mlp sum", o_sum), ("mlp norm", o_norm), ("proj sum", p_sum), ("proj norm", p_norm), ("fc2 sum", f_sum),
                          ("fc2 norm", f_norm), ("act", act), ("pre", pre), ("qkv", qkv), ("linear + gelu 384", g384), ("stats sum", s_sum),
-                         ("stats", s_st), ("lnin sum", l_sum), ("lnin norm", l_norm), ("h", h), ("x", x), ("a4", a4)):
+                         ("stats", s_st), ("lnin sum", l_sum), ("lnin norm", l_norm), ("lnin stats", l_st), ("qkv lnin", q2), ("h", h), ("x", x),
+                         ("a4", a4)):
             assert gd.ok(), f"{name}: guard zone overwritten"
             if gd not in (h, x, a4):
                 assert bool(torch.isfinite(gd.t.float()).all()), f"{name}: element left unwritten or fed by an out-of-bounds read"

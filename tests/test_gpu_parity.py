@@ -1233,19 +1233,46 @@ def test_mlp_kernel_applies_its_input_layernorm_from_row_statistics(ops, B, T, r
     assert torch.equal(out[0], ref[0]) and torch.equal(out[1], ref[1])
 
 
-def test_lazy_norm2_is_invisible_at_model_level(d2s, monkeypatch):
-    """engine: norm2 handed to the one-kernel MLP as statistics (D2S_LAZY_NORM2) against the same forward with the normalised
-    copy: identical logits and kept sets (the kernels are bit-identical; the CLS-only last MLP normalises its rows itself)."""
+def test_lazy_norms_are_invisible_at_model_level(d2s, monkeypatch):
+    """engine: norm2 handed to the one-kernel MLP and norm1 to the qkv GEMM as row statistics (D2S_LAZY_NORM2 / D2S_LAZY_NORM1)
+    against the same forward with the normalised copies: identical logits and kept sets (the kernels are bit-identical; the
+    CLS-only last MLP normalises its rows itself)."""
     torch.manual_seed(3)
     m = d2s.variant_a.DefaultVisionTransformerDiffPruning(patch_size=16, embed_dim=384, depth=6, num_heads=6, num_classes=32, mlp_ratio=4,
                                                           qkv_bias=True, pruning_loc=[2, 4], token_ratio=[0.7, 0.49], distill=True)
     m = m.cuda().eval().to(torch.bfloat16)
     img = cu(fx.randn(55, 5, 3, 224, 224)).bfloat16()
+    outs = []
     with torch.no_grad():
-        monkeypatch.setattr(d2s.engine, "_LAZY_NORM2", True)
-        a = m(img)
-        ka = [k.clone() for k in m.kept_token_indices]
-        monkeypatch.setattr(d2s.engine, "_LAZY_NORM2", False)
-        b = m(img)
-        kb = m.kept_token_indices
-    assert torch.equal(a, b) and all(torch.equal(p, q) for p, q in zip(ka, kb))
+        for n1, n2 in ((True, True), (False, True), (True, False), (False, False)):
+            monkeypatch.setattr(d2s.engine, "_LAZY_NORM1", n1)      # norm1 inside the qkv GEMM, from the MLP kernel's row statistics
+            monkeypatch.setattr(d2s.engine, "_LAZY_NORM2", n2)      # norm2 inside the MLP kernel, from the proj kernel's
+            n0 = d2s._lib.launch_count()
+            logits = m(img)
+            outs.append((logits, [k.clone() for k in m.kept_token_indices], d2s._lib.launch_count() - n0))
+    for logits, kept, _ in outs[1:]:
+        assert torch.equal(logits, outs[0][0]) and all(torch.equal(p, q) for p, q in zip(kept, outs[0][1]))
+    assert len({n for _, _, n in outs}) == 1                        # same kernels launched, only what they read / write differs
+
+
+@pytest.mark.parametrize("B,T", [(3, 197), (2, 138), (7, 97), (1, 1), (300, 68)])
+def test_qkv_gemm_applies_norm1_from_the_mlp_kernels_row_statistics(ops, B, T):
+    """d2s_mlp_lnin_residual_ln_bf16 with out_stats -> d2s_linear_lnin_act_pair_bf16 (the next block's qkv projection normalising
+    its resident input rows): bit-identical to the chain that materialises LayerNorm(x'') in between."""
+    D, HID = 384, 1536
+    bf = torch.bfloat16
+    r = lambda seed, *s, sc=1.0: cu(fx.randn(seed, *s) * sc).to(bf)
+    W1, b1, W2, b2 = r(3, HID, D, sc=D ** -0.5), r(4, HID, sc=0.1), r(5, D, HID, sc=HID ** -0.5), r(6, D, sc=0.1)
+    Wq, bq = r(13, 3 * D, D, sc=D ** -0.5), r(14, 3 * D, sc=0.1)
+    g2, bt2 = (1 + 0.2 * cu(fx.randn(7, D))).to(bf), r(8, D, sc=0.2)
+    g1, bt1 = (1 + 0.2 * cu(fx.randn(9, D))).to(bf), r(10, D, sc=0.2)
+    x = r(20 + T, B, T, D, sc=2.0)
+    xf = x.float().reshape(B * T, D)
+    st = torch.stack([xf.mean(-1), torch.rsqrt(xf.var(-1, unbiased=False) + 1e-6)], -1).contiguous()
+    x2, hn = ops.mlp_residual_ln(None, W1, b1, W2, b2, x, g1, bt1, 1e-6, in_stats=st, in_ln_weight=g2, in_ln_bias=bt2)
+    ref = ops.linear_act(hn, Wq, bq, ops.ACT_NONE)
+    x3, st2 = ops.mlp_residual_ln(None, W1, b1, W2, b2, x, None, None, 1e-6, want_norm=False, in_stats=st, in_ln_weight=g2,
+                                  in_ln_bias=bt2, want_stats=True)
+    out = ops.linear_act(x3, Wq, bq, ops.ACT_NONE, in_stats=st2, in_ln_weight=g1, in_ln_bias=bt1)
+    assert torch.equal(x3, x2) and torch.equal(out, ref)
+    torch.testing.assert_close(out.float(), torch.nn.functional.linear(hn.float(), Wq.float(), bq.float()), rtol=2e-2, atol=2e-2)
