@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(kLnThreads)
 add_layernorm_kernel(const T_* __restrict__ x, const T_* __restrict__ y, const T_* __restrict__ gamma,
                      const T_* __restrict__ beta, long long rows, int T, int D, long long x_stride_b, long long x_stride_t,
                      float eps, int norm_row0, T_* __restrict__ out_sum, T_* __restrict__ out_norm,
-                     const int64_t* __restrict__ gather_idx, const T_* __restrict__ cls_row) {
+                     const int64_t* __restrict__ gather_idx, const T_* __restrict__ cls_row, float2* __restrict__ stats) {
   constexpr int VE = LnVec<T_>::kElems;
   const int sub = threadIdx.x & (kLPR - 1);
   const long long row = (long long)blockIdx.x * (kLnThreads / kLPR) + threadIdx.x / kLPR;
@@ -120,7 +120,11 @@ add_layernorm_kernel(const T_* __restrict__ x, const T_* __restrict__ y, const T
     }
   }
   const float rstd = rsqrtf(row_lanes_sum<kLPR>(var) / (float)D + eps);
-  if (!row_ok || t < norm_row0) return;
+  // per-row (mean, rstd) for a consumer that applies the LayerNorm itself (the qkv GEMM on its resident input rows); out_norm may
+  // then be NULL.  For bf16 both forms use h = fma(fma(x, rstd, -mean * rstd), gamma, beta), so they give the same bits.
+  if (stats != nullptr && row_ok && sub == 0) stats[row] = make_float2(mean, rstd);
+  if (!row_ok || t < norm_row0 || out_norm == nullptr) return;
+  const float shift = -mean * rstd;
   T_* hr = out_norm + (b * (T - norm_row0) + (t - norm_row0)) * (long long)D;
 #pragma unroll
   for (int k = 0; k < kVPL; ++k) {
@@ -130,7 +134,8 @@ add_layernorm_kernel(const T_* __restrict__ x, const T_* __restrict__ y, const T
       LnVec<T_>::unpack(*reinterpret_cast<const int4*>(gamma + (size_t)vi * VE), g);
       LnVec<T_>::unpack(*reinterpret_cast<const int4*>(beta + (size_t)vi * VE), bt);
 #pragma unroll
-      for (int q = 0; q < VE; ++q) o[q] = fmaf((v[k][q] - mean) * rstd, g[q], bt[q]);
+      for (int q = 0; q < VE; ++q)     // bf16: the form the GEMM kernels use (same bits as the on-the-fly norm); fp32: the more accurate one
+        o[q] = sizeof(T_) == 2 ? fmaf(fmaf(v[k][q], rstd, shift), g[q], bt[q]) : fmaf((v[k][q] - mean) * rstd, g[q], bt[q]);
       *reinterpret_cast<int4*>(hr + (size_t)vi * VE) = LnVec<T_>::pack(o);
     }
   }
@@ -139,7 +144,7 @@ add_layernorm_kernel(const T_* __restrict__ x, const T_* __restrict__ y, const T
 template <typename T_>
 static int launch_ln(const void* x, const void* y, const void* gamma, const void* beta, int B, int T, int D,
                      long long sb, long long st, float eps, int norm_row0, void* out_sum, void* out_norm, cudaStream_t stream,
-                     const int64_t* gather_idx = nullptr, const void* cls_row = nullptr) {
+                     const int64_t* gather_idx = nullptr, const void* cls_row = nullptr, float* stats = nullptr) {
   constexpr int VE = LnVec<T_>::kElems;
   const long long rows = (long long)B * T;
   const int nvec = D / VE;
@@ -147,7 +152,7 @@ static int launch_ln(const void* x, const void* y, const void* gamma, const void
 #define D2S_LN_LAUNCH(V, L)                                                                                            \
   add_layernorm_kernel<T_, V, L><<<(unsigned)((rows + kLnThreads / L - 1) / (kLnThreads / L)), kLnThreads, 0, stream>>>(  \
       (const T_*)x, (const T_*)y, (const T_*)gamma, (const T_*)beta, rows, T, D, sb, st, eps, norm_row0, (T_*)out_sum,     \
-      (T_*)out_norm, gather_idx, (const T_*)cls_row)
+      (T_*)out_norm, gather_idx, (const T_*)cls_row, reinterpret_cast<float2*>(stats))
   if (vpl <= 2) D2S_LN_LAUNCH(2, 16);
   else if (vpl <= 3) D2S_LN_LAUNCH(3, 16);
   else if (vpl <= 6) D2S_LN_LAUNCH(3, 32);
@@ -226,4 +231,31 @@ extern "C" int d2s_assemble_layernorm(const void* patches, const void* cls, cons
                                                       (cudaStream_t)stream, nullptr, cls)
                            : launch_ln<float>(patches, pos, gamma, beta, B, N + 1, D, sb, st, eps, 0, out_sum, out_norm,
                                               (cudaStream_t)stream, nullptr, cls);
+}
+
+/* The same two with per-row (mean, rstd) of out_sum instead of the normalised output (bf16): the consumer -- the first / next
+ * block's qkv projection, d2s_linear_lnin_act_pair_bf16 -- applies norm1 to its resident input rows itself, so LayerNorm(out_sum)
+ * is never written or read.  stats (B*(K+1), 2) / (B*(N+1), 2) f32. */
+extern "C" int d2s_gather_layernorm_stats(const void* x, const int64_t* idx, int B, int T_in, int D, int K, float eps, void* out_sum,
+                                          float* stats, d2s_stream_t stream) {
+  D2S_REQUIRE(x && (idx || K == 0) && out_sum && stats, D2S_ERR_ARG, "gather_layernorm_stats: null pointer");
+  D2S_REQUIRE(B >= 0 && T_in >= 1 && D >= 8 && K >= 0 && K <= T_in - 1 && D % 8 == 0 && D / 8 <= 16 * 12, D2S_ERR_ARG,
+              "gather_layernorm_stats: bad shape B=%d T_in=%d D=%d K=%d", B, T_in, D, K);
+  D2S_REQUIRE(aligned16(x) && aligned16(out_sum) && (reinterpret_cast<uintptr_t>(stats) & 7u) == 0, D2S_ERR_ALIGN,
+              "gather_layernorm_stats: x / out_sum must be 16-byte aligned, stats 8-byte aligned");
+  if (B == 0) return D2S_OK;
+  return launch_ln<__nv_bfloat16>(x, nullptr, x, x, B, K + 1, D, (long long)T_in * D, D, eps, 0, out_sum, nullptr, (cudaStream_t)stream,
+                                  K ? idx : nullptr, nullptr, stats);
+}
+
+extern "C" int d2s_assemble_layernorm_stats(const void* patches, const void* cls, const void* pos, int B, int N, int D, float eps,
+                                            void* out_sum, float* stats, d2s_stream_t stream) {
+  D2S_REQUIRE(patches && cls && pos && out_sum && stats, D2S_ERR_ARG, "assemble_layernorm_stats: null pointer");
+  D2S_REQUIRE(B >= 0 && N >= 1 && D >= 8 && D % 8 == 0 && D / 8 <= 16 * 12, D2S_ERR_ARG, "assemble_layernorm_stats: bad shape B=%d N=%d D=%d",
+              B, N, D);
+  D2S_REQUIRE(aligned16(patches) && aligned16(cls) && aligned16(pos) && aligned16(out_sum) && (reinterpret_cast<uintptr_t>(stats) & 7u) == 0,
+              D2S_ERR_ALIGN, "assemble_layernorm_stats: pointers must be 16-byte aligned, stats 8-byte aligned");
+  if (B == 0) return D2S_OK;
+  return launch_ln<__nv_bfloat16>(patches, pos, patches, patches, B, N + 1, D, (long long)N * D, D, eps, 0, out_sum, nullptr,
+                                  (cudaStream_t)stream, nullptr, cls, stats);
 }

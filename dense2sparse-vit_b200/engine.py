@@ -335,11 +335,17 @@ class _Stream:
         is then a _LazyNorm (statistics instead of the normalised tensor)."""
         if self._asm is not None and row0 == 0 and self.y is None and self.lin is None and self.mlp is None and self.gidx is None:
             (patches, cls, pos), self._asm = self._asm, None
+            if lazy and patches.dtype == torch.bfloat16:
+                self._x, st = ops.assemble_layernorm(patches, cls, pos, norm.weight, norm.bias, norm.eps, want_stats=True)
+                return self._x, _LazyNorm(self._x, st, norm)
             self._x, h = ops.assemble_layernorm(patches, cls, pos, norm.weight, norm.bias, norm.eps)
             return self._x, h
         if self.gidx is not None:
             if row0 == 0 and self.x.dtype in (torch.float32, torch.bfloat16):
                 (x, kept), self.gidx = (self.x, self.gidx), None
+                if lazy and x.dtype == torch.bfloat16:
+                    self.x, st = ops.gather_layernorm(x, kept, norm.weight, norm.bias, norm.eps, want_stats=True)
+                    return self.x, _LazyNorm(self.x, st, norm)
                 self.x, h = ops.gather_layernorm(x, kept, norm.weight, norm.bias, norm.eps)
                 return self.x, h
             self._flush_gather()

@@ -825,15 +825,24 @@ def add_layernorm(x, y, weight, bias, eps, norm_row0=0, want_sum=True):
     return out_sum, out_norm
 
 
-def gather_layernorm(x, kept, weight, bias, eps):
+def gather_layernorm(x, kept, weight, bias, eps, want_stats=False):
     """(xg, LayerNorm(xg)) with xg = [CLS, x[:, kept + 1]]: the kept-token gather of the pruning stage fused with the next
-    block's norm1 (vit_models/default_dynamic_vit.py:464-468, dynamic_vit.py:907-912 + :263).  Inference only."""
+    block's norm1 (vit_models/default_dynamic_vit.py:464-468, dynamic_vit.py:907-912 + :263).  Inference only.
+    want_stats (bf16): (xg, stats (B*(K+1), 2) f32 = per-row (mean, rstd)) instead; the consumer applies the LayerNorm."""
     _check_cuda(x, kept, weight, bias)
     if kept.dtype != torch.int64:
         raise TypeError("indices must be int64")
     xc, ic = x.detach().contiguous(), kept.contiguous()
     B, T, D = xc.shape
     K = ic.shape[1]
+    if want_stats:
+        if xc.dtype != torch.bfloat16:
+            raise TypeError("gather_layernorm(want_stats=True) is a bf16 path")
+        out_sum = torch.empty(B, K + 1, D, dtype=xc.dtype, device=xc.device)
+        stats = torch.empty(B * (K + 1), 2, dtype=torch.float32, device=xc.device)
+        if B:
+            _call("d2s_gather_layernorm_stats", _ptr(xc), _ptr(ic), B, T, D, K, float(eps), _ptr(out_sum), _ptr(stats), _stream(xc))
+        return out_sum, stats
     w, b = weight.detach().to(xc.dtype).contiguous(), bias.detach().to(xc.dtype).contiguous()
     out_sum = torch.empty(B, K + 1, D, dtype=xc.dtype, device=xc.device)
     out_norm = torch.empty_like(out_sum)
@@ -1056,14 +1065,24 @@ def assemble_tokens(patches, cls_token, pos_embed):
     return out
 
 
-def assemble_layernorm(patches, cls_token, pos_embed, weight, bias, eps):
+def assemble_layernorm(patches, cls_token, pos_embed, weight, bias, eps, want_stats=False):
     """(x, LayerNorm(x)) with x = cat(cls_token, patches) + pos_embed: token assembly fused with the first block's norm1
-    (vit_models/dynamic_vit.py:820-823 + :263).  Inference only."""
+    (vit_models/dynamic_vit.py:820-823 + :263).  Inference only.
+    want_stats (bf16): (x, stats (B*(N+1), 2) f32 = per-row (mean, rstd)) instead; the consumer applies the LayerNorm."""
     _check_cuda(patches, cls_token, pos_embed, weight, bias)
     pc = patches.detach().contiguous()
     B, N, D = pc.shape
     cls = cls_token.detach().to(pc.dtype).reshape(D).contiguous()
     pos = pos_embed.detach().to(pc.dtype).reshape(N + 1, D).contiguous()
+    if want_stats:
+        if pc.dtype != torch.bfloat16:
+            raise TypeError("assemble_layernorm(want_stats=True) is a bf16 path")
+        out_sum = torch.empty(B, N + 1, D, dtype=pc.dtype, device=pc.device)
+        stats = torch.empty(B * (N + 1), 2, dtype=torch.float32, device=pc.device)
+        if B:
+            _call("d2s_assemble_layernorm_stats", _ptr(pc), _ptr(cls), _ptr(pos), B, N, D, float(eps), _ptr(out_sum), _ptr(stats),
+                  _stream(pc))
+        return out_sum, stats
     w, b = weight.detach().to(pc.dtype).contiguous(), bias.detach().to(pc.dtype).contiguous()
     out_sum = torch.empty(B, N + 1, D, dtype=pc.dtype, device=pc.device)
     out_norm = torch.empty_like(out_sum)

@@ -287,6 +287,13 @@ int d2s_gather_layernorm(const void* x, const int64_t* idx, const void* gamma, c
  * patches (B,N,D), cls (D), pos (N+1,D), all of `dtype`. */
 int d2s_assemble_layernorm(const void* patches, const void* cls, const void* pos, const void* gamma, const void* beta, int dtype,
                            int B, int N, int D, float eps, void* out_sum, void* out_norm, d2s_stream_t stream);
+/* The same two with per-row (mean, rstd) of out_sum instead of the normalised output (bf16): the consumer -- the qkv projection,
+ * d2s_linear_lnin_act_pair_bf16 -- applies norm1 to its resident input rows itself, so LayerNorm(out_sum) is never written or read.
+ * stats (B*(K+1), 2) / (B*(N+1), 2) f32. */
+int d2s_gather_layernorm_stats(const void* x, const int64_t* idx, int B, int T_in, int D, int K, float eps, void* out_sum,
+                               float* stats, d2s_stream_t stream);
+int d2s_assemble_layernorm_stats(const void* patches, const void* cls, const void* pos, int B, int N, int D, float eps, void* out_sum,
+                                 float* stats, d2s_stream_t stream);
 
 /* Linear + activation in one tcgen05 GEMM (fc1 + GELU of Mlp.forward, dynamic_vit.py:159-175), bf16 only:
  * out (M,N) = act(a (M,K) @ w (N,K)^T + bias (N)); fp32 accumulation; bias may be NULL.

@@ -1252,7 +1252,8 @@ def test_lazy_norms_are_invisible_at_model_level(d2s, monkeypatch):
             outs.append((logits, [k.clone() for k in m.kept_token_indices], d2s._lib.launch_count() - n0))
     for logits, kept, _ in outs[1:]:
         assert torch.equal(logits, outs[0][0]) and all(torch.equal(p, q) for p, q in zip(kept, outs[0][1]))
-    assert len({n for _, _, n in outs}) == 1                        # same kernels launched, only what they read / write differs
+    ns = [n for _, _, n in outs]                                    # same kernels launched, only what they read / write differs
+    assert max(ns) - min(ns) <= 1, ns                               # (+ the CLS rows' norm2 in front of the CLS-only last MLP)
 
 
 @pytest.mark.parametrize("B,T", [(3, 197), (2, 138), (7, 97), (1, 1), (300, 68)])
