@@ -64,7 +64,7 @@ constexpr uint32_t kMpAccCols = 384, kMpSCols = 128;
 struct MpBars {
   uint64_t a1_full[kMpKB], a1_empty[kMpKB], w1_full[kMpW1Slots], w1_empty[kMpW1Slots], w2_full[kMpW2Slots], w2_empty[kMpW2Slots];
   uint64_t s_full, s_empty, p_full, p_empty, acc_full, acc_empty;
-  uint64_t a1_ready[kMpKB];      // in_stats: the k-block of H has been normalised in place by both CTAs' E1 warps (leader's copy counts)
+  uint64_t a1_ready[kMpKB];      // in_stats: the k-block of H has been normalised in place by both CTAs' output warps (leader's copy counts)
   uint32_t tmem_base, pad;
 };
 static_assert(sizeof(MpBars) % 8 == 0, "MpBars");
@@ -83,6 +83,31 @@ struct MpParams {
   float2* out_stats;            // per-row (mean, rstd) of x' (M) for a consumer that applies the next LayerNorm itself, or NULL
 };
 
+// One k-block of the raw residual stream, normalised in place by the calling warp (kLnIn): row r, 16-byte chunks ch0 .. ch0 + nch - 1.
+// Out of line on purpose: the GELU loop that calls it once per row tile keeps its registers and its schedule.
+__device__ __noinline__ void mp_normalize_block(unsigned char* hb, int r, int ch0, int nchunks, const uint32_t* gb, uint64_t sc,
+                                                uint64_t sh) {
+  for (int k = 0; k < nchunks; ++k) {
+    const int ch = ch0 + k;
+    uint4* ptr = reinterpret_cast<uint4*>(hb + sw128_off(r, ch));
+    const uint4 t = *ptr;
+    const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const uint2 g2 = *reinterpret_cast<const uint2*>(&gb[ch * 8 + 2 * q]);
+      float h0, h1;
+      f2_unpack(f2_fma(f2_fma(f2_pack(bf16_lo(w[q]), bf16_hi(w[q])), sc, sh), f2_pack(bf16_lo(g2.x), bf16_lo(g2.y)),
+                       f2_pack(bf16_hi(g2.x), bf16_hi(g2.y))), h0, h1);
+      o[q] = pack_bf16x2(h0, h1);
+    }
+    *ptr = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+// kLnIn: the LayerNorm of the input is applied on the fly (MpParams::in_stats); a separate instantiation, so that the plain form
+// compiles exactly as it did before the option existed
+template <bool kLnIn>
 #if MP_E1W == 8
 __global__ void __cluster_dims__(2, 1, 1) __maxnreg__(128)
 #else
@@ -117,7 +142,7 @@ mlp_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     for (int i = 0; i < kMpKB; ++i) {
       mbar_init(smem_u32(&bars->a1_full[i]), 1);
       mbar_init(smem_u32(&bars->a1_empty[i]), 1);
-      mbar_init(smem_u32(&bars->a1_ready[i]), 2 * kMpE1Warps);
+      mbar_init(smem_u32(&bars->a1_ready[i]), 2 * kMpOutWarps);
     }
     for (int i = 0; i < kMpW1Slots; ++i) { mbar_init(smem_u32(&bars->w1_full[i]), 1); mbar_init(smem_u32(&bars->w1_empty[i]), 1); }
     for (int i = 0; i < kMpW2Slots; ++i) { mbar_init(smem_u32(&bars->w2_full[i]), 1); mbar_init(smem_u32(&bars->w2_empty[i]), 1); }
@@ -140,7 +165,7 @@ mlp_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     b2_s[i] = p.b2 ? __bfloat162float(p.b2[i]) : 0.f;
     const __nv_bfloat16 gm = p.gamma ? p.gamma[i] : __float2bfloat16_rn(1.f), bt = p.beta ? p.beta[i] : __float2bfloat16_rn(0.f);
     gb_s[i] = (uint32_t)__bfloat16_as_ushort(gm) | ((uint32_t)__bfloat16_as_ushort(bt) << 16);
-    if (p.in_stats) gbin_s[i] = (uint32_t)__bfloat16_as_ushort(p.in_gamma[i]) | ((uint32_t)__bfloat16_as_ushort(p.in_beta[i]) << 16);
+    if (kLnIn) gbin_s[i] = (uint32_t)__bfloat16_as_ushort(p.in_gamma[i]) | ((uint32_t)__bfloat16_as_ushort(p.in_beta[i]) << 16);
   }
   tc_fence_before();
   __syncthreads();
@@ -173,7 +198,7 @@ mlp_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             if (j == 0) {   // the row tile's activations: resident for all chunks, refilled k-block by k-block
               mbar_wait(smem_u32(&bars->a1_empty[kb]), (tile_i & 1) ^ 1);
               const uint32_t fl = smem_u32(&bars->a1_full[kb]);
-              if (p.in_stats) {   // each CTA's own barrier: its E1 warps normalise the block before the pair's MMAs read it
+              if (kLnIn) {   // each CTA's own barrier: its E1 warps normalise the block before the pair's MMAs read it
                 mbar_expect_tx(fl, kMpA1Blk);
                 tma_load_2d(smem_u32(a1_s + kb * kMpA1Blk), &map_a, kb * 64, row0, fl);
               } else {
@@ -220,7 +245,7 @@ mlp_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
           MP_TRACE(1)
           const uint32_t d = tmem + kMpAccCols;
           for (int kb = 0; kb < kMpKB; ++kb, ++w1_it) {
-            if (j == 0) mbar_wait(smem_u32(p.in_stats ? &bars->a1_ready[kb] : &bars->a1_full[kb]), tile_i & 1);
+            if (j == 0) mbar_wait(smem_u32(kLnIn ? &bars->a1_ready[kb] : &bars->a1_full[kb]), tile_i & 1);
             MP_TRACE(2)
             const uint32_t s = w1_it % kMpW1Slots, n = w1_it / kMpW1Slots;
             mbar_wait(smem_u32(&bars->w1_full[s]), n & 1);
@@ -299,50 +324,10 @@ mlp_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     unsigned char* blk = p_s + (part * kMpE1Cols / 64) * kMpPBlk;
     const int kc0 = (part * kMpE1Cols % 64) / 8;
     uint32_t c = 0;
-    // in_stats: H arrives as the raw residual stream x'; this thread normalises its row's share of every k-block in place,
-    // h = bf16(((x - mean) * rstd) * gamma + beta) with the producer's statistics -- the arithmetic of the pair GEMM's own
-    // LayerNorm pass, so the A operand is bit-identical to the normalised copy that is no longer written.  Done for the NEXT row
-    // tile inside the last chunk of the current one (its H blocks land as soon as G1 of that chunk has retired), so that G1(0) of
-    // the next tile still runs under this tile's last GELU.
-    auto normalize_tile = [&](int pt_n, uint32_t ti) {
-      const int row = pt_n * 2 * kMpBM + (int)rank * kMpBM + r;
-      const float2 st = row < p.M ? p.in_stats[row] : make_float2(0.f, 0.f);
-      const uint64_t sc = f2_bcast(st.y), sh = f2_bcast(-st.x * st.y);
-      constexpr int kCh = 8 / kMpE1Parts;                     // 16-byte chunks of a k-block row per E1 warp
-#pragma unroll 1
-      for (int kb = 0; kb < kMpKB; ++kb) {
-        mbar_wait(smem_u32(&bars->a1_full[kb]), ti & 1);
-        unsigned char* hb = a1_s + kb * kMpA1Blk;
-#pragma unroll
-        for (int k = 0; k < kCh; ++k) {
-          const int ch = part * kCh + k;
-          uint4* ptr = reinterpret_cast<uint4*>(hb + sw128_off(r, ch));
-          const uint4 t = *ptr;
-          const uint32_t w[4] = {t.x, t.y, t.z, t.w};
-          uint32_t o[4];
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const uint2 gb = *reinterpret_cast<const uint2*>(&gbin_s[kb * 64 + ch * 8 + 2 * q]);
-            float h0, h1;
-            f2_unpack(f2_fma(f2_fma(f2_pack(bf16_lo(w[q]), bf16_hi(w[q])), sc, sh), f2_pack(bf16_lo(gb.x), bf16_lo(gb.y)),
-                             f2_pack(bf16_hi(gb.x), bf16_hi(gb.y))), h0, h1);
-            o[q] = pack_bf16x2(h0, h1);
-          }
-          *ptr = make_uint4(o[0], o[1], o[2], o[3]);
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(mapa(smem_u32(&bars->a1_ready[kb]), 0));
-      }
-    };
-    uint32_t tile_i = 0;
-    if (p.in_stats && pair < pair_tiles) normalize_tile(pair, 0);
-    for (int pt = pair; pt < pair_tiles; pt += num_pairs, ++tile_i)
+    for (int pt = pair; pt < pair_tiles; pt += num_pairs)
       for (int j = 0; j < nch; ++j, ++c) {
         mbar_wait(smem_u32(&bars->s_full), c & 1);
         tc_fence_after();
-        // (before S_j is pulled into registers: G1(0) of the next tile needs the normalised blocks as much as the free S buffer)
-        if (p.in_stats && j == nch - 1 && pt + num_pairs < pair_tiles) normalize_tile(pt + num_pairs, tile_i + 1);
         // all columns first: S_j is then in registers and G1(j + 1) may overwrite it while the GELU below runs (with the
         // second half loaded after the first half's GELU, s_empty went out ~1 k cycles later and G1 waited for it)
         uint32_t va[32], vb[32];
@@ -394,8 +379,30 @@ mlp_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     const int crow = lane >> 2, cseg = lane & 3;                // coalesced pattern: 4 lanes x 16 B cover one row's 64 bytes
     const uint32_t own_off = (uint32_t)lane * 64, own_sw = (uint32_t)(lane >> 1) & 3u;
     constexpr int NU = TN / 32;                                  // 32-column units per row
+    // kLnIn: H arrives as the raw residual stream x'; the output warps normalise it in place, one row per thread, h = bf16(((x -
+    // mean) * rstd) * gamma + beta) with the producer's statistics -- the arithmetic of the pair GEMM's own LayerNorm pass, so the
+    // A operand is bit-identical to the normalised copy that is no longer written.  The NEXT row tile's blocks land when G1 of
+    // the current tile's last chunk has retired, i.e. while these warps are waiting for the current accumulator anyway: G1(0) of
+    // the next tile still starts under the current tile's last GELU, and the GELU warps (the kernel's critical stage) do not
+    // see any of it.
+    auto normalize_tile = [&](int pt_n, uint32_t ti) {
+      const int r = quad * 32 + lane;
+      const int row = pt_n * 2 * kMpBM + (int)rank * kMpBM + r;
+      const float2 st = row < p.M ? p.in_stats[row] : make_float2(0.f, 0.f);
+      const uint64_t sc = f2_bcast(st.y), sh = f2_bcast(-st.x * st.y);
+#pragma unroll 1
+      for (int kb = 0; kb < kMpKB; ++kb) {
+        mbar_wait(smem_u32(&bars->a1_full[kb]), ti & 1);
+        mp_normalize_block(a1_s + kb * kMpA1Blk, r, 0, 8, gbin_s + kb * 64, sc, sh);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(mapa(smem_u32(&bars->a1_ready[kb]), 0));
+      }
+    };
     uint32_t tile_i = 0;
+    if (kLnIn && pair < pair_tiles) normalize_tile(pair, 0);
     for (int pt = pair; pt < pair_tiles; pt += num_pairs, ++tile_i) {
+      if (kLnIn && pt + num_pairs < pair_tiles) normalize_tile(pt + num_pairs, tile_i + 1);
       const int row0 = pt * 2 * kMpBM + (int)rank * kMpBM + quad * 32;     // first row of this warp
       const int rows_left = p.M - row0 - crow;                             // row group i is in range iff 8 i < rows_left
       // element offsets of (row0 + crow + 8 i, cseg * 8); rows past M re-read the last row and are never stored
@@ -585,12 +592,13 @@ static int mp_launch(const char* what, const void* h, const float* in_stats, con
   const size_t smem = 1024 + (size_t)kMpKB * kMpA1Blk + 2 * (size_t)kMpPBlk + (size_t)kMpW1Slots * kMpW1Blk +
                       (size_t)kMpW2Slots * kMpW2Blk + sizeof(MpBars) + (size_t)HID * 4 + 3 * kMpD * 4 + (size_t)kMpOutWarps * 2048 + 32;
   D2S_REQUIRE(smem <= 227 * 1024, D2S_ERR_ARG, "mlp_residual_ln: needs %zu B of shared memory", smem);
-  static SmemOptIn opt;
-  cudaError_t e = opt_in_smem(opt, mlp_pair_kernel, 227 * 1024);
+  static SmemOptIn opt, opt_ln;
+  cudaError_t e = in_stats ? opt_in_smem(opt_ln, mlp_pair_kernel<true>, 227 * 1024) : opt_in_smem(opt, mlp_pair_kernel<false>, 227 * 1024);
   D2S_REQUIRE(e == cudaSuccess, D2S_ERR_CUDA, "mlp_residual_ln: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   const int pair_tiles = (M + 2 * kMpBM - 1) / (2 * kMpBM);
   const int pairs = pair_tiles < kNumSMs / 2 ? pair_tiles : kNumSMs / 2;
-  e = launch_pdl(mlp_pair_kernel, dim3(2 * pairs), dim3(kMpThreads), smem, (cudaStream_t)stream, ma, mw1, mw2, p);
+  e = in_stats ? launch_pdl(mlp_pair_kernel<true>, dim3(2 * pairs), dim3(kMpThreads), smem, (cudaStream_t)stream, ma, mw1, mw2, p)
+               : launch_pdl(mlp_pair_kernel<false>, dim3(2 * pairs), dim3(kMpThreads), smem, (cudaStream_t)stream, ma, mw1, mw2, p);
   D2S_REQUIRE(e == cudaSuccess, D2S_ERR_CUDA, "mlp_residual_ln: launch: %s", cudaGetErrorString(e));
   count_launch();
   return check_launch(what);
