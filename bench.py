@@ -324,8 +324,12 @@ def kernel_breakdown(ops, B, dev, torch, pk):
         # qkv projection on the CTA-pair GEMM (192-column tiles, input rows resident): write-bound, 3 of its 4 (B,T,D) units are stores
         wq, bq = torch.randn(3 * D, D, device=dev, dtype=bf) * 0.05, torch.zeros(3 * D, device=dev, dtype=bf)
         by, fl = B * T * e * 4 * D, 2.0 * B * T * D * 3 * D
-        ms = time_graphed([lambda x=x: ops.linear_act(x, wq, bq, ops.ACT_NONE) for x, _ in xs], torch, launches=12)
-        rows.append(row("linear_act(qkv projection, tcgen05 pair, 192-column tiles)", f"M={B * T},N={3 * D},K={D}", ms, by, 3, fl))
+        sts_q = [torch.stack([x.float().mean(-1), torch.rsqrt(x.float().var(-1, unbiased=False) + 1e-6)], -1).reshape(-1, 2).contiguous()
+                 for x, _ in xs]
+        ms = time_graphed([lambda x=x, st=st: ops.linear_act(x, wq, bq, ops.ACT_NONE, in_stats=st, in_ln_weight=gw, in_ln_bias=gb)
+                           for (x, _), st in zip(xs, sts_q)], torch, launches=12)
+        rows.append(row("linear_act(norm1 + qkv projection, tcgen05 pair, 192-column tiles)", f"M={B * T},N={3 * D},K={D}", ms, by, 3, fl))
+        del sts_q
         # attn.proj + residual; norm2 is NOT materialised: the kernel writes x' and per-row (mean, rstd), the MLP kernel applies the norm
         by, fl = B * T * (e * 3 * D + 8), 2.0 * B * T * D * D
         ms = time_graphed([lambda x=x, y=y: ops.linear_residual_ln(y, wp, gb, x, eps=1e-6, want_norm=False, want_stats=True) for x, y in xs],
@@ -336,10 +340,12 @@ def kernel_breakdown(ops, B, dev, torch, pk):
         # kernel, tensor-bound (4.7 MFLOP per token against 2.3 KB of HBM traffic: x' in (also the residual), x'' and hn out)
         sts = [torch.stack([x.float().mean(-1), torch.rsqrt(x.float().var(-1, unbiased=False) + 1e-6)], -1).reshape(-1, 2).contiguous()
                for x, _ in xs]
-        by, fl = B * T * (e * 3 * D + 8), 4.0 * B * T * D * 4 * D
-        ms = time_graphed([lambda x=x, st=st: ops.mlp_residual_ln(None, w1, b1, w2, gb, x, gw, gb, 1e-6, in_stats=st, in_ln_weight=gw,
-                                                                  in_ln_bias=gb) for (x, _), st in zip(xs, sts)], torch, launches=8)
-        rows.append(row("mlp_residual_ln(norm2+fc1+GELU+fc2+add+LN, tcgen05 pair)", f"M={B * T},D={D},HID={4 * D}", ms, by, 2, fl))
+        # (x' and its statistics in, x'' and ITS statistics out: the next norm1 is applied by the qkv GEMM)
+        by, fl = B * T * (e * 2 * D + 16), 4.0 * B * T * D * 4 * D
+        ms = time_graphed([lambda x=x, st=st: ops.mlp_residual_ln(None, w1, b1, w2, gb, x, None, None, 1e-6, want_norm=False, in_stats=st,
+                                                                  in_ln_weight=gw, in_ln_bias=gb, want_stats=True)
+                           for (x, _), st in zip(xs, sts)], torch, launches=8)
+        rows.append(row("mlp_residual_ln(norm2+fc1+GELU+fc2+add+row statistics, tcgen05 pair)", f"M={B * T},D={D},HID={4 * D}", ms, by, 2, fl))
         acc("mlp", ms, by, fl, 2)
         if gi < 3:   # the block in front of a pruning stage: the LayerNorm is the predictor's, over x[:, 1:]
             ms = time_graphed([lambda x=x, st=st: ops.mlp_residual_ln(None, w1, b1, w2, gb, x, gw, gb, 1e-6, norm_row0=1, in_stats=st,

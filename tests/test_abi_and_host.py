@@ -297,4 +297,6 @@ def test_traffic_json_is_reproducible_from_the_committed_ncu_capture(tmp_path):
                    check=True, capture_output=True)
     assert json.load(open(out)) == committed
     k = committed["mlp_pair_kernel"]
-    assert k["launches_per_step"] == 11 and 0.5 < k["dram_bytes_per_step"] / (11 * 409.3e6) < 1.2    # at most the algorithmic bytes
+    # algorithmic bytes per launch, averaged over the step's 11 launches: (B,T,D) bf16 in and out (+ the predictor norm in 3 of
+    # them) = 2.27 / 4 of the 409.3 MB the kernel moved while it still read a normalised copy and wrote the next one
+    assert k["launches_per_step"] == 11 and 0.35 < k["dram_bytes_per_step"] / (11 * 409.3e6) < 0.7
