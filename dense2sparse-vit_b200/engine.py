@@ -604,8 +604,9 @@ def _predictor_b_fusable(m, dtype):
 
 def _linear_act(x, lin, act):
     """act(lin(x)): the tcgen05 GEMM with the activation in its epilogue when the shape allows, else cuBLAS + in-place act."""
-    if (_FUSED_PAIR and x.dtype == torch.bfloat16 and lin.weight.dtype == torch.bfloat16 and lin.out_features % 256 == 0
-            and lin.out_features <= 4096 and lin.in_features % 64 == 0):
+    if (_FUSED_PAIR and x.dtype == torch.bfloat16 and lin.weight.dtype == torch.bfloat16
+            and (lin.out_features % 256 == 0 or lin.out_features % 192 == 0) and 192 <= lin.out_features <= 4096
+            and lin.in_features % 64 == 0):
         return ops.linear_act(x, lin.weight, lin.bias, act)
     u = lin(x)
     return ops.bias_act_(u, None, act)
