@@ -51,7 +51,8 @@ SIGNATURES = {
     "d2s_pool_act": [_p, _p, _i, _i, _i, _i, _i, _p, _p, _p],
     "d2s_bias_act": [_p, _p, _i, ctypes.c_longlong, _i, _i, _i, _p],
     "d2s_pool_concat_inplace": [_p, _i, _i, _i, _i, _p],
-    "d2s_predictor_a_tail_bf16": [_p, _i, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p],
+    "d2s_predictor_a_tail_bf16": [_p, _i, ctypes.c_longlong, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p],
+    "d2s_pool_strided_bf16": [_p, _p, _i, _i, _i, ctypes.c_longlong, _i, _p, _p],
     "d2s_pool_concat_fwd": [_p, _p, _i, _i, _i, _i, _p, _p, _p, _p],
     "d2s_pool_concat_bwd": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p],
     "d2s_assemble_tokens": [_p, _p, _p, _i, _i, _i, _i, _p, _p],

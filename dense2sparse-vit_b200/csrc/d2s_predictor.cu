@@ -87,7 +87,7 @@ constexpr int kPoolThreads = D2S_POOL_THREADS;
 template <typename T_>
 __global__ void __launch_bounds__(kPoolThreads)
 pool_act_kernel(const T_* __restrict__ z, const float* __restrict__ policy, int N, int C, int act,
-                T_* __restrict__ local, T_* __restrict__ pooled) {
+                T_* __restrict__ local, T_* __restrict__ pooled, long long zbs) {
   constexpr int VE = PVec<T_>::kElems;
   extern __shared__ float red[];  // groups x (C/2) partial sums, then groups partial policy sums
   const int b = blockIdx.x;
@@ -127,7 +127,7 @@ pool_act_kernel(const T_* __restrict__ z, const float* __restrict__ policy, int 
         if (v == half_vec) psum += p;
       }
     };
-    const T_* zb = z + (size_t)b * N * C + (size_t)v * VE;
+    const T_* zb = z + (size_t)b * zbs + (size_t)v * VE;          // zbs: elements between images (N * C when dense)
     int n = g;
     for (; n + 3 * groups < N; n += 4 * groups) {      // four token rows in flight per thread
       const int4 r0 = ld_stream16(zb + (size_t)n * C);
@@ -459,12 +459,31 @@ extern "C" int d2s_pool_act(const void* z, const float* policy, int dtype, int B
   const size_t smem = ((size_t)groups * (C / 2) + groups) * sizeof(float);
   if (dtype == D2S_BF16)
     pool_act_kernel<__nv_bfloat16><<<B, kPoolThreads, smem, (cudaStream_t)stream>>>(
-        (const __nv_bfloat16*)z, policy, N, C, act, (__nv_bfloat16*)local, (__nv_bfloat16*)pooled);
+        (const __nv_bfloat16*)z, policy, N, C, act, (__nv_bfloat16*)local, (__nv_bfloat16*)pooled, (long long)N * C);
   else
     pool_act_kernel<float><<<B, kPoolThreads, smem, (cudaStream_t)stream>>>((const float*)z, policy, N, C, act,
-                                                                           (float*)local, (float*)pooled);
+                                                                           (float*)local, (float*)pooled, (long long)N * C);
   count_launch();
   return check_launch("d2s_pool_act");
+}
+
+/* pooled only, over a row slice of a wider tensor: z points at the first pooled row of image 0, images are z_batch_stride elements
+ * apart (e.g. x[:, 1:] of a (B, N + 1, C) tensor: z = x + C, z_batch_stride = (N + 1) * C).  bf16. */
+extern "C" int d2s_pool_strided_bf16(const void* z, const float* policy, int B, int N, int C, long long z_batch_stride, int act,
+                                     void* pooled, d2s_stream_t stream) {
+  D2S_REQUIRE(z && pooled, D2S_ERR_ARG, "pool_strided: null pointer");
+  D2S_REQUIRE(B >= 0 && N >= 1 && C >= 16 && C % 16 == 0 && C / 8 <= kPoolThreads, D2S_ERR_ARG, "pool_strided: bad shape B=%d N=%d C=%d", B, N, C);
+  D2S_REQUIRE(z_batch_stride >= (long long)N * C && z_batch_stride % 8 == 0, D2S_ERR_ARG,
+              "pool_strided: z_batch_stride=%lld must be a multiple of 8, at least N * C", z_batch_stride);
+  D2S_REQUIRE(act >= D2S_ACT_NONE && act <= D2S_ACT_RELU, D2S_ERR_ARG, "pool_strided: bad activation %d", act);
+  D2S_REQUIRE(aligned16(z), D2S_ERR_ALIGN, "pool_strided: z must be 16-byte aligned");
+  if (B == 0) return D2S_OK;
+  const int groups = kPoolThreads / (C / 8 / 2);
+  const size_t smem = ((size_t)groups * (C / 2) + groups) * sizeof(float);
+  pool_act_kernel<__nv_bfloat16><<<B, kPoolThreads, smem, (cudaStream_t)stream>>>((const __nv_bfloat16*)z, policy, N, C, act, nullptr,
+                                                                                 (__nv_bfloat16*)pooled, z_batch_stride);
+  count_launch();
+  return check_launch("d2s_pool_strided_bf16");
 }
 
 extern "C" int d2s_pool_concat_inplace(void* z, int dtype, int B, int N, int C, d2s_stream_t stream) {

@@ -371,7 +371,7 @@ static int pf_map(CUtensorMap* map, const void* base, int rank, const cuuint64_t
 
 using namespace d2s;
 
-extern "C" int d2s_predictor_a_tail_bf16(const void* local, int ld, const void* per_image, const void* w2, const void* w3,
+extern "C" int d2s_predictor_a_tail_bf16(const void* local, int ld, long long lb, const void* per_image, const void* w2, const void* w3,
                                          const void* b3, const float* w4, const float* b4, const float* prev, int B, int N, int H,
                                          int K, float* logp, int64_t* kept, float* prev_kept, d2s_stream_t stream) {
   const char* what = "d2s_predictor_a_tail_bf16";
@@ -380,6 +380,8 @@ extern "C" int d2s_predictor_a_tail_bf16(const void* local, int ld, const void* 
   D2S_REQUIRE(B >= 0 && N >= 1 && N <= kPfMaxN, D2S_ERR_ARG, "predictor_a_tail: N=%d outside [1,%d]", N, kPfMaxN);
   D2S_REQUIRE(K >= 0 && K <= N, D2S_ERR_ARG, "predictor_a_tail: K=%d outside [0,N=%d]", K, N);
   D2S_REQUIRE(ld >= H && ld % 8 == 0, D2S_ERR_ARG, "predictor_a_tail: row stride ld=%d must be a multiple of 8 elements, at least H=%d", ld, H);
+  D2S_REQUIRE(lb >= (long long)N * ld && lb % 8 == 0, D2S_ERR_ARG,
+              "predictor_a_tail: batch stride lb=%lld must be a multiple of 8 elements, at least N * ld", lb);
   D2S_REQUIRE(aligned16(local) && aligned16(per_image) && aligned16(w2) && aligned16(w3) && aligned16(logp), D2S_ERR_ALIGN,
               "predictor_a_tail: local / per_image / weights / logp must be 16-byte aligned");
   if (B == 0) return D2S_OK;
@@ -387,7 +389,7 @@ extern "C" int d2s_predictor_a_tail_bf16(const void* local, int ld, const void* 
   int rc;
   {
     const cuuint64_t gdim[3] = {(cuuint64_t)H, (cuuint64_t)N, (cuuint64_t)B};
-    const cuuint64_t gstr[2] = {(cuuint64_t)ld * 2, (cuuint64_t)N * ld * 2};
+    const cuuint64_t gstr[2] = {(cuuint64_t)ld * 2, (cuuint64_t)lb * 2};
     const cuuint32_t box[3] = {64, 128, 1};
     if ((rc = pf_map(&mx, local, 3, gdim, gstr, box, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, what))) return rc;
   }

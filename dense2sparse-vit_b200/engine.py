@@ -26,6 +26,7 @@ _FROZEN_BF16 = os.environ.get("D2S_FROZEN_BF16", "1") != "0"   # A/B switch: cac
 _FUSED_ADD_LN_TRAIN = os.environ.get("D2S_FUSED_ADD_LN_TRAIN", "1") != "0"   # A/B switch: residual adds folded into LayerNorm fwd/bwd
 _FUSED_MLP = os.environ.get("D2S_FUSED_MLP", "1") != "0"      # A/B switch for the one-kernel MLP (ops.mlp_residual_ln)
 _FUSED_PAIR = os.environ.get("D2S_FUSED_PAIR", "1") != "0"  # A/B switch for the CTA-pair GEMMs (fc1 pair; proj/fc2 + add + LN)
+_LAZY_PRED = os.environ.get("D2S_LAZY_PRED", "1") != "0"    # A/B switch: the predictors' input norm applied inside their first GEMM (row statistics)
 _LAZY_NORM1 = os.environ.get("D2S_LAZY_NORM1", "1") != "0"  # A/B switch: norm1 applied inside the qkv GEMM from the MLP kernel's row statistics
 _LAZY_NORM2 = os.environ.get("D2S_LAZY_NORM2", "1") != "0"  # A/B switch: norm2 applied inside the one-kernel MLP from per-row statistics (no normalised copy)
 _QKV_PAIR = os.environ.get("D2S_QKV_PAIR", "1") != "0"     # A/B switch: inference qkv projection on the CTA-pair tcgen05 GEMM (else the library GEMM)
@@ -254,13 +255,14 @@ class _LazyNorm:
     its input tile in shared memory (ops.mlp_residual_ln(in_stats=...)): the normalised copy -- a quarter of the proj + residual +
     LayerNorm kernel's traffic -- is never written or read.  Any other consumer materialises what it needs."""
 
-    def __init__(self, x, stats, norm):
-        self.x, self.stats, self.norm = x, stats, norm
+    def __init__(self, x, stats, norm, row0=0):
+        # row0 > 0: the norm is taken over x[:, row0:] (the predictors' input norm); stats still cover every row of x
+        self.x, self.stats, self.norm, self.row0 = x, stats, norm, row0
         self.dtype, self.shape, self.is_cuda, self.requires_grad = x.dtype, x.shape, x.is_cuda, False
 
     def value(self):
         n = self.norm
-        return ops.add_layernorm(self.x, None, n.weight, n.bias, n.eps, want_sum=False)[1]
+        return ops.add_layernorm(self.x, None, n.weight, n.bias, n.eps, norm_row0=self.row0, want_sum=False)[1]
 
     def cls_rows(self):
         n = self.norm
@@ -353,12 +355,12 @@ class _Stream:
             h, m = self.mlp
             if _mlp_fused_ok(m, h, self.x):
                 self.mlp = None
-                if isinstance(h, _LazyNorm) and h.x is self.x and lazy and row0 == 0:
+                if isinstance(h, _LazyNorm) and h.x is self.x and lazy:
                     # ... and the NEXT norm handed on as statistics too (its only reader is the qkv GEMM)
                     self.x, st = ops.mlp_residual_ln(None, m.fc1.weight, m.fc1.bias, m.fc2.weight, m.fc2.bias, self.x, eps=norm.eps,
                                                      want_norm=False, in_stats=h.stats, in_ln_weight=h.norm.weight,
                                                      in_ln_bias=h.norm.bias, want_stats=True)
-                    return self.x, _LazyNorm(self.x, st, norm)
+                    return self.x, _LazyNorm(self.x, st, norm, row0)
                 if isinstance(h, _LazyNorm) and h.x is self.x:      # norm2 applied inside the kernel, from its statistics
                     self.x, hn = ops.mlp_residual_ln(None, m.fc1.weight, m.fc1.bias, m.fc2.weight, m.fc2.bias, self.x,
                                                      norm.weight, norm.bias, norm.eps, norm_row0=row0, in_stats=h.stats,
@@ -432,11 +434,12 @@ class _Stream:
         self.x = out
         return None
 
-    def normed(self, norm, row0=0, rows=None):
-        """(x + y, norm((x + y)[:, row0:])) with the add folded in; leaves the stream holding the summed x."""
+    def normed(self, norm, row0=0, rows=None, lazy=False):
+        """(x + y, norm((x + y)[:, row0:])) with the add folded in; leaves the stream holding the summed x.
+        lazy: the caller can take a _LazyNorm (row statistics; it applies the norm inside its first GEMM)."""
         if (_is_plain_ln(norm) and self.x.is_cuda and _d2s_float(self.x) and _ln_rows_ok(self.x)
                 and not _needs_grad(self.x, self.y, norm.weight)):
-            return self._sum_norm(norm, row0)
+            return self._sum_norm(norm, row0, lazy=lazy and row0 > 0 and self.mlp is not None)
         x = self.value()
         return x, norm(x[:, row0:])
 
@@ -527,6 +530,14 @@ def _predictor_a_fusable(m):
             and oc[4].in_features % 8 == 0 and 8 <= oc[4].in_features <= 1024)
 
 
+def _predictor_a_gemm_ok(m, x):
+    """in_conv's Linear(D,D) + GELU runs on the pair GEMM with its input LayerNorm applied inside (bf16, D = 384)."""
+    l1 = m.in_conv[1]
+    return (_PRED_FUSED and _FUSED_PAIR and _predictor_a_fusable(m) and x.is_cuda and x.dtype == torch.bfloat16
+            and l1.weight.dtype == torch.bfloat16 and l1.in_features == 384 and l1.out_features == 384 and l1.bias is not None
+            and m.in_conv[0].weight.dtype == torch.bfloat16)
+
+
 def predictor_a_select(m, normed, prev, k):
     """Inference form of PredictorLG.forward + selection (default_dynamic_vit.py:324-330, :461-467) without the
     GELU / multiply / reduce / expand / concat passes: `normed` = in_conv's LayerNorm output (from the fused
@@ -535,6 +546,18 @@ def predictor_a_select(m, normed, prev, k):
     l1, l0, l2, lin = m.in_conv[1], m.out_conv[0], m.out_conv[2], m.out_conv[4]
     half = l0.in_features // 2
     tail_ok = _PRED_FUSED and l0.bias is not None and l2.bias is not None and lin.bias is not None
+    if isinstance(normed, _LazyNorm):
+        if tail_ok and _predictor_a_gemm_ok(m, normed.x):
+            # in_conv's LayerNorm was not materialised: Linear(D,D) + GELU normalises its resident input rows from the row statistics
+            # (over every token of x: the GEMM's rows must be dense; the CLS rows' results are simply not read)
+            ln = m.in_conv[0]
+            g = ops.linear_act(normed.x, l1.weight, l1.bias, ops.ACT_GELU, in_stats=normed.stats, in_ln_weight=ln.weight,
+                               in_ln_bias=ln.bias)[:, normed.row0:]
+            if ops.predictor_a_tail_ok(g[:, :, :half], l0.weight, l2.weight, lin.weight):
+                _, pooled = ops.pool_act(g, prev, ops.ACT_NONE, want_local=False)
+                per_image = F.linear(pooled, l0.weight[:, half:], l0.bias)
+                return ops.predictor_a_tail(g[:, :, :half], per_image, l0.weight, l2.weight, l2.bias, lin.weight, lin.bias, k, prev=prev)
+        normed = normed.value()
     if (tail_ok and _FUSED_PAIR and normed.dtype == torch.bfloat16 and l1.weight.dtype == torch.bfloat16
             and l1.out_features % 192 == 0 and l1.in_features % 64 == 0
             and ops.predictor_a_tail_ok(normed[:, :, :half], l0.weight, l2.weight, lin.weight)):
@@ -722,7 +745,7 @@ def variant_a_forward(model, img):
                 if (ln is not None and _predictor_a_fusable(pred) and st._probe().is_cuda and _d2s_float(st._probe())
                         and not _needs_grad(st.x, st.y, ln.weight)):
                     # residual add folded into the predictor's LayerNorm over x[:, 1:]; fused predictor body
-                    x, hn = st.normed(ln, row0=1)
+                    x, hn = st.normed(ln, row0=1, lazy=_LAZY_PRED and _LAZY_NORM1 and _predictor_a_gemm_ok(pred, st._probe()))
                     _, keep_policy, prev_f32 = predictor_a_select(pred, hn, prev_f32, k)
                     prev_decision = None                 # materialised on demand below
                 else:

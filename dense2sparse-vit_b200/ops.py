@@ -860,8 +860,16 @@ def pool_act(z, policy=None, act=ACT_GELU, want_local=True):
     act(z[..., C/2:])) in one pass (vit_models/default_dynamic_vit.py:325-328; dynamic_vit.py:538-542).
     want_local=False: (None, pooled) -- z is already activated and its local half is consumed in place by the next kernel."""
     _check_cuda(z, policy)
-    zc = z.detach().contiguous()
-    B, N, C = zc.shape
+    zd = z.detach()
+    B, N, C = zd.shape
+    if (not want_local and zd.dtype == torch.bfloat16 and not zd.is_contiguous() and B > 1 and N > 1 and zd.stride(2) == 1
+            and zd.stride(1) == C and zd.stride(0) >= N * C and zd.stride(0) % 8 == 0 and zd.data_ptr() % 16 == 0 and C % 16 == 0):
+        # a row slice of a wider tensor (x[:, 1:]): pooled in place through the batch stride
+        pol = _f32c(policy.reshape(B, N)) if policy is not None else None
+        pooled = torch.empty(B, C // 2, dtype=zd.dtype, device=zd.device)
+        _call("d2s_pool_strided_bf16", _ptr(zd), _ptr(pol), B, N, C, zd.stride(0), int(act), _ptr(pooled), _stream(zd))
+        return None, pooled
+    zc = zd.contiguous()
     pol = _f32c(policy.reshape(B, N)) if policy is not None else None
     local = torch.empty(B, N, C // 2, dtype=zc.dtype, device=zc.device) if want_local else None
     pooled = torch.empty(B, C // 2, dtype=zc.dtype, device=zc.device)
@@ -932,10 +940,10 @@ def predictor_a_tail(local, per_image, w2, w3, b3, w4, b4, k, prev=None, want_pr
     h = local.detach()
     B, N, H = h.shape
     # a column slice of a wider contiguous (B, N, ld) tensor is read in place through the tensor map's row stride
-    if not (h.stride(2) == 1 and h.stride(1) % 8 == 0 and h.stride(1) >= H and (B <= 1 or h.stride(0) == N * h.stride(1))
-            and h.data_ptr() % 16 == 0):
+    if not (h.stride(2) == 1 and h.stride(1) % 8 == 0 and h.stride(1) >= H and N > 1 and B > 1 and h.stride(0) >= N * h.stride(1)
+            and h.stride(0) % 8 == 0 and h.data_ptr() % 16 == 0):
         h = h.contiguous()
-    ld = h.stride(1) if N > 1 else H
+    ld, lb = h.stride(1), h.stride(0)
     pl = per_image.detach().to(torch.bfloat16).contiguous()
     if not 0 <= k <= N:
         raise RuntimeError(f"predictor_a_tail: K={k} outside [0, N={N}]")
@@ -950,7 +958,7 @@ def predictor_a_tail(local, per_image, w2, w3, b3, w4, b4, k, prev=None, want_pr
     p = _f32c(prev.reshape(B, N)) if prev is not None else None
     b3c = b3.detach().to(torch.bfloat16).contiguous()
     w4f, b4f = _f32c_param(w4), _f32c_param(b4)
-    _call("d2s_predictor_a_tail_bf16", _ptr(h), int(ld), _ptr(pl), _ptr(w2.detach()), _ptr(w3.detach()), _ptr(b3c),
+    _call("d2s_predictor_a_tail_bf16", _ptr(h), int(ld), int(lb), _ptr(pl), _ptr(w2.detach()), _ptr(w3.detach()), _ptr(b3c),
           _ptr(w4f), _ptr(b4f), _ptr(p), B, N, H, k, _ptr(logp), _ptr(kept), _ptr(prev_kept), _stream(h))
     return (logp, kept, prev_kept) if want_prev_kept else (logp, kept)
 

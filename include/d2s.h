@@ -223,17 +223,22 @@ int d2s_attn_policy_bwd(const void* qkv, const float* policy, const void* out, c
 int d2s_pool_act(const void* z, const float* policy, int dtype, int B, int N, int C, int act, void* local, void* pooled,
                  d2s_stream_t stream);
 int d2s_bias_act(void* u, const void* bias, int dtype, long long rows, int N, int C, int act, d2s_stream_t stream);
+/* pooled only, over a row slice of a wider bf16 tensor: z points at the first pooled row of image 0, images are z_batch_stride
+ * elements apart (x[:, 1:] of a (B,N+1,C) tensor: z = x + C, z_batch_stride = (N+1)*C). */
+int d2s_pool_strided_bf16(const void* z, const float* policy, int B, int N, int C, long long z_batch_stride, int act, void* pooled,
+                          d2s_stream_t stream);
 /* The second half of the Variant-A predictor of one pruning stage as ONE tcgen05 kernel (bf16, D == 384; PredictorLG.forward,
  * default_dynamic_vit.py:329-330 = out_conv on cat(local, pooled.expand), fused with the stage's selection, :461-467):
  * Linear(D,D/2) + GELU (split as local @ W2[:, :D/2]^T + per_image, per_image = pooled @ W2[:, D/2:]^T + b2), Linear(D/2,D/4) +
  * GELU, Linear(D/4,2), LogSoftmax and the stable descending top-K -- replaces two library GEMMs, d2s_bias_act and d2s_score_tail_a.
  *   local (B,N,H) bf16 (H = D/2 = 192) with a row stride of ld elements (ld = H: dense, as written by d2s_pool_act; ld = 2H: the
- *   first half of every row of the (B,N,D) Linear + GELU output, read in place), per_image (B,H) bf16; w2 (H,2H) (only its first H columns
+ *   first half of every row of the (B,N,D) Linear + GELU output, read in place) and a batch stride of lb elements (N * ld when
+ *   dense; (N + 1) * ld for the rows 1.. of a (B,N+1,D) tensor), per_image (B,H) bf16; w2 (H,2H) (only its first H columns
  *   are read), w3 (H/2,H) bf16 row-major as nn.Linear stores them, b3 bf16; w4 (2,H/2), b4 (2) f32; prev (B,N) f32 keep
  *   decisions or NULL (all ones);
  *   logp (B,N,2) f32, kept (B,K) int64 in descending-score order (ties: lower index first), prev_kept (B,K) f32 =
  *   prev gathered at kept (NULL to skip).  N <= 256.  The hidden activations never touch HBM. */
-int d2s_predictor_a_tail_bf16(const void* local, int ld, const void* per_image, const void* w2, const void* w3, const void* b3,
+int d2s_predictor_a_tail_bf16(const void* local, int ld, long long lb, const void* per_image, const void* w2, const void* w3, const void* b3,
                               const float* w4, const float* b4, const float* prev, int B, int N, int H, int K,
                               float* logp, int64_t* kept, float* prev_kept, d2s_stream_t stream);
 /* Variant B's concat (dynamic_vit.py:539-545) in place: z (B,N,C) <- cat(z[:,:,:C/2], mean_n(z[:,:,C/2:]).expand). */

@@ -261,7 +261,7 @@ def test_predictor_tail_kernel_stays_in_bounds(d2s, B, N, K):
     outs = []
     for _ in range(2):
         logp, kept, pk = Guarded((B, N, 2), torch.float32), Guarded((B, K), torch.int64), Guarded((B, K), torch.float32)
-        lib.call("d2s_predictor_a_tail_bf16", local.ptr, H, per_image.ptr, w2.ptr, w3.ptr, b3.ptr, w4.ptr, b4.ptr, prev.ptr, B, N, H, K,
+        lib.call("d2s_predictor_a_tail_bf16", local.ptr, H, N * H, per_image.ptr, w2.ptr, w3.ptr, b3.ptr, w4.ptr, b4.ptr, prev.ptr, B, N, H, K,
                  logp.ptr, kept.ptr, pk.ptr, _stream())
         torch.cuda.synchronize()
         for name, gd in [("logp", logp), ("kept", kept), ("prev_kept", pk), ("local", local), ("per_image", per_image), ("w2", w2),

@@ -1277,3 +1277,19 @@ def test_qkv_gemm_applies_norm1_from_the_mlp_kernels_row_statistics(ops, B, T):
     out = ops.linear_act(x3, Wq, bq, ops.ACT_NONE, in_stats=st2, in_ln_weight=g1, in_ln_bias=bt1)
     assert torch.equal(x3, x2) and torch.equal(out, ref)
     torch.testing.assert_close(out.float(), torch.nn.functional.linear(hn.float(), Wq.float(), bq.float()), rtol=2e-2, atol=2e-2)
+
+
+def test_pool_and_tail_kernels_read_a_row_slice_in_place(ops):
+    """x[:, 1:] of a (B, N + 1, 384) tensor (the predictor's Linear + GELU output over every token, CLS row included): the pooled
+    rows and the tail kernel's results through the batch stride are identical to those on a dense copy of the slice."""
+    B, N, K, C = 5, 196, 137, 384
+    local, per_image, w2, w3, b3, w4, b4, prev = _tail_inputs(B, N, 1200)
+    wide = cu(torch.cat([fx.randn(1201, B, N + 1, 192).bfloat16(), fx.randn(1202, B, N + 1, 192).bfloat16()], -1))   # (B, N+1, 384)
+    view = wide[:, 1:]
+    dense = view.contiguous()
+    _, p_view = ops.pool_act(view, cu(prev), ops.ACT_NONE, want_local=False)
+    _, p_dense = ops.pool_act(dense, cu(prev), ops.ACT_NONE, want_local=False)
+    assert torch.equal(p_view, p_dense)
+    a = ops.predictor_a_tail(view[:, :, :192], cu(per_image), cu(w2), cu(w3), cu(b3), cu(w4), cu(b4), K, prev=cu(prev))
+    b = ops.predictor_a_tail(dense[:, :, :192].contiguous(), cu(per_image), cu(w2), cu(w3), cu(b3), cu(w4), cu(b4), K, prev=cu(prev))
+    assert all(torch.equal(x, y) for x, y in zip(a, b))
