@@ -22,10 +22,18 @@
 //   warps 4-11  E1: GELU of the hidden chunks (two groups of four warps; -DMP_E1W=16: four groups of 32 columns under setmaxnreg,
 //               measured slower -- the stage is bound by the sub-partitions' issue / MUFU slots, not by per-warp latency)
 //   warps 12-15 output: residual add + LayerNorm of the finished row tile, overlapped with the next tile's GEMMs
-// Build options for experiments: -DMP_W1 / -DMP_W2 (weight ring depths, default 5 / 3), -DMP_E1W (8 | 16), -DD2S_GEMM_TRACE_BUILD
+// Build options for experiments: -DMP_W1 / -DMP_W2 (weight ring depths, default 5 / 3), -DMP_E1W (8 | 16), -DMP_NO_GELU (the activation
+// stage without its arithmetic: 412 -> 399 us at T = 197, i.e. the GELU is not what bounds the kernel), -DD2S_GEMM_TRACE_BUILD
 // (clock64 totals of the issuers' barrier waits into MpParams::trace, a device buffer named by the D2S_GEMM_TRACE environment variable).
 #include <stdlib.h>
 #include "d2s_tc.cuh"
+
+// -DMP_NO_GELU (profiling builds only): the activation stage without its arithmetic, to see what the GELU costs the pipeline
+#ifdef MP_NO_GELU
+#define MP_GELU(x) (x)
+#else
+#define MP_GELU(x) gelu_erf_pair(x)
+#endif
 
 namespace d2s {
 
@@ -342,7 +350,7 @@ mlp_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         for (int q = 0; q < 16; ++q) {
           const float2 bq = *reinterpret_cast<const float2*>(&b1_s[j * kMpCH + part * kMpE1Cols + 2 * q]);
           float g0, g1;
-          f2_unpack(gelu_erf_pair(f2_add(f2_pack(__uint_as_float(va[2 * q]), __uint_as_float(va[2 * q + 1])), f2_pack(bq.x, bq.y))), g0, g1);
+          f2_unpack(MP_GELU(f2_add(f2_pack(__uint_as_float(va[2 * q]), __uint_as_float(va[2 * q + 1])), f2_pack(bq.x, bq.y))), g0, g1);
           o[q] = pack_bf16x2(g0, g1);
         }
         if (kMpE1Cols == 64) {
@@ -350,7 +358,7 @@ mlp_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
           for (int q = 0; q < 16; ++q) {
             const float2 bq = *reinterpret_cast<const float2*>(&b1_s[j * kMpCH + part * kMpE1Cols + 32 + 2 * q]);
             float g0, g1;
-            f2_unpack(gelu_erf_pair(f2_add(f2_pack(__uint_as_float(vb[2 * q]), __uint_as_float(vb[2 * q + 1])), f2_pack(bq.x, bq.y))), g0, g1);
+            f2_unpack(MP_GELU(f2_add(f2_pack(__uint_as_float(vb[2 * q]), __uint_as_float(vb[2 * q + 1])), f2_pack(bq.x, bq.y))), g0, g1);
             o[(kMpE1Cols == 64 ? 16 : 0) + q] = pack_bf16x2(g0, g1);
           }
         }
