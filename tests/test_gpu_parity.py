@@ -1293,3 +1293,31 @@ def test_pool_and_tail_kernels_read_a_row_slice_in_place(ops):
     a = ops.predictor_a_tail(view[:, :, :192], cu(per_image), cu(w2), cu(w3), cu(b3), cu(w4), cu(b4), K, prev=cu(prev))
     b = ops.predictor_a_tail(dense[:, :, :192].contiguous(), cu(per_image), cu(w2), cu(w3), cu(b3), cu(w4), cu(b4), K, prev=cu(prev))
     assert all(torch.equal(x, y) for x, y in zip(a, b))
+
+
+@pytest.mark.parametrize("B,T,K", [(3, 197, 137), (2, 138, 96), (5, 97, 1), (1, 8, 0)])
+def test_gather_and_assemble_hand_norm1_on_as_row_statistics(ops, B, T, K):
+    """d2s_gather_layernorm_stats / d2s_assemble_layernorm_stats: the same summed rows as the forms that also write LayerNorm(x),
+    per-row (mean, rstd) equal to the fp32 statistics of those rows, and the qkv GEMM fed with (x, stats) BIT-identical to the qkv
+    GEMM fed with the materialised LayerNorm output (both use fma(fma(x, rstd, -mean * rstd), gamma, beta))."""
+    D = 384
+    bf = torch.bfloat16
+    x = cu(fx.randn(1300 + T, B, T, D) * 1.5).to(bf)
+    kept = torch.stack([torch.randperm(T - 1, generator=fx.gen(1301 + b))[:K].sort().values for b in range(B)]).cuda()
+    g, bt = (1 + 0.2 * cu(fx.randn(1302, D))).to(bf), cu(fx.randn(1303, D) * 0.2).to(bf)
+    Wq, bq = cu(fx.randn(1304, 3 * D, D) * D ** -0.5).to(bf), cu(fx.randn(1305, 3 * D) * 0.1).to(bf)
+    xg, hn = ops.gather_layernorm(x, kept, g, bt, 1e-6)
+    xs, st = ops.gather_layernorm(x, kept, g, bt, 1e-6, want_stats=True)
+    assert torch.equal(xs, xg) and st.shape == (B * (K + 1), 2)
+    xf = xs.float().reshape(-1, D)
+    torch.testing.assert_close(st[:, 0], xf.mean(-1), rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(st[:, 1], torch.rsqrt(xf.var(-1, unbiased=False) + 1e-6), rtol=1e-4, atol=1e-5)
+    assert torch.equal(ops.linear_act(xs, Wq, bq, ops.ACT_NONE, in_stats=st, in_ln_weight=g, in_ln_bias=bt),
+                       ops.linear_act(hn, Wq, bq, ops.ACT_NONE))
+    patches = cu(fx.randn(1306, B, T - 1, D)).to(bf) if T > 1 else None
+    cls, pos = cu(fx.randn(1307, 1, 1, D)).to(bf), cu(fx.randn(1308, 1, T, D) * 0.5).to(bf)
+    xa, ha = ops.assemble_layernorm(patches, cls, pos, g, bt, 1e-6)
+    xb, sb = ops.assemble_layernorm(patches, cls, pos, g, bt, 1e-6, want_stats=True)
+    assert torch.equal(xa, xb)
+    assert torch.equal(ops.linear_act(xb, Wq, bq, ops.ACT_NONE, in_stats=sb, in_ln_weight=g, in_ln_bias=bt),
+                       ops.linear_act(ha, Wq, bq, ops.ACT_NONE))
