@@ -72,6 +72,7 @@ SIGNATURES = {
     "d2s_assemble_layernorm": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _f, _p, _p, _p],
     "d2s_gather_layernorm_stats": [_p, _p, _i, _i, _i, _i, _f, _p, _p, _p],
     "d2s_assemble_layernorm_stats": [_p, _p, _p, _i, _i, _i, _f, _p, _p, _p],
+    "d2s_apply_layernorm_stats_bf16": [_p, _p, _p, _p, _i, _i, ctypes.c_longlong, ctypes.c_longlong, _p, _p],
     "d2s_mlp_residual_ln_bf16": [_p, _p, _p, _p, _p, _p, _p, _p, _f, _i, _i, _i, _i, _i, _p, _p, _p],
     "d2s_mlp_lnin_residual_ln_bf16": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _f, _i, _i, _i, _i, _i, _p, _p, _p, _p],
     "d2s_add_layernorm": [_p, _p, _p, _p, _i, _i, _i, _i, ctypes.c_longlong, ctypes.c_longlong, _f, _i, _p, _p, _p],

@@ -141,6 +141,22 @@ add_layernorm_kernel(const T_* __restrict__ x, const T_* __restrict__ y, const T
   }
 }
 
+// LayerNorm applied from GIVEN per-row statistics (bf16): out[r] = bf16(fma(fma(x[r], rstd_r, -mean_r * rstd_r), gamma, beta)) -- the
+// arithmetic the GEMM kernels use when they normalise their input tiles themselves, for the few rows another consumer needs
+// materialised (the CLS rows in front of the CLS-only last MLP).  One warp per row.
+__global__ void apply_ln_stats_kernel(const __nv_bfloat16* __restrict__ x, const float2* __restrict__ stats,
+                                      const __nv_bfloat16* __restrict__ gamma, const __nv_bfloat16* __restrict__ beta, int rows, int D,
+                                      long long x_row_stride, long long stat_row_stride, __nv_bfloat16* __restrict__ out) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float2 st = stats[(long long)row * stat_row_stride];
+  const float shift = -st.x * st.y;
+  const __nv_bfloat16* xr = x + (long long)row * x_row_stride;
+  for (int c = lane; c < D; c += 32)
+    out[(long long)row * D + c] =
+        __float2bfloat16_rn(fmaf(fmaf(__bfloat162float(xr[c]), st.y, shift), __bfloat162float(gamma[c]), __bfloat162float(beta[c])));
+}
+
 template <typename T_>
 static int launch_ln(const void* x, const void* y, const void* gamma, const void* beta, int B, int T, int D,
                      long long sb, long long st, float eps, int norm_row0, void* out_sum, void* out_norm, cudaStream_t stream,
@@ -258,4 +274,19 @@ extern "C" int d2s_assemble_layernorm_stats(const void* patches, const void* cls
   if (B == 0) return D2S_OK;
   return launch_ln<__nv_bfloat16>(patches, pos, patches, patches, B, N + 1, D, (long long)N * D, D, eps, 0, out_sum, nullptr,
                                   (cudaStream_t)stream, nullptr, cls, stats);
+}
+
+/* out (rows, D) = LayerNorm of rows of x taken from GIVEN statistics: row r of x at x + r * x_row_stride elements, its (mean, rstd)
+ * at stats + 2 * r * stat_row_stride floats (bf16; same arithmetic as the GEMM kernels' on-the-fly normalisation). */
+extern "C" int d2s_apply_layernorm_stats_bf16(const void* x, const float* stats, const void* gamma, const void* beta, int rows, int D,
+                                              long long x_row_stride, long long stat_row_stride, void* out, d2s_stream_t stream) {
+  D2S_REQUIRE(x && stats && gamma && beta && out, D2S_ERR_ARG, "apply_layernorm_stats: null pointer");
+  D2S_REQUIRE(rows >= 0 && D >= 1 && x_row_stride >= D && stat_row_stride >= 1, D2S_ERR_ARG,
+              "apply_layernorm_stats: bad shape rows=%d D=%d strides (%lld, %lld)", rows, D, x_row_stride, stat_row_stride);
+  if (rows == 0) return D2S_OK;
+  apply_ln_stats_kernel<<<(rows + 7) / 8, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, reinterpret_cast<const float2*>(stats),
+                                                                         (const __nv_bfloat16*)gamma, (const __nv_bfloat16*)beta, rows, D,
+                                                                         x_row_stride, stat_row_stride, (__nv_bfloat16*)out);
+  count_launch();
+  return check_launch("d2s_apply_layernorm_stats_bf16");
 }

@@ -266,6 +266,8 @@ class _LazyNorm:
 
     def cls_rows(self):
         n = self.norm
+        if self.x.dtype == torch.bfloat16 and self.x.is_contiguous() and self.x.dim() == 3:
+            return ops.layernorm_from_stats(self.x, self.stats, n.weight, n.bias)     # same bits as the normalised copy would hold
         return ops.add_layernorm(self.x[:, :1], None, n.weight, n.bias, n.eps, want_sum=False)[1]
 
 

@@ -825,6 +825,20 @@ def add_layernorm(x, y, weight, bias, eps, norm_row0=0, want_sum=True):
     return out_sum, out_norm
 
 
+def layernorm_from_stats(x, stats, weight, bias, rows_per_image=1):
+    """LayerNorm of the first `rows_per_image` rows of every image of x (B,T,D) bf16 from GIVEN per-row (mean, rstd) (stats (B*T, 2)
+    f32, as the producers of x write them), with the arithmetic of the GEMM kernels' on-the-fly normalisation.  (B, rows, D)."""
+    _check_cuda(x, stats, weight, bias)
+    B, T, D = x.shape
+    if x.dtype != torch.bfloat16 or rows_per_image != 1 or not x.is_contiguous():
+        raise RuntimeError("layernorm_from_stats: contiguous bf16 (B,T,D) input, first row of every image")
+    st = stats.detach().contiguous()
+    w, b = weight.detach().to(torch.bfloat16).contiguous(), bias.detach().to(torch.bfloat16).contiguous()
+    out = torch.empty(B, 1, D, dtype=x.dtype, device=x.device)
+    _call("d2s_apply_layernorm_stats_bf16", _ptr(x.detach()), _ptr(st), _ptr(w), _ptr(b), B, D, T * D, T, _ptr(out), _stream(x))
+    return out
+
+
 def gather_layernorm(x, kept, weight, bias, eps, want_stats=False):
     """(xg, LayerNorm(xg)) with xg = [CLS, x[:, kept + 1]]: the kept-token gather of the pruning stage fused with the next
     block's norm1 (vit_models/default_dynamic_vit.py:464-468, dynamic_vit.py:907-912 + :263).  Inference only.

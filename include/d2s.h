@@ -299,6 +299,11 @@ int d2s_gather_layernorm_stats(const void* x, const int64_t* idx, int B, int T_i
                                float* stats, d2s_stream_t stream);
 int d2s_assemble_layernorm_stats(const void* patches, const void* cls, const void* pos, int B, int N, int D, float eps, void* out_sum,
                                  float* stats, d2s_stream_t stream);
+/* out (rows, D) bf16 = LayerNorm of rows of x taken from GIVEN statistics (row r of x at x + r * x_row_stride elements, its (mean,
+ * rstd) at stats + 2 * r * stat_row_stride floats), with the arithmetic of the GEMM kernels' on-the-fly normalisation: for the few
+ * rows another consumer needs materialised (the CLS rows in front of the CLS-only last MLP). */
+int d2s_apply_layernorm_stats_bf16(const void* x, const float* stats, const void* gamma, const void* beta, int rows, int D,
+                                   long long x_row_stride, long long stat_row_stride, void* out, d2s_stream_t stream);
 
 /* Linear + activation in one tcgen05 GEMM (fc1 + GELU of Mlp.forward, dynamic_vit.py:159-175), bf16 only:
  * out (M,N) = act(a (M,K) @ w (N,K)^T + bias (N)); fp32 accumulation; bias may be NULL.
