@@ -48,7 +48,7 @@ def _fingerprint():
         [os.path.join(PKG_DIR, "..", "include", "d2s.h"), os.path.abspath(__file__)]
     for f in files:
         with open(f, "rb") as fh:
-            h.update(f.encode())
+            h.update(os.path.basename(f).encode())   # not the absolute path: the stamp travels with the snapshot
             h.update(fh.read())
     return h.hexdigest()
 
