@@ -17,7 +17,7 @@ scaling: every rank owns its own 1024 images).  Rank 0 prints ONE JSON line.
                  losses, AdamW as one flat kernel), bf16 autocast, batch 256 per GPU, whole step one CUDA graph; N > 1: one NCCL
                  all-reduce of the flat gradient buffer per step; train.e2e: pinned host batch copied in under the previous step
   ptopk          BASELINE configs[3]: PerturbedTopK forward + backward (N=196, k=98, 500 samples), B in {1, 8, 64, 256}
-  sweep          BASELINE configs[4]: select / gather / scatter, D in {384, 768}, bf16 and fp32, keep 0.3-0.9, B 64-4096
+  sweep          BASELINE configs[4]: select / gather / scatter, D in {384, 768}, bf16 and fp32, keep 0.3-0.9, B 1-4096
   arch_base      the same inference path at DeiT-B widths (D = 768, 12 heads, hidden 3072), batch 512
   variant_b      Dense2Sparse (Variant B): inference at batch 1024 and the reference's train.py loop (MaskLoss + BackboneLoss) at 256
   h2d_only       the host->device copy of the e2e leg alone (its ceiling), at N ranks
@@ -459,8 +459,10 @@ def ptopk_leg(ops, dev, torch, pk):
 def sweep_leg(ops, dev, torch, pk):
     N = 196
     rows = []
-    for B in (64, 1024, 4096):
+    for B in (1, 8, 64, 1024, 4096):
         for ratio in (0.3, 0.7, 0.9):
+            if B < 64 and ratio != 0.7:
+                continue                              # the launch-bound batches at the headline keep rate only
             K = int(N * ratio)
             scs = [torch.rand(B, N, device=dev) for _ in range(nsets_for(B * 12 * N))]
             ms = time_graphed([lambda s=s: ops.select_topk(s, K, ops.ORDER_INDEX_ASC) for s in scs], torch)
@@ -482,7 +484,7 @@ def sweep_leg(ops, dev, torch, pk):
                     del gs
     for r in rows:
         r["frac_hbm"] = r["gbs"] / pk["hbm"]
-    return {"config": "N=196; D in {384,768}; keep 0.3/0.7/0.9; B in {64,1024,4096}; bf16 and fp32; HBM fraction of the measured peak",
+    return {"config": "N=196; D in {384,768}; keep 0.3/0.7/0.9; B in {1,8,64,1024,4096} (B < 64 and B = 4096 at keep 0.7 only); bf16 and fp32; HBM fraction of the measured peak",
             "rows": rows}
 
 
