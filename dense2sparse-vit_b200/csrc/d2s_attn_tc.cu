@@ -55,7 +55,8 @@ template <int kNT, bool kPol, int kSW>
 __global__ void __launch_bounds__(tc_threads(kSW), kNT == 1 ? 4 : 2)
 attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                    const float* __restrict__ policy, int num_units, int T, int H, int Tkp, int kbufs, float scale,
-                   float eps, __nv_bfloat16* __restrict__ out, float* __restrict__ cls_row, float* __restrict__ stats) {
+                   float eps, __nv_bfloat16* __restrict__ out, float* __restrict__ cls_row, float* __restrict__ stats,
+                   const __nv_bfloat16* __restrict__ qkv) {
   constexpr int kTmemCols = kNT == 1 ? 128 : 256;
   // O accumulator columns: beyond the packed-P columns.  One softmax warp per row: P at [0, Tkp/2).  Two warps per row
   // (kSW == 8): the second column half writes its P over ITS OWN consumed S columns, at [16*ceil(n/2), ...) <= 192.
@@ -328,6 +329,36 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             if (ch_ref * 16 + q < T) mx = fmaxf(mx, __uint_as_float(v[q]));
           mxk = floorf(mx * k2);
           mx_true = mx;
+          // exponentials of S chunk `c` (in `src`) against the current reference, times the policy.  The diagonal (mask 1 whatever
+          // the policy) lies in the chunks that overlap this warp's 32 query rows: a warp-uniform split, so that every other chunk is
+          // a plain multiply by the policy (fetched as four 16-byte broadcasts)
+          auto exps_of = [&](const uint32_t (&src)[16], int c, float (&dst)[16]) {
+            const bool cfull = c * 16 + 16 <= T;
+            float pj[16];
+            if (kPol) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const float4 p4 = *reinterpret_cast<const float4*>(&pol_s[c * 16 + 4 * q]);
+                pj[4 * q] = p4.x; pj[4 * q + 1] = p4.y; pj[4 * q + 2] = p4.z; pj[4 * q + 3] = p4.w;
+              }
+              if (c * 16 < t * kTileRows + quad * 32 + 32 && c * 16 + 16 > t * kTileRows + quad * 32) {
+#pragma unroll
+                for (int q = 0; q < 16; ++q)
+                  if (c * 16 + q == i) pj[q] = 1.0f;
+              }
+            }
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+              float e = ex2_approx(fmaf(__uint_as_float(src[q]), k2, -mxk));
+              if (kPol) e *= pj[q];                       // columns past T: the policy buffer holds zeros there
+              else if (!cfull && c * 16 + q >= T) e = 0.f;
+              dst[q] = e;
+            }
+          };
+          // The chunk loop carries NO overflow handling: a logit more than 128 binades above the reference simply turns into inf
+          // (or NaN under a zero policy) and shows in the row's partial sums, which are tested ONCE after the loop (a vote and a
+          // branch inside the loop, between a chunk's last exponential and its tcgen05.st, cost 14 % of the kernel at T = 197 and
+          // more below, profiles/r02zz_attn_overflow_check.txt).
           for (int ch = ch_lo; ch < ch_hi; ++ch) {
             TC_TRACE(6)
             if (ch != ch_ref || ch != ch_lo) {   // (the reference chunk is still in registers only if it comes first)
@@ -337,36 +368,9 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             TC_TRACE(1)
             float a[16];
             const bool full = ch * 16 + 16 <= T;
-            // exponentials against the current reference; the chunk's own partial sums double as the overflow detector (a sum
-            // beyond 2^kMaxBinades, inf or NaN), so the common path carries no dependence on a row maximum
-            // the diagonal (mask 1 whatever the policy) lies in the chunks that overlap this warp's 32 query rows: a warp-uniform
-            // split, so that every other chunk is a plain multiply by the policy (fetched as four 16-byte broadcasts)
-            const bool diag_chunk = kPol && ch * 16 < t * kTileRows + quad * 32 + 32 && ch * 16 + 16 > t * kTileRows + quad * 32;
-            auto exps = [&]() {
-              float pj[16];
-              if (kPol) {
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                  const float4 p4 = *reinterpret_cast<const float4*>(&pol_s[ch * 16 + 4 * q]);
-                  pj[4 * q] = p4.x; pj[4 * q + 1] = p4.y; pj[4 * q + 2] = p4.z; pj[4 * q + 3] = p4.w;
-                }
-                if (diag_chunk) {
-#pragma unroll
-                  for (int q = 0; q < 16; ++q)
-                    if (ch * 16 + q == i) pj[q] = 1.0f;
-                }
-              }
-#pragma unroll
-              for (int q = 0; q < 16; ++q) {
-                float e = ex2_approx(fmaf(__uint_as_float(v[q]), k2, -mxk));
-                if (kPol) e *= pj[q];                       // columns past T: the policy buffer holds zeros there
-                else if (!full && ch * 16 + q >= T) e = 0.f;
-                a[q] = e;
-              }
-            };
-            exps();
-            float c0 = (a[0] + a[4]) + (a[8] + a[12]), c1 = (a[1] + a[5]) + (a[9] + a[13]);
-            float c2 = (a[2] + a[6]) + (a[10] + a[14]), c3 = (a[3] + a[7]) + (a[11] + a[15]);
+            exps_of(v, ch, a);
+            s0 += (a[0] + a[4]) + (a[8] + a[12]); s1 += (a[1] + a[5]) + (a[9] + a[13]);
+            s2 += (a[2] + a[6]) + (a[10] + a[14]); s3 += (a[3] + a[7]) + (a[11] + a[15]);
             if (kPol) {
               // the true row maximum (masked keys included: the reference's eps terms follow it); off the critical path
               if (full) {
@@ -382,20 +386,6 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                   if (ch * 16 + q < T) mx_true = fmaxf(mx_true, __uint_as_float(v[q]));
               }
             }
-            if (__any_sync(0xffffffffu, !((c0 + c1) + (c2 + c3) <= kBigSum))) {   // rare: raise the reference, rescale what exists
-              float cm = __uint_as_float(v[0]);     // chunk maximum over the valid key columns (zero-filled columns past T excluded)
-#pragma unroll
-              for (int q = 1; q < 16; ++q)
-                if (full || ch * 16 + q < T) cm = fmaxf(cm, __uint_as_float(v[q]));
-              const float over = fmaf(cm, k2, -mxk);
-              const float d = over > kMaxBinades ? floorf(over) : 0.f;
-              rescale_row(ch, exp2_neg_int(d), s0, s1, s2, s3);
-              mxk += d;
-              exps();
-              c0 = (a[0] + a[4]) + (a[8] + a[12]); c1 = (a[1] + a[5]) + (a[9] + a[13]);
-              c2 = (a[2] + a[6]) + (a[10] + a[14]); c3 = (a[3] + a[7]) + (a[11] + a[15]);
-            }
-            s0 += c0; s1 += c1; s2 += c2; s3 += c3;
             if (want_cls) {
 #pragma unroll
               for (int q = 0; q < 16; ++q) cls_s[ch * 16 + q] = a[q];
@@ -408,11 +398,62 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             tmem_st8(lane_addr + pcol(ch), packed);
             TC_TRACE(2)
           }
+          // (rows past T take no part in the votes: inside the last 16-row granule they are zero-filled by TMA, beyond it the MMA
+          // reads shared memory nobody wrote, and a NaN there would send the whole warp down the rare paths for nothing)
+          if (__any_sync(0xffffffffu, i < T && !((s0 + s1) + (s2 + s3) <= kBigSum))) {
+            // Rare (never seen on trained ViTs, but nothing forbids it): a row of this warp holds a logit more than kMaxBinades
+            // above its reference (a partial sum beyond 2^kMaxBinades, inf or NaN).  S is gone by now -- P overlays it -- so the
+            // warp redoes its 32 rows from the packed qkv in global memory, two passes: fp32 dot products q_i . k_j for the row
+            // maximum over this warp's key columns, reference = floor(k2 max) (no overflow possible), then the exponentials.  With
+            // two warps per row the halves may now end on different references; the exchange below reconciles them (exact).
+            const int iq = i < T ? i : T - 1;
+            const uint4* qrow = reinterpret_cast<const uint4*>(qkv + ((size_t)b * T + iq) * (size_t)(3 * H * kTcHD) + (size_t)h * kTcHD);
+            const __nv_bfloat16* kbase = qkv + (size_t)b * T * (size_t)(3 * H * kTcHD) + (size_t)(H + h) * kTcHD;
+            auto dot = [&](int j) -> float {
+              const uint4* krow = reinterpret_cast<const uint4*>(kbase + (size_t)j * (size_t)(3 * H * kTcHD));
+              float acc = 0.f;
+#pragma unroll 1
+              for (int w = 0; w < kTcHD / 8; ++w) {
+                const uint4 x = qrow[w], y = krow[w];
+                acc = fmaf(bf16_lo(x.x), bf16_lo(y.x), acc); acc = fmaf(bf16_hi(x.x), bf16_hi(y.x), acc);
+                acc = fmaf(bf16_lo(x.y), bf16_lo(y.y), acc); acc = fmaf(bf16_hi(x.y), bf16_hi(y.y), acc);
+                acc = fmaf(bf16_lo(x.z), bf16_lo(y.z), acc); acc = fmaf(bf16_hi(x.z), bf16_hi(y.z), acc);
+                acc = fmaf(bf16_lo(x.w), bf16_lo(y.w), acc); acc = fmaf(bf16_hi(x.w), bf16_hi(y.w), acc);
+              }
+              return acc;
+            };
+            const int j_hi = ch_hi * 16 < T ? ch_hi * 16 : T;
+            float rmx = -INFINITY;
+#pragma unroll 1
+            for (int j = ch_lo * 16; j < j_hi; ++j) rmx = fmaxf(rmx, dot(j));
+            mxk = floorf(rmx * k2);
+            mx_true = rmx;
+            s0 = s1 = s2 = s3 = 0.f;
+            tmem_st_wait();
+#pragma unroll 1
+            for (int c = ch_lo; c < ch_hi; ++c) {
+              uint32_t u[16];
+#pragma unroll 1
+              for (int q = 0; q < 16; ++q) u[q] = __float_as_uint(c * 16 + q < T ? dot(c * 16 + q) : 0.f);
+              float e16[16];
+              exps_of(u, c, e16);
+              s0 += (e16[0] + e16[4]) + (e16[8] + e16[12]); s1 += (e16[1] + e16[5]) + (e16[9] + e16[13]);
+              s2 += (e16[2] + e16[6]) + (e16[10] + e16[14]); s3 += (e16[3] + e16[7]) + (e16[11] + e16[15]);
+              if (want_cls) {
+#pragma unroll
+                for (int q = 0; q < 16; ++q) cls_s[c * 16 + q] = e16[q];
+              }
+              uint32_t w8[8];
+#pragma unroll
+              for (int q = 0; q < 8; ++q) w8[q] = pack_bf16x2(e16[2 * q], e16[2 * q + 1]);
+              tmem_st8(lane_addr + pcol(c), w8);
+            }
+          }
           if (kPol) {
             // a MASKED key far above every kept one never shows in the sums: the reference still subtracts it (its row then
             // degenerates to the eps terms), so the reference is raised for it as well
             const float over = fmaf(mx_true, k2, -mxk);
-            if (__any_sync(0xffffffffu, over > kMaxBinades)) {
+            if (__any_sync(0xffffffffu, i < T && over > kMaxBinades)) {
               const float d = over > kMaxBinades ? floorf(over) : 0.f;
               rescale_row(ch_hi, exp2_neg_int(d), s0, s1, s2, s3);
               mxk += d;
@@ -428,7 +469,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
           asm volatile("bar.sync %0, 64;" ::"r"(3 + quad) : "memory");        // the two warps of this row quadrant
           const float o_ref = ref_s[(half ^ 1) * kTileRows + r];
           float o_sum = sum_s[(half ^ 1) * kTileRows + r];
-          if (__any_sync(0xffffffffu, warp_active && o_ref != mxk)) {   // rare: one half raised its reference
+          if (__any_sync(0xffffffffu, warp_active && i < T && o_ref != mxk)) {   // rare: one half raised its reference
             const float d = warp_active ? fmaxf(o_ref - mxk, 0.f) : 0.f;   // integer: both started from the same m'
             if (warp_active) o_sum *= exp2_neg_int(fmaxf(mxk - o_ref, 0.f));
             rescale_row(ch_hi, exp2_neg_int(d), s0, s1, s2, s3);
@@ -579,7 +620,8 @@ static size_t tc_smem_bytes(int knt, int Tkp, int kbufs) {
 
 template <int kNT, bool kPol, int kSW>
 static int launch_tc(const CUtensorMap& map_a, const CUtensorMap& map_b, const float* policy, int units, int T, int H,
-                     int Tkp, float scale, float eps, void* out, float* cls_row, float* stats, cudaStream_t stream) {
+                     int Tkp, float scale, float eps, void* out, float* cls_row, float* stats, const void* qkv,
+                     cudaStream_t stream) {
   auto kern = attn_tc_fwd_kernel<kNT, kPol, kSW>;
   // two K buffers when they still leave room for the intended number of CTAs per SM
   const int per_sm = kNT == 1 ? 4 : 2;
@@ -591,7 +633,7 @@ static int launch_tc(const CUtensorMap& map_a, const CUtensorMap& map_b, const f
   D2S_REQUIRE(e == cudaSuccess, D2S_ERR_CUDA, "attn_policy_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   const int grid = units < per_sm * kNumSMs ? units : per_sm * kNumSMs;
   e = launch_pdl(kern, dim3(grid), dim3(tc_threads(kSW)), smem, stream, map_a, map_b, policy, units, T, H, Tkp, kbufs, scale, eps,
-                 (__nv_bfloat16*)out, cls_row, stats);
+                 (__nv_bfloat16*)out, cls_row, stats, (const __nv_bfloat16*)qkv);
   D2S_REQUIRE(e == cudaSuccess, D2S_ERR_CUDA, "attn_policy_fwd: launch: %s", cudaGetErrorString(e));
   count_launch();
   return check_launch("d2s_attn_policy_fwd(tcgen05)");
@@ -647,11 +689,11 @@ extern "C" int d2s_attn_policy_fwd(const void* qkv, const float* policy, int dty
   }
   const int units = B * H;
   if (T <= kTileRows) {
-    return policy ? launch_tc<1, true, 4>(map_a, map_b, policy, units, T, H, Tkp, scale, eps, out, cls_row, stats, stream)
-                  : launch_tc<1, false, 4>(map_a, map_b, policy, units, T, H, Tkp, scale, eps, out, cls_row, stats, stream);
+    return policy ? launch_tc<1, true, 4>(map_a, map_b, policy, units, T, H, Tkp, scale, eps, out, cls_row, stats, qkv, stream)
+                  : launch_tc<1, false, 4>(map_a, map_b, policy, units, T, H, Tkp, scale, eps, out, cls_row, stats, qkv, stream);
   }
   static const bool pol8 = []() { const char* e = getenv("D2S_ATTN_POL_SW"); return !(e && e[0] == '4'); }();
-  if (policy && !pol8) return launch_tc<2, true, 4>(map_a, map_b, policy, units, T, H, Tkp, scale, eps, out, cls_row, stats, stream);
-  return policy ? launch_tc<2, true, 8>(map_a, map_b, policy, units, T, H, Tkp, scale, eps, out, cls_row, stats, stream)
-                : launch_tc<2, false, 8>(map_a, map_b, policy, units, T, H, Tkp, scale, eps, out, cls_row, stats, stream);
+  if (policy && !pol8) return launch_tc<2, true, 4>(map_a, map_b, policy, units, T, H, Tkp, scale, eps, out, cls_row, stats, qkv, stream);
+  return policy ? launch_tc<2, true, 8>(map_a, map_b, policy, units, T, H, Tkp, scale, eps, out, cls_row, stats, qkv, stream)
+                : launch_tc<2, false, 8>(map_a, map_b, policy, units, T, H, Tkp, scale, eps, out, cls_row, stats, qkv, stream);
 }
