@@ -28,7 +28,7 @@ namespace d2s {
 constexpr int tc_threads(int ksw) { return 32 * (ksw + 1); }
 // a logit this many binades (powers of two, after scaling) above the row's exponent reference raises the reference
 constexpr float kMaxBinades = 100.0f;
-constexpr float kBigSum = 1.2676506e30f;   // 2^100: a 16-column partial sum beyond it triggers the check of the chunk maximum
+constexpr float kBigSum = 1.2676506e30f;   // 2^100: a row whose partial sums end beyond it (or inf, or NaN) is redone with its true maximum
 
 // clock64 wait / phase totals per CTA (profiling builds only: D2S_NVCC_EXTRA=-DD2S_ATTN_TRACE_BUILD; scripts/bench_attn_trace.py)
 #ifdef D2S_ATTN_TRACE_BUILD
@@ -312,10 +312,11 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
           // Exponentials are taken against a reference m' = floor(k2 * max of 16 columns of the row), not the row max: softmax
           // is shift invariant and bf16 keeps fp32's exponent range, so P = 2^(k2 s - m') is as accurate as 2^(k2 (s - max)).
           // The true max is tracked on the side because the reference's eps terms are not shift invariant; they are rescaled
-          // by 2^(k2 max - m') below, which restores the reference formula exactly.  m' is an INTEGER number of binades: when a
-          // later chunk holds a logit more than kMaxBinades above it (never seen on trained ViTs, but nothing forbids it), the
-          // reference is raised by a whole number of binades and what was already produced is multiplied by the matching power
-          // of two -- exact, so the result does not depend on where the maximum sits in the row.
+          // by 2^(k2 max - m') below, which restores the reference formula exactly.  m' is an INTEGER number of binades, so that
+          // it can be raised after the fact by multiplying what was produced with a power of two (exact): the masked-key case
+          // and the two-warps-per-row reconciliation below.  A row holding a logit more than kMaxBinades above m' (never seen on
+          // trained ViTs, but nothing forbids it) is found by ONE test of its finished partial sums after the loop and redone
+          // from global memory with its true maximum as the reference, so the result does not depend on where the maximum sits.
           // Reference chunk: chunk 0 with one warp per row.  With two warps per row both must derive the SAME m' from
           // columns neither of them overwrites with P before the other has read them: the last chunk of the first
           // half (the first half's P ends at column 8*ceil(n/2), below that chunk; the second half's P starts above it).
